@@ -1,0 +1,227 @@
+"""
+ORACLE -- TEST INFRASTRUCTURE ONLY.
+
+Generates tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference, CPU, fp32)
+on seeded weights and inputs from oracle/golden_util.py.  Runs only in the authoring container (the GPU box
+has no /root/reference); the fixtures it writes are committed and are what pins the oracle and the CUDA path.
+
+    python oracle/make_golden.py            # rewrites every fixture
+
+Stub modules: torchsummaryX / Levenshtein / seaborn / matplotlib are imported by the reference for
+non-numerical purposes and are absent from this image.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import golden_util as gu            # noqa: E402
+from oracle.las_oracle import levenshtein, idx_to_str, VOCAB   # noqa: E402
+
+REF = os.environ.get('LAS_REFERENCE', '/root/reference')
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def import_reference():
+    for name in ['torchsummaryX', 'Levenshtein', 'seaborn', 'matplotlib', 'matplotlib.pyplot']:
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['torchsummaryX'].summary = lambda *a, **k: None
+    sys.modules['Levenshtein'].distance = levenshtein
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    sys.path.insert(0, REF)
+    import src.models as ref_models              # the reference, unmodified
+    return ref_models
+
+
+def build_ref_model(ref_models, cfg, sd_np):
+    import copy
+    c = copy.deepcopy(cfg)
+    model = ref_models.ListenAttendSpell(**c)
+    ref_sd = model.state_dict()
+    # the state_dict contract: same keys, same shapes
+    assert set(ref_sd.keys()) == set(sd_np.keys()), (set(ref_sd) ^ set(sd_np))
+    for k, v in ref_sd.items():
+        assert tuple(v.shape) == tuple(sd_np[k].shape), (k, v.shape, sd_np[k].shape)
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd_np.items()})
+    assert model.spell.cls.weight is model.spell.char_emb.weight
+    return model
+
+
+class Recorder:
+    """Records, in call order, every tf coin (torch.rand(1)), locked-dropout mask (Tensor.bernoulli_ followed by
+    an in-place div_) and nn.Dropout mask (F.dropout) the reference draws."""
+
+    def __init__(self):
+        self.coins, self.locked, self.drops = [], [], []
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self._rand, self._bern, self._drop = torch.rand, torch.Tensor.bernoulli_, F.dropout
+        rec = self
+
+        def rand(*a, **k):
+            r = rec._rand(*a, **k)
+            if tuple(r.shape) == (1,):
+                rec.coins.append(float(r.item()))
+            return r
+
+        def bern(self_, *a, **k):
+            r = rec._bern(self_, *a, **k)
+            rec.locked.append(r)            # later div_'ed in place -> holds the final mask
+            return r
+
+        def drop(x, p=0.5, training=True, inplace=False):
+            if not training or p == 0.0:
+                return x
+            m = rec._drop(torch.ones_like(x), p, True, False)
+            rec.drops.append(m)
+            return x * m
+
+        torch.rand, torch.Tensor.bernoulli_, F.dropout = rand, bern, drop
+        return self
+
+    def __exit__(self, *exc):
+        import torch.nn.functional as F
+        torch.rand, torch.Tensor.bernoulli_, F.dropout = self._rand, self._bern, self._drop
+
+
+def train_case(ref_models, name, cfg_name, seed, B, T, L, lx, ly, tf_rate, dropout=None, init_force=False,
+               grads_full=True):
+    over = {}
+    if dropout:
+        over = dict(init_dropout=dropout[0], mid_dropout=dropout[1], final_dropout=dropout[2],
+                    dec_lstm_dropout=dropout[3])
+    cfg = gu.get_config(cfg_name, **over)
+    sd = gu.make_state_dict(cfg, seed)
+    x, lx, y = gu.make_inputs(seed + 1, B, T, L, lx)
+    ly = np.asarray(ly if ly is not None else [L] * B, dtype=np.int64)
+    model = build_ref_model(ref_models, cfg, sd).train()
+    torch.manual_seed(seed)
+    with Recorder() as rec:
+        logits, att = model(torch.from_numpy(x), torch.from_numpy(lx), torch.from_numpy(y), tf_rate, init_force)
+    # caller-side masked CE, src/train.py:117-136 (y here is already the post-<sos> view)
+    crit = torch.nn.CrossEntropyLoss(reduction='none')
+    V = logits.shape[-1]
+    ymask = (torch.arange(L).unsqueeze(0) < torch.from_numpy(ly).unsqueeze(1)).flatten().to(torch.int)
+    loss = (crit(logits.view(-1, V), torch.from_numpy(y).view(-1)) * ymask).sum() / ymask.sum()
+    loss.backward()
+    out = dict(cfg_name=cfg_name, seed=seed, x=x, lx=lx, y=y, ly=ly, tf_rate=tf_rate, init_force=init_force,
+               logits=logits.detach().numpy(), att=att.numpy(), loss=loss.item(),
+               coins=np.asarray(rec.coins, dtype=np.float64),
+               dropout=np.asarray(dropout if dropout else [0, 0, 0, 0], dtype=np.float64))
+    for i, m in enumerate(rec.locked):
+        out[f'locked_mask_{i}'] = m.numpy()
+    for i, m in enumerate(rec.drops):
+        out[f'drop_mask_{i}'] = m.numpy()
+    out['n_locked'] = len(rec.locked)
+    out['n_drops'] = len(rec.drops)
+    nograd = []
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            nograd.append(k)
+            continue
+        g = p.grad.numpy()
+        if grads_full:
+            out['grad.' + k] = g
+        out['gradnorm.' + k] = float(np.linalg.norm(g.astype(np.float64)))
+    out['nograd'] = np.asarray(nograd)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(f'{name}: loss={loss.item():.6f} logits={tuple(logits.shape)} att={tuple(att.shape)} '
+          f'coins={len(rec.coins)} locked={len(rec.locked)} drops={len(rec.drops)} nograd={nograd}')
+
+
+def greedy_case(ref_models, name, cfg_name, seed, B, T, lx, max_steps=None, scale=1.0):
+    over = {} if max_steps is None else dict(CHR_MAX_STEPS=max_steps)
+    cfg = gu.get_config(cfg_name, **over)
+    sd = gu.make_state_dict(cfg, seed, scale=scale)
+    x, lx, y = gu.make_inputs(seed + 1, B, T, 8, lx)
+    model = build_ref_model(ref_models, cfg, sd).eval()
+    with torch.no_grad():
+        logits, att = model(torch.from_numpy(x), torch.from_numpy(lx))
+    chars = logits.argmax(-1).numpy()
+    strs = [idx_to_str(c, VOCAB, 0, 29) for c in chars]
+    gold = [idx_to_str(r, VOCAB, 0, 29) for r in y]
+    ld = [levenshtein(s, g) for s, g in zip(strs, gold)]
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), cfg_name=cfg_name, seed=seed, scale=scale, x=x, lx=lx, y=y,
+                        max_steps=cfg['speller_configs']['CHR_MAX_STEPS'], logits=logits.numpy(), att=att.numpy(),
+                        chars=chars, transcripts=np.asarray(strs), ld=np.asarray(ld, dtype=np.int64))
+    print(f'{name}: logits={tuple(logits.shape)} att={tuple(att.shape)} transcripts={strs[:2]} ld={ld}')
+
+
+def optimizer_case(name, seed):
+    """src/train.py:165-183 sequence with the real torch classes: GradScaler.unscale_ -> clip_grad_norm_(5.0) ->
+    scaler.step(AdamW amsgrad) -> scaler.update -> zero_grad.  Step 3 carries an inf (skip path)."""
+    rng = np.random.default_rng(seed)
+    shapes = [(7, 5), (33,), (4, 3, 2), (129,), (2, 2)]
+    p0 = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    params = [torch.nn.Parameter(torch.from_numpy(a.copy())) for a in p0]
+    opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=5e-6, amsgrad=True)
+    scaler = torch.amp.GradScaler('cpu', init_scale=65536.0)
+    out = {f'p0_{i}': a for i, a in enumerate(p0)}
+    n_steps = 6
+    for s in range(n_steps):
+        scale = scaler.get_scale()
+        out[f'scale_{s}'] = scale
+        for i, p in enumerate(params):
+            if i == 4:          # a parameter that never receives a grad (like spell.attention.final_map)
+                continue
+            g = (rng.standard_normal(shapes[i]) * (3.0 if s % 2 == 0 else 0.01)).astype(np.float32)
+            if s == 3 and i == 1:
+                g[5] = np.inf
+            out[f'g_{s}_{i}'] = g                    # UNSCALED gradient
+            p.grad = torch.from_numpy(g.copy()) * scale
+        # the scaler must have seen a scale() call to be "enabled + initialised"
+        scaler.scale(torch.zeros(1))
+        scaler.unscale_(opt)
+        torch.nn.utils.clip_grad_norm_(params, 5.0)
+        scaler.step(opt)
+        scaler.update()
+        opt.zero_grad()
+        for i, p in enumerate(params):
+            out[f'p_{s}_{i}'] = p.detach().numpy().copy()
+    out['final_scale'] = scaler.get_scale()
+    out['n_steps'] = n_steps
+    out['n_params'] = len(shapes)
+    st = opt.state_dict()['state']
+    for i in st:
+        for k in ('exp_avg', 'exp_avg_sq', 'max_exp_avg_sq'):
+            out[f'state_{i}_{k}'] = st[i][k].numpy()
+        out[f'state_{i}_step'] = float(st[i]['step'])
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(f'{name}: final scale {scaler.get_scale()} steps {[float(st[i]["step"]) for i in st]}')
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    ref_models = import_reference()
+    # (1) micro, ragged + unsorted lengths, odd at every pyramid level, teacher forcing 1.0, no dropout
+    train_case(ref_models, 'micro_train_tf1', 'micro', 101, B=3, T=37, L=7, lx=[19, 37, 30], ly=[7, 5, 6], tf_rate=1.0)
+    # (2) micro, max(lx) < padded T, a row of length exactly 8 (-> enc_len 1), tf 0.5 (coins recorded)
+    train_case(ref_models, 'micro_train_tf05', 'micro', 202, B=4, T=50, L=9, lx=[45, 8, 33, 26], ly=None, tf_rate=0.5)
+    # (3) micro with every dropout on (masks recorded)
+    train_case(ref_models, 'micro_train_dropout', 'micro', 303, B=3, T=41, L=6, lx=[41, 40, 17], ly=None,
+               tf_rate=1.0, dropout=(0.3, 0.3, 0.35, 0.3))
+    # (4) micro with the init_force diagonal prior
+    train_case(ref_models, 'micro_train_initforce', 'micro', 404, B=2, T=48, L=8, lx=[48, 40], ly=None, tf_rate=1.0,
+               init_force=True)
+    # (5) tiny = BASELINE configs[0]: B=4, T=400, hid 128, 1 pLSTM, one teacher-forced step
+    train_case(ref_models, 'tiny_train_tf1', 'tiny', 505, B=4, T=400, L=30, lx=[400, 380, 333, 251], ly=None,
+               tf_rate=1.0, grads_full=False)
+    # (6) greedy decode, micro and tiny (weights scaled up so transcripts are not degenerate)
+    greedy_case(ref_models, 'micro_greedy', 'micro', 606, B=3, T=37, lx=[37, 21, 30], scale=3.0)
+    greedy_case(ref_models, 'tiny_greedy', 'tiny', 707, B=4, T=400, lx=[400, 380, 333, 251], scale=2.0)
+    # (7) optimizer
+    optimizer_case('optimizer_adamw_amsgrad', 808)
+
+
+if __name__ == '__main__':
+    main()
