@@ -1,0 +1,211 @@
+// Fused single-query attention step: energy -> x sqrt(d) -> length mask -> softmax -> zero pads -> context.
+//
+// Replaces MultiheadCrossAttention.forward after the query projection (reference src/models.py:168-185):
+//   e = (q . K^T) / norm_factor  with norm_factor = 1/sqrt(d)  => e = q . K^T * sqrt(d)   (:93, :170)
+//   e[t >= len] = finfo.min ; w = softmax(e) ; w[t >= len] = 0 ; ctx = w . V                (:171-185)
+// One CTA per (batch row, head).  Keys and values are (B, T_enc, P) row-major: each warp streams whole rows with
+// 128-bit loads (lane l reads floats [4l, 4l+4) and [128+4l, ...)), reduces the dot product with warp shuffles,
+// and K and V are each read exactly once per step: algorithmic bytes = 2 * B * T_enc * P * 4.
+#include "las_common.cuh"
+#include "las_b200.h"
+#include <float.h>
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int NW = NT / 32;
+constexpr int MAXCH = 2;     // head dim <= 256 (2 x 128-float chunks per warp row pass)
+
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+    v = is_max ? warp_max(v) : warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) r = is_max ? fmaxf(r, red[i]) : (r + red[i]);
+    return r;
+}
+
+// phase A: s[t] = scale * dot(vec, M[t]) for t < len, over rows of M (B,T,P) restricted to one head
+// phase C: out[p] = sum_t s2[t] * M2[t][p]
+// Used as fwd (vec=q, M=K, M2=V) and bwd (vec=dctx, M=V, M2=K).
+template <bool BWD>
+__global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
+    extern __shared__ __align__(16) float sm[];
+    const int T = a.T, P = a.P, heads = a.heads, d = P / heads;
+    const int Tp = (T + 3) & ~3;    // keep `part` 16-byte aligned
+    float* sc = sm;                 // [Tp]  scores / weights
+    float* red = sm + Tp;           // [NW]
+    float* part = red + NW;         // [NW][d] cross-warp partials for phase C
+    const int bh = blockIdx.x, b = bh / heads, h = bh - b * heads;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int len = min(a.lens[b], T);
+    const float* Mat1 = (BWD ? a.V : a.K) + (long long)b * T * P + h * d;
+    const float* Mat2 = (BWD ? a.K : a.V) + (long long)b * T * P + h * d;
+    const float* vec = (BWD ? a.dctx + (long long)b * a.ld_dctx : a.q + (long long)b * a.ld_q) + h * d;
+    const int nch = (d + 127) / 128;
+
+    float4 v4[MAXCH];
+#pragma unroll
+    for (int c = 0; c < MAXCH; ++c) {
+        int k = c * 128 + lane * 4;
+        v4[c] = (c < nch && k < d) ? *reinterpret_cast<const float4*>(vec + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (BWD && a.dctx2 && c < nch && k < d) {
+            // dctx_total = dctx (classifier path) + dctx2 (next step's cell-0 input path); the sum is written back so
+            // the deferred dV = w^T . dctx GEMM sees it.  Every warp computes the same sum; warp 0 stores it.
+            const float4 e = *reinterpret_cast<const float4*>(a.dctx2 + (long long)b * a.ld_dctx2 + h * d + k);
+            v4[c].x += e.x; v4[c].y += e.y; v4[c].z += e.z; v4[c].w += e.w;
+        }
+    }
+    if (BWD && a.dctx2) {
+        __syncthreads();   // all warps have read dctx before warp 0 overwrites it
+        if (w == 0) {
+#pragma unroll
+            for (int c = 0; c < MAXCH; ++c) {
+                int k = c * 128 + lane * 4;
+                if (c < nch && k < d) *reinterpret_cast<float4*>(a.dctx + (long long)b * a.ld_dctx + h * d + k) = v4[c];
+            }
+        }
+    }
+    // ---- phase A: one warp per row, 2 rows in flight per warp ----
+    for (int t = w; t < len; t += NW) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXCH; ++c) {
+            int k = c * 128 + lane * 4;
+            if (c < nch && k < d) {
+                float4 m = ldg4_stream(Mat1 + (long long)t * P + k);
+                acc = fmaf(m.x, v4[c].x, acc); acc = fmaf(m.y, v4[c].y, acc);
+                acc = fmaf(m.z, v4[c].z, acc); acc = fmaf(m.w, v4[c].w, acc);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sc[t] = acc;
+    }
+    __syncthreads();
+    float* wrow = a.w + ((long long)b * heads + h) * a.ld_w;
+    if (!BWD) {
+        // ---- softmax over t < len (masked entries: exp(finfo.min - max) == 0 exactly, then forced to 0) ----
+        float mx = -FLT_MAX;
+        for (int t = tid; t < len; t += NT) mx = fmaxf(mx, sc[t] * a.scale);
+        mx = block_reduce(mx, red, true);
+        float sum = 0.f;
+        for (int t = tid; t < len; t += NT) {
+            float e = expf(sc[t] * a.scale - mx);
+            sc[t] = e;
+            sum += e;
+        }
+        sum = block_reduce(sum, red, false);
+        const float inv = 1.f / sum;
+        for (int t = tid; t < T; t += NT) {
+            float wv = (t < len) ? sc[t] * inv : 0.f;
+            if (t < len) sc[t] = wv;
+            wrow[t] = wv;
+            if (b == 0 && a.w_b0) a.w_b0[(long long)h * T + t] = wv;
+        }
+    } else {
+        // dw[t] = sc[t]; de[t] = w[t] * (dw[t] - sum_t' w[t'] dw[t']) ; stored pre-multiplied by scale
+        float dot = 0.f;
+        for (int t = tid; t < len; t += NT) dot = fmaf(wrow[t], sc[t], dot);
+        dot = block_reduce(dot, red, false);
+        float* derow = a.de + ((long long)b * heads + h) * a.ld_w;
+        for (int t = tid; t < T; t += NT) {
+            float de = (t < len) ? wrow[t] * (sc[t] - dot) * a.scale : 0.f;
+            if (t < len) sc[t] = de;
+            derow[t] = de;
+        }
+    }
+    __syncthreads();
+    // ---- phase C: out[p] = sum_t sc[t] * Mat2[t][p] ----
+    float4 o4[MAXCH];
+#pragma unroll
+    for (int c = 0; c < MAXCH; ++c) o4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = w; t < len; t += NW) {
+        const float s = sc[t];
+#pragma unroll
+        for (int c = 0; c < MAXCH; ++c) {
+            int k = c * 128 + lane * 4;
+            if (c < nch && k < d) {
+                float4 m = ldg4_stream(Mat2 + (long long)t * P + k);
+                o4[c].x = fmaf(s, m.x, o4[c].x); o4[c].y = fmaf(s, m.y, o4[c].y);
+                o4[c].z = fmaf(s, m.z, o4[c].z); o4[c].w = fmaf(s, m.w, o4[c].w);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < MAXCH; ++c) {
+        int k = c * 128 + lane * 4;
+        if (c < nch && k < d) *reinterpret_cast<float4*>(part + w * d + k) = o4[c];
+    }
+    __syncthreads();
+    for (int p = tid; p < d; p += NT) {
+        float r = 0.f;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) r += part[i * d + p];
+        if (!BWD) {
+            a.ctx[(long long)b * a.ld_ctx + h * d + p] = r;
+            if (a.ctx2) a.ctx2[(long long)b * a.ld_ctx2 + h * d + p] = r;
+        } else {
+            float* dq = a.dq + (long long)b * a.ld_dq + h * d + p;
+            *dq = (a.dq_accumulate ? *dq : 0.f) + r;
+        }
+    }
+}
+
+int check(const LasAttnStep* a, bool bwd) {
+    LAS_CHECK_ARG(a != nullptr, "attn_step: null descriptor");
+    LAS_CHECK_ARG(a->B >= 1 && a->T >= 1 && a->P >= 4 && a->heads >= 1, "attn_step: bad dims B=%d T=%d P=%d heads=%d", a->B,
+                  a->T, a->P, a->heads);
+    LAS_CHECK_ARG(a->P % a->heads == 0, "attn_step: proj_dim %d %% heads %d != 0", a->P, a->heads);
+    int d = a->P / a->heads;
+    LAS_CHECK_ARG(d % 4 == 0 && d <= 128 * MAXCH, "attn_step: head dim %d must be a multiple of 4 and <= %d", d, 128 * MAXCH);
+    LAS_CHECK_ARG(a->K && a->V && a->lens && a->w, "attn_step: null K/V/lens/w");
+    if (!bwd) {
+        LAS_CHECK_ARG(a->q && a->ctx, "attn_step_fwd: null q/ctx");
+        LAS_CHECK_ARG(a->ld_q % 4 == 0, "attn_step_fwd: ld_q must be a multiple of 4");
+    } else {
+        LAS_CHECK_ARG(a->dctx && a->dq && a->de, "attn_step_bwd: null dctx/dq/de");
+        LAS_CHECK_ARG(a->ld_dctx % 4 == 0 && (!a->dctx2 || a->ld_dctx2 % 4 == 0), "attn_step_bwd: ld_dctx must be a multiple of 4");
+    }
+    return LAS_OK;
+}
+
+size_t smem_bytes(const LasAttnStep* a) { return sizeof(float) * ((size_t)((a->T + 3) & ~3) + NW + (size_t)NW * (a->P / a->heads)); }
+
+}  // namespace
+
+extern "C" int las_attn_step_fwd_f32(const LasAttnStep* a, void* stream) {
+    int rc = check(a, false);
+    if (rc) return rc;
+    rc = las_set_device_of(a->K);
+    if (rc) return rc;
+    size_t smem = smem_bytes(a);
+    LasProfScope prof(LAS_PROF_ATTN_FWD, stream, 2.0 * a->B * (double)a->T * a->P * sizeof(float));
+    if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_step_kernel<false><<<a->B * a->heads, NT, smem, (cudaStream_t)stream>>>(*a);
+    LAS_LAUNCH_CHECK();
+    return LAS_OK;
+}
+
+extern "C" int las_attn_step_bwd_f32(const LasAttnStep* a, void* stream) {
+    int rc = check(a, true);
+    if (rc) return rc;
+    rc = las_set_device_of(a->K);
+    if (rc) return rc;
+    size_t smem = smem_bytes(a);
+    LasProfScope prof(LAS_PROF_ATTN_BWD, stream, 2.0 * a->B * (double)a->T * a->P * sizeof(float));
+    if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_step_kernel<true><<<a->B * a->heads, NT, smem, (cudaStream_t)stream>>>(*a);
+    LAS_LAUNCH_CHECK();
+    return LAS_OK;
+}

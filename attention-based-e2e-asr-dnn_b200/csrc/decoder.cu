@@ -1,0 +1,551 @@
+// Speller decoder loop (forward + backward), fp32 parity mode.
+//
+// Replaces the Python time loop of Speller.forward (reference src/models.py:336-385): embedding lookup / teacher
+// forcing select (:354-358), AutoRegDecoderLSTMCell.forward (src/modules.py:340-365: cat[emb, ctx] -> LSTMCell ->
+// Dropout (dropped h is the recurrent state) -> LSTMCell -> Dropout), query_map + attention (:366), the tied
+// classifier on cat[q_proj, ctx] (:370-373) and the greedy argmax feedback (:380).  The host enqueues every kernel of
+// every step on one stream without ever synchronising; per-step history is laid out so that all weight gradients are
+// single GEMMs over (steps*B) rows after the backward loop.
+//
+// Restructuring that keeps the arithmetic equivalent:
+//   * cell-0 input GEMM: [emb, ctx, h0] . [W_ih0 | W_hh0]^T is split into a per-forward table
+//     Gemb = emb . W_ih0[:, :E]^T + b_ih0 + b_hh0  (V x 4DH; the embedding has only V=30 rows) that is gathered by token,
+//     plus one GEMM over the packed row S0[t] = [ctx_t | h0_{t-1}] with Wcat0 = [W_ih0[:, E:] | W_hh0];
+//   * cell-1: packed row S1[t] = [h0_t | h1_{t-1}], Wcat1 = [W_ih1 | W_hh1];
+//   * QC[t] = [q_proj_t | ctx_t] is both the classifier input and where attention reads its query.
+#include "las_common.cuh"
+#include "las_b200.h"
+#include <vector>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------------------------
+struct CellFwd {
+    float* G;                 // (B, 4H) in: partial pre-activations ; out: activated gates
+    const float* Gtab;        // (V, 4H) or null: row gathered by token and added
+    const int* y; long long ld_y;   // gold tokens (B, >=steps) or null
+    const int* chars_prev;    // (B) argmax of the previous step or null
+    int* tok_out;             // (B) token actually fed (saved for backward) or null
+    int t, use_gold, sos_idx;
+    const float* c_prev; long long ld_cp;
+    float* c_out; long long ld_co;
+    const float* mask;        // (B, H) or null
+    float* h1; long long ld_h1;
+    float* h2; long long ld_h2;   // nullable second destination
+    int B, H;
+};
+
+__global__ void __launch_bounds__(256) cell_fwd_kernel(CellFwd a) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= a.B * a.H) return;
+    const int b = idx / a.H, u = idx - b * a.H;
+    const int H = a.H;
+    float* g = a.G + (long long)b * 4 * H + u;
+    float p0 = g[0], p1 = g[H], p2 = g[2 * H], p3 = g[3 * H];
+    if (a.Gtab) {
+        int tok;
+        if (a.t == 0) tok = a.sos_idx;
+        else if (a.use_gold) tok = a.y[(long long)b * a.ld_y + a.t - 1];
+        else tok = a.chars_prev[b];
+        if (a.tok_out && u == 0) a.tok_out[b] = tok;
+        const float* tr = a.Gtab + (long long)tok * 4 * H + u;
+        p0 += tr[0]; p1 += tr[H]; p2 += tr[2 * H]; p3 += tr[3 * H];
+    }
+    const float gi = sigmoidf_acc(p0), gf = sigmoidf_acc(p1), gg = tanhf(p2), go = sigmoidf_acc(p3);
+    const float c = fmaf(gf, a.c_prev[(long long)b * a.ld_cp + u], gi * gg);
+    float h = go * tanhf(c);
+    if (a.mask) h *= a.mask[(long long)b * H + u];
+    g[0] = gi; g[H] = gf; g[2 * H] = gg; g[3 * H] = go;
+    a.c_out[(long long)b * a.ld_co + u] = c;
+    a.h1[(long long)b * a.ld_h1 + u] = h;
+    if (a.h2) a.h2[(long long)b * a.ld_h2 + u] = h;
+}
+
+struct CellBwd {
+    float* G;                 // (B,4H) in: activated gates ; out: d(pre-activation)
+    const float* dh_a; long long ld_a;   // nullable
+    const float* dh_b; long long ld_b;   // nullable
+    const float* mask;        // (B,H) or null (dropout applied to h)
+    const float* c; long long ld_c;
+    const float* c_prev; long long ld_cp;
+    float* dc;                // (B,H) carried in/out
+    int first;                // 1: dc carried-in is zero
+    int B, H;
+};
+
+__global__ void __launch_bounds__(256) cell_bwd_kernel(CellBwd a) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= a.B * a.H) return;
+    const int b = idx / a.H, u = idx - b * a.H;
+    const int H = a.H;
+    float dh = 0.f;
+    if (a.dh_a) dh += a.dh_a[(long long)b * a.ld_a + u];
+    if (a.dh_b) dh += a.dh_b[(long long)b * a.ld_b + u];
+    if (a.mask) dh *= a.mask[(long long)b * H + u];
+    float* g = a.G + (long long)b * 4 * H + u;
+    const float gi = g[0], gf = g[H], gg = g[2 * H], go = g[3 * H];
+    const float c = a.c[(long long)b * a.ld_c + u], cp = a.c_prev[(long long)b * a.ld_cp + u];
+    const float dcin = a.first ? 0.f : a.dc[(long long)b * H + u];
+    const float tc = tanhf(c);
+    const float dct = fmaf(dh * go, 1.f - tc * tc, dcin);
+    g[0] = dct * gg * gi * (1.f - gi);
+    g[H] = dct * cp * gf * (1.f - gf);
+    g[2 * H] = dct * gi * (1.f - gg * gg);
+    g[3 * H] = dh * tc * go * (1.f - go);
+    a.dc[(long long)b * H + u] = dct * gf;
+}
+
+// logits[b, :] = x[b, :] . emb^T + bias ; chars[b] = argmax (first maximum, like torch.argmax)
+__global__ void __launch_bounds__(256) logits_argmax_kernel(const float* __restrict__ x, long long ld_x, const float* __restrict__ emb,
+                                                            const float* __restrict__ bias, float* __restrict__ logits,
+                                                            long long ld_l, int* __restrict__ chars, int K, int V) {
+    extern __shared__ float lsm[];   // [V]
+    const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float* xr = x + (long long)b * ld_x;
+    for (int v = w; v < V; v += 8) {
+        const float* er = emb + (long long)v * K;
+        float acc = 0.f;
+        for (int k = lane; k < K; k += 32) acc = fmaf(xr[k], er[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) lsm[v] = acc + bias[v];
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < V; v += 256) logits[(long long)b * ld_l + v] = lsm[v];
+    if (threadIdx.x == 0) {
+        int best = 0;
+        float bv = lsm[0];
+        for (int v = 1; v < V; ++v)
+            if (lsm[v] > bv) { bv = lsm[v]; best = v; }
+        chars[b] = best;
+    }
+}
+
+// dGemb[v][n] = sum over (t,b) with tok[t,b] == v of dG0[t,b,n]   (deterministic gather-reduce)
+__global__ void __launch_bounds__(256) token_reduce_kernel(const float* __restrict__ dG, const int* __restrict__ tok, float* __restrict__ out,
+                                                           int rows, int N) {
+    const int v = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
+    __shared__ int stok[256];
+    float acc = 0.f;
+    for (int r0 = 0; r0 < rows; r0 += 256) {
+        __syncthreads();
+        stok[threadIdx.x] = (r0 + threadIdx.x < rows) ? tok[r0 + threadIdx.x] : -1;
+        __syncthreads();
+        if (n < N) {
+            const int lim = min(256, rows - r0);
+            for (int i = 0; i < lim; ++i)
+                if (stok[i] == v) acc += dG[(long long)(r0 + i) * N + n];
+        }
+    }
+    if (n < N) out[(long long)v * N + n] = acc;
+}
+
+// two-stage deterministic column sum
+constexpr int CS_ROWSPLIT = 64;
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ X, long long ld, int M, int N, float* __restrict__ part) {
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rl = threadIdx.x >> 5;          // 8 row lanes
+    const int rs = blockIdx.y;
+    __shared__ float sm[8][33];
+    float acc = 0.f;
+    if (n < N)
+        for (int m = rs * 8 + rl; m < M; m += CS_ROWSPLIT * 8) acc += X[(long long)m * ld + n];
+    sm[rl][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (rl == 0 && n < N) {
+        float r = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r += sm[i][threadIdx.x & 31];
+        part[(long long)rs * N + n] = r;
+    }
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int N, float* __restrict__ out, int accumulate) {
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= N) return;
+    float r = 0.f;
+    for (int i = 0; i < CS_ROWSPLIT; ++i) r += part[(long long)i * N + n];
+    out[n] = accumulate ? out[n] + r : r;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host-side helpers
+// ------------------------------------------------------------------------------------------------------------------
+// plain row-major GEMM helper: C[M,N](ldc) = A[M,K](lda, row-major) . op(B) + beta*C + biases
+//   transB = 1: B is (N,K) row-major with row stride ldb  (C = A . B^T)
+//   transB = 0: B is (K,N) row-major with row stride ldb  (C = A . B)
+int gemm(cudaStream_t st, const float* A, long long lda, const float* B, long long ldb, int transB, float* C, long long ldc, int M,
+         int N, int K, float beta = 0.f, const float* bias1 = nullptr, const float* bias2 = nullptr) {
+    LasGemmF32 d{};
+    d.A = A; d.B = B; d.C = C; d.bias1 = bias1; d.bias2 = bias2;
+    d.M = M; d.N = N; d.K = K; d.batch = 1;
+    d.a_m_si = lda; d.a_k_si = 1;
+    if (transB) { d.b_k_si = 1; d.b_n_s = ldb; } else { d.b_k_si = ldb; d.b_n_s = 1; }
+    d.c_m_si = ldc;
+    d.alpha = 1.f; d.beta = beta;
+    return las_gemm_f32(&d, st);
+}
+// C[M,N](ldc) = A^T . B where A is (K,M) row-major (lda), B is (K,N) row-major (ldb): weight-gradient form
+int gemm_tn(cudaStream_t st, const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int M, int N, int K,
+            float beta = 0.f) {
+    LasGemmF32 d{};
+    d.A = A; d.B = B; d.C = C;
+    d.M = M; d.N = N; d.K = K; d.batch = 1;
+    d.a_m_si = 1; d.a_k_si = lda;
+    d.b_k_si = ldb; d.b_n_s = 1;
+    d.c_m_si = ldc;
+    d.alpha = 1.f; d.beta = beta;
+    return las_gemm_f32(&d, st);
+}
+
+struct Layout {
+    // float workspace offsets
+    size_t Wcat0, Wcat1, Gemb, S0, S1, C0, C1, G0, G1, QC, W, dQC, dS0, dS1, dc0, dc1, dh1, DE, dGemb, tmpq, cs_scratch, total_f;
+    // int workspace offsets
+    size_t tok, total_i;
+    int hist, ghist;
+};
+
+Layout make_layout(const LasSpeller* s) {
+    Layout L{};
+    const size_t B = s->B, T = s->T, P = s->P, E = s->E, DH = s->DH, DO = s->DO, V = s->V, S = s->steps, h = s->heads;
+    (void)E;
+    L.hist = s->training ? (int)S + 1 : 2;
+    L.ghist = s->training ? (int)S : 1;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
+    L.Wcat0 = take(4 * DH * (P + DH));
+    L.Wcat1 = take(4 * DO * (DH + DO));
+    L.Gemb = take(V * 4 * DH);
+    L.S0 = take((size_t)L.hist * B * (P + DH));
+    L.S1 = take((size_t)L.hist * B * (DH + DO));
+    L.C0 = take((size_t)L.hist * B * DH);
+    L.C1 = take((size_t)L.hist * B * DO);
+    L.G0 = take((size_t)L.ghist * B * 4 * DH);
+    L.G1 = take((size_t)L.ghist * B * 4 * DO);
+    L.QC = take((size_t)L.hist * B * 2 * P);
+    L.W = take((size_t)L.hist * B * h * T);
+    if (s->training) {
+        L.dQC = take((S + 1) * B * 2 * P);
+        L.dS0 = take(B * (P + DH));
+        L.dS1 = take(B * (DH + DO));
+        L.dc0 = take(B * DH);
+        L.dc1 = take(B * DO);
+        L.dh1 = take(B * DO);
+        L.DE = take((S + 1) * B * h * T);
+        L.dGemb = take(V * 4 * DH);
+        L.tmpq = take(B * DO);
+        size_t maxn = 4 * DH;
+        if (maxn < 2 * P) maxn = 2 * P;
+        L.cs_scratch = take((size_t)CS_ROWSPLIT * maxn);
+    }
+    L.total_f = o;
+    L.tok = 0;
+    L.total_i = s->training ? S * B : 4;
+    return L;
+}
+
+int check_speller(const LasSpeller* s) {
+    LAS_CHECK_ARG(s != nullptr, "speller: null descriptor");
+    LAS_CHECK_ARG(s->B >= 1 && s->T >= 1 && s->steps >= 1 && s->V >= 2, "speller: bad dims B=%d T=%d steps=%d V=%d", s->B, s->T,
+                  s->steps, s->V);
+    LAS_CHECK_ARG(s->E == 2 * s->P, "speller: dec_emb_dim (%d) must equal 2*att_proj_dim (%d) (tied classifier, reference "
+                  "src/models.py:285-287,371)", s->E, 2 * s->P);
+    LAS_CHECK_ARG(s->P % s->heads == 0, "speller: proj_dim %d %% heads %d != 0", s->P, s->heads);
+    LAS_CHECK_ARG(s->P % 4 == 0 && s->DH % 4 == 0 && s->DO % 4 == 0, "speller: P/DH/DO must be multiples of 4");
+    LAS_CHECK_ARG(s->emb && s->cls_b && s->w_ih0 && s->w_hh0 && s->b_ih0 && s->b_hh0 && s->w_ih1 && s->w_hh1 && s->b_ih1 && s->b_hh1 &&
+                      s->wq && s->bq && s->init_query, "speller: null parameter pointer");
+    LAS_CHECK_ARG(s->K && s->V_ && s->enc_lens && s->logits && s->chars && s->fws && s->iws, "speller: null input/output pointer");
+    LAS_CHECK_ARG(!s->training || s->dec_y, "speller: training needs dec_y");
+    return LAS_OK;
+}
+
+#define RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+}  // namespace
+
+extern "C" size_t las_colsum_scratch_floats(int N) { return (size_t)CS_ROWSPLIT * (size_t)(N > 0 ? N : 1); }
+
+extern "C" int las_colsum_f32(const float* X, long long ld, int M, int N, float* out, int accumulate, float* scratch, void* stream) {
+    LAS_CHECK_ARG(X && out && scratch && M >= 0 && N >= 1, "colsum: bad arguments");
+    RC(las_set_device_of(out));
+    cudaStream_t st = (cudaStream_t)stream;
+    colsum_partial_kernel<<<dim3(ceil_div(N, 32), CS_ROWSPLIT), 256, 0, st>>>(X, ld, M, N, scratch);
+    LAS_LAUNCH_CHECK();
+    colsum_final_kernel<<<ceil_div(N, 256), 256, 0, st>>>(scratch, N, out, accumulate);
+    LAS_LAUNCH_CHECK();
+    return LAS_OK;
+}
+
+// standalone single-step LSTM cell pointwise (AutoRegDecoderLSTMCell.forward's API for external callers)
+extern "C" int las_lstm_cell_fwd_f32(float* gates, const float* c_prev, const float* mask, float* h_out, float* c_out, int B, int H,
+                                     void* stream) {
+    LAS_CHECK_ARG(gates && c_prev && h_out && c_out && B >= 1 && H >= 1, "lstm_cell_fwd: bad arguments");
+    RC(las_set_device_of(gates));
+    CellFwd c{};
+    c.G = gates; c.c_prev = c_prev; c.ld_cp = H; c.c_out = c_out; c.ld_co = H; c.mask = mask; c.h1 = h_out; c.ld_h1 = H;
+    c.B = B; c.H = H;
+    cell_fwd_kernel<<<ceil_div(B * H, 256), 256, 0, (cudaStream_t)stream>>>(c);
+    LAS_LAUNCH_CHECK();
+    return LAS_OK;
+}
+
+extern "C" int las_lstm_cell_bwd_f32(float* gates, const float* dh, const float* mask, const float* c, const float* c_prev, float* dc_io,
+                                     int B, int H, void* stream) {
+    LAS_CHECK_ARG(gates && dh && c && c_prev && dc_io && B >= 1 && H >= 1, "lstm_cell_bwd: bad arguments");
+    RC(las_set_device_of(gates));
+    CellBwd b{};
+    b.G = gates; b.dh_a = dh; b.ld_a = H; b.mask = mask; b.c = c; b.ld_c = H; b.c_prev = c_prev; b.ld_cp = H; b.dc = dc_io;
+    b.first = 0; b.B = B; b.H = H;
+    cell_bwd_kernel<<<ceil_div(B * H, 256), 256, 0, (cudaStream_t)stream>>>(b);
+    LAS_LAUNCH_CHECK();
+    return LAS_OK;
+}
+
+extern "C" size_t las_speller_workspace_floats(const LasSpeller* s) { return s ? make_layout(s).total_f : 0; }
+extern "C" size_t las_speller_workspace_ints(const LasSpeller* s) { return s ? make_layout(s).total_i : 0; }
+
+extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
+    RC(check_speller(s));
+    const Layout L = make_layout(s);
+    if (s->fws_floats < L.total_f || s->iws_ints < L.total_i) {
+        las_set_error("speller_fwd: workspace too small (%zu/%zu floats, %zu/%zu ints)", s->fws_floats, L.total_f, s->iws_ints, L.total_i);
+        return LAS_ERR_WORKSPACE;
+    }
+    RC(las_set_device_of(s->fws));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = s->B, T = s->T, P = s->P, E = s->E, DH = s->DH, DO = s->DO, V = s->V, S = s->steps, heads = s->heads;
+    const int K0 = P + DH, K1 = DH + DO;
+    LasProfScope prof(LAS_PROF_SPELLER_FWD, stream, (double)S);
+    float* f = s->fws;
+    float *Wcat0 = f + L.Wcat0, *Wcat1 = f + L.Wcat1, *Gemb = f + L.Gemb, *S0 = f + L.S0, *S1 = f + L.S1, *C0 = f + L.C0, *C1 = f + L.C1,
+          *G0 = f + L.G0, *G1 = f + L.G1, *QC = f + L.QC, *W = f + L.W;
+    int* tok = s->iws + L.tok;
+    const size_t fsz = sizeof(float);
+
+    // packed weights
+    LAS_CUDA(cudaMemcpy2DAsync(Wcat0, K0 * fsz, s->w_ih0 + E, (size_t)(E + P) * fsz, P * fsz, 4 * DH, cudaMemcpyDeviceToDevice, st));
+    LAS_CUDA(cudaMemcpy2DAsync(Wcat0 + P, K0 * fsz, s->w_hh0, DH * fsz, DH * fsz, 4 * DH, cudaMemcpyDeviceToDevice, st));
+    LAS_CUDA(cudaMemcpy2DAsync(Wcat1, K1 * fsz, s->w_ih1, DH * fsz, DH * fsz, 4 * DO, cudaMemcpyDeviceToDevice, st));
+    LAS_CUDA(cudaMemcpy2DAsync(Wcat1 + DH, K1 * fsz, s->w_hh1, DO * fsz, DO * fsz, 4 * DO, cudaMemcpyDeviceToDevice, st));
+    // embedding-side gate table (+ both cell-0 biases)
+    RC(gemm(st, s->emb, E, s->w_ih0, E + P, 1, Gemb, 4 * DH, V, 4 * DH, E, 0.f, s->b_ih0, s->b_hh0));
+    // zero initial states (init_hiddens are always zero: reference src/models.py:275-281)
+    LAS_CUDA(cudaMemset2DAsync(S0 + P, K0 * fsz, 0, DH * fsz, B, st));      // h0_{-1}
+    LAS_CUDA(cudaMemset2DAsync(S1 + DH, K1 * fsz, 0, DO * fsz, B, st));     // h1_{-1}
+    LAS_CUDA(cudaMemsetAsync(C0, 0, (size_t)B * DH * fsz, st));
+    LAS_CUDA(cudaMemsetAsync(C1, 0, (size_t)B * DO * fsz, st));
+    // initial query (src/models.py:345-346): q_init = query_map(init_query) for every row
+    {
+        LasGemmF32 d{};
+        d.A = s->init_query; d.B = s->wq; d.C = QC; d.bias1 = s->bq;
+        d.M = B; d.N = P; d.K = DO; d.batch = 1;
+        d.a_m_si = 0; d.a_k_si = 1; d.b_k_si = 1; d.b_n_s = DO; d.c_m_si = 2 * P;
+        d.alpha = 1.f; d.beta = 0.f;
+        RC(las_gemm_f32(&d, st));
+    }
+    LasAttnStep at{};
+    at.K = s->K; at.V = s->V_; at.lens = s->enc_lens; at.B = B; at.T = T; at.P = P; at.heads = heads;
+    at.scale = sqrtf((float)(P / heads));
+    at.ld_q = 2 * P; at.ld_ctx = 2 * P; at.ld_ctx2 = K0; at.ld_w = T;
+    at.q = QC; at.ctx = QC + P; at.ctx2 = S0; at.w = W; at.w_b0 = s->att0;
+    RC(las_attn_step_fwd_f32(&at, st));
+
+    bool all_gold = s->training != 0;
+    if (s->training)
+        for (int t = 1; t < S; ++t) all_gold = all_gold && s->use_gold_host && s->use_gold_host[t];
+    const bool per_step_logits = !all_gold;
+
+    for (int t = 0; t < S; ++t) {
+        const int r = t % L.hist, rn = (t + 1) % L.hist, rg = t % L.ghist;
+        float* S0r = S0 + (size_t)r * B * K0;  float* S0n = S0 + (size_t)rn * B * K0;
+        float* S1r = S1 + (size_t)r * B * K1;  float* S1n = S1 + (size_t)rn * B * K1;
+        float* G0r = G0 + (size_t)rg * B * 4 * DH;  float* G1r = G1 + (size_t)rg * B * 4 * DO;
+        float* QCn = QC + (size_t)rn * B * 2 * P;
+        // cell 0
+        RC(gemm(st, S0r, K0, Wcat0, K0, 1, G0r, 4 * DH, B, 4 * DH, K0));
+        CellFwd c0{};
+        c0.G = G0r; c0.Gtab = Gemb; c0.y = s->dec_y; c0.ld_y = s->ld_y;
+        c0.chars_prev = (t > 0) ? s->chars + (size_t)(t - 1) * B : nullptr;
+        c0.tok_out = s->training ? tok + (size_t)t * B : nullptr;
+        c0.t = t; c0.sos_idx = s->sos_idx;
+        c0.use_gold = (s->training && t > 0 && s->use_gold_host && s->use_gold_host[t]) ? 1 : 0;
+        c0.c_prev = C0 + (size_t)r * B * DH; c0.ld_cp = DH;
+        c0.c_out = C0 + (size_t)rn * B * DH; c0.ld_co = DH;
+        c0.mask = s->drop0 ? s->drop0 + (size_t)t * B * DH : nullptr;
+        c0.h1 = S0n + P; c0.ld_h1 = K0;      // recurrent slot of the next step's cell-0 row
+        c0.h2 = S1r; c0.ld_h2 = K1;          // input slot of this step's cell-1 row
+        c0.B = B; c0.H = DH;
+        cell_fwd_kernel<<<ceil_div(B * DH, 256), 256, 0, st>>>(c0);
+        LAS_LAUNCH_CHECK();
+        // cell 1
+        RC(gemm(st, S1r, K1, Wcat1, K1, 1, G1r, 4 * DO, B, 4 * DO, K1, 0.f, s->b_ih1, s->b_hh1));
+        CellFwd c1{};
+        c1.G = G1r; c1.Gtab = nullptr; c1.t = t;
+        c1.c_prev = C1 + (size_t)r * B * DO; c1.ld_cp = DO;
+        c1.c_out = C1 + (size_t)rn * B * DO; c1.ld_co = DO;
+        c1.mask = s->drop1 ? s->drop1 + (size_t)t * B * DO : nullptr;
+        c1.h1 = S1n + DH; c1.ld_h1 = K1; c1.h2 = nullptr;
+        c1.B = B; c1.H = DO;
+        cell_fwd_kernel<<<ceil_div(B * DO, 256), 256, 0, st>>>(c1);
+        LAS_LAUNCH_CHECK();
+        // query projection into QC[t+1][:, :P]
+        RC(gemm(st, S1n + DH, K1, s->wq, DO, 1, QCn, 2 * P, B, P, DO, 0.f, s->bq));
+        // attention: context into QC[t+1][:, P:] and into the next cell-0 row
+        at.q = QCn; at.ctx = QCn + P; at.ctx2 = S0n; at.w = W + (size_t)rn * B * heads * T;
+        at.w_b0 = s->att0 ? s->att0 + (size_t)(t + 1) * heads * T : nullptr;
+        RC(las_attn_step_fwd_f32(&at, st));
+        if (per_step_logits) {
+            logits_argmax_kernel<<<B, 256, V * sizeof(float), st>>>(QCn, 2 * P, s->emb, s->cls_b, s->logits + (size_t)t * V, (long long)S * V,
+                                                                 s->chars + (size_t)t * B, 2 * P, V);
+            LAS_LAUNCH_CHECK();
+        }
+    }
+    if (!per_step_logits) {
+        // all classifier rows at once: row m = t*B + b of QC[1..S] -> logits[b, t, :]
+        LasGemmF32 d{};
+        d.A = QC + (size_t)B * 2 * P; d.B = s->emb; d.C = s->logits; d.bias1 = s->cls_b;
+        d.M = S * B; d.N = V; d.K = 2 * P; d.batch = 1;
+        d.a_m_si = 2 * P; d.a_k_si = 1; d.b_k_si = 1; d.b_n_s = E;
+        d.c_m_inner = B; d.c_m_so = V; d.c_m_si = (long long)S * V;
+        d.alpha = 1.f; d.beta = 0.f;
+        RC(las_gemm_f32(&d, st));
+    }
+    return LAS_OK;
+}
+
+extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g, void* stream) {
+    RC(check_speller(s));
+    LAS_CHECK_ARG(s->training, "speller_bwd: forward was not run in training mode");
+    LAS_CHECK_ARG(g && g->dlogits && g->d_emb && g->d_cls_b && g->d_w_ih0 && g->d_w_hh0 && g->d_b_ih0 && g->d_b_hh0 && g->d_w_ih1 &&
+                      g->d_w_hh1 && g->d_b_ih1 && g->d_b_hh1 && g->d_wq && g->d_bq && g->d_init_query && g->dK && g->dV,
+                  "speller_bwd: null gradient pointer");
+    const Layout L = make_layout(s);
+    if (s->fws_floats < L.total_f || s->iws_ints < L.total_i) {
+        las_set_error("speller_bwd: workspace too small");
+        return LAS_ERR_WORKSPACE;
+    }
+    RC(las_set_device_of(s->fws));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = s->B, T = s->T, P = s->P, E = s->E, DH = s->DH, DO = s->DO, V = s->V, S = s->steps, heads = s->heads;
+    const int K0 = P + DH, K1 = DH + DO, d_head = P / heads;
+    LasProfScope prof(LAS_PROF_SPELLER_BWD, stream, (double)S);
+    float* f = s->fws;
+    float *Wcat0 = f + L.Wcat0, *Wcat1 = f + L.Wcat1, *S0 = f + L.S0, *S1 = f + L.S1, *C0 = f + L.C0, *C1 = f + L.C1, *G0 = f + L.G0,
+          *G1 = f + L.G1, *QC = f + L.QC, *W = f + L.W, *dQC = f + L.dQC, *dS0 = f + L.dS0, *dS1 = f + L.dS1, *dc0 = f + L.dc0,
+          *dc1 = f + L.dc1, *dh1 = f + L.dh1, *DE = f + L.DE, *dGemb = f + L.dGemb, *tmpq = f + L.tmpq, *csw = f + L.cs_scratch;
+    const int* tok = s->iws + L.tok;
+    const size_t fsz = sizeof(float);
+    const long long SB = (long long)S * B;
+
+    // dQC[1..S] = dlogits . emb  (row m = t*B + b  <-  dlogits[b, t, :])
+    LAS_CUDA(cudaMemsetAsync(dQC, 0, (size_t)B * 2 * P * fsz, st));
+    {
+        LasGemmF32 d{};
+        d.A = g->dlogits; d.B = s->emb; d.C = dQC + (size_t)B * 2 * P;
+        d.M = (int)SB; d.N = 2 * P; d.K = V; d.batch = 1;
+        d.a_m_inner = B; d.a_m_so = V; d.a_m_si = (long long)S * V; d.a_k_si = 1;
+        d.b_k_si = E; d.b_n_s = 1; d.c_m_si = 2 * P;
+        d.alpha = 1.f; d.beta = 0.f;
+        RC(las_gemm_f32(&d, st));
+    }
+    // tied classifier weight: d_emb = dlogits^T . QC[1..S]
+    {
+        LasGemmF32 d{};
+        d.A = g->dlogits; d.B = QC + (size_t)B * 2 * P; d.C = g->d_emb;
+        d.M = V; d.N = 2 * P; d.K = (int)SB; d.batch = 1;
+        d.a_m_si = 1; d.a_k_inner = B; d.a_k_so = V; d.a_k_si = (long long)S * V;
+        d.b_k_si = 2 * P; d.b_n_s = 1; d.c_m_si = E;
+        d.alpha = 1.f; d.beta = 0.f;
+        RC(las_gemm_f32(&d, st));
+    }
+    RC(las_colsum_f32(g->dlogits, V, (int)SB, V, g->d_cls_b, 0, csw, st));
+
+    LasAttnStep at{};
+    at.K = s->K; at.V = s->V_; at.lens = s->enc_lens; at.B = B; at.T = T; at.P = P; at.heads = heads;
+    at.scale = sqrtf((float)d_head);
+    at.ld_q = 2 * P; at.ld_w = T; at.ld_dctx = 2 * P; at.ld_dctx2 = K0; at.ld_dq = 2 * P; at.dq_accumulate = 1;
+
+    for (int t = S - 1; t >= 0; --t) {
+        const int rn = t + 1;
+        float* dQCn = dQC + (size_t)rn * B * 2 * P;
+        // attention step (t+1): dctx_total = classifier path + cell-0 path of step t+1
+        at.q = QC + (size_t)rn * B * 2 * P; at.w = W + (size_t)rn * B * heads * T;
+        at.dctx = dQCn + P; at.dctx2 = (t == S - 1) ? nullptr : dS0;
+        at.dq = dQCn; at.de = DE + (size_t)rn * B * heads * T;
+        RC(las_attn_step_bwd_f32(&at, st));
+        // dh1_t (dropped) = dq_total . Wq  (+ recurrent path, added inside cell_bwd)
+        RC(gemm(st, dQCn, 2 * P, s->wq, DO, 0, dh1, DO, B, DO, P));
+        CellBwd b1{};
+        b1.G = G1 + (size_t)t * B * 4 * DO;
+        b1.dh_a = dh1; b1.ld_a = DO;
+        b1.dh_b = (t == S - 1) ? nullptr : dS1 + DH; b1.ld_b = K1;
+        b1.mask = s->drop1 ? s->drop1 + (size_t)t * B * DO : nullptr;
+        b1.c = C1 + (size_t)rn * B * DO; b1.ld_c = DO; b1.c_prev = C1 + (size_t)t * B * DO; b1.ld_cp = DO;
+        b1.dc = dc1; b1.first = (t == S - 1); b1.B = B; b1.H = DO;
+        cell_bwd_kernel<<<ceil_div(B * DO, 256), 256, 0, st>>>(b1);
+        LAS_LAUNCH_CHECK();
+        // dS1[t] = dG1_t . Wcat1  -> [dh0_t | dh1_{t-1}]
+        RC(gemm(st, b1.G, 4 * DO, Wcat1, K1, 0, dS1, K1, B, K1, 4 * DO));
+        CellBwd b0{};
+        b0.G = G0 + (size_t)t * B * 4 * DH;
+        b0.dh_a = dS1; b0.ld_a = K1;
+        b0.dh_b = (t == S - 1) ? nullptr : dS0 + P; b0.ld_b = K0;
+        b0.mask = s->drop0 ? s->drop0 + (size_t)t * B * DH : nullptr;
+        b0.c = C0 + (size_t)rn * B * DH; b0.ld_c = DH; b0.c_prev = C0 + (size_t)t * B * DH; b0.ld_cp = DH;
+        b0.dc = dc0; b0.first = (t == S - 1); b0.B = B; b0.H = DH;
+        cell_bwd_kernel<<<ceil_div(B * DH, 256), 256, 0, st>>>(b0);
+        LAS_LAUNCH_CHECK();
+        // dS0[t] = dG0_t . Wcat0 -> [dctx_t | dh0_{t-1}]
+        RC(gemm(st, b0.G, 4 * DH, Wcat0, K0, 0, dS0, K0, B, K0, 4 * DH));
+    }
+    // initial attention (src/models.py:346): its context feeds cell 0 of step 0 only
+    at.q = QC; at.w = W; at.dctx = dQC + P; at.dctx2 = dS0; at.dq = dQC; at.de = DE;
+    RC(las_attn_step_bwd_f32(&at, st));
+
+    // ---- batched parameter gradients ----
+    // query_map: rows 1..S see h1_t (S1[t+1] slot), row 0 sees init_query
+    RC(gemm_tn(st, dQC + (size_t)B * 2 * P, 2 * P, S1 + (size_t)B * K1 + DH, K1, g->d_wq, DO, P, DO, (int)SB));
+    {
+        LasGemmF32 d{};
+        d.A = dQC; d.B = s->init_query; d.C = g->d_wq;
+        d.M = P; d.N = DO; d.K = B; d.batch = 1;
+        d.a_m_si = 1; d.a_k_si = 2 * P; d.b_k_si = 0; d.b_n_s = 1; d.c_m_si = DO;
+        d.alpha = 1.f; d.beta = 1.f;
+        RC(las_gemm_f32(&d, st));
+    }
+    RC(las_colsum_f32(dQC, 2 * P, (S + 1) * B, P, g->d_bq, 0, csw, st));
+    RC(gemm(st, dQC, 2 * P, s->wq, DO, 0, tmpq, DO, B, DO, P));
+    RC(las_colsum_f32(tmpq, DO, B, DO, g->d_init_query, 0, csw, st));
+    // cell 1
+    RC(gemm_tn(st, G1, 4 * DO, S1, K1, g->d_w_ih1, DH, 4 * DO, DH, (int)SB));
+    RC(gemm_tn(st, G1, 4 * DO, S1 + DH, K1, g->d_w_hh1, DO, 4 * DO, DO, (int)SB));
+    RC(las_colsum_f32(G1, 4 * DO, (int)SB, 4 * DO, g->d_b_ih1, 0, csw, st));
+    LAS_CUDA(cudaMemcpyAsync(g->d_b_hh1, g->d_b_ih1, (size_t)4 * DO * fsz, cudaMemcpyDeviceToDevice, st));
+    // cell 0: context columns, recurrent weight, biases
+    RC(gemm_tn(st, G0, 4 * DH, S0, K0, g->d_w_ih0 + E, E + P, 4 * DH, P, (int)SB));
+    RC(gemm_tn(st, G0, 4 * DH, S0 + P, K0, g->d_w_hh0, DH, 4 * DH, DH, (int)SB));
+    RC(las_colsum_f32(G0, 4 * DH, (int)SB, 4 * DH, g->d_b_ih0, 0, csw, st));
+    LAS_CUDA(cudaMemcpyAsync(g->d_b_hh0, g->d_b_ih0, (size_t)4 * DH * fsz, cudaMemcpyDeviceToDevice, st));
+    // cell 0: embedding columns through the token table
+    token_reduce_kernel<<<dim3(ceil_div(4 * DH, 256), V), 256, 0, st>>>(G0, tok, dGemb, (int)SB, 4 * DH);
+    LAS_LAUNCH_CHECK();
+    RC(gemm_tn(st, dGemb, 4 * DH, s->emb, E, g->d_w_ih0, E + P, 4 * DH, E, V));
+    // embedding rows via lookups: padding_idx row receives no lookup gradient (nn.Embedding(padding_idx), src/models.py:261-265)
+    if (s->pad_idx >= 0 && s->pad_idx < V) LAS_CUDA(cudaMemsetAsync(dGemb + (size_t)s->pad_idx * 4 * DH, 0, (size_t)4 * DH * fsz, st));
+    RC(gemm(st, dGemb, 4 * DH, s->w_ih0, E + P, 0, g->d_emb, E, V, E, 4 * DH, 1.f));
+    // keys / values: dK[b] = DE[:, b]^T . Q[:, b] ; dV[b] = W[:, b]^T . dctx[:, b]   (batched over b, per head)
+    for (int h = 0; h < heads; ++h) {
+        LasGemmF32 d{};
+        d.M = T; d.N = d_head; d.K = S + 1; d.batch = B;
+        d.a_m_si = 1; d.a_k_si = (long long)B * heads * T; d.bsA = (long long)heads * T;
+        d.b_k_si = (long long)B * 2 * P; d.b_n_s = 1; d.bsB = 2 * P;
+        d.c_m_si = P; d.bsC = (long long)T * P;
+        d.alpha = 1.f; d.beta = 0.f;
+        d.A = DE + (size_t)h * T; d.B = QC + (size_t)h * d_head; d.C = g->dK + (size_t)h * d_head;
+        RC(las_gemm_f32(&d, st));
+        d.A = W + (size_t)h * T; d.B = dQC + P + (size_t)h * d_head; d.C = g->dV + (size_t)h * d_head;
+        RC(las_gemm_f32(&d, st));
+    }
+    return LAS_OK;
+}

@@ -1,0 +1,379 @@
+"""autograd.Function wrappers around the C ABI (include/las_b200.h).
+
+PyTorch is plumbing here: it owns device memory (inputs, outputs, saved activations, workspaces), streams and the
+autograd graph.  All arithmetic of the hot path runs in liblas_b200.so; there is no PyTorch/CPU fallback -- a CPU
+tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import LasAttnStep, LasGemmF32, LasSpeller, LasSpellerGrads, check, ptr, stream_ptr
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('las_b200 runs on CUDA tensors only (sm_100a kernels, no CPU fallback); got a '
+                               f'{t.device} tensor')
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 + contiguous view/copy (parameters already are)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def gemm_raw(A, B, Cout, M, N, K, *, am=(0, 0, 0), ak=(0, 1, 0), bk=(0, 1, 0), bn=1, cm=(0, 0, 0), bias1=None, bias2=None,
+             alpha=1.0, beta=0.0, batch=1, bsA=0, bsB=0, bsC=0, a_off=0, b_off=0, c_off=0, gate=False):
+    """Thin wrapper over las_gemm_f32.  am/ak/bk/cm = (s_outer, s_inner, inner); *_off are element offsets."""
+    d = LasGemmF32()
+    d.A = A.data_ptr() + 4 * a_off
+    d.B = B.data_ptr() + 4 * b_off
+    d.C = Cout.data_ptr() + 4 * c_off
+    d.bias1 = ptr(bias1)
+    d.bias2 = ptr(bias2)
+    d.M, d.N, d.K, d.batch = int(M), int(N), int(K), int(batch)
+    d.a_m_so, d.a_m_si, d.a_m_inner = int(am[0]), int(am[1]), int(am[2])
+    d.a_k_so, d.a_k_si, d.a_k_inner = int(ak[0]), int(ak[1]), int(ak[2])
+    d.b_k_so, d.b_k_si, d.b_k_inner = int(bk[0]), int(bk[1]), int(bk[2])
+    d.b_n_s = int(bn)
+    d.c_m_so, d.c_m_si, d.c_m_inner = int(cm[0]), int(cm[1]), int(cm[2])
+    d.bsA, d.bsB, d.bsC = int(bsA), int(bsB), int(bsC)
+    d.alpha, d.beta = float(alpha), float(beta)
+    d.prof_tag = 1 if gate else 0
+    check(_lib.load().las_gemm_f32(C.byref(d), stream_ptr()), 'gemm_f32')
+
+
+def colsum(X: torch.Tensor, ld: int, M: int, N: int, out: torch.Tensor, x_off: int = 0, accumulate: bool = False):
+    lib = _lib.load()
+    scratch = torch.empty(lib.las_colsum_scratch_floats(int(N)), dtype=torch.float32, device=X.device)
+    check(lib.las_colsum_f32(X.data_ptr() + 4 * x_off, int(ld), int(M), int(N), out.data_ptr(), int(accumulate),
+                             scratch.data_ptr(), stream_ptr()), 'colsum')
+
+
+def _rows3d(x: torch.Tensor):
+    """(B, T, F) tensor with contiguous features -> (batch stride, time stride)."""
+    assert x.dim() == 3 and x.stride(2) == 1
+    return x.stride(0), x.stride(1)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# nn.Linear on (B, T, F) / (M, F) inputs -- key_map / value_map / query_map (reference src/models.py:143-149,166)
+# ----------------------------------------------------------------------------------------------------------------------
+class LinearFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, bias2=None):
+        _require_cuda(x, weight, bias, bias2)
+        x = x if x.dtype == torch.float32 else x.float()
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        weight = _f32c(weight)
+        N, K = weight.shape
+        if x.dim() == 3:
+            Bn, T, _ = x.shape
+            sb, st = _rows3d(x)
+            am = (sb, st, T)
+            M = Bn * T
+            out = torch.empty(Bn, T, N, dtype=torch.float32, device=x.device)
+        else:
+            x2 = x.reshape(-1, K)
+            if not x2.is_contiguous():
+                x2 = x2.contiguous()
+            x = x2
+            M = x.shape[0]
+            am = (0, K, 0)
+            out = torch.empty(*x.shape[:-1], N, dtype=torch.float32, device=x.device)
+        gemm_raw(x, weight, out, M, N, K, am=am, ak=(0, 1, 0), bk=(0, 1, 0), bn=K, cm=(0, N, 0),
+                 bias1=_f32c(bias) if bias is not None else None, bias2=_f32c(bias2) if bias2 is not None else None)
+        ctx.save_for_backward(x, weight)
+        ctx.am, ctx.M, ctx.has_bias, ctx.has_bias2 = am, M, bias is not None, bias2 is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        N, K = weight.shape
+        M, am = ctx.M, ctx.am
+        dy = _f32c(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+            gemm_raw(dy, weight, dx, M, K, N, am=(0, N, 0), ak=(0, 1, 0), bk=(0, K, 0), bn=1, cm=(0, K, 0))
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight)
+            # dW[n][k] = sum_m dy[m][n] x[m][k]
+            gemm_raw(dy, x, dw, N, K, M, am=(0, 1, 0), ak=(0, N, 0), bk=am, bn=1, cm=(0, K, 0))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(N, dtype=torch.float32, device=x.device)
+            colsum(dy, N, M, N, db)
+        db2 = None
+        if ctx.has_bias2 and ctx.needs_input_grad[3]:
+            if db is not None:
+                db2 = db.clone()
+            else:
+                db2 = torch.empty(N, dtype=torch.float32, device=x.device)
+                colsum(dy, N, M, N, db2)
+        return dx, dw, db, db2
+
+
+def linear(x, weight, bias=None, bias2=None):
+    return LinearFunction.apply(x, weight, bias, bias2)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# One (Bi)LSTM layer over a padded batch with PackedSequence semantics (+ optional pyramidal frame-pair concat and
+# locked dropout): reference src/modules.py:74-84 (LockedLSTM loop body) and :165-193 (pyramLockedLSTM loop body).
+# ----------------------------------------------------------------------------------------------------------------------
+class LSTMLayerFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, lens_dev, T, pyramid, mask, *weights):
+        """x (B, Tin, D) fp32 with contiguous features; lens_dev (B) int32 = lengths AFTER the pyramid halving;
+        T = max of those lengths; weights = (w_ih, w_hh, b_ih, b_hh) per direction."""
+        _require_cuda(x, lens_dev, *weights)
+        lib = _lib.load()
+        ndir = len(weights) // 4
+        assert ndir in (1, 2) and len(weights) == 4 * ndir
+        if x.dtype != torch.float32:
+            x = x.float()
+        if x.stride(2) != 1:
+            x = x.contiguous()
+        Bn, Tin, D = x.shape
+        sb, st = _rows3d(x)
+        if pyramid:
+            if st != D:            # frame pairs must be adjacent in memory for the concat-as-addressing trick
+                x = x.contiguous()
+                sb, st = _rows3d(x)
+            Din, st_eff = 2 * D, 2 * st
+            assert 2 * T <= Tin
+        else:
+            Din, st_eff = D, st
+            assert T <= Tin
+        ws = [_f32c(w) for w in weights]
+        H = ws[1].shape[1]
+        F_ = ndir * H
+        G4 = 4 * H
+        dev = x.device
+        gates = torch.empty(Bn, T, ndir, G4, dtype=torch.float32, device=dev)
+        for d in range(ndir):
+            w_ih, _, b_ih, b_hh = ws[4 * d:4 * d + 4]
+            assert w_ih.shape == (G4, Din), (w_ih.shape, G4, Din)
+            gemm_raw(x, w_ih, gates, Bn * T, G4, Din, am=(sb, st_eff, T), ak=(0, 1, 0), bk=(0, 1, 0), bn=Din,
+                     cm=(0, ndir * G4, 0), bias1=b_ih, bias2=b_hh, c_off=d * G4, gate=True)
+        w_hh = torch.stack([ws[4 * d + 1] for d in range(ndir)], 0).contiguous()
+        hs_pad = torch.empty(Bn, T + 2, F_, dtype=torch.float32, device=dev)
+        cs_pad = torch.empty(Bn, T + 2, F_, dtype=torch.float32, device=dev)
+        out = torch.empty(Bn, T, F_, dtype=torch.float32, device=dev) if mask is not None else None
+        if mask is not None:
+            mask = _f32c(mask).reshape(Bn, F_)
+        nbytes = lib.las_lstm_rec_workspace_bytes(Bn, H, ndir)
+        wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(lib.las_lstm_rec_fwd_f32(gates.data_ptr(), w_hh.data_ptr(), lens_dev.data_ptr(), ptr(mask), ptr(out),
+                                       hs_pad.data_ptr(), cs_pad.data_ptr(), Bn, T, H, ndir, wsb.data_ptr(), nbytes,
+                                       stream_ptr()), 'lstm_rec_fwd')
+        ctx.save_for_backward(x, lens_dev, gates, hs_pad, cs_pad, w_hh, mask, *ws)
+        ctx.dims = (Bn, Tin, D, T, H, ndir, Din, sb, st_eff, bool(pyramid))
+        y = out if out is not None else hs_pad[:, 1:T + 1]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, lens_dev, gates, hs_pad, cs_pad, w_hh, mask, *ws = ctx.saved_tensors
+        Bn, Tin, D, T, H, ndir, Din, sb, st_eff, pyramid = ctx.dims
+        F_, G4 = ndir * H, 4 * H
+        dev = x.device
+        dy = _f32c(dy)
+        nbytes = lib.las_lstm_rec_workspace_bytes(Bn, H, ndir)
+        wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        # gates (activated) -> d(pre-activation), in place.  The forward's saved tensor is consumed: a second
+        # backward through the same graph is not supported (like cuDNN's reserve space, it is single use).
+        check(lib.las_lstm_rec_bwd_f32(dy.data_ptr(), gates.data_ptr(), cs_pad.data_ptr(), w_hh.data_ptr(), lens_dev.data_ptr(),
+                                       ptr(mask), Bn, T, H, ndir, wsb.data_ptr(), nbytes, stream_ptr()), 'lstm_rec_bwd')
+        dG = gates
+        M = Bn * T
+        dx = None
+        if ctx.needs_input_grad[0]:
+            full = (Tin * D == T * Din)
+            dx = (torch.empty if full else torch.zeros)(Bn, Tin, D, dtype=torch.float32, device=dev)
+            for d in range(ndir):
+                gemm_raw(dG, ws[4 * d], dx, M, Din, G4, am=(0, ndir * G4, 0), ak=(0, 1, 0), bk=(0, Din, 0), bn=1,
+                         cm=(Tin * D, Din, T), beta=0.0 if d == 0 else 1.0, a_off=d * G4, gate=True)
+        grads: List[Optional[torch.Tensor]] = []
+        for d in range(ndir):
+            dw_ih = torch.empty(G4, Din, dtype=torch.float32, device=dev)
+            gemm_raw(dG, x, dw_ih, G4, Din, M, am=(0, 1, 0), ak=(0, ndir * G4, 0), bk=(sb, st_eff, T), bn=1, cm=(0, Din, 0),
+                     a_off=d * G4, gate=True)
+            dw_hh = torch.empty(G4, H, dtype=torch.float32, device=dev)
+            # h_{t-1} for the forward direction is frame t of hs_pad, for the reverse direction frame t+2
+            gemm_raw(dG, hs_pad, dw_hh, G4, H, M, am=(0, 1, 0), ak=(0, ndir * G4, 0), bk=((T + 2) * F_, F_, T), bn=1,
+                     cm=(0, H, 0), a_off=d * G4, b_off=(2 * F_ if d == 1 else 0) + d * H)
+            db = torch.empty(G4, dtype=torch.float32, device=dev)
+            colsum(dG, ndir * G4, M, G4, db, x_off=d * G4)
+            grads += [dw_ih, dw_hh, db, db.clone()]
+        return (dx, None, None, None, None, *grads)
+
+
+def lstm_layer(x, lens_dev, T, pyramid, mask, weights: Sequence[torch.Tensor]):
+    return LSTMLayerFunction.apply(x, lens_dev, int(T), bool(pyramid), mask, *weights)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Fused attention step (reference src/models.py:168-185), standalone autograd form used by
+# MultiheadCrossAttention.forward; the Speller's fused loop calls the same kernels from C.
+# ----------------------------------------------------------------------------------------------------------------------
+class AttnStepFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, K, V, lens_dev, heads):
+        _require_cuda(q, K, V, lens_dev)
+        q, K, V = _f32c(q), _f32c(K), _f32c(V)
+        Bn, T, P = K.shape
+        ctxv = torch.empty(Bn, P, dtype=torch.float32, device=q.device)
+        w = torch.empty(Bn, heads, T, dtype=torch.float32, device=q.device)
+        d = LasAttnStep()
+        d.q, d.ld_q = q.data_ptr(), P
+        d.K, d.V, d.lens = K.data_ptr(), V.data_ptr(), lens_dev.data_ptr()
+        d.w, d.ld_w = w.data_ptr(), T
+        d.ctx, d.ld_ctx = ctxv.data_ptr(), P
+        d.B, d.T, d.P, d.heads = Bn, T, P, int(heads)
+        d.scale = float((P // heads) ** 0.5)
+        check(_lib.load().las_attn_step_fwd_f32(C.byref(d), stream_ptr()), 'attn_step_fwd')
+        ctx.save_for_backward(q, K, V, lens_dev, w)
+        ctx.heads = int(heads)
+        ctx.mark_non_differentiable(w)
+        return ctxv, w
+
+    @staticmethod
+    def backward(ctx, dctx, _dw):
+        q, K, V, lens_dev, w = ctx.saved_tensors
+        heads = ctx.heads
+        Bn, T, P = K.shape
+        dh = P // heads
+        dctx = _f32c(dctx).clone()
+        dq = torch.empty_like(q)
+        de = torch.empty_like(w)
+        d = LasAttnStep()
+        d.q, d.ld_q = q.data_ptr(), P
+        d.K, d.V, d.lens = K.data_ptr(), V.data_ptr(), lens_dev.data_ptr()
+        d.w, d.ld_w = w.data_ptr(), T
+        d.dctx, d.ld_dctx = dctx.data_ptr(), P
+        d.dq, d.ld_dq, d.dq_accumulate = dq.data_ptr(), P, 0
+        d.de = de.data_ptr()
+        d.B, d.T, d.P, d.heads = Bn, T, P, heads
+        d.scale = float(dh ** 0.5)
+        check(_lib.load().las_attn_step_bwd_f32(C.byref(d), stream_ptr()), 'attn_step_bwd')
+        dK = dV = None
+        if ctx.needs_input_grad[1]:
+            dK = torch.empty_like(K)
+            for h in range(heads):     # dK[b,t,h*d+j] = de[b,h,t] * q[b,h*d+j]
+                gemm_raw(de, q, dK, T, dh, 1, am=(0, 1, 0), ak=(0, 0, 0), bk=(0, 0, 0), bn=1, cm=(0, P, 0), batch=Bn,
+                         bsA=heads * T, bsB=P, bsC=T * P, a_off=h * T, b_off=h * dh, c_off=h * dh)
+        if ctx.needs_input_grad[2]:
+            dV = torch.empty_like(V)
+            for h in range(heads):
+                gemm_raw(w, dctx, dV, T, dh, 1, am=(0, 1, 0), ak=(0, 0, 0), bk=(0, 0, 0), bn=1, cm=(0, P, 0), batch=Bn,
+                         bsA=heads * T, bsB=P, bsC=T * P, a_off=h * T, b_off=h * dh, c_off=h * dh)
+        return dq, dK, dV, None, None
+
+
+def attn_step(q, K, V, lens_dev, heads):
+    return AttnStepFunction.apply(q, K, V, lens_dev, heads)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Speller decoder loop (reference src/models.py:336-385)
+# ----------------------------------------------------------------------------------------------------------------------
+SPELLER_PARAM_ORDER = ('emb', 'cls_b', 'w_ih0', 'w_hh0', 'b_ih0', 'b_hh0', 'w_ih1', 'w_hh1', 'b_ih1', 'b_hh1', 'wq', 'bq',
+                       'init_query')
+
+
+def _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training):
+    Bn, T, P = K.shape
+    emb = params[0]
+    s = LasSpeller()
+    s.B, s.T, s.P = Bn, T, P
+    s.E = emb.shape[1]
+    s.DH = params[3].shape[1]
+    s.DO = params[7].shape[1]
+    s.V = emb.shape[0]
+    s.heads, s.steps = int(heads), int(steps)
+    s.sos_idx, s.pad_idx = int(sos_idx), int(pad_idx)
+    s.training = int(training)
+    for name, t in zip(SPELLER_PARAM_ORDER, params):
+        setattr(s, name, t.data_ptr())
+    s.K, s.V_, s.enc_lens = K.data_ptr(), V.data_ptr(), enc_lens.data_ptr()
+    if dec_y is not None:
+        s.dec_y, s.ld_y = dec_y.data_ptr(), dec_y.stride(0)
+    keep = None
+    if use_gold is not None:
+        keep = (C.c_ubyte * len(use_gold))(*[1 if u else 0 for u in use_gold])
+        s.use_gold_host = C.cast(keep, C.c_void_p)
+    s.drop0, s.drop1 = ptr(drop0), ptr(drop1)
+    return s, keep
+
+
+class SpellerFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, K, V, enc_lens, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, *params):
+        _require_cuda(K, V, enc_lens, *params)
+        lib = _lib.load()
+        K, V = _f32c(K), _f32c(V)
+        params = tuple(_f32c(p) for p in params)
+        dev = K.device
+        Bn, T, P = K.shape
+        Vn = params[0].shape[0]
+        if dec_y is not None:
+            dec_y = dec_y.to(device=dev, dtype=torch.int32)
+            if dec_y.stride(1) != 1:
+                dec_y = dec_y.contiguous()
+        drop0 = _f32c(drop0) if drop0 is not None else None
+        drop1 = _f32c(drop1) if drop1 is not None else None
+        s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training)
+        logits = torch.empty(Bn, steps, Vn, dtype=torch.float32, device=dev)
+        att0 = torch.empty(steps + 1, heads, T, dtype=torch.float32, device=dev)
+        chars = torch.zeros(steps, Bn, dtype=torch.int32, device=dev)
+        nf = lib.las_speller_workspace_floats(C.byref(s))
+        ni = lib.las_speller_workspace_ints(C.byref(s))
+        fws = torch.empty(nf, dtype=torch.float32, device=dev)
+        iws = torch.empty(ni, dtype=torch.int32, device=dev)
+        s.logits, s.att0, s.chars = logits.data_ptr(), att0.data_ptr(), chars.data_ptr()
+        s.fws, s.fws_floats, s.iws, s.iws_ints = fws.data_ptr(), nf, iws.data_ptr(), ni
+        check(lib.las_speller_fwd_f32(C.byref(s), stream_ptr()), 'speller_fwd')
+        if training:
+            ctx.save_for_backward(K, V, enc_lens, dec_y, drop0, drop1, fws, iws, *params)
+            ctx.cfg = (use_gold, steps, heads, sos_idx, pad_idx)
+        ctx.mark_non_differentiable(att0, chars)
+        return logits, att0, chars
+
+    @staticmethod
+    def backward(ctx, dlogits, _datt, _dchars):
+        lib = _lib.load()
+        K, V, enc_lens, dec_y, drop0, drop1, fws, iws, *params = ctx.saved_tensors
+        use_gold, steps, heads, sos_idx, pad_idx = ctx.cfg
+        s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, True)
+        s.fws, s.fws_floats, s.iws, s.iws_ints = fws.data_ptr(), fws.numel(), iws.data_ptr(), iws.numel()
+        # outputs of fwd are not needed by bwd but the descriptor check wants non-null
+        dummy = torch.empty(1, dtype=torch.int32, device=K.device)
+        s.logits, s.chars = fws.data_ptr(), dummy.data_ptr()
+        dlogits = _f32c(dlogits)
+        g = LasSpellerGrads()
+        g.dlogits = dlogits.data_ptr()
+        grads = [torch.empty_like(p) for p in params]
+        for name, t in zip(SPELLER_PARAM_ORDER, grads):
+            setattr(g, 'd_' + name, t.data_ptr())
+        # d_w_ih0 is written in three column/row pieces that together cover it; no zero-init needed
+        dK, dV = torch.empty_like(K), torch.empty_like(V)
+        g.dK, g.dV = dK.data_ptr(), dV.data_ptr()
+        check(lib.las_speller_bwd_f32(C.byref(s), C.byref(g), stream_ptr()), 'speller_bwd')
+        return (dK, dV, None, None, None, None, None, None, None, None, None, None, *grads)
+
+
+def speller_loop(K, V, enc_lens, params, *, steps, heads, sos_idx, pad_idx, training, dec_y=None, use_gold=None,
+                 drop0=None, drop1=None):
+    return SpellerFunction.apply(K, V, enc_lens, dec_y, use_gold, drop0, drop1, int(steps), int(heads), int(sos_idx),
+                                 int(pad_idx), bool(training), *params)

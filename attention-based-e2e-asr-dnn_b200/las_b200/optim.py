@@ -1,0 +1,112 @@
+"""Fused AdamW(amsgrad) with the GradScaler unscale and the global-norm clip folded in.
+
+Replaces the sequence of reference src/train.py:165-183
+    scaler.unscale_(optimizer); clip_grad_norm_(params, grad_norm); scaler.step(optimizer); scaler.update()
+(~15 foreach launches, ~6 passes over the gradients) by two launches of las_adamw_amsgrad_fused.
+
+Two ways to use it:
+  * drop-in: `FusedAdamW(model.parameters(), lr=..., weight_decay=..., amsgrad=True)` is a torch.optim.Optimizer with
+    the same state_dict layout as torch.optim.AdamW (step, exp_avg, exp_avg_sq, max_exp_avg_sq); `.step()` alone is the
+    plain AdamW update (grads already unscaled / clipped by the caller, as train.py does).
+  * fused: `.step_fused(inv_scale, max_norm)` does unscale + clip + update (or skips on non-finite grads, like
+    GradScaler.step) and returns device-side (found_inf, grad_norm) without a host sync.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List
+
+import torch
+
+from . import _lib
+from ._lib import ADAM_CHUNK, LasAdamChunk, LasAdamTensor, check, stream_ptr
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)
+        super().__init__(params, defaults)
+        self._status = None
+
+    def _init_state(self, p):
+        st = self.state[p]
+        if len(st) == 0:
+            st['step'] = torch.tensor(0.0, dtype=torch.float32)      # same key set as torch.optim.AdamW
+            st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            if True:
+                st['max_exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        return st
+
+    @torch.no_grad()
+    def _run(self, inv_scale: float, max_norm: float):
+        lib = _lib.load()
+        for group in self.param_groups:
+            ps = [p for p in group['params'] if p.grad is not None]
+            if not ps:
+                continue
+            dev = ps[0].device
+            if not ps[0].is_cuda:
+                raise RuntimeError('FusedAdamW runs on CUDA parameters only (no CPU fallback)')
+            beta1, beta2 = group['betas']
+            tab = (LasAdamTensor * len(ps))()
+            chunks: List[tuple] = []
+            for i, p in enumerate(ps):
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError('FusedAdamW needs contiguous fp32 parameters')
+                st = self._init_state(p)
+                # NOTE: like torch, the step counter advances before the update; when a non-finite gradient makes the
+                # kernel skip, the caller rolls it back (see step_fused)
+                st['step'] += 1
+                step = float(st['step'])
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                if g.dtype != torch.float32:
+                    g = g.float()
+                p._las_g = g          # keep alive until the kernels ran
+                t = tab[i]
+                t.p, t.g, t.m, t.v = p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr()
+                t.vmax = st['max_exp_avg_sq'].data_ptr()
+                t.numel = p.numel()
+                t.bias_c1 = 1.0 - beta1 ** step
+                t.bias_c2_sqrt = math.sqrt(1.0 - beta2 ** step)
+                for off in range(0, p.numel(), ADAM_CHUNK):
+                    chunks.append((i, off))
+            ck = (LasAdamChunk * len(chunks))()
+            for j, (i, off) in enumerate(chunks):
+                ck[j].tensor, ck[j].offset = i, off
+            # pointer tables go up as one small pinned->device copy each (grads are re-allocated by autograd every step)
+            tab_t = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(dev, non_blocking=True)
+            ck_t = torch.frombuffer(bytearray(bytes(ck)), dtype=torch.uint8).to(dev, non_blocking=True)
+            scratch = torch.empty(len(chunks) + 8, dtype=torch.float32, device=dev)
+            status = torch.empty(2, dtype=torch.float32, device=dev)
+            check(lib.las_adamw_amsgrad_fused(tab_t.data_ptr(), len(ps), ck_t.data_ptr(), len(chunks), float(group['lr']),
+                                              float(beta1), float(beta2), float(group['eps']), float(group['weight_decay']),
+                                              float(inv_scale), float(max_norm), int(bool(group['amsgrad'])),
+                                              scratch.data_ptr(), status.data_ptr(), stream_ptr()), 'adamw_amsgrad_fused')
+            self._status = status
+            self._keep = (tab_t, ck_t, scratch)
+        return self._status
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self._run(1.0, 0.0)          # max_norm 0 => no clipping: grads were prepared by the caller
+        return loss
+
+    @torch.no_grad()
+    def step_fused(self, inv_scale: float = 1.0, max_norm: float = 5.0, sync_skip: bool = False):
+        """unscale + clip + AdamW in one go.  Returns the device tensor [found_inf, grad_norm].  With sync_skip=True the
+        host reads found_inf and rolls the step counters back on a skipped step (exact GradScaler semantics; costs a
+        sync).  Without it the counters keep advancing on skipped steps (only the bias correction of later steps is
+        affected, by one step)."""
+        status = self._run(inv_scale, max_norm)
+        if sync_skip and status is not None and bool(status[0].item() != 0):
+            for group in self.param_groups:
+                for p in group['params']:
+                    if p.grad is not None and p in self.state:
+                        self.state[p]['step'] -= 1
+        return status

@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- LAS teacher-forced training throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W                 # our arm (CUDA path through the public nn.Module API)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W  # reference arm: the CPU port of the reference algorithm
+    torchrun ... bench.py --gpus N ...                            # N > 1: one rank per GPU, NCCL gradient all-reduce
+
+A "step" = one pass of the hot path over one synthetic batch: Listener + Speller forward under teacher forcing, masked CE,
+backward (BPTT), unscale + clip + AdamW(amsgrad) update [+ gradient all-reduce].  Workload = BASELINE.json configs[1]:
+best base-LAS (hid 512, 1 LSTM + 3 pLSTM bidirectional, att_proj 256, dec 512/256), batch 96 per GPU, T=1600, L=300.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'attention-based-e2e-asr-dnn_b200')
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+METRIC = 'las_train_utterances_per_sec'
+UNIT = 'utterances/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=96, help='utterances per GPU')
+    ap.add_argument('--T', type=int, default=1600)
+    ap.add_argument('--L', type=int, default=300)
+    ap.add_argument('--config', default='best')
+    ap.add_argument('--cpu-sample-batch', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--greedy', action='store_true', help='also report greedy-decode chars/s (configs[3]) as an extra key')
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d.get('hbm_gbs', 6650.0), tf_burst=d.get('bf16_tflops', 1590.0),
+                    tf_sustained=d.get('bf16_tflops_sustained', 1400.0), source='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def oracle_cpu_step(cfg_name, B, T, L, seed=11785):
+    """One teacher-forced train step (fwd + bwd + AdamW-amsgrad) of the reference algorithm's CPU port (oracle/): the checker,
+    timed here as the CPU baseline.  Returns seconds."""
+    from oracle import golden_util as gu
+    from oracle import las_oracle as orc
+    torch.set_num_threads(os.cpu_count())
+    cfg = gu.get_config(cfg_name)
+    sd = gu.make_state_dict(cfg, seed)
+    x, lx, y = gu.make_inputs(seed + 1, B, T, L)
+    p = {k: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in sd.items() if k != 'spell.cls.weight'}
+    p['spell.cls.weight'] = p['spell.char_emb.weight']
+    lc = cfg['listener_configs']
+    t0 = time.perf_counter()
+    logits, _ = orc.las_forward(p, torch.from_numpy(x), lx.tolist(), lstm_layers=lc['lstm_layers'], plstm_layers=lc['plstm_layers'],
+                                heads=1, training=True, steps=L, dec_y=torch.from_numpy(y), coins=[True] * L)
+    loss = orc.masked_ce_loss(logits, torch.from_numpy(y), [L] * B)
+    loss.backward()
+    names = [k for k in p if k != 'spell.cls.weight']
+    params = [p[k].detach() for k in names]
+    grads = [p[k].grad for k in names]
+    orc.optimizer_step(params, grads, [dict() for _ in names], lr=5e-4, weight_decay=5e-6)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """Reference arm: the reference is pure Python (no compilable sources, nothing pip-installable: it ships no
+    setup.py / pyproject), and /root/reference does not exist on the GPU box, so this arm times the CPU port of its
+    algorithm (oracle/, pinned to the reference by tests/golden) on all host cores, on a bounded sample of the workload."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    B = args.cpu_sample_batch
+    times = []
+    for i in range(max(1, min(args.warmup, 1))):
+        oracle_cpu_step(args.config, 1, max(args.T // 8, 8), max(args.L // 8, 2))      # warm the allocator / thread pool
+    for i in range(args.steps):
+        times.append(oracle_cpu_step(args.config, B, args.T, args.L))
+    ms = 1e3 * float(np.mean(times))
+    val = B / (ms / 1e3)
+    sample = f'B={B} utterances of the same T={args.T}, L={args.L} workload per step'
+    out = dict(impl='reference', metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+               ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+               config=dict(workload=f'{args.config} base-LAS teacher-forced train step, T={args.T}, L={args.L}', sample=sample),
+               cpu_baseline=dict(value=val, unit=UNIT, cores=os.cpu_count(), kind='port', sample=sample),
+               e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import las_b200
+    from las_b200 import _lib
+    from las_b200.ddp import BucketedGradReducer
+    from las_b200.models import ListenAttendSpell
+    from las_b200.optim import FusedAdamW
+    from oracle import golden_util as gu      # config table + seeded synthetic inputs only (no oracle compute here)
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py (impl ours) needs a GPU: las_b200 has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    _lib.check(lib.las_init(local), 'las_init')
+
+    B, T, L = args.batch, args.T, args.L
+    cfg = gu.get_config(args.config)
+    torch.manual_seed(11785)                     # the reference's seed (config/sample-attention.yml:11), same on every rank
+    model = ListenAttendSpell(**cfg).to(dev).train()
+    if world > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    opt = FusedAdamW(model.parameters(), lr=5e-4, weight_decay=5e-6, amsgrad=True)
+    reducer = BucketedGradReducer(list(model.named_parameters()), world_size=world)
+    x_np, lx_np, y_np = gu.make_inputs(11785 + rank, B, T, L)
+    x_host = torch.from_numpy(x_np).pin_memory()
+    y_host = torch.from_numpy(y_np).pin_memory()
+    lx = torch.from_numpy(lx_np)                 # CPU int64, never moved (src/train.py:127)
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    crit = torch.nn.CrossEntropyLoss(reduction='none')
+    V = cfg['speller_configs']['dec_vocab_size']
+    scale = 65536.0                              # GradScaler's initial scale (torch amp/grad_scaler.py)
+
+    def step(x, y):
+        reducer.zero_grad()
+        logits, _att = model(x, lx, y, 1.0, False)                       # tf_rate 1.0 (README stage 1)
+        loss = crit(logits.view(-1, V), y.view(-1)).mean()               # all-ones mask: every target is non-pad
+        (loss * scale).backward()
+        reducer.finish()
+        opt.step_fused(inv_scale=1.0 / (scale * world), max_norm=5.0)
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, y_dev)
+    sync()
+
+    # ---- device-resident throughput (inputs already in HBM) ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    PROF_KINDS = dict(gemm_gates=0, gemm_other=1, rec_fwd=2, rec_bwd=3, attn_fwd=4, attn_bwd=5, adam=6, speller_fwd=7, speller_bwd=8)
+    lib.las_prof_reset()
+    lib.las_prof_enable(0x1FF if rank == 0 else 0)
+    las_b200.reset_launch_count()
+    ms_total = timed(lambda: step(x_dev, y_dev), args.steps)
+    launches = las_b200.launch_count()
+    lib.las_prof_enable(0)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1e3)
+
+    import ctypes as C
+    prof = {}
+    if rank == 0:
+        for name, kind in PROF_KINDS.items():
+            ms, n, work = C.c_double(), C.c_longlong(), C.c_double()
+            _lib.check(lib.las_prof_collect(kind, C.byref(ms), C.byref(n), C.byref(work)), 'prof_collect')
+            prof[name] = dict(ms_per_step=ms.value / args.steps, launches_per_step=n.value / args.steps, work_per_step=work.value / args.steps)
+        lib.las_prof_reset()
+
+    # ---- end to end: host (pinned) inputs -> device every step, loss read back every step ----
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        return float(step(xd, yd).item())
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    e2e_value = world * B / (ms_e2e / 1e3)
+    h2d = x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    gg = prof['gemm_gates']
+    tf_achieved = (gg['work_per_step'] / 1e12) / (gg['ms_per_step'] / 1e3) if gg['ms_per_step'] > 0 else 0.0
+    roofline = dict(kernel='lstm input-gate GEMMs (fwd + dgrad + wgrad, all layers)', bound='tensor', achieved=tf_achieved,
+                    peak=pk['tf_sustained'], unit='TFLOP/s', frac=tf_achieved / pk['tf_sustained'], traffic=None,
+                    peak_source=pk['source'] + ' bf16 sustained', ms_per_step=gg['ms_per_step'], flops_per_step=gg['work_per_step'])
+    af = prof['attn_fwd']
+    at_gbs = (af['work_per_step'] / 1e9) / (af['ms_per_step'] / 1e3) if af['ms_per_step'] > 0 else 0.0
+    attn_roofline = dict(kernel='fused attention step fwd (energy+masked softmax+context)', bound='hbm', achieved=at_gbs, peak=pk['hbm'],
+                         unit='GB/s', frac=at_gbs / pk['hbm'], traffic=None, peak_source=pk['source'],
+                         us_per_launch=1e3 * af['ms_per_step'] / max(af['launches_per_step'], 1),
+                         bytes_per_launch=af['work_per_step'] / max(af['launches_per_step'], 1))
+    T_total = prof['rec_fwd']['work_per_step']
+    rec = dict(fwd_us_per_timestep=1e3 * prof['rec_fwd']['ms_per_step'] / max(T_total, 1),
+               bwd_us_per_timestep=1e3 * prof['rec_bwd']['ms_per_step'] / max(T_total, 1), timesteps_per_step=T_total)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        Bs = args.cpu_sample_batch
+        sec = oracle_cpu_step(args.config, Bs, T, L)
+        cpu = dict(value=Bs / sec, unit=UNIT, cores=os.cpu_count(), kind='port',
+                   sample=f'one fwd+bwd+AdamW step of the CPU port (oracle/) at B={Bs}, T={T}, L={L}: {sec:.1f} s')
+
+    out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
+               higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+               config=dict(workload=f'{args.config} base-LAS teacher-forced train step (fwd+bwd+unscale/clip/AdamW-amsgrad), '
+                                    f'batch {B}/GPU, T={T}, L={L}, tf_rate=1.0', global_batch=B * world, parallelism=f'dp{world}',
+                           l2_policy='inputs+activations per step (>2.5 GB) exceed the 126 MB L2; no explicit flush'),
+               clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e),
+               gpu_launches=int(launches), roofline=roofline, attn_roofline=attn_roofline, recurrence=rec,
+               kernel_ms_per_step={k: round(v['ms_per_step'], 3) for k, v in prof.items()}, cpu_baseline=cpu)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

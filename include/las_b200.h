@@ -1,0 +1,194 @@
+/*
+ * las_b200 -- C ABI of the B200-native Listen-Attend-Spell hot path.
+ *
+ * The reference (Astromsoc/attention-based-e2e-asr-dnn) is pure Python/PyTorch and has NO native / FFI interface; the
+ * drop-in boundary a user sees is the nn.Module API of src/models.py / src/modules.py (kept by the Python package
+ * las_b200).  This header is the boundary underneath it: the entry points our modules bind with
+ * ctypes, each citing the reference call site (file:line under /root/reference) whose PyTorch library dispatch it
+ * replaces.  Conventions:
+ *   - extern "C", plain pointers and sizes; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller (PyTorch) owns every buffer, including workspaces (size queries: *_workspace_*);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises the host;
+ *   - return 0 on success, negative LAS_ERR_* otherwise; las_last_error() gives the message (thread-local);
+ *   - no CPU fallback: an entry either launches sm_100a kernels or returns an error;
+ *   - re-entrant across devices (one process per GPU); the device of the first pointer argument is made current,
+ *     so calls from the autograd engine thread are safe.
+ */
+#ifndef LAS_B200_H
+#define LAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAS_B200_ABI_VERSION 1
+
+/* ---- runtime ------------------------------------------------------------------------------------------------ */
+int las_abi_version(void);
+/* idempotent per-device initialisation (SM count, shared-memory opt-in, cooperative-launch check) */
+int las_init(int device);
+const char* las_last_error(void);
+/* number of kernels this library has launched on the calling thread's devices since the last reset
+ * (bench.py's gpu_launches) */
+long long las_launch_count(void);
+void las_launch_count_reset(void);
+
+/* per-kernel-kind device timing for bench.py: CUDA events recorded around launches of the enabled kinds on the
+ * launching stream.  kinds: 0 gate GEMMs, 1 other GEMMs, 2 recurrence fwd, 3 recurrence bwd, 4 attention step fwd,
+ * 5 attention step bwd, 6 optimizer, 7 speller loop fwd, 8 speller loop bwd.  Synchronise before collecting.
+ * `total_work` = algorithmic FLOPs (GEMM kinds), bytes (attention kinds) or timesteps (recurrence / speller kinds). */
+void las_prof_enable(unsigned kind_mask);
+void las_prof_reset(void);
+int las_prof_collect(int kind, double* total_ms, long long* count, double* total_work);
+
+/* ---- fp32 GEMM with two-level strided indexing ------------------------------------------------------------------
+ * C[m][n] = alpha * sum_k A(m,k) B(k,n) + beta*C[m][n] + bias1[n] + bias2[n]
+ * index i -> (i / inner) * s_outer + (i % inner) * s_inner ; inner == 0 means single level (i * s_inner).
+ * Replaces: nn.LSTM's input projection X.W_ih^T (src/modules.py:80,189), the pyramidal reshape feeding it
+ * (src/modules.py:171-185, done here as addressing), nn.Linear key/value/query maps (src/models.py:143-149,166),
+ * the LSTMCell GEMMs (src/modules.py:355), the tied classifier (src/models.py:373), and every autograd matmul of
+ * those in backward. */
+typedef struct {
+    const float* A;
+    const float* B;
+    float* C;
+    const float* bias1; /* nullable, length N */
+    const float* bias2; /* nullable, length N */
+    int M, N, K, batch;
+    long long a_m_so, a_m_si; int a_m_inner;
+    long long a_k_so, a_k_si; int a_k_inner;
+    long long b_k_so, b_k_si; int b_k_inner;
+    long long b_n_s;
+    long long c_m_so, c_m_si; int c_m_inner; /* C's n stride is 1 */
+    long long bsA, bsB, bsC;                 /* batch strides (elements) */
+    float alpha, beta;
+    int prof_tag;                            /* 1: count this launch as an LSTM input-gate GEMM in las_prof_* */
+} LasGemmF32;
+int las_gemm_f32(const LasGemmF32* desc, void* stream);
+
+/* column sums: out[n] (+)= sum_m X[m*ld + n], m < M, n < N.  Bias gradients (autograd of the bias adds in nn.LSTM /
+ * nn.LSTMCell / nn.Linear). `scratch` needs las_colsum_scratch_floats(N) floats. */
+size_t las_colsum_scratch_floats(int N);
+int las_colsum_f32(const float* X, long long ld, int M, int N, float* out, int accumulate, float* scratch, void* stream);
+
+/* ---- persistent LSTM recurrence (fp32 parity mode) ----------------------------------------------------------------
+ * Replaces the time loop of nn.LSTM over a PackedSequence, pad_packed_sequence's zero fill and the locked-dropout
+ * multiply: src/modules.py:78-84 (LockedLSTM) and :187-193 (pyramLockedLSTM); backward replaces autograd through them.
+ *   gates   (B, T, ndir, 4H)  in: X.W_ih^T + b_ih + b_hh (gate order i,f,g,o) ; out: activated gates (saved)
+ *   w_hh    (ndir, 4H, H)
+ *   lens    (B) int32, 1 <= len <= T
+ *   drop_mask (B, ndir*H) already scaled by 1/(1-p), or NULL
+ *   out     (B, T, ndir*H) masked layer output, or NULL (then the caller uses hs_pad[:,1:T+1])
+ *   hs_pad, cs_pad (B, T+2, ndir*H): frame t+1 = time t; frames 0 and T+1 are written as zeros
+ * bwd: dout (B,T,ndir*H) contiguous; gates in: activated, out: d(pre-activation) (zeros at t >= len). */
+size_t las_lstm_rec_workspace_bytes(int B, int H, int ndir);
+int las_lstm_rec_fwd_f32(float* gates, const float* w_hh, const int* lens, const float* drop_mask, float* out, float* hs_pad,
+                         float* cs_pad, int B, int T, int H, int ndir, void* ws, size_t ws_bytes, void* stream);
+int las_lstm_rec_bwd_f32(const float* dout, float* gates, const float* cs_pad, const float* w_hh, const int* lens,
+                         const float* drop_mask, int B, int T, int H, int ndir, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- fused attention step -------------------------------------------------------------------------------------------
+ * Replaces MultiheadCrossAttention.forward after query_map (src/models.py:168-185): energy * sqrt(d), pad mask from
+ * lengths (build_pad_masks :106-115, no host mask / H2D), softmax, zeroing, context.  K, V are (B, T, P) row-major.
+ * fwd: q (row stride ld_q) -> ctx (ld_ctx) [+ ctx2 (ld_ctx2)], w ((B*heads), row stride ld_w) [+ w_b0: weights of
+ *      batch row 0, (heads, T) contiguous -- the att_wgts[0] bookkeeping of src/models.py:349,377]
+ * bwd: dctx (+ dctx2, nullable; when given the sum is written back to dctx) , w -> dq (ld_dq; accumulated into when
+ *      dq_accumulate), de ((B*heads), ld_w) = d(energy) * scale, ready for the deferred dK = de^T.q GEMM. */
+typedef struct {
+    const float* q; long long ld_q;
+    const float* K; const float* V; const int* lens;
+    float* w; long long ld_w;
+    float* w_b0;
+    float* ctx; long long ld_ctx;
+    float* ctx2; long long ld_ctx2;
+    float* dctx; long long ld_dctx;
+    const float* dctx2; long long ld_dctx2;
+    float* dq; long long ld_dq; int dq_accumulate;
+    float* de;
+    int B, T, P, heads;
+    float scale;
+} LasAttnStep;
+int las_attn_step_fwd_f32(const LasAttnStep* desc, void* stream);
+int las_attn_step_bwd_f32(const LasAttnStep* desc, void* stream);
+
+/* ---- single LSTM cell, pointwise part ---------------------------------------------------------------------------------
+ * Replaces the fused pointwise of nn.LSTMCell + nn.Dropout in AutoRegDecoderLSTMCell.forward (src/modules.py:355-357)
+ * for callers that step the cell themselves.  gates (B,4H): in pre-activations (both GEMMs + biases summed),
+ * out activated gates.  bwd: gates in activated / out d(pre-activation); dc_io (B,H) carries dL/dc in and out. */
+int las_lstm_cell_fwd_f32(float* gates, const float* c_prev, const float* mask, float* h_out, float* c_out, int B, int H,
+                          void* stream);
+int las_lstm_cell_bwd_f32(float* gates, const float* dh, const float* mask, const float* c, const float* c_prev, float* dc_io,
+                          int B, int H, void* stream);
+
+/* ---- Speller decoder loop --------------------------------------------------------------------------------------------
+ * Replaces the Python loop of Speller.forward (src/models.py:336-385) including AutoRegDecoderLSTMCell.forward
+ * (src/modules.py:340-365), the per-step attention, the tied classifier and the greedy argmax feedback, with no host
+ * synchronisation per step (the reference syncs every step at src/models.py:377 and draws a host coin at :357 -- the
+ * coins are pre-drawn by the caller into use_gold_host).
+ * All matrices fp32 row-major.  `fws` / `iws` are caller-owned workspaces (las_speller_workspace_floats/ints); in
+ * training they hold everything backward needs and must be passed unchanged to las_speller_bwd_f32. */
+typedef struct {
+    /* dims */
+    int B, T, P, E, DH, DO, V, heads, steps;
+    int sos_idx, pad_idx;
+    int training;                 /* 1: save history for backward */
+    /* parameters */
+    const float* emb;             /* (V, E)  char_emb.weight == cls.weight */
+    const float* cls_b;           /* (V) */
+    const float* w_ih0; const float* w_hh0; const float* b_ih0; const float* b_hh0;   /* (4DH, E+P) (4DH, DH) (4DH) */
+    const float* w_ih1; const float* w_hh1; const float* b_ih1; const float* b_hh1;   /* (4DO, DH) (4DO, DO) (4DO) */
+    const float* wq; const float* bq;   /* (P, DO) (P) */
+    const float* init_query;      /* (DO) */
+    /* inputs */
+    const float* K; const float* V_; const int* enc_lens;   /* (B,T,P) (B,T,P) (B) */
+    const int* dec_y; long long ld_y;   /* (B, >=steps) gold tokens, training only */
+    const unsigned char* use_gold_host; /* HOST array (steps): step t>0 feeds the gold token y[:,t-1]; NULL => never */
+    const float* drop0; const float* drop1;   /* (steps,B,DH) (steps,B,DO) scaled masks or NULL */
+    /* outputs */
+    float* logits;                /* (B, steps, V) */
+    float* att0;                  /* (steps+1, heads, T): attention weights of batch row 0 */
+    int* chars;                   /* (steps, B) greedy argmax per step (written when fed back or in eval) */
+    /* workspaces */
+    float* fws; size_t fws_floats;
+    int* iws; size_t iws_ints;
+} LasSpeller;
+size_t las_speller_workspace_floats(const LasSpeller* s);
+size_t las_speller_workspace_ints(const LasSpeller* s);
+int las_speller_fwd_f32(const LasSpeller* s, void* stream);
+
+typedef struct {
+    const float* dlogits;         /* (B, steps, V) contiguous */
+    /* gradient outputs (overwritten) */
+    float* d_emb; float* d_cls_b;
+    float* d_w_ih0; float* d_w_hh0; float* d_b_ih0; float* d_b_hh0;
+    float* d_w_ih1; float* d_w_hh1; float* d_b_ih1; float* d_b_hh1;
+    float* d_wq; float* d_bq; float* d_init_query;
+    float* dK; float* dV;         /* (B,T,P) */
+} LasSpellerGrads;
+int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g, void* stream);
+
+/* ---- fused unscale + global-norm clip + AdamW(amsgrad) ---------------------------------------------------------------
+ * Replaces scaler.unscale_ -> clip_grad_norm_ -> scaler.step(AdamW amsgrad) (src/train.py:165-183; torch
+ * optim/adam.py single-tensor math, nn/utils/clip_grad.py).  `table` is a device array of n_tensors LasAdamTensor;
+ * `chunks` a device array of n_chunks {tensor, offset} pairs, `scratch` >= n_chunks + 8 floats.
+ * Pass 1 computes sum((g*inv_scale)^2) and the non-finite flag; pass 2 applies coef = min(max_norm/(norm+1e-6), 1)
+ * and the update, or skips everything when a non-finite gradient was seen (GradScaler.step semantics).
+ * status (device, 2 floats): [0] = found_inf (0/1), [1] = total grad norm (unscaled). */
+typedef struct {
+    float* p; const float* g; float* m; float* v; float* vmax;
+    long long numel;
+    float bias_c1, bias_c2_sqrt;  /* 1-beta1^step, sqrt(1-beta2^step), computed by the host in double */
+} LasAdamTensor;
+typedef struct { int tensor; int pad_; long long offset; } LasAdamChunk;
+#define LAS_ADAM_CHUNK 65536
+int las_adamw_amsgrad_fused(const LasAdamTensor* table, int n_tensors, const LasAdamChunk* chunks, int n_chunks, float lr,
+                            float beta1, float beta2, float eps, float weight_decay, float inv_scale, float max_norm,
+                            int amsgrad, float* scratch, float* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAS_B200_H */

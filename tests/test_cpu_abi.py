@@ -1,0 +1,99 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/las_b200.h declares (no compute
+calls without a GPU), the module API / state_dict contract matches the reference, and the product path fails loudly
+without CUDA (no fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import gu, ROOT
+
+
+def test_library_exports_every_header_symbol():
+    from las_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'las_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(las_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    assert declared == set(_lib.SIGNATURES.keys()), declared ^ set(_lib.SIGNATURES.keys())
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.las_abi_version() == 1
+
+
+def test_no_gpu_fails_loudly():
+    from las_b200 import _lib
+    lib = _lib.load()
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    assert lib.las_init(0) != 0
+    assert b'no CPU fallback' in lib.las_last_error()
+
+
+@pytest.mark.parametrize('name', ['micro', 'tiny', 'best'])
+def test_state_dict_contract(name):
+    from las_b200.models import ListenAttendSpell
+    cfg = gu.get_config(name)
+    model = ListenAttendSpell(**gu.get_config(name))
+    sd = model.state_dict()
+    want = dict(gu.state_dict_shapes(cfg))
+    want['spell.cls.weight'] = want['spell.char_emb.weight']
+    assert set(sd.keys()) == set(want.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(want[k]), k
+    # named_parameters order == the optimizer's param order
+    assert [k for k, _ in model.named_parameters()] == [k for k, _ in gu.state_dict_shapes(cfg)]
+    assert model.spell.cls.weight is model.spell.char_emb.weight
+    # init_hiddens are NOT registered
+    assert not any('init_hiddens' in k for k in sd)
+    if name == 'best':
+        assert sum(p.numel() for p in model.parameters()) == 37734686
+    # a state_dict produced for the reference loads
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in gu.make_state_dict(cfg, 3).items()})
+
+
+def test_public_attributes_touched_by_callers():
+    from las_b200.models import ListenAttendSpell
+    m = ListenAttendSpell(**gu.get_config('micro'))
+    assert m.spell.dec_vocab_size == 30                                   # src/train.py:66
+    for attr in ('init_dropout', 'mid_dropout', 'final_dropout'):         # src/train.py:467-469
+        setattr(m.listen, attr, getattr(m.listen, attr) * 0.5)
+    for attr in ('att_dropout', 'dec_emb_dropout', 'dec_lstm_dropout'):   # src/train.py:470-472
+        setattr(m.spell, attr, getattr(m.spell, attr) * 0.5)
+    m.spell.attention.dropout *= 0.5                                      # src/train.py:474
+    assert m.speller_configs['enc_out_dim'] == 2 * m.listener_configs['uniform_hid_dim']   # src/models.py:512
+
+
+def test_constructor_constraints():
+    from las_b200.models import MultiheadCrossAttention, Speller
+    with pytest.raises(AssertionError):
+        MultiheadCrossAttention(proj_dim=10, heads=4)                     # src/models.py:87
+    with pytest.raises(ValueError):
+        Speller(att_proj_dim=16, dec_emb_dim=48, att_heads=1)
+
+
+def test_cpu_tensors_raise_no_fallback():
+    from las_b200.models import ListenAttendSpell
+    m = ListenAttendSpell(**gu.get_config('micro'))
+    x = torch.zeros(2, 16, 15)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        m(x, torch.tensor([16, 16]), torch.ones(2, 3, dtype=torch.long), 1.0)
+
+
+def test_length_contract_matches_pack_padded_sequence():
+    from las_b200.modules import LockedLSTM
+    m = LockedLSTM(15, 32)
+    x = torch.zeros(2, 16, 15)
+    with pytest.raises(RuntimeError, match='greater than 0'):
+        m(x, torch.tensor([16, 0]))
+
+
+def test_src_shim_is_drop_in():
+    import src.models as sm
+    import src.modules as smod
+    import las_b200
+    assert sm.ListenAttendSpell is las_b200.ListenAttendSpell
+    assert smod.pyramLockedLSTM is las_b200.pyramLockedLSTM
