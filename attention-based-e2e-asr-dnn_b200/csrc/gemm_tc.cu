@@ -1,0 +1,408 @@
+// bf16 tensor-core GEMM for the all-timestep LSTM gate projections: tcgen05.mma + TMEM accumulators, TMA-fed,
+// warp-specialised and persistent (one CTA per SM).  sm_100a only.
+//
+// Replaces the input half of nn.LSTM (X . W_ih^T for every timestep at once, reference src/modules.py:80,189) and its
+// two autograd GEMMs (dX = dG . W_ih, dW = dG^T . X).  The pyramidal frame-pair concat / odd-frame drop
+// (src/modules.py:171-185), the "T = max(lx)" truncation and the batch padding are folded into the TMA tensor maps:
+// every operand is described as a 3-D tensor (contiguous dim, row dim, batch dim) with arbitrary row / batch strides,
+// and out-of-range rows are zero-filled by the TMA unit, so no reshaped / packed copy of the activations ever exists.
+//
+// Tile: 128 (M) x 256 (N) x 64 (K) per stage, 4 stages of 48 KB, UMMA 128x256x16 (cta_group::1), fp32 accumulators
+// double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp 0 : TMA producer (one elected lane)        warp 1 : MMA issuer (one elected lane)
+//   warp 2 : TMEM allocator                          warps 4-7 : epilogue (tcgen05.ld -> +bias -> global)
+// Operand layouts (SWIZZLE_128B everywhere):
+//   K-major  operand tile rows x 64k : one TMA box {64, rows, 1}; UMMA desc SBO = 1024 B, K-advance = 32 B
+//   MN-major operand tile 64k x mn   : mn/64 TMA boxes {64, 64, 1} of 8 KB; UMMA desc LBO = 8 KB, SBO = 1024 B,
+//                                      K-advance = 2048 B
+#include "las_common.cuh"
+#include "las_b200.h"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;       // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NTHREADS = 256;
+constexpr int TMEM_COLS = 512;
+
+struct TcArgs {
+    float* C;
+    const float* bias1;
+    const float* bias2;
+    // output row mapping: tile row r of batch b -> C + b*c_bs + r*ldc ; rows >= R are skipped
+    long long c_bs, ldc;
+    int R;            // rows per batch (M direction) for K-major A; total M for MN-major A
+    int NB;           // batches in the M direction (1 for MN-major A)
+    int N;            // output columns
+    int mt_per_b;     // M tiles per batch
+    int nt;           // N tiles
+    int kt_per_b;     // K iterations per K-batch
+    int KB;           // batches in the K direction (wgrad: B of (b,t) rows; else 1)
+    int accumulate;   // C += result
+    const int* lens;  // optional (NB): skip M tiles whose first row >= lens[b] (rows past a sequence's length)
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start addr [0,14) >>4, LBO [16,30) >>4,
+// SBO [32,46) >>4, version [46,48) = 1, layout type [61,64) = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format BF16 [7,10)/[10,13)=1,
+// a_major bit 15, b_major bit 16, n_dim [17,23) = N>>3, m_dim [24,29) = M>>4
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte aligned stage bases
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int total_tiles = g.NB * g.mt_per_b * g.nt;
+    const int kiters = g.KB * g.kt_per_b;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int ntile = tile % g.nt, mrem = tile / g.nt;
+                const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b;
+                if (g.lens && mtile * BM >= g.lens[b]) continue;
+                for (int kit = 0; kit < kiters; ++kit) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                    mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+                    const int kb = kit / g.kt_per_b, kk = kit - kb * g.kt_per_b;
+                    if (!A_MN) {
+                        tma_load_3d(sa, &tmA, full_bar(stage), kk * BK, mtile * BM, b);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_3d(sa + j * 8192, &tmA, full_bar(stage), mtile * BM + j * 64, kk * BK, kb);
+                    }
+                    if (!B_MN) {
+                        tma_load_3d(sb, &tmB, full_bar(stage), kk * BK, ntile * BN, 0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_3d(sb + j * 8192, &tmB, full_bar(stage), ntile * BN + j * 64, kk * BK, kb);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t accphase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mrem = tile / g.nt;
+                const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b;
+                if (g.lens && mtile * BM >= g.lens[b]) continue;
+                mbar_wait(tempty_bar(acc), accphase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kit = 0; kit < kiters; ++kit) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ad = A_MN ? make_desc(sa + k * 2048, 8192, 1024) : make_desc(sa + k * 32, 16, 1024);
+                        const uint64_t bd = B_MN ? make_desc(sb + k * 2048, 8192, 1024) : make_desc(sb + k * 32, 16, 1024);
+                        umma_bf16(d_tmem, ad, bd, idesc, (kit | k) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));                // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; accphase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> (+bias, +C) -> global =====
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        int acc = 0; uint32_t accphase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int ntile = tile % g.nt, mrem = tile / g.nt;
+            const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b;
+            if (g.lens && mtile * BM >= g.lens[b]) continue;
+            mbar_wait(tfull_bar(acc), accphase);
+            tc_fence_after();
+            const int r = mtile * BM + q * 32 + lane;
+            const bool row_ok = r < g.R;
+            float* crow = g.C + (long long)b * g.c_bs + (long long)r * g.ldc;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
+                const int n0 = ntile * BN + c * 32;
+                if (row_ok && n0 < g.N) {
+                    if (n0 + 32 <= g.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                   __uint_as_float(v[j + 3]));
+                            if (g.bias1) { const float4 bb = *reinterpret_cast<const float4*>(g.bias1 + n0 + j); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+                            if (g.bias2) { const float4 bb = *reinterpret_cast<const float4*>(g.bias2 + n0 + j); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+                            float4* dst = reinterpret_cast<float4*>(crow + n0 + j);
+                            if (g.accumulate) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                            *dst = o;
+                        }
+                    } else {
+                        for (int j = 0; j < 32 && n0 + j < g.N; ++j) {
+                            float o = __uint_as_float(v[j]);
+                            if (g.bias1) o += g.bias1[n0 + j];
+                            if (g.bias2) o += g.bias2[n0 + j];
+                            if (g.accumulate) o += crow[n0 + j];
+                            crow[n0 + j] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; accphase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (EncodeTiledFn)p;
+    return fn;
+}
+
+// 3-D bf16 tensor: dim0 contiguous (d0 elements), dim1 rows (d1, stride s1 elements), dim2 batches (d2, stride s2 elements)
+int make_map(CUtensorMap* m, const void* ptr, long long d0, long long d1, long long d2, long long s1, long long s2, int box0, int box1) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { las_set_error("cuTensorMapEncodeTiled entry point not available"); return LAS_ERR_CUDA; }
+    LAS_CHECK_ARG(((uintptr_t)ptr & 15) == 0, "gemm_tc: operand pointer %p not 16-byte aligned", ptr);
+    LAS_CHECK_ARG((s1 * 2) % 16 == 0 && (d2 <= 1 || (s2 * 2) % 16 == 0), "gemm_tc: operand strides (%lld, %lld elements) must be multiples of 8",
+                  s1, s2);
+    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)(d2 < 1 ? 1 : d2)};
+    cuuint64_t strides[2] = {(cuuint64_t)s1 * 2, (cuuint64_t)((d2 <= 1 ? s1 * d1 : s2) * 2)};
+    cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        las_set_error("cuTensorMapEncodeTiled failed (%d) dims=(%lld,%lld,%lld) strides=(%lld,%lld) box=(%d,%d)", (int)r, d0, d1, d2, s1, s2,
+                      box0, box1);
+        return LAS_ERR_CUDA;
+    }
+    return LAS_OK;
+}
+
+template <bool A_MN, bool B_MN>
+int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, cudaStream_t st) {
+    auto kern = gemm_bf16_tc_kernel<A_MN, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    const int total = g.NB * g.mt_per_b * g.nt;
+    int grid = las_device_info()->num_sms;
+    if (grid > total) grid = total;
+    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, g);
+    LAS_LAUNCH_CHECK();
+    return LAS_OK;
+}
+
+}  // namespace
+
+extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
+    LAS_CHECK_ARG(d != nullptr && d->A && d->B && d->C, "gemm_tc: null descriptor / operand");
+    LAS_CHECK_ARG(d->M >= 1 && d->N >= 1 && d->K >= 1, "gemm_tc: bad dims M=%d N=%d K=%d", d->M, d->N, d->K);
+    LAS_CHECK_ARG(d->a_batches >= 1 && d->k_batches >= 1, "gemm_tc: bad batch counts");
+    LAS_CHECK_ARG(d->ldc % 4 == 0 && ((uintptr_t)d->C & 15) == 0 && d->c_bs % 4 == 0, "gemm_tc: C must be 16-byte aligned with ldc %% 4 == 0");
+    int rc = las_set_device_of(d->C);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap ta, tb;
+    TcArgs g{};
+    g.C = d->C; g.bias1 = d->bias1; g.bias2 = d->bias2; g.c_bs = d->c_bs; g.ldc = d->ldc;
+    g.N = d->N; g.nt = ceil_div(d->N, BN); g.accumulate = d->accumulate; g.lens = d->lens;
+    const double flops = 2.0 * d->M * (double)d->N * d->K * d->a_batches * d->k_batches;
+    LasProfScope prof(d->prof_tag == 1 ? LAS_PROF_GEMM_GATES : LAS_PROF_GEMM_OTHER, stream, flops);
+    if (!d->a_mn_major) {
+        // A: (K contiguous, M rows [stride a_s1], a_batches [stride a_s2]); reduction is a single K range
+        LAS_CHECK_ARG(d->k_batches == 1, "gemm_tc: K-major A cannot have K batches");
+        rc = make_map(&ta, d->A, d->K, d->M, d->a_batches, d->a_s1, d->a_s2, BK, BM);
+        if (rc) return rc;
+        g.R = d->M; g.NB = d->a_batches; g.mt_per_b = ceil_div(d->M, BM); g.kt_per_b = ceil_div(d->K, BK); g.KB = 1;
+        if (!d->b_mn_major) {
+            rc = make_map(&tb, d->B, d->K, d->N, 1, d->b_s1, 0, BK, BN);           // B: (K contiguous, N rows)
+            if (rc) return rc;
+            return launch_tc<false, false>(ta, tb, g, st);
+        }
+        rc = make_map(&tb, d->B, d->N, d->K, 1, d->b_s1, 0, 64, 64);               // B: (N contiguous, K rows)
+        if (rc) return rc;
+        return launch_tc<false, true>(ta, tb, g, st);
+    }
+    // A: (M contiguous, K rows [stride a_s1], k_batches [stride a_s2]); B: (N contiguous, K rows [b_s1], k_batches [b_s2])
+    LAS_CHECK_ARG(d->b_mn_major && d->a_batches == 1, "gemm_tc: MN-major A needs MN-major B and a single M batch");
+    rc = make_map(&ta, d->A, d->M, d->K, d->k_batches, d->a_s1, d->a_s2, 64, 64);
+    if (rc) return rc;
+    rc = make_map(&tb, d->B, d->N, d->K, d->k_batches, d->b_s1, d->b_s2, 64, 64);
+    if (rc) return rc;
+    g.R = d->M; g.NB = 1; g.mt_per_b = ceil_div(d->M, BM); g.kt_per_b = ceil_div(d->K, BK); g.KB = d->k_batches;
+    g.lens = nullptr;
+    return launch_tc<true, true>(ta, tb, g, st);
+}
+
+// ---- fp32 -> bf16 cast with optional column padding: dst[r][c] = c < cols ? src[r*ld_src + c] : 0 ---------------------
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, long long ld_src, long long inner, long long bs,
+                                                        __nv_bfloat16* __restrict__ dst, long long ld_dst, long long rows, int cols,
+                                                        int cols_pad) {
+    const long long total = rows * (long long)(cols_pad / 2);
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long r = i / (cols_pad / 2);
+        const int c = (int)(i - r * (cols_pad / 2)) * 2;
+        const float* srow = src + (inner > 0 ? (r / inner) * bs + (r % inner) * ld_src : r * ld_src);
+        const float a = c < cols ? srow[c] : 0.f;
+        const float b = c + 1 < cols ? srow[c + 1] : 0.f;
+        *reinterpret_cast<__nv_bfloat162*>(dst + r * ld_dst + c) = __floats2bfloat162_rn(a, b);
+    }
+}
+
+extern "C" int las_cast_f32_to_bf16(const float* src, long long ld_src, long long inner, long long bs, void* dst, long long ld_dst,
+                                    long long rows, int cols, int cols_pad, void* stream) {
+    LAS_CHECK_ARG(src && dst && rows >= 0 && cols >= 1 && cols_pad >= cols && cols_pad % 2 == 0 && ld_dst % 2 == 0,
+                  "cast_bf16: bad arguments");
+    if (rows == 0) return LAS_OK;
+    int rc = las_set_device_of(dst);
+    if (rc) return rc;
+    long long total = rows * (long long)(cols_pad / 2);
+    int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    cast_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, inner, bs, (__nv_bfloat16*)dst, ld_dst, rows, cols, cols_pad);
+    LAS_LAUNCH_CHECK();
+    return LAS_OK;
+}

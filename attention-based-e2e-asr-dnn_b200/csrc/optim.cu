@@ -40,9 +40,9 @@ __global__ void __launch_bounds__(NT) adam_pass1_kernel(const LasAdamTensor* __r
 }
 
 __global__ void __launch_bounds__(NT) adam_pass2_kernel(const LasAdamTensor* __restrict__ table, const LasAdamChunk* __restrict__ chunks,
-                                                        int n_chunks, float lr, float beta1, float beta2, float eps, float wd,
-                                                        float inv_scale, float max_norm, int amsgrad, const float* __restrict__ partial,
-                                                        float* __restrict__ status) {
+                                                        int n_chunks, float one_minus_b1, float beta2, float one_minus_b2, float eps,
+                                                        float decay, float inv_scale, float max_norm, int amsgrad,
+                                                        const float* __restrict__ partial, float* __restrict__ status) {
     // every block re-reduces the per-chunk partial sums in the same order: deterministic, no extra launch
     __shared__ float red[NT / 32];
     __shared__ float s_coef;
@@ -70,14 +70,13 @@ __global__ void __launch_bounds__(NT) adam_pass2_kernel(const LasAdamTensor* __r
     float* m = tn.m + ck.offset;
     float* v = tn.v + ck.offset;
     float* vm = tn.vmax ? tn.vmax + ck.offset : nullptr;
-    const float decay = 1.f - lr * wd;
-    const float step_size = lr / tn.bias_c1;
+    const float step_size = tn.step_size;
     for (long long i = threadIdx.x; i < n; i += NT) {
         const float gi = g[i] * gmul;
         float pi = p[i] * decay;
         float mi = m[i];
-        mi = mi + (gi - mi) * (1.f - beta1);
-        float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;
+        mi = mi + (gi - mi) * one_minus_b1;
+        float vi = v[i] * beta2 + one_minus_b2 * (gi * gi);
         float dv = vi;
         if (amsgrad) {
             dv = fmaxf(vm[i], vi);
@@ -90,8 +89,8 @@ __global__ void __launch_bounds__(NT) adam_pass2_kernel(const LasAdamTensor* __r
 }
 }  // namespace
 
-extern "C" int las_adamw_amsgrad_fused(const LasAdamTensor* table, int n_tensors, const LasAdamChunk* chunks, int n_chunks, float lr,
-                                       float beta1, float beta2, float eps, float weight_decay, float inv_scale, float max_norm,
+extern "C" int las_adamw_amsgrad_fused(const LasAdamTensor* table, int n_tensors, const LasAdamChunk* chunks, int n_chunks, double lr,
+                                       double beta1_d, double beta2_d, float eps, double weight_decay, float inv_scale, float max_norm,
                                        int amsgrad, float* scratch, float* status, void* stream) {
     LAS_CHECK_ARG(table && chunks && scratch && status && n_tensors >= 1 && n_chunks >= 1, "adamw: bad arguments");
     int rc = las_set_device_of(table);
@@ -101,8 +100,11 @@ extern "C" int las_adamw_amsgrad_fused(const LasAdamTensor* table, int n_tensors
     LAS_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(float), st));
     adam_pass1_kernel<<<n_chunks, NT, 0, st>>>(table, chunks, inv_scale, scratch, status);
     LAS_LAUNCH_CHECK();
-    adam_pass2_kernel<<<n_chunks, NT, 0, st>>>(table, chunks, n_chunks, lr, beta1, beta2, eps, weight_decay, inv_scale, max_norm, amsgrad,
-                                               scratch, status);
+    // scalar constants are formed in double on the host and rounded once, like torch's Python-float arithmetic
+    const float one_minus_b1 = (float)(1.0 - (double)beta1_d), one_minus_b2 = (float)(1.0 - (double)beta2_d);
+    const float decay = (float)(1.0 - (double)lr * (double)weight_decay);
+    adam_pass2_kernel<<<n_chunks, NT, 0, st>>>(table, chunks, n_chunks, one_minus_b1, (float)beta2_d, one_minus_b2, eps, decay, inv_scale,
+                                               max_norm, amsgrad, scratch, status);
     LAS_LAUNCH_CHECK();
     return LAS_OK;
 }

@@ -30,6 +30,19 @@ class LasGemmF32(C.Structure):
     ]
 
 
+class LasGemmTc(C.Structure):
+    _fields_ = [
+        ('A', C.c_void_p), ('B', C.c_void_p), ('C', C.c_void_p), ('bias1', C.c_void_p), ('bias2', C.c_void_p),
+        ('M', C.c_int), ('N', C.c_int), ('K', C.c_int),
+        ('a_batches', C.c_int), ('k_batches', C.c_int),
+        ('a_s1', c_ll), ('a_s2', c_ll), ('b_s1', c_ll), ('b_s2', c_ll),
+        ('c_bs', c_ll), ('ldc', c_ll),
+        ('a_mn_major', C.c_int), ('b_mn_major', C.c_int), ('accumulate', C.c_int),
+        ('lens', C.c_void_p),
+        ('prof_tag', C.c_int),
+    ]
+
+
 class LasAttnStep(C.Structure):
     _fields_ = [
         ('q', C.c_void_p), ('ld_q', c_ll),
@@ -76,7 +89,7 @@ class LasSpellerGrads(C.Structure):
 
 class LasAdamTensor(C.Structure):
     _fields_ = [('p', C.c_void_p), ('g', C.c_void_p), ('m', C.c_void_p), ('v', C.c_void_p), ('vmax', C.c_void_p),
-                ('numel', c_ll), ('bias_c1', C.c_float), ('bias_c2_sqrt', C.c_float)]
+                ('numel', c_ll), ('step_size', C.c_float), ('bias_c2_sqrt', C.c_float)]
 
 
 class LasAdamChunk(C.Structure):
@@ -96,6 +109,8 @@ SIGNATURES = {
     'las_prof_reset': (None, []),
     'las_prof_collect': (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(c_ll), C.POINTER(C.c_double)]),
     'las_gemm_f32': (C.c_int, [C.POINTER(LasGemmF32), C.c_void_p]),
+    'las_gemm_bf16_tc': (C.c_int, [C.POINTER(LasGemmTc), C.c_void_p]),
+    'las_cast_f32_to_bf16': (C.c_int, [C.c_void_p, c_ll, c_ll, c_ll, C.c_void_p, c_ll, c_ll, C.c_int, C.c_int, C.c_void_p]),
     'las_colsum_scratch_floats': (C.c_size_t, [C.c_int]),
     'las_colsum_f32': (C.c_int, [C.c_void_p, c_ll, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'las_lstm_rec_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
@@ -109,8 +124,8 @@ SIGNATURES = {
     'las_speller_workspace_ints': (C.c_size_t, [C.POINTER(LasSpeller)]),
     'las_speller_fwd_f32': (C.c_int, [C.POINTER(LasSpeller), C.c_void_p]),
     'las_speller_bwd_f32': (C.c_int, [C.POINTER(LasSpeller), C.POINTER(LasSpellerGrads), C.c_void_p]),
-    'las_adamw_amsgrad_fused': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_void_p,
-                                                                                                    C.c_void_p, C.c_void_p]),
+    'las_adamw_amsgrad_fused': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_float,
+                                          C.c_double, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -12,7 +12,8 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import LasAttnStep, LasGemmF32, LasSpeller, LasSpellerGrads, check, ptr, stream_ptr
+from ._lib import LasAttnStep, LasGemmF32, LasGemmTc, LasSpeller, LasSpellerGrads, check, ptr, stream_ptr
+from .precision import use_tensor_cores
 
 
 def _require_cuda(*tensors):
@@ -48,6 +49,35 @@ def gemm_raw(A, B, Cout, M, N, K, *, am=(0, 0, 0), ak=(0, 1, 0), bk=(0, 1, 0), b
     d.alpha, d.beta = float(alpha), float(beta)
     d.prof_tag = 1 if gate else 0
     check(_lib.load().las_gemm_f32(C.byref(d), stream_ptr()), 'gemm_f32')
+
+
+def gemm_tc(A, B, Cout, M, N, K, *, a_batches=1, k_batches=1, a_s1, a_s2=0, b_s1, b_s2=0, c_bs=0, ldc, a_mn=False, b_mn=False,
+            bias1=None, bias2=None, accumulate=False, lens=None, a_off=0, b_off=0, c_off=0, gate=True):
+    """las_gemm_bf16_tc wrapper; A/B are bf16 tensors, Cout fp32; *_off are element offsets."""
+    d = LasGemmTc()
+    d.A = A.data_ptr() + 2 * a_off
+    d.B = B.data_ptr() + 2 * b_off
+    d.C = Cout.data_ptr() + 4 * c_off
+    d.bias1, d.bias2 = ptr(bias1), ptr(bias2)
+    d.M, d.N, d.K = int(M), int(N), int(K)
+    d.a_batches, d.k_batches = int(a_batches), int(k_batches)
+    d.a_s1, d.a_s2, d.b_s1, d.b_s2 = int(a_s1), int(a_s2), int(b_s1), int(b_s2)
+    d.c_bs, d.ldc = int(c_bs), int(ldc)
+    d.a_mn_major, d.b_mn_major, d.accumulate = int(a_mn), int(b_mn), int(accumulate)
+    d.lens = ptr(lens)
+    d.prof_tag = 1 if gate else 0
+    check(_lib.load().las_gemm_bf16_tc(C.byref(d), stream_ptr()), 'gemm_bf16_tc')
+
+
+def cast_bf16(src: torch.Tensor, rows: int, cols: int, cols_pad: int, ld_src: int, *, inner: int = 0, bs: int = 0,
+              dst: Optional[torch.Tensor] = None, dst_off: int = 0) -> torch.Tensor:
+    """fp32 rows x cols -> bf16 rows x cols_pad (zero padded columns).  Source row r lives at
+    (r // inner) * bs + (r % inner) * ld_src (inner == 0: r * ld_src).  Writes into `dst` (+dst_off elements) or a new tensor."""
+    if dst is None:
+        dst = torch.empty(rows, cols_pad, dtype=torch.bfloat16, device=src.device)
+    check(_lib.load().las_cast_f32_to_bf16(src.data_ptr(), int(ld_src), int(inner), int(bs), dst.data_ptr() + 2 * dst_off, int(cols_pad),
+                                           int(rows), int(cols), int(cols_pad), stream_ptr()), 'cast_f32_to_bf16')
+    return dst
 
 
 def colsum(X: torch.Tensor, ld: int, M: int, N: int, out: torch.Tensor, x_off: int = 0, accumulate: bool = False):
@@ -158,13 +188,33 @@ class LSTMLayerFunction(torch.autograd.Function):
         H = ws[1].shape[1]
         F_ = ndir * H
         G4 = 4 * H
+        NG = ndir * G4
         dev = x.device
+        # tensor-pipe mode: bf16 tcgen05 GEMMs for the gate projections (pyramid layers need D % 8 == 0 so that the
+        # frame-pair concat stays a pure TMA stride; the 15-dim base layer is zero-padded to K = 64)
+        tc = use_tensor_cores() and (D % 8 == 0 if pyramid else True)
         gates = torch.empty(Bn, T, ndir, G4, dtype=torch.float32, device=dev)
-        for d in range(ndir):
-            w_ih, _, b_ih, b_hh = ws[4 * d:4 * d + 4]
-            assert w_ih.shape == (G4, Din), (w_ih.shape, G4, Din)
-            gemm_raw(x, w_ih, gates, Bn * T, G4, Din, am=(sb, st_eff, T), ak=(0, 1, 0), bk=(0, 1, 0), bn=Din,
-                     cm=(0, ndir * G4, 0), bias1=b_ih, bias2=b_hh, c_off=d * G4, gate=True)
+        xb = wcat = None
+        Dp = Kp = 0
+        if tc:
+            Dp = D if D % 8 == 0 and D >= 64 else ((D + 63) // 64) * 64
+            if pyramid:
+                Dp = D
+            Kp = 2 * Dp if pyramid else Dp
+            xb = cast_bf16(x, Bn * Tin, D, Dp, st, inner=Tin, bs=sb)                      # (B*Tin, Dp) bf16, compact
+            wcat = torch.empty(NG, Kp, dtype=torch.bfloat16, device=dev)
+            for d in range(ndir):
+                cast_bf16(ws[4 * d], G4, Din, Kp, Din, dst=wcat, dst_off=d * G4 * Kp)
+            b1 = torch.cat([ws[4 * d + 2] for d in range(ndir)])
+            b2 = torch.cat([ws[4 * d + 3] for d in range(ndir)])
+            gemm_tc(xb, wcat, gates, T, NG, Kp, a_batches=Bn, a_s1=(2 * Dp if pyramid else Dp), a_s2=Tin * Dp, b_s1=Kp,
+                    c_bs=T * NG, ldc=NG, bias1=b1, bias2=b2, lens=lens_dev)
+        else:
+            for d in range(ndir):
+                w_ih, _, b_ih, b_hh = ws[4 * d:4 * d + 4]
+                assert w_ih.shape == (G4, Din), (w_ih.shape, G4, Din)
+                gemm_raw(x, w_ih, gates, Bn * T, G4, Din, am=(sb, st_eff, T), ak=(0, 1, 0), bk=(0, 1, 0), bn=Din,
+                         cm=(0, NG, 0), bias1=b_ih, bias2=b_hh, c_off=d * G4, gate=True)
         w_hh = torch.stack([ws[4 * d + 1] for d in range(ndir)], 0).contiguous()
         hs_pad = torch.empty(Bn, T + 2, F_, dtype=torch.float32, device=dev)
         cs_pad = torch.empty(Bn, T + 2, F_, dtype=torch.float32, device=dev)
@@ -176,8 +226,11 @@ class LSTMLayerFunction(torch.autograd.Function):
         check(lib.las_lstm_rec_fwd_f32(gates.data_ptr(), w_hh.data_ptr(), lens_dev.data_ptr(), ptr(mask), ptr(out),
                                        hs_pad.data_ptr(), cs_pad.data_ptr(), Bn, T, H, ndir, wsb.data_ptr(), nbytes,
                                        stream_ptr()), 'lstm_rec_fwd')
-        ctx.save_for_backward(x, lens_dev, gates, hs_pad, cs_pad, w_hh, mask, *ws)
-        ctx.dims = (Bn, Tin, D, T, H, ndir, Din, sb, st_eff, bool(pyramid))
+        if tc:
+            ctx.save_for_backward(xb, lens_dev, gates, hs_pad, cs_pad, w_hh, mask, wcat)
+        else:
+            ctx.save_for_backward(x, lens_dev, gates, hs_pad, cs_pad, w_hh, mask, *ws)
+        ctx.dims = (Bn, Tin, D, T, H, ndir, Din, sb, st_eff, bool(pyramid), tc, Dp, Kp)
         y = out if out is not None else hs_pad[:, 1:T + 1]
         return y
 
@@ -185,8 +238,9 @@ class LSTMLayerFunction(torch.autograd.Function):
     def backward(ctx, dy):
         lib = _lib.load()
         x, lens_dev, gates, hs_pad, cs_pad, w_hh, mask, *ws = ctx.saved_tensors
-        Bn, Tin, D, T, H, ndir, Din, sb, st_eff, pyramid = ctx.dims
+        Bn, Tin, D, T, H, ndir, Din, sb, st_eff, pyramid, tc, Dp, Kp = ctx.dims
         F_, G4 = ndir * H, 4 * H
+        NG = ndir * G4
         dev = x.device
         dy = _f32c(dy)
         nbytes = lib.las_lstm_rec_workspace_bytes(Bn, H, ndir)
@@ -198,23 +252,44 @@ class LSTMLayerFunction(torch.autograd.Function):
         dG = gates
         M = Bn * T
         dx = None
+        grads: List[Optional[torch.Tensor]] = []
+        if tc:
+            xb, wcat = x, ws[0]
+            dGb = cast_bf16(dG, M, NG, NG, NG)                                            # (B*T, NG) bf16
+            if ctx.needs_input_grad[0]:
+                dx = torch.zeros(Bn, Tin, D, dtype=torch.float32, device=dev)             # tiles past a row's length are skipped
+                gemm_tc(dGb, wcat, dx, T, Din, NG, a_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=Kp, b_mn=True, c_bs=Tin * D,
+                        ldc=Din, lens=lens_dev)
+            dwcat = torch.empty(NG, Kp, dtype=torch.float32, device=dev)
+            gemm_tc(dGb, xb, dwcat, NG, Kp, T, k_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=(2 * Dp if pyramid else Dp),
+                    b_s2=Tin * Dp, ldc=Kp, a_mn=True, b_mn=True)
+            hsb = cast_bf16(hs_pad, Bn * (T + 2), F_, F_, F_)                             # (B*(T+2), F) bf16
+            for d in range(ndir):
+                dw_ih = dwcat[d * G4:(d + 1) * G4, :Din].contiguous()
+                dw_hh = torch.empty(G4, H, dtype=torch.float32, device=dev)
+                # h_{t-1} for the forward direction is frame t of hs_pad, for the reverse direction frame t+2
+                gemm_tc(dGb, hsb, dw_hh, G4, H, T, k_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=F_, b_s2=(T + 2) * F_, ldc=H,
+                        a_mn=True, b_mn=True, a_off=d * G4, b_off=(2 * F_ if d == 1 else 0) + d * H)
+                db = torch.empty(G4, dtype=torch.float32, device=dev)
+                colsum(dG, NG, M, G4, db, x_off=d * G4)
+                grads += [dw_ih, dw_hh, db, db.clone()]
+            return (dx, None, None, None, None, *grads)
         if ctx.needs_input_grad[0]:
             full = (Tin * D == T * Din)
             dx = (torch.empty if full else torch.zeros)(Bn, Tin, D, dtype=torch.float32, device=dev)
             for d in range(ndir):
-                gemm_raw(dG, ws[4 * d], dx, M, Din, G4, am=(0, ndir * G4, 0), ak=(0, 1, 0), bk=(0, Din, 0), bn=1,
+                gemm_raw(dG, ws[4 * d], dx, M, Din, G4, am=(0, NG, 0), ak=(0, 1, 0), bk=(0, Din, 0), bn=1,
                          cm=(Tin * D, Din, T), beta=0.0 if d == 0 else 1.0, a_off=d * G4, gate=True)
-        grads: List[Optional[torch.Tensor]] = []
         for d in range(ndir):
             dw_ih = torch.empty(G4, Din, dtype=torch.float32, device=dev)
-            gemm_raw(dG, x, dw_ih, G4, Din, M, am=(0, 1, 0), ak=(0, ndir * G4, 0), bk=(sb, st_eff, T), bn=1, cm=(0, Din, 0),
+            gemm_raw(dG, x, dw_ih, G4, Din, M, am=(0, 1, 0), ak=(0, NG, 0), bk=(sb, st_eff, T), bn=1, cm=(0, Din, 0),
                      a_off=d * G4, gate=True)
             dw_hh = torch.empty(G4, H, dtype=torch.float32, device=dev)
             # h_{t-1} for the forward direction is frame t of hs_pad, for the reverse direction frame t+2
-            gemm_raw(dG, hs_pad, dw_hh, G4, H, M, am=(0, 1, 0), ak=(0, ndir * G4, 0), bk=((T + 2) * F_, F_, T), bn=1,
+            gemm_raw(dG, hs_pad, dw_hh, G4, H, M, am=(0, 1, 0), ak=(0, NG, 0), bk=((T + 2) * F_, F_, T), bn=1,
                      cm=(0, H, 0), a_off=d * G4, b_off=(2 * F_ if d == 1 else 0) + d * H)
             db = torch.empty(G4, dtype=torch.float32, device=dev)
-            colsum(dG, ndir * G4, M, G4, db, x_off=d * G4)
+            colsum(dG, NG, M, G4, db, x_off=d * G4)
             grads += [dw_ih, dw_hh, db, db.clone()]
         return (dx, None, None, None, None, *grads)
 

@@ -68,7 +68,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 t.p, t.g, t.m, t.v = p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr()
                 t.vmax = st['max_exp_avg_sq'].data_ptr()
                 t.numel = p.numel()
-                t.bias_c1 = 1.0 - beta1 ** step
+                t.step_size = group['lr'] / (1.0 - beta1 ** step)
                 t.bias_c2_sqrt = math.sqrt(1.0 - beta2 ** step)
                 for off in range(0, p.numel(), ADAM_CHUNK):
                     chunks.append((i, off))

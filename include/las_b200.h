@@ -69,6 +69,35 @@ typedef struct {
 } LasGemmF32;
 int las_gemm_f32(const LasGemmF32* desc, void* stream);
 
+/* ---- bf16 tensor-core GEMM (tcgen05.mma + TMEM + TMA), fp32 accumulate / fp32 output ---------------------------------
+ * The tensor-pipe path of the LSTM input-gate projections (same reference call sites as las_gemm_f32's gate uses:
+ * src/modules.py:80,189 forward; autograd dX / dW_ih / dW_hh in backward).  Operands are bf16; each is a 3-D tensor
+ * (contiguous dim, rows with stride s1, batches with stride s2) handed to TMA, so the pyramid reshape-concat, odd-frame
+ * drop and padding of src/modules.py:171-185 are tensor-map geometry, not copies.
+ *   a_mn_major = 0 (forward / dgrad):  A[b][r][k] = A + b*a_s2 + r*a_s1 + k , r < M rows per batch, a_batches batches
+ *        b_mn_major = 0: B[n][k] = B + n*b_s1 + k      (C = A . B^T, weights as stored)
+ *        b_mn_major = 1: B[k][n] = B + k*b_s1 + n      (C = A . B,   weights as stored, dgrad)
+ *        C row (b, r) at C + b*c_bs + r*ldc ; `lens` (a_batches, nullable) skips 128-row tiles starting at r >= lens[b]
+ *   a_mn_major = 1 (weight gradient):  A[kb][k][m] = A + kb*a_s2 + k*a_s1 + m, B[kb][k][n] = B + kb*b_s2 + k*b_s1 + n,
+ *        K rows per K-batch, k_batches batches;  C[m][n] = sum_{kb,k} A*B at C + m*ldc + n
+ * bias1/bias2 (length N, nullable) are added in the epilogue; accumulate != 0 adds into C. */
+typedef struct {
+    const void* A; const void* B; float* C;
+    const float* bias1; const float* bias2;
+    int M, N, K;
+    int a_batches, k_batches;
+    long long a_s1, a_s2, b_s1, b_s2;
+    long long c_bs, ldc;
+    int a_mn_major, b_mn_major, accumulate;
+    const int* lens;
+    int prof_tag;
+} LasGemmTc;
+int las_gemm_bf16_tc(const LasGemmTc* desc, void* stream);
+/* dst[r][c] (bf16, row stride ld_dst) = c < cols ? srcrow(r)[c] : 0, c < cols_pad; source row r starts at
+ * (r / inner)*bs + (r % inner)*ld_src when inner > 0 (a (B,T,F) view with a batch stride), else at r*ld_src */
+int las_cast_f32_to_bf16(const float* src, long long ld_src, long long inner, long long bs, void* dst, long long ld_dst,
+                         long long rows, int cols, int cols_pad, void* stream);
+
 /* column sums: out[n] (+)= sum_m X[m*ld + n], m < M, n < N.  Bias gradients (autograd of the bias adds in nn.LSTM /
  * nn.LSTMCell / nn.Linear). `scratch` needs las_colsum_scratch_floats(N) floats. */
 size_t las_colsum_scratch_floats(int N);
@@ -180,12 +209,12 @@ int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g, void* str
 typedef struct {
     float* p; const float* g; float* m; float* v; float* vmax;
     long long numel;
-    float bias_c1, bias_c2_sqrt;  /* 1-beta1^step, sqrt(1-beta2^step), computed by the host in double */
+    float step_size, bias_c2_sqrt;  /* lr/(1-beta1^step), sqrt(1-beta2^step): computed by the host in double */
 } LasAdamTensor;
 typedef struct { int tensor; int pad_; long long offset; } LasAdamChunk;
 #define LAS_ADAM_CHUNK 65536
-int las_adamw_amsgrad_fused(const LasAdamTensor* table, int n_tensors, const LasAdamChunk* chunks, int n_chunks, float lr,
-                            float beta1, float beta2, float eps, float weight_decay, float inv_scale, float max_norm,
+int las_adamw_amsgrad_fused(const LasAdamTensor* table, int n_tensors, const LasAdamChunk* chunks, int n_chunks, double lr,
+                            double beta1, double beta2, float eps, double weight_decay, float inv_scale, float max_norm,
                             int amsgrad, float* scratch, float* status, void* stream);
 
 #ifdef __cplusplus

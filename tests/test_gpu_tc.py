@@ -1,0 +1,135 @@
+"""GPU tests of the tcgen05 bf16 tensor-core GEMM (las_gemm_bf16_tc) and of the bf16 ("AMP") mode of the model.
+Reference for the GEMM: torch fp32/fp64 matmul of the SAME bf16-rounded operands (so only accumulation order differs);
+tolerance 2e-3 relative to the output scale.  For the model: north_star's AMP bar, logits within 2e-3 absolute of the fp32
+reference."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import gu, orc, load_golden, fixture_cfg, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _rand_bf16(shape, seed):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return torch.randn(*shape, generator=g).to(torch.bfloat16).to(DEV)
+
+
+@pytest.mark.parametrize('B,R,K,N', [(1, 128, 64, 256), (1, 300, 192, 512), (3, 200, 128, 1024), (2, 77, 64, 100), (4, 129, 2048, 4096)])
+def test_tc_gemm_forward_form(B, R, K, N):
+    """C[b,r,:] = A[b,r,:] . W^T + bias1 + bias2 with A a strided (batch, row) view -- the forward gate projection."""
+    from las_b200 import functional as LF
+    Rpad = R + 3                                            # batch stride != R * row stride (padded batch)
+    A = _rand_bf16((B, Rpad, K), 1)
+    W = _rand_bf16((N, K), 2)
+    b1 = torch.randn(N, device=DEV)
+    b2 = torch.randn(N, device=DEV)
+    C = torch.full((B, R, N), float('nan'), device=DEV)
+    LF.gemm_tc(A, W, C, R, N, K, a_batches=B, a_s1=K, a_s2=Rpad * K, b_s1=K, c_bs=R * N, ldc=N, bias1=b1, bias2=b2)
+    ref = A[:, :R].float().double() @ W.float().double().t() + (b1 + b2).double()
+    assert torch.isfinite(C).all()
+    assert rel_err(C.cpu().numpy(), ref.cpu().numpy()) < 2e-3
+
+
+def test_tc_gemm_pyramid_concat_is_tma_geometry():
+    """(B,T,D) -> drop odd frame -> (B,T//2,2D) as tensor-map strides (reference src/modules.py:171-185)."""
+    from las_b200 import functional as LF
+    B, T, D, N = 3, 271, 64, 256
+    x = _rand_bf16((B, T, D), 3)
+    W = _rand_bf16((N, 2 * D), 4)
+    Tp = T // 2
+    C = torch.empty(B, Tp, N, device=DEV)
+    LF.gemm_tc(x, W, C, Tp, N, 2 * D, a_batches=B, a_s1=2 * D, a_s2=T * D, b_s1=2 * D, c_bs=Tp * N, ldc=N)
+    ref = x[:, :2 * Tp].reshape(B, Tp, 2 * D).float() @ W.float().t()
+    assert rel_err(C.cpu().numpy(), ref.cpu().numpy()) < 2e-3
+
+
+def test_tc_gemm_length_tile_skip():
+    from las_b200 import functional as LF
+    B, R, K, N = 3, 400, 64, 256
+    A = _rand_bf16((B, R, K), 5)
+    W = _rand_bf16((N, K), 6)
+    lens = torch.tensor([400, 130, 10], dtype=torch.int32, device=DEV)
+    C = torch.zeros(B, R, N, device=DEV)
+    LF.gemm_tc(A, W, C, R, N, K, a_batches=B, a_s1=K, a_s2=R * K, b_s1=K, c_bs=R * N, ldc=N, lens=lens)
+    ref = A.float() @ W.float().t()
+    for b, l in enumerate([400, 130, 10]):
+        assert rel_err(C[b, :l].cpu().numpy(), ref[b, :l].cpu().numpy()) < 2e-3
+    assert float(C[2, 128:].abs().max()) == 0.0           # tiles wholly past the length were never touched
+
+
+@pytest.mark.parametrize('B,R,K,N', [(1, 128, 256, 256), (2, 130, 512, 64), (3, 64, 4096, 2048)])
+def test_tc_gemm_dgrad_form(B, R, K, N):
+    """dX[b,r,:] = dG[b,r,:] . W  with W (K, N) row-major as stored (MN-major B operand)."""
+    from las_b200 import functional as LF
+    dG = _rand_bf16((B, R, K), 7)
+    W = _rand_bf16((K, N), 8)
+    C = torch.empty(B, R, N, device=DEV)
+    LF.gemm_tc(dG, W, C, R, N, K, a_batches=B, a_s1=K, a_s2=R * K, b_s1=N, b_mn=True, c_bs=R * N, ldc=N)
+    ref = dG.float().double() @ W.float().double()
+    assert rel_err(C.cpu().numpy(), ref.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.parametrize('B,T,M,N', [(1, 64, 128, 256), (3, 100, 256, 192), (2, 333, 4096, 2048), (5, 7, 128, 64)])
+def test_tc_gemm_wgrad_form(B, T, M, N):
+    """dW[m,n] = sum_{b,t} dG[b,t,m] X[b,t,n]: both operands MN-major, reduction over (batch, row) with OOB zero fill."""
+    from las_b200 import functional as LF
+    Tpad = T + 2
+    dG = _rand_bf16((B, T, M), 9)
+    X = _rand_bf16((B, Tpad, N), 10)
+    C = torch.empty(M, N, device=DEV)
+    # X is read with a +1 frame shift inside a padded batch, like the shifted h_{t-1} operand of dW_hh
+    LF.gemm_tc(dG, X, C, M, N, T, k_batches=B, a_s1=M, a_s2=T * M, b_s1=N, b_s2=Tpad * N, ldc=N, a_mn=True, b_mn=True, b_off=N)
+    ref = torch.einsum('btm,btn->mn', dG.float().double(), X[:, 1:T + 1].float().double())
+    assert rel_err(C.cpu().numpy(), ref.cpu().numpy()) < 2e-3
+
+
+def test_bf16_mode_lstm_layer_close_to_fp32_oracle():
+    from las_b200 import functional as LF
+    from las_b200.precision import set_precision
+    rng = np.random.default_rng(5)
+    H, D, B, T = 128, 64, 4, 50
+    lens = [25, 20, 7, 25]
+    x = torch.from_numpy(rng.standard_normal((B, T, D)).astype(np.float32))
+    k = 1 / np.sqrt(H)
+    names = ['weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0']
+    shapes = [(4 * H, 2 * D), (4 * H, H), (4 * H,), (4 * H,)]
+    p = {'l.' + n + suf: torch.from_numpy(rng.uniform(-k, k, size=s).astype(np.float32)) for suf in ['', '_reverse'] for n, s in zip(names, shapes)}
+    po = {k_: v.clone().requires_grad_(True) for k_, v in p.items()}
+    xo = x.clone().requires_grad_(True)
+    yo = orc.bilstm_layer(xo.reshape(B, T // 2, 2 * D), lens, po, 'l.')
+    wout = torch.from_numpy(rng.standard_normal(tuple(yo.shape)).astype(np.float32))
+    (yo * wout).sum().backward()
+    set_precision('bf16')
+    try:
+        pc = {k_: v.clone().to(DEV).requires_grad_(True) for k_, v in p.items()}
+        xc = x.clone().to(DEV).requires_grad_(True)
+        ws = [pc['l.' + n + suf] for suf in ['', '_reverse'] for n in names]
+        yc = LF.lstm_layer(xc, torch.tensor(lens, dtype=torch.int32, device=DEV), max(lens), True, None, ws)
+        (yc * wout.to(DEV)).sum().backward()
+    finally:
+        set_precision('auto')
+    assert np.abs(yc.detach().cpu().numpy() - yo.detach().numpy()).max() < 2e-2
+    assert rel_err(xc.grad.cpu().numpy(), xo.grad.numpy()) < 3e-2
+    for k_ in p:
+        assert rel_err(pc[k_].grad.cpu().numpy(), po[k_].grad.numpy()) < 3e-2, k_
+
+
+@pytest.mark.parametrize('name', ['micro_train_tf1', 'tiny_train_tf1'])
+def test_bf16_mode_logits_within_amp_tolerance(name):
+    """north_star: AMP/bf16 logits within 2e-3 absolute of the reference."""
+    from las_b200.models import ListenAttendSpell
+    g = load_golden(name)
+    cfg = fixture_cfg(g)
+    sd = gu.make_state_dict(cfg, int(g['seed']))
+    model = ListenAttendSpell(**cfg).to(DEV)
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    model.train()
+    y = torch.from_numpy(g['y']).to(DEV)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        logits, _ = model(torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['lx']), y, 1.0, False)
+    err = np.abs(logits.detach().float().cpu().numpy() - g['logits']).max()
+    print(f'{name}: bf16-mode max abs logit error vs fp32 reference = {err:.3e}')
+    assert err < 2e-3
