@@ -1,0 +1,676 @@
+// Persistent LSTM recurrence on the tensor pipe (bf16 operands, fp32 accumulate / state), forward + BPTT.  sm_100a only.
+//
+// Same contract as lstm_rec_f32.cu (replaces the time loop of nn.LSTM over a PackedSequence, reference
+// src/modules.py:78-82 / :187-191), different engine:
+//   * CTA (r, s, dir) owns 32 hidden units (= 128 gate rows: 4 gates x 32 units) of direction `dir` for batch slice(s)
+//     of 32 rows.  Its 128 x H slice of W_hh is loaded ONCE by TMA into shared memory (SWIZZLE_128B, K-major) and stays
+//     resident for the whole sequence as the A operand of tcgen05.mma (M = 128 gate rows, N = 32 batch rows, K = H).
+//   * per timestep: wait for the group's h_{t-1} (release/acquire counter), TMA-load the 32 x H bf16 slice of h_{t-1} as
+//     the B operand, issue H/16 UMMAs into a TMEM accumulator, then the 4 epilogue warps (one per gate) read the
+//     accumulator (tcgen05.ld), add the precomputed input projection, apply sigmoid / tanh, exchange the four gates
+//     through shared memory, do the cell update with c_t held in registers, write h_t (bf16, for the next step's TMA),
+//     the saved tensors and the (locked-dropout-masked) layer output, and publish the step.
+//   * only the RS = H/32 CTAs that share (direction, batch slice) synchronise with one another -- the recurrence is
+//     independent across batch rows -- so the barrier is 16-wide at H = 512, not grid-wide.
+//   * a CTA may own several batch slices ("chains"): they are independent dependency chains, so while one chain waits
+//     for its peers the tensor pipe and the epilogue work on the other.
+#include "las_common.cuh"
+#include "las_b200.h"
+#include <cuda.h>
+
+namespace {
+
+constexpr int NB_SLICE = 32;          // batch rows per chain (UMMA N)
+constexpr int UNITS = 32;             // hidden units per CTA
+constexpr int ROWS = 4 * UNITS;       // gate rows per CTA (UMMA M)
+constexpr int MAX_CHAINS = 2;
+constexpr int NTHREADS = 256;
+
+struct RecTcArgs {
+    float* gates;          // (B, T, ndir, 4H) in: x-gates ; out: activated gates (when save_gates)
+    const int* lens;
+    const float* mask;     // (B, ndir*H) or null
+    float* out;            // (B, T, ndir*H) or null
+    float* hs_pad;         // (B, T+2, ndir*H) fp32
+    float* cs_pad;         // (B, T+2, ndir*H) fp32
+    __nv_bfloat16* hbuf;   // (ndir, 2, Bpad, H) bf16 exchange buffer
+    unsigned* ctr;         // (ndir, nslices) step counters
+    int B, T, H, ndir, nslices, Bpad, chains, bsg, save;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {     // K-major, SWIZZLE_128B: LBO 16 B, SBO 1024 B
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// AMP-mode activations: one MUFU each (tanh.approx.f32, |err| ~ 2^-11, below bf16 operand rounding)
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// idesc: F32 accumulate, BF16 x BF16, both K-major, M = 128, N = 32
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB_SLICE >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+
+__global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW,
+                                                                     const __grid_constant__ CUtensorMap tmH, const RecTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const int H = a.H, T = a.T, KB = H / 64;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w_sm = base;                                   // KB x [128 rows x 128 B]
+    const uint32_t h_sm = w_sm + KB * 16384;                      // chains x KB x [32 rows x 128 B]
+    const uint32_t ex_off = (h_sm - smem_u32(smem_raw)) + a.chains * KB * 4096;
+    float* ex = reinterpret_cast<float*>(smem_raw + ex_off);      // [4][32][32] gate exchange
+    const uint32_t bar_base = smem_u32(smem_raw) + ex_off + 4 * 32 * 32 * 4;
+    auto full_bar = [&](int c) { return bar_base + 8u * c; };
+    auto tfull_bar = [&](int c) { return bar_base + 8u * (MAX_CHAINS + c); };
+    const uint32_t wbar = bar_base + 8u * (2 * MAX_CHAINS);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_CHAINS + 1);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int r = blockIdx.x, sg = blockIdx.y, dir = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int F = a.ndir * H;
+    const long long brow = (long long)(T + 2) * F;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmH) : "memory");
+        for (int c = 0; c < MAX_CHAINS; ++c) { mbar_init(full_bar(c), 1); mbar_init(tfull_bar(c), 1); }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== producer: resident W_hh slice once, then h_{t-1} slices per step =====
+            mbar_arrive_expect_tx(wbar, (uint32_t)KB * 16384u);
+            for (int kb = 0; kb < KB; ++kb)
+                for (int g = 0; g < 4; ++g)
+                    tma_load_2d(w_sm + kb * 16384 + g * 4096, &tmW, wbar, kb * 64, dir * 4 * H + g * H + r * UNITS);
+            for (int s = 1; s < T; ++s) {
+                for (int c = 0; c < a.chains; ++c) {
+                    const int slice = sg + c * a.bsg;
+                    if (slice >= a.nslices) continue;
+                    const unsigned* ctr = a.ctr + dir * a.nslices + slice;
+                    const unsigned target = (unsigned)(H / UNITS) * (unsigned)s;
+                    while (ld_acquire_gpu(ctr) < target) { }
+                    asm volatile("fence.proxy.async;" ::: "memory");       // peers' generic-proxy writes -> our TMA reads
+                    mbar_arrive_expect_tx(full_bar(c), (uint32_t)KB * 4096u);
+                    const int row0 = (dir * 2 + ((s - 1) & 1)) * a.Bpad + slice * NB_SLICE;
+                    for (int kb = 0; kb < KB; ++kb) tma_load_2d(h_sm + (c * KB + kb) * 4096, &tmH, full_bar(c), kb * 64, row0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            mbar_wait(wbar, 0);
+            for (int s = 1; s < T; ++s) {
+                for (int c = 0; c < a.chains; ++c) {
+                    const int slice = sg + c * a.bsg;
+                    if (slice >= a.nslices) continue;
+                    mbar_wait(full_bar(c), (uint32_t)((s - 1) & 1));
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + c * NB_SLICE;
+                    for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = make_desc_k(w_sm + kb * 16384 + k * 32);
+                            const uint64_t bd = make_desc_k(h_sm + (c * KB + kb) * 4096 + k * 32);
+                            umma_bf16(d_tmem, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(tfull_bar(c));
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: one warp per gate =====
+        const int q = warp & 3, j = lane;          // gate q, unit r*32 + j
+        const int te = (warp - 4) * 32 + lane;     // 0..127
+        const int u = r * UNITS + j;
+        float cst[MAX_CHAINS][8];
+#pragma unroll
+        for (int c = 0; c < MAX_CHAINS; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cst[c][i] = 0.f;
+        // zero the pad frames (0 and T+1) of this CTA's (rows, units): the shifted h_{t-1} / c_{t-1} reads of backward
+        for (int c = 0; c < a.chains; ++c) {
+            const int slice = sg + c * a.bsg;
+            if (slice >= a.nslices) continue;
+            for (int i = 0; i < 8; ++i) {
+                const int b = slice * NB_SLICE + q * 8 + i;
+                if (b < a.B) {
+                    const long long o0 = (long long)b * brow + dir * H + u, o1 = o0 + (long long)(T + 1) * F;
+                    a.hs_pad[o0] = 0.f; a.cs_pad[o0] = 0.f; a.hs_pad[o1] = 0.f; a.cs_pad[o1] = 0.f;
+                }
+            }
+        }
+        for (int s = 0; s < T; ++s) {
+            const int t = (dir == 0) ? s : (T - 1 - s);
+            for (int c = 0; c < a.chains; ++c) {
+                const int slice = sg + c * a.bsg;
+                if (slice >= a.nslices) continue;
+                const int b0 = slice * NB_SLICE;
+                // input projection for (gate q, unit j) of the 32 batch rows: coalesced 128 B per row, issued before the wait
+                float xg[32];
+                float* gbase = a.gates + ((long long)t * a.ndir + dir) * 4 * H + q * H + u;
+                const long long gstride = (long long)T * a.ndir * 4 * H;
+#pragma unroll
+                for (int n = 0; n < 32; ++n) xg[n] = (b0 + n < a.B) ? gbase[(long long)(b0 + n) * gstride] : 0.f;
+                uint32_t v[32];
+                if (s > 0) {
+                    mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
+                    tc_fence_after();
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * NB_SLICE, v);
+                } else {
+#pragma unroll
+                    for (int n = 0; n < 32; ++n) v[n] = 0u;
+                }
+#pragma unroll
+                for (int n = 0; n < 32; ++n) {
+                    const float pre = __uint_as_float(v[n]) + xg[n];
+                    const float act = (q == 2) ? tanh_fast(pre) : sigmoid_fast(pre);
+                    ex[(q * 32 + n) * 32 + j] = act;
+                    xg[n] = act;                                   // kept for the deferred save below
+                }
+                tc_fence_before();
+                named_bar_sync(1, 128);
+                // cell update: thread (q, j) owns unit j for batch rows n = q*8 + i
+                float hh[8], cc[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int n = q * 8 + i, b = b0 + n;
+                    const float gi = ex[(0 * 32 + n) * 32 + j], gf = ex[(1 * 32 + n) * 32 + j];
+                    const float gg = ex[(2 * 32 + n) * 32 + j], go = ex[(3 * 32 + n) * 32 + j];
+                    const bool valid = (b < a.B) && (t < a.lens[b]);
+                    cc[i] = 0.f; hh[i] = 0.f;
+                    if (valid) {
+                        cc[i] = fmaf(gf, cst[c][i], gi * gg);
+                        hh[i] = go * tanh_fast(cc[i]);
+                    }
+                    cst[c][i] = cc[i];
+                    // the only data peers wait for: h_t as bf16
+                    a.hbuf[((long long)(dir * 2 + (s & 1)) * a.Bpad + b) * H + u] = __float2bfloat16(hh[i]);
+                }
+                // publish step s of this chain FIRST (the release only has the 8 bf16 stores per thread in front of it) ...
+                named_bar_sync(1, 128);
+                if (te == 0 && s + 1 < T) red_release_gpu_add(a.ctr + dir * a.nslices + slice, 1u);
+                // ... then write what only backward / the next layer read; these stores overlap the wait for the next step
+                if (a.save) {
+#pragma unroll
+                    for (int n = 0; n < 32; ++n)
+                        if (b0 + n < a.B) gbase[(long long)(b0 + n) * gstride] = xg[n];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + q * 8 + i;
+                    if (b < a.B) {
+                        const long long so = (long long)b * brow + (long long)(t + 1) * F + dir * H + u;
+                        a.hs_pad[so] = hh[i];
+                        a.cs_pad[so] = cc[i];
+                        if (a.out) {
+                            const float m = a.mask ? a.mask[(long long)b * F + dir * H + u] : 1.f;
+                            a.out[((long long)b * T + t) * F + dir * H + u] = hh[i] * m;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode2() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (EncodeTiledFn)p;
+    return fn;
+}
+int make_map_2d(CUtensorMap* m, const void* ptr, long long cols, long long rows, int box_cols, int box_rows) {
+    EncodeTiledFn enc = get_encode2();
+    if (!enc) { las_set_error("cuTensorMapEncodeTiled entry point not available"); return LAS_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { las_set_error("cuTensorMapEncodeTiled (2d) failed (%d)", (int)rc); return LAS_ERR_CUDA; }
+    return LAS_OK;
+}
+
+struct Plan { int rs, nslices, bsg, chains, Bpad; size_t smem; };
+int make_plan(int B, int H, int ndir, Plan* p) {
+    LAS_CHECK_ARG(H % 64 == 0 && H >= 64, "lstm_rec_tc: hidden size %d must be a multiple of 64", H);
+    const LasDeviceInfo* di = las_device_info();
+    p->rs = H / UNITS;
+    p->nslices = ceil_div(B, NB_SLICE);
+    int max_bsg = di->num_sms / (p->rs * ndir);
+    LAS_CHECK_ARG(max_bsg >= 1, "lstm_rec_tc: H=%d needs more co-resident CTAs than SMs", H);
+    p->bsg = p->nslices < max_bsg ? p->nslices : max_bsg;
+    p->chains = ceil_div(p->nslices, p->bsg);
+    LAS_CHECK_ARG(p->chains <= MAX_CHAINS, "lstm_rec_tc: batch %d needs %d chains per CTA (max %d) at H=%d", B, p->chains, MAX_CHAINS, H);
+    p->Bpad = p->nslices * NB_SLICE;
+    const int KB = H / 64;
+    p->smem = 1024 + (size_t)KB * 16384 + (size_t)p->chains * KB * 4096 + 4 * 32 * 32 * 4 + 8 * (2 * MAX_CHAINS + 2) + 64;
+    LAS_CHECK_ARG(p->smem <= (size_t)di->max_smem_optin, "lstm_rec_tc: needs %zu B of shared memory", p->smem);
+    return LAS_OK;
+}
+
+}  // namespace
+
+extern "C" int las_lstm_rec_tc_supported(int B, int H, int ndir) {
+    Plan p;
+    if (B < 1 || (ndir != 1 && ndir != 2)) return 0;
+    if (H % 64 != 0 || H < 64) return 0;
+    const LasDeviceInfo* di = las_device_info();
+    int rs = H / UNITS, nsl = ceil_div(B, NB_SLICE);
+    int max_bsg = di->num_sms / (rs * ndir);
+    if (max_bsg < 1) return 0;
+    int bsg = nsl < max_bsg ? nsl : max_bsg;
+    if (ceil_div(nsl, bsg) > MAX_CHAINS) return 0;
+    (void)p;
+    return 1;
+}
+
+extern "C" size_t las_lstm_rec_tc_workspace_bytes(int B, int H, int ndir) {
+    const int nsl = ceil_div(B, NB_SLICE);
+    // counters (1 KB) + bf16 h exchange buffer (ndir, 2, Bpad, H)
+    return 1024 + (size_t)ndir * 2 * nsl * NB_SLICE * H * 2;
+}
+
+extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const int* lens, const float* drop_mask, float* out,
+                                   float* hs_pad, float* cs_pad, int B, int T, int H, int ndir, int save_gates, void* ws, size_t ws_bytes,
+                                   void* stream) {
+    LAS_CHECK_ARG(gates && w_hh_bf16 && lens && hs_pad && cs_pad && ws, "lstm_rec_fwd_tc: null pointer");
+    LAS_CHECK_ARG(B >= 1 && T >= 1 && (ndir == 1 || ndir == 2), "lstm_rec_fwd_tc: bad dims");
+    int rc = las_set_device_of(gates);
+    if (rc) return rc;
+    Plan p;
+    rc = make_plan(B, H, ndir, &p);
+    if (rc) return rc;
+    if (ws_bytes < las_lstm_rec_tc_workspace_bytes(B, H, ndir)) { las_set_error("lstm_rec_fwd_tc: workspace too small"); return LAS_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    RecTcArgs a{};
+    a.gates = gates; a.lens = lens; a.mask = drop_mask; a.out = out; a.hs_pad = hs_pad; a.cs_pad = cs_pad;
+    a.ctr = (unsigned*)ws; a.hbuf = (__nv_bfloat16*)((char*)ws + 1024);
+    a.B = B; a.T = T; a.H = H; a.ndir = ndir; a.nslices = p.nslices; a.Bpad = p.Bpad; a.chains = p.chains; a.bsg = p.bsg; a.save = save_gates;
+    LAS_CHECK_ARG((size_t)ndir * p.nslices * sizeof(unsigned) <= 1024, "lstm_rec_fwd_tc: too many batch slices");
+    CUtensorMap tmW, tmH;
+    rc = make_map_2d(&tmW, w_hh_bf16, H, (long long)ndir * 4 * H, 64, 32);
+    if (rc) return rc;
+    rc = make_map_2d(&tmH, a.hbuf, H, (long long)ndir * 2 * p.Bpad, 64, 32);
+    if (rc) return rc;
+    LAS_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    LAS_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
+    LasProfScope prof(LAS_PROF_REC_FWD, stream, (double)T);
+    void* args[] = {(void*)&tmW, (void*)&tmH, (void*)&a};
+    LAS_CUDA(cudaLaunchCooperativeKernel((void*)lstm_rec_fwd_tc_kernel, dim3(p.rs, p.bsg, ndir), dim3(NTHREADS), args, p.smem, st));
+    las_count_launch(1);
+    return LAS_OK;
+}
+
+// =====================================================================================================================
+// BPTT on the tensor pipe.
+//   dh_rec[b, u] = sum_r dG_{next}[b, r] * W_hh[r, u]   (r over all 4H gate rows)   -- the serial dependency of backward.
+// CTA (r, s, dir) owns the same 32 units / batch slice as in forward.  Resident in shared memory: the 32 x 4H slice of
+// W_hh^T (bf16, K-major) as the B operand (N = 32 units).  Per step the 32 x 4H bf16 slice of the previous step's
+// d(pre-activation) arrives by TMA straight from the (B*T, ndir*4H) bf16 dG array -- which is also exactly what the
+// dX / dW_ih / dW_hh tensor-core GEMMs consume afterwards -- in 4 chunks through a 2-stage ring, as the A operand.
+// UMMA M = 64 with 32 real batch rows: descriptors of rows 32-63 run into the next k-block's bytes; those accumulator
+// lanes are never read.  The pointwise LSTM backward (gate derivatives, dc carry in registers) is fused in the epilogue.
+// =====================================================================================================================
+namespace {
+
+struct RecTcBwdArgs {
+    float* gates;            // (B, T, ndir, 4H) in: activated gates ; out: d(pre-activation), fp32
+    __nv_bfloat16* dgb;      // (B*T, ndir*4H) bf16 copy of the same (TMA source + GEMM operand)
+    const float* dout;       // (B, T, ndir*H)
+    const float* cs_pad;     // (B, T+2, ndir*H)
+    const int* lens;
+    const float* mask;
+    unsigned* ctr;
+    int B, T, H, ndir, nslices, chains, bsg, KBr, CH;
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+constexpr uint32_t IDESC_BWD = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UNITS >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+constexpr int BWD_STAGES = 2;
+
+__global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWt,
+                                                                     const __grid_constant__ CUtensorMap tmG, const RecTcBwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const int H = a.H, T = a.T, KBr = a.KBr, CH = a.CH, NCHUNK = KBr / CH;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_sm = base;                                        // KBr x [32 rows(u) x 128 B]   resident W_hh^T slice
+    const uint32_t a_sm = b_sm + KBr * 4096;                           // BWD_STAGES x CH x [32 rows(b) x 128 B] (+4 KB slack)
+    const uint32_t ex_off = (a_sm - smem_u32(smem_raw)) + BWD_STAGES * CH * 4096 + 4096;
+    float* exD = reinterpret_cast<float*>(smem_raw + ex_off);          // [32][33]
+    const uint32_t bar_base = smem_u32(smem_raw) + ex_off + 32 * 33 * 4 + 8;
+    const uint32_t bar_al = (bar_base + 7u) & ~7u;
+    auto full_bar = [&](int s) { return bar_al + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_al + 8u * (BWD_STAGES + s); };
+    auto tfull_bar = [&](int c) { return bar_al + 8u * (2 * BWD_STAGES + c); };
+    const uint32_t wbar = bar_al + 8u * (2 * BWD_STAGES + MAX_CHAINS);
+    const uint32_t tmem_slot = bar_al + 8u * (2 * BWD_STAGES + MAX_CHAINS + 1);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int r = blockIdx.x, sg = blockIdx.y, dir = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int F = a.ndir * H, G4 = 4 * H, NG = a.ndir * G4;
+    const long long brow = (long long)(T + 2) * F;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWt) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
+        for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int c = 0; c < MAX_CHAINS; ++c) mbar_init(tfull_bar(c), 1);
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(wbar, (uint32_t)KBr * 4096u);
+            for (int kb = 0; kb < KBr; ++kb) tma_load_2d(b_sm + kb * 4096, &tmWt, wbar, kb * 64, dir * H + r * UNITS);
+            int stage = 0; uint32_t phase = 0;
+            for (int s = 1; s < T; ++s) {
+                const int t_prev = (dir == 0) ? (T - s) : (s - 1);        // time index processed at step s-1
+                for (int c = 0; c < a.chains; ++c) {
+                    const int slice = sg + c * a.bsg;
+                    if (slice >= a.nslices) continue;
+                    const unsigned* ctr = a.ctr + dir * a.nslices + slice;
+                    const unsigned target = (unsigned)(H / UNITS) * (unsigned)s;
+                    while (ld_acquire_gpu(ctr) < target) { }
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    for (int ch = 0; ch < NCHUNK; ++ch) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)CH * 4096u);
+                        for (int kl = 0; kl < CH; ++kl)
+                            tma_load_3d(a_sm + (stage * CH + kl) * 4096, &tmG, full_bar(stage), dir * G4 + (ch * CH + kl) * 64, t_prev,
+                                        slice * NB_SLICE);
+                        if (++stage == BWD_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(wbar, 0);
+            int stage = 0; uint32_t phase = 0;
+            for (int s = 1; s < T; ++s) {
+                for (int c = 0; c < a.chains; ++c) {
+                    const int slice = sg + c * a.bsg;
+                    if (slice >= a.nslices) continue;
+                    const uint32_t d_tmem = tmem_base + c * UNITS;
+                    for (int ch = 0; ch < NCHUNK; ++ch) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        for (int kl = 0; kl < CH; ++kl) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t ad = make_desc_k(a_sm + (stage * CH + kl) * 4096 + k * 32);
+                                const uint64_t bd = make_desc_k(b_sm + (ch * CH + kl) * 4096 + k * 32);
+                                umma_bf16(d_tmem, ad, bd, IDESC_BWD, (ch | kl | k) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(empty_bar(stage));
+                        if (++stage == BWD_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit(tfull_bar(c));
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3, j = lane;
+        const int te = (warp - 4) * 32 + lane;
+        const int u = r * UNITS + j;
+        float dcst[MAX_CHAINS][8];
+#pragma unroll
+        for (int c = 0; c < MAX_CHAINS; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dcst[c][i] = 0.f;
+        for (int s = 0; s < T; ++s) {
+            const int t = (dir == 0) ? (T - 1 - s) : s;
+            const int fprev = (dir == 0) ? t : t + 2, fcur = t + 1;
+            for (int c = 0; c < a.chains; ++c) {
+                const int slice = sg + c * a.bsg;
+                if (slice >= a.nslices) continue;
+                const int b0 = slice * NB_SLICE;
+                // operands of the pointwise backward, issued before waiting on the tensor pipe
+                float gi[8], gf[8], gg[8], go[8], ct[8], cp[8], dh[8];
+                bool valid[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + q * 8 + i;
+                    valid[i] = (b < a.B) && (t < a.lens[b]);
+                    if (valid[i]) {
+                        const float* gp = a.gates + (((long long)b * T + t) * a.ndir + dir) * G4 + u;
+                        gi[i] = gp[0]; gf[i] = gp[H]; gg[i] = gp[2 * H]; go[i] = gp[3 * H];
+                        ct[i] = a.cs_pad[(long long)b * brow + (long long)fcur * F + dir * H + u];
+                        cp[i] = a.cs_pad[(long long)b * brow + (long long)fprev * F + dir * H + u];
+                        const float m = a.mask ? a.mask[(long long)b * F + dir * H + u] : 1.f;
+                        dh[i] = a.dout[((long long)b * T + t) * F + dir * H + u] * m;
+                    } else {
+                        gi[i] = gf[i] = gg[i] = go[i] = ct[i] = cp[i] = dh[i] = 0.f;
+                    }
+                }
+                if (s > 0) {
+                    mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
+                    tc_fence_after();
+                    if (q < 2) {
+                        // UMMA M = 64: accumulator rows 0-15 sit in TMEM lanes 0-15, rows 16-31 in lanes 32-47
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * UNITS, v);
+                        if (lane < 16) {
+#pragma unroll
+                            for (int n = 0; n < 32; ++n) exD[(q * 16 + lane) * 33 + n] = __uint_as_float(v[n]);
+                        }
+                    }
+                    tc_fence_before();
+                    named_bar_sync(1, 128);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dh[i] += exD[(q * 8 + i) * 33 + j];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + q * 8 + i;
+                    if (b >= a.B) continue;
+                    float dai = 0.f, daf = 0.f, dag = 0.f, dao = 0.f, dcn = 0.f;
+                    if (valid[i]) {
+                        const float tcv = tanh_fast(ct[i]);
+                        const float dct = fmaf(dh[i] * go[i], 1.f - tcv * tcv, dcst[c][i]);
+                        dai = dct * gg[i] * gi[i] * (1.f - gi[i]);
+                        daf = dct * cp[i] * gf[i] * (1.f - gf[i]);
+                        dag = dct * gi[i] * (1.f - gg[i] * gg[i]);
+                        dao = dh[i] * tcv * go[i] * (1.f - go[i]);
+                        dcn = dct * gf[i];
+                    }
+                    dcst[c][i] = dcn;
+                    const long long row = (long long)b * T + t;
+                    // peers (and the GEMMs afterwards) read the bf16 copy; it is what the publish below releases
+                    __nv_bfloat16* bp = a.dgb + row * NG + dir * G4 + u;
+                    bp[0] = __float2bfloat16(dai); bp[H] = __float2bfloat16(daf);
+                    bp[2 * H] = __float2bfloat16(dag); bp[3 * H] = __float2bfloat16(dao);
+                    gi[i] = dai; gf[i] = daf; gg[i] = dag; go[i] = dao;
+                }
+                named_bar_sync(1, 128);
+                if (te == 0 && s + 1 < T) red_release_gpu_add(a.ctr + dir * a.nslices + slice, 1u);
+                // fp32 d(pre-activation) (bias-gradient column sums read it) after the publish
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + q * 8 + i;
+                    if (b >= a.B) continue;
+                    float* gp = a.gates + ((((long long)b * T + t) * a.ndir + dir) * G4) + u;
+                    gp[0] = gi[i]; gp[H] = gf[i]; gp[2 * H] = gg[i]; gp[3 * H] = go[i];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+    }
+}
+
+int make_map_3d(CUtensorMap* m, const void* ptr, long long d0, long long d1, long long d2, long long s1, long long s2, int b0, int b1, int b2) {
+    EncodeTiledFn enc = get_encode2();
+    if (!enc) { las_set_error("cuTensorMapEncodeTiled entry point not available"); return LAS_ERR_CUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t strides[2] = {(cuuint64_t)s1 * 2, (cuuint64_t)s2 * 2};
+    cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { las_set_error("cuTensorMapEncodeTiled (3d) failed (%d)", (int)rc); return LAS_ERR_CUDA; }
+    return LAS_OK;
+}
+
+// dst[b][c][r] (bf16) = src[b][r][c] (fp32): W_hh (ndir, 4H, H) -> W_hh^T (ndir, H, 4H)
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* s = src + (long long)b * rows * cols;
+    __nv_bfloat16* d = dst + (long long)b * rows * cols;
+    for (int i = ty; i < 32; i += 8) tile[i][tx] = (r0 + i < rows && c0 + tx < cols) ? s[(long long)(r0 + i) * cols + c0 + tx] : 0.f;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < cols && r0 + tx < rows) d[(long long)(c0 + i) * rows + r0 + tx] = __float2bfloat16(tile[tx][i]);
+}
+
+}  // namespace
+
+extern "C" int las_transpose_cast_bf16(const float* src, void* dst, int batch, int rows, int cols, void* stream) {
+    LAS_CHECK_ARG(src && dst && batch >= 1 && rows >= 1 && cols >= 1, "transpose_cast: bad arguments");
+    int rc = las_set_device_of(dst);
+    if (rc) return rc;
+    transpose_cast_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32), batch), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, rows, cols);
+    LAS_LAUNCH_CHECK();
+    return LAS_OK;
+}
+
+extern "C" int las_lstm_rec_bwd_tc(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16,
+                                   const int* lens, const float* drop_mask, int B, int T, int H, int ndir, void* ws, size_t ws_bytes,
+                                   void* stream) {
+    LAS_CHECK_ARG(dout && gates && dgates_bf16 && cs_pad && w_hh_t_bf16 && lens && ws, "lstm_rec_bwd_tc: null pointer");
+    LAS_CHECK_ARG(B >= 1 && T >= 1 && (ndir == 1 || ndir == 2), "lstm_rec_bwd_tc: bad dims");
+    int rc = las_set_device_of(gates);
+    if (rc) return rc;
+    Plan p;
+    rc = make_plan(B, H, ndir, &p);
+    if (rc) return rc;
+    if (ws_bytes < 1024) { las_set_error("lstm_rec_bwd_tc: workspace too small"); return LAS_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    RecTcBwdArgs a{};
+    a.gates = gates; a.dgb = (__nv_bfloat16*)dgates_bf16; a.dout = dout; a.cs_pad = cs_pad; a.lens = lens; a.mask = drop_mask;
+    a.ctr = (unsigned*)ws;
+    a.B = B; a.T = T; a.H = H; a.ndir = ndir; a.nslices = p.nslices; a.chains = p.chains; a.bsg = p.bsg;
+    a.KBr = 4 * H / 64; a.CH = a.KBr < 8 ? a.KBr : 8;
+    const size_t smem = 1024 + (size_t)a.KBr * 4096 + (size_t)BWD_STAGES * a.CH * 4096 + 4096 + 32 * 33 * 4 + 16 +
+                        8 * (2 * BWD_STAGES + MAX_CHAINS + 2) + 64;
+    LAS_CHECK_ARG(smem <= (size_t)las_device_info()->max_smem_optin, "lstm_rec_bwd_tc: needs %zu B of shared memory", smem);
+    const long long NG = (long long)ndir * 4 * H;
+    CUtensorMap tmWt, tmG;
+    rc = make_map_2d(&tmWt, w_hh_t_bf16, 4LL * H, (long long)ndir * H, 64, 32);
+    if (rc) return rc;
+    rc = make_map_3d(&tmG, dgates_bf16, NG, T, B, NG, (long long)T * NG, 64, 1, 32);
+    if (rc) return rc;
+    LAS_CUDA(cudaFuncSetAttribute(lstm_rec_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAS_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
+    LasProfScope prof(LAS_PROF_REC_BWD, stream, (double)T);
+    void* args[] = {(void*)&tmWt, (void*)&tmG, (void*)&a};
+    LAS_CUDA(cudaLaunchCooperativeKernel((void*)lstm_rec_bwd_tc_kernel, dim3(p.rs, p.bsg, ndir), dim3(NTHREADS), args, smem, st));
+    las_count_launch(1);
+    return LAS_OK;
+}

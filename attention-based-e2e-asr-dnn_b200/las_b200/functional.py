@@ -7,6 +7,7 @@ tensor or a missing library raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -221,11 +222,21 @@ class LSTMLayerFunction(torch.autograd.Function):
         out = torch.empty(Bn, T, F_, dtype=torch.float32, device=dev) if mask is not None else None
         if mask is not None:
             mask = _f32c(mask).reshape(Bn, F_)
-        nbytes = lib.las_lstm_rec_workspace_bytes(Bn, H, ndir)
-        wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        check(lib.las_lstm_rec_fwd_f32(gates.data_ptr(), w_hh.data_ptr(), lens_dev.data_ptr(), ptr(mask), ptr(out),
-                                       hs_pad.data_ptr(), cs_pad.data_ptr(), Bn, T, H, ndir, wsb.data_ptr(), nbytes,
-                                       stream_ptr()), 'lstm_rec_fwd')
+        rec_tc = tc and os.environ.get('LAS_REC_TC', '1') == '1' and bool(lib.las_lstm_rec_tc_supported(Bn, H, ndir))
+        if rec_tc:
+            # tensor-pipe recurrence: W_hh as bf16 (ndir*4H, H), resident in shared memory inside the kernel
+            w_hh_b = cast_bf16(w_hh, ndir * G4, H, H, H)
+            nbytes = lib.las_lstm_rec_tc_workspace_bytes(Bn, H, ndir)
+            wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            check(lib.las_lstm_rec_fwd_tc(gates.data_ptr(), w_hh_b.data_ptr(), lens_dev.data_ptr(), ptr(mask), ptr(out),
+                                          hs_pad.data_ptr(), cs_pad.data_ptr(), Bn, T, H, ndir, 1, wsb.data_ptr(), nbytes,
+                                          stream_ptr()), 'lstm_rec_fwd_tc')
+        else:
+            nbytes = lib.las_lstm_rec_workspace_bytes(Bn, H, ndir)
+            wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            check(lib.las_lstm_rec_fwd_f32(gates.data_ptr(), w_hh.data_ptr(), lens_dev.data_ptr(), ptr(mask), ptr(out),
+                                           hs_pad.data_ptr(), cs_pad.data_ptr(), Bn, T, H, ndir, wsb.data_ptr(), nbytes,
+                                           stream_ptr()), 'lstm_rec_fwd')
         if tc:
             ctx.save_for_backward(xb, lens_dev, gates, hs_pad, cs_pad, w_hh, mask, wcat)
         else:
@@ -247,15 +258,26 @@ class LSTMLayerFunction(torch.autograd.Function):
         wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         # gates (activated) -> d(pre-activation), in place.  The forward's saved tensor is consumed: a second
         # backward through the same graph is not supported (like cuDNN's reserve space, it is single use).
-        check(lib.las_lstm_rec_bwd_f32(dy.data_ptr(), gates.data_ptr(), cs_pad.data_ptr(), w_hh.data_ptr(), lens_dev.data_ptr(),
-                                       ptr(mask), Bn, T, H, ndir, wsb.data_ptr(), nbytes, stream_ptr()), 'lstm_rec_bwd')
-        dG = gates
         M = Bn * T
+        dGb = None
+        rec_tc = tc and os.environ.get('LAS_REC_TC', '1') == '1' and bool(lib.las_lstm_rec_tc_supported(Bn, H, ndir))
+        if rec_tc:
+            w_hh_t = torch.empty(ndir, H, G4, dtype=torch.bfloat16, device=dev)
+            check(lib.las_transpose_cast_bf16(w_hh.data_ptr(), w_hh_t.data_ptr(), ndir, G4, H, stream_ptr()), 'transpose_cast')
+            dGb = torch.empty(M, NG, dtype=torch.bfloat16, device=dev)
+            check(lib.las_lstm_rec_bwd_tc(dy.data_ptr(), gates.data_ptr(), dGb.data_ptr(), cs_pad.data_ptr(), w_hh_t.data_ptr(),
+                                          lens_dev.data_ptr(), ptr(mask), Bn, T, H, ndir, wsb.data_ptr(), nbytes, stream_ptr()),
+                  'lstm_rec_bwd_tc')
+        else:
+            check(lib.las_lstm_rec_bwd_f32(dy.data_ptr(), gates.data_ptr(), cs_pad.data_ptr(), w_hh.data_ptr(), lens_dev.data_ptr(),
+                                           ptr(mask), Bn, T, H, ndir, wsb.data_ptr(), nbytes, stream_ptr()), 'lstm_rec_bwd')
+        dG = gates
         dx = None
         grads: List[Optional[torch.Tensor]] = []
         if tc:
             xb, wcat = x, ws[0]
-            dGb = cast_bf16(dG, M, NG, NG, NG)                                            # (B*T, NG) bf16
+            if dGb is None:
+                dGb = cast_bf16(dG, M, NG, NG, NG)                                        # (B*T, NG) bf16
             if ctx.needs_input_grad[0]:
                 dx = torch.zeros(Bn, Tin, D, dtype=torch.float32, device=dev)             # tiles past a row's length are skipped
                 gemm_tc(dGb, wcat, dx, T, Din, NG, a_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=Kp, b_mn=True, c_bs=Tin * D,

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument('--config', default='best')
     ap.add_argument('--cpu-sample-batch', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
+                    help="bf16: the AMP path (gate GEMMs on the tensor pipe, like the reference's autocast runs); fp32: parity mode")
     ap.add_argument('--greedy', action='store_true', help='also report greedy-decode chars/s (configs[3]) as an extra key')
     return ap.parse_args()
 
@@ -185,8 +187,10 @@ def main():
 
     def step(x, y):
         reducer.zero_grad()
-        logits, _att = model(x, lx, y, 1.0, False)                       # tf_rate 1.0 (README stage 1)
-        loss = crit(logits.view(-1, V), y.view(-1)).mean()               # all-ones mask: every target is non-pad
+        # like src/train.py:130-137: forward + loss under autocast (which selects our tensor-pipe kernels)
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=(args.precision == 'bf16')):
+            logits, _att = model(x, lx, y, 1.0, False)                   # tf_rate 1.0 (README stage 1)
+        loss = crit(logits.float().view(-1, V), y.view(-1)).mean()       # all-ones mask: every target is non-pad
         (loss * scale).backward()
         reducer.finish()
         opt.step_fused(inv_scale=1.0 / (scale * world), max_norm=5.0)
@@ -280,7 +284,7 @@ def main():
                    sample=f'one fwd+bwd+AdamW step of the CPU port (oracle/) at B={Bs}, T={T}, L={L}: {sec:.1f} s')
 
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, min_warm), ms_per_step=ms_step,
-               higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+               higher_is_better=True, scaling='weak', vs_baseline=None, dtype=('bf16' if args.precision == 'bf16' else 'f32'), data='synthetic',
                config=dict(workload=f'{args.config} base-LAS teacher-forced train step (fwd+bwd+unscale/clip/AdamW-amsgrad), '
                                     f'batch {B}/GPU, T={T}, L={L}, tf_rate=1.0', global_batch=B * world, parallelism=f'dp{world}',
                            l2_policy='inputs+activations per step (>2.5 GB) exceed the 126 MB L2; no explicit flush'),

@@ -119,6 +119,25 @@ int las_lstm_rec_fwd_f32(float* gates, const float* w_hh, const int* lens, const
 int las_lstm_rec_bwd_f32(const float* dout, float* gates, const float* cs_pad, const float* w_hh, const int* lens,
                          const float* drop_mask, int B, int T, int H, int ndir, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- persistent LSTM recurrence on the tensor pipe (bf16 operands, fp32 state) --------------------------------------
+ * Same call sites and tensor contract as las_lstm_rec_fwd_f32, for the AMP path: W_hh is passed as bf16
+ * (ndir, 4H, H); the 128 x H slice each CTA owns stays resident in shared memory as the A operand of tcgen05.mma and
+ * h_{t-1} arrives by TMA each step.  H must be a multiple of 64; las_lstm_rec_tc_supported() says whether (B, H, ndir)
+ * fits the co-resident grid.  save_gates = 0 skips writing the activated gates (inference). */
+int las_lstm_rec_tc_supported(int B, int H, int ndir);
+size_t las_lstm_rec_tc_workspace_bytes(int B, int H, int ndir);
+int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const int* lens, const float* drop_mask, float* out, float* hs_pad,
+                        float* cs_pad, int B, int T, int H, int ndir, int save_gates, void* ws, size_t ws_bytes, void* stream);
+
+/* BPTT on the tensor pipe.  w_hh_t_bf16 = W_hh transposed per direction, (ndir, H, 4H) bf16 (las_transpose_cast_bf16).
+ * gates: in activated gates, out fp32 d(pre-activation); dgates_bf16 (B*T, ndir*4H): the same values as bf16, written
+ * for every (b, t) (zeros at t >= len) -- the operand of the dX / dW_ih / dW_hh tensor-core GEMMs. */
+int las_lstm_rec_bwd_tc(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16,
+                        const int* lens, const float* drop_mask, int B, int T, int H, int ndir, void* ws, size_t ws_bytes,
+                        void* stream);
+/* dst[b][c][r] (bf16) = src[b][r][c] (fp32) */
+int las_transpose_cast_bf16(const float* src, void* dst, int batch, int rows, int cols, void* stream);
+
 /* ---- fused attention step -------------------------------------------------------------------------------------------
  * Replaces MultiheadCrossAttention.forward after query_map (src/models.py:168-185): energy * sqrt(d), pad mask from
  * lengths (build_pad_masks :106-115, no host mask / H2D), softmax, zeroing, context.  K, V are (B, T, P) row-major.

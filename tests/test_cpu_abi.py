@@ -97,3 +97,27 @@ def test_src_shim_is_drop_in():
     import las_b200
     assert sm.ListenAttendSpell is las_b200.ListenAttendSpell
     assert smod.pyramLockedLSTM is las_b200.pyramLockedLSTM
+
+
+@pytest.mark.reference
+def test_shim_resolves_reference_drivers_and_our_models():
+    """`python -m src.train` of the reference picks up OUR src.models / src.modules and ITS OWN src.utils / src.constants
+    (authoring container only: needs /root/reference)."""
+    import subprocess
+    import sys
+    if not os.path.isdir('/root/reference/src'):
+        pytest.skip('reference checkout not present')
+    code = ("import sys, types\n"
+            "for n in ['torchsummaryX','Levenshtein','seaborn','matplotlib','matplotlib.pyplot','wandb']:\n"
+            "    sys.modules.setdefault(n, types.ModuleType(n))\n"
+            "sys.modules['torchsummaryX'].summary = lambda *a, **k: None\n"
+            "sys.modules['Levenshtein'].distance = lambda a, b: 0\n"
+            "sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']\n"
+            "import src.models, src.constants, src.utils\n"
+            "import las_b200\n"
+            "assert src.models.ListenAttendSpell is las_b200.ListenAttendSpell\n"
+            "assert src.constants.EOS_IDX == 29 and '/root/reference' in src.utils.__file__\n"
+            "print('ok')\n")
+    env = dict(os.environ, LAS_REFERENCE_SRC='/root/reference/src', PYTHONPATH=os.path.join(ROOT, 'attention-based-e2e-asr-dnn_b200'))
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, cwd='/tmp')
+    assert out.returncode == 0 and 'ok' in out.stdout, out.stderr[-2000:]

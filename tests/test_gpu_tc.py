@@ -133,3 +133,97 @@ def test_bf16_mode_logits_within_amp_tolerance(name):
     err = np.abs(logits.detach().float().cpu().numpy() - g['logits']).max()
     print(f'{name}: bf16-mode max abs logit error vs fp32 reference = {err:.3e}')
     assert err < 2e-3
+
+
+@pytest.mark.parametrize('H,B,T,lens', [(64, 5, 9, [9, 3, 7, 1, 9]), (128, 40, 21, None), (512, 96, 12, None), (512, 130, 6, None)])
+def test_tc_recurrence_forward_vs_fp32_kernel(H, B, T, lens):
+    """The tensor-pipe recurrence (bf16 operands) against the fp32 recurrence kernel on the same x-gates: same
+    PackedSequence semantics (zeros past each length, reverse direction from each row's own end), values within bf16
+    operand rounding."""
+    import ctypes as C
+    from las_b200 import _lib, functional as LF
+    lib = _lib.load()
+    rng = np.random.default_rng(H + B)
+    if lens is None:
+        lens = [T] + [int(v) for v in rng.integers(1, T + 1, size=B - 1)]
+    ndir, F = 2, 2 * H
+    assert lib.las_lstm_rec_tc_supported(B, H, ndir)
+    gates0 = torch.from_numpy(rng.standard_normal((B, T, ndir, 4 * H)).astype(np.float32)).to(DEV)
+    w_hh = torch.from_numpy((rng.uniform(-1, 1, size=(ndir, 4 * H, H)) / np.sqrt(H)).astype(np.float32)).to(DEV)
+    lens_dev = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    mask = torch.from_numpy(((rng.random((B, F)) > 0.3) / 0.7).astype(np.float32)).to(DEV)
+    res = []
+    for tc in (False, True):
+        gates = gates0.clone()
+        hs = torch.full((B, T + 2, F), 7.0, device=DEV)
+        cs = torch.full((B, T + 2, F), 7.0, device=DEV)
+        out = torch.full((B, T, F), 7.0, device=DEV)
+        if tc:
+            wb = LF.cast_bf16(w_hh, ndir * 4 * H, H, H, H)
+            nbytes = lib.las_lstm_rec_tc_workspace_bytes(B, H, ndir)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+            _lib.check(lib.las_lstm_rec_fwd_tc(gates.data_ptr(), wb.data_ptr(), lens_dev.data_ptr(), mask.data_ptr(), out.data_ptr(),
+                                               hs.data_ptr(), cs.data_ptr(), B, T, H, ndir, 1, ws.data_ptr(), nbytes,
+                                               torch.cuda.current_stream().cuda_stream), 'rec_fwd_tc')
+        else:
+            nbytes = lib.las_lstm_rec_workspace_bytes(B, H, ndir)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+            _lib.check(lib.las_lstm_rec_fwd_f32(gates.data_ptr(), w_hh.data_ptr(), lens_dev.data_ptr(), mask.data_ptr(), out.data_ptr(),
+                                                hs.data_ptr(), cs.data_ptr(), B, T, H, ndir, ws.data_ptr(), nbytes,
+                                                torch.cuda.current_stream().cuda_stream), 'rec_fwd')
+        torch.cuda.synchronize()
+        res.append((gates, hs, cs, out))
+    (g0, h0, c0, o0), (g1, h1, c1, o1) = res
+    assert np.abs((o1 - o0).cpu().numpy()).max() < 3e-2
+    assert np.abs((h1 - h0).cpu().numpy()).max() < 3e-2
+    assert np.abs((c1 - c0).cpu().numpy()).max() < 6e-2
+    for b, l in enumerate(lens):
+        if l < T:
+            assert float(o1[b, l:].abs().max()) == 0.0 and float(h1[b, l + 1:].abs().max()) == 0.0
+        # activated gates agree where the row is valid
+        assert np.abs((g1[b, :l] - g0[b, :l]).cpu().numpy()).max() < 3e-2
+    assert float(h1[:, 0].abs().max()) == 0.0 and float(h1[:, T + 1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('H,B,T,lens', [(64, 5, 9, [9, 3, 7, 1, 9]), (128, 40, 21, None), (512, 96, 12, None), (256, 130, 6, None)])
+def test_tc_recurrence_backward_vs_fp32_kernel(H, B, T, lens):
+    """BPTT on the tensor pipe against the fp32 BPTT kernel on identical saved activations."""
+    from las_b200 import _lib, functional as LF
+    lib = _lib.load()
+    rng = np.random.default_rng(H + B + 1)
+    if lens is None:
+        lens = [T] + [int(v) for v in rng.integers(1, T + 1, size=B - 1)]
+    ndir, F = 2, 2 * H
+    st = torch.cuda.current_stream().cuda_stream
+    gates0 = torch.from_numpy(rng.standard_normal((B, T, ndir, 4 * H)).astype(np.float32)).to(DEV)
+    w_hh = torch.from_numpy((rng.uniform(-1, 1, size=(ndir, 4 * H, H)) / np.sqrt(H)).astype(np.float32)).to(DEV)
+    lens_dev = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    mask = torch.from_numpy(((rng.random((B, F)) > 0.3) / 0.7).astype(np.float32)).to(DEV)
+    dout = torch.from_numpy(rng.standard_normal((B, T, F)).astype(np.float32)).to(DEV)
+    # forward once with the fp32 kernel to get consistent saved activations
+    gates = gates0.clone()
+    hs = torch.zeros(B, T + 2, F, device=DEV); cs = torch.zeros(B, T + 2, F, device=DEV); out = torch.zeros(B, T, F, device=DEV)
+    nbytes = lib.las_lstm_rec_workspace_bytes(B, H, ndir)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.las_lstm_rec_fwd_f32(gates.data_ptr(), w_hh.data_ptr(), lens_dev.data_ptr(), mask.data_ptr(), out.data_ptr(),
+                                        hs.data_ptr(), cs.data_ptr(), B, T, H, ndir, ws.data_ptr(), nbytes, st), 'fwd')
+    g_ref = gates.clone()
+    _lib.check(lib.las_lstm_rec_bwd_f32(dout.data_ptr(), g_ref.data_ptr(), cs.data_ptr(), w_hh.data_ptr(), lens_dev.data_ptr(),
+                                        mask.data_ptr(), B, T, H, ndir, ws.data_ptr(), nbytes, st), 'bwd_f32')
+    g_tc = gates.clone()
+    w_t = torch.empty(ndir, H, 4 * H, dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.las_transpose_cast_bf16(w_hh.data_ptr(), w_t.data_ptr(), ndir, 4 * H, H, st), 'transpose')
+    assert torch.equal(w_t.float(), w_hh.transpose(1, 2).to(torch.bfloat16).float())
+    dgb = torch.full((B * T, ndir * 4 * H), float('nan'), dtype=torch.bfloat16, device=DEV)
+    nb2 = max(nbytes, 1024)
+    ws2 = torch.empty(nb2, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.las_lstm_rec_bwd_tc(dout.data_ptr(), g_tc.data_ptr(), dgb.data_ptr(), cs.data_ptr(), w_t.data_ptr(), lens_dev.data_ptr(),
+                                       mask.data_ptr(), B, T, H, ndir, ws2.data_ptr(), nb2, st), 'bwd_tc')
+    torch.cuda.synchronize()
+    scale = float(g_ref.abs().max())
+    assert np.abs((g_tc - g_ref).cpu().numpy()).max() < 2e-2 * scale
+    assert torch.isfinite(dgb.float()).all()
+    assert np.abs(dgb.float().view(B, T, ndir, 4 * H).cpu().numpy() - g_tc.cpu().numpy()).max() < 1e-2 * scale
+    for b, l in enumerate(lens):
+        if l < T:
+            assert float(g_tc[b, l:].abs().max()) == 0.0
