@@ -12,7 +12,7 @@
 
 namespace {
 
-constexpr int NT = 256;
+constexpr int NT = 512;     // 16 warps: 4 rows in flight per warp -> ~64 KB of loads in flight per SM
 constexpr int NW = NT / 32;
 constexpr int MAXCH = 2;     // head dim <= 256 (2 x 128-float chunks per warp row pass)
 
@@ -77,20 +77,31 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
             }
         }
     }
-    // ---- phase A: one warp per row, 2 rows in flight per warp ----
-    for (int t = w; t < len; t += NW) {
-        float acc = 0.f;
+    // ---- phase A: one warp per row, RU rows in flight per warp (all loads issued before any reduction) ----
+    constexpr int RU = 4;
+    for (int t0 = w; t0 < len; t0 += NW * RU) {
+        float4 m[RU][MAXCH];
 #pragma unroll
-        for (int c = 0; c < MAXCH; ++c) {
-            int k = c * 128 + lane * 4;
-            if (c < nch && k < d) {
-                float4 m = ldg4_stream(Mat1 + (long long)t * P + k);
-                acc = fmaf(m.x, v4[c].x, acc); acc = fmaf(m.y, v4[c].y, acc);
-                acc = fmaf(m.z, v4[c].z, acc); acc = fmaf(m.w, v4[c].w, acc);
+        for (int r = 0; r < RU; ++r) {
+            const int t = t0 + r * NW;
+#pragma unroll
+            for (int c = 0; c < MAXCH; ++c) {
+                int k = c * 128 + lane * 4;
+                m[r][c] = (t < len && c < nch && k < d) ? ldg4_stream(Mat1 + (long long)t * P + k) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) sc[t] = acc;
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+            const int t = t0 + r * NW;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < MAXCH; ++c) {
+                acc = fmaf(m[r][c].x, v4[c].x, acc); acc = fmaf(m[r][c].y, v4[c].y, acc);
+                acc = fmaf(m[r][c].z, v4[c].z, acc); acc = fmaf(m[r][c].w, v4[c].w, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0 && t < len) sc[t] = acc;
+        }
     }
     __syncthreads();
     float* wrow = a.w + ((long long)b * heads + h) * a.ld_w;
@@ -130,17 +141,26 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
     float4 o4[MAXCH];
 #pragma unroll
     for (int c = 0; c < MAXCH; ++c) o4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = w; t < len; t += NW) {
-        const float s = sc[t];
+    for (int t0 = w; t0 < len; t0 += NW * RU) {
+        float4 m[RU][MAXCH];
+        float sv[RU];
 #pragma unroll
-        for (int c = 0; c < MAXCH; ++c) {
-            int k = c * 128 + lane * 4;
-            if (c < nch && k < d) {
-                float4 m = ldg4_stream(Mat2 + (long long)t * P + k);
-                o4[c].x = fmaf(s, m.x, o4[c].x); o4[c].y = fmaf(s, m.y, o4[c].y);
-                o4[c].z = fmaf(s, m.z, o4[c].z); o4[c].w = fmaf(s, m.w, o4[c].w);
+        for (int r = 0; r < RU; ++r) {
+            const int t = t0 + r * NW;
+            sv[r] = (t < len) ? sc[t] : 0.f;
+#pragma unroll
+            for (int c = 0; c < MAXCH; ++c) {
+                int k = c * 128 + lane * 4;
+                m[r][c] = (t < len && c < nch && k < d) ? ldg4_stream(Mat2 + (long long)t * P + k) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+#pragma unroll
+        for (int r = 0; r < RU; ++r)
+#pragma unroll
+            for (int c = 0; c < MAXCH; ++c) {
+                o4[c].x = fmaf(sv[r], m[r][c].x, o4[c].x); o4[c].y = fmaf(sv[r], m[r][c].y, o4[c].y);
+                o4[c].z = fmaf(sv[r], m[r][c].z, o4[c].z); o4[c].w = fmaf(sv[r], m[r][c].w, o4[c].w);
+            }
     }
 #pragma unroll
     for (int c = 0; c < MAXCH; ++c) {
@@ -155,9 +175,12 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
         if (!BWD) {
             a.ctx[(long long)b * a.ld_ctx + h * d + p] = r;
             if (a.ctx2) a.ctx2[(long long)b * a.ld_ctx2 + h * d + p] = r;
+            if (a.ctx2_bf16) ((__nv_bfloat16*)a.ctx2_bf16)[(long long)b * a.ld_ctx2_bf16 + h * d + p] = __float2bfloat16(r);
         } else {
             float* dq = a.dq + (long long)b * a.ld_dq + h * d + p;
-            *dq = (a.dq_accumulate ? *dq : 0.f) + r;
+            const float tot = (a.dq_accumulate ? *dq : 0.f) + r;
+            *dq = tot;
+            if (a.dq_bf16) ((__nv_bfloat16*)a.dq_bf16)[(long long)b * a.ld_dq_bf16 + h * d + p] = __float2bfloat16(tot);
         }
     }
 }

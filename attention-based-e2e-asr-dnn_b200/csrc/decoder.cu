@@ -34,6 +34,8 @@ struct CellFwd {
     const float* mask;        // (B, H) or null
     float* h1; long long ld_h1;
     float* h2; long long ld_h2;   // nullable second destination
+    __nv_bfloat16* h1b; long long ld_h1b;   // nullable bf16 copies (tensor-pipe mode: next GEMMs' A operand)
+    __nv_bfloat16* h2b; long long ld_h2b;
     int B, H;
 };
 
@@ -61,6 +63,8 @@ __global__ void __launch_bounds__(256) cell_fwd_kernel(CellFwd a) {
     a.c_out[(long long)b * a.ld_co + u] = c;
     a.h1[(long long)b * a.ld_h1 + u] = h;
     if (a.h2) a.h2[(long long)b * a.ld_h2 + u] = h;
+    if (a.h1b) a.h1b[(long long)b * a.ld_h1b + u] = __float2bfloat16(h);
+    if (a.h2b) a.h2b[(long long)b * a.ld_h2b + u] = __float2bfloat16(h);
 }
 
 struct CellBwd {
@@ -71,6 +75,7 @@ struct CellBwd {
     const float* c; long long ld_c;
     const float* c_prev; long long ld_cp;
     float* dc;                // (B,H) carried in/out
+    __nv_bfloat16* Gb;        // nullable (B,4H) bf16 copy of the d(pre-activation) (tensor-pipe mode)
     int first;                // 1: dc carried-in is zero
     int B, H;
 };
@@ -90,10 +95,13 @@ __global__ void __launch_bounds__(256) cell_bwd_kernel(CellBwd a) {
     const float dcin = a.first ? 0.f : a.dc[(long long)b * H + u];
     const float tc = tanhf(c);
     const float dct = fmaf(dh * go, 1.f - tc * tc, dcin);
-    g[0] = dct * gg * gi * (1.f - gi);
-    g[H] = dct * cp * gf * (1.f - gf);
-    g[2 * H] = dct * gi * (1.f - gg * gg);
-    g[3 * H] = dh * tc * go * (1.f - go);
+    const float d0 = dct * gg * gi * (1.f - gi), d1 = dct * cp * gf * (1.f - gf);
+    const float d2 = dct * gi * (1.f - gg * gg), d3 = dh * tc * go * (1.f - go);
+    g[0] = d0; g[H] = d1; g[2 * H] = d2; g[3 * H] = d3;
+    if (a.Gb) {
+        __nv_bfloat16* gb = a.Gb + (long long)b * 4 * H + u;
+        gb[0] = __float2bfloat16(d0); gb[H] = __float2bfloat16(d1); gb[2 * H] = __float2bfloat16(d2); gb[3 * H] = __float2bfloat16(d3);
+    }
     a.dc[(long long)b * H + u] = dct * gf;
 }
 
@@ -198,9 +206,40 @@ int gemm_tn(cudaStream_t st, const float* A, long long lda, const float* B, long
     return las_gemm_f32(&d, st);
 }
 
+// tensor-pipe forms (bf16 operands, fp32 output)
+//   tc_nt: C[M,N] = A[M,K] . B[N,K]^T (+biases)     A rows stride lda, B rows stride ldb (both K contiguous)
+//   tc_nn: C[M,N] = A[M,K] . B[K,N]                  B rows stride ldb (N contiguous)
+//   tc_tn: C[M,N] = A[K,M]^T . B[K,N]                both reduction-major (weight gradients)
+int tc_nt(cudaStream_t st, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb, float* C, long long ldc, int M, int N,
+          int K, const float* bias1 = nullptr, const float* bias2 = nullptr) {
+    LasGemmTc d{};
+    d.A = A; d.B = B; d.C = C; d.bias1 = bias1; d.bias2 = bias2; d.M = M; d.N = N; d.K = K; d.a_batches = 1; d.k_batches = 1;
+    d.a_s1 = lda; d.b_s1 = ldb; d.ldc = ldc;
+    return las_gemm_bf16_tc(&d, st);
+}
+int tc_nn(cudaStream_t st, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb, float* C, long long ldc, int M, int N,
+          int K) {
+    LasGemmTc d{};
+    d.A = A; d.B = B; d.C = C; d.M = M; d.N = N; d.K = K; d.a_batches = 1; d.k_batches = 1;
+    d.a_s1 = lda; d.b_s1 = ldb; d.ldc = ldc; d.b_mn_major = 1;
+    return las_gemm_bf16_tc(&d, st);
+}
+int tc_tn(cudaStream_t st, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb, float* C, long long ldc, int M, int N,
+          int K) {
+    LasGemmTc d{};
+    d.A = A; d.B = B; d.C = C; d.M = M; d.N = N; d.K = K; d.a_batches = 1; d.k_batches = 1;
+    d.a_s1 = lda; d.b_s1 = ldb; d.ldc = ldc; d.a_mn_major = 1; d.b_mn_major = 1;
+    return las_gemm_bf16_tc(&d, st);
+}
+int cast_rows(cudaStream_t st, const float* src, long long ld_src, __nv_bfloat16* dst, long long ld_dst, long long rows, int cols) {
+    return las_cast_f32_to_bf16(src, ld_src, 0, 0, dst, ld_dst, rows, cols, cols, st);
+}
+
 struct Layout {
     // float workspace offsets
     size_t Wcat0, Wcat1, Gemb, S0, S1, C0, C1, G0, G1, QC, W, dQC, dS0, dS1, dc0, dc1, dh1, DE, dGemb, tmpq, cs_scratch, total_f;
+    // bf16 region (offsets in floats, buffers hold bf16): tensor-pipe mode only
+    size_t Wcat0b, Wcat1b, Wqb, S0b, S1b, G0b, G1b, dQb;
     // int workspace offsets
     size_t tok, total_i;
     int hist, ghist;
@@ -239,6 +278,19 @@ Layout make_layout(const LasSpeller* s) {
         if (maxn < 2 * P) maxn = 2 * P;
         L.cs_scratch = take((size_t)CS_ROWSPLIT * maxn);
     }
+    if (s->use_tc) {
+        auto takeb = [&](size_t n_bf16) { return take((n_bf16 + 1) / 2 + 4); };
+        L.Wcat0b = takeb(4 * DH * (P + DH));
+        L.Wcat1b = takeb(4 * DO * (DH + DO));
+        L.Wqb = takeb(P * DO);
+        L.S0b = takeb((size_t)L.hist * B * (P + DH));
+        L.S1b = takeb((size_t)L.hist * B * (DH + DO));
+        if (s->training) {
+            L.G0b = takeb(S * B * 4 * DH);
+            L.G1b = takeb(S * B * 4 * DO);
+            L.dQb = takeb((S + 1) * B * P);
+        }
+    }
     L.total_f = o;
     L.tok = 0;
     L.total_i = s->training ? S * B : 4;
@@ -257,6 +309,8 @@ int check_speller(const LasSpeller* s) {
                       s->wq && s->bq && s->init_query, "speller: null parameter pointer");
     LAS_CHECK_ARG(s->K && s->V_ && s->enc_lens && s->logits && s->chars && s->fws && s->iws, "speller: null input/output pointer");
     LAS_CHECK_ARG(!s->training || s->dec_y, "speller: training needs dec_y");
+    LAS_CHECK_ARG(!s->use_tc || (s->P % 8 == 0 && s->DH % 8 == 0 && s->DO % 8 == 0),
+                  "speller: tensor-pipe mode needs P/DH/DO multiples of 8 (TMA 16-byte strides)");
     return LAS_OK;
 }
 
@@ -322,12 +376,22 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
           *G0 = f + L.G0, *G1 = f + L.G1, *QC = f + L.QC, *W = f + L.W;
     int* tok = s->iws + L.tok;
     const size_t fsz = sizeof(float);
+    const bool tc = s->use_tc != 0;
+    __nv_bfloat16 *Wcat0b = (__nv_bfloat16*)(f + L.Wcat0b), *Wcat1b = (__nv_bfloat16*)(f + L.Wcat1b), *Wqb = (__nv_bfloat16*)(f + L.Wqb),
+                  *S0b = (__nv_bfloat16*)(f + L.S0b), *S1b = (__nv_bfloat16*)(f + L.S1b);
 
     // packed weights
     LAS_CUDA(cudaMemcpy2DAsync(Wcat0, K0 * fsz, s->w_ih0 + E, (size_t)(E + P) * fsz, P * fsz, 4 * DH, cudaMemcpyDeviceToDevice, st));
     LAS_CUDA(cudaMemcpy2DAsync(Wcat0 + P, K0 * fsz, s->w_hh0, DH * fsz, DH * fsz, 4 * DH, cudaMemcpyDeviceToDevice, st));
     LAS_CUDA(cudaMemcpy2DAsync(Wcat1, K1 * fsz, s->w_ih1, DH * fsz, DH * fsz, 4 * DO, cudaMemcpyDeviceToDevice, st));
     LAS_CUDA(cudaMemcpy2DAsync(Wcat1 + DH, K1 * fsz, s->w_hh1, DO * fsz, DO * fsz, 4 * DO, cudaMemcpyDeviceToDevice, st));
+    if (tc) {
+        RC(cast_rows(st, Wcat0, K0, Wcat0b, K0, 4 * DH, K0));
+        RC(cast_rows(st, Wcat1, K1, Wcat1b, K1, 4 * DO, K1));
+        RC(cast_rows(st, s->wq, DO, Wqb, DO, P, DO));
+        LAS_CUDA(cudaMemset2DAsync(S0b + P, K0 * 2, 0, DH * 2, B, st));       // h0_{-1} = 0 (bf16)
+        LAS_CUDA(cudaMemset2DAsync(S1b + DH, K1 * 2, 0, DO * 2, B, st));      // h1_{-1} = 0
+    }
     // embedding-side gate table (+ both cell-0 biases)
     RC(gemm(st, s->emb, E, s->w_ih0, E + P, 1, Gemb, 4 * DH, V, 4 * DH, E, 0.f, s->b_ih0, s->b_hh0));
     // zero initial states (init_hiddens are always zero: reference src/models.py:275-281)
@@ -349,6 +413,7 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
     at.scale = sqrtf((float)(P / heads));
     at.ld_q = 2 * P; at.ld_ctx = 2 * P; at.ld_ctx2 = K0; at.ld_w = T;
     at.q = QC; at.ctx = QC + P; at.ctx2 = S0; at.w = W; at.w_b0 = s->att0;
+    at.ctx2_bf16 = tc ? (void*)S0b : nullptr; at.ld_ctx2_bf16 = K0;
     RC(las_attn_step_fwd_f32(&at, st));
 
     bool all_gold = s->training != 0;
@@ -362,8 +427,11 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
         float* S1r = S1 + (size_t)r * B * K1;  float* S1n = S1 + (size_t)rn * B * K1;
         float* G0r = G0 + (size_t)rg * B * 4 * DH;  float* G1r = G1 + (size_t)rg * B * 4 * DO;
         float* QCn = QC + (size_t)rn * B * 2 * P;
+        __nv_bfloat16* S0rb = S0b + (size_t)r * B * K0;  __nv_bfloat16* S0nb = S0b + (size_t)rn * B * K0;
+        __nv_bfloat16* S1rb = S1b + (size_t)r * B * K1;  __nv_bfloat16* S1nb = S1b + (size_t)rn * B * K1;
         // cell 0
-        RC(gemm(st, S0r, K0, Wcat0, K0, 1, G0r, 4 * DH, B, 4 * DH, K0));
+        if (tc) RC(tc_nt(st, S0rb, K0, Wcat0b, K0, G0r, 4 * DH, B, 4 * DH, K0));
+        else RC(gemm(st, S0r, K0, Wcat0, K0, 1, G0r, 4 * DH, B, 4 * DH, K0));
         CellFwd c0{};
         c0.G = G0r; c0.Gtab = Gemb; c0.y = s->dec_y; c0.ld_y = s->ld_y;
         c0.chars_prev = (t > 0) ? s->chars + (size_t)(t - 1) * B : nullptr;
@@ -375,24 +443,29 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
         c0.mask = s->drop0 ? s->drop0 + (size_t)t * B * DH : nullptr;
         c0.h1 = S0n + P; c0.ld_h1 = K0;      // recurrent slot of the next step's cell-0 row
         c0.h2 = S1r; c0.ld_h2 = K1;          // input slot of this step's cell-1 row
+        if (tc) { c0.h1b = S0nb + P; c0.ld_h1b = K0; c0.h2b = S1rb; c0.ld_h2b = K1; }
         c0.B = B; c0.H = DH;
         cell_fwd_kernel<<<ceil_div(B * DH, 256), 256, 0, st>>>(c0);
         LAS_LAUNCH_CHECK();
         // cell 1
-        RC(gemm(st, S1r, K1, Wcat1, K1, 1, G1r, 4 * DO, B, 4 * DO, K1, 0.f, s->b_ih1, s->b_hh1));
+        if (tc) RC(tc_nt(st, S1rb, K1, Wcat1b, K1, G1r, 4 * DO, B, 4 * DO, K1, s->b_ih1, s->b_hh1));
+        else RC(gemm(st, S1r, K1, Wcat1, K1, 1, G1r, 4 * DO, B, 4 * DO, K1, 0.f, s->b_ih1, s->b_hh1));
         CellFwd c1{};
         c1.G = G1r; c1.Gtab = nullptr; c1.t = t;
         c1.c_prev = C1 + (size_t)r * B * DO; c1.ld_cp = DO;
         c1.c_out = C1 + (size_t)rn * B * DO; c1.ld_co = DO;
         c1.mask = s->drop1 ? s->drop1 + (size_t)t * B * DO : nullptr;
         c1.h1 = S1n + DH; c1.ld_h1 = K1; c1.h2 = nullptr;
+        if (tc) { c1.h1b = S1nb + DH; c1.ld_h1b = K1; }
         c1.B = B; c1.H = DO;
         cell_fwd_kernel<<<ceil_div(B * DO, 256), 256, 0, st>>>(c1);
         LAS_LAUNCH_CHECK();
         // query projection into QC[t+1][:, :P]
-        RC(gemm(st, S1n + DH, K1, s->wq, DO, 1, QCn, 2 * P, B, P, DO, 0.f, s->bq));
+        if (tc) RC(tc_nt(st, S1nb + DH, K1, Wqb, DO, QCn, 2 * P, B, P, DO, s->bq));
+        else RC(gemm(st, S1n + DH, K1, s->wq, DO, 1, QCn, 2 * P, B, P, DO, 0.f, s->bq));
         // attention: context into QC[t+1][:, P:] and into the next cell-0 row
         at.q = QCn; at.ctx = QCn + P; at.ctx2 = S0n; at.w = W + (size_t)rn * B * heads * T;
+        at.ctx2_bf16 = tc ? (void*)S0nb : nullptr;
         at.w_b0 = s->att0 ? s->att0 + (size_t)(t + 1) * heads * T : nullptr;
         RC(las_attn_step_fwd_f32(&at, st));
         if (per_step_logits) {
@@ -437,6 +510,10 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     const int* tok = s->iws + L.tok;
     const size_t fsz = sizeof(float);
     const long long SB = (long long)S * B;
+    const bool tc = s->use_tc != 0;
+    __nv_bfloat16 *Wcat0b = (__nv_bfloat16*)(f + L.Wcat0b), *Wcat1b = (__nv_bfloat16*)(f + L.Wcat1b), *Wqb = (__nv_bfloat16*)(f + L.Wqb),
+                  *S0b = (__nv_bfloat16*)(f + L.S0b), *S1b = (__nv_bfloat16*)(f + L.S1b), *G0b = (__nv_bfloat16*)(f + L.G0b),
+                  *G1b = (__nv_bfloat16*)(f + L.G1b), *dQb = (__nv_bfloat16*)(f + L.dQb);
 
     // dQC[1..S] = dlogits . emb  (row m = t*B + b  <-  dlogits[b, t, :])
     LAS_CUDA(cudaMemsetAsync(dQC, 0, (size_t)B * 2 * P * fsz, st));
@@ -473,9 +550,11 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
         at.q = QC + (size_t)rn * B * 2 * P; at.w = W + (size_t)rn * B * heads * T;
         at.dctx = dQCn + P; at.dctx2 = (t == S - 1) ? nullptr : dS0;
         at.dq = dQCn; at.de = DE + (size_t)rn * B * heads * T;
+        at.dq_bf16 = tc ? (void*)(dQb + (size_t)rn * B * P) : nullptr; at.ld_dq_bf16 = P;
         RC(las_attn_step_bwd_f32(&at, st));
         // dh1_t (dropped) = dq_total . Wq  (+ recurrent path, added inside cell_bwd)
-        RC(gemm(st, dQCn, 2 * P, s->wq, DO, 0, dh1, DO, B, DO, P));
+        if (tc) RC(tc_nn(st, dQb + (size_t)rn * B * P, P, Wqb, DO, dh1, DO, B, DO, P));
+        else RC(gemm(st, dQCn, 2 * P, s->wq, DO, 0, dh1, DO, B, DO, P));
         CellBwd b1{};
         b1.G = G1 + (size_t)t * B * 4 * DO;
         b1.dh_a = dh1; b1.ld_a = DO;
@@ -483,10 +562,12 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
         b1.mask = s->drop1 ? s->drop1 + (size_t)t * B * DO : nullptr;
         b1.c = C1 + (size_t)rn * B * DO; b1.ld_c = DO; b1.c_prev = C1 + (size_t)t * B * DO; b1.ld_cp = DO;
         b1.dc = dc1; b1.first = (t == S - 1); b1.B = B; b1.H = DO;
+        b1.Gb = tc ? G1b + (size_t)t * B * 4 * DO : nullptr;
         cell_bwd_kernel<<<ceil_div(B * DO, 256), 256, 0, st>>>(b1);
         LAS_LAUNCH_CHECK();
         // dS1[t] = dG1_t . Wcat1  -> [dh0_t | dh1_{t-1}]
-        RC(gemm(st, b1.G, 4 * DO, Wcat1, K1, 0, dS1, K1, B, K1, 4 * DO));
+        if (tc) RC(tc_nn(st, b1.Gb, 4 * DO, Wcat1b, K1, dS1, K1, B, K1, 4 * DO));
+        else RC(gemm(st, b1.G, 4 * DO, Wcat1, K1, 0, dS1, K1, B, K1, 4 * DO));
         CellBwd b0{};
         b0.G = G0 + (size_t)t * B * 4 * DH;
         b0.dh_a = dS1; b0.ld_a = K1;
@@ -494,18 +575,22 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
         b0.mask = s->drop0 ? s->drop0 + (size_t)t * B * DH : nullptr;
         b0.c = C0 + (size_t)rn * B * DH; b0.ld_c = DH; b0.c_prev = C0 + (size_t)t * B * DH; b0.ld_cp = DH;
         b0.dc = dc0; b0.first = (t == S - 1); b0.B = B; b0.H = DH;
+        b0.Gb = tc ? G0b + (size_t)t * B * 4 * DH : nullptr;
         cell_bwd_kernel<<<ceil_div(B * DH, 256), 256, 0, st>>>(b0);
         LAS_LAUNCH_CHECK();
         // dS0[t] = dG0_t . Wcat0 -> [dctx_t | dh0_{t-1}]
-        RC(gemm(st, b0.G, 4 * DH, Wcat0, K0, 0, dS0, K0, B, K0, 4 * DH));
+        if (tc) RC(tc_nn(st, b0.Gb, 4 * DH, Wcat0b, K0, dS0, K0, B, K0, 4 * DH));
+        else RC(gemm(st, b0.G, 4 * DH, Wcat0, K0, 0, dS0, K0, B, K0, 4 * DH));
     }
     // initial attention (src/models.py:346): its context feeds cell 0 of step 0 only
     at.q = QC; at.w = W; at.dctx = dQC + P; at.dctx2 = dS0; at.dq = dQC; at.de = DE;
+    at.dq_bf16 = tc ? (void*)dQb : nullptr;
     RC(las_attn_step_bwd_f32(&at, st));
 
     // ---- batched parameter gradients ----
     // query_map: rows 1..S see h1_t (S1[t+1] slot), row 0 sees init_query
-    RC(gemm_tn(st, dQC + (size_t)B * 2 * P, 2 * P, S1 + (size_t)B * K1 + DH, K1, g->d_wq, DO, P, DO, (int)SB));
+    if (tc) RC(tc_tn(st, dQb + (size_t)B * P, P, S1b + (size_t)B * K1 + DH, K1, g->d_wq, DO, P, DO, (int)SB));
+    else RC(gemm_tn(st, dQC + (size_t)B * 2 * P, 2 * P, S1 + (size_t)B * K1 + DH, K1, g->d_wq, DO, P, DO, (int)SB));
     {
         LasGemmF32 d{};
         d.A = dQC; d.B = s->init_query; d.C = g->d_wq;
@@ -518,13 +603,23 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     RC(gemm(st, dQC, 2 * P, s->wq, DO, 0, tmpq, DO, B, DO, P));
     RC(las_colsum_f32(tmpq, DO, B, DO, g->d_init_query, 0, csw, st));
     // cell 1
-    RC(gemm_tn(st, G1, 4 * DO, S1, K1, g->d_w_ih1, DH, 4 * DO, DH, (int)SB));
-    RC(gemm_tn(st, G1, 4 * DO, S1 + DH, K1, g->d_w_hh1, DO, 4 * DO, DO, (int)SB));
+    if (tc) {
+        RC(tc_tn(st, G1b, 4 * DO, S1b, K1, g->d_w_ih1, DH, 4 * DO, DH, (int)SB));
+        RC(tc_tn(st, G1b, 4 * DO, S1b + DH, K1, g->d_w_hh1, DO, 4 * DO, DO, (int)SB));
+    } else {
+        RC(gemm_tn(st, G1, 4 * DO, S1, K1, g->d_w_ih1, DH, 4 * DO, DH, (int)SB));
+        RC(gemm_tn(st, G1, 4 * DO, S1 + DH, K1, g->d_w_hh1, DO, 4 * DO, DO, (int)SB));
+    }
     RC(las_colsum_f32(G1, 4 * DO, (int)SB, 4 * DO, g->d_b_ih1, 0, csw, st));
     LAS_CUDA(cudaMemcpyAsync(g->d_b_hh1, g->d_b_ih1, (size_t)4 * DO * fsz, cudaMemcpyDeviceToDevice, st));
     // cell 0: context columns, recurrent weight, biases
-    RC(gemm_tn(st, G0, 4 * DH, S0, K0, g->d_w_ih0 + E, E + P, 4 * DH, P, (int)SB));
-    RC(gemm_tn(st, G0, 4 * DH, S0 + P, K0, g->d_w_hh0, DH, 4 * DH, DH, (int)SB));
+    if (tc) {
+        RC(tc_tn(st, G0b, 4 * DH, S0b, K0, g->d_w_ih0 + E, E + P, 4 * DH, P, (int)SB));
+        RC(tc_tn(st, G0b, 4 * DH, S0b + P, K0, g->d_w_hh0, DH, 4 * DH, DH, (int)SB));
+    } else {
+        RC(gemm_tn(st, G0, 4 * DH, S0, K0, g->d_w_ih0 + E, E + P, 4 * DH, P, (int)SB));
+        RC(gemm_tn(st, G0, 4 * DH, S0 + P, K0, g->d_w_hh0, DH, 4 * DH, DH, (int)SB));
+    }
     RC(las_colsum_f32(G0, 4 * DH, (int)SB, 4 * DH, g->d_b_ih0, 0, csw, st));
     LAS_CUDA(cudaMemcpyAsync(g->d_b_hh0, g->d_b_ih0, (size_t)4 * DH * fsz, cudaMemcpyDeviceToDevice, st));
     // cell 0: embedding columns through the token table

@@ -36,6 +36,7 @@ struct RecTcArgs {
     __nv_bfloat16* hbuf;   // (ndir, 2, Bpad, H) bf16 exchange buffer
     unsigned* ctr;         // (ndir, nslices) step counters
     int B, T, H, ndir, nslices, Bpad, chains, bsg, save;
+    long long* dbg;        // optional (debug): per-step clock64 stamps of CTA (0,0,0), 16 slots per step
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,6 +60,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                  "l"(map), "r"(bar), "r"(c0), "r"(c1)
                  : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -100,6 +113,11 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+#define REC_STAMP(slot)                                                                              \
+    do {                                                                                            \
+        if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && s < 256) a.dbg[s * 16 + (slot)] = clock64(); \
+    } while (0)
 
 // idesc: F32 accumulate, BF16 x BF16, both K-major, M = 128, N = 32
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB_SLICE >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
@@ -155,10 +173,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     const unsigned* ctr = a.ctr + dir * a.nslices + slice;
                     const unsigned target = (unsigned)(H / UNITS) * (unsigned)s;
                     while (ld_acquire_gpu(ctr) < target) { }
+                    REC_STAMP(0);
                     asm volatile("fence.proxy.async;" ::: "memory");       // peers' generic-proxy writes -> our TMA reads
+                    REC_STAMP(11);
                     mbar_arrive_expect_tx(full_bar(c), (uint32_t)KB * 4096u);
                     const int row0 = (dir * 2 + ((s - 1) & 1)) * a.Bpad + slice * NB_SLICE;
-                    for (int kb = 0; kb < KB; ++kb) tma_load_2d(h_sm + (c * KB + kb) * 4096, &tmH, full_bar(c), kb * 64, row0);
+                    tma_load_3d(h_sm + c * KB * 4096, &tmH, full_bar(c), 0, row0, 0);   // box (64, 32 rows, KB k-blocks): one issue
+                    REC_STAMP(1);
                 }
             }
         }
@@ -171,6 +192,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     const int slice = sg + c * a.bsg;
                     if (slice >= a.nslices) continue;
                     mbar_wait(full_bar(c), (uint32_t)((s - 1) & 1));
+                    REC_STAMP(2);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + c * NB_SLICE;
                     for (int kb = 0; kb < KB; ++kb) {
@@ -182,6 +204,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                         }
                     }
                     umma_commit(tfull_bar(c));
+                    REC_STAMP(3);
                 }
             }
         }
@@ -191,10 +214,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
         const int te = (warp - 4) * 32 + lane;     // 0..127
         const int u = r * UNITS + j;
         float cst[MAX_CHAINS][8];
+        int lenr[MAX_CHAINS][8];      // lengths of this thread's 8 batch rows per chain (0 for rows >= B): loaded once
 #pragma unroll
         for (int c = 0; c < MAX_CHAINS; ++c)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cst[c][i] = 0.f;
+            for (int i = 0; i < 8; ++i) {
+                cst[c][i] = 0.f;
+                const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
+                lenr[c][i] = (c < a.chains && sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
+            }
         // zero the pad frames (0 and T+1) of this CTA's (rows, units): the shifted h_{t-1} / c_{t-1} reads of backward
         for (int c = 0; c < a.chains; ++c) {
             const int slice = sg + c * a.bsg;
@@ -209,9 +237,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
         }
         for (int s = 0; s < T; ++s) {
             const int t = (dir == 0) ? s : (T - 1 - s);
-            for (int c = 0; c < a.chains; ++c) {
+#pragma unroll
+            for (int c = 0; c < MAX_CHAINS; ++c) {
                 const int slice = sg + c * a.bsg;
-                if (slice >= a.nslices) continue;
+                if (c >= a.chains || slice >= a.nslices) continue;
                 const int b0 = slice * NB_SLICE;
                 // input projection for (gate q, unit j) of the 32 batch rows: coalesced 128 B per row, issued before the wait
                 float xg[32];
@@ -220,10 +249,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
 #pragma unroll
                 for (int n = 0; n < 32; ++n) xg[n] = (b0 + n < a.B) ? gbase[(long long)(b0 + n) * gstride] : 0.f;
                 uint32_t v[32];
+                if (te == 0) REC_STAMP(4);
                 if (s > 0) {
                     mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
+                    if (te == 0) REC_STAMP(5);
                     tc_fence_after();
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * NB_SLICE, v);
+                    if (te == 0) REC_STAMP(6);
                 } else {
 #pragma unroll
                     for (int n = 0; n < 32; ++n) v[n] = 0u;
@@ -237,6 +269,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                 }
                 tc_fence_before();
                 named_bar_sync(1, 128);
+                if (te == 0) REC_STAMP(7);
                 // cell update: thread (q, j) owns unit j for batch rows n = q*8 + i
                 float hh[8], cc[8];
 #pragma unroll
@@ -244,7 +277,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     const int n = q * 8 + i, b = b0 + n;
                     const float gi = ex[(0 * 32 + n) * 32 + j], gf = ex[(1 * 32 + n) * 32 + j];
                     const float gg = ex[(2 * 32 + n) * 32 + j], go = ex[(3 * 32 + n) * 32 + j];
-                    const bool valid = (b < a.B) && (t < a.lens[b]);
+                    const bool valid = t < lenr[c][i];
                     cc[i] = 0.f; hh[i] = 0.f;
                     if (valid) {
                         cc[i] = fmaf(gf, cst[c][i], gi * gg);
@@ -256,7 +289,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                 }
                 // publish step s of this chain FIRST (the release only has the 8 bf16 stores per thread in front of it) ...
                 named_bar_sync(1, 128);
+                if (te == 0) REC_STAMP(8);
                 if (te == 0 && s + 1 < T) red_release_gpu_add(a.ctr + dir * a.nslices + slice, 1u);
+                if (te == 0) REC_STAMP(9);
                 // ... then write what only backward / the next layer read; these stores overlap the wait for the next step
                 if (a.save) {
 #pragma unroll
@@ -276,6 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                         }
                     }
                 }
+                if (te == 0) REC_STAMP(10);
             }
         }
     }
@@ -313,6 +349,20 @@ int make_map_2d(CUtensorMap* m, const void* ptr, long long cols, long long rows,
     return LAS_OK;
 }
 
+// rank-N bf16 map: dims[0] contiguous; strides_elems[i] = stride of dims[i+1] in elements
+int make_map_nd(CUtensorMap* m, const void* ptr, int rank, const long long* dims_, const long long* strides_elems, const int* box_) {
+    EncodeTiledFn enc = get_encode2();
+    if (!enc) { las_set_error("cuTensorMapEncodeTiled entry point not available"); return LAS_ERR_CUDA; }
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], estr[5];
+    for (int i = 0; i < rank; ++i) { dims[i] = (cuuint64_t)dims_[i]; box[i] = (cuuint32_t)box_[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) strides[i] = (cuuint64_t)strides_elems[i] * 2;
+    CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { las_set_error("cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, (int)rc); return LAS_ERR_CUDA; }
+    return LAS_OK;
+}
+
 struct Plan { int rs, nslices, bsg, chains, Bpad; size_t smem; };
 int make_plan(int B, int H, int ndir, Plan* p) {
     LAS_CHECK_ARG(H % 64 == 0 && H >= 64, "lstm_rec_tc: hidden size %d must be a multiple of 64", H);
@@ -332,6 +382,10 @@ int make_plan(int B, int H, int ndir, Plan* p) {
 }
 
 }  // namespace
+
+static long long* g_rec_dbg = nullptr;
+// debug aid: device buffer of 256*16 long long receiving clock64 stamps of CTA (0,0,0) of the next forward launches
+extern "C" void las_lstm_rec_tc_set_debug(void* dev_buf) { g_rec_dbg = (long long*)dev_buf; }
 
 extern "C" int las_lstm_rec_tc_supported(int B, int H, int ndir) {
     Plan p;
@@ -368,13 +422,18 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
     RecTcArgs a{};
     a.gates = gates; a.lens = lens; a.mask = drop_mask; a.out = out; a.hs_pad = hs_pad; a.cs_pad = cs_pad;
     a.ctr = (unsigned*)ws; a.hbuf = (__nv_bfloat16*)((char*)ws + 1024);
-    a.B = B; a.T = T; a.H = H; a.ndir = ndir; a.nslices = p.nslices; a.Bpad = p.Bpad; a.chains = p.chains; a.bsg = p.bsg; a.save = save_gates;
+    a.B = B; a.T = T; a.H = H; a.ndir = ndir; a.nslices = p.nslices; a.Bpad = p.Bpad; a.chains = p.chains; a.bsg = p.bsg; a.save = save_gates; a.dbg = g_rec_dbg;
     LAS_CHECK_ARG((size_t)ndir * p.nslices * sizeof(unsigned) <= 1024, "lstm_rec_fwd_tc: too many batch slices");
     CUtensorMap tmW, tmH;
     rc = make_map_2d(&tmW, w_hh_bf16, H, (long long)ndir * 4 * H, 64, 32);
     if (rc) return rc;
-    rc = make_map_2d(&tmH, a.hbuf, H, (long long)ndir * 2 * p.Bpad, 64, 32);
-    if (rc) return rc;
+    {   // h exchange buffer viewed as (64 k, rows, H/64 k-blocks): one box = the whole 32 x H slice in k-block-major smem order
+        const long long dims[3] = {64, (long long)ndir * 2 * p.Bpad, H / 64};
+        const long long strides[2] = {H, 64};
+        const int box[3] = {64, NB_SLICE, H / 64};
+        rc = make_map_nd(&tmH, a.hbuf, 3, dims, strides, box);
+        if (rc) return rc;
+    }
     LAS_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     LAS_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
     LasProfScope prof(LAS_PROF_REC_FWD, stream, (double)T);
@@ -406,13 +465,6 @@ struct RecTcBwdArgs {
     unsigned* ctr;
     int B, T, H, ndir, nslices, chains, bsg, KBr, CH;
 };
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
 
 constexpr uint32_t IDESC_BWD = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UNITS >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
 constexpr int BWD_STAGES = 2;
@@ -474,9 +526,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_tc_kernel(const __gr
                     for (int ch = 0; ch < NCHUNK; ++ch) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         mbar_arrive_expect_tx(full_bar(stage), (uint32_t)CH * 4096u);
-                        for (int kl = 0; kl < CH; ++kl)
-                            tma_load_3d(a_sm + (stage * CH + kl) * 4096, &tmG, full_bar(stage), dir * G4 + (ch * CH + kl) * 64, t_prev,
-                                        slice * NB_SLICE);
+                        // box (64, 32 batch rows, CH k-blocks, 1 timestep): one issue per chunk
+                        tma_load_4d(a_sm + stage * CH * 4096, &tmG, full_bar(stage), 0, slice * NB_SLICE, dir * KBr + ch * CH, t_prev);
                         if (++stage == BWD_STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -514,16 +565,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_tc_kernel(const __gr
         const int te = (warp - 4) * 32 + lane;
         const int u = r * UNITS + j;
         float dcst[MAX_CHAINS][8];
+        int lenr[MAX_CHAINS][8];
 #pragma unroll
         for (int c = 0; c < MAX_CHAINS; ++c)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dcst[c][i] = 0.f;
+            for (int i = 0; i < 8; ++i) {
+                dcst[c][i] = 0.f;
+                const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
+                lenr[c][i] = (c < a.chains && sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
+            }
         for (int s = 0; s < T; ++s) {
             const int t = (dir == 0) ? (T - 1 - s) : s;
             const int fprev = (dir == 0) ? t : t + 2, fcur = t + 1;
-            for (int c = 0; c < a.chains; ++c) {
+#pragma unroll
+            for (int c = 0; c < MAX_CHAINS; ++c) {
                 const int slice = sg + c * a.bsg;
-                if (slice >= a.nslices) continue;
+                if (c >= a.chains || slice >= a.nslices) continue;
                 const int b0 = slice * NB_SLICE;
                 // operands of the pointwise backward, issued before waiting on the tensor pipe
                 float gi[8], gf[8], gg[8], go[8], ct[8], cp[8], dh[8];
@@ -531,7 +588,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_tc_kernel(const __gr
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int b = b0 + q * 8 + i;
-                    valid[i] = (b < a.B) && (t < a.lens[b]);
+                    valid[i] = t < lenr[c][i];
                     if (valid[i]) {
                         const float* gp = a.gates + (((long long)b * T + t) * a.ndir + dir) * G4 + u;
                         gi[i] = gp[0]; gf[i] = gp[H]; gg[i] = gp[2 * H]; go[i] = gp[3 * H];
@@ -603,18 +660,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_tc_kernel(const __gr
     }
 }
 
-int make_map_3d(CUtensorMap* m, const void* ptr, long long d0, long long d1, long long d2, long long s1, long long s2, int b0, int b1, int b2) {
-    EncodeTiledFn enc = get_encode2();
-    if (!enc) { las_set_error("cuTensorMapEncodeTiled entry point not available"); return LAS_ERR_CUDA; }
-    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
-    cuuint64_t strides[2] = {(cuuint64_t)s1 * 2, (cuuint64_t)s2 * 2};
-    cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) { las_set_error("cuTensorMapEncodeTiled (3d) failed (%d)", (int)rc); return LAS_ERR_CUDA; }
-    return LAS_OK;
-}
 
 // dst[b][c][r] (bf16) = src[b][r][c] (fp32): W_hh (ndir, 4H, H) -> W_hh^T (ndir, H, 4H)
 __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols) {
@@ -664,8 +709,13 @@ extern "C" int las_lstm_rec_bwd_tc(const float* dout, float* gates, void* dgates
     CUtensorMap tmWt, tmG;
     rc = make_map_2d(&tmWt, w_hh_t_bf16, 4LL * H, (long long)ndir * H, 64, 32);
     if (rc) return rc;
-    rc = make_map_3d(&tmG, dgates_bf16, NG, T, B, NG, (long long)T * NG, 64, 1, 32);
-    if (rc) return rc;
+    {   // dG (B*T, NG) viewed as (64 r, B rows [stride T*NG], NG/64 k-blocks [stride 64], T [stride NG])
+        const long long dims[4] = {64, B, NG / 64, T};
+        const long long strides[3] = {(long long)T * NG, 64, NG};
+        const int box[4] = {64, NB_SLICE, a.CH, 1};
+        rc = make_map_nd(&tmG, dgates_bf16, 4, dims, strides, box);
+        if (rc) return rc;
+    }
     LAS_CUDA(cudaFuncSetAttribute(lstm_rec_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAS_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
     LasProfScope prof(LAS_PROF_REC_BWD, stream, (double)T);

@@ -57,6 +57,8 @@ class LasAttnStep(C.Structure):
         ('de', C.c_void_p),
         ('B', C.c_int), ('T', C.c_int), ('P', C.c_int), ('heads', C.c_int),
         ('scale', C.c_float),
+        ('ctx2_bf16', C.c_void_p), ('ld_ctx2_bf16', c_ll),
+        ('dq_bf16', C.c_void_p), ('ld_dq_bf16', c_ll),
     ]
 
 
@@ -66,6 +68,7 @@ class LasSpeller(C.Structure):
         ('heads', C.c_int), ('steps', C.c_int),
         ('sos_idx', C.c_int), ('pad_idx', C.c_int),
         ('training', C.c_int),
+        ('use_tc', C.c_int),
         ('emb', C.c_void_p), ('cls_b', C.c_void_p),
         ('w_ih0', C.c_void_p), ('w_hh0', C.c_void_p), ('b_ih0', C.c_void_p), ('b_hh0', C.c_void_p),
         ('w_ih1', C.c_void_p), ('w_hh1', C.c_void_p), ('b_ih1', C.c_void_p), ('b_hh1', C.c_void_p),
@@ -119,6 +122,7 @@ SIGNATURES = {
     'las_lstm_rec_tc_supported': (C.c_int, [C.c_int, C.c_int, C.c_int]),
     'las_lstm_rec_tc_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'las_lstm_rec_fwd_tc': (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    'las_lstm_rec_tc_set_debug': (None, [C.c_void_p]),
     'las_lstm_rec_bwd_tc': (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'las_transpose_cast_bf16': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'las_attn_step_fwd_f32': (C.c_int, [C.POINTER(LasAttnStep), C.c_void_p]),

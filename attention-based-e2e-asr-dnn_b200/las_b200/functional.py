@@ -389,7 +389,7 @@ SPELLER_PARAM_ORDER = ('emb', 'cls_b', 'w_ih0', 'w_hh0', 'b_ih0', 'b_hh0', 'w_ih
                        'init_query')
 
 
-def _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training):
+def _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, use_tc=False):
     Bn, T, P = K.shape
     emb = params[0]
     s = LasSpeller()
@@ -401,6 +401,7 @@ def _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, 
     s.heads, s.steps = int(heads), int(steps)
     s.sos_idx, s.pad_idx = int(sos_idx), int(pad_idx)
     s.training = int(training)
+    s.use_tc = int(use_tc and s.P % 8 == 0 and s.DH % 8 == 0 and s.DO % 8 == 0)
     for name, t in zip(SPELLER_PARAM_ORDER, params):
         setattr(s, name, t.data_ptr())
     s.K, s.V_, s.enc_lens = K.data_ptr(), V.data_ptr(), enc_lens.data_ptr()
@@ -430,7 +431,8 @@ class SpellerFunction(torch.autograd.Function):
                 dec_y = dec_y.contiguous()
         drop0 = _f32c(drop0) if drop0 is not None else None
         drop1 = _f32c(drop1) if drop1 is not None else None
-        s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training)
+        use_tc = use_tensor_cores() and os.environ.get('LAS_DEC_TC', '1') == '1'
+        s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, use_tc)
         logits = torch.empty(Bn, steps, Vn, dtype=torch.float32, device=dev)
         att0 = torch.empty(steps + 1, heads, T, dtype=torch.float32, device=dev)
         chars = torch.zeros(steps, Bn, dtype=torch.int32, device=dev)
@@ -443,7 +445,7 @@ class SpellerFunction(torch.autograd.Function):
         check(lib.las_speller_fwd_f32(C.byref(s), stream_ptr()), 'speller_fwd')
         if training:
             ctx.save_for_backward(K, V, enc_lens, dec_y, drop0, drop1, fws, iws, *params)
-            ctx.cfg = (use_gold, steps, heads, sos_idx, pad_idx)
+            ctx.cfg = (use_gold, steps, heads, sos_idx, pad_idx, use_tc)
         ctx.mark_non_differentiable(att0, chars)
         return logits, att0, chars
 
@@ -451,8 +453,8 @@ class SpellerFunction(torch.autograd.Function):
     def backward(ctx, dlogits, _datt, _dchars):
         lib = _lib.load()
         K, V, enc_lens, dec_y, drop0, drop1, fws, iws, *params = ctx.saved_tensors
-        use_gold, steps, heads, sos_idx, pad_idx = ctx.cfg
-        s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, True)
+        use_gold, steps, heads, sos_idx, pad_idx, use_tc = ctx.cfg
+        s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, True, use_tc)
         s.fws, s.fws_floats, s.iws, s.iws_ints = fws.data_ptr(), fws.numel(), iws.data_ptr(), iws.numel()
         # outputs of fwd are not needed by bwd but the descriptor check wants non-null
         dummy = torch.empty(1, dtype=torch.int32, device=K.device)

@@ -129,6 +129,8 @@ size_t las_lstm_rec_tc_workspace_bytes(int B, int H, int ndir);
 int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const int* lens, const float* drop_mask, float* out, float* hs_pad,
                         float* cs_pad, int B, int T, int H, int ndir, int save_gates, void* ws, size_t ws_bytes, void* stream);
 
+/* debug aid: device buffer (256*16 long long) receiving clock64 stamps of CTA (0,0,0) per timestep; NULL disables */
+void las_lstm_rec_tc_set_debug(void* dev_buf);
 /* BPTT on the tensor pipe.  w_hh_t_bf16 = W_hh transposed per direction, (ndir, H, 4H) bf16 (las_transpose_cast_bf16).
  * gates: in activated gates, out fp32 d(pre-activation); dgates_bf16 (B*T, ndir*4H): the same values as bf16, written
  * for every (b, t) (zeros at t >= len) -- the operand of the dX / dW_ih / dW_hh tensor-core GEMMs. */
@@ -158,6 +160,8 @@ typedef struct {
     float* de;
     int B, T, P, heads;
     float scale;
+    void* ctx2_bf16; long long ld_ctx2_bf16;   /* fwd: optional bf16 copy of the context (next cell-0 GEMM operand) */
+    void* dq_bf16; long long ld_dq_bf16;       /* bwd: optional bf16 copy of the total dq */
 } LasAttnStep;
 int las_attn_step_fwd_f32(const LasAttnStep* desc, void* stream);
 int las_attn_step_bwd_f32(const LasAttnStep* desc, void* stream);
@@ -183,6 +187,7 @@ typedef struct {
     int B, T, P, E, DH, DO, V, heads, steps;
     int sos_idx, pad_idx;
     int training;                 /* 1: save history for backward */
+    int use_tc;                   /* 1: decoder GEMMs as bf16 tcgen05 tiles (AMP mode); fwd and bwd must agree */
     /* parameters */
     const float* emb;             /* (V, E)  char_emb.weight == cls.weight */
     const float* cls_b;           /* (V) */
