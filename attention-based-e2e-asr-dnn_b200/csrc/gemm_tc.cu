@@ -26,7 +26,9 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;       // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_LD = 36;                          // floats per staged row (144 B: 16-byte aligned, conflict-free STS.128/LDS.128)
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;      // one 32x32 fp32 transpose tile per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 constexpr int NTHREADS = 256;
 constexpr int TMEM_COLS = 512;
 
@@ -45,6 +47,9 @@ struct TcArgs {
     int KB;           // batches in the K direction (wgrad: B of (b,t) rows; else 1)
     int accumulate;   // C += result
     const int* lens;  // optional (NB): skip M tiles whose first row >= lens[b] (rows past a sequence's length)
+    int splitk;       // >1: the K range of every output tile is split over `splitk` CTAs writing partials to Cpart
+    float* Cpart;     // (splitk, R, ldp) partial sums
+    long long ldp;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
@@ -164,18 +169,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int total_tiles = g.NB * g.mt_per_b * g.nt;
-    const int kiters = g.KB * g.kt_per_b;
+    const int splitk = g.splitk > 1 ? g.splitk : 1;
+    const int total_tiles = g.NB * g.mt_per_b * g.nt * splitk;
+    const int kiters_all = g.KB * g.kt_per_b;
+    float* epi_sm = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += gridDim.x) {
+                const int split = tile0 % splitk, tile = tile0 / splitk;
                 const int ntile = tile % g.nt, mrem = tile / g.nt;
                 const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b;
                 if (g.lens && mtile * BM >= g.lens[b]) continue;
-                for (int kit = 0; kit < kiters; ++kit) {
+                const int k_lo = (int)((long long)kiters_all * split / splitk), k_hi = (int)((long long)kiters_all * (split + 1) / splitk);
+                for (int kit = k_lo; kit < k_hi; ++kit) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
                     mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
@@ -204,14 +213,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
             constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t accphase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += gridDim.x) {
+                const int split = tile0 % splitk, tile = tile0 / splitk;
                 const int mrem = tile / g.nt;
                 const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b;
                 if (g.lens && mtile * BM >= g.lens[b]) continue;
+                const int k_lo = (int)((long long)kiters_all * split / splitk), k_hi = (int)((long long)kiters_all * (split + 1) / splitk);
                 mbar_wait(tempty_bar(acc), accphase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kit = 0; kit < kiters; ++kit) {
+                for (int kit = k_lo; kit < k_hi; ++kit) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
@@ -219,7 +230,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t ad = A_MN ? make_desc(sa + k * 2048, 8192, 1024) : make_desc(sa + k * 32, 16, 1024);
                         const uint64_t bd = B_MN ? make_desc(sb + k * 2048, 8192, 1024) : make_desc(sb + k * 32, 16, 1024);
-                        umma_bf16(d_tmem, ad, bd, idesc, (kit | k) ? 1u : 0u);
+                        umma_bf16(d_tmem, ad, bd, idesc, ((kit - k_lo) | k) ? 1u : 0u);
                     }
                     umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -229,45 +240,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> (+bias, +C) -> global =====
+        // ===== epilogue: TMEM -> registers -> smem transpose -> (+bias, +C) -> 128-byte coalesced global stores =====
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        float* tileS = epi_sm + q * 32 * EPI_LD;
         int acc = 0; uint32_t accphase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += gridDim.x) {
+            const int split = tile0 % splitk, tile = tile0 / splitk;
             const int ntile = tile % g.nt, mrem = tile / g.nt;
             const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b;
             if (g.lens && mtile * BM >= g.lens[b]) continue;
             mbar_wait(tfull_bar(acc), accphase);
             tc_fence_after();
-            const int r = mtile * BM + q * 32 + lane;
-            const bool row_ok = r < g.R;
-            float* crow = g.C + (long long)b * g.c_bs + (long long)r * g.ldc;
+            const int r0 = mtile * BM + q * 32;                     // first row of this warp's 32-row band
+            float* cbase;
+            long long ldo;
+            if (splitk > 1) { cbase = g.Cpart + (long long)split * g.R * g.ldp; ldo = g.ldp; }
+            else { cbase = g.C + (long long)b * g.c_bs; ldo = g.ldc; }
+            const bool plain = splitk > 1;                          // partials carry no bias / accumulate
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
                 const int n0 = ntile * BN + c * 32;
-                if (row_ok && n0 < g.N) {
-                    if (n0 + 32 <= g.N) {
+                if (n0 >= g.N) continue;                            // warp-uniform
+                // stage: thread `lane` owns row r0+lane -> tileS[lane][0..31]
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                                   __uint_as_float(v[j + 3]));
-                            if (g.bias1) { const float4 bb = *reinterpret_cast<const float4*>(g.bias1 + n0 + j); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
-                            if (g.bias2) { const float4 bb = *reinterpret_cast<const float4*>(g.bias2 + n0 + j); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
-                            float4* dst = reinterpret_cast<float4*>(crow + n0 + j);
-                            if (g.accumulate) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(tileS + lane * EPI_LD + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                __syncwarp();
+                // drain: each instruction writes 4 rows x 128 contiguous bytes
+                const int cq = (lane & 7) * 4, rsub = lane >> 3;
+                const int n = n0 + cq;
+                if (n0 + 32 <= g.N) {
+                    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!plain && g.bias1) { const float4 t = *reinterpret_cast<const float4*>(g.bias1 + n); bb.x += t.x; bb.y += t.y; bb.z += t.z; bb.w += t.w; }
+                    if (!plain && g.bias2) { const float4 t = *reinterpret_cast<const float4*>(g.bias2 + n); bb.x += t.x; bb.y += t.y; bb.z += t.z; bb.w += t.w; }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = i * 4 + rsub;
+                        if (r0 + rr < g.R) {
+                            float4 o = *reinterpret_cast<const float4*>(tileS + rr * EPI_LD + cq);
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                            float4* dst = reinterpret_cast<float4*>(cbase + (long long)(r0 + rr) * ldo + n);
+                            if (!plain && g.accumulate) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
                             *dst = o;
                         }
-                    } else {
-                        for (int j = 0; j < 32 && n0 + j < g.N; ++j) {
-                            float o = __uint_as_float(v[j]);
-                            if (g.bias1) o += g.bias1[n0 + j];
-                            if (g.bias2) o += g.bias2[n0 + j];
-                            if (g.accumulate) o += crow[n0 + j];
-                            crow[n0 + j] = o;
+                    }
+                } else {
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = i * 4 + rsub;
+                        if (r0 + rr >= g.R) continue;
+                        for (int e = 0; e < 4 && n + e < g.N; ++e) {
+                            float o = tileS[rr * EPI_LD + cq + e];
+                            if (!plain && g.bias1) o += g.bias1[n + e];
+                            if (!plain && g.bias2) o += g.bias2[n + e];
+                            float* dst = cbase + (long long)(r0 + rr) * ldo + n + e;
+                            if (!plain && g.accumulate) o += *dst;
+                            *dst = o;
                         }
                     }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -320,6 +354,26 @@ int make_map(CUtensorMap* m, const void* ptr, long long d0, long long d1, long l
     return LAS_OK;
 }
 
+// C[m][n] (+)= sum_s part[s][m][n] (+ biases): deterministic split-K reduction
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, long long ldp, int splitk, int R, int N, float* __restrict__ C,
+                                                            long long ldc, const float* __restrict__ bias1, const float* __restrict__ bias2,
+                                                            int accumulate) {
+    const long long total = (long long)R * (N / 4);
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int m = (int)(i / (N / 4)), n = (int)(i % (N / 4)) * 4;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sidx = 0; sidx < splitk; ++sidx) {
+            const float4 t = *reinterpret_cast<const float4*>(part + ((long long)sidx * R + m) * ldp + n);
+            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+        }
+        if (bias1) { o.x += bias1[n]; o.y += bias1[n + 1]; o.z += bias1[n + 2]; o.w += bias1[n + 3]; }
+        if (bias2) { o.x += bias2[n]; o.y += bias2[n + 1]; o.z += bias2[n + 2]; o.w += bias2[n + 3]; }
+        float4* dst = reinterpret_cast<float4*>(C + (long long)m * ldc + n);
+        if (accumulate) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+        *dst = o;
+    }
+}
+
 template <bool A_MN, bool B_MN>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, cudaStream_t st) {
     auto kern = gemm_bf16_tc_kernel<A_MN, B_MN>;
@@ -328,7 +382,7 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, cud
         LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    const int total = g.NB * g.mt_per_b * g.nt;
+    const int total = g.NB * g.mt_per_b * g.nt * (g.splitk > 1 ? g.splitk : 1);
     int grid = las_device_info()->num_sms;
     if (grid > total) grid = total;
     kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, g);
@@ -350,7 +404,7 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
     TcArgs g{};
     g.C = d->C; g.bias1 = d->bias1; g.bias2 = d->bias2; g.c_bs = d->c_bs; g.ldc = d->ldc;
     g.N = d->N; g.nt = ceil_div(d->N, BN); g.accumulate = d->accumulate; g.lens = d->lens;
-    const double flops = 2.0 * d->M * (double)d->N * d->K * d->a_batches * d->k_batches;
+    const double flops = d->prof_flops > 0 ? d->prof_flops : 2.0 * d->M * (double)d->N * d->K * d->a_batches * d->k_batches;
     LasProfScope prof(d->prof_tag == 1 ? LAS_PROF_GEMM_GATES : LAS_PROF_GEMM_OTHER, stream, flops);
     if (!d->a_mn_major) {
         // A: (K contiguous, M rows [stride a_s1], a_batches [stride a_s2]); reduction is a single K range
@@ -375,6 +429,17 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
     if (rc) return rc;
     g.R = d->M; g.NB = 1; g.mt_per_b = ceil_div(d->M, BM); g.kt_per_b = ceil_div(d->K, BK); g.KB = d->k_batches;
     g.lens = nullptr;
+    if (d->splitk > 1) {
+        LAS_CHECK_ARG(d->workspace != nullptr && d->N % 4 == 0, "gemm_tc: split-K needs a workspace and N %% 4 == 0");
+        g.splitk = d->splitk; g.Cpart = d->workspace; g.ldp = (d->N + 3) & ~3;
+        rc = launch_tc<true, true>(ta, tb, g, st);
+        if (rc) return rc;
+        const long long total = (long long)d->M * (d->N / 4);
+        int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+        splitk_reduce_kernel<<<grid, 256, 0, st>>>(g.Cpart, g.ldp, g.splitk, d->M, d->N, d->C, d->ldc, d->bias1, d->bias2, d->accumulate);
+        LAS_LAUNCH_CHECK();
+        return LAS_OK;
+    }
     return launch_tc<true, true>(ta, tb, g, st);
 }
 

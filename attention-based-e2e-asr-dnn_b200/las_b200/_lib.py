@@ -40,6 +40,9 @@ class LasGemmTc(C.Structure):
         ('a_mn_major', C.c_int), ('b_mn_major', C.c_int), ('accumulate', C.c_int),
         ('lens', C.c_void_p),
         ('prof_tag', C.c_int),
+        ('prof_flops', C.c_double),
+        ('splitk', C.c_int),
+        ('workspace', C.c_void_p),
     ]
 
 

@@ -53,7 +53,7 @@ def gemm_raw(A, B, Cout, M, N, K, *, am=(0, 0, 0), ak=(0, 1, 0), bk=(0, 1, 0), b
 
 
 def gemm_tc(A, B, Cout, M, N, K, *, a_batches=1, k_batches=1, a_s1, a_s2=0, b_s1, b_s2=0, c_bs=0, ldc, a_mn=False, b_mn=False,
-            bias1=None, bias2=None, accumulate=False, lens=None, a_off=0, b_off=0, c_off=0, gate=True):
+            bias1=None, bias2=None, accumulate=False, lens=None, a_off=0, b_off=0, c_off=0, gate=True, flops=0.0, splitk=0):
     """las_gemm_bf16_tc wrapper; A/B are bf16 tensors, Cout fp32; *_off are element offsets."""
     d = LasGemmTc()
     d.A = A.data_ptr() + 2 * a_off
@@ -67,6 +67,16 @@ def gemm_tc(A, B, Cout, M, N, K, *, a_batches=1, k_batches=1, a_s1, a_s2=0, b_s1
     d.a_mn_major, d.b_mn_major, d.accumulate = int(a_mn), int(b_mn), int(accumulate)
     d.lens = ptr(lens)
     d.prof_tag = 1 if gate else 0
+    d.prof_flops = float(flops)
+    ws = None
+    if a_mn and splitk == 0:
+        # weight-gradient form: few output tiles, long reduction -> split K so every SM has a tile
+        tiles = ((int(M) + 127) // 128) * ((int(N) + 255) // 256)
+        if tiles < 74 and int(N) % 4 == 0:
+            splitk = max(1, min(16, 148 // tiles, int(k_batches) * ((int(K) + 63) // 64)))
+    if a_mn and splitk > 1:
+        ws = torch.empty(splitk * int(M) * ((int(N) + 3) // 4 * 4), dtype=torch.float32, device=Cout.device)
+        d.splitk, d.workspace = int(splitk), ws.data_ptr()
     check(_lib.load().las_gemm_bf16_tc(C.byref(d), stream_ptr()), 'gemm_bf16_tc')
 
 
@@ -209,7 +219,7 @@ class LSTMLayerFunction(torch.autograd.Function):
             b1 = torch.cat([ws[4 * d + 2] for d in range(ndir)])
             b2 = torch.cat([ws[4 * d + 3] for d in range(ndir)])
             gemm_tc(xb, wcat, gates, T, NG, Kp, a_batches=Bn, a_s1=(2 * Dp if pyramid else Dp), a_s2=Tin * Dp, b_s1=Kp,
-                    c_bs=T * NG, ldc=NG, bias1=b1, bias2=b2, lens=lens_dev)
+                    c_bs=T * NG, ldc=NG, bias1=b1, bias2=b2, lens=lens_dev, flops=2.0 * Bn * T * NG * Din)
         else:
             for d in range(ndir):
                 w_ih, _, b_ih, b_hh = ws[4 * d:4 * d + 4]
@@ -281,17 +291,17 @@ class LSTMLayerFunction(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = torch.zeros(Bn, Tin, D, dtype=torch.float32, device=dev)             # tiles past a row's length are skipped
                 gemm_tc(dGb, wcat, dx, T, Din, NG, a_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=Kp, b_mn=True, c_bs=Tin * D,
-                        ldc=Din, lens=lens_dev)
+                        ldc=Din, lens=lens_dev, flops=2.0 * Bn * T * NG * Din)
             dwcat = torch.empty(NG, Kp, dtype=torch.float32, device=dev)
             gemm_tc(dGb, xb, dwcat, NG, Kp, T, k_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=(2 * Dp if pyramid else Dp),
-                    b_s2=Tin * Dp, ldc=Kp, a_mn=True, b_mn=True)
+                    b_s2=Tin * Dp, ldc=Kp, a_mn=True, b_mn=True, flops=2.0 * Bn * T * NG * Din)
             hsb = cast_bf16(hs_pad, Bn * (T + 2), F_, F_, F_)                             # (B*(T+2), F) bf16
             for d in range(ndir):
                 dw_ih = dwcat[d * G4:(d + 1) * G4, :Din].contiguous()
                 dw_hh = torch.empty(G4, H, dtype=torch.float32, device=dev)
                 # h_{t-1} for the forward direction is frame t of hs_pad, for the reverse direction frame t+2
                 gemm_tc(dGb, hsb, dw_hh, G4, H, T, k_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=F_, b_s2=(T + 2) * F_, ldc=H,
-                        a_mn=True, b_mn=True, a_off=d * G4, b_off=(2 * F_ if d == 1 else 0) + d * H)
+                        a_mn=True, b_mn=True, a_off=d * G4, b_off=(2 * F_ if d == 1 else 0) + d * H, gate=False)
                 db = torch.empty(G4, dtype=torch.float32, device=dev)
                 colsum(dG, NG, M, G4, db, x_off=d * G4)
                 grads += [dw_ih, dw_hh, db, db.clone()]

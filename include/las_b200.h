@@ -80,7 +80,8 @@ int las_gemm_f32(const LasGemmF32* desc, void* stream);
  *        C row (b, r) at C + b*c_bs + r*ldc ; `lens` (a_batches, nullable) skips 128-row tiles starting at r >= lens[b]
  *   a_mn_major = 1 (weight gradient):  A[kb][k][m] = A + kb*a_s2 + k*a_s1 + m, B[kb][k][n] = B + kb*b_s2 + k*b_s1 + n,
  *        K rows per K-batch, k_batches batches;  C[m][n] = sum_{kb,k} A*B at C + m*ldc + n
- * bias1/bias2 (length N, nullable) are added in the epilogue; accumulate != 0 adds into C. */
+ * bias1/bias2 (length N, nullable) are added in the epilogue; accumulate != 0 adds into C.  Split-K partials are reduced by
+ * a second, deterministic kernel. */
 typedef struct {
     const void* A; const void* B; float* C;
     const float* bias1; const float* bias2;
@@ -91,6 +92,9 @@ typedef struct {
     int a_mn_major, b_mn_major, accumulate;
     const int* lens;
     int prof_tag;
+    double prof_flops;     /* algorithmic FLOPs credited to this launch by las_prof_* (0: 2*M*N*K*batches as launched) */
+    int splitk;            /* weight-gradient form only: > 1 splits the reduction over that many CTAs per output tile */
+    float* workspace;      /* split-K partial sums, >= splitk * M * round_up(N, 4) floats */
 } LasGemmTc;
 int las_gemm_bf16_tc(const LasGemmTc* desc, void* stream);
 /* dst[r][c] (bf16, row stride ld_dst) = c < cols ? srcrow(r)[c] : 0, c < cols_pad; source row r starts at
