@@ -130,10 +130,19 @@ class LinearFunction(torch.autograd.Function):
             M = x.shape[0]
             am = (0, K, 0)
             out = torch.empty(*x.shape[:-1], N, dtype=torch.float32, device=x.device)
-        gemm_raw(x, weight, out, M, N, K, am=am, ak=(0, 1, 0), bk=(0, 1, 0), bn=K, cm=(0, N, 0),
-                 bias1=_f32c(bias) if bias is not None else None, bias2=_f32c(bias2) if bias2 is not None else None)
-        ctx.save_for_backward(x, weight)
-        ctx.am, ctx.M, ctx.has_bias, ctx.has_bias2 = am, M, bias is not None, bias2 is not None
+        b1 = _f32c(bias) if bias is not None else None
+        b2 = _f32c(bias2) if bias2 is not None else None
+        tc = use_tensor_cores() and K % 8 == 0 and N % 4 == 0 and M >= 64
+        if tc:
+            # AMP mode: bf16 operands on the tensor pipe, fp32 accumulate / output
+            xb = cast_bf16(x, M, K, K, am[1], inner=am[2], bs=am[0])          # (M, K) bf16 compact
+            wb = cast_bf16(weight, N, K, K, K)
+            gemm_tc(xb, wb, out, M, N, K, a_s1=K, b_s1=K, ldc=N, bias1=b1, bias2=b2, gate=False)
+            ctx.save_for_backward(xb, wb)
+        else:
+            gemm_raw(x, weight, out, M, N, K, am=am, ak=(0, 1, 0), bk=(0, 1, 0), bn=K, cm=(0, N, 0), bias1=b1, bias2=b2)
+            ctx.save_for_backward(x, weight)
+        ctx.am, ctx.M, ctx.has_bias, ctx.has_bias2, ctx.tc, ctx.xshape = am, M, bias is not None, bias2 is not None, tc, tuple(x.shape)
         return out
 
     @staticmethod
@@ -143,22 +152,31 @@ class LinearFunction(torch.autograd.Function):
         M, am = ctx.M, ctx.am
         dy = _f32c(dy)
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty(x.shape, dtype=torch.float32, device=x.device)
-            gemm_raw(dy, weight, dx, M, K, N, am=(0, N, 0), ak=(0, 1, 0), bk=(0, K, 0), bn=1, cm=(0, K, 0))
-        if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(weight)
-            # dW[n][k] = sum_m dy[m][n] x[m][k]
-            gemm_raw(dy, x, dw, N, K, M, am=(0, 1, 0), ak=(0, N, 0), bk=am, bn=1, cm=(0, K, 0))
+        if ctx.tc:
+            dyb = cast_bf16(dy, M, N, N, N)
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(ctx.xshape, dtype=torch.float32, device=dy.device)
+                gemm_tc(dyb, weight, dx, M, K, N, a_s1=N, b_s1=K, b_mn=True, ldc=K, gate=False)
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+                gemm_tc(dyb, x, dw, N, K, M, a_s1=N, b_s1=K, ldc=K, a_mn=True, b_mn=True, gate=False)
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+                gemm_raw(dy, weight, dx, M, K, N, am=(0, N, 0), ak=(0, 1, 0), bk=(0, K, 0), bn=1, cm=(0, K, 0))
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty_like(weight)
+                # dW[n][k] = sum_m dy[m][n] x[m][k]
+                gemm_raw(dy, x, dw, N, K, M, am=(0, 1, 0), ak=(0, N, 0), bk=am, bn=1, cm=(0, K, 0))
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.empty(N, dtype=torch.float32, device=x.device)
+            db = torch.empty(N, dtype=torch.float32, device=dy.device)
             colsum(dy, N, M, N, db)
         db2 = None
         if ctx.has_bias2 and ctx.needs_input_grad[3]:
             if db is not None:
                 db2 = db.clone()
             else:
-                db2 = torch.empty(N, dtype=torch.float32, device=x.device)
+                db2 = torch.empty(N, dtype=torch.float32, device=dy.device)
                 colsum(dy, N, M, N, db2)
         return dx, dw, db, db2
 
@@ -239,8 +257,8 @@ class LSTMLayerFunction(torch.autograd.Function):
             nbytes = lib.las_lstm_rec_tc_workspace_bytes(Bn, H, ndir)
             wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             check(lib.las_lstm_rec_fwd_tc(gates.data_ptr(), w_hh_b.data_ptr(), lens_dev.data_ptr(), ptr(mask), ptr(out),
-                                          hs_pad.data_ptr(), cs_pad.data_ptr(), Bn, T, H, ndir, 1, wsb.data_ptr(), nbytes,
-                                          stream_ptr()), 'lstm_rec_fwd_tc')
+                                          hs_pad.data_ptr(), cs_pad.data_ptr(), Bn, T, H, ndir, int(any(ctx.needs_input_grad)), wsb.data_ptr(),
+                                          nbytes, stream_ptr()), 'lstm_rec_fwd_tc')
         else:
             nbytes = lib.las_lstm_rec_workspace_bytes(Bn, H, ndir)
             wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)

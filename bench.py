@@ -45,7 +45,9 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help="bf16: the AMP path (gate GEMMs on the tensor pipe, like the reference's autocast runs); fp32: parity mode")
-    ap.add_argument('--greedy', action='store_true', help='also report greedy-decode chars/s (configs[3]) as an extra key')
+    ap.add_argument('--no-greedy', action='store_true', help='skip the greedy-decode leg (BASELINE configs[3]) reported under "greedy"')
+    ap.add_argument('--greedy-batch', type=int, default=256)
+    ap.add_argument('--greedy-T', type=int, default=3000)
     return ap.parse_args()
 
 
@@ -255,6 +257,51 @@ def main():
     e2e_value = world * B / (ms_e2e / 1e3)
     h2d = x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()
 
+    # ---- greedy decoding (BASELINE configs[3]): eval mode, CHR_MAX_STEPS = 600 steps always (src/models.py:315), no collective ----
+    greedy = None
+    if not args.no_greedy:
+        del x_dev, y_dev
+        reducer.zero_grad()
+        torch.cuda.empty_cache()
+        Bg, Tg = args.greedy_batch, args.greedy_T
+        xg_np, lxg_np, _ = gu.make_inputs(4242 + rank, Bg, Tg, 4)
+        xg_host = torch.from_numpy(xg_np).pin_memory()
+        xg = xg_host.to(dev)
+        lxg = torch.from_numpy(lxg_np)
+        model.eval()
+        steps_g = cfg['speller_configs']['CHR_MAX_STEPS']
+
+        def decode(xin):
+            with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16, enabled=(args.precision == 'bf16')):
+                lg, _ = model(xin, lxg)
+            return lg
+        for _ in range(2):
+            decode(xg)
+        lib.las_prof_reset()
+        lib.las_prof_enable((1 << 4) if rank == 0 else 0)
+        n_g = 3
+        ms_g = timed(lambda: decode(xg), n_g) / n_g
+        lib.las_prof_enable(0)
+        ga = dict(ms=0.0, n=0, work=0.0)
+        if rank == 0:
+            import ctypes as C2
+            ms_, n_, w_ = C2.c_double(), C2.c_longlong(), C2.c_double()
+            _lib.check(lib.las_prof_collect(4, C2.byref(ms_), C2.byref(n_), C2.byref(w_)), 'prof_collect')
+            ga = dict(ms=ms_.value, n=n_.value, work=w_.value)
+            lib.las_prof_reset()
+
+        def decode_e2e():
+            lg = decode(xg_host.to(dev, non_blocking=True))
+            return lg.argmax(-1).to(torch.int16).cpu()        # transcripts back on the host
+        decode_e2e()
+        ms_ge = timed(decode_e2e, 2) / 2
+        greedy = dict(metric='las_greedy_decode_chars_per_sec', value=world * Bg * steps_g / (ms_g / 1e3), unit='chars/s',
+                      ms_per_batch=ms_g, e2e_value=world * Bg * steps_g / (ms_ge / 1e3),
+                      config=dict(workload=f'{args.config} base-LAS greedy decode, batch {Bg}/GPU, T={Tg}, {steps_g} steps (CHR_MAX_STEPS), eval mode'),
+                      attn_step=dict(us_per_launch=1e3 * ga['ms'] / max(ga['n'], 1), bytes_per_launch=ga['work'] / max(ga['n'], 1),
+                                     gbs=(ga['work'] / 1e9) / (ga['ms'] / 1e3) if ga['ms'] > 0 else 0.0))
+        model.train()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -290,7 +337,7 @@ def main():
                            l2_policy='inputs+activations per step (>2.5 GB) exceed the 126 MB L2; no explicit flush'),
                clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e),
                gpu_launches=int(launches), roofline=roofline, attn_roofline=attn_roofline, recurrence=rec,
-               kernel_ms_per_step={k: round(v['ms_per_step'], 3) for k, v in prof.items()}, cpu_baseline=cpu)
+               kernel_ms_per_step={k: round(v['ms_per_step'], 3) for k, v in prof.items()}, greedy=greedy, cpu_baseline=cpu)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
