@@ -225,11 +225,29 @@ int tc_nn(cudaStream_t st, const __nv_bfloat16* A, long long lda, const __nv_bfl
     return las_gemm_bf16_tc(&d, st);
 }
 int tc_tn(cudaStream_t st, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb, float* C, long long ldc, int M, int N,
-          int K) {
+          int K, float* skws = nullptr, size_t skws_floats = 0) {
     LasGemmTc d{};
     d.A = A; d.B = B; d.C = C; d.M = M; d.N = N; d.K = K; d.a_batches = 1; d.k_batches = 1;
     d.a_s1 = lda; d.b_s1 = ldb; d.ldc = ldc; d.a_mn_major = 1; d.b_mn_major = 1;
+    // few output tiles, long reduction (K = steps*B): split K across SMs when a workspace is available
+    const int tiles = ceil_div(M, 128) * ceil_div(N, 256);
+    if (skws && tiles < 74 && N % 4 == 0) {
+        int sk = 148 / tiles;
+        if (sk > 16) sk = 16;
+        const int kiters = ceil_div(K, 64);
+        if (sk > kiters) sk = kiters;
+        while (sk > 1 && (size_t)sk * M * N > skws_floats) --sk;
+        if (sk > 1) { d.splitk = sk; d.workspace = skws; }
+    }
     return las_gemm_bf16_tc(&d, st);
+}
+
+// oh[r][v] = (tok[r] == v), v < 32: one-hot rows so that the token-wise scatter-reduce becomes a tensor-core GEMM
+__global__ void __launch_bounds__(256) onehot_kernel(const int* __restrict__ tok, __nv_bfloat16* __restrict__ oh, int rows) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= rows * 32) return;
+    const int r = i >> 5, v = i & 31;
+    oh[i] = __float2bfloat16(tok[r] == v ? 1.f : 0.f);
 }
 int cast_rows(cudaStream_t st, const float* src, long long ld_src, __nv_bfloat16* dst, long long ld_dst, long long rows, int cols) {
     return las_cast_f32_to_bf16(src, ld_src, 0, 0, dst, ld_dst, rows, cols, cols, st);
@@ -239,7 +257,8 @@ struct Layout {
     // float workspace offsets
     size_t Wcat0, Wcat1, Gemb, S0, S1, C0, C1, G0, G1, QC, W, dQC, dS0, dS1, dc0, dc1, dh1, DE, dGemb, tmpq, cs_scratch, total_f;
     // bf16 region (offsets in floats, buffers hold bf16): tensor-pipe mode only
-    size_t Wcat0b, Wcat1b, Wqb, S0b, S1b, G0b, G1b, dQb;
+    size_t Wcat0b, Wcat1b, Wqb, S0b, S1b, G0b, G1b, dQb, dlb, ohb, QCb, tmp32, skws;
+    size_t skws_floats;
     // int workspace offsets
     size_t tok, total_i;
     int hist, ghist;
@@ -289,6 +308,14 @@ Layout make_layout(const LasSpeller* s) {
             L.G0b = takeb(S * B * 4 * DH);
             L.G1b = takeb(S * B * 4 * DO);
             L.dQb = takeb((S + 1) * B * P);
+            if (V <= 32) {      // padded-to-32 one-hot / dlogits operands for the token-side GEMMs
+                L.dlb = takeb(S * B * 32);
+                L.ohb = takeb(S * B * 32);
+                L.QCb = takeb(S * B * 2 * P);
+                L.tmp32 = take(32 * 4 * DH > 32 * 2 * P ? 32 * 4 * DH : 32 * 2 * P);
+                L.skws_floats = (size_t)16 * 4 * DH * (P + DH);
+                L.skws = take(L.skws_floats);
+            }
         }
     }
     L.total_f = o;
@@ -526,8 +553,17 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
         d.alpha = 1.f; d.beta = 0.f;
         RC(las_gemm_f32(&d, st));
     }
+    __nv_bfloat16 *dlb = (__nv_bfloat16*)(f + L.dlb), *ohb = (__nv_bfloat16*)(f + L.ohb), *QCb = (__nv_bfloat16*)(f + L.QCb);
+    float *tmp32 = f + L.tmp32, *skws = f + L.skws;
+    const bool tc_tok = tc && V <= 32;
     // tied classifier weight: d_emb = dlogits^T . QC[1..S]
-    {
+    if (tc_tok) {
+        // (S*B, 32) bf16 zero-padded dlogits in (t, b) row order and bf16 QC rows -> one split-K tensor-core GEMM
+        RC(las_cast_f32_to_bf16(g->dlogits, (long long)S * V, B, V, dlb, 32, SB, V, 32, st));
+        RC(cast_rows(st, QC + (size_t)B * 2 * P, 2 * P, QCb, 2 * P, SB, 2 * P));
+        RC(tc_tn(st, dlb, 32, QCb, 2 * P, tmp32, 2 * P, 32, 2 * P, (int)SB, skws, L.skws_floats));
+        LAS_CUDA(cudaMemcpyAsync(g->d_emb, tmp32, (size_t)V * E * fsz, cudaMemcpyDeviceToDevice, st));
+    } else {
         LasGemmF32 d{};
         d.A = g->dlogits; d.B = QC + (size_t)B * 2 * P; d.C = g->d_emb;
         d.M = V; d.N = 2 * P; d.K = (int)SB; d.batch = 1;
@@ -589,7 +625,7 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
 
     // ---- batched parameter gradients ----
     // query_map: rows 1..S see h1_t (S1[t+1] slot), row 0 sees init_query
-    if (tc) RC(tc_tn(st, dQb + (size_t)B * P, P, S1b + (size_t)B * K1 + DH, K1, g->d_wq, DO, P, DO, (int)SB));
+    if (tc) RC(tc_tn(st, dQb + (size_t)B * P, P, S1b + (size_t)B * K1 + DH, K1, g->d_wq, DO, P, DO, (int)SB, skws, L.skws_floats));
     else RC(gemm_tn(st, dQC + (size_t)B * 2 * P, 2 * P, S1 + (size_t)B * K1 + DH, K1, g->d_wq, DO, P, DO, (int)SB));
     {
         LasGemmF32 d{};
@@ -604,8 +640,8 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     RC(las_colsum_f32(tmpq, DO, B, DO, g->d_init_query, 0, csw, st));
     // cell 1
     if (tc) {
-        RC(tc_tn(st, G1b, 4 * DO, S1b, K1, g->d_w_ih1, DH, 4 * DO, DH, (int)SB));
-        RC(tc_tn(st, G1b, 4 * DO, S1b + DH, K1, g->d_w_hh1, DO, 4 * DO, DO, (int)SB));
+        RC(tc_tn(st, G1b, 4 * DO, S1b, K1, g->d_w_ih1, DH, 4 * DO, DH, (int)SB, skws, L.skws_floats));
+        RC(tc_tn(st, G1b, 4 * DO, S1b + DH, K1, g->d_w_hh1, DO, 4 * DO, DO, (int)SB, skws, L.skws_floats));
     } else {
         RC(gemm_tn(st, G1, 4 * DO, S1, K1, g->d_w_ih1, DH, 4 * DO, DH, (int)SB));
         RC(gemm_tn(st, G1, 4 * DO, S1 + DH, K1, g->d_w_hh1, DO, 4 * DO, DO, (int)SB));
@@ -614,8 +650,8 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     LAS_CUDA(cudaMemcpyAsync(g->d_b_hh1, g->d_b_ih1, (size_t)4 * DO * fsz, cudaMemcpyDeviceToDevice, st));
     // cell 0: context columns, recurrent weight, biases
     if (tc) {
-        RC(tc_tn(st, G0b, 4 * DH, S0b, K0, g->d_w_ih0 + E, E + P, 4 * DH, P, (int)SB));
-        RC(tc_tn(st, G0b, 4 * DH, S0b + P, K0, g->d_w_hh0, DH, 4 * DH, DH, (int)SB));
+        RC(tc_tn(st, G0b, 4 * DH, S0b, K0, g->d_w_ih0 + E, E + P, 4 * DH, P, (int)SB, skws, L.skws_floats));
+        RC(tc_tn(st, G0b, 4 * DH, S0b + P, K0, g->d_w_hh0, DH, 4 * DH, DH, (int)SB, skws, L.skws_floats));
     } else {
         RC(gemm_tn(st, G0, 4 * DH, S0, K0, g->d_w_ih0 + E, E + P, 4 * DH, P, (int)SB));
         RC(gemm_tn(st, G0, 4 * DH, S0 + P, K0, g->d_w_hh0, DH, 4 * DH, DH, (int)SB));
@@ -623,8 +659,16 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     RC(las_colsum_f32(G0, 4 * DH, (int)SB, 4 * DH, g->d_b_ih0, 0, csw, st));
     LAS_CUDA(cudaMemcpyAsync(g->d_b_hh0, g->d_b_ih0, (size_t)4 * DH * fsz, cudaMemcpyDeviceToDevice, st));
     // cell 0: embedding columns through the token table
-    token_reduce_kernel<<<dim3(ceil_div(4 * DH, 256), V), 256, 0, st>>>(G0, tok, dGemb, (int)SB, 4 * DH);
-    LAS_LAUNCH_CHECK();
+    if (tc_tok) {
+        // dGemb = OneHot(tok)^T . dG0 : the token-wise scatter-reduce as a split-K tensor-core GEMM
+        onehot_kernel<<<ceil_div((int)SB * 32, 256), 256, 0, st>>>(tok, ohb, (int)SB);
+        LAS_LAUNCH_CHECK();
+        RC(tc_tn(st, ohb, 32, G0b, 4 * DH, tmp32, 4 * DH, 32, 4 * DH, (int)SB, skws, L.skws_floats));
+        LAS_CUDA(cudaMemcpyAsync(dGemb, tmp32, (size_t)V * 4 * DH * fsz, cudaMemcpyDeviceToDevice, st));
+    } else {
+        token_reduce_kernel<<<dim3(ceil_div(4 * DH, 256), V), 256, 0, st>>>(G0, tok, dGemb, (int)SB, 4 * DH);
+        LAS_LAUNCH_CHECK();
+    }
     RC(gemm_tn(st, dGemb, 4 * DH, s->emb, E, g->d_w_ih0, E + P, 4 * DH, E, V));
     // embedding rows via lookups: padding_idx row receives no lookup gradient (nn.Embedding(padding_idx), src/models.py:261-265)
     if (s->pad_idx >= 0 && s->pad_idx < V) LAS_CUDA(cudaMemsetAsync(dGemb + (size_t)s->pad_idx * 4 * DH, 0, (size_t)4 * DH * fsz, st));

@@ -21,16 +21,20 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64;
+// BN is a template parameter: 256 for the big gate GEMMs (one tile per SM per wave), 64 for the small decoder GEMMs
+// (M = batch <= 128): four times as many CTAs, a quarter of the MMA + epilogue time per CTA.
+constexpr int BM = 128, BK = 64;
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;       // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_LD = 36;                          // floats per staged row (144 B: 16-byte aligned, conflict-free STS.128/LDS.128)
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;      // one 32x32 fp32 transpose tile per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 constexpr int NTHREADS = 256;
-constexpr int TMEM_COLS = 512;
+template <int BN> struct Cfg {
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;       // 512 or 128: a power of two >= 32
+};
 
 struct TcArgs {
     float* C;
@@ -134,14 +138,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format BF16 [7,10)/[10,13)=1,
 // a_major bit 15, b_major bit 16, n_dim [17,23) = N>>3, m_dim [24,29) = M>>4
-__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(bn >> 3) << 17) |
            ((uint32_t)(BM >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
+    constexpr int STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
+    constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned stage bases
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
-            constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+            constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t accphase = 0;
             for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += gridDim.x) {
@@ -374,9 +380,10 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, cudaStream_t st) {
-    auto kern = gemm_bf16_tc_kernel<A_MN, B_MN>;
+    auto kern = gemm_bf16_tc_kernel<A_MN, B_MN, BN>;
+    constexpr int SMEM_BYTES = Cfg<BN>::SMEM_BYTES;
     static bool attr_set = false;
     if (!attr_set) {
         LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -403,9 +410,14 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
     CUtensorMap ta, tb;
     TcArgs g{};
     g.C = d->C; g.bias1 = d->bias1; g.bias2 = d->bias2; g.c_bs = d->c_bs; g.ldc = d->ldc;
-    g.N = d->N; g.nt = ceil_div(d->N, BN); g.accumulate = d->accumulate; g.lens = d->lens;
+    g.N = d->N; g.accumulate = d->accumulate; g.lens = d->lens;
     const double flops = d->prof_flops > 0 ? d->prof_flops : 2.0 * d->M * (double)d->N * d->K * d->a_batches * d->k_batches;
     LasProfScope prof(d->prof_tag == 1 ? LAS_PROF_GEMM_GATES : LAS_PROF_GEMM_OTHER, stream, flops);
+    // narrow N tiles when the 128x256 tiling would leave most SMs idle (decoder-step GEMMs: M = batch)
+    const long long tiles256 = (long long)ceil_div(d->M, BM) * ceil_div(d->N, 256) * d->a_batches;
+    const bool narrow = tiles256 < 40 && !(d->a_mn_major && d->splitk > 1);
+    const int BNsel = narrow ? 64 : 256;
+    g.nt = ceil_div(d->N, BNsel);
     if (!d->a_mn_major) {
         // A: (K contiguous, M rows [stride a_s1], a_batches [stride a_s2]); reduction is a single K range
         LAS_CHECK_ARG(d->k_batches == 1, "gemm_tc: K-major A cannot have K batches");
@@ -413,13 +425,13 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
         if (rc) return rc;
         g.R = d->M; g.NB = d->a_batches; g.mt_per_b = ceil_div(d->M, BM); g.kt_per_b = ceil_div(d->K, BK); g.KB = 1;
         if (!d->b_mn_major) {
-            rc = make_map(&tb, d->B, d->K, d->N, 1, d->b_s1, 0, BK, BN);           // B: (K contiguous, N rows)
+            rc = make_map(&tb, d->B, d->K, d->N, 1, d->b_s1, 0, BK, BNsel);        // B: (K contiguous, N rows)
             if (rc) return rc;
-            return launch_tc<false, false>(ta, tb, g, st);
+            return narrow ? launch_tc<false, false, 64>(ta, tb, g, st) : launch_tc<false, false, 256>(ta, tb, g, st);
         }
         rc = make_map(&tb, d->B, d->N, d->K, 1, d->b_s1, 0, 64, 64);               // B: (N contiguous, K rows)
         if (rc) return rc;
-        return launch_tc<false, true>(ta, tb, g, st);
+        return narrow ? launch_tc<false, true, 64>(ta, tb, g, st) : launch_tc<false, true, 256>(ta, tb, g, st);
     }
     // A: (M contiguous, K rows [stride a_s1], k_batches [stride a_s2]); B: (N contiguous, K rows [b_s1], k_batches [b_s2])
     LAS_CHECK_ARG(d->b_mn_major && d->a_batches == 1, "gemm_tc: MN-major A needs MN-major B and a single M batch");
@@ -432,7 +444,7 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
     if (d->splitk > 1) {
         LAS_CHECK_ARG(d->workspace != nullptr && d->N % 4 == 0, "gemm_tc: split-K needs a workspace and N %% 4 == 0");
         g.splitk = d->splitk; g.Cpart = d->workspace; g.ldp = (d->N + 3) & ~3;
-        rc = launch_tc<true, true>(ta, tb, g, st);
+        rc = launch_tc<true, true, 256>(ta, tb, g, st);
         if (rc) return rc;
         const long long total = (long long)d->M * (d->N / 4);
         int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
@@ -440,7 +452,7 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
         LAS_LAUNCH_CHECK();
         return LAS_OK;
     }
-    return launch_tc<true, true>(ta, tb, g, st);
+    return narrow ? launch_tc<true, true, 64>(ta, tb, g, st) : launch_tc<true, true, 256>(ta, tb, g, st);
 }
 
 // ---- fp32 -> bf16 cast with optional column padding: dst[r][c] = c < cols ? src[r*ld_src + c] : 0 ---------------------
