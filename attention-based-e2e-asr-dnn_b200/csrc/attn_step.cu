@@ -39,7 +39,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 // phase A: s[t] = scale * dot(vec, M[t]) for t < len, over rows of M (B,T,P) restricted to one head
 // phase C: out[p] = sum_t s2[t] * M2[t][p]
 // Used as fwd (vec=q, M=K, M2=V) and bwd (vec=dctx, M=V, M2=K).
-template <bool BWD>
+template <bool BWD, int RU>
 __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
     extern __shared__ __align__(16) float sm[];
     const int T = a.T, P = a.P, heads = a.heads, d = P / heads;
@@ -78,7 +78,6 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
         }
     }
     // ---- phase A: one warp per row, RU rows in flight per warp (all loads issued before any reduction) ----
-    constexpr int RU = 4;
     for (int t0 = w; t0 < len; t0 += NW * RU) {
         float4 m[RU][MAXCH];
 #pragma unroll
@@ -214,8 +213,14 @@ extern "C" int las_attn_step_fwd_f32(const LasAttnStep* a, void* stream) {
     if (rc) return rc;
     size_t smem = smem_bytes(a);
     LasProfScope prof(LAS_PROF_ATTN_FWD, stream, 2.0 * a->B * (double)a->T * a->P * sizeof(float));
-    if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_step_kernel<false><<<a->B * a->heads, NT, smem, (cudaStream_t)stream>>>(*a);
+    // rows in flight per warp: 8 when the grid leaves SMs idle (train: 96 CTAs), 4 when it over-subscribes them (greedy: 256 CTAs)
+    if (a->B * a->heads >= las_device_info()->num_sms) {
+        if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_step_kernel<false, 4><<<a->B * a->heads, NT, smem, (cudaStream_t)stream>>>(*a);
+    } else {
+        if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_step_kernel<false, 8><<<a->B * a->heads, NT, smem, (cudaStream_t)stream>>>(*a);
+    }
     LAS_LAUNCH_CHECK();
     return LAS_OK;
 }
@@ -227,8 +232,13 @@ extern "C" int las_attn_step_bwd_f32(const LasAttnStep* a, void* stream) {
     if (rc) return rc;
     size_t smem = smem_bytes(a);
     LasProfScope prof(LAS_PROF_ATTN_BWD, stream, 2.0 * a->B * (double)a->T * a->P * sizeof(float));
-    if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_step_kernel<true><<<a->B * a->heads, NT, smem, (cudaStream_t)stream>>>(*a);
+    if (a->B * a->heads >= las_device_info()->num_sms) {
+        if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_step_kernel<true, 4><<<a->B * a->heads, NT, smem, (cudaStream_t)stream>>>(*a);
+    } else {
+        if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_step_kernel<true, 8><<<a->B * a->heads, NT, smem, (cudaStream_t)stream>>>(*a);
+    }
     LAS_LAUNCH_CHECK();
     return LAS_OK;
 }

@@ -17,7 +17,15 @@
 #include "las_b200.h"
 #include <vector>
 
+// prepared tensor-core GEMM plans (gemm_tc.cu): tensor maps encoded once per loop, one launch per step
+size_t las_tc_plan_bytes();
+int las_tc_plan_make(void* plan_mem, const void* A, const void* B, int M, int N, int K, int a_batches, long long a_s1, long long a_s2,
+                     long long b_s1, int b_mn_major);
+int las_tc_plan_launch(const void* plan_mem, int a_batch, float* C, long long ldc, const float* bias1, const float* bias2, void* stream);
+
 namespace {
+
+struct alignas(64) PlanBuf { unsigned char b[1024]; };
 
 // ------------------------------------------------------------------------------------------------------------------
 // kernels
@@ -419,6 +427,13 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
         LAS_CUDA(cudaMemset2DAsync(S0b + P, K0 * 2, 0, DH * 2, B, st));       // h0_{-1} = 0 (bf16)
         LAS_CUDA(cudaMemset2DAsync(S1b + DH, K1 * 2, 0, DO * 2, B, st));      // h1_{-1} = 0
     }
+    PlanBuf pl0, pl1, plq;
+    if (tc) {
+        LAS_CHECK_ARG(las_tc_plan_bytes() <= sizeof(PlanBuf), "speller: plan buffer too small");
+        RC(las_tc_plan_make(&pl0, S0b, Wcat0b, B, 4 * DH, K0, L.hist, K0, (long long)B * K0, K0, 0));
+        RC(las_tc_plan_make(&pl1, S1b, Wcat1b, B, 4 * DO, K1, L.hist, K1, (long long)B * K1, K1, 0));
+        RC(las_tc_plan_make(&plq, S1b + DH, Wqb, B, P, DO, L.hist, K1, (long long)B * K1, DO, 0));
+    }
     // embedding-side gate table (+ both cell-0 biases)
     RC(gemm(st, s->emb, E, s->w_ih0, E + P, 1, Gemb, 4 * DH, V, 4 * DH, E, 0.f, s->b_ih0, s->b_hh0));
     // zero initial states (init_hiddens are always zero: reference src/models.py:275-281)
@@ -457,7 +472,7 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
         __nv_bfloat16* S0rb = S0b + (size_t)r * B * K0;  __nv_bfloat16* S0nb = S0b + (size_t)rn * B * K0;
         __nv_bfloat16* S1rb = S1b + (size_t)r * B * K1;  __nv_bfloat16* S1nb = S1b + (size_t)rn * B * K1;
         // cell 0
-        if (tc) RC(tc_nt(st, S0rb, K0, Wcat0b, K0, G0r, 4 * DH, B, 4 * DH, K0));
+        if (tc) RC(las_tc_plan_launch(&pl0, r, G0r, 4 * DH, nullptr, nullptr, st));
         else RC(gemm(st, S0r, K0, Wcat0, K0, 1, G0r, 4 * DH, B, 4 * DH, K0));
         CellFwd c0{};
         c0.G = G0r; c0.Gtab = Gemb; c0.y = s->dec_y; c0.ld_y = s->ld_y;
@@ -475,7 +490,7 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
         cell_fwd_kernel<<<ceil_div(B * DH, 256), 256, 0, st>>>(c0);
         LAS_LAUNCH_CHECK();
         // cell 1
-        if (tc) RC(tc_nt(st, S1rb, K1, Wcat1b, K1, G1r, 4 * DO, B, 4 * DO, K1, s->b_ih1, s->b_hh1));
+        if (tc) RC(las_tc_plan_launch(&pl1, r, G1r, 4 * DO, s->b_ih1, s->b_hh1, st));
         else RC(gemm(st, S1r, K1, Wcat1, K1, 1, G1r, 4 * DO, B, 4 * DO, K1, 0.f, s->b_ih1, s->b_hh1));
         CellFwd c1{};
         c1.G = G1r; c1.Gtab = nullptr; c1.t = t;
@@ -488,7 +503,7 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
         cell_fwd_kernel<<<ceil_div(B * DO, 256), 256, 0, st>>>(c1);
         LAS_LAUNCH_CHECK();
         // query projection into QC[t+1][:, :P]
-        if (tc) RC(tc_nt(st, S1nb + DH, K1, Wqb, DO, QCn, 2 * P, B, P, DO, s->bq));
+        if (tc) RC(las_tc_plan_launch(&plq, rn, QCn, 2 * P, s->bq, nullptr, st));
         else RC(gemm(st, S1n + DH, K1, s->wq, DO, 1, QCn, 2 * P, B, P, DO, 0.f, s->bq));
         // attention: context into QC[t+1][:, P:] and into the next cell-0 row
         at.q = QCn; at.ctx = QCn + P; at.ctx2 = S0n; at.w = W + (size_t)rn * B * heads * T;
@@ -578,6 +593,13 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     at.K = s->K; at.V = s->V_; at.lens = s->enc_lens; at.B = B; at.T = T; at.P = P; at.heads = heads;
     at.scale = sqrtf((float)d_head);
     at.ld_q = 2 * P; at.ld_w = T; at.ld_dctx = 2 * P; at.ld_dctx2 = K0; at.ld_dq = 2 * P; at.dq_accumulate = 1;
+    PlanBuf bq1, bq2, bq3;
+    if (tc) {
+        LAS_CHECK_ARG(las_tc_plan_bytes() <= sizeof(PlanBuf), "speller: plan buffer too small");
+        RC(las_tc_plan_make(&bq1, dQb, Wqb, B, DO, P, S + 1, P, (long long)B * P, DO, 1));
+        RC(las_tc_plan_make(&bq2, G1b, Wcat1b, B, K1, 4 * DO, S, 4 * DO, (long long)B * 4 * DO, K1, 1));
+        RC(las_tc_plan_make(&bq3, G0b, Wcat0b, B, K0, 4 * DH, S, 4 * DH, (long long)B * 4 * DH, K0, 1));
+    }
 
     for (int t = S - 1; t >= 0; --t) {
         const int rn = t + 1;
@@ -589,7 +611,7 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
         at.dq_bf16 = tc ? (void*)(dQb + (size_t)rn * B * P) : nullptr; at.ld_dq_bf16 = P;
         RC(las_attn_step_bwd_f32(&at, st));
         // dh1_t (dropped) = dq_total . Wq  (+ recurrent path, added inside cell_bwd)
-        if (tc) RC(tc_nn(st, dQb + (size_t)rn * B * P, P, Wqb, DO, dh1, DO, B, DO, P));
+        if (tc) RC(las_tc_plan_launch(&bq1, rn, dh1, DO, nullptr, nullptr, st));
         else RC(gemm(st, dQCn, 2 * P, s->wq, DO, 0, dh1, DO, B, DO, P));
         CellBwd b1{};
         b1.G = G1 + (size_t)t * B * 4 * DO;
@@ -602,7 +624,7 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
         cell_bwd_kernel<<<ceil_div(B * DO, 256), 256, 0, st>>>(b1);
         LAS_LAUNCH_CHECK();
         // dS1[t] = dG1_t . Wcat1  -> [dh0_t | dh1_{t-1}]
-        if (tc) RC(tc_nn(st, b1.Gb, 4 * DO, Wcat1b, K1, dS1, K1, B, K1, 4 * DO));
+        if (tc) RC(las_tc_plan_launch(&bq2, t, dS1, K1, nullptr, nullptr, st));
         else RC(gemm(st, b1.G, 4 * DO, Wcat1, K1, 0, dS1, K1, B, K1, 4 * DO));
         CellBwd b0{};
         b0.G = G0 + (size_t)t * B * 4 * DH;
@@ -615,7 +637,7 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
         cell_bwd_kernel<<<ceil_div(B * DH, 256), 256, 0, st>>>(b0);
         LAS_LAUNCH_CHECK();
         // dS0[t] = dG0_t . Wcat0 -> [dctx_t | dh0_{t-1}]
-        if (tc) RC(tc_nn(st, b0.Gb, 4 * DH, Wcat0b, K0, dS0, K0, B, K0, 4 * DH));
+        if (tc) RC(las_tc_plan_launch(&bq3, t, dS0, K0, nullptr, nullptr, st));
         else RC(gemm(st, b0.G, 4 * DH, Wcat0, K0, 0, dS0, K0, B, K0, 4 * DH));
     }
     // initial attention (src/models.py:346): its context feeds cell 0 of step 0 only

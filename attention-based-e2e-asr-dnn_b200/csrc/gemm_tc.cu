@@ -18,6 +18,7 @@
 #include "las_common.cuh"
 #include "las_b200.h"
 #include <cuda.h>
+#include <new>
 
 namespace {
 
@@ -51,6 +52,7 @@ struct TcArgs {
     int KB;           // batches in the K direction (wgrad: B of (b,t) rows; else 1)
     int accumulate;   // C += result
     const int* lens;  // optional (NB): skip M tiles whose first row >= lens[b] (rows past a sequence's length)
+    int b_first;      // first M-batch index (prepared plans address one batch of a multi-batch tensor map per launch)
     int splitk;       // >1: the K range of every output tile is split over `splitk` CTAs writing partials to Cpart
     float* Cpart;     // (splitk, R, ldp) partial sums
     long long ldp;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
             for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += gridDim.x) {
                 const int split = tile0 % splitk, tile = tile0 / splitk;
                 const int ntile = tile % g.nt, mrem = tile / g.nt;
-                const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b;
+                const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b + g.b_first;
                 if (g.lens && mtile * BM >= g.lens[b]) continue;
                 const int k_lo = (int)((long long)kiters_all * split / splitk), k_hi = (int)((long long)kiters_all * (split + 1) / splitk);
                 for (int kit = k_lo; kit < k_hi; ++kit) {
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
             for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += gridDim.x) {
                 const int split = tile0 % splitk, tile = tile0 / splitk;
                 const int mrem = tile / g.nt;
-                const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b;
+                const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b + g.b_first;
                 if (g.lens && mtile * BM >= g.lens[b]) continue;
                 const int k_lo = (int)((long long)kiters_all * split / splitk), k_hi = (int)((long long)kiters_all * (split + 1) / splitk);
                 mbar_wait(tempty_bar(acc), accphase ^ 1u);
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
         for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += gridDim.x) {
             const int split = tile0 % splitk, tile = tile0 / splitk;
             const int ntile = tile % g.nt, mrem = tile / g.nt;
-            const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b;
+            const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b + g.b_first;
             if (g.lens && mtile * BM >= g.lens[b]) continue;
             mbar_wait(tfull_bar(acc), accphase);
             tc_fence_after();
@@ -398,6 +400,42 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, cud
 }
 
 }  // namespace
+
+// ---- prepared plans (internal C++ API used by the decoder loop): tensor maps are encoded once, every step only launches
+struct LasTcPlan {
+    CUtensorMap ta, tb;
+    TcArgs g;
+    int variant;     // 0: A,B K-major (C = A.B^T) ; 1: B MN-major (C = A.B)
+};
+size_t las_tc_plan_bytes() { return sizeof(LasTcPlan); }
+
+// A: (K contiguous, M rows [a_s1], a_batches [a_s2]); one batch is selected per launch.  Always the BN = 64 tiling.
+int las_tc_plan_make(void* plan_mem, const void* A, const void* B, int M, int N, int K, int a_batches, long long a_s1, long long a_s2,
+                     long long b_s1, int b_mn_major) {
+    LasTcPlan* p = new (plan_mem) LasTcPlan();
+    int rc = make_map(&p->ta, A, K, M, a_batches, a_s1, a_s2, BK, BM);
+    if (rc) return rc;
+    if (!b_mn_major) rc = make_map(&p->tb, B, K, N, 1, b_s1, 0, BK, 64);
+    else rc = make_map(&p->tb, B, N, K, 1, b_s1, 0, 64, 64);
+    if (rc) return rc;
+    p->variant = b_mn_major ? 1 : 0;
+    TcArgs& g = p->g;
+    g = TcArgs{};
+    g.R = M; g.NB = 1; g.N = N; g.mt_per_b = ceil_div(M, BM); g.nt = ceil_div(N, 64); g.kt_per_b = ceil_div(K, BK); g.KB = 1;
+    return LAS_OK;
+}
+
+int las_tc_plan_launch(const void* plan_mem, int a_batch, float* C, long long ldc, const float* bias1, const float* bias2, void* stream) {
+    const LasTcPlan* p = (const LasTcPlan*)plan_mem;
+    TcArgs g = p->g;
+    g.C = C; g.ldc = ldc; g.c_bs = 0; g.bias1 = bias1; g.bias2 = bias2; g.b_first = a_batch;
+    LAS_CHECK_ARG(ldc % 4 == 0 && ((uintptr_t)C & 15) == 0, "tc plan: C must be 16-byte aligned with ldc %% 4 == 0");
+    LasProfScope prof(LAS_PROF_GEMM_OTHER, stream, 2.0 * g.R * (double)g.N * g.kt_per_b * BK);
+    // the c_bs * b term must vanish for the selected batch: C is already the step's output
+    g.c_bs = 0;
+    if (p->variant == 0) return launch_tc<false, false, 64>(p->ta, p->tb, g, (cudaStream_t)stream);
+    return launch_tc<false, true, 64>(p->ta, p->tb, g, (cudaStream_t)stream);
+}
 
 extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
     LAS_CHECK_ARG(d != nullptr && d->A && d->B && d->C, "gemm_tc: null descriptor / operand");

@@ -17,6 +17,9 @@
 #include "las_common.cuh"
 #include "las_b200.h"
 #include <cuda.h>
+#include <stdlib.h>
+
+static long long* g_rec_dbg = nullptr;   // debug aid, see las_lstm_rec_tc_set_debug
 
 namespace {
 
@@ -36,6 +39,8 @@ struct RecTcArgs {
     __nv_bfloat16* hbuf;   // (ndir, 2, Bpad, H) bf16 exchange buffer
     unsigned* ctr;         // (ndir, nslices) step counters
     int B, T, H, ndir, nslices, Bpad, chains, bsg, save;
+    const __nv_bfloat16* w_gl;  // W_hh bf16 (ndir, 4H, H) for the TMEM-resident-A variant
+    int w_tmem;            // 1: W_hh slice lives in TMEM (A operand from tensor memory); 0: in shared memory
     long long* dbg;        // optional (debug): per-step clock64 stamps of CTA (0,0,0), 16 slots per step
 };
 
@@ -77,6 +82,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
     asm volatile(
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// A operand from tensor memory (".ts" form): D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -122,13 +143,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 // idesc: F32 accumulate, BF16 x BF16, both K-major, M = 128, N = 32
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB_SLICE >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
 
+template <bool WTMEM>
 __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW,
                                                                      const __grid_constant__ CUtensorMap tmH, const RecTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const int H = a.H, T = a.T, KB = H / 64;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t w_sm = base;                                   // KB x [128 rows x 128 B]
-    const uint32_t h_sm = w_sm + KB * 16384;                      // chains x KB x [32 rows x 128 B]
+    const uint32_t w_sm = base;                                   // KB x [128 rows x 128 B] (absent when W lives in TMEM)
+    const uint32_t h_sm = w_sm + (WTMEM ? 0 : KB * 16384);        // chains x KB x [32 rows x 128 B]
     const uint32_t ex_off = (h_sm - smem_u32(smem_raw)) + a.chains * KB * 4096;
     float* ex = reinterpret_cast<float*>(smem_raw + ex_off);      // [4][32][32] gate exchange
     const uint32_t bar_base = smem_u32(smem_raw) + ex_off + 4 * 32 * 32 * 4;
@@ -150,22 +172,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    const uint32_t tmem_cols = WTMEM ? 512u : 64u;
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // TMEM map: accumulators (MAX_CHAINS x 32 columns) first, then the resident W_hh slice (H/2 columns: two bf16 per
+    // 32-bit column, K ascending; TMEM lane = gate row, the layout tcgen05.mma expects for an A operand in tensor memory)
+    const uint32_t tmem_w = tmem_base + 64;
+    if (WTMEM) {
+        if (warp >= 4) {
+            const int q = warp & 3;
+            const uint32_t* wrow = reinterpret_cast<const uint32_t*>(a.w_gl + ((long long)dir * 4 * H + q * H + r * UNITS + lane) * H);
+            for (int cb = 0; cb < H / 64; ++cb) {
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 t4 = *reinterpret_cast<const uint4*>(wrow + cb * 32 + i * 4);
+                    v[i * 4 + 0] = t4.x; v[i * 4 + 1] = t4.y; v[i * 4 + 2] = t4.z; v[i * 4 + 3] = t4.w;
+                }
+                tmem_st32(tmem_w + ((uint32_t)(q * 32) << 16) + cb * 32, v);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     if (warp == 0) {
         if (lane == 0) {
-            // ===== producer: resident W_hh slice once, then h_{t-1} slices per step =====
-            mbar_arrive_expect_tx(wbar, (uint32_t)KB * 16384u);
-            for (int kb = 0; kb < KB; ++kb)
-                for (int g = 0; g < 4; ++g)
-                    tma_load_2d(w_sm + kb * 16384 + g * 4096, &tmW, wbar, kb * 64, dir * 4 * H + g * H + r * UNITS);
+            // ===== producer: resident W_hh slice once (shared-memory variant), then h_{t-1} slices per step =====
+            if (!WTMEM) {
+                mbar_arrive_expect_tx(wbar, (uint32_t)KB * 16384u);
+                for (int kb = 0; kb < KB; ++kb)
+                    for (int g = 0; g < 4; ++g)
+                        tma_load_2d(w_sm + kb * 16384 + g * 4096, &tmW, wbar, kb * 64, dir * 4 * H + g * H + r * UNITS);
+            }
             for (int s = 1; s < T; ++s) {
                 for (int c = 0; c < a.chains; ++c) {
                     const int slice = sg + c * a.bsg;
@@ -186,7 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
-            mbar_wait(wbar, 0);
+            if (!WTMEM) mbar_wait(wbar, 0);
             for (int s = 1; s < T; ++s) {
                 for (int c = 0; c < a.chains; ++c) {
                     const int slice = sg + c * a.bsg;
@@ -198,9 +245,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t ad = make_desc_k(w_sm + kb * 16384 + k * 32);
                             const uint64_t bd = make_desc_k(h_sm + (c * KB + kb) * 4096 + k * 32);
-                            umma_bf16(d_tmem, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+                            if (WTMEM) {
+                                umma_bf16_ts(d_tmem, tmem_w + kb * 32 + k * 8, bd, IDESC, (kb | k) ? 1u : 0u);
+                            } else {
+                                const uint64_t ad = make_desc_k(w_sm + kb * 16384 + k * 32);
+                                umma_bf16(d_tmem, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+                            }
                         }
                     }
                     umma_commit(tfull_bar(c));
@@ -319,7 +370,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -383,7 +434,6 @@ int make_plan(int B, int H, int ndir, Plan* p) {
 
 }  // namespace
 
-static long long* g_rec_dbg = nullptr;
 // debug aid: device buffer of 256*16 long long receiving clock64 stamps of CTA (0,0,0) of the next forward launches
 extern "C" void las_lstm_rec_tc_set_debug(void* dev_buf) { g_rec_dbg = (long long*)dev_buf; }
 
@@ -403,8 +453,8 @@ extern "C" int las_lstm_rec_tc_supported(int B, int H, int ndir) {
 
 extern "C" size_t las_lstm_rec_tc_workspace_bytes(int B, int H, int ndir) {
     const int nsl = ceil_div(B, NB_SLICE);
-    // counters (1 KB) + bf16 h exchange buffer (ndir, 2, Bpad, H)
-    return 1024 + (size_t)ndir * 2 * nsl * NB_SLICE * H * 2;
+    // counters (1 KB) + bf16 exchange buffer: forward h (ndir, 2, Bpad, H); backward dG (ndir, 2, 4, Bpad, H)
+    return 1024 + (size_t)ndir * 2 * 4 * nsl * NB_SLICE * H * 2;
 }
 
 extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const int* lens, const float* drop_mask, float* out,
@@ -423,6 +473,11 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
     a.gates = gates; a.lens = lens; a.mask = drop_mask; a.out = out; a.hs_pad = hs_pad; a.cs_pad = cs_pad;
     a.ctr = (unsigned*)ws; a.hbuf = (__nv_bfloat16*)((char*)ws + 1024);
     a.B = B; a.T = T; a.H = H; a.ndir = ndir; a.nslices = p.nslices; a.Bpad = p.Bpad; a.chains = p.chains; a.bsg = p.bsg; a.save = save_gates; a.dbg = g_rec_dbg;
+    a.w_gl = (const __nv_bfloat16*)w_hh_bf16;
+    {
+        const char* e = getenv("LAS_REC_WTMEM");
+        a.w_tmem = (e ? atoi(e) : 0) && H <= 512;   // measured slower than shared-memory A at N = 32: off by default
+    }
     LAS_CHECK_ARG((size_t)ndir * p.nslices * sizeof(unsigned) <= 1024, "lstm_rec_fwd_tc: too many batch slices");
     CUtensorMap tmW, tmH;
     rc = make_map_2d(&tmW, w_hh_bf16, H, (long long)ndir * 4 * H, 64, 32);
@@ -434,11 +489,12 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
         rc = make_map_nd(&tmH, a.hbuf, 3, dims, strides, box);
         if (rc) return rc;
     }
-    LAS_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    void* kern = a.w_tmem ? (void*)lstm_rec_fwd_tc_kernel<true> : (void*)lstm_rec_fwd_tc_kernel<false>;
+    LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     LAS_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
     LasProfScope prof(LAS_PROF_REC_FWD, stream, (double)T);
     void* args[] = {(void*)&tmW, (void*)&tmH, (void*)&a};
-    LAS_CUDA(cudaLaunchCooperativeKernel((void*)lstm_rec_fwd_tc_kernel, dim3(p.rs, p.bsg, ndir), dim3(NTHREADS), args, p.smem, st));
+    LAS_CUDA(cudaLaunchCooperativeKernel(kern, dim3(p.rs, p.bsg, ndir), dim3(NTHREADS), args, p.smem, st));
     las_count_launch(1);
     return LAS_OK;
 }
@@ -463,7 +519,9 @@ struct RecTcBwdArgs {
     const int* lens;
     const float* mask;
     unsigned* ctr;
-    int B, T, H, ndir, nslices, chains, bsg, KBr, CH;
+    int B, T, H, ndir, nslices, chains, bsg, KBr, CH, Bpad;
+    __nv_bfloat16* dgx;      // K-split variant: compact bf16 exchange buffer (ndir, 2, 4 gates, Bpad, H)
+    long long* dbg;
 };
 
 constexpr uint32_t IDESC_BWD = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UNITS >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
@@ -583,22 +641,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_tc_kernel(const __gr
                 if (c >= a.chains || slice >= a.nslices) continue;
                 const int b0 = slice * NB_SLICE;
                 // operands of the pointwise backward, issued before waiting on the tensor pipe
-                float gi[8], gf[8], gg[8], go[8], ct[8], cp[8], dh[8];
+                float gi[8], gf[8], gg[8], go[8], ct[8], cp[8], dh[8], mk[8], rec[8];
                 bool valid[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int b = b0 + q * 8 + i;
                     valid[i] = t < lenr[c][i];
-                    if (valid[i]) {
-                        const float* gp = a.gates + (((long long)b * T + t) * a.ndir + dir) * G4 + u;
-                        gi[i] = gp[0]; gf[i] = gp[H]; gg[i] = gp[2 * H]; go[i] = gp[3 * H];
-                        ct[i] = a.cs_pad[(long long)b * brow + (long long)fcur * F + dir * H + u];
-                        cp[i] = a.cs_pad[(long long)b * brow + (long long)fprev * F + dir * H + u];
-                        const float m = a.mask ? a.mask[(long long)b * F + dir * H + u] : 1.f;
-                        dh[i] = a.dout[((long long)b * T + t) * F + dir * H + u] * m;
-                    } else {
-                        gi[i] = gf[i] = gg[i] = go[i] = ct[i] = cp[i] = dh[i] = 0.f;
-                    }
+                    // pure loads, no branches and no arithmetic: an in-order warp would otherwise stall on the first use and
+                    // serialise the eight rows' HBM latencies.  Rows past B are clamped to a valid address; invalid rows are
+                    // zeroed in the pointwise step.
+                    const int bc = b < a.B ? b : a.B - 1;
+                    const float* gp = a.gates + (((long long)bc * T + t) * a.ndir + dir) * G4 + u;
+                    gi[i] = gp[0]; gf[i] = gp[H]; gg[i] = gp[2 * H]; go[i] = gp[3 * H];
+                    ct[i] = a.cs_pad[(long long)bc * brow + (long long)fcur * F + dir * H + u];
+                    cp[i] = a.cs_pad[(long long)bc * brow + (long long)fprev * F + dir * H + u];
+                    mk[i] = a.mask ? a.mask[(long long)bc * F + dir * H + u] : 1.f;
+                    dh[i] = a.dout[((long long)bc * T + t) * F + dir * H + u];
+                    rec[i] = 0.f;
                 }
                 if (s > 0) {
                     mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
@@ -615,7 +674,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_tc_kernel(const __gr
                     tc_fence_before();
                     named_bar_sync(1, 128);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dh[i] += exD[(q * 8 + i) * 33 + j];
+                    for (int i = 0; i < 8; ++i) rec[i] = exD[(q * 8 + i) * 33 + j];
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -624,11 +683,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_tc_kernel(const __gr
                     float dai = 0.f, daf = 0.f, dag = 0.f, dao = 0.f, dcn = 0.f;
                     if (valid[i]) {
                         const float tcv = tanh_fast(ct[i]);
-                        const float dct = fmaf(dh[i] * go[i], 1.f - tcv * tcv, dcst[c][i]);
+                        const float dhv = fmaf(dh[i], mk[i], rec[i]);
+                        const float dct = fmaf(dhv * go[i], 1.f - tcv * tcv, dcst[c][i]);
                         dai = dct * gg[i] * gi[i] * (1.f - gi[i]);
                         daf = dct * cp[i] * gf[i] * (1.f - gf[i]);
                         dag = dct * gi[i] * (1.f - gg[i] * gg[i]);
-                        dao = dh[i] * tcv * go[i] * (1.f - go[i]);
+                        dao = dhv * tcv * go[i] * (1.f - go[i]);
                         dcn = dct * gf[i];
                     }
                     dcst[c][i] = dcn;
@@ -685,6 +745,9 @@ extern "C" int las_transpose_cast_bf16(const float* src, void* dst, int batch, i
     return LAS_OK;
 }
 
+static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16, const int* lens,
+                          const float* drop_mask, int B, int T, int H, int ndir, void* ws, cudaStream_t st, void* stream);
+
 extern "C" int las_lstm_rec_bwd_tc(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16,
                                    const int* lens, const float* drop_mask, int B, int T, int H, int ndir, void* ws, size_t ws_bytes,
                                    void* stream) {
@@ -695,8 +758,15 @@ extern "C" int las_lstm_rec_bwd_tc(const float* dout, float* gates, void* dgates
     Plan p;
     rc = make_plan(B, H, ndir, &p);
     if (rc) return rc;
-    if (ws_bytes < 1024) { las_set_error("lstm_rec_bwd_tc: workspace too small"); return LAS_ERR_WORKSPACE; }
+    if (ws_bytes < las_lstm_rec_tc_workspace_bytes(B, H, ndir)) { las_set_error("lstm_rec_bwd_tc: workspace too small"); return LAS_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        const char* e = getenv("LAS_REC_BWD_KSPLIT");
+        if (!e || atoi(e) != 0) {
+            rc = launch_bwd_tc2(dout, gates, dgates_bf16, cs_pad, w_hh_t_bf16, lens, drop_mask, B, T, H, ndir, ws, st, stream);
+            if (rc == LAS_OK) return LAS_OK;          // otherwise fall through to the streaming variant
+        }
+    }
     RecTcBwdArgs a{};
     a.gates = gates; a.dgb = (__nv_bfloat16*)dgates_bf16; a.dout = dout; a.cs_pad = cs_pad; a.lens = lens; a.mask = drop_mask;
     a.ctr = (unsigned*)ws;
@@ -721,6 +791,300 @@ extern "C" int las_lstm_rec_bwd_tc(const float* dout, float* gates, void* dgates
     LasProfScope prof(LAS_PROF_REC_BWD, stream, (double)T);
     void* args[] = {(void*)&tmWt, (void*)&tmG, (void*)&a};
     LAS_CUDA(cudaLaunchCooperativeKernel((void*)lstm_rec_bwd_tc_kernel, dim3(p.rs, p.bsg, ndir), dim3(NTHREADS), args, smem, st));
+    las_count_launch(1);
+    return LAS_OK;
+}
+
+// =====================================================================================================================
+// BPTT, K-split variant (H % 128 == 0): the default.
+// The per-step product dh_rec = dG . W_hh has a 4H-long reduction, 4x the forward's.  Instead of streaming the whole
+// 32 x 4H dG slice through every CTA, the reduction is split by GATE over a 4-CTA thread-block cluster:
+//   CTA (kq, ub, s, dir), kq = cluster rank = gate index, ub = 128-unit block.
+//   resident A operand : W_hh^T[units of block ub, rows of gate kq]           128 x H bf16  (K-major, shared memory)
+//   per-step B operand : dG_prev[32 batch rows, gate kq, all H units]          32 x H bf16  (one TMA issue, same size as fwd)
+//   UMMA M = 128, N = 32, K = H  ->  partial dh_rec for 128 units x 32 rows over one gate, in TMEM.
+// The four partials are summed through distributed shared memory (each CTA finalises 32 of the block's 128 units), then
+// the pointwise LSTM backward runs for those 32 units exactly as in the other variant.  Cross-cluster ordering (a CTA's B
+// operand spans all units, i.e. all 4*H/128 CTAs of the (direction, batch slice) group) still uses the release/acquire counter.
+// =====================================================================================================================
+namespace {
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_saddr, uint32_t cta) {
+    uint32_t raddr;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_saddr), "r"(cta));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr));
+    return v;
+}
+
+constexpr int PART_LD = 132;          // floats per batch row of the partial tile [32 b][128 u] (+4 pad)
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
+    lstm_rec_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmWt, const __grid_constant__ CUtensorMap tmG, const RecTcBwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const int H = a.H, T = a.T, KB = H / 64;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_sm = base;                                        // KB x [128 rows(u) x 128 B]  resident W_hh^T tile
+    const uint32_t b_sm = a_sm + KB * 16384;                           // chains x KB x [32 rows(b) x 128 B]
+    const uint32_t part_off = (b_sm - smem_u32(smem_raw)) + a.chains * KB * 4096;
+    float* part0 = reinterpret_cast<float*>(smem_raw + part_off);      // [2][32][PART_LD]: ping-pong, so one cluster barrier per step suffices
+    const uint32_t part_saddr0 = smem_u32(smem_raw) + part_off;
+    const uint32_t bar_base = (part_saddr0 + 2 * 32 * PART_LD * 4 + 15u) & ~15u;
+    auto full_bar = [&](int c) { return bar_base + 8u * c; };
+    auto tfull_bar = [&](int c) { return bar_base + 8u * (MAX_CHAINS + c); };
+    const uint32_t wbar = bar_base + 8u * (2 * MAX_CHAINS);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_CHAINS + 1);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int kq = (int)cluster_ctarank();            // gate handled by this CTA's reduction slice
+    const int ub = blockIdx.x >> 2;                   // 128-unit block
+    const int sg = blockIdx.y, dir = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int F = a.ndir * H, G4 = 4 * H, NG = a.ndir * G4;
+    const long long brow = (long long)(T + 2) * F;
+    const unsigned group = (unsigned)(4 * (H / 128));  // CTAs sharing one (direction, batch slice)
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWt) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
+        for (int c = 0; c < MAX_CHAINS; ++c) { mbar_init(full_bar(c), 1); mbar_init(tfull_bar(c), 1); }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    // per-thread state of the epilogue role (declared for all so the step loop below is shared by every warp)
+    const int q = warp & 3, j = lane;
+    const int te = (warp - 4) * 32 + lane;
+    const int u = ub * 128 + kq * 32 + j;              // the unit this thread finalises (epilogue warps)
+    float dcst[MAX_CHAINS][8];
+    int lenr[MAX_CHAINS][8];
+#pragma unroll
+    for (int c = 0; c < MAX_CHAINS; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            dcst[c][i] = 0.f;
+            const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
+            lenr[c][i] = (warp >= 4 && c < a.chains && sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
+        }
+
+    if (warp == 0 && lane == 0) {
+        mbar_arrive_expect_tx(wbar, (uint32_t)KB * 16384u);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(a_sm + kb * 16384, &tmWt, wbar, kq * H + kb * 64, dir * H + ub * 128);
+    }
+    if (warp == 1 && lane == 0) mbar_wait(wbar, 0);
+
+    // Every warp walks the same (step, chain) sequence: the cluster barrier of each iteration needs all threads of all 4 CTAs.
+    int iter = 0;
+    for (int s = 0; s < T; ++s) {
+        const int t = (dir == 0) ? (T - 1 - s) : s;
+        const int t_prev = (dir == 0) ? (T - s) : (s - 1);
+        const int fprev = (dir == 0) ? t : t + 2, fcur = t + 1;
+#pragma unroll
+        for (int c = 0; c < MAX_CHAINS; ++c) {
+            const int slice = sg + c * a.bsg;
+            if (c >= a.chains || slice >= a.nslices) continue;          // uniform across the cluster (same sg, chains)
+            const int b0 = slice * NB_SLICE;
+            float* part = part0 + (iter & 1) * 32 * PART_LD;
+            const uint32_t part_saddr = part_saddr0 + (uint32_t)((iter & 1) * 32 * PART_LD * 4);
+            ++iter;
+            float gi[8], gf[8], gg[8], go[8], ct[8], cp[8], dh[8], mk[8], rec[8];
+            bool valid[8];
+            if (warp == 0) {
+                if (lane == 0 && s > 0) {
+                    const unsigned* ctr = a.ctr + dir * a.nslices + slice;
+                    const unsigned target = group * (unsigned)s;
+                    while (ld_acquire_gpu(ctr) < target) { }
+                    REC_STAMP(0);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    mbar_arrive_expect_tx(full_bar(c), (uint32_t)KB * 4096u);
+                    // compact exchange buffer (dir, parity, gate, Bpad, H): the 32 x H tile of gate kq is 32 contiguous rows
+                    tma_load_3d(b_sm + c * KB * 4096, &tmG, full_bar(c), 0, ((dir * 2 + ((s - 1) & 1)) * 4 + kq) * a.Bpad + b0, 0);
+                    REC_STAMP(1);
+                }
+                __syncwarp();
+            } else if (warp == 1) {
+                if (lane == 0 && s > 0) {
+                    mbar_wait(full_bar(c), (uint32_t)((s - 1) & 1));
+                    REC_STAMP(2);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + c * NB_SLICE;
+                    for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = make_desc_k(a_sm + kb * 16384 + k * 32);
+                            const uint64_t bd = make_desc_k(b_sm + (c * KB + kb) * 4096 + k * 32);
+                            umma_bf16(d_tmem, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(tfull_bar(c));
+                    REC_STAMP(3);
+                }
+                __syncwarp();
+            } else if (warp >= 4) {
+                // operands of the pointwise backward for this thread's unit, issued before waiting on the tensor pipe
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + q * 8 + i;
+                    valid[i] = t < lenr[c][i];
+                    // pure loads, no branches and no arithmetic: an in-order warp would otherwise stall on the first use and
+                    // serialise the eight rows' HBM latencies.  Rows past B are clamped to a valid address; invalid rows are
+                    // zeroed in the pointwise step.
+                    const int bc = b < a.B ? b : a.B - 1;
+                    const float* gp = a.gates + (((long long)bc * T + t) * a.ndir + dir) * G4 + u;
+                    gi[i] = gp[0]; gf[i] = gp[H]; gg[i] = gp[2 * H]; go[i] = gp[3 * H];
+                    ct[i] = a.cs_pad[(long long)bc * brow + (long long)fcur * F + dir * H + u];
+                    cp[i] = a.cs_pad[(long long)bc * brow + (long long)fprev * F + dir * H + u];
+                    mk[i] = a.mask ? a.mask[(long long)bc * F + dir * H + u] : 1.f;
+                    dh[i] = a.dout[((long long)bc * T + t) * F + dir * H + u];
+                    rec[i] = 0.f;
+                }
+                if (te == 0) REC_STAMP(4);
+                if (s > 0) {
+                    mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
+                    if (te == 0) REC_STAMP(5);
+                    tc_fence_after();
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * NB_SLICE, v);
+                    // TMEM lane = unit (32q + lane) of the block, column = batch row: park the partial as part[b][unit]
+#pragma unroll
+                    for (int n = 0; n < 32; ++n) part[n * PART_LD + q * 32 + lane] = __uint_as_float(v[n]);
+                    tc_fence_before();
+                    if (te == 0) REC_STAMP(6);
+                }
+            }
+            if (s > 0) {
+                cluster_sync_all();                                   // all four gate-partials are in shared memory
+                if (warp == 4 && lane == 0) REC_STAMP(7);
+                if (warp >= 4) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t off = part_saddr + (uint32_t)(((q * 8 + i) * PART_LD + kq * 32 + j) * 4);
+                        float p4[4];
+#pragma unroll
+                        for (int src = 0; src < 4; ++src) p4[src] = ld_dsmem_f32(off, (uint32_t)src);
+                        rec[i] = (p4[0] + p4[1]) + (p4[2] + p4[3]);
+                    }
+                }
+                if (warp == 4 && lane == 0) REC_STAMP(11);
+                // no second barrier: the partial tile ping-pongs, and a peer can only be two iterations ahead of my reads
+                // after I have passed the next iteration's barrier
+            }
+            if (warp >= 4) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + q * 8 + i;
+                    float dai = 0.f, daf = 0.f, dag = 0.f, dao = 0.f, dcn = 0.f;
+                    if (valid[i]) {
+                        const float tcv = tanh_fast(ct[i]);
+                        const float dhv = fmaf(dh[i], mk[i], rec[i]);
+                        const float dct = fmaf(dhv * go[i], 1.f - tcv * tcv, dcst[c][i]);
+                        dai = dct * gg[i] * gi[i] * (1.f - gi[i]);
+                        daf = dct * cp[i] * gf[i] * (1.f - gf[i]);
+                        dag = dct * gi[i] * (1.f - gg[i] * gg[i]);
+                        dao = dhv * tcv * go[i] * (1.f - go[i]);
+                        dcn = dct * gf[i];
+                    }
+                    dcst[c][i] = dcn;
+                    // what the peers' next step reads: bf16 d(pre-activation) in the compact exchange buffer
+                    __nv_bfloat16* xp = a.dgx + ((long long)((dir * 2 + (s & 1)) * 4) * a.Bpad + b) * H + u;
+                    const long long gst = (long long)a.Bpad * H;
+                    xp[0] = __float2bfloat16(dai); xp[gst] = __float2bfloat16(daf);
+                    xp[2 * gst] = __float2bfloat16(dag); xp[3 * gst] = __float2bfloat16(dao);
+                    gi[i] = dai; gf[i] = daf; gg[i] = dag; go[i] = dao;
+                }
+                named_bar_sync(1, 128);
+                if (te == 0) REC_STAMP(8);
+                if (te == 0 && s + 1 < T) red_release_gpu_add(a.ctr + dir * a.nslices + slice, 1u);
+                if (te == 0) REC_STAMP(9);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + q * 8 + i;
+                    if (b >= a.B) continue;
+                    float* gp = a.gates + ((((long long)b * T + t) * a.ndir + dir) * G4) + u;
+                    gp[0] = gi[i]; gp[H] = gf[i]; gp[2 * H] = gg[i]; gp[3 * H] = go[i];
+                    // the (B*T, NG) bf16 copy the dX / dW GEMMs consume
+                    __nv_bfloat16* bp = a.dgb + ((long long)b * T + t) * NG + dir * G4 + u;
+                    bp[0] = __float2bfloat16(gi[i]); bp[H] = __float2bfloat16(gf[i]);
+                    bp[2 * H] = __float2bfloat16(gg[i]); bp[3 * H] = __float2bfloat16(go[i]);
+                }
+                if (te == 0) REC_STAMP(10);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                               // no CTA of the cluster exits while a peer may still read its smem
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+    }
+}
+
+}  // namespace
+
+// returns LAS_OK, or a negative code when this variant cannot run (caller falls back to las_lstm_rec_bwd_tc's streaming variant)
+static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16, const int* lens,
+                          const float* drop_mask, int B, int T, int H, int ndir, void* ws, cudaStream_t st, void* stream) {
+    if (H % 128 != 0) return LAS_ERR_UNSUPPORTED;
+    const LasDeviceInfo* di = las_device_info();
+    const int rs = 4 * (H / 128);
+    const int nslices = ceil_div(B, NB_SLICE);
+    int max_bsg = di->num_sms / (rs * ndir);
+    if (max_bsg < 1) return LAS_ERR_UNSUPPORTED;
+    const int bsg = nslices < max_bsg ? nslices : max_bsg;
+    const int chains = ceil_div(nslices, bsg);
+    if (chains > MAX_CHAINS) return LAS_ERR_UNSUPPORTED;
+    const int KB = H / 64;
+    const size_t smem = 1024 + (size_t)KB * 16384 + (size_t)chains * KB * 4096 + 2 * 32 * PART_LD * 4 + 16 + 8 * (2 * MAX_CHAINS + 2) + 64;
+    if (smem > (size_t)di->max_smem_optin) return LAS_ERR_UNSUPPORTED;
+    RecTcBwdArgs a{};
+    a.gates = gates; a.dgb = (__nv_bfloat16*)dgates_bf16; a.dout = dout; a.cs_pad = cs_pad; a.lens = lens; a.mask = drop_mask;
+    a.ctr = (unsigned*)ws;
+    a.B = B; a.T = T; a.H = H; a.ndir = ndir; a.nslices = nslices; a.chains = chains; a.bsg = bsg; a.KBr = 4 * H / 64; a.CH = KB; a.dbg = g_rec_dbg;
+    const long long NG = (long long)ndir * 4 * H;
+    CUtensorMap tmWt, tmG;
+    int rc = make_map_2d(&tmWt, w_hh_t_bf16, 4LL * H, (long long)ndir * H, 64, 128);
+    if (rc) return rc;
+    a.Bpad = nslices * NB_SLICE;
+    a.dgx = (__nv_bfloat16*)((char*)ws + 1024);
+    {   // exchange buffer (ndir*2*4*Bpad rows, H) viewed as (64, rows, H/64): one box = a 32 x H tile in k-block-major smem order
+        const long long dims[3] = {64, (long long)ndir * 2 * 4 * a.Bpad, KB};
+        const long long strides[2] = {H, 64};
+        const int box[3] = {64, NB_SLICE, KB};
+        rc = make_map_nd(&tmG, a.dgx, 3, dims, strides, box);
+        if (rc) return rc;
+    }
+    (void)NG;
+    if (cudaFuncSetAttribute(lstm_rec_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return LAS_ERR_UNSUPPORTED;
+    }
+    LAS_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
+    LasProfScope prof(LAS_PROF_REC_BWD, stream, (double)T);
+    void* args[] = {(void*)&tmWt, (void*)&tmG, (void*)&a};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)lstm_rec_bwd_tc2_kernel, dim3(rs, bsg, ndir), dim3(NTHREADS), args, smem, st);
+    if (e != cudaSuccess) {
+        las_set_error("lstm_rec_bwd_tc2 launch failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return LAS_ERR_UNSUPPORTED;
+    }
     las_count_launch(1);
     return LAS_OK;
 }

@@ -282,13 +282,13 @@ class LSTMLayerFunction(torch.autograd.Function):
         NG = ndir * G4
         dev = x.device
         dy = _f32c(dy)
-        nbytes = lib.las_lstm_rec_workspace_bytes(Bn, H, ndir)
+        rec_tc = tc and os.environ.get('LAS_REC_TC', '1') == '1' and bool(lib.las_lstm_rec_tc_supported(Bn, H, ndir))
+        nbytes = lib.las_lstm_rec_tc_workspace_bytes(Bn, H, ndir) if rec_tc else lib.las_lstm_rec_workspace_bytes(Bn, H, ndir)
         wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         # gates (activated) -> d(pre-activation), in place.  The forward's saved tensor is consumed: a second
         # backward through the same graph is not supported (like cuDNN's reserve space, it is single use).
         M = Bn * T
         dGb = None
-        rec_tc = tc and os.environ.get('LAS_REC_TC', '1') == '1' and bool(lib.las_lstm_rec_tc_supported(Bn, H, ndir))
         if rec_tc:
             w_hh_t = torch.empty(ndir, H, G4, dtype=torch.bfloat16, device=dev)
             check(lib.las_transpose_cast_bf16(w_hh.data_ptr(), w_hh_t.data_ptr(), ndir, G4, H, stream_ptr()), 'transpose_cast')

@@ -215,7 +215,7 @@ def test_tc_recurrence_backward_vs_fp32_kernel(H, B, T, lens):
     _lib.check(lib.las_transpose_cast_bf16(w_hh.data_ptr(), w_t.data_ptr(), ndir, 4 * H, H, st), 'transpose')
     assert torch.equal(w_t.float(), w_hh.transpose(1, 2).to(torch.bfloat16).float())
     dgb = torch.full((B * T, ndir * 4 * H), float('nan'), dtype=torch.bfloat16, device=DEV)
-    nb2 = max(nbytes, 1024)
+    nb2 = lib.las_lstm_rec_tc_workspace_bytes(B, H, ndir)
     ws2 = torch.empty(nb2, dtype=torch.uint8, device=DEV)
     _lib.check(lib.las_lstm_rec_bwd_tc(dout.data_ptr(), g_tc.data_ptr(), dgb.data_ptr(), cs.data_ptr(), w_t.data_ptr(), lens_dev.data_ptr(),
                                        mask.data_ptr(), B, T, H, ndir, ws2.data_ptr(), nb2, st), 'bwd_tc')
