@@ -24,6 +24,18 @@ __device__ __forceinline__ float4 ldg4_stream(const float* p) {
     return v;
 }
 
+// 4 consecutive elements of a K/V row as floats: fp32 rows -> one 128-bit load; bf16 rows (AMP mode) -> one 64-bit load
+template <bool KV16>
+__device__ __forceinline__ float4 load_kv4(const void* base, long long elem) {
+    if (KV16) {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"((const __nv_bfloat16*)base + elem));
+        return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                           __uint_as_float(r.y & 0xffff0000u));
+    }
+    return ldg4_stream((const float*)base + elem);
+}
+
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
     v = is_max ? warp_max(v) : warp_sum(v);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -39,7 +51,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 // phase A: s[t] = scale * dot(vec, M[t]) for t < len, over rows of M (B,T,P) restricted to one head
 // phase C: out[p] = sum_t s2[t] * M2[t][p]
 // Used as fwd (vec=q, M=K, M2=V) and bwd (vec=dctx, M=V, M2=K).
-template <bool BWD, int RU>
+template <bool BWD, int RU, bool KV16>
 __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
     extern __shared__ __align__(16) float sm[];
     const int T = a.T, P = a.P, heads = a.heads, d = P / heads;
@@ -50,8 +62,9 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
     const int bh = blockIdx.x, b = bh / heads, h = bh - b * heads;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int len = min(a.lens[b], T);
-    const float* Mat1 = (BWD ? a.V : a.K) + (long long)b * T * P + h * d;
-    const float* Mat2 = (BWD ? a.K : a.V) + (long long)b * T * P + h * d;
+    const void* Mat1 = BWD ? (const void*)a.V : (const void*)a.K;      // fp32 or bf16 (KV16) elements
+    const void* Mat2 = BWD ? (const void*)a.K : (const void*)a.V;
+    const long long mbase = (long long)b * T * P + h * d;
     const float* vec = (BWD ? a.dctx + (long long)b * a.ld_dctx : a.q + (long long)b * a.ld_q) + h * d;
     const int nch = (d + 127) / 128;
 
@@ -86,7 +99,7 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
 #pragma unroll
             for (int c = 0; c < MAXCH; ++c) {
                 int k = c * 128 + lane * 4;
-                m[r][c] = (t < len && c < nch && k < d) ? ldg4_stream(Mat1 + (long long)t * P + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                m[r][c] = (t < len && c < nch && k < d) ? load_kv4<KV16>(Mat1, mbase + (long long)t * P + k) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
 #pragma unroll
@@ -150,7 +163,7 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
 #pragma unroll
             for (int c = 0; c < MAXCH; ++c) {
                 int k = c * 128 + lane * 4;
-                m[r][c] = (t < len && c < nch && k < d) ? ldg4_stream(Mat2 + (long long)t * P + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                m[r][c] = (t < len && c < nch && k < d) ? load_kv4<KV16>(Mat2, mbase + (long long)t * P + k) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
 #pragma unroll
@@ -204,6 +217,19 @@ int check(const LasAttnStep* a, bool bwd) {
 
 size_t smem_bytes(const LasAttnStep* a) { return sizeof(float) * ((size_t)((a->T + 3) & ~3) + NW + (size_t)NW * (a->P / a->heads)); }
 
+template <bool BWD, int RU, bool KV16>
+int launch_one(const LasAttnStep* a, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<BWD, RU, KV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_step_kernel<BWD, RU, KV16><<<a->B * a->heads, NT, smem, st>>>(*a);
+    return LAS_OK;
+}
+template <bool BWD>
+int launch_attn(const LasAttnStep* a, size_t smem, cudaStream_t st) {
+    const bool big = a->B * a->heads >= las_device_info()->num_sms;
+    if (a->kv_bf16) return big ? launch_one<BWD, 4, true>(a, smem, st) : launch_one<BWD, 8, true>(a, smem, st);
+    return big ? launch_one<BWD, 4, false>(a, smem, st) : launch_one<BWD, 8, false>(a, smem, st);
+}
+
 }  // namespace
 
 extern "C" int las_attn_step_fwd_f32(const LasAttnStep* a, void* stream) {
@@ -212,15 +238,10 @@ extern "C" int las_attn_step_fwd_f32(const LasAttnStep* a, void* stream) {
     rc = las_set_device_of(a->K);
     if (rc) return rc;
     size_t smem = smem_bytes(a);
-    LasProfScope prof(LAS_PROF_ATTN_FWD, stream, 2.0 * a->B * (double)a->T * a->P * sizeof(float));
+    LasProfScope prof(LAS_PROF_ATTN_FWD, stream, 2.0 * a->B * (double)a->T * a->P * (a->kv_bf16 ? 2 : 4));
     // rows in flight per warp: 8 when the grid leaves SMs idle (train: 96 CTAs), 4 when it over-subscribes them (greedy: 256 CTAs)
-    if (a->B * a->heads >= las_device_info()->num_sms) {
-        if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_step_kernel<false, 4><<<a->B * a->heads, NT, smem, (cudaStream_t)stream>>>(*a);
-    } else {
-        if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_step_kernel<false, 8><<<a->B * a->heads, NT, smem, (cudaStream_t)stream>>>(*a);
-    }
+    rc = launch_attn<false>(a, smem, (cudaStream_t)stream);
+    if (rc) return rc;
     LAS_LAUNCH_CHECK();
     return LAS_OK;
 }
@@ -231,14 +252,9 @@ extern "C" int las_attn_step_bwd_f32(const LasAttnStep* a, void* stream) {
     rc = las_set_device_of(a->K);
     if (rc) return rc;
     size_t smem = smem_bytes(a);
-    LasProfScope prof(LAS_PROF_ATTN_BWD, stream, 2.0 * a->B * (double)a->T * a->P * sizeof(float));
-    if (a->B * a->heads >= las_device_info()->num_sms) {
-        if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_step_kernel<true, 4><<<a->B * a->heads, NT, smem, (cudaStream_t)stream>>>(*a);
-    } else {
-        if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_step_kernel<true, 8><<<a->B * a->heads, NT, smem, (cudaStream_t)stream>>>(*a);
-    }
+    LasProfScope prof(LAS_PROF_ATTN_BWD, stream, 2.0 * a->B * (double)a->T * a->P * (a->kv_bf16 ? 2 : 4));
+    rc = launch_attn<true>(a, smem, (cudaStream_t)stream);
+    if (rc) return rc;
     LAS_LAUNCH_CHECK();
     return LAS_OK;
 }

@@ -453,6 +453,7 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
     LasAttnStep at{};
     at.K = s->K; at.V = s->V_; at.lens = s->enc_lens; at.B = B; at.T = T; at.P = P; at.heads = heads;
     at.scale = sqrtf((float)(P / heads));
+    at.kv_bf16 = s->kv_bf16;
     at.ld_q = 2 * P; at.ld_ctx = 2 * P; at.ld_ctx2 = K0; at.ld_w = T;
     at.q = QC; at.ctx = QC + P; at.ctx2 = S0; at.w = W; at.w_b0 = s->att0;
     at.ctx2_bf16 = tc ? (void*)S0b : nullptr; at.ld_ctx2_bf16 = K0;
@@ -592,6 +593,7 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     LasAttnStep at{};
     at.K = s->K; at.V = s->V_; at.lens = s->enc_lens; at.B = B; at.T = T; at.P = P; at.heads = heads;
     at.scale = sqrtf((float)d_head);
+    at.kv_bf16 = s->kv_bf16;
     at.ld_q = 2 * P; at.ld_w = T; at.ld_dctx = 2 * P; at.ld_dctx2 = K0; at.ld_dq = 2 * P; at.dq_accumulate = 1;
     PlanBuf bq1, bq2, bq3;
     if (tc) {

@@ -460,7 +460,14 @@ class SpellerFunction(torch.autograd.Function):
         drop0 = _f32c(drop0) if drop0 is not None else None
         drop1 = _f32c(drop1) if drop1 is not None else None
         use_tc = use_tensor_cores() and os.environ.get('LAS_DEC_TC', '1') == '1'
+        kv16 = bool(use_tc) and P % 4 == 0 and os.environ.get('LAS_KV_BF16', '0') == '1'   # measured slower than fp32 rows with 64-bit loads: off by default
+        if kv16:
+            # AMP mode: the decoder re-reads K and V every step -- keep them as bf16 (half the bytes per step); the energies and
+            # the context still accumulate in fp32
+            K = cast_bf16(K, Bn * T, P, P, P).view(Bn, T, P)
+            V = cast_bf16(V, Bn * T, P, P, P).view(Bn, T, P)
         s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, use_tc)
+        s.kv_bf16 = int(kv16)
         logits = torch.empty(Bn, steps, Vn, dtype=torch.float32, device=dev)
         att0 = torch.empty(steps + 1, heads, T, dtype=torch.float32, device=dev)
         chars = torch.zeros(steps, Bn, dtype=torch.int32, device=dev)
@@ -473,7 +480,7 @@ class SpellerFunction(torch.autograd.Function):
         check(lib.las_speller_fwd_f32(C.byref(s), stream_ptr()), 'speller_fwd')
         if training:
             ctx.save_for_backward(K, V, enc_lens, dec_y, drop0, drop1, fws, iws, *params)
-            ctx.cfg = (use_gold, steps, heads, sos_idx, pad_idx, use_tc)
+            ctx.cfg = (use_gold, steps, heads, sos_idx, pad_idx, use_tc, kv16)
         ctx.mark_non_differentiable(att0, chars)
         return logits, att0, chars
 
@@ -481,8 +488,9 @@ class SpellerFunction(torch.autograd.Function):
     def backward(ctx, dlogits, _datt, _dchars):
         lib = _lib.load()
         K, V, enc_lens, dec_y, drop0, drop1, fws, iws, *params = ctx.saved_tensors
-        use_gold, steps, heads, sos_idx, pad_idx, use_tc = ctx.cfg
+        use_gold, steps, heads, sos_idx, pad_idx, use_tc, kv16 = ctx.cfg
         s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, True, use_tc)
+        s.kv_bf16 = int(kv16)
         s.fws, s.fws_floats, s.iws, s.iws_ints = fws.data_ptr(), fws.numel(), iws.data_ptr(), iws.numel()
         # outputs of fwd are not needed by bwd but the descriptor check wants non-null
         dummy = torch.empty(1, dtype=torch.int32, device=K.device)
@@ -494,7 +502,8 @@ class SpellerFunction(torch.autograd.Function):
         for name, t in zip(SPELLER_PARAM_ORDER, grads):
             setattr(g, 'd_' + name, t.data_ptr())
         # d_w_ih0 is written in three column/row pieces that together cover it; no zero-init needed
-        dK, dV = torch.empty_like(K), torch.empty_like(V)
+        dK = torch.empty(K.shape, dtype=torch.float32, device=K.device)
+        dV = torch.empty(V.shape, dtype=torch.float32, device=K.device)
         g.dK, g.dV = dK.data_ptr(), dV.data_ptr()
         check(lib.las_speller_bwd_f32(C.byref(s), C.byref(g), stream_ptr()), 'speller_bwd')
         return (dK, dV, None, None, None, None, None, None, None, None, None, None, *grads)

@@ -166,6 +166,7 @@ typedef struct {
     float scale;
     void* ctx2_bf16; long long ld_ctx2_bf16;   /* fwd: optional bf16 copy of the context (next cell-0 GEMM operand) */
     void* dq_bf16; long long ld_dq_bf16;       /* bwd: optional bf16 copy of the total dq */
+    int kv_bf16;                               /* 1: K and V point to bf16 (B,T,P) memory (AMP mode: half the bytes per step) */
 } LasAttnStep;
 int las_attn_step_fwd_f32(const LasAttnStep* desc, void* stream);
 int las_attn_step_bwd_f32(const LasAttnStep* desc, void* stream);
@@ -192,6 +193,7 @@ typedef struct {
     int sos_idx, pad_idx;
     int training;                 /* 1: save history for backward */
     int use_tc;                   /* 1: decoder GEMMs as bf16 tcgen05 tiles (AMP mode); fwd and bwd must agree */
+    int kv_bf16;                  /* 1: K and V_ point to bf16 (B,T,P) memory */
     /* parameters */
     const float* emb;             /* (V, E)  char_emb.weight == cls.weight */
     const float* cls_b;           /* (V) */
