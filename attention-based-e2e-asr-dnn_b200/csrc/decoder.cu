@@ -16,12 +16,15 @@
 #include "las_common.cuh"
 #include "las_b200.h"
 #include <vector>
+#include <stdlib.h>
 
 // prepared tensor-core GEMM plans (gemm_tc.cu): tensor maps encoded once per loop, one launch per step
 size_t las_tc_plan_bytes();
 int las_tc_plan_make(void* plan_mem, const void* A, const void* B, int M, int N, int K, int a_batches, long long a_s1, long long a_s2,
                      long long b_s1, int b_mn_major);
 int las_tc_plan_launch(const void* plan_mem, int a_batch, float* C, long long ldc, const float* bias1, const float* bias2, void* stream);
+int las_tc_plan_launch_lstm(const void* plan_mem, int a_batch, const LasLstmEpi* le, void* stream);
+int las_permute_cast_lstm_rows(const float* src, long long ld_src, void* dst, int H, int K, void* stream);
 
 namespace {
 
@@ -265,7 +268,7 @@ struct Layout {
     // float workspace offsets
     size_t Wcat0, Wcat1, Gemb, S0, S1, C0, C1, G0, G1, QC, W, dQC, dS0, dS1, dc0, dc1, dh1, DE, dGemb, tmpq, cs_scratch, total_f;
     // bf16 region (offsets in floats, buffers hold bf16): tensor-pipe mode only
-    size_t Wcat0b, Wcat1b, Wqb, S0b, S1b, G0b, G1b, dQb, dlb, ohb, QCb, tmp32, skws;
+    size_t Wcat0b, Wcat1b, Wqb, S0b, S1b, G0b, G1b, dQb, dlb, ohb, QCb, tmp32, skws, Wcat0p, Wcat1p;
     size_t skws_floats;
     // int workspace offsets
     size_t tok, total_i;
@@ -310,6 +313,8 @@ Layout make_layout(const LasSpeller* s) {
         L.Wcat0b = takeb(4 * DH * (P + DH));
         L.Wcat1b = takeb(4 * DO * (DH + DO));
         L.Wqb = takeb(P * DO);
+        L.Wcat0p = takeb(4 * DH * (P + DH));       // row-permuted copies for the fused LSTM epilogue (forward)
+        L.Wcat1p = takeb(4 * DO * (DH + DO));
         L.S0b = takeb((size_t)L.hist * B * (P + DH));
         L.S1b = takeb((size_t)L.hist * B * (DH + DO));
         if (s->training) {
@@ -428,10 +433,19 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
         LAS_CUDA(cudaMemset2DAsync(S1b + DH, K1 * 2, 0, DO * 2, B, st));      // h1_{-1} = 0
     }
     PlanBuf pl0, pl1, plq;
+    // LSTM pointwise fused into the GEMM epilogue: measured SLOWER than GEMM + coalesced cell kernel (thread-per-row epilogue
+    // accesses are uncoalesced), so it is opt-in (LAS_DEC_FUSE=1) until the epilogue is staged through shared memory
+    const char* fuse_env = getenv("LAS_DEC_FUSE");
+    const bool fuse = tc && DH % 16 == 0 && DO % 16 == 0 && fuse_env && atoi(fuse_env) == 1;
     if (tc) {
         LAS_CHECK_ARG(las_tc_plan_bytes() <= sizeof(PlanBuf), "speller: plan buffer too small");
-        RC(las_tc_plan_make(&pl0, S0b, Wcat0b, B, 4 * DH, K0, L.hist, K0, (long long)B * K0, K0, 0));
-        RC(las_tc_plan_make(&pl1, S1b, Wcat1b, B, 4 * DO, K1, L.hist, K1, (long long)B * K1, K1, 0));
+        __nv_bfloat16 *Wcat0p = (__nv_bfloat16*)(f + L.Wcat0p), *Wcat1p = (__nv_bfloat16*)(f + L.Wcat1p);
+        if (fuse) {
+            RC(las_permute_cast_lstm_rows(Wcat0, K0, Wcat0p, DH, K0, st));
+            RC(las_permute_cast_lstm_rows(Wcat1, K1, Wcat1p, DO, K1, st));
+        }
+        RC(las_tc_plan_make(&pl0, S0b, fuse ? Wcat0p : Wcat0b, B, 4 * DH, K0, L.hist, K0, (long long)B * K0, K0, 0));
+        RC(las_tc_plan_make(&pl1, S1b, fuse ? Wcat1p : Wcat1b, B, 4 * DO, K1, L.hist, K1, (long long)B * K1, K1, 0));
         RC(las_tc_plan_make(&plq, S1b + DH, Wqb, B, P, DO, L.hist, K1, (long long)B * K1, DO, 0));
     }
     // embedding-side gate table (+ both cell-0 biases)
@@ -472,37 +486,60 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
         float* QCn = QC + (size_t)rn * B * 2 * P;
         __nv_bfloat16* S0rb = S0b + (size_t)r * B * K0;  __nv_bfloat16* S0nb = S0b + (size_t)rn * B * K0;
         __nv_bfloat16* S1rb = S1b + (size_t)r * B * K1;  __nv_bfloat16* S1nb = S1b + (size_t)rn * B * K1;
+        // cell 0 and cell 1
+        if (fuse) {
+            LasLstmEpi e0{};
+            e0.H = DH; e0.tab = Gemb; e0.y = s->dec_y; e0.ld_y = s->ld_y;
+            e0.chars_prev = (t > 0) ? s->chars + (size_t)(t - 1) * B : nullptr;
+            e0.tok_out = s->training ? tok + (size_t)t * B : nullptr;
+            e0.t = t; e0.sos_idx = s->sos_idx;
+            e0.use_gold = (s->training && t > 0 && s->use_gold_host && s->use_gold_host[t]) ? 1 : 0;
+            e0.c_prev = C0 + (size_t)r * B * DH; e0.ld_cp = DH; e0.c_out = C0 + (size_t)rn * B * DH; e0.ld_co = DH;
+            e0.mask = s->drop0 ? s->drop0 + (size_t)t * B * DH : nullptr;
+            e0.G = G0r;
+            e0.h1 = S0n + P; e0.ld_h1 = K0; e0.h2 = S1r; e0.ld_h2 = K1;
+            e0.h1b = S0nb + P; e0.ld_h1b = K0; e0.h2b = S1rb; e0.ld_h2b = K1;
+            RC(las_tc_plan_launch_lstm(&pl0, r, &e0, st));
+            LasLstmEpi e1{};
+            e1.H = DO; e1.bias1 = s->b_ih1; e1.bias2 = s->b_hh1; e1.t = t;
+            e1.c_prev = C1 + (size_t)r * B * DO; e1.ld_cp = DO; e1.c_out = C1 + (size_t)rn * B * DO; e1.ld_co = DO;
+            e1.mask = s->drop1 ? s->drop1 + (size_t)t * B * DO : nullptr;
+            e1.G = G1r;
+            e1.h1 = S1n + DH; e1.ld_h1 = K1; e1.h1b = S1nb + DH; e1.ld_h1b = K1;
+            RC(las_tc_plan_launch_lstm(&pl1, r, &e1, st));
+        } else {
         // cell 0
-        if (tc) RC(las_tc_plan_launch(&pl0, r, G0r, 4 * DH, nullptr, nullptr, st));
-        else RC(gemm(st, S0r, K0, Wcat0, K0, 1, G0r, 4 * DH, B, 4 * DH, K0));
-        CellFwd c0{};
-        c0.G = G0r; c0.Gtab = Gemb; c0.y = s->dec_y; c0.ld_y = s->ld_y;
-        c0.chars_prev = (t > 0) ? s->chars + (size_t)(t - 1) * B : nullptr;
-        c0.tok_out = s->training ? tok + (size_t)t * B : nullptr;
-        c0.t = t; c0.sos_idx = s->sos_idx;
-        c0.use_gold = (s->training && t > 0 && s->use_gold_host && s->use_gold_host[t]) ? 1 : 0;
-        c0.c_prev = C0 + (size_t)r * B * DH; c0.ld_cp = DH;
-        c0.c_out = C0 + (size_t)rn * B * DH; c0.ld_co = DH;
-        c0.mask = s->drop0 ? s->drop0 + (size_t)t * B * DH : nullptr;
-        c0.h1 = S0n + P; c0.ld_h1 = K0;      // recurrent slot of the next step's cell-0 row
-        c0.h2 = S1r; c0.ld_h2 = K1;          // input slot of this step's cell-1 row
-        if (tc) { c0.h1b = S0nb + P; c0.ld_h1b = K0; c0.h2b = S1rb; c0.ld_h2b = K1; }
-        c0.B = B; c0.H = DH;
-        cell_fwd_kernel<<<ceil_div(B * DH, 256), 256, 0, st>>>(c0);
-        LAS_LAUNCH_CHECK();
-        // cell 1
-        if (tc) RC(las_tc_plan_launch(&pl1, r, G1r, 4 * DO, s->b_ih1, s->b_hh1, st));
-        else RC(gemm(st, S1r, K1, Wcat1, K1, 1, G1r, 4 * DO, B, 4 * DO, K1, 0.f, s->b_ih1, s->b_hh1));
-        CellFwd c1{};
-        c1.G = G1r; c1.Gtab = nullptr; c1.t = t;
-        c1.c_prev = C1 + (size_t)r * B * DO; c1.ld_cp = DO;
-        c1.c_out = C1 + (size_t)rn * B * DO; c1.ld_co = DO;
-        c1.mask = s->drop1 ? s->drop1 + (size_t)t * B * DO : nullptr;
-        c1.h1 = S1n + DH; c1.ld_h1 = K1; c1.h2 = nullptr;
-        if (tc) { c1.h1b = S1nb + DH; c1.ld_h1b = K1; }
-        c1.B = B; c1.H = DO;
-        cell_fwd_kernel<<<ceil_div(B * DO, 256), 256, 0, st>>>(c1);
-        LAS_LAUNCH_CHECK();
+            if (tc) RC(las_tc_plan_launch(&pl0, r, G0r, 4 * DH, nullptr, nullptr, st));
+            else RC(gemm(st, S0r, K0, Wcat0, K0, 1, G0r, 4 * DH, B, 4 * DH, K0));
+            CellFwd c0{};
+            c0.G = G0r; c0.Gtab = Gemb; c0.y = s->dec_y; c0.ld_y = s->ld_y;
+            c0.chars_prev = (t > 0) ? s->chars + (size_t)(t - 1) * B : nullptr;
+            c0.tok_out = s->training ? tok + (size_t)t * B : nullptr;
+            c0.t = t; c0.sos_idx = s->sos_idx;
+            c0.use_gold = (s->training && t > 0 && s->use_gold_host && s->use_gold_host[t]) ? 1 : 0;
+            c0.c_prev = C0 + (size_t)r * B * DH; c0.ld_cp = DH;
+            c0.c_out = C0 + (size_t)rn * B * DH; c0.ld_co = DH;
+            c0.mask = s->drop0 ? s->drop0 + (size_t)t * B * DH : nullptr;
+            c0.h1 = S0n + P; c0.ld_h1 = K0;      // recurrent slot of the next step's cell-0 row
+            c0.h2 = S1r; c0.ld_h2 = K1;          // input slot of this step's cell-1 row
+            if (tc) { c0.h1b = S0nb + P; c0.ld_h1b = K0; c0.h2b = S1rb; c0.ld_h2b = K1; }
+            c0.B = B; c0.H = DH;
+            cell_fwd_kernel<<<ceil_div(B * DH, 256), 256, 0, st>>>(c0);
+            LAS_LAUNCH_CHECK();
+            // cell 1
+            if (tc) RC(las_tc_plan_launch(&pl1, r, G1r, 4 * DO, s->b_ih1, s->b_hh1, st));
+            else RC(gemm(st, S1r, K1, Wcat1, K1, 1, G1r, 4 * DO, B, 4 * DO, K1, 0.f, s->b_ih1, s->b_hh1));
+            CellFwd c1{};
+            c1.G = G1r; c1.Gtab = nullptr; c1.t = t;
+            c1.c_prev = C1 + (size_t)r * B * DO; c1.ld_cp = DO;
+            c1.c_out = C1 + (size_t)rn * B * DO; c1.ld_co = DO;
+            c1.mask = s->drop1 ? s->drop1 + (size_t)t * B * DO : nullptr;
+            c1.h1 = S1n + DH; c1.ld_h1 = K1; c1.h2 = nullptr;
+            if (tc) { c1.h1b = S1nb + DH; c1.ld_h1b = K1; }
+            c1.B = B; c1.H = DO;
+            cell_fwd_kernel<<<ceil_div(B * DO, 256), 256, 0, st>>>(c1);
+            LAS_LAUNCH_CHECK();
+        }
         // query projection into QC[t+1][:, :P]
         if (tc) RC(las_tc_plan_launch(&plq, rn, QCn, 2 * P, s->bq, nullptr, st));
         else RC(gemm(st, S1n + DH, K1, s->wq, DO, 1, QCn, 2 * P, B, P, DO, 0.f, s->bq));

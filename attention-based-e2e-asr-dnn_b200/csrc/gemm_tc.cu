@@ -53,6 +53,7 @@ struct TcArgs {
     int accumulate;   // C += result
     const int* lens;  // optional (NB): skip M tiles whose first row >= lens[b] (rows past a sequence's length)
     int b_first;      // first M-batch index (prepared plans address one batch of a multi-batch tensor map per launch)
+    LasLstmEpi le;    // fused LSTM-cell epilogue (EPI == 1 instantiation only)
     int splitk;       // >1: the K range of every output tile is split over `splitk` CTAs writing partials to Cpart
     float* Cpart;     // (splitk, R, ldp) partial sums
     long long ldp;
@@ -145,7 +146,14 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) 
            ((uint32_t)(BM >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN, int BN>
+__device__ __forceinline__ float tc_tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float tc_sigmoid_fast(float x) { return fmaf(0.5f, tc_tanh_fast(0.5f * x), 0.5f); }
+
+template <bool A_MN, bool B_MN, int BN, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
     constexpr int STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
@@ -259,6 +267,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
             if (g.lens && mtile * BM >= g.lens[b]) continue;
             mbar_wait(tfull_bar(acc), accphase);
             tc_fence_after();
+            if (EPI == 1) {
+                // ---- fused LSTM cell: this thread = batch row, tile = units [ntile*16, +16) x gates (i|f|g|o) ----
+                const LasLstmEpi& le = g.le;
+                const int H = le.H, bb = mtile * BM + q * 32 + lane, ub = ntile * 16;
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, v0);          // [i(16) | f(16)]
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + 32, v1);     // [g(16) | o(16)]
+                if (bb < g.R) {
+                    const float* tr = nullptr;
+                    if (le.tab) {
+                        int tok;
+                        if (le.t == 0) tok = le.sos_idx;
+                        else if (le.use_gold) tok = le.y[(long long)bb * le.ld_y + le.t - 1];
+                        else tok = le.chars_prev[bb];
+                        if (le.tok_out && ntile == 0) le.tok_out[bb] = tok;
+                        tr = le.tab + (long long)tok * 4 * H;
+                    }
+                    const float* cp = le.c_prev + (long long)bb * le.ld_cp;
+                    float* co = le.c_out + (long long)bb * le.ld_co;
+                    float* gout = le.G + (long long)bb * 4 * H;
+#pragma unroll
+                    for (int ul = 0; ul < 16; ++ul) {
+                        const int u = ub + ul;
+                        if (u < H) {
+                            float p0 = __uint_as_float(v0[ul]), p1 = __uint_as_float(v0[16 + ul]);
+                            float p2 = __uint_as_float(v1[ul]), p3 = __uint_as_float(v1[16 + ul]);
+                            if (tr) { p0 += tr[u]; p1 += tr[H + u]; p2 += tr[2 * H + u]; p3 += tr[3 * H + u]; }
+                            if (le.bias1) { p0 += le.bias1[u]; p1 += le.bias1[H + u]; p2 += le.bias1[2 * H + u]; p3 += le.bias1[3 * H + u]; }
+                            if (le.bias2) { p0 += le.bias2[u]; p1 += le.bias2[H + u]; p2 += le.bias2[2 * H + u]; p3 += le.bias2[3 * H + u]; }
+                            const float gi = tc_sigmoid_fast(p0), gf = tc_sigmoid_fast(p1), gg = tc_tanh_fast(p2), go = tc_sigmoid_fast(p3);
+                            const float c = fmaf(gf, cp[u], gi * gg);
+                            float h = go * tc_tanh_fast(c);
+                            if (le.mask) h *= le.mask[(long long)bb * H + u];
+                            gout[u] = gi; gout[H + u] = gf; gout[2 * H + u] = gg; gout[3 * H + u] = go;
+                            co[u] = c;
+                            le.h1[(long long)bb * le.ld_h1 + u] = h;
+                            if (le.h2) le.h2[(long long)bb * le.ld_h2 + u] = h;
+                            if (le.h1b) le.h1b[(long long)bb * le.ld_h1b + u] = __float2bfloat16(h);
+                            if (le.h2b) le.h2b[(long long)bb * le.ld_h2b + u] = __float2bfloat16(h);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                if (++acc == 2) { acc = 0; accphase ^= 1u; }
+                continue;
+            }
             const int r0 = mtile * BM + q * 32;                     // first row of this warp's 32-row band
             float* cbase;
             long long ldo;
@@ -382,9 +438,9 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     }
 }
 
-template <bool A_MN, bool B_MN, int BN>
+template <bool A_MN, bool B_MN, int BN, int EPI = 0>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, cudaStream_t st) {
-    auto kern = gemm_bf16_tc_kernel<A_MN, B_MN, BN>;
+    auto kern = gemm_bf16_tc_kernel<A_MN, B_MN, BN, EPI>;
     constexpr int SMEM_BYTES = Cfg<BN>::SMEM_BYTES;
     static bool attr_set = false;
     if (!attr_set) {
@@ -435,6 +491,35 @@ int las_tc_plan_launch(const void* plan_mem, int a_batch, float* C, long long ld
     g.c_bs = 0;
     if (p->variant == 0) return launch_tc<false, false, 64>(p->ta, p->tb, g, (cudaStream_t)stream);
     return launch_tc<false, true, 64>(p->ta, p->tb, g, (cudaStream_t)stream);
+}
+
+// plan launch with the fused LSTM-cell epilogue (plan must be the K-major-B form with permuted weight rows, N = 4H)
+int las_tc_plan_launch_lstm(const void* plan_mem, int a_batch, const LasLstmEpi* le, void* stream) {
+    const LasTcPlan* p = (const LasTcPlan*)plan_mem;
+    LAS_CHECK_ARG(p->variant == 0 && le && le->H % 16 == 0 && p->g.N == 4 * le->H, "tc plan (lstm epilogue): bad plan / H");
+    TcArgs g = p->g;
+    g.C = nullptr; g.b_first = a_batch; g.le = *le;
+    LasProfScope prof(LAS_PROF_GEMM_OTHER, stream, 2.0 * g.R * (double)g.N * g.kt_per_b * BK);
+    return launch_tc<false, false, 64, 1>(p->ta, p->tb, g, (cudaStream_t)stream);
+}
+
+// dst[n'][k] (bf16) = src[perm(n')][k]: rows regrouped so each 64-row block is 16 units x (i|f|g|o); src is gate-major (4H, K)
+__global__ void __launch_bounds__(256) permute_cast_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst,
+                                                           int H, int K) {
+    const long long total = (long long)4 * H * K;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int np = (int)(i / K), k = (int)(i - (long long)np * K);
+        const int nt = np >> 6, j = np & 63, gidx = j >> 4, ul = j & 15;
+        dst[i] = __float2bfloat16(src[(long long)(gidx * H + nt * 16 + ul) * ld_src + k]);
+    }
+}
+int las_permute_cast_lstm_rows(const float* src, long long ld_src, void* dst, int H, int K, void* stream) {
+    LAS_CHECK_ARG(src && dst && H % 16 == 0 && K >= 1, "permute_cast: bad arguments");
+    const long long total = (long long)4 * H * K;
+    int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    permute_cast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__nv_bfloat16*)dst, H, K);
+    LAS_LAUNCH_CHECK();
+    return LAS_OK;
 }
 
 extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {

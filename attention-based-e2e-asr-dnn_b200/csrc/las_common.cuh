@@ -109,3 +109,22 @@ private:
     size_t idx_;
     void* stream_;
 };
+
+// ---- fused LSTM-cell epilogue of the decoder-step tensor-core GEMM (gemm_tc.cu <-> decoder.cu) ----
+// The GEMM's B operand rows are permuted so that every 64-column tile holds 16 units x 4 gates ([i|f|g|o] x 16); each epilogue
+// thread owns one batch row and finishes those 16 units: + table/bias, nonlinearities, cell update, dropout, all outputs.
+struct LasLstmEpi {
+    int H;                                        // units of this cell (GEMM N = 4H)
+    const float* tab;                             // optional (V, 4H) table gathered by token (gate-major layout)
+    const float* bias1; const float* bias2;       // optional (4H) biases (gate-major layout)
+    const int* y; long long ld_y;                 // gold tokens (B, >= steps) or null
+    const int* chars_prev;                        // (B) greedy argmax of the previous step or null
+    int* tok_out;                                 // (B) token fed this step (saved for backward) or null
+    int t, use_gold, sos_idx;
+    const float* c_prev; long long ld_cp;
+    float* c_out; long long ld_co;
+    const float* mask;                            // (B, H) dropout mask or null
+    float* G;                                     // (B, 4H) activated gates, gate-major layout (saved for backward)
+    float* h1; long long ld_h1; float* h2; long long ld_h2;                       // fp32 destinations (h2 nullable)
+    __nv_bfloat16* h1b; long long ld_h1b; __nv_bfloat16* h2b; long long ld_h2b;   // bf16 destinations (nullable)
+};
