@@ -117,6 +117,7 @@ LasProfScope::~LasProfScope() {
 }
 
 extern "C" void las_prof_enable(unsigned kind_mask) { g_prof_mask.store(kind_mask); }
+unsigned las_prof_mask_get() { return g_prof_mask.load(std::memory_order_relaxed); }
 
 extern "C" void las_prof_reset(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
