@@ -9,6 +9,7 @@
 #include "las_common.cuh"
 #include "las_b200.h"
 #include <float.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -197,6 +198,234 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Single-pass, T-split variant (the default path).
+//   * grid (S, B*heads), cluster (S,1,1): the S CTAs of a cluster split the valid rows [0, len) of one (batch row, head),
+//     so B = 96 fills all 148 SMs instead of 96 of them;
+//   * K[t] and V[t] of a row are loaded TOGETHER (all loads of an iteration are issued before any arithmetic), so the
+//     kernel is one pass over memory with no dependent second phase:
+//       fwd: online softmax (running max / sum / weighted V sum per warp), merged across warps in shared memory and
+//            across the cluster through distributed shared memory; w[t] = exp(e_t - M) / S is written once M, S are final;
+//       bwd: sum_t w_t (dctx . V_t) == dctx . ctx, so with the saved context the softmax backward needs no pre-pass:
+//            de_t = w_t (dctx . V_t - dctx . ctx) scale ;  dq = sum_t de_t K_t.
+// K and V are still read exactly once per step.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int NT2 = 256;
+constexpr int NW2 = NT2 / 32;
+constexpr int RU2 = 4;        // (K row + V row) x 4 in flight per warp: 8 KB (fp32, d = 256)
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, unsigned rank) {
+    unsigned la = (unsigned)__cvta_generic_to_shared(local_ptr), ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+template <bool BWD, bool KV16>
+__global__ void __launch_bounds__(NT2, 2) attn_step_split_kernel(LasAttnStep a) {
+    extern __shared__ __align__(16) float sm[];
+    const int T = a.T, P = a.P, heads = a.heads, d = P / heads;
+    const int S = gridDim.x, rank = blockIdx.x;
+    const int bh = blockIdx.y, b = bh / heads, h = bh - b * heads;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int len = min(a.lens[b], T);
+    const int per = (len + S - 1) / S;                       // rows of this (row, head) per CTA
+    const int cap = ((T + S - 1) / S + 3) & ~3;
+    const int t_lo = min(rank * per, len), t_hi = min(t_lo + per, len);
+    float* sc = sm;                 // [cap]    fwd: scaled energies of this CTA's rows
+    float* wm = sm + cap;           // [NW2]    per-warp running max
+    float* wsum = wm + NW2;         // [NW2]    per-warp running sum
+    float* cl = wsum + NW2;         // [2*8]    (m, s) of every CTA of the cluster, gathered
+    float* cta_ms = cl + 16;        // [4]      this CTA's (m, s)
+    float* cta_o = cta_ms + 4;      // [d]      this CTA's partial output vector
+    float* part = cta_o + d;        // [NW2][d] per-warp partial output vectors
+    const void* MatK = a.K;
+    const void* MatV = a.V;
+    const long long mbase = (long long)b * T * P + h * d;
+    const float* vec = (BWD ? a.dctx + (long long)b * a.ld_dctx : a.q + (long long)b * a.ld_q) + h * d;
+    const int nch = (d + 127) / 128;
+
+    float4 v4[MAXCH];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXCH; ++c) {
+        const int k = c * 128 + lane * 4;
+        const bool in = c < nch && k < d;
+        v4[c] = in ? *reinterpret_cast<const float4*>(vec + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (BWD && in) {
+            if (a.dctx2) {      // dctx_total = classifier path + next step's cell-0 input path
+                const float4 e = *reinterpret_cast<const float4*>(a.dctx2 + (long long)b * a.ld_dctx2 + h * d + k);
+                v4[c].x += e.x; v4[c].y += e.y; v4[c].z += e.z; v4[c].w += e.w;
+            }
+            const float4 c4 = *reinterpret_cast<const float4*>(a.ctx + (long long)b * a.ld_ctx + h * d + k);
+            dot = fmaf(v4[c].x, c4.x, dot); dot = fmaf(v4[c].y, c4.y, dot); dot = fmaf(v4[c].z, c4.z, dot); dot = fmaf(v4[c].w, c4.w, dot);
+        }
+    }
+    if (BWD) dot = warp_sum(dot);
+    const float* wrow_c = a.w + ((long long)b * heads + h) * a.ld_w;
+
+    float m_run = -INFINITY, s_run = 0.f;
+    float4 o4[MAXCH];
+#pragma unroll
+    for (int c = 0; c < MAXCH; ++c) o4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int tb = t_lo + w; tb < t_hi; tb += NW2 * RU2) {
+        float4 kk[RU2][MAXCH], vv[RU2][MAXCH];
+        float wt[RU2];
+#pragma unroll
+        for (int r = 0; r < RU2; ++r) {
+            const int t = tb + r * NW2;
+            const bool ok = t < t_hi;
+#pragma unroll
+            for (int c = 0; c < MAXCH; ++c) {
+                const int k = c * 128 + lane * 4;
+                const bool in = ok && c < nch && k < d;
+                kk[r][c] = in ? load_kv4<KV16>(MatK, mbase + (long long)t * P + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vv[r][c] = in ? load_kv4<KV16>(MatV, mbase + (long long)t * P + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            wt[r] = (BWD && ok) ? wrow_c[t] : 0.f;
+        }
+        float e[RU2];
+#pragma unroll
+        for (int r = 0; r < RU2; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < MAXCH; ++c) {
+                const float4 m = BWD ? vv[r][c] : kk[r][c];
+                acc = fmaf(m.x, v4[c].x, acc); acc = fmaf(m.y, v4[c].y, acc);
+                acc = fmaf(m.z, v4[c].z, acc); acc = fmaf(m.w, v4[c].w, acc);
+            }
+            e[r] = warp_sum(acc);
+        }
+        if (!BWD) {
+            float m_new = m_run;
+#pragma unroll
+            for (int r = 0; r < RU2; ++r) {
+                const int t = tb + r * NW2;
+                e[r] = (t < t_hi) ? e[r] * a.scale : -INFINITY;
+                if (lane == 0 && t < t_hi) sc[t - t_lo] = e[r];
+                m_new = fmaxf(m_new, e[r]);
+            }
+            const float f = expf(m_run - m_new);          // first iteration: exp(-inf) = 0 ; row tb itself is valid, so m_new is finite
+            s_run *= f;
+#pragma unroll
+            for (int c = 0; c < MAXCH; ++c) { o4[c].x *= f; o4[c].y *= f; o4[c].z *= f; o4[c].w *= f; }
+#pragma unroll
+            for (int r = 0; r < RU2; ++r) {
+                const float p = expf(e[r] - m_new);
+                s_run += p;
+#pragma unroll
+                for (int c = 0; c < MAXCH; ++c) {
+                    o4[c].x = fmaf(p, vv[r][c].x, o4[c].x); o4[c].y = fmaf(p, vv[r][c].y, o4[c].y);
+                    o4[c].z = fmaf(p, vv[r][c].z, o4[c].z); o4[c].w = fmaf(p, vv[r][c].w, o4[c].w);
+                }
+            }
+            m_run = m_new;
+        } else {
+            float* derow = a.de + ((long long)b * heads + h) * a.ld_w;
+#pragma unroll
+            for (int r = 0; r < RU2; ++r) {
+                const int t = tb + r * NW2;
+                const float de = wt[r] * (e[r] - dot) * a.scale;      // 0 for rows past t_hi (wt = 0)
+                if (lane == 0 && t < t_hi) derow[t] = de;
+#pragma unroll
+                for (int c = 0; c < MAXCH; ++c) {
+                    o4[c].x = fmaf(de, kk[r][c].x, o4[c].x); o4[c].y = fmaf(de, kk[r][c].y, o4[c].y);
+                    o4[c].z = fmaf(de, kk[r][c].z, o4[c].z); o4[c].w = fmaf(de, kk[r][c].w, o4[c].w);
+                }
+            }
+        }
+    }
+    // ---- merge the warps of this CTA ----
+    if (lane == 0) { wm[w] = m_run; wsum[w] = s_run; }
+#pragma unroll
+    for (int c = 0; c < MAXCH; ++c) {
+        const int k = c * 128 + lane * 4;
+        if (c < nch && k < d) *reinterpret_cast<float4*>(part + w * d + k) = o4[c];
+    }
+    __syncthreads();
+    float m_c = -INFINITY;
+    if (!BWD) {
+#pragma unroll
+        for (int i = 0; i < NW2; ++i) m_c = fmaxf(m_c, wm[i]);
+    }
+    for (int p = tid; p < d; p += NT2) {
+        float r = 0.f;
+#pragma unroll
+        for (int i = 0; i < NW2; ++i) {
+            const float f = BWD ? 1.f : ((wm[i] == -INFINITY) ? 0.f : expf(wm[i] - m_c));
+            r = fmaf(f, part[i * d + p], r);
+        }
+        cta_o[p] = r;
+    }
+    if (!BWD && tid == 0) {
+        float s_c = 0.f;
+#pragma unroll
+        for (int i = 0; i < NW2; ++i) s_c += (wm[i] == -INFINITY) ? 0.f : wsum[i] * expf(wm[i] - m_c);
+        cta_ms[0] = m_c; cta_ms[1] = s_c;
+    }
+    cluster_sync_all();          // every CTA's (m, s, o) is in its shared memory and visible cluster-wide
+    float M = 0.f, inv = 1.f;
+    if (!BWD) {
+        if (tid < 2 * S) cl[tid] = ld_dsmem_f32(cta_ms + (tid & 1), (unsigned)(tid >> 1));
+        __syncthreads();
+        M = -INFINITY;
+        for (int j = 0; j < S; ++j) M = fmaxf(M, cl[2 * j]);
+        float tot = 0.f;
+        for (int j = 0; j < S; ++j) tot += (cl[2 * j] == -INFINITY) ? 0.f : cl[2 * j + 1] * expf(cl[2 * j] - M);
+        inv = 1.f / tot;
+        // normalised weights of this CTA's rows; exact zeros past the length (src/models.py:171-175)
+        float* wrow = a.w + ((long long)b * heads + h) * a.ld_w;
+        for (int t = t_lo + tid; t < t_hi; t += NT2) {
+            const float wv = expf(sc[t - t_lo] - M) * inv;
+            wrow[t] = wv;
+            if (b == 0 && a.w_b0) a.w_b0[(long long)h * T + t] = wv;
+        }
+        for (int t = len + rank * NT2 + tid; t < T; t += S * NT2) {
+            wrow[t] = 0.f;
+            if (b == 0 && a.w_b0) a.w_b0[(long long)h * T + t] = 0.f;
+        }
+    } else {
+        float* derow = a.de + ((long long)b * heads + h) * a.ld_w;
+        for (int t = len + rank * NT2 + tid; t < T; t += S * NT2) derow[t] = 0.f;
+        if (a.dctx2 && rank == 0 && w == 0) {       // every CTA read dctx before the cluster barrier above
+#pragma unroll
+            for (int c = 0; c < MAXCH; ++c) {
+                const int k = c * 128 + lane * 4;
+                if (c < nch && k < d) *reinterpret_cast<float4*>(a.dctx + (long long)b * a.ld_dctx + h * d + k) = v4[c];
+            }
+        }
+    }
+    // ---- output columns [rank*dper, (rank+1)*dper) of this (row, head): sum the cluster's partial vectors over DSMEM ----
+    const int dper = (d + S - 1) / S;
+    for (int i = tid; i < dper; i += NT2) {
+        const int p = rank * dper + i;
+        if (p >= d) break;
+        float r = 0.f;
+        for (int j = 0; j < S; ++j) {
+            const float f = BWD ? 1.f : ((cl[2 * j] == -INFINITY) ? 0.f : expf(cl[2 * j] - M));
+            r = fmaf(f, ld_dsmem_f32(cta_o + p, (unsigned)j), r);
+        }
+        if (!BWD) {
+            r *= inv;
+            a.ctx[(long long)b * a.ld_ctx + h * d + p] = r;
+            if (a.ctx2) a.ctx2[(long long)b * a.ld_ctx2 + h * d + p] = r;
+            if (a.ctx2_bf16) ((__nv_bfloat16*)a.ctx2_bf16)[(long long)b * a.ld_ctx2_bf16 + h * d + p] = __float2bfloat16(r);
+        } else {
+            float* dq = a.dq + (long long)b * a.ld_dq + h * d + p;
+            const float tot = (a.dq_accumulate ? *dq : 0.f) + r;
+            *dq = tot;
+            if (a.dq_bf16) ((__nv_bfloat16*)a.dq_bf16)[(long long)b * a.ld_dq_bf16 + h * d + p] = __float2bfloat16(tot);
+        }
+    }
+    cluster_sync_all();          // keep this CTA's shared memory alive until every peer has read it
+}
+
 int check(const LasAttnStep* a, bool bwd) {
     LAS_CHECK_ARG(a != nullptr, "attn_step: null descriptor");
     LAS_CHECK_ARG(a->B >= 1 && a->T >= 1 && a->P >= 4 && a->heads >= 1, "attn_step: bad dims B=%d T=%d P=%d heads=%d", a->B,
@@ -223,8 +452,43 @@ int launch_one(const LasAttnStep* a, size_t smem, cudaStream_t st) {
     attn_step_kernel<BWD, RU, KV16><<<a->B * a->heads, NT, smem, st>>>(*a);
     return LAS_OK;
 }
+template <bool BWD, bool KV16>
+int launch_split(const LasAttnStep* a, int S, cudaStream_t st) {
+    const int d = a->P / a->heads;
+    const int cap = ((a->T + S - 1) / S + 3) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)cap + 2 * NW2 + 16 + 4 + d + (size_t)NW2 * d);
+    if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_split_kernel<BWD, KV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(S, a->B * a->heads, 1);
+    cfg.blockDim = dim3(NT2, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    LAS_CUDA(cudaLaunchKernelEx(&cfg, attn_step_split_kernel<BWD, KV16>, *a));
+    return LAS_OK;
+}
+
+// CTAs per (batch row, head).  Measured on B200 (scripts/bench_attn.py, graph-replayed launches, profiles/attn_split_sweep_r1.txt):
+// B=96,T=200: S=1 8.9 us, S=2 8.0 us, S=3 11.3 us, S=4 11.1 us, S=8 14.6 us (fwd; clusters larger than a CTA pair cost more
+// to schedule than the extra SMs give back); B=256,T=375: S=1 31.2 us (6.3 TB/s), S=2 33.6 us.  So: a pair when the rows
+// alone cannot fill the SMs and each half still has >= 32 rows, else one CTA per row.
+int split_factor(const LasAttnStep* a) {
+    const char* e = getenv("LAS_ATTN_SPLIT");       // tuning / test override (0 = two-phase kernel)
+    const int forced = (e && *e) ? atoi(e) : -1;
+    if (forced >= 0) return forced > 8 ? 8 : forced;
+    const int rows = a->B * a->heads;
+    return (rows <= las_device_info()->num_sms && a->T >= 64) ? 2 : 1;
+}
+
 template <bool BWD>
 int launch_attn(const LasAttnStep* a, size_t smem, cudaStream_t st) {
+    // single-pass T-split kernel; backward needs the saved context for it (dot = dctx . ctx).  LAS_ATTN_SPLIT=0 or a
+    // backward descriptor without ctx selects the two-phase one-CTA-per-row kernel.
+    const int S = (BWD && !a->ctx) ? 0 : split_factor(a);
+    if (S >= 1) return a->kv_bf16 ? launch_split<BWD, true>(a, S, st) : launch_split<BWD, false>(a, S, st);
     const bool big = a->B * a->heads >= las_device_info()->num_sms;
     if (a->kv_bf16) return big ? launch_one<BWD, 4, true>(a, smem, st) : launch_one<BWD, 8, true>(a, smem, st);
     return big ? launch_one<BWD, 4, false>(a, smem, st) : launch_one<BWD, 8, false>(a, smem, st);

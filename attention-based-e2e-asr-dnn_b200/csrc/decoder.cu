@@ -722,6 +722,7 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
         float* dQCn = dQC + (size_t)rn * B * 2 * P;
         // attention step (t+1): dctx_total = classifier path + cell-0 path of step t+1
         at.q = QC + (size_t)rn * B * 2 * P; at.w = W + (size_t)rn * B * heads * T;
+        at.ctx = QC + (size_t)rn * B * 2 * P + P; at.ld_ctx = 2 * P;        // saved context: sum_t w_t (dctx.V_t) == dctx.ctx
         at.dctx = dQCn + P; at.dctx2 = (t == S - 1) ? nullptr : dS0;
         at.dq = dQCn; at.de = DE + (size_t)rn * B * heads * T;
         at.dq_bf16 = tc ? (void*)(dQb + (size_t)rn * B * P) : nullptr; at.ld_dq_bf16 = P;
@@ -757,7 +758,7 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
         else RC(gemm(st, b0.G, 4 * DH, Wcat0, K0, 0, dS0, K0, B, K0, 4 * DH));
     }
     // initial attention (src/models.py:346): its context feeds cell 0 of step 0 only
-    at.q = QC; at.w = W; at.dctx = dQC + P; at.dctx2 = dS0; at.dq = dQC; at.de = DE;
+    at.q = QC; at.w = W; at.ctx = QC + P; at.dctx = dQC + P; at.dctx2 = dS0; at.dq = dQC; at.de = DE;
     at.dq_bf16 = tc ? (void*)dQb : nullptr;
     RC(las_attn_step_bwd_f32(&at, st));
 

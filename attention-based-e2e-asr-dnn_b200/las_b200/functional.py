@@ -368,14 +368,14 @@ class AttnStepFunction(torch.autograd.Function):
         d.B, d.T, d.P, d.heads = Bn, T, P, int(heads)
         d.scale = float((P // heads) ** 0.5)
         check(_lib.load().las_attn_step_fwd_f32(C.byref(d), stream_ptr()), 'attn_step_fwd')
-        ctx.save_for_backward(q, K, V, lens_dev, w)
+        ctx.save_for_backward(q, K, V, lens_dev, w, ctxv)
         ctx.heads = int(heads)
         ctx.mark_non_differentiable(w)
         return ctxv, w
 
     @staticmethod
     def backward(ctx, dctx, _dw):
-        q, K, V, lens_dev, w = ctx.saved_tensors
+        q, K, V, lens_dev, w, ctxv = ctx.saved_tensors
         heads = ctx.heads
         Bn, T, P = K.shape
         dh = P // heads
@@ -386,6 +386,7 @@ class AttnStepFunction(torch.autograd.Function):
         d.q, d.ld_q = q.data_ptr(), P
         d.K, d.V, d.lens = K.data_ptr(), V.data_ptr(), lens_dev.data_ptr()
         d.w, d.ld_w = w.data_ptr(), T
+        d.ctx, d.ld_ctx = ctxv.data_ptr(), P      # saved context: lets backward run as one pass (dot = dctx . ctx)
         d.dctx, d.ld_dctx = dctx.data_ptr(), P
         d.dq, d.ld_dq, d.dq_accumulate = dq.data_ptr(), P, 0
         d.de = de.data_ptr()

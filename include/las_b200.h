@@ -150,7 +150,10 @@ int las_transpose_cast_bf16(const float* src, void* dst, int batch, int rows, in
  * fwd: q (row stride ld_q) -> ctx (ld_ctx) [+ ctx2 (ld_ctx2)], w ((B*heads), row stride ld_w) [+ w_b0: weights of
  *      batch row 0, (heads, T) contiguous -- the att_wgts[0] bookkeeping of src/models.py:349,377]
  * bwd: dctx (+ dctx2, nullable; when given the sum is written back to dctx) , w -> dq (ld_dq; accumulated into when
- *      dq_accumulate), de ((B*heads), ld_w) = d(energy) * scale, ready for the deferred dK = de^T.q GEMM. */
+ *      dq_accumulate), de ((B*heads), ld_w) = d(energy) * scale, ready for the deferred dK = de^T.q GEMM.
+ *      ctx (ld_ctx), when given, must be the context the forward call produced: sum_t w_t (dctx.V_t) == dctx.ctx lets
+ *      backward run as ONE pass over K and V (T-split across a thread-block cluster); NULL selects the two-phase kernel.
+ * Both directions read K and V exactly once: algorithmic bytes per call = 2 * B * T * P * sizeof(element). */
 typedef struct {
     const float* q; long long ld_q;
     const float* K; const float* V; const int* lens;

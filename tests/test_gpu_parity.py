@@ -119,8 +119,15 @@ def test_lstm_layer_vs_oracle(H, Din, B, T, lens, pyramid, use_mask):
 
 @pytest.mark.parametrize('B,T,P,heads,lens', [(3, 5, 16, 1, [5, 1, 3]), (4, 200, 256, 1, [200, 187, 31, 100]),
                                               (2, 37, 64, 4, [37, 20]), (5, 375, 128, 1, None)])
-def test_attention_step_vs_oracle(B, T, P, heads, lens):
+@pytest.mark.parametrize('split', [None, 0, 1, 2, 3, 8])
+def test_attention_step_vs_oracle(B, T, P, heads, lens, split, monkeypatch):
+    """split = CTAs per (batch row, head) of the single-pass T-split kernel (None: the library's own choice; 0: the
+    two-phase one-CTA-per-row kernel).  Rows shorter than the split leave some CTAs of the cluster without work."""
     from las_b200 import functional as LF
+    if split is None:
+        monkeypatch.delenv('LAS_ATTN_SPLIT', raising=False)
+    else:
+        monkeypatch.setenv('LAS_ATTN_SPLIT', str(split))
     rng = np.random.default_rng(B * T + P)
     if lens is None:
         lens = [T] + [int(v) for v in rng.integers(1, T + 1, size=B - 1)]
