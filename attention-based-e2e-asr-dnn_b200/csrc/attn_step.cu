@@ -91,8 +91,12 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
             }
         }
     }
+    // init-force prior (src/models.py:177-181): the second softmax runs over ALL T positions (pads included), so the value
+    // pass of forward and backward covers T rows instead of len
+    const float* fm = a.fmask ? a.fmask + ((long long)b * heads + h) * a.ld_fmask : nullptr;
+    const int lenA = (BWD && fm) ? T : len, lenC = (!BWD && fm) ? T : len;
     // ---- phase A: one warp per row, RU rows in flight per warp (all loads issued before any reduction) ----
-    for (int t0 = w; t0 < len; t0 += NW * RU) {
+    for (int t0 = w; t0 < lenA; t0 += NW * RU) {
         float4 m[RU][MAXCH];
 #pragma unroll
         for (int r = 0; r < RU; ++r) {
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
 #pragma unroll
             for (int c = 0; c < MAXCH; ++c) {
                 int k = c * 128 + lane * 4;
-                m[r][c] = (t < len && c < nch && k < d) ? load_kv4<KV16>(Mat1, mbase + (long long)t * P + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                m[r][c] = (t < lenA && c < nch && k < d) ? load_kv4<KV16>(Mat1, mbase + (long long)t * P + k) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
 #pragma unroll
@@ -113,11 +117,12 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
                 acc = fmaf(m[r][c].z, v4[c].z, acc); acc = fmaf(m[r][c].w, v4[c].w, acc);
             }
             acc = warp_sum(acc);
-            if (lane == 0 && t < len) sc[t] = acc;
+            if (lane == 0 && t < lenA) sc[t] = acc;
         }
     }
     __syncthreads();
     float* wrow = a.w + ((long long)b * heads + h) * a.ld_w;
+    float* w2row = fm ? a.w2 + ((long long)b * heads + h) * a.ld_w : nullptr;
     if (!BWD) {
         // ---- softmax over t < len (masked entries: exp(finfo.min - max) == 0 exactly, then forced to 0) ----
         float mx = -FLT_MAX;
@@ -137,7 +142,37 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
             wrow[t] = wv;
             if (b == 0 && a.w_b0) a.w_b0[(long long)h * T + t] = wv;
         }
+        if (fm) {
+            // w2 = softmax(w * prior) over all T positions; the returned / recorded weights stay the pre-prior ones (:178,188)
+            float mx2 = -FLT_MAX;
+            for (int t = tid; t < T; t += NT) {
+                const float x = (t < len) ? sc[t] * fm[t] : 0.f;
+                sc[t] = x;
+                mx2 = fmaxf(mx2, x);
+            }
+            mx2 = block_reduce(mx2, red, true);
+            float sum2 = 0.f;
+            for (int t = tid; t < T; t += NT) {
+                const float e = expf(sc[t] - mx2);
+                sc[t] = e;
+                sum2 += e;
+            }
+            sum2 = block_reduce(sum2, red, false);
+            const float inv2 = 1.f / sum2;
+            for (int t = tid; t < T; t += NT) {
+                const float wv = sc[t] * inv2;
+                sc[t] = wv;
+                w2row[t] = wv;
+            }
+        }
     } else {
+        if (fm) {
+            // sc[t] = dw2[t] for all t < T -> d(w * prior) = w2 (dw2 - sum w2 dw2) -> dw[t] = that * prior[t] (0 at pads)
+            float dot2 = 0.f;
+            for (int t = tid; t < T; t += NT) dot2 = fmaf(w2row[t], sc[t], dot2);
+            dot2 = block_reduce(dot2, red, false);
+            for (int t = tid; t < T; t += NT) sc[t] = (t < len) ? w2row[t] * (sc[t] - dot2) * fm[t] : 0.f;
+        }
         // dw[t] = sc[t]; de[t] = w[t] * (dw[t] - sum_t' w[t'] dw[t']) ; stored pre-multiplied by scale
         float dot = 0.f;
         for (int t = tid; t < len; t += NT) dot = fmaf(wrow[t], sc[t], dot);
@@ -154,17 +189,17 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
     float4 o4[MAXCH];
 #pragma unroll
     for (int c = 0; c < MAXCH; ++c) o4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t0 = w; t0 < len; t0 += NW * RU) {
+    for (int t0 = w; t0 < lenC; t0 += NW * RU) {
         float4 m[RU][MAXCH];
         float sv[RU];
 #pragma unroll
         for (int r = 0; r < RU; ++r) {
             const int t = t0 + r * NW;
-            sv[r] = (t < len) ? sc[t] : 0.f;
+            sv[r] = (t < lenC) ? sc[t] : 0.f;
 #pragma unroll
             for (int c = 0; c < MAXCH; ++c) {
                 int k = c * 128 + lane * 4;
-                m[r][c] = (t < len && c < nch && k < d) ? load_kv4<KV16>(Mat2, mbase + (long long)t * P + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                m[r][c] = (t < lenC && c < nch && k < d) ? load_kv4<KV16>(Mat2, mbase + (long long)t * P + k) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
 #pragma unroll
@@ -434,6 +469,7 @@ int check(const LasAttnStep* a, bool bwd) {
     int d = a->P / a->heads;
     LAS_CHECK_ARG(d % 4 == 0 && d <= 128 * MAXCH, "attn_step: head dim %d must be a multiple of 4 and <= %d", d, 128 * MAXCH);
     LAS_CHECK_ARG(a->K && a->V && a->lens && a->w, "attn_step: null K/V/lens/w");
+    LAS_CHECK_ARG(!a->fmask || a->w2, "attn_step: the init-force prior (fmask) needs w2 (second-softmax weights)");
     if (!bwd) {
         LAS_CHECK_ARG(a->q && a->ctx, "attn_step_fwd: null q/ctx");
         LAS_CHECK_ARG(a->ld_q % 4 == 0, "attn_step_fwd: ld_q must be a multiple of 4");
@@ -487,7 +523,7 @@ template <bool BWD>
 int launch_attn(const LasAttnStep* a, size_t smem, cudaStream_t st) {
     // single-pass T-split kernel; backward needs the saved context for it (dot = dctx . ctx).  LAS_ATTN_SPLIT=0 or a
     // backward descriptor without ctx selects the two-phase one-CTA-per-row kernel.
-    const int S = (BWD && !a->ctx) ? 0 : split_factor(a);
+    const int S = ((BWD && !a->ctx) || a->fmask) ? 0 : split_factor(a);
     if (S >= 1) return a->kv_bf16 ? launch_split<BWD, true>(a, S, st) : launch_split<BWD, false>(a, S, st);
     const bool big = a->B * a->heads >= las_device_info()->num_sms;
     if (a->kv_bf16) return big ? launch_one<BWD, 4, true>(a, smem, st) : launch_one<BWD, 8, true>(a, smem, st);

@@ -160,6 +160,16 @@ __global__ void __launch_bounds__(256) token_reduce_kernel(const float* __restri
     if (n < N) out[(long long)v * N + n] = acc;
 }
 
+// init-force prior (reference src/models.py:326-330): block_diag of six ones((T/6+1, steps/6+1)) blocks cut to (T, steps);
+// stored transposed, fm[t][t_enc], so that step t reads one contiguous row
+__global__ void __launch_bounds__(256) force_mask_kernel(float* __restrict__ fm, int T, int steps) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= T * steps) return;
+    const int t = i / T, te = i - t * T;
+    const int a_side = T / 6 + 1, b_side = steps / 6 + 1;
+    fm[i] = (te / a_side == t / b_side) ? 1.f : 0.f;
+}
+
 // two-stage deterministic column sum
 constexpr int CS_ROWSPLIT = 64;
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ X, long long ld, int M, int N, float* __restrict__ part) {
@@ -266,7 +276,7 @@ int cast_rows(cudaStream_t st, const float* src, long long ld_src, __nv_bfloat16
 
 struct Layout {
     // float workspace offsets
-    size_t Wcat0, Wcat1, Gemb, S0, S1, C0, C1, G0, G1, QC, W, dQC, dS0, dS1, dc0, dc1, dh1, DE, dGemb, tmpq, cs_scratch, total_f;
+    size_t Wcat0, Wcat1, Gemb, S0, S1, C0, C1, G0, G1, QC, W, W2, FM, dQC, dS0, dS1, dc0, dc1, dh1, DE, dGemb, tmpq, cs_scratch, total_f;
     // bf16 region (offsets in floats, buffers hold bf16): tensor-pipe mode only
     size_t Wcat0b, Wcat1b, Wqb, S0b, S1b, G0b, G1b, dQb, dlb, ohb, QCb, tmp32, skws, Wcat0p, Wcat1p;
     size_t skws_floats;
@@ -294,6 +304,10 @@ Layout make_layout(const LasSpeller* s) {
     L.G1 = take((size_t)L.ghist * B * 4 * DO);
     L.QC = take((size_t)L.hist * B * 2 * P);
     L.W = take((size_t)L.hist * B * h * T);
+    if (s->init_force) {          // second-softmax weights per step + the block-diagonal prior (steps, T)
+        L.W2 = take((size_t)L.hist * B * h * T);
+        L.FM = take(S * T);
+    }
     if (s->training) {
         L.dQC = take((S + 1) * B * 2 * P);
         L.dS0 = take(B * (P + DH));
@@ -547,6 +561,13 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
     at.q = QC; at.ctx = QC + P; at.ctx2 = S0; at.w = W; at.w_b0 = s->att0;
     at.ctx2_bf16 = tc ? (void*)S0b : nullptr; at.ld_ctx2_bf16 = K0;
     RC(las_attn_step_fwd_f32(&at, st));
+    float *W2 = f + L.W2, *FM = f + L.FM;
+    if (s->init_force) {
+        force_mask_kernel<<<ceil_div(S * T, 256), 256, 0, st>>>(FM, T, S);
+        LAS_LAUNCH_CHECK();
+        // the initial attention has no prior: its weights double as "second-softmax" weights for the batched dV GEMM
+        if (s->training) LAS_CUDA(cudaMemcpyAsync(W2, W, (size_t)B * heads * T * fsz, cudaMemcpyDeviceToDevice, st));
+    }
 
     bool all_gold = s->training != 0;
     if (s->training)
@@ -622,6 +643,7 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
         at.q = QCn; at.ctx = QCn + P; at.ctx2 = S0n; at.w = W + (size_t)rn * B * heads * T;
         at.ctx2_bf16 = tc ? (void*)S0nb : nullptr;
         at.w_b0 = s->att0 ? s->att0 + (size_t)(t + 1) * heads * T : nullptr;
+        if (s->init_force) { at.fmask = FM + (size_t)t * T; at.ld_fmask = 0; at.w2 = W2 + (size_t)rn * B * heads * T; }
         RC(las_attn_step_fwd_f32(&at, st));
         if (per_step_logits) {
             logits_argmax_kernel<<<B, 256, V * sizeof(float), st>>>(QCn, 2 * P, s->emb, s->cls_b, s->logits + (size_t)t * V, (long long)S * V,
@@ -663,7 +685,8 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     float* f = s->fws;
     float *Wcat0 = f + L.Wcat0, *Wcat1 = f + L.Wcat1, *S0 = f + L.S0, *S1 = f + L.S1, *C0 = f + L.C0, *C1 = f + L.C1, *G0 = f + L.G0,
           *G1 = f + L.G1, *QC = f + L.QC, *W = f + L.W, *dQC = f + L.dQC, *dS0 = f + L.dS0, *dS1 = f + L.dS1, *dc0 = f + L.dc0,
-          *dc1 = f + L.dc1, *dh1 = f + L.dh1, *DE = f + L.DE, *dGemb = f + L.dGemb, *tmpq = f + L.tmpq, *csw = f + L.cs_scratch;
+          *dc1 = f + L.dc1, *dh1 = f + L.dh1, *DE = f + L.DE, *dGemb = f + L.dGemb, *tmpq = f + L.tmpq, *csw = f + L.cs_scratch,
+          *W2 = f + L.W2, *FM = f + L.FM;
     const int* tok = s->iws + L.tok;
     const size_t fsz = sizeof(float);
     const long long SB = (long long)S * B;
@@ -726,6 +749,7 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
         at.dctx = dQCn + P; at.dctx2 = (t == S - 1) ? nullptr : dS0;
         at.dq = dQCn; at.de = DE + (size_t)rn * B * heads * T;
         at.dq_bf16 = tc ? (void*)(dQb + (size_t)rn * B * P) : nullptr; at.ld_dq_bf16 = P;
+        if (s->init_force) { at.fmask = FM + (size_t)t * T; at.ld_fmask = 0; at.w2 = W2 + (size_t)rn * B * heads * T; }
         RC(las_attn_step_bwd_f32(&at, st));
         // dh1_t (dropped) = dq_total . Wq  (+ recurrent path, added inside cell_bwd)
         if (tc) RC(las_tc_plan_launch(&bq1, rn, dh1, DO, nullptr, nullptr, st));
@@ -760,6 +784,7 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     // initial attention (src/models.py:346): its context feeds cell 0 of step 0 only
     at.q = QC; at.w = W; at.ctx = QC + P; at.dctx = dQC + P; at.dctx2 = dS0; at.dq = dQC; at.de = DE;
     at.dq_bf16 = tc ? (void*)dQb : nullptr;
+    at.fmask = nullptr; at.w2 = nullptr;
     RC(las_attn_step_bwd_f32(&at, st));
 
     // ---- batched parameter gradients ----
@@ -822,7 +847,7 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
         d.alpha = 1.f; d.beta = 0.f;
         d.A = DE + (size_t)h * T; d.B = QC + (size_t)h * d_head; d.C = g->dK + (size_t)h * d_head;
         RC(las_gemm_f32(&d, st));
-        d.A = W + (size_t)h * T; d.B = dQC + P + (size_t)h * d_head; d.C = g->dV + (size_t)h * d_head;
+        d.A = (s->init_force ? W2 : W) + (size_t)h * T; d.B = dQC + P + (size_t)h * d_head; d.C = g->dV + (size_t)h * d_head;
         RC(las_gemm_f32(&d, st));
     }
     return LAS_OK;

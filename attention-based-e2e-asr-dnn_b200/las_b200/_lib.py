@@ -63,6 +63,8 @@ class LasAttnStep(C.Structure):
         ('ctx2_bf16', C.c_void_p), ('ld_ctx2_bf16', c_ll),
         ('dq_bf16', C.c_void_p), ('ld_dq_bf16', c_ll),
         ('kv_bf16', C.c_int),
+        ('fmask', C.c_void_p), ('ld_fmask', c_ll),
+        ('w2', C.c_void_p),
     ]
 
 
@@ -74,6 +76,7 @@ class LasSpeller(C.Structure):
         ('training', C.c_int),
         ('use_tc', C.c_int),
         ('kv_bf16', C.c_int),
+        ('init_force', C.c_int),
         ('emb', C.c_void_p), ('cls_b', C.c_void_p),
         ('w_ih0', C.c_void_p), ('w_hh0', C.c_void_p), ('b_ih0', C.c_void_p), ('b_hh0', C.c_void_p),
         ('w_ih1', C.c_void_p), ('w_hh1', C.c_void_p), ('b_ih1', C.c_void_p), ('b_hh1', C.c_void_p),

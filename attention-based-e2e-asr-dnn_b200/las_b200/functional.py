@@ -354,13 +354,19 @@ def lstm_layer(x, lens_dev, T, pyramid, mask, weights: Sequence[torch.Tensor]):
 # ----------------------------------------------------------------------------------------------------------------------
 class AttnStepFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, K, V, lens_dev, heads):
+    def forward(ctx, q, K, V, lens_dev, heads, fmask=None):
         _require_cuda(q, K, V, lens_dev)
         q, K, V = _f32c(q), _f32c(K), _f32c(V)
         Bn, T, P = K.shape
         ctxv = torch.empty(Bn, P, dtype=torch.float32, device=q.device)
         w = torch.empty(Bn, heads, T, dtype=torch.float32, device=q.device)
         d = LasAttnStep()
+        w2 = None
+        if fmask is not None:         # init-force prior, (B*heads, T) contiguous
+            _require_cuda(fmask)
+            fmask = _f32c(fmask)
+            w2 = torch.empty_like(w)
+            d.fmask, d.ld_fmask, d.w2 = fmask.data_ptr(), T, w2.data_ptr()
         d.q, d.ld_q = q.data_ptr(), P
         d.K, d.V, d.lens = K.data_ptr(), V.data_ptr(), lens_dev.data_ptr()
         d.w, d.ld_w = w.data_ptr(), T
@@ -368,14 +374,14 @@ class AttnStepFunction(torch.autograd.Function):
         d.B, d.T, d.P, d.heads = Bn, T, P, int(heads)
         d.scale = float((P // heads) ** 0.5)
         check(_lib.load().las_attn_step_fwd_f32(C.byref(d), stream_ptr()), 'attn_step_fwd')
-        ctx.save_for_backward(q, K, V, lens_dev, w, ctxv)
+        ctx.save_for_backward(q, K, V, lens_dev, w, ctxv, fmask, w2)
         ctx.heads = int(heads)
         ctx.mark_non_differentiable(w)
         return ctxv, w
 
     @staticmethod
     def backward(ctx, dctx, _dw):
-        q, K, V, lens_dev, w, ctxv = ctx.saved_tensors
+        q, K, V, lens_dev, w, ctxv, fmask, w2 = ctx.saved_tensors
         heads = ctx.heads
         Bn, T, P = K.shape
         dh = P // heads
@@ -392,6 +398,9 @@ class AttnStepFunction(torch.autograd.Function):
         d.de = de.data_ptr()
         d.B, d.T, d.P, d.heads = Bn, T, P, heads
         d.scale = float(dh ** 0.5)
+        if fmask is not None:
+            d.fmask, d.ld_fmask, d.w2 = fmask.data_ptr(), T, w2.data_ptr()
+        wv = w if fmask is None else w2           # the weights that multiplied V
         check(_lib.load().las_attn_step_bwd_f32(C.byref(d), stream_ptr()), 'attn_step_bwd')
         dK = dV = None
         if ctx.needs_input_grad[1]:
@@ -402,13 +411,14 @@ class AttnStepFunction(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             dV = torch.empty_like(V)
             for h in range(heads):
-                gemm_raw(w, dctx, dV, T, dh, 1, am=(0, 1, 0), ak=(0, 0, 0), bk=(0, 0, 0), bn=1, cm=(0, P, 0), batch=Bn,
+                gemm_raw(wv, dctx, dV, T, dh, 1, am=(0, 1, 0), ak=(0, 0, 0), bk=(0, 0, 0), bn=1, cm=(0, P, 0), batch=Bn,
                          bsA=heads * T, bsB=P, bsC=T * P, a_off=h * T, b_off=h * dh, c_off=h * dh)
-        return dq, dK, dV, None, None
+        return dq, dK, dV, None, None, None
 
 
-def attn_step(q, K, V, lens_dev, heads):
-    return AttnStepFunction.apply(q, K, V, lens_dev, heads)
+def attn_step(q, K, V, lens_dev, heads, fmask=None):
+    """fmask: optional (B*heads, T) init-force prior (reference src/models.py:177-181); returns (ctx, pre-prior weights)."""
+    return AttnStepFunction.apply(q, K, V, lens_dev, heads, fmask)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -418,7 +428,8 @@ SPELLER_PARAM_ORDER = ('emb', 'cls_b', 'w_ih0', 'w_hh0', 'b_ih0', 'b_hh0', 'w_ih
                        'init_query')
 
 
-def _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, use_tc=False):
+def _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, use_tc=False,
+                  init_force=False):
     Bn, T, P = K.shape
     emb = params[0]
     s = LasSpeller()
@@ -430,6 +441,7 @@ def _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, 
     s.heads, s.steps = int(heads), int(steps)
     s.sos_idx, s.pad_idx = int(sos_idx), int(pad_idx)
     s.training = int(training)
+    s.init_force = int(bool(init_force))
     s.use_tc = int(use_tc and s.P % 8 == 0 and s.DH % 8 == 0 and s.DO % 8 == 0)
     for name, t in zip(SPELLER_PARAM_ORDER, params):
         setattr(s, name, t.data_ptr())
@@ -446,7 +458,7 @@ def _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, 
 
 class SpellerFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, K, V, enc_lens, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, *params):
+    def forward(ctx, K, V, enc_lens, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, init_force, *params):
         _require_cuda(K, V, enc_lens, *params)
         lib = _lib.load()
         K, V = _f32c(K), _f32c(V)
@@ -467,7 +479,8 @@ class SpellerFunction(torch.autograd.Function):
             # the context still accumulate in fp32
             K = cast_bf16(K, Bn * T, P, P, P).view(Bn, T, P)
             V = cast_bf16(V, Bn * T, P, P, P).view(Bn, T, P)
-        s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, use_tc)
+        s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, use_tc,
+                                init_force)
         s.kv_bf16 = int(kv16)
         logits = torch.empty(Bn, steps, Vn, dtype=torch.float32, device=dev)
         att0 = torch.empty(steps + 1, heads, T, dtype=torch.float32, device=dev)
@@ -481,7 +494,7 @@ class SpellerFunction(torch.autograd.Function):
         check(lib.las_speller_fwd_f32(C.byref(s), stream_ptr()), 'speller_fwd')
         if training:
             ctx.save_for_backward(K, V, enc_lens, dec_y, drop0, drop1, fws, iws, *params)
-            ctx.cfg = (use_gold, steps, heads, sos_idx, pad_idx, use_tc, kv16)
+            ctx.cfg = (use_gold, steps, heads, sos_idx, pad_idx, use_tc, kv16, init_force)
         ctx.mark_non_differentiable(att0, chars)
         return logits, att0, chars
 
@@ -489,8 +502,9 @@ class SpellerFunction(torch.autograd.Function):
     def backward(ctx, dlogits, _datt, _dchars):
         lib = _lib.load()
         K, V, enc_lens, dec_y, drop0, drop1, fws, iws, *params = ctx.saved_tensors
-        use_gold, steps, heads, sos_idx, pad_idx, use_tc, kv16 = ctx.cfg
-        s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, True, use_tc)
+        use_gold, steps, heads, sos_idx, pad_idx, use_tc, kv16, init_force = ctx.cfg
+        s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, True, use_tc,
+                                init_force)
         s.kv_bf16 = int(kv16)
         s.fws, s.fws_floats, s.iws, s.iws_ints = fws.data_ptr(), fws.numel(), iws.data_ptr(), iws.numel()
         # outputs of fwd are not needed by bwd but the descriptor check wants non-null
@@ -507,10 +521,10 @@ class SpellerFunction(torch.autograd.Function):
         dV = torch.empty(V.shape, dtype=torch.float32, device=K.device)
         g.dK, g.dV = dK.data_ptr(), dV.data_ptr()
         check(lib.las_speller_bwd_f32(C.byref(s), C.byref(g), stream_ptr()), 'speller_bwd')
-        return (dK, dV, None, None, None, None, None, None, None, None, None, None, *grads)
+        return (dK, dV, None, None, None, None, None, None, None, None, None, None, None, *grads)
 
 
 def speller_loop(K, V, enc_lens, params, *, steps, heads, sos_idx, pad_idx, training, dec_y=None, use_gold=None,
-                 drop0=None, drop1=None):
+                 drop0=None, drop1=None, init_force=False):
     return SpellerFunction.apply(K, V, enc_lens, dec_y, use_gold, drop0, drop1, int(steps), int(heads), int(sos_idx),
-                                 int(pad_idx), bool(training), *params)
+                                 int(pad_idx), bool(training), bool(init_force), *params)

@@ -86,13 +86,17 @@ class MultiheadCrossAttention(nn.Module):
         self.masks = mask[:, None, None, :].expand((B, self.heads, 1, T)).to(enc_h.device)
 
     def forward(self, dec_h, return_wgts: bool = False, init_wgts_mask: torch.Tensor = None):
-        if init_wgts_mask is not None:
-            raise NotImplementedError('init_force attention prior is not implemented yet in las_b200 (SURVEY 8(f) row 2)')
         B = dec_h.size(0)
         q = LF.linear(dec_h, self.query_map.weight, self.query_map.bias)
         self.queries = q.view(B, self.heads, self.dims_per_head).unsqueeze(2)
-        ctx, w = LF.attn_step(q, self._K, self._V, self._lens_dev, self.heads)
+        fmask = None
+        if init_wgts_mask is not None:          # (B, heads, 1, T) prior (reference :177-181), usually an expanded view
+            T = self._K.shape[1]
+            fmask = init_wgts_mask.to(device=q.device, dtype=torch.float32).expand(B, self.heads, 1, T).reshape(B * self.heads, T)
+        ctx, w = LF.attn_step(q, self._K, self._V, self._lens_dev, self.heads, fmask)
         wgts = w.view(B, self.heads, 1, -1)
+        if init_wgts_mask is not None:
+            return ctx, wgts.detach()           # the reference returns the detached pre-prior weights (:178,188)
         return (ctx, wgts) if return_wgts else ctx
 
 
@@ -158,8 +162,6 @@ class Speller(nn.Module):
         return m0, m1
 
     def forward(self, enc_h, enc_l, dec_y=None, teacher_forcing_rate: float = 1, init_force: bool = False):
-        if init_force:
-            raise NotImplementedError('init_force attention prior is not implemented yet in las_b200 (SURVEY 8(f) row 2)')
         B, T_enc, _ = enc_h.shape
         if self.training:
             steps = dec_y.size(-1)
@@ -180,7 +182,8 @@ class Speller(nn.Module):
                   self.attention.query_map.bias, self.init_query)
         logits, att0, chars = LF.speller_loop(K, V, lens_dev, params, steps=steps, heads=self.att_heads,
                                               sos_idx=self.CHR_SOS_IDX, pad_idx=self.CHR_PAD_IDX, training=self.training,
-                                              dec_y=dec_y if self.training else None, use_gold=use_gold, drop0=drop0, drop1=drop1)
+                                              dec_y=dec_y if self.training else None, use_gold=use_gold, drop0=drop0, drop1=drop1,
+                                              init_force=bool(init_force))
         self.last_chars = chars                         # (steps, B) greedy indices, device-side (extra, not in reference)
         # reference returns the attention map of sample 0 as a CPU tensor (heads, T_enc, steps+1) (:349,377,385):
         # one D2H at the end instead of one blocking copy per step

@@ -170,6 +170,12 @@ typedef struct {
     void* ctx2_bf16; long long ld_ctx2_bf16;   /* fwd: optional bf16 copy of the context (next cell-0 GEMM operand) */
     void* dq_bf16; long long ld_dq_bf16;       /* bwd: optional bf16 copy of the total dq */
     int kv_bf16;                               /* 1: K and V point to bf16 (B,T,P) memory (AMP mode: half the bytes per step) */
+    /* init-force prior (src/models.py:177-181): when fmask != NULL, ctx = softmax(w * fmask) . V over all T positions;
+     * fmask row of (batch b, head h) = fmask + (b*heads+h)*ld_fmask (ld_fmask = 0: one (T) row shared by all).
+     * w keeps the pre-prior weights (what the reference returns); w2 ((B*heads), ld_w) receives the second-softmax
+     * weights in fwd and must be passed back to bwd. */
+    const float* fmask; long long ld_fmask;
+    float* w2;
 } LasAttnStep;
 int las_attn_step_fwd_f32(const LasAttnStep* desc, void* stream);
 int las_attn_step_bwd_f32(const LasAttnStep* desc, void* stream);
@@ -197,6 +203,7 @@ typedef struct {
     int training;                 /* 1: save history for backward */
     int use_tc;                   /* 1: decoder GEMMs as bf16 tcgen05 tiles (AMP mode); fwd and bwd must agree */
     int kv_bf16;                  /* 1: K and V_ point to bf16 (B,T,P) memory */
+    int init_force;               /* 1: block-diagonal attention prior on every loop step (src/models.py:326-330,364-366) */
     /* parameters */
     const float* emb;             /* (V, E)  char_emb.weight == cls.weight */
     const float* cls_b;           /* (V) */

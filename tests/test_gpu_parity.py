@@ -157,10 +157,41 @@ def test_attention_step_vs_oracle(B, T, P, heads, lens, split, monkeypatch):
     assert rel_err(Vc.grad.cpu().numpy(), Vo.grad.numpy()) < TOL
 
 
+@pytest.mark.parametrize('B,T,P,heads,lens', [(3, 23, 16, 1, [23, 9, 17]), (2, 40, 64, 4, [40, 22])])
+def test_attention_step_init_force_prior_vs_oracle(B, T, P, heads, lens):
+    """init_wgts_mask path of MultiheadCrossAttention.forward (src/models.py:177-181): second softmax over all T
+    positions (pads included), pre-prior weights returned."""
+    from las_b200 import functional as LF
+    rng = np.random.default_rng(7 * B + T)
+    q = torch.from_numpy(rng.standard_normal((B, P)).astype(np.float32) * 0.3)
+    K = torch.from_numpy(rng.standard_normal((B, T, P)).astype(np.float32) * 0.3)
+    V = torch.from_numpy(rng.standard_normal((B, T, P)).astype(np.float32))
+    wctx = torch.from_numpy(rng.standard_normal((B, P)).astype(np.float32))
+    prior = torch.zeros(T)
+    prior[T // 4: T // 4 + T // 3] = 1.0
+    d = P // heads
+    po = {'a.query_map.weight': torch.eye(P), 'a.query_map.bias': torch.zeros(P)}
+    qo, Ko, Vo = q.clone().requires_grad_(True), K.clone().requires_grad_(True), V.clone().requires_grad_(True)
+    keys = Ko.view(B, T, heads, d).permute(0, 2, 1, 3)
+    vals = Vo.view(B, T, heads, d).permute(0, 2, 1, 3)
+    pad = torch.arange(T).unsqueeze(0) >= torch.tensor(lens).unsqueeze(1)
+    ctx_o, w_o, _ = orc.attention_step(po, qo, keys, vals, pad, heads, prior.expand(B, heads, T), 'a.')
+    (ctx_o * wctx).sum().backward()
+    qc, Kc, Vc = (t.clone().to(DEV).requires_grad_(True) for t in (q, K, V))
+    fmask = prior.to(DEV).expand(B * heads, T).contiguous()
+    ctx_c, w_c = LF.attn_step(qc, Kc, Vc, torch.tensor(lens, dtype=torch.int32, device=DEV), heads, fmask)
+    (ctx_c * wctx.to(DEV)).sum().backward()
+    assert rel_err(ctx_c.detach().cpu().numpy(), ctx_o.detach().numpy()) < TOL
+    assert np.abs(w_c.cpu().numpy() - w_o.detach().numpy()).max() < 1e-5
+    assert rel_err(qc.grad.cpu().numpy(), qo.grad.numpy()) < TOL
+    assert rel_err(Kc.grad.cpu().numpy(), Ko.grad.numpy()) < TOL
+    assert rel_err(Vc.grad.cpu().numpy(), Vo.grad.numpy()) < TOL
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # whole model against the reference's golden fixtures
 # ----------------------------------------------------------------------------------------------------------------------
-TRAIN_CASES = ['micro_train_tf1', 'micro_train_tf05', 'micro_train_dropout', 'tiny_train_tf1']
+TRAIN_CASES = ['micro_train_tf1', 'micro_train_tf05', 'micro_train_dropout', 'micro_train_initforce', 'tiny_train_tf1']
 
 
 @pytest.mark.parametrize('name', TRAIN_CASES)
@@ -176,7 +207,8 @@ def test_las_train_step_matches_reference_golden(name):
     set_mask_override(locked, drops, [float(c) for c in g['coins']])
     try:
         y = torch.from_numpy(g['y']).to(DEV)
-        logits, att = model(torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['lx']), y, float(g['tf_rate']), False)
+        logits, att = model(torch.from_numpy(g['x']).to(DEV), torch.from_numpy(g['lx']), y, float(g['tf_rate']),
+                            bool(g['init_force']))
         loss = _masked_ce(logits, y, g['ly'])
         loss.backward()
     finally:
