@@ -17,6 +17,7 @@
 #include "las_b200.h"
 #include <vector>
 #include <stdlib.h>
+#include <string.h>
 
 // prepared tensor-core GEMM plans (gemm_tc.cu): tensor maps encoded once per loop, one launch per step
 size_t las_tc_plan_bytes();
@@ -418,13 +419,14 @@ unsigned las_prof_mask_get();
 // ---- CUDA-graph cache for the forward loop -----------------------------------------------------------------------
 // The loop is ~7 launches per step (2100 at L = 300, 4200 for greedy decoding) and the host cannot enqueue them as fast
 // as the GPU retires them.  The whole enqueue sequence is therefore captured once per (descriptor, coin pattern) --
-// every pointer in the descriptor is part of the key; PyTorch's caching allocator returns the same blocks in a steady
-// training / decoding loop -- and replayed with a single cudaGraphLaunch.  Any capture failure falls back to direct
+// every device pointer in the descriptor is part of the key; the Python wrapper stages inputs / workspaces / outputs in a
+// pointer-stable pooled buffer set (las_b200/functional.py::_SpellerSlot) -- and replayed with a single cudaGraphLaunch.  Any capture failure falls back to direct
 // enqueueing.  LAS_DEC_GRAPH=0 disables it; it is also bypassed while per-kernel profiling of inner kernels is on.
 namespace {
 struct GraphEntry { unsigned long long key; cudaGraphExec_t exec; unsigned long long stamp; int nlaunch; };
 std::vector<GraphEntry> g_graphs;
 unsigned long long g_graph_clock = 0;
+long long g_graph_captures = 0, g_graph_replays = 0;
 cudaStream_t g_capture_stream[64];
 bool g_capture_stream_ok[64];
 
@@ -435,6 +437,11 @@ unsigned long long fnv1a(const void* p, size_t n, unsigned long long h) {
 }
 int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st);
 }  // namespace
+
+extern "C" void las_speller_graph_stats(long long* captures, long long* replays) {
+    if (captures) *captures = g_graph_captures;
+    if (replays) *replays = g_graph_replays;
+}
 
 extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
     RC(check_speller(s));
@@ -452,12 +459,17 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
     cudaGetDevice(&dev);
     if ((genv && atoi(genv) == 0) || inner_prof || dev < 0 || dev >= 64) return speller_fwd_enqueue(s, L, st);
 
-    unsigned long long key = fnv1a(s, sizeof(LasSpeller), 1469598103934665603ULL);
+    // key: every field of the descriptor except the HOST coin pointer (a fresh host array per call), whose contents are hashed
+    LasSpeller kd;
+    memcpy(&kd, s, sizeof(LasSpeller));
+    kd.use_gold_host = nullptr;
+    unsigned long long key = fnv1a(&kd, sizeof(LasSpeller), 1469598103934665603ULL);
     if (s->use_gold_host) key = fnv1a(s->use_gold_host, (size_t)s->steps, key);
     key = fnv1a(&dev, sizeof(dev), key);
     for (auto& e : g_graphs)
         if (e.key == key) {
             e.stamp = ++g_graph_clock;
+            ++g_graph_replays;
             LAS_CUDA(cudaGraphLaunch(e.exec, st));
             las_count_launch(e.nlaunch);          // the replay runs the same kernels the capture recorded
             return LAS_OK;
@@ -490,6 +502,7 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
         g_graphs.erase(g_graphs.begin() + lru);
     }
     g_graphs.push_back({key, exec, ++g_graph_clock, (int)(las_launch_count() - launches_before)});
+    ++g_graph_captures;
     LAS_CUDA(cudaGraphLaunch(exec, st));
     return LAS_OK;
 }

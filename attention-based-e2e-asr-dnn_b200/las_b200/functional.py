@@ -456,44 +456,112 @@ def _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, 
     return s, keep
 
 
+class _SpellerSlot:
+    """One pointer-stable buffer set for a decoder loop of a given shape: the staged inputs (K, V, lengths, gold tokens,
+    dropout masks), the workspaces and the raw outputs.  las_speller_fwd_f32 replays a CUDA graph keyed on the descriptor
+    (every pointer in it), so a steady training / decoding loop must present the SAME pointers every step -- PyTorch's
+    caching allocator does not promise that for per-step allocations, a slot does."""
+    __slots__ = ('t', 'busy')
+
+    def __init__(self):
+        self.t, self.busy = {}, False
+
+    def buf(self, name, shape, dtype, device):
+        b = self.t.get(name)
+        if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
+            b = torch.empty(shape, dtype=dtype, device=device)
+            self.t[name] = b
+        return b
+
+
+class _SlotLease:
+    """Held by the autograd node of a training forward; frees the slot when backward has run or the graph is dropped."""
+    __slots__ = ('slot',)
+
+    def __init__(self, slot):
+        self.slot = slot
+        slot.busy = True
+
+    def release(self):
+        if self.slot is not None:
+            self.slot.busy = False
+            self.slot = None
+
+    def __del__(self):
+        self.release()
+
+
+_SPELLER_POOL = {}
+
+
+def _acquire_slot(key):
+    slots = _SPELLER_POOL.setdefault(key, [])
+    for sl in slots:
+        if not sl.busy:
+            return sl
+    sl = _SpellerSlot()
+    slots.append(sl)
+    return sl
+
+
+def speller_pool_clear():
+    """Drop every pooled decoder buffer set (they are retained between steps on purpose)."""
+    _SPELLER_POOL.clear()
+
+
 class SpellerFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, K, V, enc_lens, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, init_force, *params):
         _require_cuda(K, V, enc_lens, *params)
         lib = _lib.load()
-        K, V = _f32c(K), _f32c(V)
         params = tuple(_f32c(p) for p in params)
         dev = K.device
         Bn, T, P = K.shape
         Vn = params[0].shape[0]
-        if dec_y is not None:
-            dec_y = dec_y.to(device=dev, dtype=torch.int32)
-            if dec_y.stride(1) != 1:
-                dec_y = dec_y.contiguous()
-        drop0 = _f32c(drop0) if drop0 is not None else None
-        drop1 = _f32c(drop1) if drop1 is not None else None
         use_tc = use_tensor_cores() and os.environ.get('LAS_DEC_TC', '1') == '1'
         kv16 = bool(use_tc) and P % 4 == 0 and os.environ.get('LAS_KV_BF16', '0') == '1'   # measured slower than fp32 rows with 64-bit loads: off by default
+        key = (dev.index, Bn, T, P, int(steps), int(heads), bool(training), bool(use_tc), kv16, bool(init_force), Vn,
+               params[3].shape[1], params[7].shape[1], drop0 is not None)
+        slot = _acquire_slot(key)
+        # ---- stage the per-step inputs into the slot (device-to-device copies, a few tens of microseconds) ----
         if kv16:
-            # AMP mode: the decoder re-reads K and V every step -- keep them as bf16 (half the bytes per step); the energies and
-            # the context still accumulate in fp32
-            K = cast_bf16(K, Bn * T, P, P, P).view(Bn, T, P)
-            V = cast_bf16(V, Bn * T, P, P, P).view(Bn, T, P)
-        s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, use_tc,
+            # AMP mode option: K and V as bf16 (half the bytes per step); the energies and the context still accumulate in fp32
+            Kb = slot.buf('K', (Bn, T, P), torch.bfloat16, dev)
+            Vb = slot.buf('V', (Bn, T, P), torch.bfloat16, dev)
+            Kb.copy_(K); Vb.copy_(V)
+        else:
+            Kb = slot.buf('K', (Bn, T, P), torch.float32, dev)
+            Vb = slot.buf('V', (Bn, T, P), torch.float32, dev)
+            Kb.copy_(K); Vb.copy_(V)
+        lens_b = slot.buf('lens', (Bn,), torch.int32, dev)
+        lens_b.copy_(enc_lens)
+        y_b = None
+        if dec_y is not None:
+            y_b = slot.buf('y', tuple(dec_y.shape), torch.int32, dev)
+            y_b.copy_(dec_y)
+        d0 = d1 = None
+        if drop0 is not None:
+            d0 = slot.buf('drop0', tuple(drop0.shape), torch.float32, dev)
+            d1 = slot.buf('drop1', tuple(drop1.shape), torch.float32, dev)
+            d0.copy_(drop0); d1.copy_(drop1)
+        s, keep = _speller_desc(Kb, Vb, lens_b, params, y_b, use_gold, d0, d1, steps, heads, sos_idx, pad_idx, training, use_tc,
                                 init_force)
         s.kv_bf16 = int(kv16)
-        logits = torch.empty(Bn, steps, Vn, dtype=torch.float32, device=dev)
-        att0 = torch.empty(steps + 1, heads, T, dtype=torch.float32, device=dev)
-        chars = torch.zeros(steps, Bn, dtype=torch.int32, device=dev)
         nf = lib.las_speller_workspace_floats(C.byref(s))
         ni = lib.las_speller_workspace_ints(C.byref(s))
-        fws = torch.empty(nf, dtype=torch.float32, device=dev)
-        iws = torch.empty(ni, dtype=torch.int32, device=dev)
-        s.logits, s.att0, s.chars = logits.data_ptr(), att0.data_ptr(), chars.data_ptr()
+        fws = slot.buf('fws', (nf,), torch.float32, dev)
+        iws = slot.buf('iws', (ni,), torch.int32, dev)
+        logits_b = slot.buf('logits', (Bn, steps, Vn), torch.float32, dev)
+        att0_b = slot.buf('att0', (steps + 1, heads, T), torch.float32, dev)
+        chars_b = slot.buf('chars', (steps, Bn), torch.int32, dev)
+        chars_b.zero_()         # steps that do not compute per-step logits (full teacher forcing) leave their row at 0
+        s.logits, s.att0, s.chars = logits_b.data_ptr(), att0_b.data_ptr(), chars_b.data_ptr()
         s.fws, s.fws_floats, s.iws, s.iws_ints = fws.data_ptr(), nf, iws.data_ptr(), ni
         check(lib.las_speller_fwd_f32(C.byref(s), stream_ptr()), 'speller_fwd')
+        logits, att0, chars = logits_b.clone(), att0_b.clone(), chars_b.clone()      # the caller owns its outputs
         if training:
-            ctx.save_for_backward(K, V, enc_lens, dec_y, drop0, drop1, fws, iws, *params)
+            ctx.lease = _SlotLease(slot)
+            ctx.save_for_backward(*params)
             ctx.cfg = (use_gold, steps, heads, sos_idx, pad_idx, use_tc, kv16, init_force)
         ctx.mark_non_differentiable(att0, chars)
         return logits, att0, chars
@@ -501,26 +569,31 @@ class SpellerFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits, _datt, _dchars):
         lib = _lib.load()
-        K, V, enc_lens, dec_y, drop0, drop1, fws, iws, *params = ctx.saved_tensors
+        params = ctx.saved_tensors
+        lease = ctx.lease
+        if lease.slot is None:
+            raise RuntimeError('speller backward called twice: the decoder history buffers were already released')
+        t = lease.slot.t
+        K, V, enc_lens, dec_y, drop0, drop1, fws, iws = t['K'], t['V'], t['lens'], t.get('y'), t.get('drop0'), t.get('drop1'), t['fws'], t['iws']
         use_gold, steps, heads, sos_idx, pad_idx, use_tc, kv16, init_force = ctx.cfg
         s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, True, use_tc,
                                 init_force)
         s.kv_bf16 = int(kv16)
         s.fws, s.fws_floats, s.iws, s.iws_ints = fws.data_ptr(), fws.numel(), iws.data_ptr(), iws.numel()
         # outputs of fwd are not needed by bwd but the descriptor check wants non-null
-        dummy = torch.empty(1, dtype=torch.int32, device=K.device)
-        s.logits, s.chars = fws.data_ptr(), dummy.data_ptr()
+        s.logits, s.chars = fws.data_ptr(), t['chars'].data_ptr()
         dlogits = _f32c(dlogits)
         g = LasSpellerGrads()
         g.dlogits = dlogits.data_ptr()
         grads = [torch.empty_like(p) for p in params]
-        for name, t in zip(SPELLER_PARAM_ORDER, grads):
-            setattr(g, 'd_' + name, t.data_ptr())
+        for name, tt in zip(SPELLER_PARAM_ORDER, grads):
+            setattr(g, 'd_' + name, tt.data_ptr())
         # d_w_ih0 is written in three column/row pieces that together cover it; no zero-init needed
         dK = torch.empty(K.shape, dtype=torch.float32, device=K.device)
         dV = torch.empty(V.shape, dtype=torch.float32, device=K.device)
         g.dK, g.dV = dK.data_ptr(), dV.data_ptr()
         check(lib.las_speller_bwd_f32(C.byref(s), C.byref(g), stream_ptr()), 'speller_bwd')
+        lease.release()
         return (dK, dV, None, None, None, None, None, None, None, None, None, None, None, *grads)
 
 

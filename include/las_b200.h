@@ -227,6 +227,9 @@ typedef struct {
 size_t las_speller_workspace_floats(const LasSpeller* s);
 size_t las_speller_workspace_ints(const LasSpeller* s);
 int las_speller_fwd_f32(const LasSpeller* s, void* stream);
+/* The forward loop is captured once per descriptor (all device pointers + the coin pattern) as a CUDA graph and replayed;
+ * counts since library load: graphs captured / graph replays.  A steady loop must show replays only. */
+void las_speller_graph_stats(long long* captures, long long* replays);
 
 typedef struct {
     const float* dlogits;         /* (B, steps, V) contiguous */

@@ -322,3 +322,46 @@ def test_fused_adamw_matches_torch_golden():
         assert float(sd[i]['step']) == float(g[f'state_{i}_step'])
         np.testing.assert_allclose(sd[i]['max_exp_avg_sq'].cpu().numpy(), g[f'state_{i}_max_exp_avg_sq'], rtol=1e-5, atol=1e-9)
     assert 4 not in sd or float(sd[4]['step']) == 0            # the grad-less parameter was never touched
+
+
+def test_decoder_graph_replays_in_a_steady_loop_and_slots_do_not_alias():
+    """The Speller forward loop is one CUDA graph keyed on the descriptor's pointers; the Python wrapper stages everything in
+    pooled, pointer-stable buffers.  A steady train loop must capture once and replay afterwards; two forwards that are both
+    alive (no backward in between) must not share history buffers."""
+    import ctypes as C
+    from las_b200 import _lib
+    lib = _lib.load()
+    cfg = gu.get_config('micro')
+    sd = gu.make_state_dict(cfg, 5)
+    model = _model(cfg, sd, train=True)
+    x, lx, y = gu.make_inputs(9, 3, 40, 6, [40, 25, 33])
+    xd, yd = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+
+    def stats():
+        c, r = C.c_longlong(), C.c_longlong()
+        lib.las_speller_graph_stats(C.byref(c), C.byref(r))
+        return c.value, r.value
+
+    grads = []
+    for it in range(4):
+        model.zero_grad(set_to_none=True)
+        junk = torch.empty(1000 + 997 * it, device=DEV)          # perturb the caching allocator between steps
+        logits, _ = model(xd, torch.from_numpy(lx), yd, 1.0, False)
+        del junk
+        if it == 0:
+            c0, r0 = stats()
+        logits.square().mean().backward()
+        grads.append(model.spell.attention.query_map.weight.grad.clone())
+    c1, r1 = stats()
+    assert c1 == c0, 'steady loop re-captured the decoder graph'
+    assert r1 - r0 == 3
+    for g in grads[1:]:
+        assert torch.equal(g, grads[0])
+    # two live forwards: the first one's backward must still see its own history
+    model.zero_grad(set_to_none=True)
+    la, _ = model(xd, torch.from_numpy(lx), yd, 1.0, False)
+    y2 = torch.from_numpy(np.roll(y, 1, axis=1).copy()).to(DEV)
+    lb, _ = model(xd, torch.from_numpy(lx), y2, 1.0, False)
+    la.square().mean().backward()
+    assert torch.equal(model.spell.attention.query_map.weight.grad, grads[0])
+    del lb
