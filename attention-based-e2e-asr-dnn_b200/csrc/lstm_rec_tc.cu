@@ -133,6 +133,13 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return y;
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+// one elected lane of a converged warp: unlike `if (lane == 0)` the compiler keeps the surrounding control flow warp-uniform, so
+// the UMMA descriptors stay in uniform registers and each tcgen05.mma issues without a divergence-handling loop around it
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 #define REC_STAMP(slot)                                                                              \
@@ -142,6 +149,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 
 // idesc: F32 accumulate, BF16 x BF16, both K-major, M = 128, N = 32
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB_SLICE >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+
+constexpr int FWD_NACC = 4;          // independent TMEM accumulators per chain in the forward recurrence (one per k sub-step)
 
 template <bool WTMEM>
 __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW,
@@ -172,7 +181,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const uint32_t tmem_cols = WTMEM ? 512u : 64u;
+    // TMEM map: FWD_NACC independent accumulators per chain (MAX_CHAINS x FWD_NACC x 32 columns) first, then (WTMEM) the
+    // resident W_hh slice
+    const uint32_t tmem_cols = WTMEM ? 512u : 256u;
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
     const uint32_t tmem_base = *tmem_slot_ptr;
     // TMEM map: accumulators (MAX_CHAINS x 32 columns) first, then the resident W_hh slice (H/2 columns: two bf16 per
     // 32-bit column, K ascending; TMEM lane = gate row, the layout tcgen05.mma expects for an A operand in tensor memory)
-    const uint32_t tmem_w = tmem_base + 64;
+    const uint32_t tmem_w = tmem_base + MAX_CHAINS * FWD_NACC * NB_SLICE;
     if (WTMEM) {
         if (warp >= 4) {
             const int q = warp & 3;
@@ -231,32 +242,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            if (!WTMEM) mbar_wait(wbar, 0);
-            for (int s = 1; s < T; ++s) {
-                for (int c = 0; c < a.chains; ++c) {
-                    const int slice = sg + c * a.bsg;
-                    if (slice >= a.nslices) continue;
-                    mbar_wait(full_bar(c), (uint32_t)((s - 1) & 1));
-                    REC_STAMP(2);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + c * NB_SLICE;
+        // ===== MMA issuer: the whole warp walks the loop (waits included), one elected lane issues =====
+        if (!WTMEM) mbar_wait(wbar, 0);
+        for (int s = 1; s < T; ++s) {
+            for (int c = 0; c < a.chains; ++c) {
+                const int slice = sg + c * a.bsg;
+                if (slice >= a.nslices) continue;
+                mbar_wait(full_bar(c), (uint32_t)((s - 1) & 1));
+                if (lane == 0) REC_STAMP(2);
+                tc_fence_after();
+                if (elect_one()) {
+                    // consecutive UMMAs into ONE accumulator serialise on it: round-robin over FWD_NACC independent
+                    // accumulators, summed by the epilogue
                     for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((c * FWD_NACC + k) * NB_SLICE);
                             const uint64_t bd = make_desc_k(h_sm + (c * KB + kb) * 4096 + k * 32);
                             if (WTMEM) {
-                                umma_bf16_ts(d_tmem, tmem_w + kb * 32 + k * 8, bd, IDESC, (kb | k) ? 1u : 0u);
+                                umma_bf16_ts(d_tmem, tmem_w + kb * 32 + k * 8, bd, IDESC, kb ? 1u : 0u);
                             } else {
                                 const uint64_t ad = make_desc_k(w_sm + kb * 16384 + k * 32);
-                                umma_bf16(d_tmem, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+                                umma_bf16(d_tmem, ad, bd, IDESC, kb ? 1u : 0u);
                             }
                         }
                     }
                     umma_commit(tfull_bar(c));
-                    REC_STAMP(3);
                 }
+                __syncwarp();
+                if (lane == 0) REC_STAMP(3);
             }
         }
     } else if (warp >= 4) {
@@ -299,21 +313,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                 const long long gstride = (long long)T * a.ndir * 4 * H;
 #pragma unroll
                 for (int n = 0; n < 32; ++n) xg[n] = (b0 + n < a.B) ? gbase[(long long)(b0 + n) * gstride] : 0.f;
-                uint32_t v[32];
                 if (te == 0) REC_STAMP(4);
                 if (s > 0) {
                     mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
                     if (te == 0) REC_STAMP(5);
                     tc_fence_after();
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * NB_SLICE, v);
-                    if (te == 0) REC_STAMP(6);
-                } else {
 #pragma unroll
-                    for (int n = 0; n < 32; ++n) v[n] = 0u;
+                    for (int acc = 0; acc < FWD_NACC; ++acc) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c * FWD_NACC + acc) * NB_SLICE), v);
+#pragma unroll
+                        for (int n = 0; n < 32; ++n) xg[n] += __uint_as_float(v[n]);
+                    }
+                    if (te == 0) REC_STAMP(6);
                 }
 #pragma unroll
                 for (int n = 0; n < 32; ++n) {
-                    const float pre = __uint_as_float(v[n]) + xg[n];
+                    const float pre = xg[n];
                     const float act = (q == 2) ? tanh_fast(pre) : sigmoid_fast(pre);
                     ex[(q * 32 + n) * 32 + j] = act;
                     xg[n] = act;                                   // kept for the deferred save below
@@ -371,6 +387,340 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+
+// =====================================================================================================================
+// "LL" exchange variant of the forward recurrence (the default).
+// The step-to-step exchange of h_t between the H/32 CTAs of a (direction, batch slice) group is the serial bottleneck of
+// the recurrence.  With a release/acquire counter it costs four dependent L2 round trips per step (writer: stores ->
+// release fence; reader: counter poll -> proxy fence -> TMA load); measured 4200 of the 8000 cycles of a step.
+// Here every 8-byte word of the exchange buffer carries its own validity tag -- {2 x bf16 of h_t, step number} -- the way
+// NCCL's LL protocol does: an 8-byte store is single-copy atomic, so a reader that sees the tag sees the data.  Writers
+// just store (no fence, no barrier, no counter); four loader warps poll the words themselves, strip the tags and lay the
+// 32 x H tile out in shared memory in the UMMA K-major SWIZZLE_128B layout, k-block by k-block, each k-block handed to
+// the MMA thread through its own mbarrier so the tensor pipe starts on the first 64 columns while the rest still arrive.
+// =====================================================================================================================
+constexpr int NLOAD = 96;                  // exchange loader threads: warps 0, 2, 3 (warp 1 issues the MMAs)
+constexpr int NTHREADS_LL = 256;
+constexpr int NACC = 4;                    // independent TMEM accumulators per chain (see the MMA issuer)
+
+// two tagged words per load; each 64-bit half is one scalar access (single-copy atomic): x = data0, y = tag0, z = data1, w = tag1
+__device__ __forceinline__ uint4 ld_ll16(const unsigned long long* p) {
+    unsigned long long w0, w1;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    return make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
+}
+__device__ __forceinline__ void st_ll8(unsigned long long* p, uint32_t data, uint32_t tag) {
+    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)data;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// four tagged words (32 bytes, one L2 sector) per load
+struct Ll32 { uint32_t d0, t0, d1, t1, d2, t2, d3, t3; };
+__device__ __forceinline__ Ll32 ld_ll32(const unsigned long long* p) {
+    unsigned long long w0, w1, w2, w3;
+    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(p) : "memory");
+    Ll32 r;
+    r.d0 = (uint32_t)w0; r.t0 = (uint32_t)(w0 >> 32); r.d1 = (uint32_t)w1; r.t1 = (uint32_t)(w1 >> 32);
+    r.d2 = (uint32_t)w2; r.t2 = (uint32_t)(w2 >> 32); r.d3 = (uint32_t)w3; r.t3 = (uint32_t)(w3 >> 32);
+    return r;
+}
+__device__ __forceinline__ unsigned long long ld_ll8(const unsigned long long* p) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return w;
+}
+
+// One 32 x H tile: tagged words (row stride ldw words; word k of a row = units 2k, 2k+1) -> shared memory, UMMA K-major
+// SWIZZLE_128B, k-block-major ([kb][32 rows][128 B]).  96 loader threads (warps 0, 2, 3), lt = 0..95: 16-byte output chunk
+// cc = lt & 7 (= one 32-byte sector of tagged words) of rows n0 = lt >> 3, n0 + 12 and (n0 < 8 only) n0 + 24, for every k-block.
+//   * waiting costs almost no L2 traffic: 16 lanes of warp 0 poll ONE sentinel word per source CTA (its last row, last unit
+//     pair); when all 16 carry the step's tag the three warps meet on a named barrier and issue the real loads.  (Polling with
+//     the real loads from 96 CTAs x 96 threads saturated the L2 and every latency with it -- measured.)  The sentinel is a
+//     hint, not a guarantee: every word is still validated by its own tag and re-loaded until valid.
+//   * the whole tile (KB x 3 sector loads per thread) is in flight at once;
+//   * ONE generic->async proxy fence per thread, after its last load has landed (a proxy fence with global loads in flight
+//     waits for them), then one arrive on `tile_bar`.
+template <int KB>
+__device__ __forceinline__ void ll_load_tile(const unsigned long long* __restrict__ tile, int ldw, uint32_t smem_tile, uint32_t tile_bar,
+                                             uint32_t tag, int lt, uint32_t reuse_bar, uint32_t reuse_parity, bool reuse_wait,
+                                             long long* dbg) {
+    const int cc = lt & 7, n0 = lt >> 3;
+    const bool third = n0 < 8;
+    if (lt < 32) {
+        // sentinel of source CTA r = lane (r < 2*KB): row 31, last word of its 16-word span
+        const unsigned long long* sp = tile + 31LL * ldw + ((lt < 2 * KB ? lt : 0) * 16 + 15);
+        for (;;) {
+            const bool ok = (uint32_t)(ld_ll8(sp) >> 32) == tag;
+            if (__all_sync(0xffffffffu, ok)) break;
+            __nanosleep(20);
+        }
+    }
+    if (dbg) dbg[0] = clock64();
+    named_bar_sync(2, NLOAD);
+    const unsigned long long* p[3];
+    uint32_t so[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int n = (j == 2 && !third) ? n0 : n0 + 12 * j;         // inactive third task aliases the first (never stored)
+        p[j] = tile + (long long)n * ldw + cc * 4;
+        so[j] = smem_tile + n * 128 + ((cc ^ (n & 7)) << 4);
+    }
+    Ll32 buf[KB][3];
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) buf[kb][j] = ld_ll32(p[j] + kb * 32);
+    // fast peers can publish this step while OUR tensor pipe still reads the previous tile: wait for the previous step's MMAs
+    if (reuse_wait) mbar_wait(reuse_bar, reuse_parity);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            Ll32& v = buf[kb][j];
+            while (v.t0 != tag || v.t1 != tag || v.t2 != tag || v.t3 != tag) v = ld_ll32(p[j] + kb * 32);
+            if (j < 2 || third)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(so[j] + kb * 4096), "r"(v.d0), "r"(v.d1), "r"(v.d2), "r"(v.d3) : "memory");
+        }
+    }
+    if (dbg) dbg[11] = clock64();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive(tile_bar);
+}
+
+struct RecLlArgs {
+    float* gates; const int* lens; const float* mask; float* out; float* hs_pad; float* cs_pad;
+    unsigned long long* ll;   // (ndir, 2, Bpad, H/2) tagged words
+    int B, T, H, ndir, nslices, Bpad, chains, bsg, save;
+    long long* dbg;
+};
+
+constexpr int MAX_KB = 8;      // H <= 512 (W_hh slice of 128 x H bf16 must fit in shared memory anyway)
+
+template <int KB, int CHAINS>
+__global__ void __launch_bounds__(NTHREADS_LL, 1) lstm_rec_fwd_ll_kernel(const __grid_constant__ CUtensorMap tmW, const RecLlArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const int H = a.H, T = a.T;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w_sm = base;                                   // KB x [128 rows x 128 B]
+    const uint32_t h_sm = w_sm + KB * 16384;                      // chains x KB x [32 rows x 128 B]
+    const uint32_t ex_off = (h_sm - smem_u32(smem_raw)) + CHAINS * KB * 4096;
+    float* ex = reinterpret_cast<float*>(smem_raw + ex_off);      // [4][32][32] gate exchange
+    const uint32_t bar_base = smem_u32(smem_raw) + ex_off + 4 * 32 * 32 * 4;
+    auto tile_bar = [&](int c) { return bar_base + 8u * c; };
+    auto tfull_bar = [&](int c) { return bar_base + 8u * (MAX_CHAINS + c); };
+    const uint32_t wbar = bar_base + 8u * (2 * MAX_CHAINS);
+    const uint32_t tmem_slot = wbar + 8u;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int r = blockIdx.x, sg = blockIdx.y, dir = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int F = a.ndir * H;
+    const long long brow = (long long)(T + 2) * F;
+    const int ldw = H / 2;
+    constexpr int NA = KB < NACC ? KB : NACC;                     // accumulators actually used
+    constexpr uint32_t TMEM_COLS = MAX_CHAINS * NACC * NB_SLICE;  // 256
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        for (int c = 0; c < MAX_CHAINS; ++c) {
+            mbar_init(tile_bar(c), NLOAD);
+            mbar_init(tfull_bar(c), 1);
+        }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            // resident W_hh slice, once
+            mbar_arrive_expect_tx(wbar, (uint32_t)KB * 16384u);
+            for (int kb = 0; kb < KB; ++kb)
+                for (int g = 0; g < 4; ++g)
+                    tma_load_2d(w_sm + kb * 16384 + g * 4096, &tmW, wbar, kb * 64, dir * 4 * H + g * H + r * UNITS);
+        }
+        __syncwarp();
+        // ===== MMA issuer: the whole warp walks the loop, one elected lane issues.  Consecutive UMMAs into ONE accumulator
+        // serialise on it, so the K loop round-robins over NACC independent accumulators that the epilogue adds up. =====
+        mbar_wait(wbar, 0);
+        for (int s = 1; s < T; ++s) {
+            for (int c = 0; c < CHAINS; ++c) {
+                const int slice = sg + c * a.bsg;
+                if (slice >= a.nslices) continue;
+                mbar_wait(tile_bar(c), (uint32_t)((s - 1) & 1));
+                if (lane == 0) REC_STAMP(2);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int acc = (kb * 4 + k) % NA;
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((c * NACC + acc) * NB_SLICE);
+                            const uint64_t bd = make_desc_k(h_sm + (c * KB + kb) * 4096 + k * 32);
+                            const uint64_t ad = make_desc_k(w_sm + kb * 16384 + k * 32);
+                            umma_bf16(d_tmem, ad, bd, IDESC, (kb * 4 + k) >= NA ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(tfull_bar(c));
+                }
+                __syncwarp();
+                if (lane == 0) REC_STAMP(3);
+            }
+        }
+    } else if (warp < 4) {
+        // ===== exchange loaders (warps 0, 2, 3): poll the group's tagged h_{s-1} words, strip the tags, build the B operand =====
+        const int lt = (warp == 0 ? 0 : warp - 1) * 32 + lane;
+        for (int s = 1; s < T; ++s) {
+            for (int c = 0; c < CHAINS; ++c) {
+                const int slice = sg + c * a.bsg;
+                if (slice >= a.nslices) continue;
+                const unsigned long long* tile = a.ll + ((long long)(dir * 2 + ((s - 1) & 1)) * a.Bpad + slice * NB_SLICE) * ldw;
+                ll_load_tile<KB>(tile, ldw, h_sm + c * KB * 4096, tile_bar(c), (uint32_t)s, lt, tfull_bar(c), (uint32_t)(s & 1), s > 1,
+                                 (a.dbg && lt == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && s < 256) ? a.dbg + s * 16 : nullptr);
+                if (lt == 0) REC_STAMP(1);
+            }
+        }
+    } else {
+        // ===== epilogue (warps 4-7): one warp per gate =====
+        const int q = warp & 3, j = lane;          // gate q, unit r*32 + j
+        const int te = (warp - 4) * 32 + lane;     // 0..127
+        const int u = r * UNITS + j;
+        float cst[CHAINS][8];
+        int lenr[CHAINS][8];
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                cst[c][i] = 0.f;
+                const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
+                lenr[c][i] = (sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
+            }
+        for (int c = 0; c < CHAINS; ++c) {
+            const int slice = sg + c * a.bsg;
+            if (slice >= a.nslices) continue;
+            for (int i = 0; i < 8; ++i) {
+                const int b = slice * NB_SLICE + q * 8 + i;
+                if (b < a.B) {
+                    const long long o0 = (long long)b * brow + dir * H + u, o1 = o0 + (long long)(T + 1) * F;
+                    a.hs_pad[o0] = 0.f; a.cs_pad[o0] = 0.f; a.hs_pad[o1] = 0.f; a.cs_pad[o1] = 0.f;
+                }
+            }
+        }
+        const bool odd = (j & 1) != 0;
+        for (int s = 0; s < T; ++s) {
+            const int t = (dir == 0) ? s : (T - 1 - s);
+#pragma unroll
+            for (int c = 0; c < CHAINS; ++c) {
+                const int slice = sg + c * a.bsg;
+                if (slice >= a.nslices) continue;
+                const int b0 = slice * NB_SLICE;
+                // input projection for (gate q, unit j) of the 32 batch rows: coalesced 128 B per row, issued before the wait
+                float xg[32];
+                float* gbase = a.gates + ((long long)t * a.ndir + dir) * 4 * H + q * H + u;
+                const long long gstride = (long long)T * a.ndir * 4 * H;
+#pragma unroll
+                for (int n = 0; n < 32; ++n) xg[n] = (b0 + n < a.B) ? gbase[(long long)(b0 + n) * gstride] : 0.f;
+                if (te == 0) REC_STAMP(4);
+                if (s > 0) {
+                    mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
+                    if (te == 0) REC_STAMP(5);
+                    tc_fence_after();
+#pragma unroll
+                    for (int acc = 0; acc < NA; ++acc) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c * NACC + acc) * NB_SLICE), v);
+#pragma unroll
+                        for (int n = 0; n < 32; ++n) xg[n] += __uint_as_float(v[n]);
+                    }
+                    if (te == 0) REC_STAMP(6);
+                }
+#pragma unroll
+                for (int n = 0; n < 32; ++n) {
+                    const float act = (q == 2) ? tanh_fast(xg[n]) : sigmoid_fast(xg[n]);
+                    ex[(q * 32 + n) * 32 + j] = act;
+                    xg[n] = act;                                   // kept for the deferred save below
+                }
+                tc_fence_before();
+                named_bar_sync(1, 128);
+                if (te == 0) REC_STAMP(7);
+                // cell update: thread (q, j) owns unit j for batch rows n = q*8 + i
+                float hh[8], cc[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int n = q * 8 + i;
+                    const float gi = ex[(0 * 32 + n) * 32 + j], gf = ex[(1 * 32 + n) * 32 + j];
+                    const float gg = ex[(2 * 32 + n) * 32 + j], go = ex[(3 * 32 + n) * 32 + j];
+                    const bool valid = t < lenr[c][i];
+                    cc[i] = 0.f; hh[i] = 0.f;
+                    if (valid) {
+                        cc[i] = fmaf(gf, cst[c][i], gi * gg);
+                        hh[i] = go * tanh_fast(cc[i]);
+                    }
+                    cst[c][i] = cc[i];
+                }
+                // publish h_t: tagged 8-byte words {units (2k, 2k+1), step}; even lanes carry rows 0-3 of this warp's 8, odd
+                // lanes rows 4-7.  Nothing else: no fence, no barrier, no counter -- the peers' loaders poll the words themselves.
+                if (s + 1 < T) {
+                    float oth[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) oth[i] = __shfl_xor_sync(0xffffffffu, hh[i], 1);
+                    unsigned long long* wbase = a.ll + ((long long)(dir * 2 + (s & 1)) * a.Bpad + b0 + q * 8 + (odd ? 4 : 0)) * ldw + (u >> 1);
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const float own = odd ? hh[4 + ii] : hh[ii], ot = odd ? oth[4 + ii] : oth[ii];
+                        st_ll8(wbase + (long long)ii * ldw, odd ? pack_bf16x2(ot, own) : pack_bf16x2(own, ot), (uint32_t)(s + 1));
+                    }
+                }
+                if (te == 0) REC_STAMP(9);
+                // `ex` is rewritten by this chain's next step only after every peer -- hence every warp of this CTA -- has
+                // published, i.e. has read it; with several chains per CTA the next chain reuses it right away
+                if (CHAINS > 1) named_bar_sync(1, 128);
+                // ... then what only backward / the next layer read; these stores overlap the wait for the next step
+                if (a.save) {
+#pragma unroll
+                    for (int n = 0; n < 32; ++n)
+                        if (b0 + n < a.B) gbase[(long long)(b0 + n) * gstride] = xg[n];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + q * 8 + i;
+                    if (b < a.B) {
+                        const long long so = (long long)b * brow + (long long)(t + 1) * F + dir * H + u;
+                        a.hs_pad[so] = hh[i];
+                        a.cs_pad[so] = cc[i];
+                        if (a.out) {
+                            const float m = a.mask ? a.mask[(long long)b * F + dir * H + u] : 1.f;
+                            a.out[((long long)b * T + t) * F + dir * H + u] = hh[i] * m;
+                        }
+                    }
+                }
+                if (te == 0) REC_STAMP(10);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -453,8 +803,9 @@ extern "C" int las_lstm_rec_tc_supported(int B, int H, int ndir) {
 
 extern "C" size_t las_lstm_rec_tc_workspace_bytes(int B, int H, int ndir) {
     const int nsl = ceil_div(B, NB_SLICE);
-    // counters (1 KB) + bf16 exchange buffer: forward h (ndir, 2, Bpad, H); backward dG (ndir, 2, 4, Bpad, H)
-    return 1024 + (size_t)ndir * 2 * 4 * nsl * NB_SLICE * H * 2;
+    // counters (1 KB) + exchange buffer of tagged 8-byte words {2 x bf16, step}: forward h (ndir, 2, Bpad, H/2);
+    // backward dG (ndir, 2, 4, Bpad, H/2)
+    return 1024 + (size_t)ndir * 2 * 4 * nsl * NB_SLICE * H * 4;
 }
 
 extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const int* lens, const float* drop_mask, float* out,
@@ -469,6 +820,45 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
     if (rc) return rc;
     if (ws_bytes < las_lstm_rec_tc_workspace_bytes(B, H, ndir)) { las_set_error("lstm_rec_fwd_tc: workspace too small"); return LAS_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        const char* e = getenv("LAS_REC_LL");
+        const int KBh = H / 64;
+        if ((e && atoi(e) != 0) && (KBh == 1 || KBh == 2 || KBh == 4 || KBh == 8) && (p.chains == 1 || (e && atoi(e) == 2))) {
+            RecLlArgs la{};
+            la.gates = gates; la.lens = lens; la.mask = drop_mask; la.out = out; la.hs_pad = hs_pad; la.cs_pad = cs_pad;
+            la.ll = (unsigned long long*)((char*)ws + 1024);
+            la.B = B; la.T = T; la.H = H; la.ndir = ndir; la.nslices = p.nslices; la.Bpad = p.Bpad; la.chains = p.chains; la.bsg = p.bsg;
+            la.save = save_gates; la.dbg = g_rec_dbg;
+            const int KB = H / 64;
+            const size_t smem = 1024 + (size_t)KB * 16384 + (size_t)p.chains * KB * 4096 + 4 * 32 * 32 * 4 +
+                                8 * (MAX_CHAINS * MAX_KB + MAX_CHAINS + 2) + 64;
+            LAS_CHECK_ARG(smem <= (size_t)las_device_info()->max_smem_optin, "lstm_rec_fwd_tc: needs %zu B of shared memory", smem);
+            CUtensorMap tmW;
+            rc = make_map_2d(&tmW, w_hh_bf16, H, (long long)ndir * 4 * H, 64, 32);
+            if (rc) return rc;
+            void* kern = nullptr;
+            const int key = KB * 10 + p.chains;
+            switch (key) {
+                case 11: kern = (void*)lstm_rec_fwd_ll_kernel<1, 1>; break;
+                case 12: kern = (void*)lstm_rec_fwd_ll_kernel<1, 2>; break;
+                case 21: kern = (void*)lstm_rec_fwd_ll_kernel<2, 1>; break;
+                case 22: kern = (void*)lstm_rec_fwd_ll_kernel<2, 2>; break;
+                case 41: kern = (void*)lstm_rec_fwd_ll_kernel<4, 1>; break;
+                case 42: kern = (void*)lstm_rec_fwd_ll_kernel<4, 2>; break;
+                case 81: kern = (void*)lstm_rec_fwd_ll_kernel<8, 1>; break;
+                case 82: kern = (void*)lstm_rec_fwd_ll_kernel<8, 2>; break;
+                default: break;
+            }
+            LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // tags are step numbers: clear the words of the previous launch
+            LAS_CUDA(cudaMemsetAsync(la.ll, 0, (size_t)ndir * 2 * p.Bpad * H * 4, st));
+            LasProfScope prof(LAS_PROF_REC_FWD, stream, (double)T);
+            void* args[] = {(void*)&tmW, (void*)&la};
+            LAS_CUDA(cudaLaunchCooperativeKernel(kern, dim3(p.rs, p.bsg, ndir), dim3(NTHREADS_LL), args, smem, st));
+            las_count_launch(1);
+            return LAS_OK;
+        }
+    }
     RecTcArgs a{};
     a.gates = gates; a.lens = lens; a.mask = drop_mask; a.out = out; a.hs_pad = hs_pad; a.cs_pad = cs_pad;
     a.ctr = (unsigned*)ws; a.hbuf = (__nv_bfloat16*)((char*)ws + 1024);
@@ -476,7 +866,9 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
     a.w_gl = (const __nv_bfloat16*)w_hh_bf16;
     {
         const char* e = getenv("LAS_REC_WTMEM");
-        a.w_tmem = (e ? atoi(e) : 0) && H <= 512;   // measured slower than shared-memory A at N = 32: off by default
+        // W_hh slice as the A operand from tensor memory: with the elected-lane issue + 4 accumulators the 32 UMMAs of a step
+        // take 840 cycles instead of 1600 (shared-memory A: 4 KB of operand reads per UMMA bound it); LAS_REC_WTMEM=0 disables
+        a.w_tmem = (e ? atoi(e) != 0 : true) && H <= 512;
     }
     LAS_CHECK_ARG((size_t)ndir * p.nslices * sizeof(unsigned) <= 1024, "lstm_rec_fwd_tc: too many batch slices");
     CUtensorMap tmW, tmH;
@@ -521,6 +913,7 @@ struct RecTcBwdArgs {
     unsigned* ctr;
     int B, T, H, ndir, nslices, chains, bsg, KBr, CH, Bpad;
     __nv_bfloat16* dgx;      // K-split variant: compact bf16 exchange buffer (ndir, 2, 4 gates, Bpad, H)
+    const __nv_bfloat16* w_t; // W_hh^T bf16 (ndir, H, 4H): source of the TMEM-resident A operand
     long long* dbg;
 };
 
@@ -828,13 +1221,16 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_saddr, uint32_t cta
 
 constexpr int PART_LD = 132;          // floats per batch row of the partial tile [32 b][128 u] (+4 pad)
 
+constexpr int BWD_NACC = 4;
+
+template <bool WTMEM>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
     lstm_rec_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmWt, const __grid_constant__ CUtensorMap tmG, const RecTcBwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const int H = a.H, T = a.T, KB = H / 64;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_sm = base;                                        // KB x [128 rows(u) x 128 B]  resident W_hh^T tile
-    const uint32_t b_sm = a_sm + KB * 16384;                           // chains x KB x [32 rows(b) x 128 B]
+    const uint32_t b_sm = a_sm + (WTMEM ? 0 : KB * 16384);             // chains x KB x [32 rows(b) x 128 B]
     const uint32_t part_off = (b_sm - smem_u32(smem_raw)) + a.chains * KB * 4096;
     float* part0 = reinterpret_cast<float*>(smem_raw + part_off);      // [2][32][PART_LD]: ping-pong, so one cluster barrier per step suffices
     const uint32_t part_saddr0 = smem_u32(smem_raw) + part_off;
@@ -860,14 +1256,37 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // TMEM map: BWD_NACC independent accumulators per chain first, then (WTMEM) the resident W_hh^T tile (H/2 columns)
+    const uint32_t tmem_cols = WTMEM ? 512u : 256u;
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t tmem_w = tmem_base + MAX_CHAINS * BWD_NACC * NB_SLICE;
+    if (WTMEM) {
+        if (warp >= 4) {
+            // A operand in tensor memory: TMEM lane = unit row of the block, column pair = two consecutive k (gate rows of gate kq)
+            const int qq = warp & 3;
+            const uint32_t* wrow = reinterpret_cast<const uint32_t*>(a.w_t + ((long long)(dir * H + ub * 128 + qq * 32 + lane)) * G4 + kq * H);
+            for (int cb = 0; cb < H / 64; ++cb) {
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 t4 = *reinterpret_cast<const uint4*>(wrow + cb * 32 + i * 4);
+                    v[i * 4 + 0] = t4.x; v[i * 4 + 1] = t4.y; v[i * 4 + 2] = t4.z; v[i * 4 + 3] = t4.w;
+                }
+                tmem_st32(tmem_w + ((uint32_t)(qq * 32) << 16) + cb * 32, v);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     // per-thread state of the epilogue role (declared for all so the step loop below is shared by every warp)
     const int q = warp & 3, j = lane;
@@ -884,11 +1303,13 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
             lenr[c][i] = (warp >= 4 && c < a.chains && sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
         }
 
-    if (warp == 0 && lane == 0) {
-        mbar_arrive_expect_tx(wbar, (uint32_t)KB * 16384u);
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(a_sm + kb * 16384, &tmWt, wbar, kq * H + kb * 64, dir * H + ub * 128);
+    if (!WTMEM) {
+        if (warp == 0 && lane == 0) {
+            mbar_arrive_expect_tx(wbar, (uint32_t)KB * 16384u);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(a_sm + kb * 16384, &tmWt, wbar, kq * H + kb * 64, dir * H + ub * 128);
+        }
+        if (warp == 1) mbar_wait(wbar, 0);
     }
-    if (warp == 1 && lane == 0) mbar_wait(wbar, 0);
 
     // Every warp walks the same (step, chain) sequence: the cluster barrier of each iteration needs all threads of all 4 CTAs.
     int iter = 0;
@@ -920,21 +1341,30 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                 }
                 __syncwarp();
             } else if (warp == 1) {
-                if (lane == 0 && s > 0) {
+                if (s > 0) {
+                    // whole warp waits, one elected lane issues (uniform control flow keeps the descriptors in uniform registers);
+                    // BWD_NACC independent accumulators (one per k sub-step) break the accumulate-dependency chain
                     mbar_wait(full_bar(c), (uint32_t)((s - 1) & 1));
-                    REC_STAMP(2);
+                    if (lane == 0) REC_STAMP(2);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + c * NB_SLICE;
-                    for (int kb = 0; kb < KB; ++kb) {
+                    if (elect_one()) {
+                        for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t ad = make_desc_k(a_sm + kb * 16384 + k * 32);
-                            const uint64_t bd = make_desc_k(b_sm + (c * KB + kb) * 4096 + k * 32);
-                            umma_bf16(d_tmem, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t d_tmem = tmem_base + (uint32_t)((c * BWD_NACC + k) * NB_SLICE);
+                                const uint64_t bd = make_desc_k(b_sm + (c * KB + kb) * 4096 + k * 32);
+                                if (WTMEM) {
+                                    umma_bf16_ts(d_tmem, tmem_w + kb * 32 + k * 8, bd, IDESC, kb ? 1u : 0u);
+                                } else {
+                                    const uint64_t ad = make_desc_k(a_sm + kb * 16384 + k * 32);
+                                    umma_bf16(d_tmem, ad, bd, IDESC, kb ? 1u : 0u);
+                                }
+                            }
                         }
+                        umma_commit(tfull_bar(c));
                     }
-                    umma_commit(tfull_bar(c));
-                    REC_STAMP(3);
+                    __syncwarp();
+                    if (lane == 0) REC_STAMP(3);
                 }
                 __syncwarp();
             } else if (warp >= 4) {
@@ -960,11 +1390,17 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                     mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
                     if (te == 0) REC_STAMP(5);
                     tc_fence_after();
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * NB_SLICE, v);
+                    float accv[32];
+#pragma unroll
+                    for (int acc = 0; acc < BWD_NACC; ++acc) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c * BWD_NACC + acc) * NB_SLICE), v);
+#pragma unroll
+                        for (int n = 0; n < 32; ++n) accv[n] = acc ? accv[n] + __uint_as_float(v[n]) : __uint_as_float(v[n]);
+                    }
                     // TMEM lane = unit (32q + lane) of the block, column = batch row: park the partial as part[b][unit]
 #pragma unroll
-                    for (int n = 0; n < 32; ++n) part[n * PART_LD + q * 32 + lane] = __uint_as_float(v[n]);
+                    for (int n = 0; n < 32; ++n) part[n * PART_LD + q * 32 + lane] = accv[n];
                     tc_fence_before();
                     if (te == 0) REC_STAMP(6);
                 }
@@ -973,14 +1409,17 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                 cluster_sync_all();                                   // all four gate-partials are in shared memory
                 if (warp == 4 && lane == 0) REC_STAMP(7);
                 if (warp >= 4) {
+                    // all 32 remote loads are issued before the first add (an in-order warp would otherwise pay the DSMEM latency
+                    // once per row)
+                    float p4[8][4];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const uint32_t off = part_saddr + (uint32_t)(((q * 8 + i) * PART_LD + kq * 32 + j) * 4);
-                        float p4[4];
 #pragma unroll
-                        for (int src = 0; src < 4; ++src) p4[src] = ld_dsmem_f32(off, (uint32_t)src);
-                        rec[i] = (p4[0] + p4[1]) + (p4[2] + p4[3]);
+                        for (int src = 0; src < 4; ++src) p4[i][src] = ld_dsmem_f32(off, (uint32_t)src);
                     }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rec[i] = (p4[i][0] + p4[i][1]) + (p4[i][2] + p4[i][3]);
                 }
                 if (warp == 4 && lane == 0) REC_STAMP(11);
                 // no second barrier: the partial tile ping-pongs, and a peer can only be two iterations ahead of my reads
@@ -1033,7 +1472,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
     cluster_sync_all();                                               // no CTA of the cluster exits while a peer may still read its smem
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -1052,9 +1491,12 @@ static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, co
     const int chains = ceil_div(nslices, bsg);
     if (chains > MAX_CHAINS) return LAS_ERR_UNSUPPORTED;
     const int KB = H / 64;
-    const size_t smem = 1024 + (size_t)KB * 16384 + (size_t)chains * KB * 4096 + 2 * 32 * PART_LD * 4 + 16 + 8 * (2 * MAX_CHAINS + 2) + 64;
+    const char* wt_env = getenv("LAS_REC_WTMEM");
+    const bool wtmem = (wt_env ? atoi(wt_env) != 0 : true) && H <= 512;
+    const size_t smem = 1024 + (wtmem ? 0 : (size_t)KB * 16384) + (size_t)chains * KB * 4096 + 2 * 32 * PART_LD * 4 + 16 + 8 * (2 * MAX_CHAINS + 2) + 64;
     if (smem > (size_t)di->max_smem_optin) return LAS_ERR_UNSUPPORTED;
     RecTcBwdArgs a{};
+    a.w_t = (const __nv_bfloat16*)w_hh_t_bf16;
     a.gates = gates; a.dgb = (__nv_bfloat16*)dgates_bf16; a.dout = dout; a.cs_pad = cs_pad; a.lens = lens; a.mask = drop_mask;
     a.ctr = (unsigned*)ws;
     a.B = B; a.T = T; a.H = H; a.ndir = ndir; a.nslices = nslices; a.chains = chains; a.bsg = bsg; a.KBr = 4 * H / 64; a.CH = KB; a.dbg = g_rec_dbg;
@@ -1072,14 +1514,15 @@ static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, co
         if (rc) return rc;
     }
     (void)NG;
-    if (cudaFuncSetAttribute(lstm_rec_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    void* kern = wtmem ? (void*)lstm_rec_bwd_tc2_kernel<true> : (void*)lstm_rec_bwd_tc2_kernel<false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return LAS_ERR_UNSUPPORTED;
     }
     LAS_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
     LasProfScope prof(LAS_PROF_REC_BWD, stream, (double)T);
     void* args[] = {(void*)&tmWt, (void*)&tmG, (void*)&a};
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)lstm_rec_bwd_tc2_kernel, dim3(rs, bsg, ndir), dim3(NTHREADS), args, smem, st);
+    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(rs, bsg, ndir), dim3(NTHREADS), args, smem, st);
     if (e != cudaSuccess) {
         las_set_error("lstm_rec_bwd_tc2 launch failed: %s", cudaGetErrorString(e));
         cudaGetLastError();

@@ -26,10 +26,16 @@ for it in range(2):
 lib.las_lstm_rec_tc_set_debug(None)
 d = dbg.cpu().numpy().reshape(256, 16).astype(np.float64)
 names = ['P flag seen', 'P tma issued', 'M full', 'M committed', 'E start', 'E tfull', 'E tmem ld', 'E act+bar', 'E cell+bar', 'E released', 'E stores', 'P fence done']
+if os.environ.get('LAS_REC_LL', '1') != '0':
+    # LL exchange variant: slot 1 = loader: whole tile in smem (stamped during the step that consumes it), 2 = first k-block handed
+    # to the MMA thread, 3 = MMAs committed, 9 = h_t published (tagged stores issued)
+    names = ['L sentinels ok', 'L arrived', 'M tile ready', 'M committed', 'E start', 'E tfull', 'E tmem ld', 'E act+bar', '-', 'E published', 'E stores', 'L words valid']
 lo, hi = 20, min(T - 1, 200)
 base = d[lo:hi, 4]                      # epilogue start of step s
 prev_rel = d[lo - 1:hi - 1, 9]          # release of step s-1
 print('cycles relative to the release of the previous step (mean over steps %d..%d):' % (lo, hi))
 for k, nm in enumerate(names):
+    if nm == '-':
+        continue
     print(f'  {nm:14s} {np.mean(d[lo:hi, k] - prev_rel):9.0f}')
 print('step period (release to release): %.0f cycles' % np.mean(d[lo:hi, 9] - prev_rel))
