@@ -16,6 +16,7 @@
 #include "las_common.cuh"
 #include "las_b200.h"
 #include <vector>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
 
@@ -438,6 +439,64 @@ unsigned long long fnv1a(const void* p, size_t n, unsigned long long h) {
 int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st);
 }  // namespace
 
+namespace {
+int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Layout& L, cudaStream_t st);
+std::mutex g_graph_mu;
+
+// Runs `enqueue(stream)` through the graph cache: replay when `key` is known, else capture on a side stream, instantiate,
+// remember (LRU of 8) and launch.  Any capture failure (and LAS_DEC_GRAPH=0, or per-kernel profiling of the inner kernels)
+// falls back to enqueueing directly on `st`.
+template <class F>
+int run_graph_cached(unsigned long long key, cudaStream_t st, F enqueue) {
+    const char* genv = getenv("LAS_DEC_GRAPH");
+    const bool inner_prof = (las_prof_mask_get() & ((1u << LAS_PROF_GEMM_OTHER) | (1u << LAS_PROF_ATTN_FWD) | (1u << LAS_PROF_ATTN_BWD))) != 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if ((genv && atoi(genv) == 0) || inner_prof || dev < 0 || dev >= 64) return enqueue(st);
+    key = fnv1a(&dev, sizeof(dev), key);
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    for (auto& e : g_graphs)
+        if (e.key == key) {
+            e.stamp = ++g_graph_clock;
+            ++g_graph_replays;
+            LAS_CUDA(cudaGraphLaunch(e.exec, st));
+            las_count_launch(e.nlaunch);          // the replay runs the same kernels the capture recorded
+            return LAS_OK;
+        }
+    if (!g_capture_stream_ok[dev]) {
+        if (cudaStreamCreateWithFlags(&g_capture_stream[dev], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return enqueue(st); }
+        g_capture_stream_ok[dev] = true;
+    }
+    cudaStream_t cs = g_capture_stream[dev];
+    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return enqueue(st); }
+    const long long launches_before = las_launch_count();
+    int rc = enqueue(cs);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (rc != LAS_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc != LAS_OK) return rc;
+        return enqueue(st);
+    }
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess || !exec) { cudaGetLastError(); return enqueue(st); }
+    if (g_graphs.size() >= 8) {           // evict the least recently used
+        size_t lru = 0;
+        for (size_t i = 1; i < g_graphs.size(); ++i)
+            if (g_graphs[i].stamp < g_graphs[lru].stamp) lru = i;
+        cudaGraphExecDestroy(g_graphs[lru].exec);
+        g_graphs.erase(g_graphs.begin() + lru);
+    }
+    g_graphs.push_back({key, exec, ++g_graph_clock, (int)(las_launch_count() - launches_before)});
+    ++g_graph_captures;
+    LAS_CUDA(cudaGraphLaunch(exec, st));
+    return LAS_OK;
+}
+}  // namespace
+
 extern "C" void las_speller_graph_stats(long long* captures, long long* replays) {
     if (captures) *captures = g_graph_captures;
     if (replays) *replays = g_graph_replays;
@@ -453,58 +512,13 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
     RC(las_set_device_of(s->fws));
     cudaStream_t st = (cudaStream_t)stream;
     LasProfScope prof(LAS_PROF_SPELLER_FWD, stream, (double)s->steps);
-    const char* genv = getenv("LAS_DEC_GRAPH");
-    const bool inner_prof = (las_prof_mask_get() & ((1u << LAS_PROF_GEMM_OTHER) | (1u << LAS_PROF_ATTN_FWD) | (1u << LAS_PROF_ATTN_BWD))) != 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if ((genv && atoi(genv) == 0) || inner_prof || dev < 0 || dev >= 64) return speller_fwd_enqueue(s, L, st);
-
     // key: every field of the descriptor except the HOST coin pointer (a fresh host array per call), whose contents are hashed
     LasSpeller kd;
     memcpy(&kd, s, sizeof(LasSpeller));
     kd.use_gold_host = nullptr;
     unsigned long long key = fnv1a(&kd, sizeof(LasSpeller), 1469598103934665603ULL);
     if (s->use_gold_host) key = fnv1a(s->use_gold_host, (size_t)s->steps, key);
-    key = fnv1a(&dev, sizeof(dev), key);
-    for (auto& e : g_graphs)
-        if (e.key == key) {
-            e.stamp = ++g_graph_clock;
-            ++g_graph_replays;
-            LAS_CUDA(cudaGraphLaunch(e.exec, st));
-            las_count_launch(e.nlaunch);          // the replay runs the same kernels the capture recorded
-            return LAS_OK;
-        }
-    if (!g_capture_stream_ok[dev]) {
-        if (cudaStreamCreateWithFlags(&g_capture_stream[dev], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return speller_fwd_enqueue(s, L, st); }
-        g_capture_stream_ok[dev] = true;
-    }
-    cudaStream_t cs = g_capture_stream[dev];
-    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return speller_fwd_enqueue(s, L, st); }
-    const long long launches_before = las_launch_count();
-    int rc = speller_fwd_enqueue(s, L, cs);
-    cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-    if (rc != LAS_OK || ce != cudaSuccess || !graph) {
-        if (graph) cudaGraphDestroy(graph);
-        cudaGetLastError();
-        if (rc != LAS_OK) return rc;
-        return speller_fwd_enqueue(s, L, st);
-    }
-    cudaGraphExec_t exec = nullptr;
-    ce = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess || !exec) { cudaGetLastError(); return speller_fwd_enqueue(s, L, st); }
-    if (g_graphs.size() >= 8) {           // evict the least recently used
-        size_t lru = 0;
-        for (size_t i = 1; i < g_graphs.size(); ++i)
-            if (g_graphs[i].stamp < g_graphs[lru].stamp) lru = i;
-        cudaGraphExecDestroy(g_graphs[lru].exec);
-        g_graphs.erase(g_graphs.begin() + lru);
-    }
-    g_graphs.push_back({key, exec, ++g_graph_clock, (int)(las_launch_count() - launches_before)});
-    ++g_graph_captures;
-    LAS_CUDA(cudaGraphLaunch(exec, st));
-    return LAS_OK;
+    return run_graph_cached(key, st, [&](cudaStream_t q) { return speller_fwd_enqueue(s, L, q); });
 }
 
 namespace {
@@ -692,9 +706,21 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     }
     RC(las_set_device_of(s->fws));
     cudaStream_t st = (cudaStream_t)stream;
+    LasProfScope prof(LAS_PROF_SPELLER_BWD, stream, (double)s->steps);
+    // same graph cache as the forward loop: key = descriptor (coin contents hashed) + every gradient pointer
+    LasSpeller kd;
+    memcpy(&kd, s, sizeof(LasSpeller));
+    kd.use_gold_host = nullptr;
+    unsigned long long key = fnv1a(&kd, sizeof(LasSpeller), 7809847782465536322ULL);
+    if (s->use_gold_host) key = fnv1a(s->use_gold_host, (size_t)s->steps, key);
+    key = fnv1a(g, sizeof(LasSpellerGrads), key);
+    return run_graph_cached(key, st, [&](cudaStream_t q) { return speller_bwd_enqueue(s, g, L, q); });
+}
+
+namespace {
+int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Layout& L, cudaStream_t st) {
     const int B = s->B, T = s->T, P = s->P, E = s->E, DH = s->DH, DO = s->DO, V = s->V, S = s->steps, heads = s->heads;
     const int K0 = P + DH, K1 = DH + DO, d_head = P / heads;
-    LasProfScope prof(LAS_PROF_SPELLER_BWD, stream, (double)S);
     float* f = s->fws;
     float *Wcat0 = f + L.Wcat0, *Wcat1 = f + L.Wcat1, *S0 = f + L.S0, *S1 = f + L.S1, *C0 = f + L.C0, *C1 = f + L.C1, *G0 = f + L.G0,
           *G1 = f + L.G1, *QC = f + L.QC, *W = f + L.W, *dQC = f + L.dQC, *dS0 = f + L.dS0, *dS1 = f + L.dS1, *dc0 = f + L.dc0,
@@ -865,3 +891,4 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     }
     return LAS_OK;
 }
+}  // namespace

@@ -582,17 +582,22 @@ class SpellerFunction(torch.autograd.Function):
         s.fws, s.fws_floats, s.iws, s.iws_ints = fws.data_ptr(), fws.numel(), iws.data_ptr(), iws.numel()
         # outputs of fwd are not needed by bwd but the descriptor check wants non-null
         s.logits, s.chars = fws.data_ptr(), t['chars'].data_ptr()
-        dlogits = _f32c(dlogits)
+        # the backward loop is graph-cached on its pointers too: stage dlogits in, write every gradient into slot buffers
+        slot = lease.slot
+        dl = slot.buf('dlogits', tuple(dlogits.shape), torch.float32, K.device)
+        dl.copy_(dlogits)
         g = LasSpellerGrads()
-        g.dlogits = dlogits.data_ptr()
-        grads = [torch.empty_like(p) for p in params]
-        for name, tt in zip(SPELLER_PARAM_ORDER, grads):
+        g.dlogits = dl.data_ptr()
+        gbufs = [slot.buf('g_' + name, tuple(p.shape), torch.float32, K.device) for name, p in zip(SPELLER_PARAM_ORDER, params)]
+        for name, tt in zip(SPELLER_PARAM_ORDER, gbufs):
             setattr(g, 'd_' + name, tt.data_ptr())
         # d_w_ih0 is written in three column/row pieces that together cover it; no zero-init needed
-        dK = torch.empty(K.shape, dtype=torch.float32, device=K.device)
-        dV = torch.empty(V.shape, dtype=torch.float32, device=K.device)
-        g.dK, g.dV = dK.data_ptr(), dV.data_ptr()
+        dKb = slot.buf('dK', tuple(K.shape), torch.float32, K.device)
+        dVb = slot.buf('dV', tuple(V.shape), torch.float32, K.device)
+        g.dK, g.dV = dKb.data_ptr(), dVb.data_ptr()
         check(lib.las_speller_bwd_f32(C.byref(s), C.byref(g), stream_ptr()), 'speller_bwd')
+        grads = [t_.clone() for t_ in gbufs]           # the caller (autograd) owns what it receives
+        dK, dV = dKb.clone(), dVb.clone()
         lease.release()
         return (dK, dV, None, None, None, None, None, None, None, None, None, None, None, *grads)
 
