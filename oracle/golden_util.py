@@ -125,3 +125,66 @@ def make_inputs(seed: int, B: int, T: int, L: int, lx: List[int] = None, input_d
         x[b, lx[b]:] = 0.0
     y = rng.integers(1, 29, size=(B, L)).astype(np.int64)
     return x, lx, y
+
+
+# ---- Rewriter (src/lmtrain.py:95-253, config/rewriter.yml:46-63) ----
+REWRITER_CONFIGS = {
+    # fp32-kernel-sized fixture
+    'rw_micro': dict(vocab_size=30, emb_dim=32, enc_lstm_layers=2, enc_lstm_hid_dim=32, enc_dropouts=[0.0, 0.0], att_proj_dim=16,
+                     att_heads=4, att_dropout=0.0, dec_lstm_layers=2, dec_lstm_hid_dim=24, dec_lstm_out_dim=8, dec_lstm_dropout=0.0,
+                     CHR_PAD_IDX=29, CHR_MAX_STEPS=12, CHR_SOS_IDX=0),
+    # config/rewriter.yml dims
+    'rw_yml': dict(vocab_size=30, emb_dim=256, enc_lstm_layers=2, enc_lstm_hid_dim=256, enc_dropouts=[0.3, 0.3], att_proj_dim=128,
+                   att_heads=4, att_dropout=0.2, dec_lstm_layers=2, dec_lstm_hid_dim=256, dec_lstm_out_dim=128, dec_lstm_dropout=0.3,
+                   CHR_PAD_IDX=29, CHR_MAX_STEPS=600, CHR_SOS_IDX=0),
+}
+
+
+def get_rewriter_config(name: str, **overrides) -> dict:
+    cfg = copy.deepcopy(REWRITER_CONFIGS[name])
+    cfg.update(overrides)
+    return cfg
+
+
+def rewriter_state_dict_shapes(cfg: dict) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Rewriter.state_dict() keys / shapes in named_parameters() order (verified against the reference in make_golden)."""
+    V, E, H, P, DH, DO = (cfg['vocab_size'], cfg['emb_dim'], cfg['enc_lstm_hid_dim'], cfg['att_proj_dim'], cfg['dec_lstm_hid_dim'],
+                          cfg['dec_lstm_out_dim'])
+    out: List[Tuple[str, Tuple[int, ...]]] = [('init_query', (1, DO)), ('char_emb.weight', (V, E))]
+    for i in range(cfg['enc_lstm_layers']):
+        din = E if i == 0 else 2 * H
+        for suf in ['', '_reverse']:
+            out += [(f'enc_lstm.lstms.{i}.weight_ih_l0{suf}', (4 * H, din)), (f'enc_lstm.lstms.{i}.weight_hh_l0{suf}', (4 * H, H)),
+                    (f'enc_lstm.lstms.{i}.bias_ih_l0{suf}', (4 * H,)), (f'enc_lstm.lstms.{i}.bias_hh_l0{suf}', (4 * H,))]
+    for nm, (o, i) in (('key_map', (P, 2 * H)), ('value_map', (P, 2 * H)), ('query_map', (P, DO)), ('final_map', (P, P))):
+        out += [(f'mha.{nm}.weight', (o, i)), (f'mha.{nm}.bias', (o,))]
+    out += [('dec_lstm.lstms.0.weight_ih', (4 * DH, E + P)), ('dec_lstm.lstms.0.weight_hh', (4 * DH, DH)),
+            ('dec_lstm.lstms.0.bias_ih', (4 * DH,)), ('dec_lstm.lstms.0.bias_hh', (4 * DH,)),
+            ('dec_lstm.lstms.1.weight_ih', (4 * DO, DH)), ('dec_lstm.lstms.1.weight_hh', (4 * DO, DO)),
+            ('dec_lstm.lstms.1.bias_ih', (4 * DO,)), ('dec_lstm.lstms.1.bias_hh', (4 * DO,)), ('cls.bias', (V,))]
+    return out
+
+
+def make_rewriter_state_dict(cfg: dict, seed: int, scale: float = 1.0) -> Dict[str, np.ndarray]:
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for k, shp in rewriter_state_dict_shapes(cfg):
+        fan = shp[-1] if len(shp) > 1 else shp[0]
+        bound = scale / np.sqrt(max(fan, 1))
+        if k == 'init_query':
+            sd[k] = rng.uniform(0, 1, size=shp).astype(np.float32)
+        else:
+            sd[k] = rng.uniform(-bound, bound, size=shp).astype(np.float32)
+    sd['cls.weight'] = sd['char_emb.weight']
+    return sd
+
+
+def make_token_inputs(seed: int, B: int, Tx: int, L: int, lx=None):
+    """Rewriter inputs: x tokens (B,Tx) in 1..28 padded with 29 past each length, lx, y tokens (B,L)."""
+    rng = np.random.default_rng(seed)
+    lx = np.asarray(lx if lx is not None else [Tx] * B, dtype=np.int64)
+    x = rng.integers(1, 29, size=(B, Tx)).astype(np.int64)
+    for b in range(B):
+        x[b, lx[b]:] = 29
+    y = rng.integers(1, 29, size=(B, L)).astype(np.int64)
+    return x, lx, y

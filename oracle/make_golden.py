@@ -199,6 +199,46 @@ def optimizer_case(name, seed):
     print(f'{name}: final scale {scaler.get_scale()} steps {[float(st[i]["step"]) for i in st]}')
 
 
+def rewriter_case(name, cfg_name, seed, B, Tx, L, lx, train=True, scale=1.0):
+    """src/lmtrain.py Rewriter (unmodified reference class): one train step (masked CE, backward) or one greedy decode."""
+    import src.lmtrain as ref_lm
+    cfg = gu.get_rewriter_config(cfg_name)
+    sd = gu.make_rewriter_state_dict(cfg, seed, scale)
+    model = ref_lm.Rewriter(**cfg)
+    ref_sd = model.state_dict()
+    assert set(ref_sd.keys()) == set(sd.keys()), set(ref_sd) ^ set(sd)
+    for k, v in ref_sd.items():
+        assert tuple(v.shape) == tuple(sd[k].shape), (k, v.shape, sd[k].shape)
+    assert [k for k, _ in model.named_parameters()] == [k for k, _ in gu.rewriter_state_dict_shapes(cfg)]
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()})
+    x, lx, y = gu.make_token_inputs(seed + 1, B, Tx, L, lx)
+    out = dict(cfg_name=cfg_name, seed=seed, scale=scale, x=x, lx=lx, y=y)
+    if train:
+        model.train()
+        torch.manual_seed(seed)
+        with Recorder() as rec:
+            logits, att = model(torch.from_numpy(x), torch.from_numpy(lx), torch.from_numpy(y), 0.5)
+        loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), torch.from_numpy(y).reshape(-1))
+        loss.backward()
+        out.update(logits=logits.detach().numpy(), att=att.numpy(), loss=loss.item(), n_coins=len(rec.coins))
+        nograd = []
+        for k, p in model.named_parameters():
+            if p.grad is None:
+                nograd.append(k)
+                continue
+            out['grad.' + k] = p.grad.numpy()
+        out['nograd'] = np.asarray(nograd)
+        print(f'{name}: loss={loss.item():.6f} logits={tuple(logits.shape)} att={tuple(att.shape)} coins={len(rec.coins)} nograd={nograd}')
+    else:
+        model.eval()
+        with torch.no_grad():
+            logits, att = model(torch.from_numpy(x), torch.from_numpy(lx))
+        chars = logits.argmax(-1).numpy()
+        out.update(logits=logits.numpy(), att=att.numpy(), chars=chars)
+        print(f'{name}: logits={tuple(logits.shape)} chars[0]={chars[0][:12]}')
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -221,6 +261,9 @@ def main():
     greedy_case(ref_models, 'tiny_greedy', 'tiny', 707, B=4, T=400, lx=[400, 380, 333, 251], scale=2.0)
     # (7) optimizer
     optimizer_case('optimizer_adamw_amsgrad', 808)
+    # (8) Rewriter (src/lmtrain.py): ragged token inputs, 4 heads; train step (tf_rate 0.5: the coin is drawn, never used) + greedy
+    rewriter_case('rewriter_train', 'rw_micro', 909, B=3, Tx=11, L=6, lx=[11, 7, 9], train=True)
+    rewriter_case('rewriter_greedy', 'rw_micro', 910, B=3, Tx=13, L=6, lx=[13, 5, 10], train=False, scale=3.0)
 
 
 if __name__ == '__main__':
