@@ -149,7 +149,8 @@ def attn_step_replay_us(lib, B, T, P, dev, nrep=50):
         with torch.cuda.stream(side):
             _lib.check(fn(C.byref(d), side.cuda_stream), name)
             torch.cuda.synchronize()
-            with torch.cuda.graph(g, stream=side):
+            # thread_local: the NCCL watchdog thread keeps polling events while this thread captures
+            with torch.cuda.graph(g, stream=side, capture_error_mode='thread_local'):
                 for _ in range(nrep):
                     _lib.check(fn(C.byref(d), side.cuda_stream), name)
         torch.cuda.synchronize()
@@ -293,11 +294,13 @@ def main():
             _lib.check(lib.las_prof_collect(kind, C.byref(ms), C.byref(n), C.byref(work)), 'prof_collect')
             prof[name] = dict(ms_per_step=ms.value / args.steps, launches_per_step=n.value / args.steps, work_per_step=work.value / args.steps)
         lib.las_prof_reset()
-        # one extra (untimed) step with the decoder's inner kernels profiled: attention step fwd / bwd, small GEMMs
-        lib.las_prof_enable((1 << 1) | (1 << 4) | (1 << 5))
-        step(x_dev, y_dev)
-        torch.cuda.synchronize()
-        lib.las_prof_enable(0)
+    # one extra (untimed) step with the decoder's inner kernels profiled on rank 0: attention step fwd / bwd, small GEMMs.
+    # EVERY rank runs the step (it contains the gradient all-reduce); only rank 0 records.
+    lib.las_prof_enable(((1 << 1) | (1 << 4) | (1 << 5)) if rank == 0 else 0)
+    step(x_dev, y_dev)
+    torch.cuda.synchronize()
+    lib.las_prof_enable(0)
+    if rank == 0:
         for name in ('gemm_other', 'attn_fwd', 'attn_bwd'):
             ms, n, work = C.c_double(), C.c_longlong(), C.c_double()
             _lib.check(lib.las_prof_collect(PROF_KINDS[name], C.byref(ms), C.byref(n), C.byref(work)), 'prof_collect')
