@@ -55,6 +55,8 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 template <bool BWD, int RU, bool KV16>
 __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
     extern __shared__ __align__(16) float sm[];
+    pdl_wait();
+    pdl_trigger();
     const int T = a.T, P = a.P, heads = a.heads, d = P / heads;
     const int Tp = (T + 3) & ~3;    // keep `part` 16-byte aligned
     float* sc = sm;                 // [Tp]  scores / weights
@@ -264,6 +266,8 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, unsigned r
 template <bool BWD, bool KV16>
 __global__ void __launch_bounds__(NT2, 2) attn_step_split_kernel(LasAttnStep a) {
     extern __shared__ __align__(16) float sm[];
+    pdl_wait();
+    pdl_trigger();
     const int T = a.T, P = a.P, heads = a.heads, d = P / heads;
     const int S = gridDim.x, rank = blockIdx.x;
     const int bh = blockIdx.y, b = bh / heads, h = bh - b * heads;
@@ -485,7 +489,7 @@ size_t smem_bytes(const LasAttnStep* a) { return sizeof(float) * ((size_t)((a->T
 template <bool BWD, int RU, bool KV16>
 int launch_one(const LasAttnStep* a, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_kernel<BWD, RU, KV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_step_kernel<BWD, RU, KV16><<<a->B * a->heads, NT, smem, st>>>(*a);
+    LAS_CUDA(las_launch(attn_step_kernel<BWD, RU, KV16>, dim3(a->B * a->heads), dim3(NT), smem, st, *a));
     return LAS_OK;
 }
 template <bool BWD, bool KV16>
@@ -499,10 +503,12 @@ int launch_split(const LasAttnStep* a, int S, cudaStream_t st) {
     cfg.blockDim = dim3(NT2, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = las_pdl_active() ? 2 : 1;
     LAS_CUDA(cudaLaunchKernelEx(&cfg, attn_step_split_kernel<BWD, KV16>, *a));
     return LAS_OK;
 }

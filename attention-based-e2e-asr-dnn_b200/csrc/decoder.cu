@@ -53,6 +53,8 @@ struct CellFwd {
 };
 
 __global__ void __launch_bounds__(256) cell_fwd_kernel(CellFwd a) {
+    pdl_wait();
+    pdl_trigger();
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= a.B * a.H) return;
     const int b = idx / a.H, u = idx - b * a.H;
@@ -94,6 +96,8 @@ struct CellBwd {
 };
 
 __global__ void __launch_bounds__(256) cell_bwd_kernel(CellBwd a) {
+    pdl_wait();
+    pdl_trigger();
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= a.B * a.H) return;
     const int b = idx / a.H, u = idx - b * a.H;
@@ -123,6 +127,8 @@ __global__ void __launch_bounds__(256) logits_argmax_kernel(const float* __restr
                                                             const float* __restrict__ bias, float* __restrict__ logits,
                                                             long long ld_l, int* __restrict__ chars, int K, int V) {
     extern __shared__ float lsm[];   // [V]
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const float* xr = x + (long long)b * ld_x;
     for (int v = w; v < V; v += 8) {
@@ -601,6 +607,7 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
         for (int t = 1; t < S; ++t) all_gold = all_gold && s->use_gold_host && s->use_gold_host[t];
     const bool per_step_logits = !all_gold;
 
+    LasPdlScope pdl_scope;       // the per-step kernels below overlap their launch / prologue with the predecessor's tail
     for (int t = 0; t < S; ++t) {
         const int r = t % L.hist, rn = (t + 1) % L.hist, rg = t % L.ghist;
         float* S0r = S0 + (size_t)r * B * K0;  float* S0n = S0 + (size_t)rn * B * K0;
@@ -647,7 +654,7 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
             c0.h2 = S1r; c0.ld_h2 = K1;          // input slot of this step's cell-1 row
             if (tc) { c0.h1b = S0nb + P; c0.ld_h1b = K0; c0.h2b = S1rb; c0.ld_h2b = K1; }
             c0.B = B; c0.H = DH;
-            cell_fwd_kernel<<<ceil_div(B * DH, 256), 256, 0, st>>>(c0);
+            LAS_CUDA(las_launch(cell_fwd_kernel, dim3(ceil_div(B * DH, 256)), dim3(256), 0, st, c0));
             LAS_LAUNCH_CHECK();
             // cell 1
             if (tc) RC(las_tc_plan_launch(&pl1, r, G1r, 4 * DO, s->b_ih1, s->b_hh1, st));
@@ -660,7 +667,7 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
             c1.h1 = S1n + DH; c1.ld_h1 = K1; c1.h2 = nullptr;
             if (tc) { c1.h1b = S1nb + DH; c1.ld_h1b = K1; }
             c1.B = B; c1.H = DO;
-            cell_fwd_kernel<<<ceil_div(B * DO, 256), 256, 0, st>>>(c1);
+            LAS_CUDA(las_launch(cell_fwd_kernel, dim3(ceil_div(B * DO, 256)), dim3(256), 0, st, c1));
             LAS_LAUNCH_CHECK();
         }
         // query projection into QC[t+1][:, :P]
@@ -673,8 +680,8 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
         if (s->init_force) { at.fmask = FM + (size_t)t * T; at.ld_fmask = 0; at.w2 = W2 + (size_t)rn * B * heads * T; }
         RC(las_attn_step_fwd_f32(&at, st));
         if (per_step_logits) {
-            logits_argmax_kernel<<<B, 256, V * sizeof(float), st>>>(QCn, 2 * P, s->emb, s->cls_b, s->logits + (size_t)t * V, (long long)S * V,
-                                                                 s->chars + (size_t)t * B, 2 * P, V);
+            LAS_CUDA(las_launch(logits_argmax_kernel, dim3(B), dim3(256), V * sizeof(float), st, (const float*)QCn, (long long)(2 * P), s->emb,
+                                s->cls_b, s->logits + (size_t)t * V, (long long)S * V, s->chars + (size_t)t * B, 2 * P, V));
             LAS_LAUNCH_CHECK();
         }
     }
@@ -779,6 +786,8 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
         RC(las_tc_plan_make(&bq3, G0b, Wcat0b, B, K0, 4 * DH, S, 4 * DH, (long long)B * 4 * DH, K0, 1));
     }
 
+    {
+    LasPdlScope pdl_scope;       // the per-step kernels overlap their launch / prologue with the predecessor's tail
     for (int t = S - 1; t >= 0; --t) {
         const int rn = t + 1;
         float* dQCn = dQC + (size_t)rn * B * 2 * P;
@@ -801,7 +810,7 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
         b1.c = C1 + (size_t)rn * B * DO; b1.ld_c = DO; b1.c_prev = C1 + (size_t)t * B * DO; b1.ld_cp = DO;
         b1.dc = dc1; b1.first = (t == S - 1); b1.B = B; b1.H = DO;
         b1.Gb = tc ? G1b + (size_t)t * B * 4 * DO : nullptr;
-        cell_bwd_kernel<<<ceil_div(B * DO, 256), 256, 0, st>>>(b1);
+        LAS_CUDA(las_launch(cell_bwd_kernel, dim3(ceil_div(B * DO, 256)), dim3(256), 0, st, b1));
         LAS_LAUNCH_CHECK();
         // dS1[t] = dG1_t . Wcat1  -> [dh0_t | dh1_{t-1}]
         if (tc) RC(las_tc_plan_launch(&bq2, t, dS1, K1, nullptr, nullptr, st));
@@ -814,12 +823,13 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
         b0.c = C0 + (size_t)rn * B * DH; b0.ld_c = DH; b0.c_prev = C0 + (size_t)t * B * DH; b0.ld_cp = DH;
         b0.dc = dc0; b0.first = (t == S - 1); b0.B = B; b0.H = DH;
         b0.Gb = tc ? G0b + (size_t)t * B * 4 * DH : nullptr;
-        cell_bwd_kernel<<<ceil_div(B * DH, 256), 256, 0, st>>>(b0);
+        LAS_CUDA(las_launch(cell_bwd_kernel, dim3(ceil_div(B * DH, 256)), dim3(256), 0, st, b0));
         LAS_LAUNCH_CHECK();
         // dS0[t] = dG0_t . Wcat0 -> [dctx_t | dh0_{t-1}]
         if (tc) RC(las_tc_plan_launch(&bq3, t, dS0, K0, nullptr, nullptr, st));
         else RC(gemm(st, b0.G, 4 * DH, Wcat0, K0, 0, dS0, K0, B, K0, 4 * DH));
     }
+    }                            // PDL scope ends: the batched GEMMs below are ordinary launches
     // initial attention (src/models.py:346): its context feeds cell 0 of step 0 only
     at.q = QC; at.w = W; at.ctx = QC + P; at.dctx = dQC + P; at.dctx2 = dS0; at.dq = dQC; at.de = DE;
     at.dq_bf16 = tc ? (void*)dQb : nullptr;

@@ -22,6 +22,12 @@
 
 namespace {
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // BN is a template parameter: 256 for the big gate GEMMs (one tile per SM per wave), 64 for the small decoder GEMMs
 // (M = batch <= 128): four times as many CTAs, a quarter of the MMA + epilogue time per CTA.
 constexpr int BM = 128, BK = 64;
@@ -184,6 +190,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // PDL: everything above (barriers, TMEM, descriptor prefetch) may overlap the previous kernel; nothing below may
+    pdl_wait();
+    pdl_trigger();
 
     const int splitk = g.splitk > 1 ? g.splitk : 1;
     const int total_tiles = g.NB * g.mt_per_b * g.nt * splitk;
@@ -224,24 +233,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BN);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t accphase = 0;
-            for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += gridDim.x) {
-                const int split = tile0 % splitk, tile = tile0 / splitk;
-                const int mrem = tile / g.nt;
-                const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b + g.b_first;
-                if (g.lens && mtile * BM >= g.lens[b]) continue;
-                const int k_lo = (int)((long long)kiters_all * split / splitk), k_hi = (int)((long long)kiters_all * (split + 1) / splitk);
-                mbar_wait(tempty_bar(acc), accphase ^ 1u);
+        // ===== MMA issuer: the whole warp walks the loop (waits included) and ONE elected lane issues -- with `if (lane == 0)`
+        // the branch is divergent, every tcgen05.mma gets wrapped in a divergence loop with R2UR moves (~65 cycles per issue,
+        // more than a 128x64x16 UMMA takes); warp-uniform control flow keeps the descriptors in uniform registers =====
+        constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BN);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t accphase = 0;
+        for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += gridDim.x) {
+            const int split = tile0 % splitk, tile = tile0 / splitk;
+            const int mrem = tile / g.nt;
+            const int mtile = mrem % g.mt_per_b, b = mrem / g.mt_per_b + g.b_first;
+            if (g.lens && mtile * BM >= g.lens[b]) continue;
+            const int k_lo = (int)((long long)kiters_all * split / splitk), k_hi = (int)((long long)kiters_all * (split + 1) / splitk);
+            mbar_wait(tempty_bar(acc), accphase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kit = k_lo; kit < k_hi; ++kit) {
+                mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kit = k_lo; kit < k_hi; ++kit) {
-                    mbar_wait(full_bar(stage), phase);
-                    tc_fence_after();
-                    const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t ad = A_MN ? make_desc(sa + k * 2048, 8192, 1024) : make_desc(sa + k * 32, 16, 1024);
@@ -249,11 +260,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
                         umma_bf16(d_tmem, ad, bd, idesc, ((kit - k_lo) | k) ? 1u : 0u);
                     }
                     umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(tfull_bar(acc));                // accumulator ready for the epilogue
-                if (++acc == 2) { acc = 0; accphase ^= 1u; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
+            if (elect_one()) umma_commit(tfull_bar(acc));   // accumulator ready for the epilogue
+            __syncwarp();
+            if (++acc == 2) { acc = 0; accphase ^= 1u; }
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> smem transpose -> (+bias, +C) -> 128-byte coalesced global stores =====
@@ -450,7 +463,7 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, cud
     const int total = g.NB * g.mt_per_b * g.nt * (g.splitk > 1 ? g.splitk : 1);
     int grid = las_device_info()->num_sms;
     if (grid > total) grid = total;
-    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, g);
+    LAS_CUDA(las_launch(kern, dim3(grid), dim3(NTHREADS), SMEM_BYTES, st, ta, tb, g));
     LAS_LAUNCH_CHECK();
     return LAS_OK;
 }

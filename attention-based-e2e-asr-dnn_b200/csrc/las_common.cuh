@@ -96,6 +96,35 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------------
+// Inside the decoder loops (thousands of tiny dependent kernels) every launch carries the programmatic-stream-serialization
+// attribute: kernel N+1 is scheduled while kernel N still runs and sits in griddepcontrol.wait until N has completed and
+// flushed, so launch latency, CTA scheduling and each kernel's prologue (barrier init, TMEM allocation, descriptor
+// prefetch) overlap the predecessor's tail.  Every participating kernel executes pdl_wait() BEFORE its first global-memory
+// access (reads AND writes: the predecessor may still be reading what we overwrite) and pdl_trigger() right after.
+// Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool las_pdl_active();                 // true inside a LasPdlScope on this thread (and LAS_PDL != 0)
+struct LasPdlScope {
+    LasPdlScope();
+    ~LasPdlScope();
+    bool prev_;
+};
+
+// kernel launch that adds the PDL attribute when a LasPdlScope is active
+template <typename... KArgs, typename... Args>
+inline cudaError_t las_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = las_pdl_active() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- profiling scope (see las_runtime.cu) ----
 enum LasProfKind { LAS_PROF_GEMM_GATES = 0, LAS_PROF_GEMM_OTHER = 1, LAS_PROF_REC_FWD = 2, LAS_PROF_REC_BWD = 3,
                    LAS_PROF_ATTN_FWD = 4, LAS_PROF_ATTN_BWD = 5, LAS_PROF_ADAM = 6, LAS_PROF_SPELLER_FWD = 7,

@@ -1,5 +1,6 @@
 // Runtime plumbing of the C ABI: error string, device info cache, launch counter.
 #include "las_common.cuh"
+#include <stdlib.h>
 #include "las_b200.h"
 #include <atomic>
 #include <mutex>
@@ -146,3 +147,13 @@ extern "C" int las_prof_collect(int kind, double* total_ms, long long* count, do
     if (total_work) *total_work = work;
     return LAS_OK;
 }
+
+
+// ---- programmatic dependent launch scope (las_common.cuh) ----
+namespace { thread_local bool t_pdl = false; }
+bool las_pdl_active() { return t_pdl; }
+LasPdlScope::LasPdlScope() : prev_(t_pdl) {
+    const char* e = getenv("LAS_PDL");
+    t_pdl = !(e && atoi(e) == 0);
+}
+LasPdlScope::~LasPdlScope() { t_pdl = prev_; }
