@@ -229,7 +229,8 @@ def main():
     y_host = torch.from_numpy(y_np).pin_memory()
     lx = torch.from_numpy(lx_np)                 # CPU int64, never moved (src/train.py:127)
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
-    crit = torch.nn.CrossEntropyLoss(reduction='none')
+    from las_b200.loss import masked_ce
+    ly_cpu = torch.full((B,), L, dtype=torch.int64)      # every target position is non-pad in the synthetic batch
     V = cfg['speller_configs']['dec_vocab_size']
     scale = 65536.0                              # GradScaler's initial scale (torch amp/grad_scaler.py)
 
@@ -238,7 +239,7 @@ def main():
         # like src/train.py:130-137: forward + loss under autocast (which selects our tensor-pipe kernels)
         with torch.autocast('cuda', dtype=torch.bfloat16, enabled=(args.precision == 'bf16')):
             logits, _att = model(x, lx, y, 1.0, False)                   # tf_rate 1.0 (README stage 1)
-        loss = crit(logits.float().view(-1, V), y.view(-1)).mean()       # all-ones mask: every target is non-pad
+        loss, _ppl = masked_ce(logits, y, ly_cpu)                         # the trainer's masked CE (src/train.py:117-136), fused
         (loss * scale).backward()
         reducer.finish()
         opt.step_fused(inv_scale=1.0 / (scale * world), max_norm=5.0)

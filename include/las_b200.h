@@ -242,6 +242,16 @@ typedef struct {
 } LasSpellerGrads;
 int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g, void* stream);
 
+/* ---- fused masked cross-entropy of the trainer --------------------------------------------------------------------------
+ * Replaces the caller-side loss of src/train.py:117-136: y_mask = arange(L) < ly ; loss = sum(CE_none * y_mask) /
+ * (n_nonpad * accu_grad) ; ppl = exp(loss) (:139).  logits (B*L, V) contiguous; y (B, >= L) int32 (row stride ld_y): the
+ * targets AFTER the <sos> strip; ly_dev (B) int32 = ly - 1.  inv_denom = 1 / (n_nonpad * accu_grad), computed by the host
+ * from the CPU length tensor (no device sync).  loss_ppl_out (2 floats): [loss, exp(loss)].  dlogits (nullable, (B*L, V)):
+ * d loss / d logits.  Deterministic two-stage sum; scratch >= las_masked_ce_scratch_floats(B, L) floats. */
+size_t las_masked_ce_scratch_floats(int B, int L);
+int las_masked_ce_f32(const float* logits, const int* y, long long ld_y, const int* ly_dev, int B, int L, int V, float inv_denom,
+                      float* loss_ppl_out, float* dlogits, float* scratch, size_t scratch_floats, void* stream);
+
 /* ---- fused unscale + global-norm clip + AdamW(amsgrad) ---------------------------------------------------------------
  * Replaces scaler.unscale_ -> clip_grad_norm_ -> scaler.step(AdamW amsgrad) (src/train.py:165-183; torch
  * optim/adam.py single-tensor math, nn/utils/clip_grad.py).  `table` is a device array of n_tensors LasAdamTensor;

@@ -365,3 +365,27 @@ def test_decoder_graph_replays_in_a_steady_loop_and_slots_do_not_alias():
     la.square().mean().backward()
     assert torch.equal(model.spell.attention.query_map.weight.grad, grads[0])
     del lb
+
+
+@pytest.mark.parametrize('B,L,V,ly,accu', [(3, 7, 30, [7, 5, 6], 1), (5, 33, 30, [33, 1, 17, 30, 8], 4), (2, 4, 70, [4, 2], 1)])
+def test_fused_masked_ce_matches_trainer_loss(B, L, V, ly, accu):
+    """las_b200.loss.masked_ce against the reference trainer's loss (src/train.py:117-136) and the oracle's restatement:
+    loss value, perplexity and d loss / d logits."""
+    from las_b200.loss import masked_ce
+    rng = np.random.default_rng(B * L + V)
+    logits = torch.from_numpy(rng.standard_normal((B, L, V)).astype(np.float32) * 3)
+    y = torch.from_numpy(rng.integers(0, V, size=(B, L)).astype(np.int64))
+    lo = logits.clone().requires_grad_(True)
+    y_mask = (torch.arange(L).unsqueeze(0) < torch.tensor(ly).unsqueeze(1)).flatten().to(torch.int)
+    ref = (torch.nn.CrossEntropyLoss(reduction='none')(lo.view(-1, V), y.view(-1)) * y_mask).sum() / (y_mask.sum() * accu)
+    (ref * 65536.0).backward()
+    if V == 30:
+        assert abs(float(orc.masked_ce_loss(logits, y, ly, accu)) - float(ref)) < 1e-6
+    lc = logits.clone().to(DEV).requires_grad_(True)
+    loss, ppl = masked_ce(lc, y.to(DEV), torch.tensor(ly), accu)
+    (loss * 65536.0).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert abs(float(ppl) - float(torch.exp(ref))) < 1e-4 * float(torch.exp(ref))
+    assert rel_err(lc.grad.cpu().numpy(), lo.grad.numpy()) < TOL
+    l2, _ = masked_ce(lc.detach(), y.to(DEV), torch.tensor(ly), accu)
+    assert float(l2) == float(loss)                      # deterministic
