@@ -167,7 +167,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
     auto tfull_bar = [&](int c) { return bar_base + 8u * (MAX_CHAINS + c); };
     const uint32_t wbar = bar_base + 8u * (2 * MAX_CHAINS);
     const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_CHAINS + 1);
+    auto full2_bar = [&](int c) { return bar_base + 8u * (2 * MAX_CHAINS + 2 + c); };
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    // the h tile arrives as two half-tiles (k-blocks [0, KBH) and [KBH, KB)), each with its own barrier, so the UMMAs of the
+    // first half run while the second half is still in flight
+    const int KBH = (KB >= 2 && KB % 2 == 0) ? KB / 2 : KB;
 
     const int r = blockIdx.x, sg = blockIdx.y, dir = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmH) : "memory");
-        for (int c = 0; c < MAX_CHAINS; ++c) { mbar_init(full_bar(c), 1); mbar_init(tfull_bar(c), 1); }
+        for (int c = 0; c < MAX_CHAINS; ++c) { mbar_init(full_bar(c), 1); mbar_init(tfull_bar(c), 1); mbar_init(full2_bar(c), 1); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -232,11 +236,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     const unsigned target = (unsigned)(H / UNITS) * (unsigned)s;
                     while (ld_acquire_gpu(ctr) < target) { }
                     REC_STAMP(0);
-                    asm volatile("fence.proxy.async;" ::: "memory");       // peers' generic-proxy writes -> our TMA reads
+                    asm volatile("fence.proxy.async.global;" ::: "memory");       // peers' generic-proxy writes -> our TMA reads
                     REC_STAMP(11);
-                    mbar_arrive_expect_tx(full_bar(c), (uint32_t)KB * 4096u);
                     const int row0 = (dir * 2 + ((s - 1) & 1)) * a.Bpad + slice * NB_SLICE;
-                    tma_load_3d(h_sm + c * KB * 4096, &tmH, full_bar(c), 0, row0, 0);   // box (64, 32 rows, KB k-blocks): one issue
+                    mbar_arrive_expect_tx(full_bar(c), (uint32_t)KBH * 4096u);
+                    tma_load_3d(h_sm + c * KB * 4096, &tmH, full_bar(c), 0, row0, 0);   // box (64, 32 rows, KBH k-blocks)
+                    if (KBH < KB) {
+                        mbar_arrive_expect_tx(full2_bar(c), (uint32_t)(KB - KBH) * 4096u);
+                        tma_load_3d(h_sm + (c * KB + KBH) * 4096, &tmH, full2_bar(c), 0, row0, KBH);
+                    }
                     REC_STAMP(1);
                 }
             }
@@ -248,26 +256,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
             for (int c = 0; c < a.chains; ++c) {
                 const int slice = sg + c * a.bsg;
                 if (slice >= a.nslices) continue;
-                mbar_wait(full_bar(c), (uint32_t)((s - 1) & 1));
-                if (lane == 0) REC_STAMP(2);
-                tc_fence_after();
-                if (elect_one()) {
-                    // consecutive UMMAs into ONE accumulator serialise on it: round-robin over FWD_NACC independent
-                    // accumulators, summed by the epilogue
-                    for (int kb = 0; kb < KB; ++kb) {
+                for (int half = 0; half < (KBH < KB ? 2 : 1); ++half) {
+                    mbar_wait(half ? full2_bar(c) : full_bar(c), (uint32_t)((s - 1) & 1));
+                    if (lane == 0 && half == 0) REC_STAMP(2);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        // consecutive UMMAs into ONE accumulator serialise on it: round-robin over FWD_NACC independent
+                        // accumulators, summed by the epilogue
+                        const int kb_lo = half ? KBH : 0, kb_hi = half ? KB : KBH;
+                        for (int kb = kb_lo; kb < kb_hi; ++kb) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((c * FWD_NACC + k) * NB_SLICE);
-                            const uint64_t bd = make_desc_k(h_sm + (c * KB + kb) * 4096 + k * 32);
-                            if (WTMEM) {
-                                umma_bf16_ts(d_tmem, tmem_w + kb * 32 + k * 8, bd, IDESC, kb ? 1u : 0u);
-                            } else {
-                                const uint64_t ad = make_desc_k(w_sm + kb * 16384 + k * 32);
-                                umma_bf16(d_tmem, ad, bd, IDESC, kb ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t d_tmem = tmem_base + (uint32_t)((c * FWD_NACC + k) * NB_SLICE);
+                                const uint64_t bd = make_desc_k(h_sm + (c * KB + kb) * 4096 + k * 32);
+                                if (WTMEM) {
+                                    umma_bf16_ts(d_tmem, tmem_w + kb * 32 + k * 8, bd, IDESC, kb ? 1u : 0u);
+                                } else {
+                                    const uint64_t ad = make_desc_k(w_sm + kb * 16384 + k * 32);
+                                    umma_bf16(d_tmem, ad, bd, IDESC, kb ? 1u : 0u);
+                                }
                             }
                         }
+                        if (kb_hi == KB) umma_commit(tfull_bar(c));
                     }
-                    umma_commit(tfull_bar(c));
+                    __syncwarp();
                 }
                 __syncwarp();
                 if (lane == 0) REC_STAMP(3);
@@ -875,9 +887,10 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
     rc = make_map_2d(&tmW, w_hh_bf16, H, (long long)ndir * 4 * H, 64, 32);
     if (rc) return rc;
     {   // h exchange buffer viewed as (64 k, rows, H/64 k-blocks): one box = the whole 32 x H slice in k-block-major smem order
-        const long long dims[3] = {64, (long long)ndir * 2 * p.Bpad, H / 64};
+        const int KBt = H / 64, KBHt = (KBt >= 2 && KBt % 2 == 0) ? KBt / 2 : KBt;
+        const long long dims[3] = {64, (long long)ndir * 2 * p.Bpad, KBt};
         const long long strides[2] = {H, 64};
-        const int box[3] = {64, NB_SLICE, H / 64};
+        const int box[3] = {64, NB_SLICE, KBHt};      // half a tile per TMA issue (see the kernel)
         rc = make_map_nd(&tmH, a.hbuf, 3, dims, strides, box);
         if (rc) return rc;
     }
@@ -1239,6 +1252,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
     auto tfull_bar = [&](int c) { return bar_base + 8u * (MAX_CHAINS + c); };
     const uint32_t wbar = bar_base + 8u * (2 * MAX_CHAINS);
     const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_CHAINS + 1);
+    auto full2_bar = [&](int c) { return bar_base + 8u * (2 * MAX_CHAINS + 2 + c); };
+    const int KBH = (KB >= 2 && KB % 2 == 0) ? KB / 2 : KB;       // the dG tile arrives as two half-tiles (see the forward kernel)
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int kq = (int)cluster_ctarank();            // gate handled by this CTA's reduction slice
@@ -1252,7 +1267,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWt) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
-        for (int c = 0; c < MAX_CHAINS; ++c) { mbar_init(full_bar(c), 1); mbar_init(tfull_bar(c), 1); }
+        for (int c = 0; c < MAX_CHAINS; ++c) { mbar_init(full_bar(c), 1); mbar_init(tfull_bar(c), 1); mbar_init(full2_bar(c), 1); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1333,10 +1348,15 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                     const unsigned target = group * (unsigned)s;
                     while (ld_acquire_gpu(ctr) < target) { }
                     REC_STAMP(0);
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    mbar_arrive_expect_tx(full_bar(c), (uint32_t)KB * 4096u);
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
                     // compact exchange buffer (dir, parity, gate, Bpad, H): the 32 x H tile of gate kq is 32 contiguous rows
-                    tma_load_3d(b_sm + c * KB * 4096, &tmG, full_bar(c), 0, ((dir * 2 + ((s - 1) & 1)) * 4 + kq) * a.Bpad + b0, 0);
+                    const int row0 = ((dir * 2 + ((s - 1) & 1)) * 4 + kq) * a.Bpad + b0;
+                    mbar_arrive_expect_tx(full_bar(c), (uint32_t)KBH * 4096u);
+                    tma_load_3d(b_sm + c * KB * 4096, &tmG, full_bar(c), 0, row0, 0);
+                    if (KBH < KB) {
+                        mbar_arrive_expect_tx(full2_bar(c), (uint32_t)(KB - KBH) * 4096u);
+                        tma_load_3d(b_sm + (c * KB + KBH) * 4096, &tmG, full2_bar(c), 0, row0, KBH);
+                    }
                     REC_STAMP(1);
                 }
                 __syncwarp();
@@ -1344,24 +1364,28 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                 if (s > 0) {
                     // whole warp waits, one elected lane issues (uniform control flow keeps the descriptors in uniform registers);
                     // BWD_NACC independent accumulators (one per k sub-step) break the accumulate-dependency chain
-                    mbar_wait(full_bar(c), (uint32_t)((s - 1) & 1));
-                    if (lane == 0) REC_STAMP(2);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        for (int kb = 0; kb < KB; ++kb) {
+                    for (int half = 0; half < (KBH < KB ? 2 : 1); ++half) {
+                        mbar_wait(half ? full2_bar(c) : full_bar(c), (uint32_t)((s - 1) & 1));
+                        if (lane == 0 && half == 0) REC_STAMP(2);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const int kb_lo = half ? KBH : 0, kb_hi = half ? KB : KBH;
+                            for (int kb = kb_lo; kb < kb_hi; ++kb) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t d_tmem = tmem_base + (uint32_t)((c * BWD_NACC + k) * NB_SLICE);
-                                const uint64_t bd = make_desc_k(b_sm + (c * KB + kb) * 4096 + k * 32);
-                                if (WTMEM) {
-                                    umma_bf16_ts(d_tmem, tmem_w + kb * 32 + k * 8, bd, IDESC, kb ? 1u : 0u);
-                                } else {
-                                    const uint64_t ad = make_desc_k(a_sm + kb * 16384 + k * 32);
-                                    umma_bf16(d_tmem, ad, bd, IDESC, kb ? 1u : 0u);
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint32_t d_tmem = tmem_base + (uint32_t)((c * BWD_NACC + k) * NB_SLICE);
+                                    const uint64_t bd = make_desc_k(b_sm + (c * KB + kb) * 4096 + k * 32);
+                                    if (WTMEM) {
+                                        umma_bf16_ts(d_tmem, tmem_w + kb * 32 + k * 8, bd, IDESC, kb ? 1u : 0u);
+                                    } else {
+                                        const uint64_t ad = make_desc_k(a_sm + kb * 16384 + k * 32);
+                                        umma_bf16(d_tmem, ad, bd, IDESC, kb ? 1u : 0u);
+                                    }
                                 }
                             }
+                            if (kb_hi == KB) umma_commit(tfull_bar(c));
                         }
-                        umma_commit(tfull_bar(c));
+                        __syncwarp();
                     }
                     __syncwarp();
                     if (lane == 0) REC_STAMP(3);
@@ -1507,9 +1531,10 @@ static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, co
     a.Bpad = nslices * NB_SLICE;
     a.dgx = (__nv_bfloat16*)((char*)ws + 1024);
     {   // exchange buffer (ndir*2*4*Bpad rows, H) viewed as (64, rows, H/64): one box = a 32 x H tile in k-block-major smem order
+        const int KBHt = (KB >= 2 && KB % 2 == 0) ? KB / 2 : KB;
         const long long dims[3] = {64, (long long)ndir * 2 * 4 * a.Bpad, KB};
         const long long strides[2] = {H, 64};
-        const int box[3] = {64, NB_SLICE, KB};
+        const int box[3] = {64, NB_SLICE, KBHt};      // half a tile per TMA issue
         rc = make_map_nd(&tmG, a.dgx, 3, dims, strides, box);
         if (rc) return rc;
     }
