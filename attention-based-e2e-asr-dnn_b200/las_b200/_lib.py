@@ -140,6 +140,8 @@ SIGNATURES = {
     'las_speller_workspace_floats': (C.c_size_t, [C.POINTER(LasSpeller)]),
     'las_speller_workspace_ints': (C.c_size_t, [C.POINTER(LasSpeller)]),
     'las_speller_fwd_f32': (C.c_int, [C.POINTER(LasSpeller), C.c_void_p]),
+    'las_collate_specaug_f32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     'las_masked_ce_scratch_floats': (C.c_size_t, [C.c_int, C.c_int]),
     'las_masked_ce_f32': (C.c_int, [C.c_void_p, C.c_void_p, c_ll, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_size_t, C.c_void_p]),

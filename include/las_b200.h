@@ -242,6 +242,15 @@ typedef struct {
 } LasSpellerGrads;
 int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g, void* stream);
 
+/* ---- device-side collate + SpecAugment ---------------------------------------------------------------------------------
+ * Replaces pad_sequence + FrequencyMasking / TimeMasking of datasetTrainDev.collate_fn (src/utils.py:95-128, maskers :82-84)
+ * and the trainer's H2D copy of the padded batch (src/train.py:127).  frames: the length-sorted utterances back to back,
+ * (sum(lens), F); offsets (B): first frame of each utterance; out (B, T, F) = frames padded with pad_value, then positions
+ * with f in [f_lo, f_hi) or t in [t_lo, t_hi) set to mask_value (empty interval = no mask).  The mask intervals are drawn
+ * by the host exactly like torchaudio.functional.mask_along_axis (one interval per axis for the whole batch). */
+int las_collate_specaug_f32(const float* frames, const long long* offsets, const int* lens, int B, int T, int F, float pad_value,
+                            int f_lo, int f_hi, int t_lo, int t_hi, float mask_value, float* out, void* stream);
+
 /* ---- fused masked cross-entropy of the trainer --------------------------------------------------------------------------
  * Replaces the caller-side loss of src/train.py:117-136: y_mask = arange(L) < ly ; loss = sum(CE_none * y_mask) /
  * (n_nonpad * accu_grad) ; ppl = exp(loss) (:139).  logits (B*L, V) contiguous; y (B, >= L) int32 (row stride ld_y): the

@@ -239,6 +239,28 @@ def rewriter_case(name, cfg_name, seed, B, Tx, L, lx, train=True, scale=1.0):
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
 
 
+def collate_case(name, seed, lens, F=15, specaug=True):
+    """datasetTrainDev.collate_fn of the unmodified reference (src/utils.py:95-128) on a ragged synthetic batch.  The class
+    constructor reads .npy directories, so the instance is built without it and given exactly the attributes collate_fn uses."""
+    import src.utils as ref_utils
+    import torchaudio.transforms as tat
+    ds = object.__new__(ref_utils.datasetTrainDev)
+    ds.useSpecAug = specaug
+    ds.freq_masker = tat.FrequencyMasking(6)            # src/utils.py:83-84
+    ds.time_masker = tat.TimeMasking(200)
+    rng = np.random.default_rng(seed)
+    mf = [rng.standard_normal((n, F)).astype(np.float32) for n in lens]
+    tr = [rng.integers(1, 29, size=int(rng.integers(3, 12))).astype(np.int64) for _ in lens]
+    torch.manual_seed(seed)
+    x, y, lx, ly = ds.collate_fn([(torch.from_numpy(a), torch.from_numpy(b)) for a, b in zip(mf, tr)])
+    out = dict(seed=seed, specaug=specaug, n=len(lens), x=x.numpy(), y=y.numpy(), lx=lx.numpy(), ly=ly.numpy())
+    for i, (a, b) in enumerate(zip(mf, tr)):
+        out[f'mfcc_{i}'] = a
+        out[f'trans_{i}'] = b
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(f'{name}: x={tuple(x.shape)} y={tuple(y.shape)} lx={lx.tolist()} masked_frac={(x == 0).float().mean():.3f}')
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -264,6 +286,10 @@ def main():
     # (8) Rewriter (src/lmtrain.py): ragged token inputs, 4 heads; train step (tf_rate 0.5: the coin is drawn, never used) + greedy
     rewriter_case('rewriter_train', 'rw_micro', 909, B=3, Tx=11, L=6, lx=[11, 7, 9], train=True)
     rewriter_case('rewriter_greedy', 'rw_micro', 910, B=3, Tx=13, L=6, lx=[13, 5, 10], train=False, scale=3.0)
+    # (9) loader collate + SpecAugment (src/utils.py:95-128): unsorted ragged lengths incl. ties, T < 200 and T > 200
+    collate_case('collate_specaug_short', 1001, lens=[50, 37, 64, 12, 64])
+    collate_case('collate_specaug_long', 1002, lens=[310, 250, 333])
+    collate_case('collate_plain', 1003, lens=[9, 30, 21], specaug=False)
 
 
 if __name__ == '__main__':
