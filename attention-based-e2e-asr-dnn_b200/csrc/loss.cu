@@ -10,7 +10,7 @@ namespace {
 
 constexpr int ROWS_PER_BLOCK = 8;     // one warp per (b, t) row
 
-__global__ void __launch_bounds__(256) masked_ce_kernel(const float* __restrict__ logits, const int* __restrict__ y, long long ld_y,
+__global__ void __launch_bounds__(256) masked_ce_kernel(const float* __restrict__ logits, long long ld_b, const int* __restrict__ y, long long ld_y,
                                                         const int* __restrict__ ly, int B, int L, int V, float inv_denom,
                                                         float* __restrict__ dlogits, float* __restrict__ partial) {
     __shared__ float red[ROWS_PER_BLOCK];
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) masked_ce_kernel(const float* __restrict_
     if (row < (long long)B * L) {
         const int b = (int)(row / L), t = (int)(row - (long long)b * L);
         const bool on = t < ly[b];
-        const float* lr = logits + row * V;
+        const float* lr = logits + (long long)b * ld_b + (long long)t * V;      // ld_b > L*V: logits of a longer decode, truncated to L steps
         const int tgt = y[(long long)b * ld_y + t];
         float mx = -FLT_MAX;
         for (int v = lane; v < V; v += 32) mx = fmaxf(mx, lr[v]);
@@ -66,15 +66,15 @@ __global__ void __launch_bounds__(256) masked_ce_final_kernel(const float* __res
 
 extern "C" size_t las_masked_ce_scratch_floats(int B, int L) { return (size_t)ceil_div64((long long)B * L, ROWS_PER_BLOCK) + 4; }
 
-extern "C" int las_masked_ce_f32(const float* logits, const int* y, long long ld_y, const int* ly_dev, int B, int L, int V, float inv_denom,
+extern "C" int las_masked_ce_f32(const float* logits, long long ld_b, const int* y, long long ld_y, const int* ly_dev, int B, int L, int V, float inv_denom,
                                  float* loss_ppl_out, float* dlogits, float* scratch, size_t scratch_floats, void* stream) {
-    LAS_CHECK_ARG(logits && y && ly_dev && loss_ppl_out && scratch && B >= 1 && L >= 1 && V >= 2, "masked_ce: bad arguments");
+    LAS_CHECK_ARG(logits && y && ly_dev && loss_ppl_out && scratch && B >= 1 && L >= 1 && V >= 2 && ld_b >= (long long)L * V, "masked_ce: bad arguments");
     LAS_CHECK_ARG(scratch_floats >= las_masked_ce_scratch_floats(B, L), "masked_ce: scratch too small");
     int rc = las_set_device_of(logits);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int nblk = (int)ceil_div64((long long)B * L, ROWS_PER_BLOCK);
-    masked_ce_kernel<<<nblk, 256, 0, st>>>(logits, y, ld_y, ly_dev, B, L, V, inv_denom, dlogits, scratch);
+    masked_ce_kernel<<<nblk, 256, 0, st>>>(logits, ld_b, y, ld_y, ly_dev, B, L, V, inv_denom, dlogits, scratch);
     LAS_LAUNCH_CHECK();
     masked_ce_final_kernel<<<1, 256, 0, st>>>(scratch, nblk, inv_denom, loss_ppl_out);
     LAS_LAUNCH_CHECK();

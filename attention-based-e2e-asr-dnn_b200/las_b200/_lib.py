@@ -143,7 +143,7 @@ SIGNATURES = {
     'las_collate_specaug_f32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     'las_masked_ce_scratch_floats': (C.c_size_t, [C.c_int, C.c_int]),
-    'las_masked_ce_f32': (C.c_int, [C.c_void_p, C.c_void_p, c_ll, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+    'las_masked_ce_f32': (C.c_int, [C.c_void_p, c_ll, C.c_void_p, c_ll, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     'las_speller_graph_stats': (None, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     'las_speller_bwd_f32': (C.c_int, [C.POINTER(LasSpeller), C.POINTER(LasSpellerGrads), C.c_void_p]),

@@ -253,12 +253,14 @@ int las_collate_specaug_f32(const float* frames, const long long* offsets, const
 
 /* ---- fused masked cross-entropy of the trainer --------------------------------------------------------------------------
  * Replaces the caller-side loss of src/train.py:117-136: y_mask = arange(L) < ly ; loss = sum(CE_none * y_mask) /
- * (n_nonpad * accu_grad) ; ppl = exp(loss) (:139).  logits (B*L, V) contiguous; y (B, >= L) int32 (row stride ld_y): the
+ * (n_nonpad * accu_grad) ; ppl = exp(loss) (:139), and the dev-eval variant that truncates a longer decode to the target
+ * length (pred_logits[:, :L], :226-232).  logits: row (b, t) at logits + b*ld_b + t*V (ld_b = L*V for a contiguous (B, L, V)
+ * tensor, steps*V for a truncated longer decode); y (B, >= L) int32 (row stride ld_y): the
  * targets AFTER the <sos> strip; ly_dev (B) int32 = ly - 1.  inv_denom = 1 / (n_nonpad * accu_grad), computed by the host
  * from the CPU length tensor (no device sync).  loss_ppl_out (2 floats): [loss, exp(loss)].  dlogits (nullable, (B*L, V)):
  * d loss / d logits.  Deterministic two-stage sum; scratch >= las_masked_ce_scratch_floats(B, L) floats. */
 size_t las_masked_ce_scratch_floats(int B, int L);
-int las_masked_ce_f32(const float* logits, const int* y, long long ld_y, const int* ly_dev, int B, int L, int V, float inv_denom,
+int las_masked_ce_f32(const float* logits, long long ld_b, const int* y, long long ld_y, const int* ly_dev, int B, int L, int V, float inv_denom,
                       float* loss_ppl_out, float* dlogits, float* scratch, size_t scratch_floats, void* stream);
 
 /* ---- fused unscale + global-norm clip + AdamW(amsgrad) ---------------------------------------------------------------

@@ -389,3 +389,7 @@ def test_fused_masked_ce_matches_trainer_loss(B, L, V, ly, accu):
     assert rel_err(lc.grad.cpu().numpy(), lo.grad.numpy()) < TOL
     l2, _ = masked_ce(lc.detach(), y.to(DEV), torch.tensor(ly), accu)
     assert float(l2) == float(loss)                      # deterministic
+    # dev-eval form (src/train.py:226-232): a longer decode truncated to the target length
+    longer = torch.cat([logits, torch.from_numpy(rng.standard_normal((B, 5, V)).astype(np.float32))], dim=1).to(DEV)
+    l3, _ = masked_ce(longer, y.to(DEV), torch.tensor(ly), accu)
+    assert float(l3) == float(loss)
