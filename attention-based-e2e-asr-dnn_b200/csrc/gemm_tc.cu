@@ -16,6 +16,7 @@
 //   MN-major operand tile 64k x mn   : mn/64 TMA boxes {64, 64, 1} of 8 KB; UMMA desc LBO = 8 KB, SBO = 1024 B,
 //                                      K-advance = 2048 B
 #include "las_common.cuh"
+#include <stdlib.h>
 #include "las_b200.h"
 #include <cuda.h>
 #include <new>
@@ -475,6 +476,7 @@ struct LasTcPlan {
     CUtensorMap ta, tb;
     TcArgs g;
     int variant;     // 0: A,B K-major (C = A.B^T) ; 1: B MN-major (C = A.B)
+    int bn;          // N tile: 64, or 32 for the K-major form (twice the CTAs, each ingesting a smaller weight slice)
 };
 size_t las_tc_plan_bytes() { return sizeof(LasTcPlan); }
 
@@ -484,13 +486,20 @@ int las_tc_plan_make(void* plan_mem, const void* A, const void* B, int M, int N,
     LasTcPlan* p = new (plan_mem) LasTcPlan();
     int rc = make_map(&p->ta, A, K, M, a_batches, a_s1, a_s2, BK, BM);
     if (rc) return rc;
-    if (!b_mn_major) rc = make_map(&p->tb, B, K, N, 1, b_s1, 0, BK, 64);
+    // these GEMMs have one M tile (M = batch <= 128): every CTA pulls the whole activation matrix plus its own weight slice.
+    // N tiles of 32 (LAS_DEC_BN=32) put twice as many SMs to work on half the weight slice each; measured no faster than 64
+    // (decoder forward loop 10.47 vs 10.30 ms: the shared activation tile dominates what each SM ingests), so 64 is the default.
+    const char* e = getenv("LAS_DEC_BN");
+    const char* fe = getenv("LAS_DEC_FUSE");          // the opt-in fused LSTM epilogue is written for 64-column tiles
+    const int want = (fe && atoi(fe) == 1) ? 64 : (e ? atoi(e) : 64);
+    p->bn = (!b_mn_major && want == 32 && N % 32 == 0 && ceil_div(N, 32) <= las_device_info()->num_sms) ? 32 : 64;
+    if (!b_mn_major) rc = make_map(&p->tb, B, K, N, 1, b_s1, 0, BK, p->bn);
     else rc = make_map(&p->tb, B, N, K, 1, b_s1, 0, 64, 64);
     if (rc) return rc;
     p->variant = b_mn_major ? 1 : 0;
     TcArgs& g = p->g;
     g = TcArgs{};
-    g.R = M; g.NB = 1; g.N = N; g.mt_per_b = ceil_div(M, BM); g.nt = ceil_div(N, 64); g.kt_per_b = ceil_div(K, BK); g.KB = 1;
+    g.R = M; g.NB = 1; g.N = N; g.mt_per_b = ceil_div(M, BM); g.nt = ceil_div(N, p->bn); g.kt_per_b = ceil_div(K, BK); g.KB = 1;
     return LAS_OK;
 }
 
@@ -502,14 +511,17 @@ int las_tc_plan_launch(const void* plan_mem, int a_batch, float* C, long long ld
     LasProfScope prof(LAS_PROF_GEMM_OTHER, stream, 2.0 * g.R * (double)g.N * g.kt_per_b * BK);
     // the c_bs * b term must vanish for the selected batch: C is already the step's output
     g.c_bs = 0;
-    if (p->variant == 0) return launch_tc<false, false, 64>(p->ta, p->tb, g, (cudaStream_t)stream);
+    if (p->variant == 0) {
+        if (p->bn == 32) return launch_tc<false, false, 32>(p->ta, p->tb, g, (cudaStream_t)stream);
+        return launch_tc<false, false, 64>(p->ta, p->tb, g, (cudaStream_t)stream);
+    }
     return launch_tc<false, true, 64>(p->ta, p->tb, g, (cudaStream_t)stream);
 }
 
 // plan launch with the fused LSTM-cell epilogue (plan must be the K-major-B form with permuted weight rows, N = 4H)
 int las_tc_plan_launch_lstm(const void* plan_mem, int a_batch, const LasLstmEpi* le, void* stream) {
     const LasTcPlan* p = (const LasTcPlan*)plan_mem;
-    LAS_CHECK_ARG(p->variant == 0 && le && le->H % 16 == 0 && p->g.N == 4 * le->H, "tc plan (lstm epilogue): bad plan / H");
+    LAS_CHECK_ARG(p->variant == 0 && p->bn == 64 && le && le->H % 16 == 0 && p->g.N == 4 * le->H, "tc plan (lstm epilogue): bad plan / H");
     TcArgs g = p->g;
     g.C = nullptr; g.b_first = a_batch; g.le = *le;
     LasProfScope prof(LAS_PROF_GEMM_OTHER, stream, 2.0 * g.R * (double)g.N * g.kt_per_b * BK);
