@@ -927,6 +927,8 @@ struct RecTcBwdArgs {
     int B, T, H, ndir, nslices, chains, bsg, KBr, CH, Bpad;
     __nv_bfloat16* dgx;      // K-split variant: compact bf16 exchange buffer (ndir, 2, 4 gates, Bpad, H)
     const __nv_bfloat16* w_t; // W_hh^T bf16 (ndir, H, 4H): source of the TMEM-resident A operand
+    float* dbp;               // optional (ndir, nslices, 4H): per-batch-slice bias-gradient partial sums; when given the fp32
+                              // d(pre-activation) write-back into `gates` is skipped (its only reader was the bias column sum)
     long long* dbg;
 };
 
@@ -1152,11 +1154,42 @@ extern "C" int las_transpose_cast_bf16(const float* src, void* dst, int batch, i
 }
 
 static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16, const int* lens,
-                          const float* drop_mask, int B, int T, int H, int ndir, void* ws, cudaStream_t st, void* stream);
+                          const float* drop_mask, int B, int T, int H, int ndir, void* ws, cudaStream_t st, void* stream, float* dbp);
+
+static int rec_bwd_tc_impl(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16,
+                           const int* lens, const float* drop_mask, int B, int T, int H, int ndir, void* ws, size_t ws_bytes,
+                           void* stream, float* dbp);
 
 extern "C" int las_lstm_rec_bwd_tc(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16,
                                    const int* lens, const float* drop_mask, int B, int T, int H, int ndir, void* ws, size_t ws_bytes,
                                    void* stream) {
+    return rec_bwd_tc_impl(dout, gates, dgates_bf16, cs_pad, w_hh_t_bf16, lens, drop_mask, B, T, H, ndir, ws, ws_bytes, stream, nullptr);
+}
+
+extern "C" int las_lstm_rec_bwd_tc_dbias_slices(int B, int H, int ndir) {
+    // > 0: the K-split BPTT kernel runs for this shape and can emit per-batch-slice bias-gradient rows; 0: not available
+    if (H % 128 != 0 || B < 1 || (ndir != 1 && ndir != 2)) return 0;
+    const char* e = getenv("LAS_REC_BWD_KSPLIT");
+    if (e && atoi(e) == 0) return 0;
+    const int rs = 4 * (H / 128), nslices = ceil_div(B, NB_SLICE);
+    const int max_bsg = las_device_info()->num_sms / (rs * ndir);
+    if (max_bsg < 1) return 0;
+    const int bsg = nslices < max_bsg ? nslices : max_bsg;
+    if (ceil_div(nslices, bsg) > MAX_CHAINS) return 0;
+    return nslices;
+}
+
+extern "C" int las_lstm_rec_bwd_tc_db(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16,
+                                      const int* lens, const float* drop_mask, int B, int T, int H, int ndir, void* ws, size_t ws_bytes,
+                                      float* dbias_partial, void* stream) {
+    LAS_CHECK_ARG(dbias_partial != nullptr, "lstm_rec_bwd_tc_db: null dbias_partial");
+    LAS_CHECK_ARG(las_lstm_rec_bwd_tc_dbias_slices(B, H, ndir) > 0, "lstm_rec_bwd_tc_db: not available for B=%d H=%d (use las_lstm_rec_bwd_tc)", B, H);
+    return rec_bwd_tc_impl(dout, gates, dgates_bf16, cs_pad, w_hh_t_bf16, lens, drop_mask, B, T, H, ndir, ws, ws_bytes, stream, dbias_partial);
+}
+
+static int rec_bwd_tc_impl(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16,
+                           const int* lens, const float* drop_mask, int B, int T, int H, int ndir, void* ws, size_t ws_bytes,
+                           void* stream, float* dbp) {
     LAS_CHECK_ARG(dout && gates && dgates_bf16 && cs_pad && w_hh_t_bf16 && lens && ws, "lstm_rec_bwd_tc: null pointer");
     LAS_CHECK_ARG(B >= 1 && T >= 1 && (ndir == 1 || ndir == 2), "lstm_rec_bwd_tc: bad dims");
     int rc = las_set_device_of(gates);
@@ -1169,8 +1202,9 @@ extern "C" int las_lstm_rec_bwd_tc(const float* dout, float* gates, void* dgates
     {
         const char* e = getenv("LAS_REC_BWD_KSPLIT");
         if (!e || atoi(e) != 0) {
-            rc = launch_bwd_tc2(dout, gates, dgates_bf16, cs_pad, w_hh_t_bf16, lens, drop_mask, B, T, H, ndir, ws, st, stream);
+            rc = launch_bwd_tc2(dout, gates, dgates_bf16, cs_pad, w_hh_t_bf16, lens, drop_mask, B, T, H, ndir, ws, st, stream, dbp);
             if (rc == LAS_OK) return LAS_OK;          // otherwise fall through to the streaming variant
+            if (dbp) return rc;                       // (the streaming variant has no bias-gradient output)
         }
     }
     RecTcBwdArgs a{};
@@ -1308,7 +1342,13 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
     const int te = (warp - 4) * 32 + lane;
     const int u = ub * 128 + kq * 32 + j;              // the unit this thread finalises (epilogue warps)
     float dcst[MAX_CHAINS][8];
+    float dbacc[MAX_CHAINS][4];                        // bias-gradient partial sums of this thread's unit over its 8 rows, all steps
     int lenr[MAX_CHAINS][8];
+#pragma unroll
+    for (int c = 0; c < MAX_CHAINS; ++c) {
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) dbacc[c][gq] = 0.f;
+    }
 #pragma unroll
     for (int c = 0; c < MAX_CHAINS; ++c)
 #pragma unroll
@@ -1471,6 +1511,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                     xp[0] = __float2bfloat16(dai); xp[gst] = __float2bfloat16(daf);
                     xp[2 * gst] = __float2bfloat16(dag); xp[3 * gst] = __float2bfloat16(dao);
                     gi[i] = dai; gf[i] = daf; gg[i] = dag; go[i] = dao;
+                    dbacc[c][0] += dai; dbacc[c][1] += daf; dbacc[c][2] += dag; dbacc[c][3] += dao;
                 }
                 named_bar_sync(1, 128);
                 if (te == 0) REC_STAMP(8);
@@ -1480,14 +1521,41 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                 for (int i = 0; i < 8; ++i) {
                     const int b = b0 + q * 8 + i;
                     if (b >= a.B) continue;
-                    float* gp = a.gates + ((((long long)b * T + t) * a.ndir + dir) * G4) + u;
-                    gp[0] = gi[i]; gp[H] = gf[i]; gp[2 * H] = gg[i]; gp[3 * H] = go[i];
+                    if (!a.dbp) {
+                        float* gp = a.gates + ((((long long)b * T + t) * a.ndir + dir) * G4) + u;
+                        gp[0] = gi[i]; gp[H] = gf[i]; gp[2 * H] = gg[i]; gp[3 * H] = go[i];
+                    }
                     // the (B*T, NG) bf16 copy the dX / dW GEMMs consume
                     __nv_bfloat16* bp = a.dgb + ((long long)b * T + t) * NG + dir * G4 + u;
                     bp[0] = __float2bfloat16(gi[i]); bp[H] = __float2bfloat16(gf[i]);
                     bp[2 * H] = __float2bfloat16(gg[i]); bp[3 * H] = __float2bfloat16(go[i]);
                 }
                 if (te == 0) REC_STAMP(10);
+            }
+        }
+    }
+    if (a.dbp) {
+        // bias gradients: the four epilogue warps hold partial sums of the same 32 units over different batch rows; add them up in
+        // a fixed order and store this (direction, batch slice)'s row -- the host sums the few slice rows (deterministic)
+        __syncthreads();
+        float* red = part0;                                           // [chain][q][gate][32] floats, the partial tiles are idle now
+        if (warp >= 4) {
+#pragma unroll
+            for (int c = 0; c < MAX_CHAINS; ++c)
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) red[((c * 4 + q) * 4 + gq) * 32 + j] = dbacc[c][gq];
+        }
+        __syncthreads();
+        if (warp == 4) {
+            for (int c = 0; c < a.chains; ++c) {
+                const int slice = sg + c * a.bsg;
+                if (slice >= a.nslices) continue;
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    const float v = (red[((c * 4 + 0) * 4 + gq) * 32 + j] + red[((c * 4 + 1) * 4 + gq) * 32 + j]) +
+                                    (red[((c * 4 + 2) * 4 + gq) * 32 + j] + red[((c * 4 + 3) * 4 + gq) * 32 + j]);
+                    a.dbp[((long long)(dir * a.nslices + slice) * 4 + gq) * H + u] = v;
+                }
             }
         }
     }
@@ -1504,7 +1572,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
 
 // returns LAS_OK, or a negative code when this variant cannot run (caller falls back to las_lstm_rec_bwd_tc's streaming variant)
 static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16, const int* lens,
-                          const float* drop_mask, int B, int T, int H, int ndir, void* ws, cudaStream_t st, void* stream) {
+                          const float* drop_mask, int B, int T, int H, int ndir, void* ws, cudaStream_t st, void* stream, float* dbp) {
     if (H % 128 != 0) return LAS_ERR_UNSUPPORTED;
     const LasDeviceInfo* di = las_device_info();
     const int rs = 4 * (H / 128);
@@ -1521,6 +1589,7 @@ static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, co
     if (smem > (size_t)di->max_smem_optin) return LAS_ERR_UNSUPPORTED;
     RecTcBwdArgs a{};
     a.w_t = (const __nv_bfloat16*)w_hh_t_bf16;
+    a.dbp = dbp;
     a.gates = gates; a.dgb = (__nv_bfloat16*)dgates_bf16; a.dout = dout; a.cs_pad = cs_pad; a.lens = lens; a.mask = drop_mask;
     a.ctr = (unsigned*)ws;
     a.B = B; a.T = T; a.H = H; a.ndir = ndir; a.nslices = nslices; a.chains = chains; a.bsg = bsg; a.KBr = 4 * H / 64; a.CH = KB; a.dbg = g_rec_dbg;

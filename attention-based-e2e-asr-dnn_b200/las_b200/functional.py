@@ -289,13 +289,23 @@ class LSTMLayerFunction(torch.autograd.Function):
         # backward through the same graph is not supported (like cuDNN's reserve space, it is single use).
         M = Bn * T
         dGb = None
+        dbp = None
         if rec_tc:
             w_hh_t = torch.empty(ndir, H, G4, dtype=torch.bfloat16, device=dev)
             check(lib.las_transpose_cast_bf16(w_hh.data_ptr(), w_hh_t.data_ptr(), ndir, G4, H, stream_ptr()), 'transpose_cast')
             dGb = torch.empty(M, NG, dtype=torch.bfloat16, device=dev)
-            check(lib.las_lstm_rec_bwd_tc(dy.data_ptr(), gates.data_ptr(), dGb.data_ptr(), cs_pad.data_ptr(), w_hh_t.data_ptr(),
-                                          lens_dev.data_ptr(), ptr(mask), Bn, T, H, ndir, wsb.data_ptr(), nbytes, stream_ptr()),
-                  'lstm_rec_bwd_tc')
+            nsl = lib.las_lstm_rec_bwd_tc_dbias_slices(Bn, H, ndir) if os.environ.get('LAS_REC_DBIAS', '1') == '1' else 0
+            if nsl > 0:
+                # bias gradients accumulated inside the BPTT kernel (per direction and batch slice); no fp32 dG write-back, no
+                # column-sum pass over (B*T, 8H)
+                dbp = torch.empty(ndir, nsl, G4, dtype=torch.float32, device=dev)
+                check(lib.las_lstm_rec_bwd_tc_db(dy.data_ptr(), gates.data_ptr(), dGb.data_ptr(), cs_pad.data_ptr(), w_hh_t.data_ptr(),
+                                                 lens_dev.data_ptr(), ptr(mask), Bn, T, H, ndir, wsb.data_ptr(), nbytes, dbp.data_ptr(),
+                                                 stream_ptr()), 'lstm_rec_bwd_tc_db')
+            else:
+                check(lib.las_lstm_rec_bwd_tc(dy.data_ptr(), gates.data_ptr(), dGb.data_ptr(), cs_pad.data_ptr(), w_hh_t.data_ptr(),
+                                              lens_dev.data_ptr(), ptr(mask), Bn, T, H, ndir, wsb.data_ptr(), nbytes, stream_ptr()),
+                      'lstm_rec_bwd_tc')
         else:
             check(lib.las_lstm_rec_bwd_f32(dy.data_ptr(), gates.data_ptr(), cs_pad.data_ptr(), w_hh.data_ptr(), lens_dev.data_ptr(),
                                            ptr(mask), Bn, T, H, ndir, wsb.data_ptr(), nbytes, stream_ptr()), 'lstm_rec_bwd')
@@ -321,7 +331,10 @@ class LSTMLayerFunction(torch.autograd.Function):
                 gemm_tc(dGb, hsb, dw_hh, G4, H, T, k_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=F_, b_s2=(T + 2) * F_, ldc=H,
                         a_mn=True, b_mn=True, a_off=d * G4, b_off=(2 * F_ if d == 1 else 0) + d * H, gate=False)
                 db = torch.empty(G4, dtype=torch.float32, device=dev)
-                colsum(dG, NG, M, G4, db, x_off=d * G4)
+                if dbp is not None:
+                    colsum(dbp, G4, dbp.shape[1], G4, db, x_off=d * dbp.shape[1] * G4)      # add the few batch-slice rows
+                else:
+                    colsum(dG, NG, M, G4, db, x_off=d * G4)
                 grads += [dw_ih, dw_hh, db, db.clone()]
             return (dx, None, None, None, None, *grads)
         if ctx.needs_input_grad[0]:

@@ -141,6 +141,14 @@ void las_lstm_rec_tc_set_debug(void* dev_buf);
 int las_lstm_rec_bwd_tc(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16,
                         const int* lens, const float* drop_mask, int B, int T, int H, int ndir, void* ws, size_t ws_bytes,
                         void* stream);
+/* Same, with the bias gradients accumulated inside the kernel: dbias_partial (ndir, nslices, 4H) receives, per direction and
+ * 32-row batch slice, sum over (rows of the slice, t) of d(pre-activation); the caller adds the nslices rows (fixed order).
+ * In this form the fp32 write-back into `gates` is skipped (its only reader was the bias column sum); dgates_bf16 is
+ * written as before.  las_lstm_rec_bwd_tc_dbias_slices returns nslices, or 0 when the form is not available for the shape. */
+int las_lstm_rec_bwd_tc_dbias_slices(int B, int H, int ndir);
+int las_lstm_rec_bwd_tc_db(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16,
+                           const int* lens, const float* drop_mask, int B, int T, int H, int ndir, void* ws, size_t ws_bytes,
+                           float* dbias_partial, void* stream);
 /* dst[b][c][r] (bf16) = src[b][r][c] (fp32) */
 int las_transpose_cast_bf16(const float* src, void* dst, int batch, int rows, int cols, void* stream);
 

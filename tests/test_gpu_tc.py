@@ -227,3 +227,18 @@ def test_tc_recurrence_backward_vs_fp32_kernel(H, B, T, lens):
     for b, l in enumerate(lens):
         if l < T:
             assert float(g_tc[b, l:].abs().max()) == 0.0
+    # the form that accumulates the bias gradients inside the kernel (and skips the fp32 write-back): same bf16 dG, and the
+    # per-slice rows add up to the column sums of the fp32 dG
+    nsl = lib.las_lstm_rec_bwd_tc_dbias_slices(B, H, ndir)
+    if nsl > 0:
+        g_db = gates.clone()
+        dgb2 = torch.full((B * T, ndir * 4 * H), float('nan'), dtype=torch.bfloat16, device=DEV)
+        dbp = torch.full((ndir, nsl, 4 * H), float('nan'), device=DEV)
+        _lib.check(lib.las_lstm_rec_bwd_tc_db(dout.data_ptr(), g_db.data_ptr(), dgb2.data_ptr(), cs.data_ptr(), w_t.data_ptr(),
+                                              lens_dev.data_ptr(), mask.data_ptr(), B, T, H, ndir, ws2.data_ptr(), nb2, dbp.data_ptr(), st),
+                   'bwd_tc_db')
+        torch.cuda.synchronize()
+        assert torch.equal(dgb2, dgb)
+        db_ref = g_tc.double().sum(dim=(0, 1))                       # (ndir, 4H)
+        db_got = dbp.double().sum(dim=1)
+        assert float((db_got - db_ref).abs().max()) < 1e-4 * max(1.0, float(db_ref.abs().max()))
