@@ -79,8 +79,10 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
         if (BWD && a.dctx2 && c < nch && k < d) {
             // dctx_total = dctx (classifier path) + dctx2 (next step's cell-0 input path); the sum is written back so
             // the deferred dV = w^T . dctx GEMM sees it.  Every warp computes the same sum; warp 0 stores it.
-            const float4 e = *reinterpret_cast<const float4*>(a.dctx2 + (long long)b * a.ld_dctx2 + h * d + k);
-            v4[c].x += e.x; v4[c].y += e.y; v4[c].z += e.z; v4[c].w += e.w;
+            for (int sp = 0; sp < (a.dctx2_nsplit > 1 ? a.dctx2_nsplit : 1); ++sp) {      // split-K partials of the producing GEMM
+                const float4 e = *reinterpret_cast<const float4*>(a.dctx2 + sp * a.dctx2_split_stride + (long long)b * a.ld_dctx2 + h * d + k);
+                v4[c].x += e.x; v4[c].y += e.y; v4[c].z += e.z; v4[c].w += e.w;
+            }
         }
     }
     if (BWD && a.dctx2) {
@@ -297,9 +299,11 @@ __global__ void __launch_bounds__(NT2, 2) attn_step_split_kernel(LasAttnStep a) 
         const bool in = c < nch && k < d;
         v4[c] = in ? *reinterpret_cast<const float4*>(vec + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (BWD && in) {
-            if (a.dctx2) {      // dctx_total = classifier path + next step's cell-0 input path
-                const float4 e = *reinterpret_cast<const float4*>(a.dctx2 + (long long)b * a.ld_dctx2 + h * d + k);
-                v4[c].x += e.x; v4[c].y += e.y; v4[c].z += e.z; v4[c].w += e.w;
+            if (a.dctx2) {      // dctx_total = classifier path + next step's cell-0 input path (summed over its split-K partials)
+                for (int sp = 0; sp < (a.dctx2_nsplit > 1 ? a.dctx2_nsplit : 1); ++sp) {
+                    const float4 e = *reinterpret_cast<const float4*>(a.dctx2 + sp * a.dctx2_split_stride + (long long)b * a.ld_dctx2 + h * d + k);
+                    v4[c].x += e.x; v4[c].y += e.y; v4[c].z += e.z; v4[c].w += e.w;
+                }
             }
             const float4 c4 = *reinterpret_cast<const float4*>(a.ctx + (long long)b * a.ld_ctx + h * d + k);
             dot = fmaf(v4[c].x, c4.x, dot); dot = fmaf(v4[c].y, c4.y, dot); dot = fmaf(v4[c].z, c4.z, dot); dot = fmaf(v4[c].w, c4.w, dot);

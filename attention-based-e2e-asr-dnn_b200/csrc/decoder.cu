@@ -26,6 +26,9 @@ int las_tc_plan_make(void* plan_mem, const void* A, const void* B, int M, int N,
                      long long b_s1, int b_mn_major);
 int las_tc_plan_launch(const void* plan_mem, int a_batch, float* C, long long ldc, const float* bias1, const float* bias2, void* stream);
 int las_tc_plan_launch_lstm(const void* plan_mem, int a_batch, const LasLstmEpi* le, void* stream);
+int las_tc_plan_launch_split(const void* plan_mem, int a_batch, float* Cpart, long long ldp, int splitk, void* stream);
+int las_tc_plan_tiles(const void* plan_mem);
+int las_tc_plan_kiters(const void* plan_mem);
 int las_permute_cast_lstm_rows(const float* src, long long ld_src, void* dst, int H, int K, void* stream);
 
 namespace {
@@ -36,7 +39,10 @@ struct alignas(64) PlanBuf { unsigned char b[1024]; };
 // kernels
 // ------------------------------------------------------------------------------------------------------------------
 struct CellFwd {
-    float* G;                 // (B, 4H) in: partial pre-activations ; out: activated gates
+    const float* Gin;         // optional: nsplit un-reduced split-K partials (nsplit, B, 4H), split_stride floats apart, added up here
+    int nsplit; long long split_stride;
+    const float* bias1; const float* bias2;   // optional (4H) biases (a split-K GEMM cannot add them)
+    float* G;                 // (B, 4H) in: partial pre-activations (when Gin is null) ; out: activated gates
     const float* Gtab;        // (V, 4H) or null: row gathered by token and added
     const int* y; long long ld_y;   // gold tokens (B, >=steps) or null
     const int* chars_prev;    // (B) argmax of the previous step or null
@@ -60,7 +66,18 @@ __global__ void __launch_bounds__(256) cell_fwd_kernel(CellFwd a) {
     const int b = idx / a.H, u = idx - b * a.H;
     const int H = a.H;
     float* g = a.G + (long long)b * 4 * H + u;
-    float p0 = g[0], p1 = g[H], p2 = g[2 * H], p3 = g[3 * H];
+    float p0, p1, p2, p3;
+    if (a.Gin) {
+        p0 = p1 = p2 = p3 = 0.f;
+        for (int sp = 0; sp < a.nsplit; ++sp) {           // fixed order: deterministic
+            const float* gp = a.Gin + sp * a.split_stride + (long long)b * 4 * H + u;
+            p0 += gp[0]; p1 += gp[H]; p2 += gp[2 * H]; p3 += gp[3 * H];
+        }
+    } else {
+        p0 = g[0]; p1 = g[H]; p2 = g[2 * H]; p3 = g[3 * H];
+    }
+    if (a.bias1) { p0 += a.bias1[u]; p1 += a.bias1[H + u]; p2 += a.bias1[2 * H + u]; p3 += a.bias1[3 * H + u]; }
+    if (a.bias2) { p0 += a.bias2[u]; p1 += a.bias2[H + u]; p2 += a.bias2[2 * H + u]; p3 += a.bias2[3 * H + u]; }
     if (a.Gtab) {
         int tok;
         if (a.t == 0) tok = a.sos_idx;
@@ -86,6 +103,8 @@ struct CellBwd {
     float* G;                 // (B,4H) in: activated gates ; out: d(pre-activation)
     const float* dh_a; long long ld_a;   // nullable
     const float* dh_b; long long ld_b;   // nullable
+    int nsplit_a, nsplit_b;              // > 1: dh_a / dh_b are un-reduced split-K partials, stride_a / stride_b floats apart
+    long long stride_a, stride_b;
     const float* mask;        // (B,H) or null (dropout applied to h)
     const float* c; long long ld_c;
     const float* c_prev; long long ld_cp;
@@ -103,8 +122,10 @@ __global__ void __launch_bounds__(256) cell_bwd_kernel(CellBwd a) {
     const int b = idx / a.H, u = idx - b * a.H;
     const int H = a.H;
     float dh = 0.f;
-    if (a.dh_a) dh += a.dh_a[(long long)b * a.ld_a + u];
-    if (a.dh_b) dh += a.dh_b[(long long)b * a.ld_b + u];
+    if (a.dh_a)
+        for (int sp = 0; sp < (a.nsplit_a > 1 ? a.nsplit_a : 1); ++sp) dh += a.dh_a[sp * a.stride_a + (long long)b * a.ld_a + u];
+    if (a.dh_b)
+        for (int sp = 0; sp < (a.nsplit_b > 1 ? a.nsplit_b : 1); ++sp) dh += a.dh_b[sp * a.stride_b + (long long)b * a.ld_b + u];
     if (a.mask) dh *= a.mask[(long long)b * H + u];
     float* g = a.G + (long long)b * 4 * H + u;
     const float gi = g[0], gf = g[H], gg = g[2 * H], go = g[3 * H];
@@ -282,11 +303,23 @@ int cast_rows(cudaStream_t st, const float* src, long long ld_src, __nv_bfloat16
     return las_cast_f32_to_bf16(src, ld_src, 0, 0, dst, ld_dst, rows, cols, cols, st);
 }
 
+constexpr int MAX_SPLIT = 8;
+
+// split factor of a per-step GEMM: as many CTAs as fit one wave, at least two 64-wide K iterations each
+int pick_split(int tiles, int kiters) {
+    const char* e = getenv("LAS_DEC_SPLITK");
+    if (e && atoi(e) == 0) return 1;
+    int sk = las_device_info()->num_sms / (tiles > 0 ? tiles : 1);
+    if (sk > kiters / 2) sk = kiters / 2;
+    if (sk > MAX_SPLIT) sk = MAX_SPLIT;
+    return sk < 1 ? 1 : sk;
+}
+
 struct Layout {
     // float workspace offsets
     size_t Wcat0, Wcat1, Gemb, S0, S1, C0, C1, G0, G1, QC, W, W2, FM, dQC, dS0, dS1, dc0, dc1, dh1, DE, dGemb, tmpq, cs_scratch, total_f;
     // bf16 region (offsets in floats, buffers hold bf16): tensor-pipe mode only
-    size_t Wcat0b, Wcat1b, Wqb, S0b, S1b, G0b, G1b, dQb, dlb, ohb, QCb, tmp32, skws, Wcat0p, Wcat1p;
+    size_t Wcat0b, Wcat1b, Wqb, S0b, S1b, G0b, G1b, dQb, dlb, ohb, QCb, tmp32, skws, Wcat0p, Wcat1p, Gp0, Gp1, dSp0, dSp1;
     size_t skws_floats;
     // int workspace offsets
     size_t tok, total_i;
@@ -339,6 +372,13 @@ Layout make_layout(const LasSpeller* s) {
         L.Wcat1p = takeb(4 * DO * (DH + DO));
         L.S0b = takeb((size_t)L.hist * B * (P + DH));
         L.S1b = takeb((size_t)L.hist * B * (DH + DO));
+        // un-reduced split-K partials of the per-step GEMMs (summed by the pointwise kernels that consume them)
+        L.Gp0 = take((size_t)MAX_SPLIT * B * 4 * DH);
+        L.Gp1 = take((size_t)MAX_SPLIT * B * 4 * DO);
+        if (s->training) {
+            L.dSp0 = take((size_t)MAX_SPLIT * B * (P + DH));
+            L.dSp1 = take((size_t)MAX_SPLIT * B * (DH + DO));
+        }
         if (s->training) {
             L.G0b = takeb(S * B * 4 * DH);
             L.G1b = takeb(S * B * 4 * DO);
@@ -570,6 +610,10 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
         RC(las_tc_plan_make(&pl1, S1b, fuse ? Wcat1p : Wcat1b, B, 4 * DO, K1, L.hist, K1, (long long)B * K1, K1, 0));
         RC(las_tc_plan_make(&plq, S1b + DH, Wqb, B, P, DO, L.hist, K1, (long long)B * K1, DO, 0));
     }
+    // split-K of the two cell GEMMs (un-reduced partials, summed by cell_fwd_kernel): 32 / 16 output tiles cannot fill 148 SMs
+    const int sk0 = (tc && !fuse) ? pick_split(las_tc_plan_tiles(&pl0), las_tc_plan_kiters(&pl0)) : 1;
+    const int sk1 = (tc && !fuse) ? pick_split(las_tc_plan_tiles(&pl1), las_tc_plan_kiters(&pl1)) : 1;
+    float *Gp0 = f + L.Gp0, *Gp1 = f + L.Gp1;
     // embedding-side gate table (+ both cell-0 biases)
     RC(gemm(st, s->emb, E, s->w_ih0, E + P, 1, Gemb, 4 * DH, V, 4 * DH, E, 0.f, s->b_ih0, s->b_hh0));
     // zero initial states (init_hiddens are always zero: reference src/models.py:275-281)
@@ -639,9 +683,10 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
             RC(las_tc_plan_launch_lstm(&pl1, r, &e1, st));
         } else {
         // cell 0
-            if (tc) RC(las_tc_plan_launch(&pl0, r, G0r, 4 * DH, nullptr, nullptr, st));
+            if (tc) RC(las_tc_plan_launch_split(&pl0, r, Gp0, 4 * DH, sk0, st));
             else RC(gemm(st, S0r, K0, Wcat0, K0, 1, G0r, 4 * DH, B, 4 * DH, K0));
             CellFwd c0{};
+            if (tc) { c0.Gin = Gp0; c0.nsplit = sk0; c0.split_stride = (long long)B * 4 * DH; }
             c0.G = G0r; c0.Gtab = Gemb; c0.y = s->dec_y; c0.ld_y = s->ld_y;
             c0.chars_prev = (t > 0) ? s->chars + (size_t)(t - 1) * B : nullptr;
             c0.tok_out = s->training ? tok + (size_t)t * B : nullptr;
@@ -657,9 +702,10 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
             LAS_CUDA(las_launch(cell_fwd_kernel, dim3(ceil_div(B * DH, 256)), dim3(256), 0, st, c0));
             LAS_LAUNCH_CHECK();
             // cell 1
-            if (tc) RC(las_tc_plan_launch(&pl1, r, G1r, 4 * DO, s->b_ih1, s->b_hh1, st));
+            if (tc) RC(las_tc_plan_launch_split(&pl1, r, Gp1, 4 * DO, sk1, st));
             else RC(gemm(st, S1r, K1, Wcat1, K1, 1, G1r, 4 * DO, B, 4 * DO, K1, 0.f, s->b_ih1, s->b_hh1));
             CellFwd c1{};
+            if (tc) { c1.Gin = Gp1; c1.nsplit = sk1; c1.split_stride = (long long)B * 4 * DO; c1.bias1 = s->b_ih1; c1.bias2 = s->b_hh1; }
             c1.G = G1r; c1.Gtab = nullptr; c1.t = t;
             c1.c_prev = C1 + (size_t)r * B * DO; c1.ld_cp = DO;
             c1.c_out = C1 + (size_t)rn * B * DO; c1.ld_co = DO;
@@ -785,6 +831,12 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
         RC(las_tc_plan_make(&bq2, G1b, Wcat1b, B, K1, 4 * DO, S, 4 * DO, (long long)B * 4 * DO, K1, 1));
         RC(las_tc_plan_make(&bq3, G0b, Wcat0b, B, K0, 4 * DH, S, 4 * DH, (long long)B * 4 * DH, K0, 1));
     }
+    // dS1 / dS0 have 12 output tiles and 16 / 32 K iterations: split K over the idle SMs and leave the partials un-reduced;
+    // cell_bwd_kernel and the attention backward add them up as they read
+    const int skb1 = tc ? pick_split(las_tc_plan_tiles(&bq2), las_tc_plan_kiters(&bq2)) : 1;
+    const int skb0 = tc ? pick_split(las_tc_plan_tiles(&bq3), las_tc_plan_kiters(&bq3)) : 1;
+    if (tc) { dS1 = f + L.dSp1; dS0 = f + L.dSp0; }
+    const long long st1 = (long long)B * K1, st0 = (long long)B * K0;
 
     {
     LasPdlScope pdl_scope;       // the per-step kernels overlap their launch / prologue with the predecessor's tail
@@ -795,6 +847,7 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
         at.q = QC + (size_t)rn * B * 2 * P; at.w = W + (size_t)rn * B * heads * T;
         at.ctx = QC + (size_t)rn * B * 2 * P + P; at.ld_ctx = 2 * P;        // saved context: sum_t w_t (dctx.V_t) == dctx.ctx
         at.dctx = dQCn + P; at.dctx2 = (t == S - 1) ? nullptr : dS0;
+        at.dctx2_nsplit = skb0; at.dctx2_split_stride = st0;
         at.dq = dQCn; at.de = DE + (size_t)rn * B * heads * T;
         at.dq_bf16 = tc ? (void*)(dQb + (size_t)rn * B * P) : nullptr; at.ld_dq_bf16 = P;
         if (s->init_force) { at.fmask = FM + (size_t)t * T; at.ld_fmask = 0; at.w2 = W2 + (size_t)rn * B * heads * T; }
@@ -805,7 +858,7 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
         CellBwd b1{};
         b1.G = G1 + (size_t)t * B * 4 * DO;
         b1.dh_a = dh1; b1.ld_a = DO;
-        b1.dh_b = (t == S - 1) ? nullptr : dS1 + DH; b1.ld_b = K1;
+        b1.dh_b = (t == S - 1) ? nullptr : dS1 + DH; b1.ld_b = K1; b1.nsplit_b = skb1; b1.stride_b = st1;
         b1.mask = s->drop1 ? s->drop1 + (size_t)t * B * DO : nullptr;
         b1.c = C1 + (size_t)rn * B * DO; b1.ld_c = DO; b1.c_prev = C1 + (size_t)t * B * DO; b1.ld_cp = DO;
         b1.dc = dc1; b1.first = (t == S - 1); b1.B = B; b1.H = DO;
@@ -813,12 +866,12 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
         LAS_CUDA(las_launch(cell_bwd_kernel, dim3(ceil_div(B * DO, 256)), dim3(256), 0, st, b1));
         LAS_LAUNCH_CHECK();
         // dS1[t] = dG1_t . Wcat1  -> [dh0_t | dh1_{t-1}]
-        if (tc) RC(las_tc_plan_launch(&bq2, t, dS1, K1, nullptr, nullptr, st));
+        if (tc) RC(las_tc_plan_launch_split(&bq2, t, dS1, K1, skb1, st));
         else RC(gemm(st, b1.G, 4 * DO, Wcat1, K1, 0, dS1, K1, B, K1, 4 * DO));
         CellBwd b0{};
         b0.G = G0 + (size_t)t * B * 4 * DH;
-        b0.dh_a = dS1; b0.ld_a = K1;
-        b0.dh_b = (t == S - 1) ? nullptr : dS0 + P; b0.ld_b = K0;
+        b0.dh_a = dS1; b0.ld_a = K1; b0.nsplit_a = skb1; b0.stride_a = st1;
+        b0.dh_b = (t == S - 1) ? nullptr : dS0 + P; b0.ld_b = K0; b0.nsplit_b = skb0; b0.stride_b = st0;
         b0.mask = s->drop0 ? s->drop0 + (size_t)t * B * DH : nullptr;
         b0.c = C0 + (size_t)rn * B * DH; b0.ld_c = DH; b0.c_prev = C0 + (size_t)t * B * DH; b0.ld_cp = DH;
         b0.dc = dc0; b0.first = (t == S - 1); b0.B = B; b0.H = DH;
@@ -826,7 +879,7 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
         LAS_CUDA(las_launch(cell_bwd_kernel, dim3(ceil_div(B * DH, 256)), dim3(256), 0, st, b0));
         LAS_LAUNCH_CHECK();
         // dS0[t] = dG0_t . Wcat0 -> [dctx_t | dh0_{t-1}]
-        if (tc) RC(las_tc_plan_launch(&bq3, t, dS0, K0, nullptr, nullptr, st));
+        if (tc) RC(las_tc_plan_launch_split(&bq3, t, dS0, K0, skb0, st));
         else RC(gemm(st, b0.G, 4 * DH, Wcat0, K0, 0, dS0, K0, B, K0, 4 * DH));
     }
     }                            // PDL scope ends: the batched GEMMs below are ordinary launches

@@ -518,6 +518,25 @@ int las_tc_plan_launch(const void* plan_mem, int a_batch, float* C, long long ld
     return launch_tc<false, true, 64>(p->ta, p->tb, g, (cudaStream_t)stream);
 }
 
+// plan launch with the K range split over `splitk` CTAs per output tile; the partial matrices (splitk, M, ldp) are left
+// un-reduced in Cpart: the decoder's pointwise consumers (cell kernels, attention backward) add them up as they read
+int las_tc_plan_launch_split(const void* plan_mem, int a_batch, float* Cpart, long long ldp, int splitk, void* stream) {
+    const LasTcPlan* p = (const LasTcPlan*)plan_mem;
+    TcArgs g = p->g;
+    LAS_CHECK_ARG(splitk >= 1 && splitk <= g.kt_per_b && ldp % 4 == 0 && ((uintptr_t)Cpart & 15) == 0, "tc plan split: bad split / ldp");
+    g.b_first = a_batch;
+    if (splitk == 1) { g.C = Cpart; g.ldc = ldp; g.c_bs = 0; }
+    else { g.splitk = splitk; g.Cpart = Cpart; g.ldp = ldp; }
+    LasProfScope prof(LAS_PROF_GEMM_OTHER, stream, 2.0 * g.R * (double)g.N * g.kt_per_b * BK);
+    if (p->variant == 0) {
+        if (p->bn == 32) return launch_tc<false, false, 32>(p->ta, p->tb, g, (cudaStream_t)stream);
+        return launch_tc<false, false, 64>(p->ta, p->tb, g, (cudaStream_t)stream);
+    }
+    return launch_tc<false, true, 64>(p->ta, p->tb, g, (cudaStream_t)stream);
+}
+int las_tc_plan_tiles(const void* plan_mem) { const LasTcPlan* p = (const LasTcPlan*)plan_mem; return p->g.mt_per_b * p->g.nt; }
+int las_tc_plan_kiters(const void* plan_mem) { return ((const LasTcPlan*)plan_mem)->g.kt_per_b; }
+
 // plan launch with the fused LSTM-cell epilogue (plan must be the K-major-B form with permuted weight rows, N = 4H)
 int las_tc_plan_launch_lstm(const void* plan_mem, int a_batch, const LasLstmEpi* le, void* stream) {
     const LasTcPlan* p = (const LasTcPlan*)plan_mem;

@@ -65,6 +65,7 @@ class LasAttnStep(C.Structure):
         ('kv_bf16', C.c_int),
         ('fmask', C.c_void_p), ('ld_fmask', c_ll),
         ('w2', C.c_void_p),
+        ('dctx2_nsplit', C.c_int), ('dctx2_split_stride', c_ll),
     ]
 
 

@@ -184,6 +184,9 @@ typedef struct {
      * weights in fwd and must be passed back to bwd. */
     const float* fmask; long long ld_fmask;
     float* w2;
+    /* bwd: dctx2 may be the un-reduced output of a split-K GEMM: dctx2_nsplit (> 1) partial matrices, dctx2_split_stride
+     * floats apart, are added up on the fly (0 / 1: a single matrix) */
+    int dctx2_nsplit; long long dctx2_split_stride;
 } LasAttnStep;
 int las_attn_step_fwd_f32(const LasAttnStep* desc, void* stream);
 int las_attn_step_bwd_f32(const LasAttnStep* desc, void* stream);
