@@ -79,10 +79,15 @@ __global__ void __launch_bounds__(NT) attn_step_kernel(LasAttnStep a) {
         if (BWD && a.dctx2 && c < nch && k < d) {
             // dctx_total = dctx (classifier path) + dctx2 (next step's cell-0 input path); the sum is written back so
             // the deferred dV = w^T . dctx GEMM sees it.  Every warp computes the same sum; warp 0 stores it.
-            for (int sp = 0; sp < (a.dctx2_nsplit > 1 ? a.dctx2_nsplit : 1); ++sp) {      // split-K partials of the producing GEMM
-                const float4 e = *reinterpret_cast<const float4*>(a.dctx2 + sp * a.dctx2_split_stride + (long long)b * a.ld_dctx2 + h * d + k);
-                v4[c].x += e.x; v4[c].y += e.y; v4[c].z += e.z; v4[c].w += e.w;
-            }
+            // split-K partials of the producing GEMM (at most 8): all loads issued before the adds
+            float4 e[8];
+            const int ns = a.dctx2_nsplit > 1 ? a.dctx2_nsplit : 1;
+#pragma unroll
+            for (int sp = 0; sp < 8; ++sp)
+                e[sp] = sp < ns ? *reinterpret_cast<const float4*>(a.dctx2 + sp * a.dctx2_split_stride + (long long)b * a.ld_dctx2 + h * d + k)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int sp = 0; sp < 8; ++sp) { v4[c].x += e[sp].x; v4[c].y += e[sp].y; v4[c].z += e[sp].z; v4[c].w += e[sp].w; }
         }
     }
     if (BWD && a.dctx2) {
@@ -300,10 +305,14 @@ __global__ void __launch_bounds__(NT2, 2) attn_step_split_kernel(LasAttnStep a) 
         v4[c] = in ? *reinterpret_cast<const float4*>(vec + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (BWD && in) {
             if (a.dctx2) {      // dctx_total = classifier path + next step's cell-0 input path (summed over its split-K partials)
-                for (int sp = 0; sp < (a.dctx2_nsplit > 1 ? a.dctx2_nsplit : 1); ++sp) {
-                    const float4 e = *reinterpret_cast<const float4*>(a.dctx2 + sp * a.dctx2_split_stride + (long long)b * a.ld_dctx2 + h * d + k);
-                    v4[c].x += e.x; v4[c].y += e.y; v4[c].z += e.z; v4[c].w += e.w;
-                }
+                float4 e[8];                      // at most 8 partials: all loads issued before the adds
+                const int ns = a.dctx2_nsplit > 1 ? a.dctx2_nsplit : 1;
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp)
+                    e[sp] = sp < ns ? *reinterpret_cast<const float4*>(a.dctx2 + sp * a.dctx2_split_stride + (long long)b * a.ld_dctx2 + h * d + k)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp) { v4[c].x += e[sp].x; v4[c].y += e[sp].y; v4[c].z += e[sp].z; v4[c].w += e[sp].w; }
             }
             const float4 c4 = *reinterpret_cast<const float4*>(a.ctx + (long long)b * a.ld_ctx + h * d + k);
             dot = fmaf(v4[c].x, c4.x, dot); dot = fmaf(v4[c].y, c4.y, dot); dot = fmaf(v4[c].z, c4.z, dot); dot = fmaf(v4[c].w, c4.w, dot);
@@ -478,6 +487,7 @@ int check(const LasAttnStep* a, bool bwd) {
     LAS_CHECK_ARG(d % 4 == 0 && d <= 128 * MAXCH, "attn_step: head dim %d must be a multiple of 4 and <= %d", d, 128 * MAXCH);
     LAS_CHECK_ARG(a->K && a->V && a->lens && a->w, "attn_step: null K/V/lens/w");
     LAS_CHECK_ARG(!a->fmask || a->w2, "attn_step: the init-force prior (fmask) needs w2 (second-softmax weights)");
+    LAS_CHECK_ARG(a->dctx2_nsplit <= 8, "attn_step: at most 8 dctx2 partials");
     if (!bwd) {
         LAS_CHECK_ARG(a->q && a->ctx, "attn_step_fwd: null q/ctx");
         LAS_CHECK_ARG(a->ld_q % 4 == 0, "attn_step_fwd: ld_q must be a multiple of 4");

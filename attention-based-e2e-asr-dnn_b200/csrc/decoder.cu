@@ -34,6 +34,7 @@ int las_permute_cast_lstm_rows(const float* src, long long ld_src, void* dst, in
 namespace {
 
 struct alignas(64) PlanBuf { unsigned char b[1024]; };
+constexpr int MAX_SPLIT = 8;          // most split-K partials a per-step GEMM leaves for its pointwise consumer to add up
 
 // ------------------------------------------------------------------------------------------------------------------
 // kernels
@@ -69,10 +70,15 @@ __global__ void __launch_bounds__(256) cell_fwd_kernel(CellFwd a) {
     float p0, p1, p2, p3;
     if (a.Gin) {
         p0 = p1 = p2 = p3 = 0.f;
-        for (int sp = 0; sp < a.nsplit; ++sp) {           // fixed order: deterministic
+        float q0[MAX_SPLIT], q1[MAX_SPLIT], q2[MAX_SPLIT], q3[MAX_SPLIT];
+#pragma unroll
+        for (int sp = 0; sp < MAX_SPLIT; ++sp) {          // every load issued before the first add
             const float* gp = a.Gin + sp * a.split_stride + (long long)b * 4 * H + u;
-            p0 += gp[0]; p1 += gp[H]; p2 += gp[2 * H]; p3 += gp[3 * H];
+            const bool on = sp < a.nsplit;
+            q0[sp] = on ? gp[0] : 0.f; q1[sp] = on ? gp[H] : 0.f; q2[sp] = on ? gp[2 * H] : 0.f; q3[sp] = on ? gp[3 * H] : 0.f;
         }
+#pragma unroll
+        for (int sp = 0; sp < MAX_SPLIT; ++sp) { p0 += q0[sp]; p1 += q1[sp]; p2 += q2[sp]; p3 += q3[sp]; }     // fixed order: deterministic
     } else {
         p0 = g[0]; p1 = g[H]; p2 = g[2 * H]; p3 = g[3 * H];
     }
@@ -122,10 +128,19 @@ __global__ void __launch_bounds__(256) cell_bwd_kernel(CellBwd a) {
     const int b = idx / a.H, u = idx - b * a.H;
     const int H = a.H;
     float dh = 0.f;
-    if (a.dh_a)
-        for (int sp = 0; sp < (a.nsplit_a > 1 ? a.nsplit_a : 1); ++sp) dh += a.dh_a[sp * a.stride_a + (long long)b * a.ld_a + u];
-    if (a.dh_b)
-        for (int sp = 0; sp < (a.nsplit_b > 1 ? a.nsplit_b : 1); ++sp) dh += a.dh_b[sp * a.stride_b + (long long)b * a.ld_b + u];
+    {   // partial sums (at most MAX_SPLIT each): every load issued before the first add
+        float pa[MAX_SPLIT], pb[MAX_SPLIT];
+        const int na = a.dh_a ? (a.nsplit_a > 1 ? a.nsplit_a : 1) : 0, nb = a.dh_b ? (a.nsplit_b > 1 ? a.nsplit_b : 1) : 0;
+#pragma unroll
+        for (int sp = 0; sp < MAX_SPLIT; ++sp) {
+            pa[sp] = sp < na ? a.dh_a[sp * a.stride_a + (long long)b * a.ld_a + u] : 0.f;
+            pb[sp] = sp < nb ? a.dh_b[sp * a.stride_b + (long long)b * a.ld_b + u] : 0.f;
+        }
+#pragma unroll
+        for (int sp = 0; sp < MAX_SPLIT; ++sp) dh += pa[sp];
+#pragma unroll
+        for (int sp = 0; sp < MAX_SPLIT; ++sp) dh += pb[sp];
+    }
     if (a.mask) dh *= a.mask[(long long)b * H + u];
     float* g = a.G + (long long)b * 4 * H + u;
     const float gi = g[0], gf = g[H], gg = g[2 * H], go = g[3 * H];
@@ -302,8 +317,6 @@ __global__ void __launch_bounds__(256) onehot_kernel(const int* __restrict__ tok
 int cast_rows(cudaStream_t st, const float* src, long long ld_src, __nv_bfloat16* dst, long long ld_dst, long long rows, int cols) {
     return las_cast_f32_to_bf16(src, ld_src, 0, 0, dst, ld_dst, rows, cols, cols, st);
 }
-
-constexpr int MAX_SPLIT = 8;
 
 // split factor of a per-step GEMM: as many CTAs as fit one wave, at least two 64-wide K iterations each
 int pick_split(int tiles, int kiters) {
