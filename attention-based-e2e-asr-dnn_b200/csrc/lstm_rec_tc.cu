@@ -150,6 +150,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 // idesc: F32 accumulate, BF16 x BF16, both K-major, M = 128, N = 32
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB_SLICE >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
 
+// the per-step operand tile (32 x H bf16) is fetched as NP pieces of KB/NP k-blocks, each with its own barrier, so the UMMAs of a
+// piece run while the next pieces are still in flight
+// measured at H = 512 (forward / BPTT us per timestep): 1 piece 3.78 / 4.96, 2 pieces 3.54 / 4.84, 4 pieces 3.86 / 5.15
+__host__ __device__ inline int rec_pieces(int KB) { return (KB % 2 == 0) ? 2 : 1; }
+
 constexpr int FWD_NACC = 4;          // independent TMEM accumulators per chain in the forward recurrence (one per k sub-step)
 
 template <bool WTMEM>
@@ -167,11 +172,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
     auto tfull_bar = [&](int c) { return bar_base + 8u * (MAX_CHAINS + c); };
     const uint32_t wbar = bar_base + 8u * (2 * MAX_CHAINS);
     const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_CHAINS + 1);
-    auto full2_bar = [&](int c) { return bar_base + 8u * (2 * MAX_CHAINS + 2 + c); };
+    const int NP = rec_pieces(KB), KBP = KB / NP;
+    auto piece_bar = [&](int c, int pc) { return pc == 0 ? full_bar(c) : bar_base + 8u * (2 * MAX_CHAINS + 2 + (pc - 1) * MAX_CHAINS + c); };
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-    // the h tile arrives as two half-tiles (k-blocks [0, KBH) and [KBH, KB)), each with its own barrier, so the UMMAs of the
-    // first half run while the second half is still in flight
-    const int KBH = (KB >= 2 && KB % 2 == 0) ? KB / 2 : KB;
 
     const int r = blockIdx.x, sg = blockIdx.y, dir = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -181,7 +184,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmH) : "memory");
-        for (int c = 0; c < MAX_CHAINS; ++c) { mbar_init(full_bar(c), 1); mbar_init(tfull_bar(c), 1); mbar_init(full2_bar(c), 1); }
+        for (int c = 0; c < MAX_CHAINS; ++c) {
+            mbar_init(tfull_bar(c), 1);
+            for (int pc = 0; pc < 4; ++pc) mbar_init(piece_bar(c, pc), 1);
+        }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -239,11 +245,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     asm volatile("fence.proxy.async.global;" ::: "memory");       // peers' generic-proxy writes -> our TMA reads
                     REC_STAMP(11);
                     const int row0 = (dir * 2 + ((s - 1) & 1)) * a.Bpad + slice * NB_SLICE;
-                    mbar_arrive_expect_tx(full_bar(c), (uint32_t)KBH * 4096u);
-                    tma_load_3d(h_sm + c * KB * 4096, &tmH, full_bar(c), 0, row0, 0);   // box (64, 32 rows, KBH k-blocks)
-                    if (KBH < KB) {
-                        mbar_arrive_expect_tx(full2_bar(c), (uint32_t)(KB - KBH) * 4096u);
-                        tma_load_3d(h_sm + (c * KB + KBH) * 4096, &tmH, full2_bar(c), 0, row0, KBH);
+                    for (int pc = 0; pc < NP; ++pc) {                               // box (64, 32 rows, KBP k-blocks) per issue
+                        mbar_arrive_expect_tx(piece_bar(c, pc), (uint32_t)KBP * 4096u);
+                        tma_load_3d(h_sm + (c * KB + pc * KBP) * 4096, &tmH, piece_bar(c, pc), 0, row0, pc * KBP);
                     }
                     REC_STAMP(1);
                 }
@@ -256,14 +260,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
             for (int c = 0; c < a.chains; ++c) {
                 const int slice = sg + c * a.bsg;
                 if (slice >= a.nslices) continue;
-                for (int half = 0; half < (KBH < KB ? 2 : 1); ++half) {
-                    mbar_wait(half ? full2_bar(c) : full_bar(c), (uint32_t)((s - 1) & 1));
-                    if (lane == 0 && half == 0) REC_STAMP(2);
+                for (int pc = 0; pc < NP; ++pc) {
+                    mbar_wait(piece_bar(c, pc), (uint32_t)((s - 1) & 1));
+                    if (lane == 0 && pc == 0) REC_STAMP(2);
                     tc_fence_after();
                     if (elect_one()) {
                         // consecutive UMMAs into ONE accumulator serialise on it: round-robin over FWD_NACC independent
                         // accumulators, summed by the epilogue
-                        const int kb_lo = half ? KBH : 0, kb_hi = half ? KB : KBH;
+                        const int kb_lo = pc * KBP, kb_hi = kb_lo + KBP;
                         for (int kb = kb_lo; kb < kb_hi; ++kb) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -887,10 +891,10 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
     rc = make_map_2d(&tmW, w_hh_bf16, H, (long long)ndir * 4 * H, 64, 32);
     if (rc) return rc;
     {   // h exchange buffer viewed as (64 k, rows, H/64 k-blocks): one box = the whole 32 x H slice in k-block-major smem order
-        const int KBt = H / 64, KBHt = (KBt >= 2 && KBt % 2 == 0) ? KBt / 2 : KBt;
+        const int KBt = H / 64, KBPt = KBt / rec_pieces(KBt);
         const long long dims[3] = {64, (long long)ndir * 2 * p.Bpad, KBt};
         const long long strides[2] = {H, 64};
-        const int box[3] = {64, NB_SLICE, KBHt};      // half a tile per TMA issue (see the kernel)
+        const int box[3] = {64, NB_SLICE, KBPt};      // one piece of the tile per TMA issue (see the kernel)
         rc = make_map_nd(&tmH, a.hbuf, 3, dims, strides, box);
         if (rc) return rc;
     }
@@ -1286,8 +1290,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
     auto tfull_bar = [&](int c) { return bar_base + 8u * (MAX_CHAINS + c); };
     const uint32_t wbar = bar_base + 8u * (2 * MAX_CHAINS);
     const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_CHAINS + 1);
-    auto full2_bar = [&](int c) { return bar_base + 8u * (2 * MAX_CHAINS + 2 + c); };
-    const int KBH = (KB >= 2 && KB % 2 == 0) ? KB / 2 : KB;       // the dG tile arrives as two half-tiles (see the forward kernel)
+    const int NP = rec_pieces(KB), KBP = KB / NP;                 // the dG tile arrives in pieces (see the forward kernel)
+    auto piece_bar = [&](int c, int pc) { return pc == 0 ? full_bar(c) : bar_base + 8u * (2 * MAX_CHAINS + 2 + (pc - 1) * MAX_CHAINS + c); };
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int kq = (int)cluster_ctarank();            // gate handled by this CTA's reduction slice
@@ -1301,7 +1305,10 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWt) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
-        for (int c = 0; c < MAX_CHAINS; ++c) { mbar_init(full_bar(c), 1); mbar_init(tfull_bar(c), 1); mbar_init(full2_bar(c), 1); }
+        for (int c = 0; c < MAX_CHAINS; ++c) {
+            mbar_init(tfull_bar(c), 1);
+            for (int pc = 0; pc < 4; ++pc) mbar_init(piece_bar(c, pc), 1);
+        }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1391,11 +1398,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                     asm volatile("fence.proxy.async.global;" ::: "memory");
                     // compact exchange buffer (dir, parity, gate, Bpad, H): the 32 x H tile of gate kq is 32 contiguous rows
                     const int row0 = ((dir * 2 + ((s - 1) & 1)) * 4 + kq) * a.Bpad + b0;
-                    mbar_arrive_expect_tx(full_bar(c), (uint32_t)KBH * 4096u);
-                    tma_load_3d(b_sm + c * KB * 4096, &tmG, full_bar(c), 0, row0, 0);
-                    if (KBH < KB) {
-                        mbar_arrive_expect_tx(full2_bar(c), (uint32_t)(KB - KBH) * 4096u);
-                        tma_load_3d(b_sm + (c * KB + KBH) * 4096, &tmG, full2_bar(c), 0, row0, KBH);
+                    for (int pc = 0; pc < NP; ++pc) {
+                        mbar_arrive_expect_tx(piece_bar(c, pc), (uint32_t)KBP * 4096u);
+                        tma_load_3d(b_sm + (c * KB + pc * KBP) * 4096, &tmG, piece_bar(c, pc), 0, row0, pc * KBP);
                     }
                     REC_STAMP(1);
                 }
@@ -1404,12 +1409,12 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                 if (s > 0) {
                     // whole warp waits, one elected lane issues (uniform control flow keeps the descriptors in uniform registers);
                     // BWD_NACC independent accumulators (one per k sub-step) break the accumulate-dependency chain
-                    for (int half = 0; half < (KBH < KB ? 2 : 1); ++half) {
-                        mbar_wait(half ? full2_bar(c) : full_bar(c), (uint32_t)((s - 1) & 1));
-                        if (lane == 0 && half == 0) REC_STAMP(2);
+                    for (int pc = 0; pc < NP; ++pc) {
+                        mbar_wait(piece_bar(c, pc), (uint32_t)((s - 1) & 1));
+                        if (lane == 0 && pc == 0) REC_STAMP(2);
                         tc_fence_after();
                         if (elect_one()) {
-                            const int kb_lo = half ? KBH : 0, kb_hi = half ? KB : KBH;
+                            const int kb_lo = pc * KBP, kb_hi = kb_lo + KBP;
                             for (int kb = kb_lo; kb < kb_hi; ++kb) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
@@ -1600,10 +1605,10 @@ static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, co
     a.Bpad = nslices * NB_SLICE;
     a.dgx = (__nv_bfloat16*)((char*)ws + 1024);
     {   // exchange buffer (ndir*2*4*Bpad rows, H) viewed as (64, rows, H/64): one box = a 32 x H tile in k-block-major smem order
-        const int KBHt = (KB >= 2 && KB % 2 == 0) ? KB / 2 : KB;
+        const int KBPt = KB / rec_pieces(KB);
         const long long dims[3] = {64, (long long)ndir * 2 * 4 * a.Bpad, KB};
         const long long strides[2] = {H, 64};
-        const int box[3] = {64, NB_SLICE, KBHt};      // half a tile per TMA issue
+        const int box[3] = {64, NB_SLICE, KBPt};      // one piece of the tile per TMA issue
         rc = make_map_nd(&tmG, a.dgx, 3, dims, strides, box);
         if (rc) return rc;
     }
