@@ -140,6 +140,8 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 #define REC_STAMP(slot)                                                                              \
@@ -157,7 +159,10 @@ __host__ __device__ inline int rec_pieces(int KB) { return (KB % 2 == 0) ? 2 : 1
 
 constexpr int FWD_NACC = 4;          // independent TMEM accumulators per chain in the forward recurrence (one per k sub-step)
 
-template <bool WTMEM>
+// CLUSTER: the H/32 CTAs of a (direction, batch slice) group are ONE thread-block cluster and meet on the hardware cluster
+// barrier once per timestep (arrive.release after the h_t stores, wait.acquire before the TMA of the next step) instead of the
+// release/acquire counter in global memory: one fence + barrier hop instead of release fence -> counter -> poll.
+template <bool WTMEM, bool CLUSTER>
 __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW,
                                                                      const __grid_constant__ CUtensorMap tmH, const RecTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -235,12 +240,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                         tma_load_2d(w_sm + kb * 16384 + g * 4096, &tmW, wbar, kb * 64, dir * 4 * H + g * H + r * UNITS);
             }
             for (int s = 1; s < T; ++s) {
+                if (CLUSTER) {          // step s-1 of every chain has been published by the whole group
+                    cluster_arrive_release();
+                    cluster_wait_acquire();
+                }
                 for (int c = 0; c < a.chains; ++c) {
                     const int slice = sg + c * a.bsg;
                     if (slice >= a.nslices) continue;
-                    const unsigned* ctr = a.ctr + dir * a.nslices + slice;
-                    const unsigned target = (unsigned)(H / UNITS) * (unsigned)s;
-                    while (ld_acquire_gpu(ctr) < target) { }
+                    if (!CLUSTER) {
+                        const unsigned* ctr = a.ctr + dir * a.nslices + slice;
+                        const unsigned target = (unsigned)(H / UNITS) * (unsigned)s;
+                        while (ld_acquire_gpu(ctr) < target) { }
+                    }
                     REC_STAMP(0);
                     asm volatile("fence.proxy.async.global;" ::: "memory");       // peers' generic-proxy writes -> our TMA reads
                     REC_STAMP(11);
@@ -252,11 +263,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     REC_STAMP(1);
                 }
             }
+        } else if (CLUSTER) {
+            for (int s = 1; s < T; ++s) { cluster_arrive_release(); cluster_wait_acquire(); }     // every thread of the cluster takes part
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp walks the loop (waits included), one elected lane issues =====
         if (!WTMEM) mbar_wait(wbar, 0);
         for (int s = 1; s < T; ++s) {
+            if (CLUSTER) { cluster_arrive_release(); cluster_wait_acquire(); }
             for (int c = 0; c < a.chains; ++c) {
                 const int slice = sg + c * a.bsg;
                 if (slice >= a.nslices) continue;
@@ -289,7 +303,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                 if (lane == 0) REC_STAMP(3);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
+        if (CLUSTER)
+            for (int s = 1; s < T; ++s) { cluster_arrive_release(); cluster_wait_acquire(); }
+    } else {
         // ===== epilogue: one warp per gate =====
         const int q = warp & 3, j = lane;          // gate q, unit r*32 + j
         const int te = (warp - 4) * 32 + lane;     // 0..127
@@ -318,6 +335,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
         }
         for (int s = 0; s < T; ++s) {
             const int t = (dir == 0) ? s : (T - 1 - s);
+            if (CLUSTER && s > 0) cluster_wait_acquire();             // pairs with this thread's arrive at the end of step s-1
 #pragma unroll
             for (int c = 0; c < MAX_CHAINS; ++c) {
                 const int slice = sg + c * a.bsg;
@@ -371,9 +389,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     a.hbuf[((long long)(dir * 2 + (s & 1)) * a.Bpad + b) * H + u] = __float2bfloat16(hh[i]);
                 }
                 // publish step s of this chain FIRST (the release only has the 8 bf16 stores per thread in front of it) ...
-                named_bar_sync(1, 128);
-                if (te == 0) REC_STAMP(8);
-                if (te == 0 && s + 1 < T) red_release_gpu_add(a.ctr + dir * a.nslices + slice, 1u);
+                if (CLUSTER) {
+                    // `ex` is reused by the next chain / step: keep the four warps together, then (last chain) arrive on the cluster barrier
+                    named_bar_sync(1, 128);
+                    if (te == 0) REC_STAMP(8);
+                    bool last = true;
+#pragma unroll
+                    for (int c2 = c + 1; c2 < MAX_CHAINS; ++c2)
+                        if (c2 < a.chains && sg + c2 * a.bsg < a.nslices) last = false;
+                    if (last && s + 1 < T) cluster_arrive_release();
+                } else {
+                    named_bar_sync(1, 128);
+                    if (te == 0) REC_STAMP(8);
+                    if (te == 0 && s + 1 < T) red_release_gpu_add(a.ctr + dir * a.nslices + slice, 1u);
+                }
                 if (te == 0) REC_STAMP(9);
                 // ... then write what only backward / the next layer read; these stores overlap the wait for the next step
                 if (a.save) {
@@ -898,10 +927,36 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
         rc = make_map_nd(&tmH, a.hbuf, 3, dims, strides, box);
         if (rc) return rc;
     }
-    void* kern = a.w_tmem ? (void*)lstm_rec_fwd_tc_kernel<true> : (void*)lstm_rec_fwd_tc_kernel<false>;
-    LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    // LAS_REC_CLUSTER=1: one thread-block cluster per (direction, batch slice) group (<= 16 CTAs: non-portable size, every B200
+    // GPC has >= 16 SMs) synchronised by the hardware cluster barrier instead of the counter.  Measured NOT faster: the
+    // arrive.release costs the same ~1000-cycle store fence as red.release and the barrier another ~1000 cycles to complete
+    // across 16 SMs (6416 vs 6389 cycles/step at B=96; 2x slower with two chains per CTA).  Off by default.
+    const char* ce = getenv("LAS_REC_CLUSTER");
+    bool use_cluster = (ce && atoi(ce) != 0) && p.rs <= 16;
     LAS_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
     LasProfScope prof(LAS_PROF_REC_FWD, stream, (double)T);
+    if (use_cluster) {
+        auto kc = a.w_tmem ? lstm_rec_fwd_tc_kernel<true, true> : lstm_rec_fwd_tc_kernel<false, true>;
+        cudaError_t e1 = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        if (e1 == cudaSuccess && p.rs > 8) e1 = cudaFuncSetAttribute(kc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e1 == cudaSuccess) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(p.rs, p.bsg, ndir); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = p.smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = p.rs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nclusters = 0;
+            e1 = cudaOccupancyMaxActiveClusters(&nclusters, kc, &cfg);
+            // clusters are independent of one another (a group never waits for another group), so they need not all be co-resident
+            if (e1 == cudaSuccess && nclusters >= 1) e1 = cudaLaunchKernelEx(&cfg, kc, tmW, tmH, a);
+            else if (e1 == cudaSuccess) e1 = cudaErrorInvalidConfiguration;
+        }
+        if (e1 == cudaSuccess) { las_count_launch(1); return LAS_OK; }
+        cudaGetLastError();         // fall back to the counter-based cooperative launch
+    }
+    void* kern = a.w_tmem ? (void*)lstm_rec_fwd_tc_kernel<true, false> : (void*)lstm_rec_fwd_tc_kernel<false, false>;
+    LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     void* args[] = {(void*)&tmW, (void*)&tmH, (void*)&a};
     LAS_CUDA(cudaLaunchCooperativeKernel(kern, dim3(p.rs, p.bsg, ndir), dim3(NTHREADS), args, p.smem, st));
     las_count_launch(1);
