@@ -437,6 +437,320 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
 
 
 // =====================================================================================================================
+// DSMEM exchange variant of the forward recurrence (the default when the group fits one thread-block cluster).
+// The RS = H/32 CTAs of a (direction, batch slice) group form ONE cluster.  h_t never goes through global memory / L2 on
+// its way to the peers: each CTA stages its 32 rows x 32 units bf16 slice (2 KB) in shared memory in the UMMA K-major
+// *no-swizzle* core-matrix layout and pushes it into every peer's operand buffer with one bulk async copy per peer
+// (cp.async.bulk.shared::cluster.shared::cta), which also signals the peer's mbarrier (complete_tx).  No counter, no
+// release fence waiting for L2 acks, no polling, no TMA fetch: the MMA warp just waits for 2 x RS/2 x 2 KB to land.
+// Measured (scripts/micro/dsmem_bulk.cu): the 16-way all-to-all of 2 KB slices completes ~1950 cycles after the first issue
+// (~17 B/clk into each SM) against ~3750 for release -> counter -> poll -> proxy fence -> TMA.
+//   * operand layout: core matrix = 8 batch rows x 8 units (128 B); address(kc, ng) = kc*512 + ng*128 with kc = unit/8,
+//     ng = row/8 -> UMMA descriptor SWIZZLE_NONE, LBO (next core along K) = 512 B, SBO (next 8 rows) = 128 B; the slice of
+//     source CTA r is the contiguous range [r*2048, (r+1)*2048).
+//   * two operand buffers (step parity): a peer can be at most one step ahead of this CTA's tensor pipe.
+//   * sources 0..RS/2-1 signal barrier A, the others barrier B: the UMMAs of the first half of K start while the second
+//     half is still arriving.
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t remote_bar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),
+                 "r"(src_cta_addr), "r"(bytes), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc_k_noswz(uint32_t saddr) {     // K-major, no swizzle: LBO 512 B, SBO 128 B
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(512 >> 4) << 16;
+    d |= (uint64_t)(128 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+template <int CHAINS>
+__global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const RecTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const int H = a.H, T = a.T;
+    const int RS = H / UNITS;                                     // CTAs per group = cluster size
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t TILE = (uint32_t)RS * 2048u;                   // 32 rows x H bf16
+    const uint32_t h_sm = base;                                   // [chain][parity][TILE]
+    const uint32_t stage_sm = h_sm + CHAINS * 2 * TILE;         // [chain][2 KB]: this CTA's slice in core-matrix layout
+    const uint32_t ex_off = (stage_sm - smem_u32(smem_raw)) + CHAINS * 2048;
+    float* ex = reinterpret_cast<float*>(smem_raw + ex_off);      // [4][32][32] gate exchange
+    float* xgs = ex + 4 * 32 * 32;                                // [2][4][32][32] input projection of the next steps (CHAINS == 1: staged by the helper warps)
+    const uint32_t bar_base = smem_u32(smem_raw) + ex_off + 3 * 4 * 32 * 32 * 4;
+    auto hbar = [&](int c, int par, int half) { return bar_base + 8u * ((c * 2 + par) * 2 + half); };       // 8 barriers
+    auto tfull_bar = [&](int c) { return bar_base + 8u * (8 + c); };
+    const uint32_t tmem_slot = bar_base + 8u * 10;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    uint8_t* stage_ptr = smem_raw + (stage_sm - smem_u32(smem_raw));
+
+    const int r = blockIdx.x, sg = blockIdx.y, dir = blockIdx.z;   // r == rank in the cluster (cluster dims (RS,1,1))
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int F = a.ndir * H;
+    const long long brow = (long long)(T + 2) * F;
+    const int halfsrc = RS >= 2 ? RS / 2 : 1;                     // sources [0, halfsrc) -> barrier A, the rest -> barrier B
+    const int nhalf = RS >= 2 ? 2 : 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 8; ++i) mbar_init(bar_base + 8u * i, 1);
+        for (int c = 0; c < MAX_CHAINS; ++c) mbar_init(tfull_bar(c), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t tmem_cols = 512u;
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t tmem_w = tmem_base + MAX_CHAINS * FWD_NACC * NB_SLICE;
+    if (warp >= 4) {
+        // resident A operand: this CTA's 128 x H slice of W_hh in tensor memory (TMEM lane = gate row, two bf16 per column)
+        const int qq = warp & 3;
+        const uint32_t* wrow = reinterpret_cast<const uint32_t*>(a.w_gl + ((long long)dir * 4 * H + qq * H + r * UNITS + lane) * H);
+        for (int cb = 0; cb < H / 64; ++cb) {
+            uint32_t v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 t4 = *reinterpret_cast<const uint4*>(wrow + cb * 32 + i * 4);
+                v[i * 4 + 0] = t4.x; v[i * 4 + 1] = t4.y; v[i * 4 + 2] = t4.z; v[i * 4 + 3] = t4.w;
+            }
+            tmem_st32(tmem_w + ((uint32_t)(qq * 32) << 16) + cb * 32, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // every CTA of the cluster has initialised its barriers before anyone pushes data at it
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+    if (warp == 1) {
+        // ===== MMA issuer (whole warp walks the loop, one elected lane issues) =====
+        for (int s = 1; s < T; ++s) {
+            const int par = (s - 1) & 1;                          // buffer holding h_{s-1}
+            const uint32_t phase = (uint32_t)(((s - 1) >> 1) & 1);
+            for (int c = 0; c < CHAINS; ++c) {
+                const int slice = sg + c * a.bsg;
+                if (slice >= a.nslices) continue;
+                const uint32_t buf = h_sm + (uint32_t)(c * 2 + par) * TILE;
+                for (int hf = 0; hf < nhalf; ++hf) {
+                    if (lane == 0) mbar_arrive_expect_tx(hbar(c, par, hf), (uint32_t)(hf == 0 ? halfsrc : RS - halfsrc) * 2048u);
+                    __syncwarp();
+                    mbar_wait(hbar(c, par, hf), phase);
+                    if (lane == 0 && hf == 0) REC_STAMP(2);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int ks_lo = hf == 0 ? 0 : halfsrc * 2, ks_hi = hf == 0 ? (nhalf == 2 ? halfsrc * 2 : RS * 2) : RS * 2;    // 16-unit k-steps
+                        for (int ks = ks_lo; ks < ks_hi; ++ks) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((c * FWD_NACC + (ks & 3)) * NB_SLICE);
+                            const uint64_t bd = make_desc_k_noswz(buf + (uint32_t)ks * 1024u);
+                            umma_bf16_ts(d_tmem, tmem_w + ks * 8, bd, IDESC, ks >= 4 ? 1u : 0u);
+                        }
+                        if (ks_hi == RS * 2) umma_commit(tfull_bar(c));
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) REC_STAMP(3);
+            }
+        }
+    } else if (warp < 4) {
+        // ===== helper warps (0, 2, 3; CHAINS == 1): everything in global memory that is not the step-to-step dependency.
+        //   * stage the input projection x-gates of step s+1 in shared memory while step s runs (the epilogue then reads them
+        //     with LDS instead of waiting on 32 global loads per thread right when the tensor pipe delivers);
+        //   * copy the activated gates of step s from the exchange tile to global memory (backward reads them).
+        // The epilogue warps keep only the 24 stores per thread of h / c / out: after publishing, their global-memory
+        // instructions queue behind the outgoing DSMEM copies, and that queue -- not the exchange -- had become the critical path.
+        if (CHAINS == 1 && sg < a.nslices) {
+            const int hw = warp == 0 ? 0 : warp - 1;       // 0..2
+            const int b0 = sg * NB_SLICE;
+            const long long gstride = (long long)T * a.ndir * 4 * H;
+            float xr[43];
+            auto load_x = [&](int s2) {                    // rows pr = hw, hw+3, ... of step s2: pr = gate * 32 + batch row
+                const int t2 = (dir == 0) ? s2 : (T - 1 - s2);
+                const float* gb = a.gates + ((long long)t2 * a.ndir + dir) * 4 * H + r * UNITS + lane;
+#pragma unroll
+                for (int i = 0; i < 43; ++i) {
+                    const int pr = hw + 3 * i;
+                    const int qq = pr >> 5, n = pr & 31;
+                    xr[i] = (pr < 128 && b0 + n < a.B) ? gb[(long long)(b0 + n) * gstride + qq * H] : 0.f;
+                }
+            };
+            auto store_x = [&](int buf) {
+#pragma unroll
+                for (int i = 0; i < 43; ++i) {
+                    const int pr = hw + 3 * i;
+                    if (pr < 128) xgs[(buf * 128 + pr) * 32 + lane] = xr[i];
+                }
+            };
+            load_x(0);
+            store_x(0);
+            asm volatile("bar.arrive 4, 224;" ::: "memory");                      // x-gates of step 0 staged
+            for (int s = 0; s < T; ++s) {
+                const int t = (dir == 0) ? s : (T - 1 - s);
+                if (s + 1 < T) load_x(s + 1);                                      // in flight while waiting below
+                asm volatile("bar.sync 2, 224;" ::: "memory");                    // `ex` of step s complete (and xgs[s & 1] consumed)
+                if (a.save) {
+                    float* gb = a.gates + ((long long)t * a.ndir + dir) * 4 * H + r * UNITS + lane;
+                    for (int pr = hw; pr < 128; pr += 3) {
+                        const int qq = pr >> 5, n = pr & 31;
+                        if (b0 + n < a.B) gb[(long long)(b0 + n) * gstride + qq * H] = ex[pr * 32 + lane];
+                    }
+                }
+                asm volatile("bar.arrive 3, 224;" ::: "memory");                  // `ex` may be rewritten
+                if (s + 1 < T) {
+                    store_x((s + 1) & 1);                                          // that buffer was consumed at step s-1
+                    asm volatile("bar.arrive 4, 224;" ::: "memory");              // x-gates of step s+1 staged
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: one warp per gate =====
+        const int q = warp & 3, j = lane;          // gate q, unit r*32 + j
+        const int te = (warp - 4) * 32 + lane;     // 0..127
+        const int u = r * UNITS + j;
+        const bool helpers = CHAINS == 1;
+        float xg[32];
+        float cst[CHAINS][8];
+        int lenr[CHAINS][8];
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                cst[c][i] = 0.f;
+                const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
+                lenr[c][i] = (sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
+            }
+        for (int c = 0; c < CHAINS; ++c) {
+            const int slice = sg + c * a.bsg;
+            if (slice >= a.nslices) continue;
+            for (int i = 0; i < 8; ++i) {
+                const int b = slice * NB_SLICE + q * 8 + i;
+                if (b < a.B) {
+                    const long long o0 = (long long)b * brow + dir * H + u, o1 = o0 + (long long)(T + 1) * F;
+                    a.hs_pad[o0] = 0.f; a.cs_pad[o0] = 0.f; a.hs_pad[o1] = 0.f; a.cs_pad[o1] = 0.f;
+                }
+            }
+        }
+        for (int s = 0; s < T; ++s) {
+            const int t = (dir == 0) ? s : (T - 1 - s);
+#pragma unroll
+            for (int c = 0; c < CHAINS; ++c) {
+                const int slice = sg + c * a.bsg;
+                if (slice >= a.nslices) continue;
+                const int b0 = slice * NB_SLICE;
+                float* gbase = a.gates + ((long long)t * a.ndir + dir) * 4 * H + q * H + u;
+                const long long gstride = (long long)T * a.ndir * 4 * H;
+                if (helpers) {
+                    asm volatile("bar.sync 4, 224;" ::: "memory");              // the helper warps have staged this step's x-gates
+#pragma unroll
+                    for (int n = 0; n < 32; ++n) xg[n] = xgs[((s & 1) * 128 + q * 32 + n) * 32 + j];
+                } else {
+#pragma unroll
+                    for (int n = 0; n < 32; ++n) xg[n] = (b0 + n < a.B) ? gbase[(long long)(b0 + n) * gstride] : 0.f;
+                }
+                if (te == 0) REC_STAMP(4);
+                if (s > 0) {
+                    mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
+                    if (te == 0) REC_STAMP(5);
+                    tc_fence_after();
+#pragma unroll
+                    for (int acc = 0; acc < FWD_NACC; ++acc) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c * FWD_NACC + acc) * NB_SLICE), v);
+#pragma unroll
+                        for (int n = 0; n < 32; ++n) xg[n] += __uint_as_float(v[n]);
+                    }
+                    if (te == 0) REC_STAMP(6);
+                }
+                if (helpers && s > 0) asm volatile("bar.sync 3, 224;" ::: "memory");       // the savers are done with the previous step's `ex`
+#pragma unroll
+                for (int n = 0; n < 32; ++n) {
+                    const float act = (q == 2) ? tanh_fast(xg[n]) : sigmoid_fast(xg[n]);
+                    ex[(q * 32 + n) * 32 + j] = act;
+                    xg[n] = act;                                   // kept for the deferred save below (when there are no savers)
+                }
+                tc_fence_before();
+                // the bulk copies of the previous step must have finished READING the staging tile before it is rewritten
+                if (te < RS && s > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                named_bar_sync(1, 128);
+                if (helpers) asm volatile("bar.arrive 2, 224;" ::: "memory");               // `ex` complete: the savers may copy it out
+                if (te == 0) REC_STAMP(7);
+                float hh[8], cc[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int n = q * 8 + i;
+                    const float gi = ex[(0 * 32 + n) * 32 + j], gf = ex[(1 * 32 + n) * 32 + j];
+                    const float gg = ex[(2 * 32 + n) * 32 + j], go = ex[(3 * 32 + n) * 32 + j];
+                    const bool valid = t < lenr[c][i];
+                    cc[i] = 0.f; hh[i] = 0.f;
+                    if (valid) {
+                        cc[i] = fmaf(gf, cst[c][i], gi * gg);
+                        hh[i] = go * tanh_fast(cc[i]);
+                    }
+                    cst[c][i] = cc[i];
+                }
+                if (s + 1 < T) {
+                    // stage h_t (bf16) in core-matrix layout: core (kc = j/8, ng = q), row i, element j%8
+                    __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage_ptr + c * 2048 + (j >> 3) * 512 + q * 128) + (j & 7);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) st[i * 8] = __float2bfloat16(hh[i]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
+                named_bar_sync(1, 128);
+                if (te == 0) REC_STAMP(8);
+                if (s + 1 < T && te < RS) {
+                    // thread `te` pushes this CTA's slice into peer te's buffer for step s+1 (parity s&1) and signals its barrier
+                    const int par = s & 1;
+                    const uint32_t dst = mapa_u32(h_sm + (uint32_t)(c * 2 + par) * TILE + (uint32_t)r * 2048u, (uint32_t)te);
+                    const uint32_t rbar = mapa_u32(hbar(c, par, (nhalf == 2 && r >= halfsrc) ? 1 : 0), (uint32_t)te);
+                    bulk_copy_to_peer(dst, stage_sm + c * 2048, 2048u, rbar);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (te == 0) REC_STAMP(9);
+                // ... then what only backward / the next layer read; these stores overlap the exchange and the next step's UMMAs
+                if (a.save && !helpers) {
+#pragma unroll
+                    for (int n = 0; n < 32; ++n)
+                        if (b0 + n < a.B) gbase[(long long)(b0 + n) * gstride] = xg[n];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + q * 8 + i;
+                    if (b < a.B) {
+                        const long long so = (long long)b * brow + (long long)(t + 1) * F + dir * H + u;
+                        a.hs_pad[so] = hh[i];
+                        a.cs_pad[so] = cc[i];
+                        if (a.out) {
+                            const float m = a.mask ? a.mask[(long long)b * F + dir * H + u] : 1.f;
+                            a.out[((long long)b * T + t) * F + dir * H + u] = hh[i] * m;
+                        }
+                    }
+                }
+                if (te == 0) REC_STAMP(10);
+            }
+        }
+        if (te < RS) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    // no CTA of the cluster may exit while a peer's copy into its shared memory could still be in flight
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// =====================================================================================================================
 // "LL" exchange variant of the forward recurrence (the default).
 // The step-to-step exchange of h_t between the H/32 CTAs of a (direction, batch slice) group is the serial bottleneck of
 // the recurrence.  With a release/acquire counter it costs four dependent L2 round trips per step (writer: stores ->
@@ -926,6 +1240,38 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
         const int box[3] = {64, NB_SLICE, KBPt};      // one piece of the tile per TMA issue (see the kernel)
         rc = make_map_nd(&tmH, a.hbuf, 3, dims, strides, box);
         if (rc) return rc;
+    }
+    // ---- DSMEM exchange (default when one chain per CTA; LAS_REC_DSMEM=0 disables): one cluster per group, h_t pushed SM-to-SM.
+    // Measured 3.37 us/step against 3.54-3.64 for the counter/TMA exchange at B=96, H=512: the tensor pipe gets its operand
+    // ~1300 cycles earlier; the outgoing copies share the SM's memory pipeline with the epilogue's own loads / stores, which is
+    // why the helper warps take over the x-gate staging and the gate saves.  Clusters are independent of one
+    // another, so a launch that cannot place all of them at once is still correct; any launch failure falls back below. ----
+    {
+        const char* de = getenv("LAS_REC_DSMEM");
+        const size_t dsmem = 1024 + (size_t)p.chains * 2 * p.rs * 2048 + (size_t)p.chains * 2048 + 3 * 4 * 32 * 32 * 4 + 8 * 11 + 64;
+        // (two chains per CTA, i.e. more batch slices than clusters fit: measured far slower than the TMA kernel -- one chain only)
+        if ((!de || atoi(de) != 0) && p.chains == 1 && p.rs <= 16 && H <= 512 && dsmem <= (size_t)las_device_info()->max_smem_optin) {
+            auto kd = p.chains == 1 ? lstm_rec_fwd_dsm_kernel<1> : lstm_rec_fwd_dsm_kernel<2>;
+            cudaError_t e1 = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);
+            if (e1 == cudaSuccess && p.rs > 8) e1 = cudaFuncSetAttribute(kd, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e1 == cudaSuccess) {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(p.rs, p.bsg, ndir); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = dsmem; cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = p.rs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int nclusters = 0;
+                e1 = cudaOccupancyMaxActiveClusters(&nclusters, kd, &cfg);
+                if (e1 == cudaSuccess && nclusters < 1) e1 = cudaErrorInvalidConfiguration;
+                if (e1 == cudaSuccess) {
+                    LasProfScope prof(LAS_PROF_REC_FWD, stream, (double)T);
+                    e1 = cudaLaunchKernelEx(&cfg, kd, a);
+                    if (e1 == cudaSuccess) { las_count_launch(1); return LAS_OK; }
+                }
+            }
+            cudaGetLastError();         // fall through to the global-memory exchange
+        }
     }
     // LAS_REC_CLUSTER=1: one thread-block cluster per (direction, batch slice) group (<= 16 CTAs: non-portable size, every B200
     // GPC has >= 16 SMs) synchronised by the hardware cluster barrier instead of the counter.  Measured NOT faster: the

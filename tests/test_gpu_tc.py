@@ -135,14 +135,23 @@ def test_bf16_mode_logits_within_amp_tolerance(name):
     assert err < 2e-3
 
 
+@pytest.mark.parametrize('variant', ['default', 'tma', 'll', 'cluster'])
 @pytest.mark.parametrize('H,B,T,lens', [(64, 5, 9, [9, 3, 7, 1, 9]), (128, 40, 21, None), (512, 96, 12, None), (512, 130, 6, None)])
-def test_tc_recurrence_forward_vs_fp32_kernel(H, B, T, lens):
+def test_tc_recurrence_forward_vs_fp32_kernel(H, B, T, lens, variant, monkeypatch):
     """The tensor-pipe recurrence (bf16 operands) against the fp32 recurrence kernel on the same x-gates: same
     PackedSequence semantics (zeros past each length, reverse direction from each row's own end), values within bf16
     operand rounding."""
     import ctypes as C
     from las_b200 import _lib, functional as LF
     lib = _lib.load()
+    # exchange variants of the step-to-step h_t hand-off (DESIGN.md 4.2): counter + TMA (default), SM-to-SM bulk copies inside a
+    # cluster, tagged 8-byte words, hardware cluster barrier
+    for k in ('LAS_REC_DSMEM', 'LAS_REC_LL', 'LAS_REC_CLUSTER'):
+        monkeypatch.delenv(k, raising=False)
+    if variant != 'default':                     # default = DSMEM exchange when the batch gives one chain per CTA
+        monkeypatch.setenv('LAS_REC_DSMEM', '0')
+    if variant in ('ll', 'cluster'):
+        monkeypatch.setenv({'ll': 'LAS_REC_LL', 'cluster': 'LAS_REC_CLUSTER'}[variant], '1')
     rng = np.random.default_rng(H + B)
     if lens is None:
         lens = [T] + [int(v) for v in rng.integers(1, T + 1, size=B - 1)]
