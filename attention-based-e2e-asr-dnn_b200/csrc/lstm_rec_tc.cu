@@ -48,6 +48,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -487,6 +490,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
     auto hbar = [&](int c, int par, int half) { return bar_base + 8u * ((c * 2 + par) * 2 + half); };       // 8 barriers
     auto tfull_bar = [&](int c) { return bar_base + 8u * (8 + c); };
     const uint32_t tmem_slot = bar_base + 8u * 10;
+    // accumulators free again (epilogue -> MMA warp).  With the counter/TMA exchange the operand of step s+1 cannot arrive before
+    // this CTA has published step s, i.e. after its epilogue has read the accumulators; here the first half of the operand comes
+    // from OTHER CTAs only when r >= RS/2, so that ordering must be explicit.
+    auto tempty_bar = [&](int c) { return bar_base + 8u * (11 + c); };
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     uint8_t* stage_ptr = smem_raw + (stage_sm - smem_u32(smem_raw));
 
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 8; ++i) mbar_init(bar_base + 8u * i, 1);
-        for (int c = 0; c < MAX_CHAINS; ++c) mbar_init(tfull_bar(c), 1);
+        for (int c = 0; c < MAX_CHAINS; ++c) { mbar_init(tfull_bar(c), 1); mbar_init(tempty_bar(c), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const uint32_t tmem_cols = 512u;
@@ -542,6 +549,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
                 const int slice = sg + c * a.bsg;
                 if (slice >= a.nslices) continue;
                 const uint32_t buf = h_sm + (uint32_t)(c * 2 + par) * TILE;
+                if (s > 1) mbar_wait(tempty_bar(c), (uint32_t)(s & 1));          // the epilogue has read step s-1's accumulators
                 for (int hf = 0; hf < nhalf; ++hf) {
                     if (lane == 0) mbar_arrive_expect_tx(hbar(c, par, hf), (uint32_t)(hf == 0 ? halfsrc : RS - halfsrc) * 2048u);
                     __syncwarp();
@@ -669,6 +677,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
 #pragma unroll
                         for (int n = 0; n < 32; ++n) xg[n] += __uint_as_float(v[n]);
                     }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(c));
                     if (te == 0) REC_STAMP(6);
                 }
                 if (helpers && s > 0) asm volatile("bar.sync 3, 224;" ::: "memory");       // the savers are done with the previous step's `ex`
@@ -774,9 +785,6 @@ __device__ __forceinline__ uint4 ld_ll16(const unsigned long long* p) {
 __device__ __forceinline__ void st_ll8(unsigned long long* p, uint32_t data, uint32_t tag) {
     const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)data;
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -1248,7 +1256,7 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
     // another, so a launch that cannot place all of them at once is still correct; any launch failure falls back below. ----
     {
         const char* de = getenv("LAS_REC_DSMEM");
-        const size_t dsmem = 1024 + (size_t)p.chains * 2 * p.rs * 2048 + (size_t)p.chains * 2048 + 3 * 4 * 32 * 32 * 4 + 8 * 11 + 64;
+        const size_t dsmem = 1024 + (size_t)p.chains * 2 * p.rs * 2048 + (size_t)p.chains * 2048 + 3 * 4 * 32 * 32 * 4 + 8 * 13 + 64;
         // (two chains per CTA, i.e. more batch slices than clusters fit: measured far slower than the TMA kernel -- one chain only)
         if ((!de || atoi(de) != 0) && p.chains == 1 && p.rs <= 16 && H <= 512 && dsmem <= (size_t)las_device_info()->max_smem_optin) {
             auto kd = p.chains == 1 ? lstm_rec_fwd_dsm_kernel<1> : lstm_rec_fwd_dsm_kernel<2>;

@@ -136,7 +136,9 @@ def test_bf16_mode_logits_within_amp_tolerance(name):
 
 
 @pytest.mark.parametrize('variant', ['default', 'tma', 'll', 'cluster'])
-@pytest.mark.parametrize('H,B,T,lens', [(64, 5, 9, [9, 3, 7, 1, 9]), (128, 40, 21, None), (512, 96, 12, None), (512, 130, 6, None)])
+# the long sequences catch ordering races between a CTA's own epilogue and operands pushed by faster peers (seen once: T <= 21 passed)
+@pytest.mark.parametrize('H,B,T,lens', [(64, 5, 9, [9, 3, 7, 1, 9]), (128, 40, 21, None), (512, 96, 12, None), (512, 130, 6, None),
+                                        (128, 4, 400, None), (512, 96, 150, None)])
 def test_tc_recurrence_forward_vs_fp32_kernel(H, B, T, lens, variant, monkeypatch):
     """The tensor-pipe recurrence (bf16 operands) against the fp32 recurrence kernel on the same x-gates: same
     PackedSequence semantics (zeros past each length, reverse direction from each row's own end), values within bf16
@@ -194,7 +196,8 @@ def test_tc_recurrence_forward_vs_fp32_kernel(H, B, T, lens, variant, monkeypatc
     assert float(h1[:, 0].abs().max()) == 0.0 and float(h1[:, T + 1].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize('H,B,T,lens', [(64, 5, 9, [9, 3, 7, 1, 9]), (128, 40, 21, None), (512, 96, 12, None), (256, 130, 6, None)])
+@pytest.mark.parametrize('H,B,T,lens', [(64, 5, 9, [9, 3, 7, 1, 9]), (128, 40, 21, None), (512, 96, 12, None), (256, 130, 6, None),
+                                        (128, 4, 300, None)])
 def test_tc_recurrence_backward_vs_fp32_kernel(H, B, T, lens):
     """BPTT on the tensor pipe against the fp32 BPTT kernel on identical saved activations."""
     from las_b200 import _lib, functional as LF
