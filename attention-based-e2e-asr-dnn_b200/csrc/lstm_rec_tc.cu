@@ -1692,15 +1692,20 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
     const uint32_t a_sm = base;                                        // KB x [128 rows(u) x 128 B]  resident W_hh^T tile
     const uint32_t b_sm = a_sm + (WTMEM ? 0 : KB * 16384);             // chains x KB x [32 rows(b) x 128 B]
     const uint32_t part_off = (b_sm - smem_u32(smem_raw)) + a.chains * KB * 4096;
-    float* part0 = reinterpret_cast<float*>(smem_raw + part_off);      // [2][32][PART_LD]: ping-pong, so one cluster barrier per step suffices
+    // partial-sum exchange inside the 4-CTA cluster, pushed (no cluster barrier, no remote loads): stg[parity][piece q] = this
+    // CTA's partial for the 32 units CTA q finalises ([32 rows][32 units] fp32, 4 KB), rcv[parity][src] = what the four CTAs sent me
+    float* part0 = reinterpret_cast<float*>(smem_raw + part_off);      // stg: [2][4][32][32]
+    float* rcv0 = part0 + 2 * 4 * 1024;                                // rcv: [2][4][32][32]
     const uint32_t part_saddr0 = smem_u32(smem_raw) + part_off;
-    const uint32_t bar_base = (part_saddr0 + 2 * 32 * PART_LD * 4 + 15u) & ~15u;
+    const uint32_t rcv_saddr0 = part_saddr0 + 2 * 4 * 4096;
+    const uint32_t bar_base = (part_saddr0 + 4 * 4 * 4096 + 15u) & ~15u;
     auto full_bar = [&](int c) { return bar_base + 8u * c; };
     auto tfull_bar = [&](int c) { return bar_base + 8u * (MAX_CHAINS + c); };
     const uint32_t wbar = bar_base + 8u * (2 * MAX_CHAINS);
     const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_CHAINS + 1);
     const int NP = rec_pieces(KB), KBP = KB / NP;                 // the dG tile arrives in pieces (see the forward kernel)
     auto piece_bar = [&](int c, int pc) { return pc == 0 ? full_bar(c) : bar_base + 8u * (2 * MAX_CHAINS + 2 + (pc - 1) * MAX_CHAINS + c); };
+    auto rbar = [&](int par) { return bar_base + 8u * (2 * MAX_CHAINS + 2 + 3 * MAX_CHAINS + par); };      // partials received
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int kq = (int)cluster_ctarank();            // gate handled by this CTA's reduction slice
@@ -1719,6 +1724,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
             for (int pc = 0; pc < 4; ++pc) mbar_init(piece_bar(c, pc), 1);
         }
         mbar_init(wbar, 1);
+        mbar_init(rbar(0), 1); mbar_init(rbar(1), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // TMEM map: BWD_NACC independent accumulators per chain first, then (WTMEM) the resident W_hh^T tile (H/2 columns)
@@ -1753,6 +1759,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
         tc_fence_after();
     }
 
+    cluster_sync_all();              // every CTA of the cluster has initialised its barriers before a peer pushes partials at it
+
     // per-thread state of the epilogue role (declared for all so the step loop below is shared by every warp)
     const int q = warp & 3, j = lane;
     const int te = (warp - 4) * 32 + lane;
@@ -1783,7 +1791,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
     }
 
     // Every warp walks the same (step, chain) sequence: the cluster barrier of each iteration needs all threads of all 4 CTAs.
-    int iter = 0;
+    int iter = 0, riter = 0;
     for (int s = 0; s < T; ++s) {
         const int t = (dir == 0) ? (T - 1 - s) : s;
         const int t_prev = (dir == 0) ? (T - s) : (s - 1);
@@ -1793,8 +1801,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
             const int slice = sg + c * a.bsg;
             if (c >= a.chains || slice >= a.nslices) continue;          // uniform across the cluster (same sg, chains)
             const int b0 = slice * NB_SLICE;
-            float* part = part0 + (iter & 1) * 32 * PART_LD;
-            const uint32_t part_saddr = part_saddr0 + (uint32_t)((iter & 1) * 32 * PART_LD * 4);
+            const int rpar = riter & 1;                                   // parity of this reduce-iteration (s > 0 only)
+            const uint32_t rphase = (uint32_t)((riter >> 1) & 1);
+            if (s > 0) ++riter;
             ++iter;
             float gi[8], gf[8], gg[8], go[8], ct[8], cp[8], dh[8], mk[8], rec[8];
             bool valid[8];
@@ -1876,32 +1885,39 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
 #pragma unroll
                         for (int n = 0; n < 32; ++n) accv[n] = acc ? accv[n] + __uint_as_float(v[n]) : __uint_as_float(v[n]);
                     }
-                    // TMEM lane = unit (32q + lane) of the block, column = batch row: park the partial as part[b][unit]
+                    // TMEM lane = unit (32q + lane) of the block, column = batch row.  Warp q holds exactly the 32 units CTA q of the
+                    // cluster finalises: stage them as [row][unit] and push the 4 KB piece into CTA q's receive buffer
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the piece staged two iterations ago has been read
+                    __syncwarp();
+                    float* stg = part0 + (rpar * 4 + q) * 1024;
 #pragma unroll
-                    for (int n = 0; n < 32; ++n) part[n * PART_LD + q * 32 + lane] = accv[n];
+                    for (int n = 0; n < 32; ++n) stg[n * 32 + lane] = accv[n];
                     tc_fence_before();
-                    if (te == 0) REC_STAMP(6);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const uint32_t dst = mapa_u32(rcv_saddr0 + (uint32_t)((rpar * 4 + kq) * 4096), (uint32_t)q);
+                        bulk_copy_to_peer(dst, part_saddr0 + (uint32_t)((rpar * 4 + q) * 4096), 4096u, mapa_u32(rbar(rpar), (uint32_t)q));
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (te == 0) {
+                        mbar_arrive_expect_tx(rbar(rpar), 4u * 4096u);         // the four pieces for my 32 units
+                        REC_STAMP(6);
+                    }
                 }
             }
             if (s > 0) {
-                cluster_sync_all();                                   // all four gate-partials are in shared memory
-                if (warp == 4 && lane == 0) REC_STAMP(7);
                 if (warp >= 4) {
-                    // all 32 remote loads are issued before the first add (an in-order warp would otherwise pay the DSMEM latency
-                    // once per row)
-                    float p4[8][4];
+                    mbar_wait(rbar(rpar), rphase);
+                    if (te == 0) REC_STAMP(7);
+                    const float* rcv = rcv0 + rpar * 4 * 1024;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const uint32_t off = part_saddr + (uint32_t)(((q * 8 + i) * PART_LD + kq * 32 + j) * 4);
-#pragma unroll
-                        for (int src = 0; src < 4; ++src) p4[i][src] = ld_dsmem_f32(off, (uint32_t)src);
+                        const int o = (q * 8 + i) * 32 + j;
+                        rec[i] = (rcv[o] + rcv[1024 + o]) + (rcv[2048 + o] + rcv[3072 + o]);
                     }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) rec[i] = (p4[i][0] + p4[i][1]) + (p4[i][2] + p4[i][3]);
                 }
                 if (warp == 4 && lane == 0) REC_STAMP(11);
-                // no second barrier: the partial tile ping-pongs, and a peer can only be two iterations ahead of my reads
-                // after I have passed the next iteration's barrier
             }
             if (warp >= 4) {
 #pragma unroll
@@ -1999,7 +2015,7 @@ static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, co
     const int KB = H / 64;
     const char* wt_env = getenv("LAS_REC_WTMEM");
     const bool wtmem = (wt_env ? atoi(wt_env) != 0 : true) && H <= 512;
-    const size_t smem = 1024 + (wtmem ? 0 : (size_t)KB * 16384) + (size_t)chains * KB * 4096 + 2 * 32 * PART_LD * 4 + 16 + 8 * (2 * MAX_CHAINS + 2) + 64;
+    const size_t smem = 1024 + (wtmem ? 0 : (size_t)KB * 16384) + (size_t)chains * KB * 4096 + 4 * 4 * 4096 + 16 + 8 * (2 * MAX_CHAINS + 2 + 3 * MAX_CHAINS + 2) + 64;
     if (smem > (size_t)di->max_smem_optin) return LAS_ERR_UNSUPPORTED;
     RecTcBwdArgs a{};
     a.w_t = (const __nv_bfloat16*)w_hh_t_bf16;
