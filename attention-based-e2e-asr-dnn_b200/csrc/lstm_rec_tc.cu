@@ -1766,6 +1766,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
     const int te = (warp - 4) * 32 + lane;
     const int u = ub * 128 + kq * 32 + j;              // the unit this thread finalises (epilogue warps)
     float dcst[MAX_CHAINS][8];
+    float mkr[MAX_CHAINS][8];                          // locked-dropout mask of this thread's (row, unit): constant over time
+    float cnext[MAX_CHAINS][8];                        // c_{t-1} loaded at this step = c_t of the next step (time runs backwards)
     float dbacc[MAX_CHAINS][4];                        // bias-gradient partial sums of this thread's unit over its 8 rows, all steps
     int lenr[MAX_CHAINS][8];
 #pragma unroll
@@ -1780,6 +1782,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
             dcst[c][i] = 0.f;
             const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
             lenr[c][i] = (warp >= 4 && c < a.chains && sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
+            mkr[c][i] = (a.mask && lenr[c][i] > 0) ? a.mask[(long long)b * F + dir * H + u] : 1.f;
+            cnext[c][i] = 0.f;
         }
 
     if (!WTMEM) {
@@ -1866,9 +1870,10 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                     const int bc = b < a.B ? b : a.B - 1;
                     const float* gp = a.gates + (((long long)bc * T + t) * a.ndir + dir) * G4 + u;
                     gi[i] = gp[0]; gf[i] = gp[H]; gg[i] = gp[2 * H]; go[i] = gp[3 * H];
-                    ct[i] = a.cs_pad[(long long)bc * brow + (long long)fcur * F + dir * H + u];
+                    // c_t: carried over from the previous step's c_{t-1} load (first step: loaded)
+                    ct[i] = (s == 0) ? a.cs_pad[(long long)bc * brow + (long long)fcur * F + dir * H + u] : cnext[c][i];
                     cp[i] = a.cs_pad[(long long)bc * brow + (long long)fprev * F + dir * H + u];
-                    mk[i] = a.mask ? a.mask[(long long)bc * F + dir * H + u] : 1.f;
+                    mk[i] = mkr[c][i];
                     dh[i] = a.dout[((long long)bc * T + t) * F + dir * H + u];
                     rec[i] = 0.f;
                 }
@@ -1935,6 +1940,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                         dcn = dct * gf[i];
                     }
                     dcst[c][i] = dcn;
+                    cnext[c][i] = cp[i];
                     // what the peers' next step reads: bf16 d(pre-activation) in the compact exchange buffer
                     __nv_bfloat16* xp = a.dgx + ((long long)((dir * 2 + (s & 1)) * 4) * a.Bpad + b) * H + u;
                     const long long gst = (long long)a.Bpad * H;
