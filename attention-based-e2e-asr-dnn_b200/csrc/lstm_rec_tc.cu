@@ -1762,29 +1762,33 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
     cluster_sync_all();              // every CTA of the cluster has initialised its barriers before a peer pushes partials at it
 
     // per-thread state of the epilogue role (declared for all so the step loop below is shared by every warp)
+    // Epilogue ownership: thread (warp q, lane) finalises FOUR consecutive units u0..u0+3 (u0 = block base + 4*(lane & 7)) for TWO
+    // batch rows (q*8 + 2*(lane >> 3) + {0, 1}), so that every global access of the pointwise backward is a 128-bit one: a quarter
+    // of the memory instructions of a one-unit-per-lane mapping (their issue rate, not the exchange, had become the critical path).
     const int q = warp & 3, j = lane;
     const int te = (warp - 4) * 32 + lane;
-    const int u = ub * 128 + kq * 32 + j;              // the unit this thread finalises (epilogue warps)
-    float dcst[MAX_CHAINS][8];
-    float mkr[MAX_CHAINS][8];                          // locked-dropout mask of this thread's (row, unit): constant over time
-    float cnext[MAX_CHAINS][8];                        // c_{t-1} loaded at this step = c_t of the next step (time runs backwards)
-    float dbacc[MAX_CHAINS][4];                        // bias-gradient partial sums of this thread's unit over its 8 rows, all steps
-    int lenr[MAX_CHAINS][8];
+    const int jj = lane & 7, rr = lane >> 3;
+    const int u0 = ub * 128 + kq * 32 + 4 * jj;        // first of the 4 units this thread finalises
+    const int rl0 = q * 8 + rr * 2;                    // first of its 2 batch rows inside the 32-row slice
+    float4 dcst[MAX_CHAINS][2];
+    float4 mkr[MAX_CHAINS][2];                         // locked-dropout mask: constant over time
+    float4 cnext[MAX_CHAINS][2];                       // c_{t-1} loaded at this step = c_t of the next step (time runs backwards)
+    float4 dbacc[MAX_CHAINS][4];                       // bias-gradient partial sums (gate x 4 units) over this thread's rows, all steps
+    int lenr[MAX_CHAINS][2];
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < MAX_CHAINS; ++c) {
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) dbacc[c][gq] = 0.f;
-    }
+        for (int gq = 0; gq < 4; ++gq) dbacc[c][gq] = z4;
 #pragma unroll
-    for (int c = 0; c < MAX_CHAINS; ++c)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            dcst[c][i] = 0.f;
-            const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
+        for (int i = 0; i < 2; ++i) {
+            dcst[c][i] = z4; cnext[c][i] = z4;
+            const int b = (sg + c * a.bsg) * NB_SLICE + rl0 + i;
             lenr[c][i] = (warp >= 4 && c < a.chains && sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
-            mkr[c][i] = (a.mask && lenr[c][i] > 0) ? a.mask[(long long)b * F + dir * H + u] : 1.f;
-            cnext[c][i] = 0.f;
+            mkr[c][i] = (a.mask && lenr[c][i] > 0) ? *reinterpret_cast<const float4*>(a.mask + (long long)b * F + dir * H + u0)
+                                                   : make_float4(1.f, 1.f, 1.f, 1.f);
         }
+    }
 
     if (!WTMEM) {
         if (warp == 0 && lane == 0) {
@@ -1809,8 +1813,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
             const uint32_t rphase = (uint32_t)((riter >> 1) & 1);
             if (s > 0) ++riter;
             ++iter;
-            float gi[8], gf[8], gg[8], go[8], ct[8], cp[8], dh[8], mk[8], rec[8];
-            bool valid[8];
+            float4 gi[2], gf[2], gg[2], go[2], ct[2], cp[2], dh[2], rec[2];
+            bool valid[2];
             if (warp == 0) {
                 if (lane == 0 && s > 0) {
                     const unsigned* ctr = a.ctr + dir * a.nslices + slice;
@@ -1861,21 +1865,21 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
             } else if (warp >= 4) {
                 // operands of the pointwise backward for this thread's unit, issued before waiting on the tensor pipe
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int b = b0 + q * 8 + i;
+                for (int i = 0; i < 2; ++i) {
+                    const int b = b0 + rl0 + i;
                     valid[i] = t < lenr[c][i];
-                    // pure loads, no branches and no arithmetic: an in-order warp would otherwise stall on the first use and
-                    // serialise the eight rows' HBM latencies.  Rows past B are clamped to a valid address; invalid rows are
-                    // zeroed in the pointwise step.
+                    // pure 128-bit loads, no branches: rows past B are clamped to a valid address; invalid rows are zeroed in the
+                    // pointwise step
                     const int bc = b < a.B ? b : a.B - 1;
-                    const float* gp = a.gates + (((long long)bc * T + t) * a.ndir + dir) * G4 + u;
-                    gi[i] = gp[0]; gf[i] = gp[H]; gg[i] = gp[2 * H]; go[i] = gp[3 * H];
+                    const float* gp = a.gates + (((long long)bc * T + t) * a.ndir + dir) * G4 + u0;
+                    gi[i] = *reinterpret_cast<const float4*>(gp); gf[i] = *reinterpret_cast<const float4*>(gp + H);
+                    gg[i] = *reinterpret_cast<const float4*>(gp + 2 * H); go[i] = *reinterpret_cast<const float4*>(gp + 3 * H);
                     // c_t: carried over from the previous step's c_{t-1} load (first step: loaded)
-                    ct[i] = (s == 0) ? a.cs_pad[(long long)bc * brow + (long long)fcur * F + dir * H + u] : cnext[c][i];
-                    cp[i] = a.cs_pad[(long long)bc * brow + (long long)fprev * F + dir * H + u];
-                    mk[i] = mkr[c][i];
-                    dh[i] = a.dout[((long long)bc * T + t) * F + dir * H + u];
-                    rec[i] = 0.f;
+                    if (s == 0) ct[i] = *reinterpret_cast<const float4*>(a.cs_pad + (long long)bc * brow + (long long)fcur * F + dir * H + u0);
+                    else ct[i] = cnext[c][i];
+                    cp[i] = *reinterpret_cast<const float4*>(a.cs_pad + (long long)bc * brow + (long long)fprev * F + dir * H + u0);
+                    dh[i] = *reinterpret_cast<const float4*>(a.dout + ((long long)bc * T + t) * F + dir * H + u0);
+                    rec[i] = z4;
                 }
                 if (te == 0) REC_STAMP(4);
                 if (s > 0) {
@@ -1917,54 +1921,75 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                     if (te == 0) REC_STAMP(7);
                     const float* rcv = rcv0 + rpar * 4 * 1024;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int o = (q * 8 + i) * 32 + j;
-                        rec[i] = (rcv[o] + rcv[1024 + o]) + (rcv[2048 + o] + rcv[3072 + o]);
+                    for (int i = 0; i < 2; ++i) {
+                        const int o = (rl0 + i) * 32 + 4 * jj;
+                        const float4 p0 = *reinterpret_cast<const float4*>(rcv + o), p1 = *reinterpret_cast<const float4*>(rcv + 1024 + o);
+                        const float4 p2 = *reinterpret_cast<const float4*>(rcv + 2048 + o), p3 = *reinterpret_cast<const float4*>(rcv + 3072 + o);
+                        rec[i] = make_float4((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z),
+                                             (p0.w + p1.w) + (p2.w + p3.w));
                     }
                 }
                 if (warp == 4 && lane == 0) REC_STAMP(11);
             }
             if (warp >= 4) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int b = b0 + q * 8 + i;
-                    float dai = 0.f, daf = 0.f, dag = 0.f, dao = 0.f, dcn = 0.f;
-                    if (valid[i]) {
-                        const float tcv = tanh_fast(ct[i]);
-                        const float dhv = fmaf(dh[i], mk[i], rec[i]);
-                        const float dct = fmaf(dhv * go[i], 1.f - tcv * tcv, dcst[c][i]);
-                        dai = dct * gg[i] * gi[i] * (1.f - gi[i]);
-                        daf = dct * cp[i] * gf[i] * (1.f - gf[i]);
-                        dag = dct * gi[i] * (1.f - gg[i] * gg[i]);
-                        dao = dhv * tcv * go[i] * (1.f - go[i]);
-                        dcn = dct * gf[i];
+                auto pw = [&](float gi_, float gf_, float gg_, float go_, float ct_, float cp_, float dh_, float mk_, float rec_, float dc_,
+                              bool ok, float& dai, float& daf, float& dag, float& dao, float& dcn) {
+                    dai = daf = dag = dao = dcn = 0.f;
+                    if (ok) {
+                        const float tcv = tanh_fast(ct_);
+                        const float dhv = fmaf(dh_, mk_, rec_);
+                        const float dct = fmaf(dhv * go_, 1.f - tcv * tcv, dc_);
+                        dai = dct * gg_ * gi_ * (1.f - gi_);
+                        daf = dct * cp_ * gf_ * (1.f - gf_);
+                        dag = dct * gi_ * (1.f - gg_ * gg_);
+                        dao = dhv * tcv * go_ * (1.f - go_);
+                        dcn = dct * gf_;
                     }
-                    dcst[c][i] = dcn;
+                };
+                auto pack4 = [](const float4& v) {
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                    uint2 r;
+                    r.x = *reinterpret_cast<const uint32_t*>(&lo); r.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    return r;
+                };
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int b = b0 + rl0 + i;
+                    float4 dI, dF, dG, dO, dC;
+                    pw(gi[i].x, gf[i].x, gg[i].x, go[i].x, ct[i].x, cp[i].x, dh[i].x, mkr[c][i].x, rec[i].x, dcst[c][i].x, valid[i], dI.x, dF.x, dG.x, dO.x, dC.x);
+                    pw(gi[i].y, gf[i].y, gg[i].y, go[i].y, ct[i].y, cp[i].y, dh[i].y, mkr[c][i].y, rec[i].y, dcst[c][i].y, valid[i], dI.y, dF.y, dG.y, dO.y, dC.y);
+                    pw(gi[i].z, gf[i].z, gg[i].z, go[i].z, ct[i].z, cp[i].z, dh[i].z, mkr[c][i].z, rec[i].z, dcst[c][i].z, valid[i], dI.z, dF.z, dG.z, dO.z, dC.z);
+                    pw(gi[i].w, gf[i].w, gg[i].w, go[i].w, ct[i].w, cp[i].w, dh[i].w, mkr[c][i].w, rec[i].w, dcst[c][i].w, valid[i], dI.w, dF.w, dG.w, dO.w, dC.w);
+                    dcst[c][i] = dC;
                     cnext[c][i] = cp[i];
-                    // what the peers' next step reads: bf16 d(pre-activation) in the compact exchange buffer
-                    __nv_bfloat16* xp = a.dgx + ((long long)((dir * 2 + (s & 1)) * 4) * a.Bpad + b) * H + u;
+                    // what the peers' next step reads: bf16 d(pre-activation) in the compact exchange buffer, 4 units per 64-bit store
+                    __nv_bfloat16* xp = a.dgx + ((long long)((dir * 2 + (s & 1)) * 4) * a.Bpad + b) * H + u0;
                     const long long gst = (long long)a.Bpad * H;
-                    xp[0] = __float2bfloat16(dai); xp[gst] = __float2bfloat16(daf);
-                    xp[2 * gst] = __float2bfloat16(dag); xp[3 * gst] = __float2bfloat16(dao);
-                    gi[i] = dai; gf[i] = daf; gg[i] = dag; go[i] = dao;
-                    dbacc[c][0] += dai; dbacc[c][1] += daf; dbacc[c][2] += dag; dbacc[c][3] += dao;
+                    *reinterpret_cast<uint2*>(xp) = pack4(dI); *reinterpret_cast<uint2*>(xp + gst) = pack4(dF);
+                    *reinterpret_cast<uint2*>(xp + 2 * gst) = pack4(dG); *reinterpret_cast<uint2*>(xp + 3 * gst) = pack4(dO);
+                    gi[i] = dI; gf[i] = dF; gg[i] = dG; go[i] = dO;
+                    dbacc[c][0].x += dI.x; dbacc[c][0].y += dI.y; dbacc[c][0].z += dI.z; dbacc[c][0].w += dI.w;
+                    dbacc[c][1].x += dF.x; dbacc[c][1].y += dF.y; dbacc[c][1].z += dF.z; dbacc[c][1].w += dF.w;
+                    dbacc[c][2].x += dG.x; dbacc[c][2].y += dG.y; dbacc[c][2].z += dG.z; dbacc[c][2].w += dG.w;
+                    dbacc[c][3].x += dO.x; dbacc[c][3].y += dO.y; dbacc[c][3].z += dO.z; dbacc[c][3].w += dO.w;
                 }
                 named_bar_sync(1, 128);
                 if (te == 0) REC_STAMP(8);
                 if (te == 0 && s + 1 < T) red_release_gpu_add(a.ctr + dir * a.nslices + slice, 1u);
                 if (te == 0) REC_STAMP(9);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int b = b0 + q * 8 + i;
+                for (int i = 0; i < 2; ++i) {
+                    const int b = b0 + rl0 + i;
                     if (b >= a.B) continue;
                     if (!a.dbp) {
-                        float* gp = a.gates + ((((long long)b * T + t) * a.ndir + dir) * G4) + u;
-                        gp[0] = gi[i]; gp[H] = gf[i]; gp[2 * H] = gg[i]; gp[3 * H] = go[i];
+                        float* gp = a.gates + ((((long long)b * T + t) * a.ndir + dir) * G4) + u0;
+                        *reinterpret_cast<float4*>(gp) = gi[i]; *reinterpret_cast<float4*>(gp + H) = gf[i];
+                        *reinterpret_cast<float4*>(gp + 2 * H) = gg[i]; *reinterpret_cast<float4*>(gp + 3 * H) = go[i];
                     }
                     // the (B*T, NG) bf16 copy the dX / dW GEMMs consume
-                    __nv_bfloat16* bp = a.dgb + ((long long)b * T + t) * NG + dir * G4 + u;
-                    bp[0] = __float2bfloat16(gi[i]); bp[H] = __float2bfloat16(gf[i]);
-                    bp[2 * H] = __float2bfloat16(gg[i]); bp[3 * H] = __float2bfloat16(go[i]);
+                    __nv_bfloat16* bp = a.dgb + ((long long)b * T + t) * NG + dir * G4 + u0;
+                    *reinterpret_cast<uint2*>(bp) = pack4(gi[i]); *reinterpret_cast<uint2*>(bp + H) = pack4(gf[i]);
+                    *reinterpret_cast<uint2*>(bp + 2 * H) = pack4(gg[i]); *reinterpret_cast<uint2*>(bp + 3 * H) = pack4(go[i]);
                 }
                 if (te == 0) REC_STAMP(10);
             }
@@ -1974,12 +1999,12 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
         // bias gradients: the four epilogue warps hold partial sums of the same 32 units over different batch rows; add them up in
         // a fixed order and store this (direction, batch slice)'s row -- the host sums the few slice rows (deterministic)
         __syncthreads();
-        float* red = part0;                                           // [chain][q][gate][32] floats, the partial tiles are idle now
+        float* red = part0;                   // [chain][q][rr][gate][32 units] floats (8 K floats; the partial tiles are idle now)
         if (warp >= 4) {
 #pragma unroll
             for (int c = 0; c < MAX_CHAINS; ++c)
 #pragma unroll
-                for (int gq = 0; gq < 4; ++gq) red[((c * 4 + q) * 4 + gq) * 32 + j] = dbacc[c][gq];
+                for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<float4*>(red + ((((c * 4 + q) * 4 + rr) * 4 + gq) * 32) + 4 * jj) = dbacc[c][gq];
         }
         __syncthreads();
         if (warp == 4) {
@@ -1988,9 +2013,10 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
                 if (slice >= a.nslices) continue;
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) {
-                    const float v = (red[((c * 4 + 0) * 4 + gq) * 32 + j] + red[((c * 4 + 1) * 4 + gq) * 32 + j]) +
-                                    (red[((c * 4 + 2) * 4 + gq) * 32 + j] + red[((c * 4 + 3) * 4 + gq) * 32 + j]);
-                    a.dbp[((long long)(dir * a.nslices + slice) * 4 + gq) * H + u] = v;
+                    float v = 0.f;
+#pragma unroll
+                    for (int pq = 0; pq < 16; ++pq) v += red[(((c * 16 + pq) * 4 + gq) * 32) + j];      // fixed order over (q, rr)
+                    a.dbp[((long long)(dir * a.nslices + slice) * 4 + gq) * H + ub * 128 + kq * 32 + j] = v;
                 }
             }
         }
