@@ -1568,6 +1568,8 @@ extern "C" int las_transpose_cast_bf16(const float* src, void* dst, int batch, i
 
 static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16, const int* lens,
                           const float* drop_mask, int B, int T, int H, int ndir, void* ws, cudaStream_t st, void* stream, float* dbp);
+static int launch_bwd_dsm(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16, const int* lens,
+                          const float* drop_mask, int B, int T, int H, int ndir, cudaStream_t st, void* stream, float* dbp);
 
 static int rec_bwd_tc_impl(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16,
                            const int* lens, const float* drop_mask, int B, int T, int H, int ndir, void* ws, size_t ws_bytes,
@@ -1615,6 +1617,8 @@ static int rec_bwd_tc_impl(const float* dout, float* gates, void* dgates_bf16, c
     {
         const char* e = getenv("LAS_REC_BWD_KSPLIT");
         if (!e || atoi(e) != 0) {
+            rc = launch_bwd_dsm(dout, gates, dgates_bf16, cs_pad, w_hh_t_bf16, lens, drop_mask, B, T, H, ndir, st, stream, dbp);
+            if (rc == LAS_OK) return LAS_OK;
             rc = launch_bwd_tc2(dout, gates, dgates_bf16, cs_pad, w_hh_t_bf16, lens, drop_mask, B, T, H, ndir, ws, st, stream, dbp);
             if (rc == LAS_OK) return LAS_OK;          // otherwise fall through to the streaming variant
             if (dbp) return rc;                       // (the streaming variant has no bias-gradient output)
@@ -2030,7 +2034,398 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// BPTT with the SM-to-SM exchange (default when one chain per CTA): the whole (direction, batch slice) group -- 4 gate CTAs x
+// H/128 unit blocks -- is ONE thread-block cluster; the d(pre-activation) slices are pushed into the consumers' operand
+// buffers with bulk async DSMEM copies exactly like h_t in lstm_rec_fwd_dsm_kernel (no counter, no release fence, no TMA fetch,
+// no global exchange buffer), and the gate-partial reduction uses the same push.  W_hh^T tile resident in tensor memory.
+// Cluster rank = ub * 4 + kq.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const RecTcBwdArgs a) {
+    constexpr bool WTMEM = true;
+    extern __shared__ uint8_t smem_raw[];
+    const int H = a.H, T = a.T, KB = H / 64;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int RS = 4 * (H / 128);                                      // CTAs of the group = cluster size
+    const uint32_t TILE = (uint32_t)RS * 2048u;                        // 32 rows x H bf16, core-matrix (no-swizzle) layout
+    const uint32_t b_sm = base;                                        // [parity][TILE] operand buffers
+    const uint32_t xst_sm = b_sm + 2 * TILE;                           // [4 gates][2 KB]: this CTA's dG slices, staged for the push
+    uint8_t* xst_ptr = smem_raw + (xst_sm - smem_u32(smem_raw));
+    const uint32_t part_off = (xst_sm - smem_u32(smem_raw)) + 4 * 2048;
+    // partial-sum exchange inside the 4-CTA cluster, pushed (no cluster barrier, no remote loads): stg[parity][piece q] = this
+    // CTA's partial for the 32 units CTA q finalises ([32 rows][32 units] fp32, 4 KB), rcv[parity][src] = what the four CTAs sent me
+    float* part0 = reinterpret_cast<float*>(smem_raw + part_off);      // stg: [2][4][32][32]
+    float* rcv0 = part0 + 2 * 4 * 1024;                                // rcv: [2][4][32][32]
+    const uint32_t part_saddr0 = smem_u32(smem_raw) + part_off;
+    const uint32_t rcv_saddr0 = part_saddr0 + 2 * 4 * 4096;
+    const uint32_t bar_base = (part_saddr0 + 4 * 4 * 4096 + 15u) & ~15u;
+    auto full_bar = [&](int c) { return bar_base + 8u * c; };
+    auto tfull_bar = [&](int c) { return bar_base + 8u * (MAX_CHAINS + c); };
+    const uint32_t wbar = bar_base + 8u * (2 * MAX_CHAINS);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_CHAINS + 1);
+    const int NP = rec_pieces(KB), KBP = KB / NP;                 // the dG tile arrives in pieces (see the forward kernel)
+    auto piece_bar = [&](int c, int pc) { return pc == 0 ? full_bar(c) : bar_base + 8u * (2 * MAX_CHAINS + 2 + (pc - 1) * MAX_CHAINS + c); };
+    auto rbar = [&](int par) { return bar_base + 8u * (2 * MAX_CHAINS + 2 + 3 * MAX_CHAINS + par); };      // partials received
+    auto hbar = [&](int par, int half) { return bar_base + 8u * (2 * MAX_CHAINS + 2 + 3 * MAX_CHAINS + 2 + par * 2 + half); };   // operand halves landed
+    const uint32_t tempty = bar_base + 8u * (2 * MAX_CHAINS + 2 + 3 * MAX_CHAINS + 6);                     // accumulators read (epilogue -> MMA)
+    const int halfsrc = RS / 2;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int crank = (int)cluster_ctarank();         // == blockIdx.x: the cluster spans the whole group
+    const int kq = crank & 3;                         // gate handled by this CTA's reduction slice
+    const int ub = crank >> 2;                        // 128-unit block
+    const int sg = blockIdx.y, dir = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int F = a.ndir * H, G4 = 4 * H, NG = a.ndir * G4;
+    const long long brow = (long long)(T + 2) * F;
+    const unsigned group = (unsigned)(4 * (H / 128));  // CTAs sharing one (direction, batch slice)
+
+    if (warp == 0 && lane == 0) {
+        for (int c = 0; c < MAX_CHAINS; ++c) {
+            mbar_init(tfull_bar(c), 1);
+            for (int pc = 0; pc < 4; ++pc) mbar_init(piece_bar(c, pc), 1);
+        }
+        mbar_init(wbar, 1);
+        mbar_init(rbar(0), 1); mbar_init(rbar(1), 1);
+        for (int i = 0; i < 4; ++i) mbar_init(hbar(i >> 1, i & 1), 1);
+        mbar_init(tempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // TMEM map: BWD_NACC independent accumulators per chain first, then (WTMEM) the resident W_hh^T tile (H/2 columns)
+    const uint32_t tmem_cols = WTMEM ? 512u : 256u;
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t tmem_w = tmem_base + MAX_CHAINS * BWD_NACC * NB_SLICE;
+    if (WTMEM) {
+        if (warp >= 4) {
+            // A operand in tensor memory: TMEM lane = unit row of the block, column pair = two consecutive k (gate rows of gate kq)
+            const int qq = warp & 3;
+            const uint32_t* wrow = reinterpret_cast<const uint32_t*>(a.w_t + ((long long)(dir * H + ub * 128 + qq * 32 + lane)) * G4 + kq * H);
+            for (int cb = 0; cb < H / 64; ++cb) {
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 t4 = *reinterpret_cast<const uint4*>(wrow + cb * 32 + i * 4);
+                    v[i * 4 + 0] = t4.x; v[i * 4 + 1] = t4.y; v[i * 4 + 2] = t4.z; v[i * 4 + 3] = t4.w;
+                }
+                tmem_st32(tmem_w + ((uint32_t)(qq * 32) << 16) + cb * 32, v);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+
+    cluster_sync_all();              // every CTA of the cluster has initialised its barriers before a peer pushes partials at it
+
+    // per-thread state of the epilogue role (declared for all so the step loop below is shared by every warp)
+    // Epilogue ownership: thread (warp q, lane) finalises FOUR consecutive units u0..u0+3 (u0 = block base + 4*(lane & 7)) for TWO
+    // batch rows (q*8 + 2*(lane >> 3) + {0, 1}), so that every global access of the pointwise backward is a 128-bit one: a quarter
+    // of the memory instructions of a one-unit-per-lane mapping (their issue rate, not the exchange, had become the critical path).
+    const int q = warp & 3, j = lane;
+    const int te = (warp - 4) * 32 + lane;
+    const int jj = lane & 7, rr = lane >> 3;
+    const int u0 = ub * 128 + kq * 32 + 4 * jj;        // first of the 4 units this thread finalises
+    const int rl0 = q * 8 + rr * 2;                    // first of its 2 batch rows inside the 32-row slice
+    float4 dcst[MAX_CHAINS][2];
+    float4 mkr[MAX_CHAINS][2];                         // locked-dropout mask: constant over time
+    float4 cnext[MAX_CHAINS][2];                       // c_{t-1} loaded at this step = c_t of the next step (time runs backwards)
+    float4 dbacc[MAX_CHAINS][4];                       // bias-gradient partial sums (gate x 4 units) over this thread's rows, all steps
+    int lenr[MAX_CHAINS][2];
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < MAX_CHAINS; ++c) {
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) dbacc[c][gq] = z4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            dcst[c][i] = z4; cnext[c][i] = z4;
+            const int b = (sg + c * a.bsg) * NB_SLICE + rl0 + i;
+            lenr[c][i] = (warp >= 4 && c < a.chains && sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
+            mkr[c][i] = (a.mask && lenr[c][i] > 0) ? *reinterpret_cast<const float4*>(a.mask + (long long)b * F + dir * H + u0)
+                                                   : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+    }
+
+    // Every warp walks the same (step, chain) sequence: the cluster barrier of each iteration needs all threads of all 4 CTAs.
+    int iter = 0, riter = 0;
+    for (int s = 0; s < T; ++s) {
+        const int t = (dir == 0) ? (T - 1 - s) : s;
+        const int t_prev = (dir == 0) ? (T - s) : (s - 1);
+        const int fprev = (dir == 0) ? t : t + 2, fcur = t + 1;
+#pragma unroll
+        for (int c = 0; c < MAX_CHAINS; ++c) {
+            const int slice = sg + c * a.bsg;
+            if (c >= a.chains || slice >= a.nslices) continue;          // uniform across the cluster (same sg, chains)
+            const int b0 = slice * NB_SLICE;
+            const int rpar = riter & 1;                                   // parity of this reduce-iteration (s > 0 only)
+            const uint32_t rphase = (uint32_t)((riter >> 1) & 1);
+            if (s > 0) ++riter;
+            ++iter;
+            float4 gi[2], gf[2], gg[2], go[2], ct[2], cp[2], dh[2], rec[2];
+            bool valid[2];
+            if (warp == 0) {
+                // (no producer: the operand is pushed into this CTA's buffers by its peers)
+            } else if (warp == 1) {
+                if (s > 0) {
+                    // whole warp waits, one elected lane issues; BWD_NACC independent accumulators (one per k sub-step)
+                    const int par = (s - 1) & 1;                               // buffer holding dG of step s-1
+                    const uint32_t phase = (uint32_t)(((s - 1) >> 1) & 1);
+                    const uint32_t buf = b_sm + (uint32_t)par * TILE;
+                    if (s > 1) mbar_wait(tempty, (uint32_t)(s & 1));           // the epilogue has read step s-1's accumulators
+                    for (int hf = 0; hf < 2; ++hf) {
+                        if (lane == 0) mbar_arrive_expect_tx(hbar(par, hf), (uint32_t)halfsrc * 2048u);
+                        __syncwarp();
+                        mbar_wait(hbar(par, hf), phase);
+                        if (lane == 0 && hf == 0) REC_STAMP(2);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const int ks_lo = hf * halfsrc * 2, ks_hi = ks_lo + halfsrc * 2;      // 16-unit k-steps
+                            for (int ks = ks_lo; ks < ks_hi; ++ks) {
+                                const uint32_t d_tmem = tmem_base + (uint32_t)((c * BWD_NACC + (ks & 3)) * NB_SLICE);
+                                umma_bf16_ts(d_tmem, tmem_w + ks * 8, make_desc_k_noswz(buf + (uint32_t)ks * 1024u), IDESC, ks >= 4 ? 1u : 0u);
+                            }
+                            if (hf == 1) umma_commit(tfull_bar(c));
+                        }
+                        __syncwarp();
+                    }
+                    if (lane == 0) REC_STAMP(3);
+                }
+                __syncwarp();
+            } else if (warp >= 4) {
+                // operands of the pointwise backward for this thread's unit, issued before waiting on the tensor pipe
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int b = b0 + rl0 + i;
+                    valid[i] = t < lenr[c][i];
+                    // pure 128-bit loads, no branches: rows past B are clamped to a valid address; invalid rows are zeroed in the
+                    // pointwise step
+                    const int bc = b < a.B ? b : a.B - 1;
+                    const float* gp = a.gates + (((long long)bc * T + t) * a.ndir + dir) * G4 + u0;
+                    gi[i] = *reinterpret_cast<const float4*>(gp); gf[i] = *reinterpret_cast<const float4*>(gp + H);
+                    gg[i] = *reinterpret_cast<const float4*>(gp + 2 * H); go[i] = *reinterpret_cast<const float4*>(gp + 3 * H);
+                    // c_t: carried over from the previous step's c_{t-1} load (first step: loaded)
+                    if (s == 0) ct[i] = *reinterpret_cast<const float4*>(a.cs_pad + (long long)bc * brow + (long long)fcur * F + dir * H + u0);
+                    else ct[i] = cnext[c][i];
+                    cp[i] = *reinterpret_cast<const float4*>(a.cs_pad + (long long)bc * brow + (long long)fprev * F + dir * H + u0);
+                    dh[i] = *reinterpret_cast<const float4*>(a.dout + ((long long)bc * T + t) * F + dir * H + u0);
+                    rec[i] = z4;
+                }
+                if (te == 0) REC_STAMP(4);
+                if (s > 0) {
+                    mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
+                    if (te == 0) REC_STAMP(5);
+                    tc_fence_after();
+                    float accv[32];
+#pragma unroll
+                    for (int acc = 0; acc < BWD_NACC; ++acc) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c * BWD_NACC + acc) * NB_SLICE), v);
+#pragma unroll
+                        for (int n = 0; n < 32; ++n) accv[n] = acc ? accv[n] + __uint_as_float(v[n]) : __uint_as_float(v[n]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty);
+                    // TMEM lane = unit (32q + lane) of the block, column = batch row.  Warp q holds exactly the 32 units CTA q of the
+                    // cluster finalises: stage them as [row][unit] and push the 4 KB piece into CTA q's receive buffer
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the piece staged two iterations ago has been read
+                    __syncwarp();
+                    float* stg = part0 + (rpar * 4 + q) * 1024;
+#pragma unroll
+                    for (int n = 0; n < 32; ++n) stg[n * 32 + lane] = accv[n];
+                    tc_fence_before();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const uint32_t peer = (uint32_t)(ub * 4 + q);
+                        const uint32_t dst = mapa_u32(rcv_saddr0 + (uint32_t)((rpar * 4 + kq) * 4096), peer);
+                        bulk_copy_to_peer(dst, part_saddr0 + (uint32_t)((rpar * 4 + q) * 4096), 4096u, mapa_u32(rbar(rpar), peer));
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (te == 0) {
+                        mbar_arrive_expect_tx(rbar(rpar), 4u * 4096u);         // the four pieces for my 32 units
+                        REC_STAMP(6);
+                    }
+                }
+            }
+            if (s > 0) {
+                if (warp >= 4) {
+                    mbar_wait(rbar(rpar), rphase);
+                    if (te == 0) REC_STAMP(7);
+                    const float* rcv = rcv0 + rpar * 4 * 1024;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int o = (rl0 + i) * 32 + 4 * jj;
+                        const float4 p0 = *reinterpret_cast<const float4*>(rcv + o), p1 = *reinterpret_cast<const float4*>(rcv + 1024 + o);
+                        const float4 p2 = *reinterpret_cast<const float4*>(rcv + 2048 + o), p3 = *reinterpret_cast<const float4*>(rcv + 3072 + o);
+                        rec[i] = make_float4((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z),
+                                             (p0.w + p1.w) + (p2.w + p3.w));
+                    }
+                }
+                if (warp == 4 && lane == 0) REC_STAMP(11);
+            }
+            if (warp >= 4) {
+                // the dG slices staged at the previous step must have been read by their bulk copies before they are overwritten.
+                // (Thread te < RS also issued a partial-piece copy this iteration when lane == 0: wait for everything but that one.)
+                if (te < RS && s > 0) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                named_bar_sync(1, 128);
+                auto pw = [&](float gi_, float gf_, float gg_, float go_, float ct_, float cp_, float dh_, float mk_, float rec_, float dc_,
+                              bool ok, float& dai, float& daf, float& dag, float& dao, float& dcn) {
+                    dai = daf = dag = dao = dcn = 0.f;
+                    if (ok) {
+                        const float tcv = tanh_fast(ct_);
+                        const float dhv = fmaf(dh_, mk_, rec_);
+                        const float dct = fmaf(dhv * go_, 1.f - tcv * tcv, dc_);
+                        dai = dct * gg_ * gi_ * (1.f - gi_);
+                        daf = dct * cp_ * gf_ * (1.f - gf_);
+                        dag = dct * gi_ * (1.f - gg_ * gg_);
+                        dao = dhv * tcv * go_ * (1.f - go_);
+                        dcn = dct * gf_;
+                    }
+                };
+                auto pack4 = [](const float4& v) {
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                    uint2 r;
+                    r.x = *reinterpret_cast<const uint32_t*>(&lo); r.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    return r;
+                };
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int b = b0 + rl0 + i;
+                    float4 dI, dF, dG, dO, dC;
+                    pw(gi[i].x, gf[i].x, gg[i].x, go[i].x, ct[i].x, cp[i].x, dh[i].x, mkr[c][i].x, rec[i].x, dcst[c][i].x, valid[i], dI.x, dF.x, dG.x, dO.x, dC.x);
+                    pw(gi[i].y, gf[i].y, gg[i].y, go[i].y, ct[i].y, cp[i].y, dh[i].y, mkr[c][i].y, rec[i].y, dcst[c][i].y, valid[i], dI.y, dF.y, dG.y, dO.y, dC.y);
+                    pw(gi[i].z, gf[i].z, gg[i].z, go[i].z, ct[i].z, cp[i].z, dh[i].z, mkr[c][i].z, rec[i].z, dcst[c][i].z, valid[i], dI.z, dF.z, dG.z, dO.z, dC.z);
+                    pw(gi[i].w, gf[i].w, gg[i].w, go[i].w, ct[i].w, cp[i].w, dh[i].w, mkr[c][i].w, rec[i].w, dcst[c][i].w, valid[i], dI.w, dF.w, dG.w, dO.w, dC.w);
+                    dcst[c][i] = dC;
+                    cnext[c][i] = cp[i];
+                    // what the peers' next step reads: bf16 d(pre-activation), staged per gate in the UMMA no-swizzle core-matrix layout
+                    // (core (kc = unit/8, ng = row/8) at kc*512 + ng*128; row-in-core 16 B apart): 4 units = one 64-bit store
+                    if (s + 1 < T) {
+                        uint8_t* xp = xst_ptr + (jj >> 1) * 512 + q * 128 + (rr * 2 + i) * 16 + (jj & 1) * 8;
+                        *reinterpret_cast<uint2*>(xp) = pack4(dI); *reinterpret_cast<uint2*>(xp + 2048) = pack4(dF);
+                        *reinterpret_cast<uint2*>(xp + 4096) = pack4(dG); *reinterpret_cast<uint2*>(xp + 6144) = pack4(dO);
+                    }
+                    gi[i] = dI; gf[i] = dF; gg[i] = dG; go[i] = dO;
+                    dbacc[c][0].x += dI.x; dbacc[c][0].y += dI.y; dbacc[c][0].z += dI.z; dbacc[c][0].w += dI.w;
+                    dbacc[c][1].x += dF.x; dbacc[c][1].y += dF.y; dbacc[c][1].z += dF.z; dbacc[c][1].w += dF.w;
+                    dbacc[c][2].x += dG.x; dbacc[c][2].y += dG.y; dbacc[c][2].z += dG.z; dbacc[c][2].w += dG.w;
+                    dbacc[c][3].x += dO.x; dbacc[c][3].y += dO.y; dbacc[c][3].z += dO.z; dbacc[c][3].w += dO.w;
+                }
+                if (s + 1 < T) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_bar_sync(1, 128);
+                if (te == 0) REC_STAMP(8);
+                if (s + 1 < T && te < RS) {
+                    // thread `te` pushes the slice of gate g = te & 3 into the operand buffer of the consumer of that gate in unit block
+                    // te >> 2 (cluster rank (te >> 2) * 4 + g), at this CTA's position, and signals the half its rank belongs to
+                    const int g = te & 3, par = s & 1;
+                    const uint32_t peer = (uint32_t)((te >> 2) * 4 + g);
+                    const uint32_t dst = mapa_u32(b_sm + (uint32_t)par * TILE + (uint32_t)crank * 2048u, peer);
+                    bulk_copy_to_peer(dst, xst_sm + (uint32_t)g * 2048u, 2048u, mapa_u32(hbar(par, crank >= halfsrc ? 1 : 0), peer));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (te == 0) REC_STAMP(9);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int b = b0 + rl0 + i;
+                    if (b >= a.B) continue;
+                    if (!a.dbp) {
+                        float* gp = a.gates + ((((long long)b * T + t) * a.ndir + dir) * G4) + u0;
+                        *reinterpret_cast<float4*>(gp) = gi[i]; *reinterpret_cast<float4*>(gp + H) = gf[i];
+                        *reinterpret_cast<float4*>(gp + 2 * H) = gg[i]; *reinterpret_cast<float4*>(gp + 3 * H) = go[i];
+                    }
+                    // the (B*T, NG) bf16 copy the dX / dW GEMMs consume
+                    __nv_bfloat16* bp = a.dgb + ((long long)b * T + t) * NG + dir * G4 + u0;
+                    *reinterpret_cast<uint2*>(bp) = pack4(gi[i]); *reinterpret_cast<uint2*>(bp + H) = pack4(gf[i]);
+                    *reinterpret_cast<uint2*>(bp + 2 * H) = pack4(gg[i]); *reinterpret_cast<uint2*>(bp + 3 * H) = pack4(go[i]);
+                }
+                if (te == 0) REC_STAMP(10);
+            }
+        }
+    }
+    if (a.dbp) {
+        // bias gradients: the four epilogue warps hold partial sums of the same 32 units over different batch rows; add them up in
+        // a fixed order and store this (direction, batch slice)'s row -- the host sums the few slice rows (deterministic)
+        __syncthreads();
+        float* red = part0;                   // [chain][q][rr][gate][32 units] floats (8 K floats; the partial tiles are idle now)
+        if (warp >= 4) {
+#pragma unroll
+            for (int c = 0; c < MAX_CHAINS; ++c)
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<float4*>(red + ((((c * 4 + q) * 4 + rr) * 4 + gq) * 32) + 4 * jj) = dbacc[c][gq];
+        }
+        __syncthreads();
+        if (warp == 4) {
+            for (int c = 0; c < a.chains; ++c) {
+                const int slice = sg + c * a.bsg;
+                if (slice >= a.nslices) continue;
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int pq = 0; pq < 16; ++pq) v += red[(((c * 16 + pq) * 4 + gq) * 32) + j];      // fixed order over (q, rr)
+                    a.dbp[((long long)(dir * a.nslices + slice) * 4 + gq) * H + ub * 128 + kq * 32 + j] = v;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                               // no CTA of the cluster exits while a peer may still read its smem
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
 }  // namespace
+
+// BPTT with the SM-to-SM exchange; returns LAS_ERR_UNSUPPORTED when the shape / device does not allow it (caller falls back)
+static int launch_bwd_dsm(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16, const int* lens,
+                          const float* drop_mask, int B, int T, int H, int ndir, cudaStream_t st, void* stream, float* dbp) {
+    const char* de = getenv("LAS_REC_DSMEM");
+    if (de && atoi(de) == 0) return LAS_ERR_UNSUPPORTED;
+    if (H % 128 != 0 || H > 512) return LAS_ERR_UNSUPPORTED;
+    const LasDeviceInfo* di = las_device_info();
+    const int rs = 4 * (H / 128);
+    const int nslices = ceil_div(B, NB_SLICE);
+    const int max_bsg = di->num_sms / (rs * ndir);
+    if (max_bsg < 1 || nslices > max_bsg) return LAS_ERR_UNSUPPORTED;          // one chain per CTA only
+    const size_t smem = 1024 + 2 * (size_t)rs * 2048 + 4 * 2048 + 4 * 4 * 4096 + 16 + 8 * (2 * MAX_CHAINS + 2 + 3 * MAX_CHAINS + 7) + 64;
+    if (smem > (size_t)di->max_smem_optin) return LAS_ERR_UNSUPPORTED;
+    RecTcBwdArgs a{};
+    a.gates = gates; a.dgb = (__nv_bfloat16*)dgates_bf16; a.dout = dout; a.cs_pad = cs_pad; a.lens = lens; a.mask = drop_mask;
+    a.B = B; a.T = T; a.H = H; a.ndir = ndir; a.nslices = nslices; a.chains = 1; a.bsg = nslices; a.KBr = 4 * H / 64; a.CH = H / 64;
+    a.dbg = g_rec_dbg; a.Bpad = nslices * NB_SLICE;
+    a.w_t = (const __nv_bfloat16*)w_hh_t_bf16;
+    a.dbp = dbp;
+    auto kd = lstm_rec_bwd_dsm_kernel;
+    if (cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return LAS_ERR_UNSUPPORTED; }
+    if (rs > 8 && cudaFuncSetAttribute(kd, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return LAS_ERR_UNSUPPORTED; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(rs, nslices, ndir); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = rs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, kd, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); return LAS_ERR_UNSUPPORTED; }
+    LasProfScope prof(LAS_PROF_REC_BWD, stream, (double)T);
+    if (cudaLaunchKernelEx(&cfg, kd, a) != cudaSuccess) { cudaGetLastError(); return LAS_ERR_UNSUPPORTED; }
+    las_count_launch(1);
+    return LAS_OK;
+}
 
 // returns LAS_OK, or a negative code when this variant cannot run (caller falls back to las_lstm_rec_bwd_tc's streaming variant)
 static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16, const int* lens,
