@@ -581,22 +581,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
             const int hw = warp == 0 ? 0 : warp - 1;       // 0..2
             const int b0 = sg * NB_SLICE;
             const long long gstride = (long long)T * a.ndir * 4 * H;
-            float xr[43];
-            auto load_x = [&](int s2) {                    // rows pr = hw, hw+3, ... of step s2: pr = gate * 32 + batch row
+            // 128-bit accesses: lane = (row-in-group = lane >> 3, 4 units = 4 * (lane & 7)); 32 groups of 4 (gate, row) pairs over 3 warps
+            const int rg = lane >> 3, c4 = 4 * (lane & 7);
+            float4 xr[11];
+            auto load_x = [&](int s2) {
                 const int t2 = (dir == 0) ? s2 : (T - 1 - s2);
-                const float* gb = a.gates + ((long long)t2 * a.ndir + dir) * 4 * H + r * UNITS + lane;
+                const float* gb = a.gates + ((long long)t2 * a.ndir + dir) * 4 * H + r * UNITS + c4;
 #pragma unroll
-                for (int i = 0; i < 43; ++i) {
-                    const int pr = hw + 3 * i;
+                for (int i = 0; i < 11; ++i) {
+                    const int pr = 4 * (hw + 3 * i) + rg;          // pr = gate * 32 + batch row
                     const int qq = pr >> 5, n = pr & 31;
-                    xr[i] = (pr < 128 && b0 + n < a.B) ? gb[(long long)(b0 + n) * gstride + qq * H] : 0.f;
+                    xr[i] = (pr < 128 && b0 + n < a.B) ? *reinterpret_cast<const float4*>(gb + (long long)(b0 + n) * gstride + qq * H)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
             auto store_x = [&](int buf) {
 #pragma unroll
-                for (int i = 0; i < 43; ++i) {
-                    const int pr = hw + 3 * i;
-                    if (pr < 128) xgs[(buf * 128 + pr) * 32 + lane] = xr[i];
+                for (int i = 0; i < 11; ++i) {
+                    const int pr = 4 * (hw + 3 * i) + rg;
+                    if (pr < 128) *reinterpret_cast<float4*>(xgs + (buf * 128 + pr) * 32 + c4) = xr[i];
                 }
             };
             load_x(0);
@@ -607,10 +610,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
                 if (s + 1 < T) load_x(s + 1);                                      // in flight while waiting below
                 asm volatile("bar.sync 2, 224;" ::: "memory");                    // `ex` of step s complete (and xgs[s & 1] consumed)
                 if (a.save) {
-                    float* gb = a.gates + ((long long)t * a.ndir + dir) * 4 * H + r * UNITS + lane;
-                    for (int pr = hw; pr < 128; pr += 3) {
+                    float* gb = a.gates + ((long long)t * a.ndir + dir) * 4 * H + r * UNITS + c4;
+                    for (int grp = hw; grp < 32; grp += 3) {
+                        const int pr = 4 * grp + rg;
                         const int qq = pr >> 5, n = pr & 31;
-                        if (b0 + n < a.B) gb[(long long)(b0 + n) * gstride + qq * H] = ex[pr * 32 + lane];
+                        if (b0 + n < a.B)
+                            *reinterpret_cast<float4*>(gb + (long long)(b0 + n) * gstride + qq * H) = *reinterpret_cast<const float4*>(ex + pr * 32 + c4);
                     }
                 }
                 asm volatile("bar.arrive 3, 224;" ::: "memory");                  // `ex` may be rewritten
