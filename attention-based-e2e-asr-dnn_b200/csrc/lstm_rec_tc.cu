@@ -1193,6 +1193,25 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
     if (ws_bytes < las_lstm_rec_tc_workspace_bytes(B, H, ndir)) { las_set_error("lstm_rec_fwd_tc: workspace too small"); return LAS_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     {
+        // more batch slices than clusters fit at once (B > 128 at H = 512): batch rows are independent, so run the rows in passes
+        // of `bsg` slices with the one-chain DSMEM kernel (2.5 us/step each) instead of two chains per CTA on the counter/TMA
+        // kernel (6.9 us/step): every array is batch-major, a pass is a pointer offset.  LAS_REC_SPLIT_BATCH=0 disables.
+        const char* sb = getenv("LAS_REC_SPLIT_BATCH");
+        const char* de = getenv("LAS_REC_DSMEM");
+        if (p.chains > 1 && !(sb && atoi(sb) == 0) && !(de && atoi(de) == 0) && p.rs <= 16 && H <= 512) {
+            const int rows = p.bsg * NB_SLICE;
+            const long long F = (long long)ndir * H;
+            for (int b0 = 0; b0 < B; b0 += rows) {
+                const int nb = B - b0 < rows ? B - b0 : rows;
+                rc = las_lstm_rec_fwd_tc(gates + (long long)b0 * T * ndir * 4 * H, w_hh_bf16, lens + b0, drop_mask ? drop_mask + b0 * F : nullptr,
+                                         out ? out + (long long)b0 * T * F : nullptr, hs_pad + (long long)b0 * (T + 2) * F,
+                                         cs_pad + (long long)b0 * (T + 2) * F, nb, T, H, ndir, save_gates, ws, ws_bytes, stream);
+                if (rc) return rc;
+            }
+            return LAS_OK;
+        }
+    }
+    {
         const char* e = getenv("LAS_REC_LL");
         const int KBh = H / 64;
         if ((e && atoi(e) != 0) && (KBh == 1 || KBh == 2 || KBh == 4 || KBh == 8) && (p.chains == 1 || (e && atoi(e) == 2))) {
@@ -1619,6 +1638,23 @@ static int rec_bwd_tc_impl(const float* dout, float* gates, void* dgates_bf16, c
     if (rc) return rc;
     if (ws_bytes < las_lstm_rec_tc_workspace_bytes(B, H, ndir)) { las_set_error("lstm_rec_bwd_tc: workspace too small"); return LAS_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        // same batch passes as the forward launcher when the rows do not fit one chain per CTA
+        const char* sb = getenv("LAS_REC_SPLIT_BATCH");
+        const char* de = getenv("LAS_REC_DSMEM");
+        if (p.chains > 1 && !dbp && !(sb && atoi(sb) == 0) && !(de && atoi(de) == 0) && H % 128 == 0 && H <= 512) {
+            const int rows = p.bsg * NB_SLICE;
+            const long long F = (long long)ndir * H;
+            for (int b0 = 0; b0 < B; b0 += rows) {
+                const int nb = B - b0 < rows ? B - b0 : rows;
+                rc = rec_bwd_tc_impl(dout + (long long)b0 * T * F, gates + (long long)b0 * T * ndir * 4 * H,
+                                     (__nv_bfloat16*)dgates_bf16 + (long long)b0 * T * ndir * 4 * H, cs_pad + (long long)b0 * (T + 2) * F, w_hh_t_bf16,
+                                     lens + b0, drop_mask ? drop_mask + b0 * F : nullptr, nb, T, H, ndir, ws, ws_bytes, stream, nullptr);
+                if (rc) return rc;
+            }
+            return LAS_OK;
+        }
+    }
     {
         const char* e = getenv("LAS_REC_BWD_KSPLIT");
         if (!e || atoi(e) != 0) {
