@@ -1193,12 +1193,13 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
     if (ws_bytes < las_lstm_rec_tc_workspace_bytes(B, H, ndir)) { las_set_error("lstm_rec_fwd_tc: workspace too small"); return LAS_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     {
-        // more batch slices than clusters fit at once (B > 128 at H = 512): batch rows are independent, so run the rows in passes
-        // of `bsg` slices with the one-chain DSMEM kernel (2.5 us/step each) instead of two chains per CTA on the counter/TMA
-        // kernel (6.9 us/step): every array is batch-major, a pass is a pointer offset.  LAS_REC_SPLIT_BATCH=0 disables.
+        // LAS_REC_SPLIT_BATCH=1: with more batch slices than one chain per CTA allows (B > 128 at H = 512), run the rows in passes of
+        // `bsg` slices with the one-chain DSMEM kernel (every array is batch-major: a pass is a pointer offset).  Measured SLOWER at
+        // B = 256: a pass of 128 rows is 8 clusters of 16 CTAs, and with all 8 GPCs exchanging at once a step takes 4.9 us (2.5 us
+        // with 6 clusters) -- 9.7 us per step for both passes against 6.9 us for two chains per CTA on the counter/TMA kernel.
         const char* sb = getenv("LAS_REC_SPLIT_BATCH");
         const char* de = getenv("LAS_REC_DSMEM");
-        if (p.chains > 1 && !(sb && atoi(sb) == 0) && !(de && atoi(de) == 0) && p.rs <= 16 && H <= 512) {
+        if (p.chains > 1 && (sb && atoi(sb) == 1) && !(de && atoi(de) == 0) && p.rs <= 16 && H <= 512) {
             const int rows = p.bsg * NB_SLICE;
             const long long F = (long long)ndir * H;
             for (int b0 = 0; b0 < B; b0 += rows) {
@@ -1642,7 +1643,7 @@ static int rec_bwd_tc_impl(const float* dout, float* gates, void* dgates_bf16, c
         // same batch passes as the forward launcher when the rows do not fit one chain per CTA
         const char* sb = getenv("LAS_REC_SPLIT_BATCH");
         const char* de = getenv("LAS_REC_DSMEM");
-        if (p.chains > 1 && !dbp && !(sb && atoi(sb) == 0) && !(de && atoi(de) == 0) && H % 128 == 0 && H <= 512) {
+        if (p.chains > 1 && !dbp && (sb && atoi(sb) == 1) && !(de && atoi(de) == 0) && H % 128 == 0 && H <= 512) {
             const int rows = p.bsg * NB_SLICE;
             const long long F = (long long)ndir * H;
             for (int b0 = 0; b0 < B; b0 += rows) {
