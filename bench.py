@@ -34,14 +34,14 @@ UNIT = 'utterances/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=96, help='utterances per GPU')
     ap.add_argument('--T', type=int, default=1600)
     ap.add_argument('--L', type=int, default=300)
     ap.add_argument('--config', default='best')
-    ap.add_argument('--cpu-sample-batch', type=int, default=2)
+    ap.add_argument('--cpu-sample-batch', type=int, default=8, help='utterances of the CPU-baseline sample (about 10 s of CPU work per step at 8)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help="bf16: the AMP path (gate GEMMs on the tensor pipe, like the reference's autocast runs); fp32: parity mode")
@@ -78,7 +78,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(',')])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -173,10 +173,12 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    B = args.cpu_sample_batch
-    times = []
     for i in range(max(1, min(args.warmup, 1))):
         oracle_cpu_step(args.config, 1, max(args.T // 8, 8), max(args.L // 8, 2))      # warm the allocator / thread pool
+    # size the per-step sample so that the K timed steps take about two and a half minutes at most: probe one utterance first
+    per_utt = oracle_cpu_step(args.config, 1, args.T, args.L)
+    B = int(max(1, min(args.cpu_sample_batch, 150.0 / (max(args.steps, 1) * max(per_utt, 1e-3)))))
+    times = []
     for i in range(args.steps):
         times.append(oracle_cpu_step(args.config, B, args.T, args.L))
     ms = 1e3 * float(np.mean(times))
