@@ -138,7 +138,7 @@ def test_bf16_mode_logits_within_amp_tolerance(name):
 @pytest.mark.parametrize('variant', ['default', 'tma', 'll', 'cluster'])
 # the long sequences catch ordering races between a CTA's own epilogue and operands pushed by faster peers (seen once: T <= 21 passed)
 @pytest.mark.parametrize('H,B,T,lens', [(64, 5, 9, [9, 3, 7, 1, 9]), (128, 40, 21, None), (512, 96, 12, None), (512, 130, 6, None),
-                                        (128, 4, 400, None), (512, 96, 150, None)])
+                                        (128, 4, 400, None), (512, 96, 150, None), (128, 3, 1, None), (128, 3, 2, [2, 1, 2])])
 def test_tc_recurrence_forward_vs_fp32_kernel(H, B, T, lens, variant, monkeypatch):
     """The tensor-pipe recurrence (bf16 operands) against the fp32 recurrence kernel on the same x-gates: same
     PackedSequence semantics (zeros past each length, reverse direction from each row's own end), values within bf16
@@ -197,7 +197,7 @@ def test_tc_recurrence_forward_vs_fp32_kernel(H, B, T, lens, variant, monkeypatc
 
 
 @pytest.mark.parametrize('H,B,T,lens', [(64, 5, 9, [9, 3, 7, 1, 9]), (128, 40, 21, None), (512, 96, 12, None), (256, 130, 6, None),
-                                        (128, 4, 300, None)])
+                                        (128, 4, 300, None), (128, 3, 1, None), (128, 3, 2, [2, 1, 2])])
 def test_tc_recurrence_backward_vs_fp32_kernel(H, B, T, lens):
     """BPTT on the tensor pipe against the fp32 BPTT kernel on identical saved activations."""
     from las_b200 import _lib, functional as LF
