@@ -57,6 +57,9 @@ struct CellFwd {
     __nv_bfloat16* h1b; long long ld_h1b;   // nullable bf16 copies (tensor-pipe mode: next GEMMs' A operand)
     __nv_bfloat16* h2b; long long ld_h2b;
     int B, H;
+    // optional fused query projection (cell 1, H == 256 == blockDim: one batch row per CTA): q[b, :] = Wq . h[b, :] + bq with
+    // WqT = Wq transposed, bf16, (H, P); saves the separate 4-CTA GEMM launch of every decoder step
+    const __nv_bfloat16* WqT; const float* bq; float* qout; long long ld_q; int P;
 };
 
 __global__ void __launch_bounds__(256) cell_fwd_kernel(CellFwd a) {
@@ -103,6 +106,37 @@ __global__ void __launch_bounds__(256) cell_fwd_kernel(CellFwd a) {
     if (a.h2) a.h2[(long long)b * a.ld_h2 + u] = h;
     if (a.h1b) a.h1b[(long long)b * a.ld_h1b + u] = __float2bfloat16(h);
     if (a.h2b) a.h2b[(long long)b * a.ld_h2b + u] = __float2bfloat16(h);
+    if (a.WqT) {
+        // this CTA holds the whole h row of batch row b (H == blockDim.x == 256).  Warp w covers h units [32w, 32w+32), lane l the
+        // 8 outputs [8l, 8l+8): 32 x 128-bit loads of WqT per thread, then the 8 warps' partials are added through shared memory
+        __shared__ float hs[256];
+        __shared__ float part[8][256];
+        hs[u] = h;
+        __syncthreads();
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (8 * l < a.P) {
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const int uu = w * 32 + k;
+                const uint4 wv = *reinterpret_cast<const uint4*>(a.WqT + (long long)uu * a.P + 8 * l);
+                const float hv = hs[uu];
+                acc[0] = fmaf(__uint_as_float(wv.x << 16), hv, acc[0]); acc[1] = fmaf(__uint_as_float(wv.x & 0xffff0000u), hv, acc[1]);
+                acc[2] = fmaf(__uint_as_float(wv.y << 16), hv, acc[2]); acc[3] = fmaf(__uint_as_float(wv.y & 0xffff0000u), hv, acc[3]);
+                acc[4] = fmaf(__uint_as_float(wv.z << 16), hv, acc[4]); acc[5] = fmaf(__uint_as_float(wv.z & 0xffff0000u), hv, acc[5]);
+                acc[6] = fmaf(__uint_as_float(wv.w << 16), hv, acc[6]); acc[7] = fmaf(__uint_as_float(wv.w & 0xffff0000u), hv, acc[7]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) part[w][8 * l + e] = acc[e];
+        __syncthreads();
+        if ((int)threadIdx.x < a.P) {
+            float q = a.bq[threadIdx.x];
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) q += part[ww][threadIdx.x];
+            a.qout[(long long)b * a.ld_q + threadIdx.x] = q;
+        }
+    }
 }
 
 struct CellBwd {
@@ -332,7 +366,7 @@ struct Layout {
     // float workspace offsets
     size_t Wcat0, Wcat1, Gemb, S0, S1, C0, C1, G0, G1, QC, W, W2, FM, dQC, dS0, dS1, dc0, dc1, dh1, DE, dGemb, tmpq, cs_scratch, total_f;
     // bf16 region (offsets in floats, buffers hold bf16): tensor-pipe mode only
-    size_t Wcat0b, Wcat1b, Wqb, S0b, S1b, G0b, G1b, dQb, dlb, ohb, QCb, tmp32, skws, Wcat0p, Wcat1p, Gp0, Gp1, dSp0, dSp1;
+    size_t Wcat0b, Wcat1b, Wqb, S0b, S1b, G0b, G1b, dQb, dlb, ohb, QCb, tmp32, skws, Wcat0p, Wcat1p, Gp0, Gp1, dSp0, dSp1, WqT;
     size_t skws_floats;
     // int workspace offsets
     size_t tok, total_i;
@@ -381,6 +415,7 @@ Layout make_layout(const LasSpeller* s) {
         L.Wcat0b = takeb(4 * DH * (P + DH));
         L.Wcat1b = takeb(4 * DO * (DH + DO));
         L.Wqb = takeb(P * DO);
+        L.WqT = takeb(P * DO);
         L.Wcat0p = takeb(4 * DH * (P + DH));       // row-permuted copies for the fused LSTM epilogue (forward)
         L.Wcat1p = takeb(4 * DO * (DH + DO));
         L.S0b = takeb((size_t)L.hist * B * (P + DH));
@@ -604,6 +639,7 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
         RC(cast_rows(st, Wcat0, K0, Wcat0b, K0, 4 * DH, K0));
         RC(cast_rows(st, Wcat1, K1, Wcat1b, K1, 4 * DO, K1));
         RC(cast_rows(st, s->wq, DO, Wqb, DO, P, DO));
+        RC(las_transpose_cast_bf16(s->wq, f + L.WqT, 1, P, DO, st));          // WqT (DO, P) bf16 for the query projection fused into cell 1
         LAS_CUDA(cudaMemset2DAsync(S0b + P, K0 * 2, 0, DH * 2, B, st));       // h0_{-1} = 0 (bf16)
         LAS_CUDA(cudaMemset2DAsync(S1b + DH, K1 * 2, 0, DO * 2, B, st));      // h1_{-1} = 0
     }
@@ -627,6 +663,9 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
     const int sk0 = (tc && !fuse) ? pick_split(las_tc_plan_tiles(&pl0), las_tc_plan_kiters(&pl0)) : 1;
     const int sk1 = (tc && !fuse) ? pick_split(las_tc_plan_tiles(&pl1), las_tc_plan_kiters(&pl1)) : 1;
     float *Gp0 = f + L.Gp0, *Gp1 = f + L.Gp1;
+    // query projection fused into the cell-1 kernel (one CTA = one batch row needs DO == 256 == its block size)
+    const char* fq_env = getenv("LAS_DEC_FUSEQ");
+    const bool fuse_q = tc && !fuse && DO == 256 && P <= 256 && P % 8 == 0 && !(fq_env && atoi(fq_env) == 0);
     // embedding-side gate table (+ both cell-0 biases)
     RC(gemm(st, s->emb, E, s->w_ih0, E + P, 1, Gemb, 4 * DH, V, 4 * DH, E, 0.f, s->b_ih0, s->b_hh0));
     // zero initial states (init_hiddens are always zero: reference src/models.py:275-281)
@@ -726,11 +765,13 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
             c1.h1 = S1n + DH; c1.ld_h1 = K1; c1.h2 = nullptr;
             if (tc) { c1.h1b = S1nb + DH; c1.ld_h1b = K1; }
             c1.B = B; c1.H = DO;
+            if (fuse_q) { c1.WqT = (const __nv_bfloat16*)(f + L.WqT); c1.bq = s->bq; c1.qout = QCn; c1.ld_q = 2 * P; c1.P = P; }
             LAS_CUDA(las_launch(cell_fwd_kernel, dim3(ceil_div(B * DO, 256)), dim3(256), 0, st, c1));
             LAS_LAUNCH_CHECK();
         }
         // query projection into QC[t+1][:, :P]
-        if (tc) RC(las_tc_plan_launch(&plq, rn, QCn, 2 * P, s->bq, nullptr, st));
+        if (fuse_q) { /* q was written by cell 1 */ }
+        else if (tc) RC(las_tc_plan_launch(&plq, rn, QCn, 2 * P, s->bq, nullptr, st));
         else RC(gemm(st, S1n + DH, K1, s->wq, DO, 1, QCn, 2 * P, B, P, DO, 0.f, s->bq));
         // attention: context into QC[t+1][:, P:] and into the next cell-0 row
         at.q = QCn; at.ctx = QCn + P; at.ctx2 = S0n; at.w = W + (size_t)rn * B * heads * T;

@@ -117,6 +117,40 @@ def test_bf16_mode_lstm_layer_close_to_fp32_oracle():
         assert rel_err(pc[k_].grad.cpu().numpy(), po[k_].grad.numpy()) < 3e-2, k_
 
 
+@pytest.mark.parametrize('fuse_q', ['1', '0'])
+def test_bf16_mode_best_config_dims_vs_oracle(fuse_q, monkeypatch):
+    """AMP mode at the best config's dims (H 512, P 256, dec 512/256: the tcgen05 decoder GEMMs with split-K partials, the query
+    projection fused into the cell-1 kernel, the DSMEM recurrence) against the fp32 oracle: logits within the AMP tolerance and
+    the same gradients up to bf16 operand rounding.  fuse_q = 0 runs the separate query-projection GEMM instead."""
+    from las_b200.models import ListenAttendSpell
+    monkeypatch.setenv('LAS_DEC_FUSEQ', fuse_q)
+    cfg = gu.get_config('best')
+    sd = gu.make_state_dict(cfg, 11)
+    B, T, L = 3, 72, 6
+    x, lx, y = gu.make_inputs(12, B, T, L, [72, 49, 64])
+    model = ListenAttendSpell(**gu.get_config('best')).to(DEV)
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    model.train()
+    yd = torch.from_numpy(y).to(DEV)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        logits, _ = model(torch.from_numpy(x).to(DEV), torch.from_numpy(lx), yd, 1.0, False)
+    loss = torch.nn.functional.cross_entropy(logits.float().reshape(-1, 30), yd.reshape(-1))
+    loss.backward()
+    p = {k: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in sd.items() if k != 'spell.cls.weight'}
+    p['spell.cls.weight'] = p['spell.char_emb.weight']
+    ol, _ = orc.las_forward(p, torch.from_numpy(x), lx.tolist(), lstm_layers=1, plstm_layers=3, heads=1, training=True,
+                            steps=L, dec_y=torch.from_numpy(y), coins=[True] * L)
+    torch.nn.functional.cross_entropy(ol.reshape(-1, 30), torch.from_numpy(y).reshape(-1)).backward()
+    err = np.abs(logits.detach().float().cpu().numpy() - ol.detach().numpy()).max()
+    print(f'best dims, bf16 mode: max abs logit error vs fp32 oracle = {err:.3e}')
+    assert err < 2e-3
+    gmax = max(float(v.grad.abs().max()) for v in p.values() if v.grad is not None)
+    for k, prm in model.named_parameters():
+        if p[k].grad is None:
+            continue
+        assert rel_err(prm.grad.cpu().numpy(), p[k].grad.numpy(), 1e-2 * gmax) < 6e-2, k
+
+
 @pytest.mark.parametrize('name', ['micro_train_tf1', 'tiny_train_tf1'])
 def test_bf16_mode_logits_within_amp_tolerance(name):
     """north_star: AMP/bf16 logits within 2e-3 absolute of the reference."""
