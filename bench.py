@@ -203,7 +203,7 @@ def main():
     from las_b200.ddp import BucketedGradReducer
     from las_b200.models import ListenAttendSpell
     from las_b200.optim import FusedAdamW
-    from oracle import golden_util as gu      # config table + seeded synthetic inputs only (no oracle compute here)
+    from las_b200 import configs as gu        # config table + seeded synthetic inputs (the product arm never touches oracle/)
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
