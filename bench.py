@@ -395,7 +395,9 @@ def main():
     at_gbs = attn_replay['bytes_per_launch'] / attn_replay['us_fwd'] / 1e3
     at_gbs_bwd = attn_replay['bytes_per_launch'] / attn_replay['us_bwd'] / 1e3
     attn_roofline = dict(kernel='fused attention step fwd (energy+masked softmax+context), single-pass T-split', bound='hbm',
-                         achieved=at_gbs, peak=pk['hbm'], unit='GB/s', frac=at_gbs / pk['hbm'], traffic=None, peak_source=pk['source'],
+                         achieved=at_gbs, peak=pk['hbm'], unit='GB/s', frac=at_gbs / pk['hbm'], traffic=39.45e6,
+                         traffic_note='dram read+write per launch with a flushed L2 (ncu --set full, profiles/ncu_full_r1_final_kernels.csv): K and V are read exactly once; in the decoder loop they are L2 hits',
+                         peak_source=pk['source'],
                          us_per_launch=attn_replay['us_fwd'], bytes_per_launch=attn_replay['bytes_per_launch'],
                          bwd=dict(achieved=at_gbs_bwd, frac=at_gbs_bwd / pk['hbm'], us_per_launch=attn_replay['us_bwd']),
                          method='50 launches captured in a CUDA graph, replayed, CUDA events on the replay stream; K/V (39 MB) L2-warm as in the loop',
