@@ -91,11 +91,11 @@ class Rewriter(nn.Module):
         if self.training:
             # the coin is drawn like the reference (src/lmtrain.py:229-230) but its outcome is never used (:231 assigns `char_meb`)
             use_gold = [False] * steps
-            for t in range(1, steps):
-                if _MASK_OVERRIDE['coins'] is not None:
+            if _MASK_OVERRIDE['coins'] is not None:
+                for t in range(1, steps):
                     _MASK_OVERRIDE['coins'].pop(0)
-                else:
-                    torch.rand(1).item()
+            else:
+                torch.rand(max(steps - 1, 0))          # same generator consumption as steps-1 calls of torch.rand(1)
         drop0, drop1 = self._decoder_masks(steps, B, enc_h.device)
         c0, c1 = self.dec_lstm.lstms[0], self.dec_lstm.lstms[1]
         params = (self.char_emb.weight, self.cls.bias, c0.weight_ih, c0.weight_hh, c0.bias_ih, c0.bias_hh,

@@ -1,0 +1,50 @@
+"""GPU busy time vs wall time of one train step (torch.profiler / CUPTI): how much of the step is idle gaps between kernels."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'attention-based-e2e-asr-dnn_b200'))
+import torch
+from torch.profiler import profile, ProfilerActivity
+from las_b200 import _lib, configs as gu
+from las_b200.models import ListenAttendSpell
+from las_b200.optim import FusedAdamW
+from las_b200.ddp import BucketedGradReducer
+from las_b200.loss import masked_ce
+lib = _lib.load(); _lib.check(lib.las_init(0), 'init')
+dev = torch.device('cuda:0')
+B, T, L = 96, 1600, 300
+cfg = gu.get_config('best'); torch.manual_seed(11785)
+model = ListenAttendSpell(**cfg).to(dev).train()
+opt = FusedAdamW(model.parameters(), lr=5e-4, weight_decay=5e-6, amsgrad=True)
+red = BucketedGradReducer(list(model.named_parameters()), world_size=1)
+x, lx, y = gu.make_inputs(1, B, T, L)
+x, y, lx = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), torch.from_numpy(lx)
+ly = torch.full((B,), L, dtype=torch.int64)
+def step():
+    red.zero_grad()
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        logits, _ = model(x, lx, y, 1.0, False)
+    loss, _ = masked_ce(logits, y, ly)
+    (loss * 65536.0).backward(); red.finish(); opt.step_fused(inv_scale=1.0 / 65536.0, max_norm=5.0)
+for _ in range(4): step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort(key=lambda e: e.time_range.start)
+t0, t1 = evs[0].time_range.start, max(e.time_range.end for e in evs)
+busy, cur_end, gaps = 0.0, t0, []
+for e in evs:
+    s, en = e.time_range.start, e.time_range.end
+    if s > cur_end:
+        gaps.append((s - cur_end, e.name[:60])); busy += en - s; cur_end = en
+    elif en > cur_end:
+        busy += en - cur_end; cur_end = en
+print(f'3 steps: wall {(t1 - t0) / 1e3:.2f} ms, GPU busy {busy / 1e3:.2f} ms, idle {(t1 - t0 - busy) / 1e3:.2f} ms in {len(gaps)} gaps')
+gaps.sort(reverse=True)
+for g, n in gaps[:15]: print(f'  gap {g:8.1f} us before {n}')
+import collections
+small = collections.Counter(); 
+for g, n in gaps:
+    small[n.split('<')[0][:40]] += g
+for n, g in small.most_common(12): print(f'  total gap {g / 1e3:7.2f} ms before {n}')

@@ -121,3 +121,16 @@ def test_shim_resolves_reference_drivers_and_our_models():
     env = dict(os.environ, LAS_REFERENCE_SRC='/root/reference/src', PYTHONPATH=os.path.join(ROOT, 'attention-based-e2e-asr-dnn_b200'))
     out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, cwd='/tmp')
     assert out.returncode == 0 and 'ok' in out.stdout, out.stderr[-2000:]
+
+
+def test_batched_coin_draw_equals_sequential_draws():
+    """Speller.forward draws the teacher-forcing coins with one torch.rand(n) call; the reference draws torch.rand(1) n times
+    (src/models.py:357).  Same values, same generator state afterwards."""
+    for n in (1, 7, 16, 299, 600):
+        torch.manual_seed(11785)
+        seq = torch.stack([torch.rand(1) for _ in range(n)]).flatten()
+        after_seq = torch.rand(4)
+        torch.manual_seed(11785)
+        bat = torch.rand(n)
+        after_bat = torch.rand(4)
+        assert torch.equal(seq, bat) and torch.equal(after_seq, after_bat), n
