@@ -518,7 +518,42 @@ unsigned las_prof_mask_get();
 // pointer-stable pooled buffer set (las_b200/functional.py::_SpellerSlot) -- and replayed with a single cudaGraphLaunch.  Any capture failure falls back to direct
 // enqueueing.  LAS_DEC_GRAPH=0 disables it; it is also bypassed while per-kernel profiling of inner kernels is on.
 namespace {
-struct GraphEntry { unsigned long long key; cudaGraphExec_t exec; unsigned long long stamp; int nlaunch; };
+struct GraphEntry { unsigned long long key; std::vector<cudaGraphExec_t> execs; unsigned long long stamp; int nlaunch; };
+
+// Lets an enqueue function cut the sequence it is recording into several graphs at decoder-step boundaries.  Launching a
+// 2000-node graph costs the host ~1 ms before the GPU sees its first node; when the host has no lead (the backward loop
+// starts right after the host waited for the attention map of the forward loop, and greedy decoding starts cold) that is
+// GPU idle time.  A short first segment lets the GPU start while the host launches the rest.  `seg == nullptr` (direct
+// enqueue) and `cut_at(i)` false are no-ops.
+struct GraphSeg {
+    cudaStream_t cs = nullptr;
+    std::vector<cudaGraphExec_t> execs;
+    int cuts[4] = {0, 0, 0, 0};
+    int ncuts = 0;
+    bool failed = false;
+    bool cut_at(int i) const {
+        for (int k = 0; k < ncuts; ++k) if (cuts[k] == i) return true;
+        return false;
+    }
+    int end_segment() {          // ends the running capture and instantiates it
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); failed = true; return LAS_ERR_CUDA; }
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess || !exec) { cudaGetLastError(); failed = true; return LAS_ERR_CUDA; }
+        execs.push_back(exec);
+        return LAS_OK;
+    }
+    int cut() {
+        if (end_segment() != LAS_OK) return LAS_ERR_CUDA;
+        if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); failed = true; return LAS_ERR_CUDA; }
+        return LAS_OK;
+    }
+    void destroy() { for (auto e : execs) cudaGraphExecDestroy(e); execs.clear(); }
+};
+inline int seg_step(GraphSeg* seg, int i) { return (seg && seg->cut_at(i)) ? seg->cut() : LAS_OK; }
 std::vector<GraphEntry> g_graphs;
 unsigned long long g_graph_clock = 0;
 long long g_graph_captures = 0, g_graph_replays = 0;
@@ -530,11 +565,11 @@ unsigned long long fnv1a(const void* p, size_t n, unsigned long long h) {
     for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ULL; }
     return h;
 }
-int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st);
+int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st, GraphSeg* seg);
 }  // namespace
 
 namespace {
-int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Layout& L, cudaStream_t st);
+int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Layout& L, cudaStream_t st, GraphSeg* seg);
 std::mutex g_graph_mu;
 
 // Runs `enqueue(stream)` through the graph cache: replay when `key` is known, else capture on a side stream, instantiate,
@@ -546,47 +581,62 @@ int run_graph_cached(unsigned long long key, cudaStream_t st, F enqueue) {
     const bool inner_prof = (las_prof_mask_get() & ((1u << LAS_PROF_GEMM_OTHER) | (1u << LAS_PROF_ATTN_FWD) | (1u << LAS_PROF_ATTN_BWD))) != 0;
     int dev = 0;
     cudaGetDevice(&dev);
-    if ((genv && atoi(genv) == 0) || inner_prof || dev < 0 || dev >= 64) return enqueue(st);
+    if ((genv && atoi(genv) == 0) || inner_prof || dev < 0 || dev >= 64) return enqueue(st, (GraphSeg*)nullptr);
     key = fnv1a(&dev, sizeof(dev), key);
     std::lock_guard<std::mutex> lk(g_graph_mu);
     for (auto& e : g_graphs)
         if (e.key == key) {
             e.stamp = ++g_graph_clock;
             ++g_graph_replays;
-            LAS_CUDA(cudaGraphLaunch(e.exec, st));
+            for (auto x : e.execs) LAS_CUDA(cudaGraphLaunch(x, st));
             las_count_launch(e.nlaunch);          // the replay runs the same kernels the capture recorded
             return LAS_OK;
         }
     if (!g_capture_stream_ok[dev]) {
-        if (cudaStreamCreateWithFlags(&g_capture_stream[dev], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return enqueue(st); }
+        if (cudaStreamCreateWithFlags(&g_capture_stream[dev], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return enqueue(st, (GraphSeg*)nullptr); }
         g_capture_stream_ok[dev] = true;
     }
-    cudaStream_t cs = g_capture_stream[dev];
-    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return enqueue(st); }
-    const long long launches_before = las_launch_count();
-    int rc = enqueue(cs);
-    cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-    if (rc != LAS_OK || ce != cudaSuccess || !graph) {
-        if (graph) cudaGraphDestroy(graph);
-        cudaGetLastError();
-        if (rc != LAS_OK) return rc;
-        return enqueue(st);
+    GraphSeg seg;
+    seg.cs = g_capture_stream[dev];
+    {   // decoder steps (counted from the first one enqueued) before which the graph is cut; LAS_DEC_GRAPH_CUTS="a,b,..", "0" = one graph
+        const char* cenv = getenv("LAS_DEC_GRAPH_CUTS");
+        const char* c = cenv ? cenv : "16,64";
+        while (*c && seg.ncuts < 4) {
+            const int v = atoi(c);
+            if (v > 0) seg.cuts[seg.ncuts++] = v;
+            while (*c && *c != ',') ++c;
+            if (*c == ',') ++c;
+        }
     }
-    cudaGraphExec_t exec = nullptr;
-    ce = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess || !exec) { cudaGetLastError(); return enqueue(st); }
+    if (cudaStreamBeginCapture(seg.cs, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return enqueue(st, (GraphSeg*)nullptr); }
+    const long long launches_before = las_launch_count();
+    int rc = enqueue(seg.cs, &seg);
+    if (seg.failed) {            // a cut failed: the stream may or may not still be capturing
+        cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(seg.cs, &cst) == cudaSuccess && cst != cudaStreamCaptureStatusNone) { cudaGraph_t g2 = nullptr; cudaStreamEndCapture(seg.cs, &g2); if (g2) cudaGraphDestroy(g2); }
+        cudaGetLastError();
+        seg.destroy();
+        return enqueue(st, (GraphSeg*)nullptr);
+    }
+    if (rc != LAS_OK) {
+        cudaGraph_t g2 = nullptr;
+        cudaStreamEndCapture(seg.cs, &g2);
+        if (g2) cudaGraphDestroy(g2);
+        cudaGetLastError();
+        seg.destroy();
+        return rc;
+    }
+    if (seg.end_segment() != LAS_OK) { seg.destroy(); return enqueue(st, (GraphSeg*)nullptr); }
     if (g_graphs.size() >= 8) {           // evict the least recently used
         size_t lru = 0;
         for (size_t i = 1; i < g_graphs.size(); ++i)
             if (g_graphs[i].stamp < g_graphs[lru].stamp) lru = i;
-        cudaGraphExecDestroy(g_graphs[lru].exec);
+        for (auto x : g_graphs[lru].execs) cudaGraphExecDestroy(x);
         g_graphs.erase(g_graphs.begin() + lru);
     }
-    g_graphs.push_back({key, exec, ++g_graph_clock, (int)(las_launch_count() - launches_before)});
+    g_graphs.push_back({key, seg.execs, ++g_graph_clock, (int)(las_launch_count() - launches_before)});
     ++g_graph_captures;
-    LAS_CUDA(cudaGraphLaunch(exec, st));
+    for (auto x : seg.execs) LAS_CUDA(cudaGraphLaunch(x, st));
     return LAS_OK;
 }
 }  // namespace
@@ -612,11 +662,11 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
     kd.use_gold_host = nullptr;
     unsigned long long key = fnv1a(&kd, sizeof(LasSpeller), 1469598103934665603ULL);
     if (s->use_gold_host) key = fnv1a(s->use_gold_host, (size_t)s->steps, key);
-    return run_graph_cached(key, st, [&](cudaStream_t q) { return speller_fwd_enqueue(s, L, q); });
+    return run_graph_cached(key, st, [&](cudaStream_t q, GraphSeg* seg) { return speller_fwd_enqueue(s, L, q, seg); });
 }
 
 namespace {
-int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
+int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st, GraphSeg* seg) {
     void* stream = (void*)st;
     (void)stream;
     const int B = s->B, T = s->T, P = s->P, E = s->E, DH = s->DH, DO = s->DO, V = s->V, S = s->steps, heads = s->heads;
@@ -705,6 +755,7 @@ int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st) {
 
     LasPdlScope pdl_scope;       // the per-step kernels below overlap their launch / prologue with the predecessor's tail
     for (int t = 0; t < S; ++t) {
+        RC(seg_step(seg, t));
         const int r = t % L.hist, rn = (t + 1) % L.hist, rg = t % L.ghist;
         float* S0r = S0 + (size_t)r * B * K0;  float* S0n = S0 + (size_t)rn * B * K0;
         float* S1r = S1 + (size_t)r * B * K1;  float* S1n = S1 + (size_t)rn * B * K1;
@@ -821,11 +872,11 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     unsigned long long key = fnv1a(&kd, sizeof(LasSpeller), 7809847782465536322ULL);
     if (s->use_gold_host) key = fnv1a(s->use_gold_host, (size_t)s->steps, key);
     key = fnv1a(g, sizeof(LasSpellerGrads), key);
-    return run_graph_cached(key, st, [&](cudaStream_t q) { return speller_bwd_enqueue(s, g, L, q); });
+    return run_graph_cached(key, st, [&](cudaStream_t q, GraphSeg* seg) { return speller_bwd_enqueue(s, g, L, q, seg); });
 }
 
 namespace {
-int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Layout& L, cudaStream_t st) {
+int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Layout& L, cudaStream_t st, GraphSeg* seg) {
     const int B = s->B, T = s->T, P = s->P, E = s->E, DH = s->DH, DO = s->DO, V = s->V, S = s->steps, heads = s->heads;
     const int K0 = P + DH, K1 = DH + DO, d_head = P / heads;
     float* f = s->fws;
@@ -895,6 +946,7 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
     {
     LasPdlScope pdl_scope;       // the per-step kernels overlap their launch / prologue with the predecessor's tail
     for (int t = S - 1; t >= 0; --t) {
+        RC(seg_step(seg, S - 1 - t));
         const int rn = t + 1;
         float* dQCn = dQC + (size_t)rn * B * 2 * P;
         // attention step (t+1): dctx_total = classifier path + cell-0 path of step t+1

@@ -469,6 +469,49 @@ def _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, 
     return s, keep
 
 
+class LazyHostTensor(torch.Tensor):
+    """CPU tensor whose bytes are still on their way from the device.
+
+    The reference returns the attention map of sample 0 as a CPU tensor from every forward (src/models.py:349,377,385); a
+    blocking copy there stalls the host until the decoder loop has drained, so the loss and the whole backward are then
+    enqueued with no lead over the GPU (~0.7 ms of idle GPU per batch).  This subclass owns a pinned-host copy issued with
+    `non_blocking=True` plus the CUDA event recorded after it; the first torch operation / method / property that touches the
+    tensor (`.numpy()`, indexing, printing, `np.asarray`, pickling ...) waits for the event, then behaves like the plain tensor.
+    """
+
+    @staticmethod
+    def __new__(cls, data, event):
+        t = torch.Tensor._make_subclass(cls, data, False)
+        t._las_event = event
+        return t
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def plain(a):
+            if isinstance(a, LazyHostTensor):
+                ev = a.__dict__.get('_las_event')
+                if ev is not None:
+                    ev.synchronize()
+                    a.__dict__['_las_event'] = None
+                return a.as_subclass(torch.Tensor)
+            if isinstance(a, (list, tuple)):
+                return type(a)(plain(x) for x in a)
+            return a
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*[plain(a) for a in args], **{k: plain(v) for k, v in (kwargs or {}).items()})
+
+
+def host_copy_lazy(t: torch.Tensor) -> torch.Tensor:
+    """`t.cpu()` without the host wait (see LazyHostTensor).  LAS_ATT_SYNC=1 -> the plain blocking copy."""
+    if (not t.is_cuda) or os.environ.get('LAS_ATT_SYNC', '0') == '1':
+        return t.cpu()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(t.device))
+    return LazyHostTensor(host, ev)
+
+
 class _SpellerSlot:
     """One pointer-stable buffer set for a decoder loop of a given shape: the staged inputs (K, V, lengths, gold tokens,
     dropout masks), the workspaces and the raw outputs.  las_speller_fwd_f32 replays a CUDA graph keyed on the descriptor

@@ -105,5 +105,5 @@ class Rewriter(nn.Module):
                                               pad_idx=self.CHR_PAD_IDX, training=self.training,
                                               dec_y=dec_y if self.training else None, use_gold=use_gold, drop0=drop0, drop1=drop1)
         self.last_chars = chars
-        att_wgts = att0.detach().permute(1, 2, 0).cpu()       # (heads, T_enc, steps+1) CPU tensor like the reference (:249-251)
+        att_wgts = LF.host_copy_lazy(att0.detach().permute(1, 2, 0))       # (heads, T_enc, steps+1) CPU tensor like the reference (:249-251)
         return logits, att_wgts

@@ -192,7 +192,7 @@ class Speller(nn.Module):
         self.last_chars = chars                         # (steps, B) greedy indices, device-side (extra, not in reference)
         # reference returns the attention map of sample 0 as a CPU tensor (heads, T_enc, steps+1) (:349,377,385):
         # one D2H at the end instead of one blocking copy per step
-        att_wgts = att0.detach().permute(1, 2, 0).cpu()
+        att_wgts = LF.host_copy_lazy(att0.detach().permute(1, 2, 0))
         return logits, att_wgts
 
 

@@ -33,18 +33,24 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
 t0, t1 = evs[0].time_range.start, max(e.time_range.end for e in evs)
-busy, cur_end, gaps = 0.0, t0, []
+busy, cur_end, gaps, prev = 0.0, t0, [], ''
 for e in evs:
     s, en = e.time_range.start, e.time_range.end
     if s > cur_end:
-        gaps.append((s - cur_end, e.name[:60])); busy += en - s; cur_end = en
+        gaps.append((s - cur_end, e.name[:50] + '   <- after ' + prev[:50], cur_end, s)); busy += en - s; cur_end = en; prev = e.name
     elif en > cur_end:
-        busy += en - cur_end; cur_end = en
+        busy += en - cur_end; cur_end = en; prev = e.name
 print(f'3 steps: wall {(t1 - t0) / 1e3:.2f} ms, GPU busy {busy / 1e3:.2f} ms, idle {(t1 - t0 - busy) / 1e3:.2f} ms in {len(gaps)} gaps')
 gaps.sort(reverse=True)
-for g, n in gaps[:15]: print(f'  gap {g:8.1f} us before {n}')
+cpu = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CPU]
+for i, (g, n, g0, g1) in enumerate(gaps[:15]):
+    print(f'  gap {g:8.1f} us before {n}')
+    if i < 4:          # what the host was doing while the GPU sat idle
+        for e in sorted(cpu, key=lambda e: e.time_range.start):
+            a, b = max(e.time_range.start, g0), min(e.time_range.end, g1)
+            if b - a > 40: print(f'        host {b - a:7.1f} us of {e.name[:70]} (whole call {e.time_range.end - e.time_range.start:.0f} us)')
 import collections
 small = collections.Counter(); 
-for g, n in gaps:
+for g, n, _, _ in gaps:
     small[n.split('<')[0][:40]] += g
 for n, g in small.most_common(12): print(f'  total gap {g / 1e3:7.2f} ms before {n}')

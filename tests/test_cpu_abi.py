@@ -134,3 +134,35 @@ def test_batched_coin_draw_equals_sequential_draws():
         bat = torch.rand(n)
         after_bat = torch.rand(4)
         assert torch.equal(seq, bat) and torch.equal(after_seq, after_bat), n
+
+
+def test_lazy_host_tensor_waits_once_then_acts_like_a_plain_tensor():
+    """The attention map comes back as a CPU tensor whose copy may still be in flight (las_b200.functional.LazyHostTensor):
+    the first use must wait for the copy's event, and everything a trainer does with the map must keep working."""
+    import io
+    import numpy as np
+    import torch
+    from las_b200.functional import LazyHostTensor
+
+    class Ev:
+        n = 0
+        def synchronize(self):
+            Ev.n += 1
+
+    base = torch.arange(24, dtype=torch.float32).view(2, 3, 4)
+    t = LazyHostTensor(base.clone(), Ev())
+    assert isinstance(t, torch.Tensor) and Ev.n == 0
+    assert t.device.type == 'cpu' and Ev.n == 1                   # any access waits ...
+    assert tuple(t.shape) == (2, 3, 4) and Ev.n == 1              # ... once
+    a = np.asarray(t)
+    assert a.shape == (2, 3, 4) and np.array_equal(a, base.numpy())
+    r = t[0] * 2 + 1
+    assert type(r) is torch.Tensor and torch.equal(r, base[0] * 2 + 1)
+    assert torch.equal(torch.stack([t, t]).sum(0), 2 * base)
+    assert type(t.permute(1, 2, 0)) is torch.Tensor
+    assert 'tensor' in repr(t)
+    buf = io.BytesIO(); torch.save(t.clone(), buf); buf.seek(0)
+    assert torch.equal(torch.load(buf), base)
+    for fresh in (LazyHostTensor(base.clone(), Ev()),):
+        n0 = Ev.n
+        assert fresh.numpy().sum() == base.sum() and Ev.n == n0 + 1
