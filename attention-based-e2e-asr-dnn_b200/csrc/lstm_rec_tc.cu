@@ -36,6 +36,8 @@ struct RecTcArgs {
     float* out;            // (B, T, ndir*H) or null
     float* hs_pad;         // (B, T+2, ndir*H) fp32
     float* cs_pad;         // (B, T+2, ndir*H) fp32
+    __nv_bfloat16* out16;  // optional bf16 copy of `out` (B, T, ndir*H): the next layer's GEMM operand, written here instead of by a cast pass
+    __nv_bfloat16* hs16;   // optional bf16 copy of hs_pad (B, T+2, ndir*H): the dW_hh GEMM operand of backward; hs_pad may then be null
     __nv_bfloat16* hbuf;   // (ndir, 2, Bpad, H) bf16 exchange buffer
     unsigned* ctr;         // (ndir, nslices) step counters
     int B, T, H, ndir, nslices, Bpad, chains, bsg, save;
@@ -332,7 +334,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                 const int b = slice * NB_SLICE + q * 8 + i;
                 if (b < a.B) {
                     const long long o0 = (long long)b * brow + dir * H + u, o1 = o0 + (long long)(T + 1) * F;
-                    a.hs_pad[o0] = 0.f; a.cs_pad[o0] = 0.f; a.hs_pad[o1] = 0.f; a.cs_pad[o1] = 0.f;
+                    a.cs_pad[o0] = 0.f; a.cs_pad[o1] = 0.f;
+                    if (a.hs_pad) { a.hs_pad[o0] = 0.f; a.hs_pad[o1] = 0.f; }
+                    if (a.hs16) { a.hs16[o0] = __float2bfloat16(0.f); a.hs16[o1] = __float2bfloat16(0.f); }
                 }
             }
         }
@@ -418,11 +422,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     const int b = b0 + q * 8 + i;
                     if (b < a.B) {
                         const long long so = (long long)b * brow + (long long)(t + 1) * F + dir * H + u;
-                        a.hs_pad[so] = hh[i];
+                        if (a.hs_pad) a.hs_pad[so] = hh[i];
+                        if (a.hs16) a.hs16[so] = __float2bfloat16(hh[i]);
                         a.cs_pad[so] = cc[i];
-                        if (a.out) {
+                        if (a.out || a.out16) {
                             const float m = a.mask ? a.mask[(long long)b * F + dir * H + u] : 1.f;
-                            a.out[((long long)b * T + t) * F + dir * H + u] = hh[i] * m;
+                            const long long oo = ((long long)b * T + t) * F + dir * H + u;
+                            if (a.out) a.out[oo] = hh[i] * m;
+                            if (a.out16) a.out16[oo] = __float2bfloat16(hh[i] * m);
                         }
                     }
                 }
@@ -649,7 +656,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
                 const int b = slice * NB_SLICE + q * 8 + i;
                 if (b < a.B) {
                     const long long o0 = (long long)b * brow + dir * H + u, o1 = o0 + (long long)(T + 1) * F;
-                    a.hs_pad[o0] = 0.f; a.cs_pad[o0] = 0.f; a.hs_pad[o1] = 0.f; a.cs_pad[o1] = 0.f;
+                    a.cs_pad[o0] = 0.f; a.cs_pad[o1] = 0.f;
+                    if (a.hs_pad) { a.hs_pad[o0] = 0.f; a.hs_pad[o1] = 0.f; }
+                    if (a.hs16) { a.hs16[o0] = __float2bfloat16(0.f); a.hs16[o1] = __float2bfloat16(0.f); }
                 }
             }
         }
@@ -743,11 +752,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
                     const int b = b0 + q * 8 + i;
                     if (b < a.B) {
                         const long long so = (long long)b * brow + (long long)(t + 1) * F + dir * H + u;
-                        a.hs_pad[so] = hh[i];
+                        if (a.hs_pad) a.hs_pad[so] = hh[i];
+                        if (a.hs16) a.hs16[so] = __float2bfloat16(hh[i]);
                         a.cs_pad[so] = cc[i];
-                        if (a.out) {
+                        if (a.out || a.out16) {
                             const float m = a.mask ? a.mask[(long long)b * F + dir * H + u] : 1.f;
-                            a.out[((long long)b * T + t) * F + dir * H + u] = hh[i] * m;
+                            const long long oo = ((long long)b * T + t) * F + dir * H + u;
+                            if (a.out) a.out[oo] = hh[i] * m;
+                            if (a.out16) a.out16[oo] = __float2bfloat16(hh[i] * m);
                         }
                     }
                 }
@@ -1180,10 +1192,10 @@ extern "C" size_t las_lstm_rec_tc_workspace_bytes(int B, int H, int ndir) {
     return 1024 + (size_t)ndir * 2 * 4 * nsl * NB_SLICE * H * 4;
 }
 
-extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const int* lens, const float* drop_mask, float* out,
-                                   float* hs_pad, float* cs_pad, int B, int T, int H, int ndir, int save_gates, void* ws, size_t ws_bytes,
-                                   void* stream) {
-    LAS_CHECK_ARG(gates && w_hh_bf16 && lens && hs_pad && cs_pad && ws, "lstm_rec_fwd_tc: null pointer");
+static int rec_fwd_tc_impl(float* gates, const void* w_hh_bf16, const int* lens, const float* drop_mask, float* out, float* hs_pad,
+                           float* cs_pad, int B, int T, int H, int ndir, int save_gates, void* ws, size_t ws_bytes,
+                           __nv_bfloat16* out16, __nv_bfloat16* hs16, void* stream) {
+    LAS_CHECK_ARG(gates && w_hh_bf16 && lens && (hs_pad || hs16) && cs_pad && ws, "lstm_rec_fwd_tc: null pointer");
     LAS_CHECK_ARG(B >= 1 && T >= 1 && (ndir == 1 || ndir == 2), "lstm_rec_fwd_tc: bad dims");
     int rc = las_set_device_of(gates);
     if (rc) return rc;
@@ -1204,9 +1216,10 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
             const long long F = (long long)ndir * H;
             for (int b0 = 0; b0 < B; b0 += rows) {
                 const int nb = B - b0 < rows ? B - b0 : rows;
-                rc = las_lstm_rec_fwd_tc(gates + (long long)b0 * T * ndir * 4 * H, w_hh_bf16, lens + b0, drop_mask ? drop_mask + b0 * F : nullptr,
-                                         out ? out + (long long)b0 * T * F : nullptr, hs_pad + (long long)b0 * (T + 2) * F,
-                                         cs_pad + (long long)b0 * (T + 2) * F, nb, T, H, ndir, save_gates, ws, ws_bytes, stream);
+                rc = rec_fwd_tc_impl(gates + (long long)b0 * T * ndir * 4 * H, w_hh_bf16, lens + b0, drop_mask ? drop_mask + b0 * F : nullptr,
+                                     out ? out + (long long)b0 * T * F : nullptr, hs_pad ? hs_pad + (long long)b0 * (T + 2) * F : nullptr,
+                                     cs_pad + (long long)b0 * (T + 2) * F, nb, T, H, ndir, save_gates, ws, ws_bytes,
+                                     out16 ? out16 + (long long)b0 * T * F : nullptr, hs16 ? hs16 + (long long)b0 * (T + 2) * F : nullptr, stream);
                 if (rc) return rc;
             }
             return LAS_OK;
@@ -1215,7 +1228,7 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
     {
         const char* e = getenv("LAS_REC_LL");
         const int KBh = H / 64;
-        if ((e && atoi(e) != 0) && (KBh == 1 || KBh == 2 || KBh == 4 || KBh == 8) && (p.chains == 1 || (e && atoi(e) == 2))) {
+        if ((e && atoi(e) != 0) && hs_pad && !out16 && !hs16 && (KBh == 1 || KBh == 2 || KBh == 4 || KBh == 8) && (p.chains == 1 || (e && atoi(e) == 2))) {
             RecLlArgs la{};
             la.gates = gates; la.lens = lens; la.mask = drop_mask; la.out = out; la.hs_pad = hs_pad; la.cs_pad = cs_pad;
             la.ll = (unsigned long long*)((char*)ws + 1024);
@@ -1252,7 +1265,7 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
         }
     }
     RecTcArgs a{};
-    a.gates = gates; a.lens = lens; a.mask = drop_mask; a.out = out; a.hs_pad = hs_pad; a.cs_pad = cs_pad;
+    a.gates = gates; a.lens = lens; a.mask = drop_mask; a.out = out; a.hs_pad = hs_pad; a.cs_pad = cs_pad; a.out16 = out16; a.hs16 = hs16;
     a.ctr = (unsigned*)ws; a.hbuf = (__nv_bfloat16*)((char*)ws + 1024);
     a.B = B; a.T = T; a.H = H; a.ndir = ndir; a.nslices = p.nslices; a.Bpad = p.Bpad; a.chains = p.chains; a.bsg = p.bsg; a.save = save_gates; a.dbg = g_rec_dbg;
     a.w_gl = (const __nv_bfloat16*)w_hh_bf16;
@@ -1342,6 +1355,24 @@ extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const in
     LAS_CUDA(cudaLaunchCooperativeKernel(kern, dim3(p.rs, p.bsg, ndir), dim3(NTHREADS), args, p.smem, st));
     las_count_launch(1);
     return LAS_OK;
+}
+
+extern "C" int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const int* lens, const float* drop_mask, float* out,
+                                   float* hs_pad, float* cs_pad, int B, int T, int H, int ndir, int save_gates, void* ws, size_t ws_bytes,
+                                   void* stream) {
+    LAS_CHECK_ARG(hs_pad, "lstm_rec_fwd_tc: null pointer");
+    return rec_fwd_tc_impl(gates, w_hh_bf16, lens, drop_mask, out, hs_pad, cs_pad, B, T, H, ndir, save_gates, ws, ws_bytes, nullptr, nullptr, stream);
+}
+
+// Same, plus bf16 copies of the two outputs that only GEMMs read afterwards: `out_bf16` (B, T, ndir*H) = the layer output (after
+// locked dropout) as the next layer's / key_map's / value_map's A operand, `hs_bf16` (B, T+2, ndir*H) = the zero-framed hidden
+// states as the dW_hh operand of backward.  Either may be null; `hs_pad` (fp32) may be null when `hs_bf16` is given, `out` when
+// nobody reads the fp32 output.  Saves one fp32 read + bf16 write pass over (B, T, ndir*H) per copy.
+extern "C" int las_lstm_rec_fwd_tc_ex(float* gates, const void* w_hh_bf16, const int* lens, const float* drop_mask, float* out,
+                                      float* hs_pad, float* cs_pad, int B, int T, int H, int ndir, int save_gates, void* ws,
+                                      size_t ws_bytes, void* out_bf16, void* hs_bf16, void* stream) {
+    return rec_fwd_tc_impl(gates, w_hh_bf16, lens, drop_mask, out, hs_pad, cs_pad, B, T, H, ndir, save_gates, ws, ws_bytes,
+                           (__nv_bfloat16*)out_bf16, (__nv_bfloat16*)hs_bf16, stream);
 }
 
 // =====================================================================================================================

@@ -131,6 +131,7 @@ SIGNATURES = {
     'las_lstm_rec_tc_supported': (C.c_int, [C.c_int, C.c_int, C.c_int]),
     'las_lstm_rec_tc_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'las_lstm_rec_fwd_tc': (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    'las_lstm_rec_fwd_tc_ex': (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     'las_lstm_rec_tc_set_debug': (None, [C.c_void_p]),
     'las_lstm_rec_bwd_tc': (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'las_lstm_rec_bwd_tc_dbias_slices': (C.c_int, [C.c_int, C.c_int, C.c_int]),

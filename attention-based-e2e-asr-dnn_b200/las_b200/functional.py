@@ -104,12 +104,24 @@ def _rows3d(x: torch.Tensor):
     return x.stride(0), x.stride(1)
 
 
+def _bf16_shadow(x: torch.Tensor) -> Optional[torch.Tensor]:
+    """bf16 copy of `x` left on it by the recurrence kernel that produced it (lstm_layer), or None.  Only valid while `x` has not
+    been written to since (version counter), so an in-place edit by the caller silently falls back to the cast pass."""
+    sh = getattr(x, '_las_bf16', None)
+    if sh is None or not use_tensor_cores():
+        return None
+    t, ver = sh
+    if ver != x._version or tuple(t.shape) != tuple(x.shape) or t.device != x.device or not t.is_contiguous():
+        return None
+    return t
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # nn.Linear on (B, T, F) / (M, F) inputs -- key_map / value_map / query_map (reference src/models.py:143-149,166)
 # ----------------------------------------------------------------------------------------------------------------------
 class LinearFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, bias2=None):
+    def forward(ctx, x, weight, bias, bias2=None, x16=None):
         _require_cuda(x, weight, bias, bias2)
         x = x if x.dtype == torch.float32 else x.float()
         if x.stride(-1) != 1:
@@ -135,7 +147,7 @@ class LinearFunction(torch.autograd.Function):
         tc = use_tensor_cores() and K % 8 == 0 and N % 4 == 0 and M >= 64
         if tc:
             # AMP mode: bf16 operands on the tensor pipe, fp32 accumulate / output
-            xb = cast_bf16(x, M, K, K, am[1], inner=am[2], bs=am[0])          # (M, K) bf16 compact
+            xb = x16.view(M, K) if x16 is not None else cast_bf16(x, M, K, K, am[1], inner=am[2], bs=am[0])   # (M, K) bf16 compact
             wb = cast_bf16(weight, N, K, K, K)
             gemm_tc(xb, wb, out, M, N, K, a_s1=K, b_s1=K, ldc=N, bias1=b1, bias2=b2, gate=False)
             ctx.save_for_backward(xb, wb)
@@ -178,11 +190,11 @@ class LinearFunction(torch.autograd.Function):
             else:
                 db2 = torch.empty(N, dtype=torch.float32, device=dy.device)
                 colsum(dy, N, M, N, db2)
-        return dx, dw, db, db2
+        return dx, dw, db, db2, None
 
 
 def linear(x, weight, bias=None, bias2=None):
-    return LinearFunction.apply(x, weight, bias, bias2)
+    return LinearFunction.apply(x, weight, bias, bias2, _bf16_shadow(x) if x.dim() == 3 else None)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -191,7 +203,7 @@ def linear(x, weight, bias=None, bias2=None):
 # ----------------------------------------------------------------------------------------------------------------------
 class LSTMLayerFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, lens_dev, T, pyramid, mask, *weights):
+    def forward(ctx, x, lens_dev, T, pyramid, mask, x16, *weights):
         """x (B, Tin, D) fp32 with contiguous features; lens_dev (B) int32 = lengths AFTER the pyramid halving;
         T = max of those lengths; weights = (w_ih, w_hh, b_ih, b_hh) per direction."""
         _require_cuda(x, lens_dev, *weights)
@@ -207,6 +219,7 @@ class LSTMLayerFunction(torch.autograd.Function):
         if pyramid:
             if st != D:            # frame pairs must be adjacent in memory for the concat-as-addressing trick
                 x = x.contiguous()
+                x16 = None
                 sb, st = _rows3d(x)
             Din, st_eff = 2 * D, 2 * st
             assert 2 * T <= Tin
@@ -230,7 +243,10 @@ class LSTMLayerFunction(torch.autograd.Function):
             if pyramid:
                 Dp = D
             Kp = 2 * Dp if pyramid else Dp
-            xb = cast_bf16(x, Bn * Tin, D, Dp, st, inner=Tin, bs=sb)                      # (B*Tin, Dp) bf16, compact
+            if x16 is not None and Dp == D:
+                xb = x16.view(Bn * Tin, D)                                                # written by the producing recurrence kernel
+            else:
+                xb = cast_bf16(x, Bn * Tin, D, Dp, st, inner=Tin, bs=sb)                  # (B*Tin, Dp) bf16, compact
             wcat = torch.empty(NG, Kp, dtype=torch.bfloat16, device=dev)
             for d in range(ndir):
                 cast_bf16(ws[4 * d], G4, Din, Kp, Din, dst=wcat, dst_off=d * G4 * Kp)
@@ -245,20 +261,27 @@ class LSTMLayerFunction(torch.autograd.Function):
                 gemm_raw(x, w_ih, gates, Bn * T, G4, Din, am=(sb, st_eff, T), ak=(0, 1, 0), bk=(0, 1, 0), bn=Din,
                          cm=(0, NG, 0), bias1=b_ih, bias2=b_hh, c_off=d * G4, gate=True)
         w_hh = torch.stack([ws[4 * d + 1] for d in range(ndir)], 0).contiguous()
-        hs_pad = torch.empty(Bn, T + 2, F_, dtype=torch.float32, device=dev)
+        rec_tc = tc and os.environ.get('LAS_REC_TC', '1') == '1' and bool(lib.las_lstm_rec_tc_supported(Bn, H, ndir))
+        train = any(ctx.needs_input_grad)
+        # tensor-pipe recurrence: what only GEMMs read afterwards (the next layer's input, the dW_hh operand) is written as bf16 by
+        # the kernel itself; the fp32 hidden states are then only needed when they ARE the output (no locked-dropout mask)
+        shadows = rec_tc and os.environ.get('LAS_REC_BF16_OUT', '1') == '1'
+        out16 = torch.empty(Bn, T, F_, dtype=torch.bfloat16, device=dev) if shadows else None
+        hs16 = torch.empty(Bn, T + 2, F_, dtype=torch.bfloat16, device=dev) if (shadows and train) else None
+        need_hs32 = (mask is None) or hs16 is None
+        hs_pad = torch.empty(Bn, T + 2, F_, dtype=torch.float32, device=dev) if need_hs32 else None
         cs_pad = torch.empty(Bn, T + 2, F_, dtype=torch.float32, device=dev)
         out = torch.empty(Bn, T, F_, dtype=torch.float32, device=dev) if mask is not None else None
         if mask is not None:
             mask = _f32c(mask).reshape(Bn, F_)
-        rec_tc = tc and os.environ.get('LAS_REC_TC', '1') == '1' and bool(lib.las_lstm_rec_tc_supported(Bn, H, ndir))
         if rec_tc:
             # tensor-pipe recurrence: W_hh as bf16 (ndir*4H, H), resident in shared memory inside the kernel
             w_hh_b = cast_bf16(w_hh, ndir * G4, H, H, H)
             nbytes = lib.las_lstm_rec_tc_workspace_bytes(Bn, H, ndir)
             wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            check(lib.las_lstm_rec_fwd_tc(gates.data_ptr(), w_hh_b.data_ptr(), lens_dev.data_ptr(), ptr(mask), ptr(out),
-                                          hs_pad.data_ptr(), cs_pad.data_ptr(), Bn, T, H, ndir, int(any(ctx.needs_input_grad)), wsb.data_ptr(),
-                                          nbytes, stream_ptr()), 'lstm_rec_fwd_tc')
+            check(lib.las_lstm_rec_fwd_tc_ex(gates.data_ptr(), w_hh_b.data_ptr(), lens_dev.data_ptr(), ptr(mask), ptr(out),
+                                             ptr(hs_pad), cs_pad.data_ptr(), Bn, T, H, ndir, int(train), wsb.data_ptr(),
+                                             nbytes, ptr(out16), ptr(hs16), stream_ptr()), 'lstm_rec_fwd_tc')
         else:
             nbytes = lib.las_lstm_rec_workspace_bytes(Bn, H, ndir)
             wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -266,15 +289,17 @@ class LSTMLayerFunction(torch.autograd.Function):
                                            hs_pad.data_ptr(), cs_pad.data_ptr(), Bn, T, H, ndir, wsb.data_ptr(), nbytes,
                                            stream_ptr()), 'lstm_rec_fwd')
         if tc:
-            ctx.save_for_backward(xb, lens_dev, gates, hs_pad, cs_pad, w_hh, mask, wcat)
+            ctx.save_for_backward(xb, lens_dev, gates, hs16 if hs16 is not None else hs_pad, cs_pad, w_hh, mask, wcat)
         else:
             ctx.save_for_backward(x, lens_dev, gates, hs_pad, cs_pad, w_hh, mask, *ws)
         ctx.dims = (Bn, Tin, D, T, H, ndir, Din, sb, st_eff, bool(pyramid), tc, Dp, Kp)
         y = out if out is not None else hs_pad[:, 1:T + 1]
-        return y
+        if out16 is not None:
+            ctx.mark_non_differentiable(out16)
+        return y, out16
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _d16=None):
         lib = _lib.load()
         x, lens_dev, gates, hs_pad, cs_pad, w_hh, mask, *ws = ctx.saved_tensors
         Bn, Tin, D, T, H, ndir, Din, sb, st_eff, pyramid, tc, Dp, Kp = ctx.dims
@@ -323,7 +348,7 @@ class LSTMLayerFunction(torch.autograd.Function):
             dwcat = torch.empty(NG, Kp, dtype=torch.float32, device=dev)
             gemm_tc(dGb, xb, dwcat, NG, Kp, T, k_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=(2 * Dp if pyramid else Dp),
                     b_s2=Tin * Dp, ldc=Kp, a_mn=True, b_mn=True, flops=2.0 * Bn * T * NG * Din)
-            hsb = cast_bf16(hs_pad, Bn * (T + 2), F_, F_, F_)                             # (B*(T+2), F) bf16
+            hsb = hs_pad if hs_pad.dtype == torch.bfloat16 else cast_bf16(hs_pad, Bn * (T + 2), F_, F_, F_)   # (B*(T+2), F) bf16
             for d in range(ndir):
                 dw_ih = dwcat[d * G4:(d + 1) * G4, :Din].contiguous()
                 dw_hh = torch.empty(G4, H, dtype=torch.float32, device=dev)
@@ -336,7 +361,7 @@ class LSTMLayerFunction(torch.autograd.Function):
                 else:
                     colsum(dG, NG, M, G4, db, x_off=d * G4)
                 grads += [dw_ih, dw_hh, db, db.clone()]
-            return (dx, None, None, None, None, *grads)
+            return (dx, None, None, None, None, None, *grads)
         if ctx.needs_input_grad[0]:
             full = (Tin * D == T * Din)
             dx = (torch.empty if full else torch.zeros)(Bn, Tin, D, dtype=torch.float32, device=dev)
@@ -354,11 +379,14 @@ class LSTMLayerFunction(torch.autograd.Function):
             db = torch.empty(G4, dtype=torch.float32, device=dev)
             colsum(dG, NG, M, G4, db, x_off=d * G4)
             grads += [dw_ih, dw_hh, db, db.clone()]
-        return (dx, None, None, None, None, *grads)
+        return (dx, None, None, None, None, None, *grads)
 
 
 def lstm_layer(x, lens_dev, T, pyramid, mask, weights: Sequence[torch.Tensor]):
-    return LSTMLayerFunction.apply(x, lens_dev, int(T), bool(pyramid), mask, *weights)
+    y, y16 = LSTMLayerFunction.apply(x, lens_dev, int(T), bool(pyramid), mask, _bf16_shadow(x), *weights)
+    if y16 is not None:
+        y._las_bf16 = (y16, y._version)          # picked up by the next lstm_layer / linear (see _bf16_shadow)
+    return y
 
 
 # ----------------------------------------------------------------------------------------------------------------------
