@@ -452,6 +452,10 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     }
 }
 
+// LasGemmTc::max_ctas of the call being launched (0 = one CTA per SM): lets a GEMM that runs beside a persistent recurrence kernel on
+// another stream take only the SMs that kernel leaves free
+thread_local int t_max_ctas = 0;
+
 template <bool A_MN, bool B_MN, int BN, int EPI = 0>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, cudaStream_t st) {
     auto kern = gemm_bf16_tc_kernel<A_MN, B_MN, BN, EPI>;
@@ -463,6 +467,7 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, cud
     }
     const int total = g.NB * g.mt_per_b * g.nt * (g.splitk > 1 ? g.splitk : 1);
     int grid = las_device_info()->num_sms;
+    if (t_max_ctas > 0 && grid > t_max_ctas) grid = t_max_ctas;
     if (grid > total) grid = total;
     LAS_CUDA(las_launch(kern, dim3(grid), dim3(NTHREADS), SMEM_BYTES, st, ta, tb, g));
     LAS_LAUNCH_CHECK();
@@ -573,6 +578,7 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
     LAS_CHECK_ARG(d->ldc % 4 == 0 && ((uintptr_t)d->C & 15) == 0 && d->c_bs % 4 == 0, "gemm_tc: C must be 16-byte aligned with ldc %% 4 == 0");
     int rc = las_set_device_of(d->C);
     if (rc) return rc;
+    struct CapScope { CapScope(int v) { t_max_ctas = v; } ~CapScope() { t_max_ctas = 0; } } cap_scope(d->max_ctas);
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap ta, tb;
     TcArgs g{};

@@ -17,6 +17,7 @@
 #include "las_common.cuh"
 #include "las_b200.h"
 #include <cuda.h>
+#include <mutex>
 #include <stdlib.h>
 
 static long long* g_rec_dbg = nullptr;   // debug aid, see las_lstm_rec_tc_set_debug
@@ -1401,6 +1402,7 @@ struct RecTcBwdArgs {
     float* dbp;               // optional (ndir, nslices, 4H): per-batch-slice bias-gradient partial sums; when given the fp32
                               // d(pre-activation) write-back into `gates` is skipped (its only reader was the bias column sum)
     long long* dbg;
+    unsigned* start_ctr;      // optional: every CTA adds 1 when it starts (a second stream waits for the sum, see las_set_launch_start_stream)
 };
 
 constexpr uint32_t IDESC_BWD = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UNITS >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
@@ -1624,6 +1626,46 @@ extern "C" int las_transpose_cast_bf16(const float* src, void* dst, int batch, i
     return LAS_OK;
 }
 
+// ---- "start" hand-off to a second stream (las_set_launch_start_stream) ----
+// The next backward launch of this thread releases `t_start_stream` -- a stream other than the one the kernel runs on -- as soon
+// as every CTA of the recurrence kernel is resident: each CTA bumps a device counter on entry and the side stream sits in a
+// cuStreamWaitValue32 on it.  Work queued on that stream afterwards (the weight-gradient GEMMs of the layer above, capped to the
+// SMs the recurrence leaves free) then runs BESIDE the latency-bound recurrence without having delayed its cluster placement.
+// (A programmatic launch event with triggerAtBlockStart was tried first: a stream waiting on it was only released when the
+// kernel had finished.)  On the variants that do not carry the counter, or if the driver refuses the wait, the side stream
+// waits for the kernel's completion instead -- correct, without overlap; las_launch_start_mode() tells which.
+static thread_local cudaStream_t t_start_stream = nullptr;
+static thread_local bool t_start_armed = false;
+static thread_local int t_start_mode = 0;
+extern "C" void las_set_launch_start_stream(void* side_stream) {
+    t_start_stream = (cudaStream_t)side_stream;
+    t_start_armed = side_stream != nullptr;
+    t_start_mode = 0;
+}
+extern "C" int las_launch_start_mode(void) { return t_start_mode; }
+
+namespace {
+std::mutex g_start_mu;
+unsigned* g_start_ctr[64];          // per device: CTA-start counter (never reset: targets advance, the comparison is cyclic)
+unsigned g_start_target[64];
+}  // namespace
+
+// an armed hand-off that no launcher consumed: release the side stream when everything enqueued on `st` so far has finished
+struct StartEventScope {
+    cudaStream_t st;
+    bool outer;
+    explicit StartEventScope(cudaStream_t s, bool o) : st(s), outer(o) {}
+    ~StartEventScope() {
+        if (!outer || !t_start_armed) return;
+        t_start_armed = false;
+        static thread_local cudaEvent_t ev = nullptr;
+        if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ev = nullptr; }
+        if (ev && cudaEventRecord(ev, st) == cudaSuccess && cudaStreamWaitEvent(t_start_stream, ev, 0) == cudaSuccess) return;
+        cudaGetLastError();
+        cudaStreamSynchronize(st);          // last resort: the host waits
+    }
+};
+
 static int launch_bwd_tc2(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16, const int* lens,
                           const float* drop_mask, int B, int T, int H, int ndir, void* ws, cudaStream_t st, void* stream, float* dbp);
 static int launch_bwd_dsm(const float* dout, float* gates, void* dgates_bf16, const float* cs_pad, const void* w_hh_t_bf16, const int* lens,
@@ -1672,6 +1714,9 @@ static int rec_bwd_tc_impl(const float* dout, float* gates, void* dgates_bf16, c
     if (rc) return rc;
     if (ws_bytes < las_lstm_rec_tc_workspace_bytes(B, H, ndir)) { las_set_error("lstm_rec_bwd_tc: workspace too small"); return LAS_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
+    static thread_local int depth = 0;
+    struct Depth { Depth() { ++depth; } ~Depth() { --depth; } } depth_scope;
+    StartEventScope start_event_scope(st, depth == 1);
     {
         // same batch passes as the forward launcher when the rows do not fit one chain per CTA
         const char* sb = getenv("LAS_REC_SPLIT_BATCH");
@@ -2119,6 +2164,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
 __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const RecTcBwdArgs a) {
     constexpr bool WTMEM = true;
     extern __shared__ uint8_t smem_raw[];
+    if (a.start_ctr && threadIdx.x == 0) atomicAdd(a.start_ctr, 1u);   // "this CTA is resident"
+
     const int H = a.H, T = a.T, KB = H / 64;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int RS = 4 * (H / 128);                                      // CTAs of the group = cluster size
@@ -2498,7 +2545,48 @@ static int launch_bwd_dsm(const float* dout, float* gates, void* dgates_bf16, co
     int nclusters = 0;
     if (cudaOccupancyMaxActiveClusters(&nclusters, kd, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); return LAS_ERR_UNSUPPORTED; }
     LasProfScope prof(LAS_PROF_REC_BWD, stream, (double)T);
-    if (cudaLaunchKernelEx(&cfg, kd, a) != cudaSuccess) { cudaGetLastError(); return LAS_ERR_UNSUPPORTED; }
+    int dev = -1;
+    unsigned target = 0;
+    if (t_start_armed && nclusters >= nslices * ndir && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+        std::lock_guard<std::mutex> lk(g_start_mu);
+        if (!g_start_ctr[dev]) {
+            if (cudaMalloc(&g_start_ctr[dev], 256) != cudaSuccess || cudaMemset(g_start_ctr[dev], 0, 256) != cudaSuccess) {
+                cudaGetLastError();
+                g_start_ctr[dev] = nullptr;
+            }
+            g_start_target[dev] = 0;
+        }
+        if (g_start_ctr[dev]) {
+            a.start_ctr = g_start_ctr[dev];
+            g_start_target[dev] += (unsigned)(rs * nslices * ndir);
+            target = g_start_target[dev];
+        }
+    }
+    if (cudaLaunchKernelEx(&cfg, kd, a) != cudaSuccess) {
+        cudaGetLastError();
+        if (a.start_ctr) {          // no CTA ran: take the target back so that counter and target stay in step
+            std::lock_guard<std::mutex> lk(g_start_mu);
+            g_start_target[dev] -= (unsigned)(rs * nslices * ndir);
+        }
+        return LAS_ERR_UNSUPPORTED;
+    }
+    if (a.start_ctr) {
+        // (driver entry point looked up at run time: the library must load on machines without libcuda, e.g. for the CPU-side ABI tests)
+        typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+        static WaitValue32Fn wait_value32 = nullptr;
+        if (!wait_value32) {
+            void* pfn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &pfn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+                wait_value32 = (WaitValue32Fn)pfn;
+            else
+                cudaGetLastError();
+        }
+        if (wait_value32 && wait_value32((CUstream)t_start_stream, (CUdeviceptr)a.start_ctr, target, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS) {
+            t_start_armed = false;
+            t_start_mode = 1;
+        }                           // else: still armed -> the caller's scope makes the side stream wait for completion
+    }
     las_count_launch(1);
     return LAS_OK;
 }

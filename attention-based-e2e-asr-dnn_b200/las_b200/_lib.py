@@ -43,6 +43,7 @@ class LasGemmTc(C.Structure):
         ('prof_flops', C.c_double),
         ('splitk', C.c_int),
         ('workspace', C.c_void_p),
+        ('max_ctas', C.c_int),
     ]
 
 
@@ -131,6 +132,8 @@ SIGNATURES = {
     'las_lstm_rec_tc_supported': (C.c_int, [C.c_int, C.c_int, C.c_int]),
     'las_lstm_rec_tc_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'las_lstm_rec_fwd_tc': (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    'las_set_launch_start_stream': (None, [C.c_void_p]),
+    'las_launch_start_mode': (C.c_int, []),
     'las_lstm_rec_fwd_tc_ex': (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     'las_lstm_rec_tc_set_debug': (None, [C.c_void_p]),
     'las_lstm_rec_bwd_tc': (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -67,6 +67,7 @@ class BucketedGradReducer:
             off = 0
             for p in ps:
                 p.grad = flat[off:off + p.numel()].view_as(p)
+                p._las_bucketed = True          # gradients may be accumulated in place, outside autograd (functional.py, backward overlap)
                 off += p.numel()
                 self._bucket_of[id(p)] = bi
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))

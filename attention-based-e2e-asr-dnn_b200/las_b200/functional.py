@@ -53,7 +53,8 @@ def gemm_raw(A, B, Cout, M, N, K, *, am=(0, 0, 0), ak=(0, 1, 0), bk=(0, 1, 0), b
 
 
 def gemm_tc(A, B, Cout, M, N, K, *, a_batches=1, k_batches=1, a_s1, a_s2=0, b_s1, b_s2=0, c_bs=0, ldc, a_mn=False, b_mn=False,
-            bias1=None, bias2=None, accumulate=False, lens=None, a_off=0, b_off=0, c_off=0, gate=True, flops=0.0, splitk=0):
+            bias1=None, bias2=None, accumulate=False, lens=None, a_off=0, b_off=0, c_off=0, gate=True, flops=0.0, splitk=0,
+            max_ctas=0):
     """las_gemm_bf16_tc wrapper; A/B are bf16 tensors, Cout fp32; *_off are element offsets."""
     d = LasGemmTc()
     d.A = A.data_ptr() + 2 * a_off
@@ -68,6 +69,7 @@ def gemm_tc(A, B, Cout, M, N, K, *, a_batches=1, k_batches=1, a_s1, a_s2=0, b_s1
     d.lens = ptr(lens)
     d.prof_tag = 1 if gate else 0
     d.prof_flops = float(flops)
+    d.max_ctas = int(max_ctas)
     ws = None
     if a_mn and splitk == 0:
         # weight-gradient form: few output tiles, long reduction -> split K so every SM has a tile
@@ -198,12 +200,103 @@ def linear(x, weight, bias=None, bias2=None):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# Backward overlap: weight-gradient GEMMs of layer l+1 beside the BPTT kernel of layer l.
+#
+# The BPTT kernel is latency bound and occupies rs * slices * ndir SMs (96 of 148 at B = 96, H = 512); nothing on its stream can
+# use the rest.  The serial chain of the encoder's backward is  BPTT(l+1) -> dX GEMM(l+1) -> BPTT(l) -> ...; the dW_ih / dW_hh GEMMs
+# and bias sums of a layer feed nothing but the optimizer.  When the layer's parameters keep their gradients in the reducer's flat
+# buckets (las_b200.ddp.BucketedGradReducer tags them), backward therefore does not return those gradients through autograd: it
+# queues the work, and the NEXT layer's backward issues it on a second stream that is released once every CTA of its own
+# BPTT kernel is resident (las_set_launch_start_stream), capped to the SMs that kernel leaves free, accumulating straight into
+# p.grad.  What is still queued when the backward pass ends (the bottom layer's own gradients) is issued then, and the calling
+# stream waits for the second stream before backward() returns (engine callback), so callers see ordinary semantics.
+# LAS_BWD_OVERLAP=0 disables it; parameters without the reducer's tag always take the plain autograd route.
+# ----------------------------------------------------------------------------------------------------------------------
+class _BackwardOverlap:
+    def __init__(self, dev: torch.device):
+        self.dev = dev
+        self.side = torch.cuda.Stream(device=dev)
+        self.pending = []            # closures fn(max_ctas), run with the side stream current
+        self.task_id = None          # autograd graph task the queue belongs to
+        self.sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+
+    def run_pending(self, max_ctas: int):
+        with torch.cuda.stream(self.side):
+            for fn in self.pending:
+                fn(max_ctas)
+        self.pending = []
+
+
+_OVERLAP: dict = {}
+
+
+def _overlap_state(dev: torch.device) -> _BackwardOverlap:
+    st = _OVERLAP.get(dev.index)
+    if st is None:
+        st = _OVERLAP[dev.index] = _BackwardOverlap(dev)
+    return st
+
+
+def _overlap_finish():
+    """End of the backward pass (autograd engine callback, caller's thread): issue what is still queued, join the streams."""
+    for st in _OVERLAP.values():
+        st.task_id = None
+        with torch.cuda.device(st.dev):
+            main = torch.cuda.current_stream(st.dev)
+            if st.pending:
+                st.side.wait_stream(main)
+                st.run_pending(0)
+            main.wait_stream(st.side)
+
+
+def _overlap_ok(wrefs) -> bool:
+    if wrefs is None or torch.is_grad_enabled() or os.environ.get('LAS_BWD_OVERLAP', '1') == '0':
+        return False
+    for w in wrefs:
+        g = w.grad
+        if (not getattr(w, '_las_bucketed', False)) or g is None or g.dtype != torch.float32 or g.shape != w.shape or not g.is_contiguous():
+            return False
+    return True
+
+
+def _lstm_weight_grads(dGb, xb, hs, dG, dbp, dims, max_ctas=0, clone_bias=True):
+    """[dW_ih, dW_hh, db_ih, db_hh] per direction on the tensor pipe (reference: autograd of nn.LSTM, src/modules.py:80,189).
+    dGb (B*T, NG) bf16 gate gradients; xb the layer input as bf16; hs the zero-framed hidden states (bf16, or fp32 to be cast);
+    dbp per-slice bias partials from the BPTT kernel (or None: column sums of dG)."""
+    Bn, Tin, T, H, ndir, Din, pyramid, Dp, Kp = dims
+    F_, G4 = ndir * H, 4 * H
+    NG = ndir * G4
+    M = Bn * T
+    dev = dGb.device
+    dwcat = torch.empty(NG, Kp, dtype=torch.float32, device=dev)
+    gemm_tc(dGb, xb, dwcat, NG, Kp, T, k_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=(2 * Dp if pyramid else Dp),
+            b_s2=Tin * Dp, ldc=Kp, a_mn=True, b_mn=True, flops=2.0 * Bn * T * NG * Din, max_ctas=max_ctas)
+    hsb = hs if hs.dtype == torch.bfloat16 else cast_bf16(hs, Bn * (T + 2), F_, F_, F_)   # (B*(T+2), F) bf16
+    grads = []
+    for d in range(ndir):
+        dw_ih = dwcat[d * G4:(d + 1) * G4, :Din]
+        if clone_bias or Kp != Din:
+            dw_ih = dw_ih.contiguous()
+        dw_hh = torch.empty(G4, H, dtype=torch.float32, device=dev)
+        # h_{t-1} for the forward direction is frame t of hs_pad, for the reverse direction frame t+2
+        gemm_tc(dGb, hsb, dw_hh, G4, H, T, k_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=F_, b_s2=(T + 2) * F_, ldc=H,
+                a_mn=True, b_mn=True, a_off=d * G4, b_off=(2 * F_ if d == 1 else 0) + d * H, gate=False, max_ctas=max_ctas)
+        db = torch.empty(G4, dtype=torch.float32, device=dev)
+        if dbp is not None:
+            colsum(dbp, G4, dbp.shape[1], G4, db, x_off=d * dbp.shape[1] * G4)      # add the few batch-slice rows
+        else:
+            colsum(dG, NG, M, G4, db, x_off=d * G4)
+        grads += [dw_ih, dw_hh, db, db.clone() if clone_bias else db]
+    return grads
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # One (Bi)LSTM layer over a padded batch with PackedSequence semantics (+ optional pyramidal frame-pair concat and
 # locked dropout): reference src/modules.py:74-84 (LockedLSTM loop body) and :165-193 (pyramLockedLSTM loop body).
 # ----------------------------------------------------------------------------------------------------------------------
 class LSTMLayerFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, lens_dev, T, pyramid, mask, x16, *weights):
+    def forward(ctx, x, lens_dev, T, pyramid, mask, x16, wrefs, *weights):
         """x (B, Tin, D) fp32 with contiguous features; lens_dev (B) int32 = lengths AFTER the pyramid halving;
         T = max of those lengths; weights = (w_ih, w_hh, b_ih, b_hh) per direction."""
         _require_cuda(x, lens_dev, *weights)
@@ -293,6 +386,7 @@ class LSTMLayerFunction(torch.autograd.Function):
         else:
             ctx.save_for_backward(x, lens_dev, gates, hs_pad, cs_pad, w_hh, mask, *ws)
         ctx.dims = (Bn, Tin, D, T, H, ndir, Din, sb, st_eff, bool(pyramid), tc, Dp, Kp)
+        ctx.wrefs = wrefs if (tc and rec_tc) else None
         y = out if out is not None else hs_pad[:, 1:T + 1]
         if out16 is not None:
             ctx.mark_non_differentiable(out16)
@@ -315,6 +409,17 @@ class LSTMLayerFunction(torch.autograd.Function):
         M = Bn * T
         dGb = None
         dbp = None
+        ovl = _overlap_state(dev) if (rec_tc and _overlap_ok(ctx.wrefs)) else None
+        ev = False
+        if ovl is not None:
+            tid = torch._C._current_graph_task_id()
+            if ovl.task_id != tid:                 # first layer of this backward pass (or leftovers of an aborted one)
+                ovl.pending = []
+                ovl.task_id = tid
+                torch.autograd.Variable._execution_engine.queue_callback(_overlap_finish)
+            if ovl.pending:
+                ev = True
+                lib.las_set_launch_start_stream(ovl.side.cuda_stream)
         if rec_tc:
             w_hh_t = torch.empty(ndir, H, G4, dtype=torch.bfloat16, device=dev)
             check(lib.las_transpose_cast_bf16(w_hh.data_ptr(), w_hh_t.data_ptr(), ndir, G4, H, stream_ptr()), 'transpose_cast')
@@ -334,6 +439,13 @@ class LSTMLayerFunction(torch.autograd.Function):
         else:
             check(lib.las_lstm_rec_bwd_f32(dy.data_ptr(), gates.data_ptr(), cs_pad.data_ptr(), w_hh.data_ptr(), lens_dev.data_ptr(),
                                            ptr(mask), Bn, T, H, ndir, wsb.data_ptr(), nbytes, stream_ptr()), 'lstm_rec_bwd')
+        if ev:
+            # the layer above left its weight-gradient work queued: it runs beside this layer's BPTT kernel, on the SMs that
+            # kernel does not occupy (one CTA per (gate-row slice, batch slice, direction), lstm_rec_tc.cu)
+            at_start = bool(lib.las_launch_start_mode())      # else the side stream was released behind the kernel, not beside it
+            lib.las_set_launch_start_stream(None)
+            free = ovl.sm_count - 4 * (H // 128) * ((Bn + 31) // 32) * ndir
+            ovl.run_pending(free if (at_start and free >= 16) else 0)
         dG = gates
         dx = None
         grads: List[Optional[torch.Tensor]] = []
@@ -345,23 +457,22 @@ class LSTMLayerFunction(torch.autograd.Function):
                 dx = torch.zeros(Bn, Tin, D, dtype=torch.float32, device=dev)             # tiles past a row's length are skipped
                 gemm_tc(dGb, wcat, dx, T, Din, NG, a_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=Kp, b_mn=True, c_bs=Tin * D,
                         ldc=Din, lens=lens_dev, flops=2.0 * Bn * T * NG * Din)
-            dwcat = torch.empty(NG, Kp, dtype=torch.float32, device=dev)
-            gemm_tc(dGb, xb, dwcat, NG, Kp, T, k_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=(2 * Dp if pyramid else Dp),
-                    b_s2=Tin * Dp, ldc=Kp, a_mn=True, b_mn=True, flops=2.0 * Bn * T * NG * Din)
-            hsb = hs_pad if hs_pad.dtype == torch.bfloat16 else cast_bf16(hs_pad, Bn * (T + 2), F_, F_, F_)   # (B*(T+2), F) bf16
-            for d in range(ndir):
-                dw_ih = dwcat[d * G4:(d + 1) * G4, :Din].contiguous()
-                dw_hh = torch.empty(G4, H, dtype=torch.float32, device=dev)
-                # h_{t-1} for the forward direction is frame t of hs_pad, for the reverse direction frame t+2
-                gemm_tc(dGb, hsb, dw_hh, G4, H, T, k_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=F_, b_s2=(T + 2) * F_, ldc=H,
-                        a_mn=True, b_mn=True, a_off=d * G4, b_off=(2 * F_ if d == 1 else 0) + d * H, gate=False)
-                db = torch.empty(G4, dtype=torch.float32, device=dev)
-                if dbp is not None:
-                    colsum(dbp, G4, dbp.shape[1], G4, db, x_off=d * dbp.shape[1] * G4)      # add the few batch-slice rows
-                else:
-                    colsum(dG, NG, M, G4, db, x_off=d * G4)
-                grads += [dw_ih, dw_hh, db, db.clone()]
-            return (dx, None, None, None, None, None, *grads)
+            wdims = (Bn, Tin, T, H, ndir, Din, pyramid, Dp, Kp)
+            if ovl is not None:
+                wrefs = ctx.wrefs
+
+                def run(max_ctas, dGb=dGb, xb=xb, hs=hs_pad, dG=dG, dbp=dbp, wrefs=wrefs, wdims=wdims):
+                    side = torch.cuda.current_stream()
+                    for w, g in zip(wrefs, _lstm_weight_grads(dGb, xb, hs, dG, dbp, wdims, max_ctas=max_ctas, clone_bias=False)):
+                        w.grad.add_(g)
+                    for t in (dGb, xb, hs, dG, dbp):
+                        if t is not None:
+                            t.record_stream(side)        # allocated on the main stream, read here
+
+                ovl.pending.append(run)
+                return (dx, None, None, None, None, None, None, *([None] * (4 * ndir)))
+            grads = _lstm_weight_grads(dGb, xb, hs_pad, dG, dbp, wdims)
+            return (dx, None, None, None, None, None, None, *grads)
         if ctx.needs_input_grad[0]:
             full = (Tin * D == T * Din)
             dx = (torch.empty if full else torch.zeros)(Bn, Tin, D, dtype=torch.float32, device=dev)
@@ -379,11 +490,11 @@ class LSTMLayerFunction(torch.autograd.Function):
             db = torch.empty(G4, dtype=torch.float32, device=dev)
             colsum(dG, NG, M, G4, db, x_off=d * G4)
             grads += [dw_ih, dw_hh, db, db.clone()]
-        return (dx, None, None, None, None, None, *grads)
+        return (dx, None, None, None, None, None, None, *grads)
 
 
 def lstm_layer(x, lens_dev, T, pyramid, mask, weights: Sequence[torch.Tensor]):
-    y, y16 = LSTMLayerFunction.apply(x, lens_dev, int(T), bool(pyramid), mask, _bf16_shadow(x), *weights)
+    y, y16 = LSTMLayerFunction.apply(x, lens_dev, int(T), bool(pyramid), mask, _bf16_shadow(x), tuple(weights), *weights)
     if y16 is not None:
         y._las_bf16 = (y16, y._version)          # picked up by the next lstm_layer / linear (see _bf16_shadow)
     return y

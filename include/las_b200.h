@@ -95,6 +95,8 @@ typedef struct {
     double prof_flops;     /* algorithmic FLOPs credited to this launch by las_prof_* (0: 2*M*N*K*batches as launched) */
     int splitk;            /* weight-gradient form only: > 1 splits the reduction over that many CTAs per output tile */
     float* workspace;      /* split-K partial sums, >= splitk * M * round_up(N, 4) floats */
+    int max_ctas;          /* > 0: launch at most this many (persistent) CTAs -- for a GEMM that runs on a second stream beside a
+                            * recurrence kernel and should take only the SMs that kernel leaves free; 0: one CTA per SM */
 } LasGemmTc;
 int las_gemm_bf16_tc(const LasGemmTc* desc, void* stream);
 /* dst[r][c] (bf16, row stride ld_dst) = c < cols ? srcrow(r)[c] : 0, c < cols_pad; source row r starts at
@@ -140,6 +142,14 @@ int las_lstm_rec_fwd_tc_ex(float* gates, const void* w_hh_bf16, const int* lens,
                            float* cs_pad, int B, int T, int H, int ndir, int save_gates, void* ws, size_t ws_bytes,
                            void* out_bf16, void* hs_bf16, void* stream);
 
+/* Arms the NEXT las_lstm_rec_bwd_tc / las_lstm_rec_bwd_tc_db call of this host thread: `side_stream` (a stream other than the one
+ * the call is given; NULL disarms) is made to wait until every CTA of the recurrence kernel is resident -- the CTAs bump a device
+ * counter on entry, the stream waits on its value -- or, on the variants without the counter, until the kernel has finished.
+ * Work queued on side_stream afterwards can then fill the SMs the latency-bound recurrence leaves idle (the weight-gradient
+ * GEMMs of the layer above, reference: autograd of src/modules.py:189) without delaying the recurrence's own cluster placement.
+ * las_launch_start_mode(): 1 if the last armed call released side_stream at kernel start, 0 if at kernel end. */
+void las_set_launch_start_stream(void* side_stream);
+int las_launch_start_mode(void);
 /* debug aid: device buffer (256*16 long long) receiving clock64 stamps of CTA (0,0,0) per timestep; NULL disables */
 void las_lstm_rec_tc_set_debug(void* dev_buf);
 /* BPTT on the tensor pipe.  w_hh_t_bf16 = W_hh transposed per direction, (ndir, H, 4H) bf16 (las_transpose_cast_bf16).
