@@ -1044,7 +1044,22 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
     RC(gemm_tn(st, dGemb, 4 * DH, s->emb, E, g->d_w_ih0, E + P, 4 * DH, E, V));
     // embedding rows via lookups: padding_idx row receives no lookup gradient (nn.Embedding(padding_idx), src/models.py:261-265)
     if (s->pad_idx >= 0 && s->pad_idx < V) LAS_CUDA(cudaMemsetAsync(dGemb + (size_t)s->pad_idx * 4 * DH, 0, (size_t)4 * DH * fsz, st));
-    RC(gemm(st, dGemb, 4 * DH, s->w_ih0, E + P, 0, g->d_emb, E, V, E, 4 * DH, 1.f));
+    if (tc && (4 * DH) % 16 == 0 && (size_t)(16 + CS_ROWSPLIT) * V * E <= L.skws_floats) {
+        // d_emb += dGemb . W_ih0[:, :E] has M = V (30) rows, i.e. 16 output tiles for a K = 4*DH reduction (0.3 ms on 16 CTAs): cut K
+        // into 16 batched chunks (256 CTAs) and let a column-sum pass add the partial products into d_emb
+        const int NCH = 16, kc = 4 * DH / NCH;
+        LasGemmF32 d{};
+        d.A = dGemb; d.B = s->w_ih0; d.C = skws;
+        d.M = V; d.N = E; d.K = kc; d.batch = NCH;
+        d.a_m_si = 4 * DH; d.a_k_si = 1; d.bsA = kc;
+        d.b_k_si = E + P; d.b_n_s = 1; d.bsB = (long long)kc * (E + P);
+        d.c_m_si = E; d.bsC = (long long)V * E;
+        d.alpha = 1.f; d.beta = 0.f;
+        RC(las_gemm_f32(&d, st));
+        RC(las_colsum_f32(skws, (long long)V * E, NCH, V * E, g->d_emb, 1, skws + (size_t)NCH * V * E, st));
+    } else {
+        RC(gemm(st, dGemb, 4 * DH, s->w_ih0, E + P, 0, g->d_emb, E, V, E, 4 * DH, 1.f));
+    }
     // keys / values: dK[b] = DE[:, b]^T . Q[:, b] ; dV[b] = W[:, b]^T . dctx[:, b]   (batched over b, per head)
     for (int h = 0; h < heads; ++h) {
         LasGemmF32 d{};

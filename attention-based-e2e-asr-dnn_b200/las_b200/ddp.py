@@ -12,7 +12,9 @@ Design:
     optimizer sees stable pointers;
   * buckets follow the order backward produces gradients: Speller -> pLSTM[n-1] -> ... -> pLSTM[0] -> base LSTM;
   * a post-accumulate-grad hook counts a bucket's parameters down and fires its async all-reduce the moment the last
-    one lands, so communication of the Speller / upper pyramid overlaps the BPTT of the layers below;
+    one lands, so communication of the Speller / upper pyramid overlaps the BPTT of the layers below (encoder weight
+    gradients that the backward overlap accumulates on its second stream report through `p._las_grad_ready` instead:
+    the all-reduce is then issued from that stream, i.e. ordered behind the accumulation);
   * parameters that never receive a gradient (spell.attention.final_map.*) are excluded up front -- the
     classic DDP "unused parameter" trap.
 """
@@ -67,7 +69,10 @@ class BucketedGradReducer:
             off = 0
             for p in ps:
                 p.grad = flat[off:off + p.numel()].view_as(p)
-                p._las_bucketed = True          # gradients may be accumulated in place, outside autograd (functional.py, backward overlap)
+                # gradients of this parameter may be accumulated in place outside autograd (functional.py, backward overlap); the code
+                # that does so calls p._las_grad_ready(p) afterwards -- on the stream the accumulation ran on -- in place of the hook
+                p._las_bucketed = True
+                p._las_grad_ready = self._make_hook(bi)
                 off += p.numel()
                 self._bucket_of[id(p)] = bi
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))

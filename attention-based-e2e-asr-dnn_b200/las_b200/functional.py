@@ -465,6 +465,10 @@ class LSTMLayerFunction(torch.autograd.Function):
                     side = torch.cuda.current_stream()
                     for w, g in zip(wrefs, _lstm_weight_grads(dGb, xb, hs, dG, dbp, wdims, max_ctas=max_ctas, clone_bias=False)):
                         w.grad.add_(g)
+                    for w in wrefs:                        # stands in for the post-accumulate-grad hook (bucket all-reduce)
+                        ready = getattr(w, '_las_grad_ready', None)
+                        if ready is not None:
+                            ready(w)
                     for t in (dGb, xb, hs, dG, dbp):
                         if t is not None:
                             t.record_stream(side)        # allocated on the main stream, read here

@@ -35,16 +35,48 @@ class Toy(torch.nn.Module):
         return self.spell.cls(x)
 
 
+class _ManualGradLinear(torch.autograd.Function):
+    """Stand-in for the encoder layers' backward overlap (las_b200/functional.py): parameters tagged by the reducer get their
+    gradients accumulated straight into p.grad, report through p._las_grad_ready, and autograd sees None for them."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, refs):
+        ctx.save_for_backward(x, w)
+        ctx.refs = refs
+        return x @ w.t() + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        wp, bp = ctx.refs
+        dx = dy @ w
+        if getattr(wp, '_las_bucketed', False) and wp.grad is not None:
+            wp.grad.add_(dy.t() @ x)
+            bp.grad.add_(dy.sum(0))
+            for p in (wp, bp):
+                p._las_grad_ready(p)
+            return dx, None, None, None
+        return dx, dy.t() @ x, dy.sum(0), None
+
+
+class ToyManual(Toy):
+    def forward(self, x):
+        x = torch.tanh(self.listen.base(x))
+        for l in self.listen.pyramid.plstms:
+            x = torch.tanh(_ManualGradLinear.apply(x, l.weight, l.bias, (l.weight, l.bias)))
+        return self.spell.cls(x)
+
+
 def _free_port():
     s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, manual=False):
     from las_b200.ddp import BucketedGradReducer
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     torch.manual_seed(0)
-    model = Toy()
+    model = ToyManual() if manual else Toy()
     red = BucketedGradReducer(list(model.named_parameters()), world_size=world)
     assert red.bucket_names == ['spell', 'pyramid.1', 'pyramid.0', 'base'], red.bucket_names      # backward order
     assert red.excluded == ['spell.attention.final_map.weight', 'spell.attention.final_map.bias']
@@ -56,6 +88,8 @@ def _worker(rank, world, port, q):
         red.zero_grad()
         loss = ((model(xs) - ys) ** 2).sum()
         loss.backward()
+        if manual:                           # the pyramid buckets were launched by the ready callbacks, before finish()
+            assert all(red._handles[red.bucket_names.index(k)] is not None for k in ('pyramid.1', 'pyramid.0'))
         red.finish()
     grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
     # every p.grad is still a view into its bucket
@@ -71,11 +105,12 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_matches_single_process():
+@pytest.mark.parametrize('manual', [False, True], ids=['autograd', 'manual_accumulate'])
+def test_bucketed_allreduce_matches_single_process(manual):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, manual)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
