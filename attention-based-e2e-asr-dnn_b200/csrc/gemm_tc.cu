@@ -585,7 +585,7 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
     g.C = d->C; g.bias1 = d->bias1; g.bias2 = d->bias2; g.c_bs = d->c_bs; g.ldc = d->ldc;
     g.N = d->N; g.accumulate = d->accumulate; g.lens = d->lens;
     const double flops = d->prof_flops > 0 ? d->prof_flops : 2.0 * d->M * (double)d->N * d->K * d->a_batches * d->k_batches;
-    LasProfScope prof(d->prof_tag == 1 ? LAS_PROF_GEMM_GATES : LAS_PROF_GEMM_OTHER, stream, flops);
+    LasProfScope prof(d->prof_tag == 1 ? (d->max_ctas > 0 ? LAS_PROF_GEMM_GATES_SIDE : LAS_PROF_GEMM_GATES) : LAS_PROF_GEMM_OTHER, stream, flops);
     // narrow N tiles when the 128x256 tiling would leave most SMs idle (decoder-step GEMMs: M = batch)
     const long long tiles256 = (long long)ceil_div(d->M, BM) * ceil_div(d->N, 256) * d->a_batches;
     const bool narrow = tiles256 < 40 && !(d->a_mn_major && d->splitk > 1);

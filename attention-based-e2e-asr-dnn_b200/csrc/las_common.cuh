@@ -128,7 +128,8 @@ inline cudaError_t las_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 // ---- profiling scope (see las_runtime.cu) ----
 enum LasProfKind { LAS_PROF_GEMM_GATES = 0, LAS_PROF_GEMM_OTHER = 1, LAS_PROF_REC_FWD = 2, LAS_PROF_REC_BWD = 3,
                    LAS_PROF_ATTN_FWD = 4, LAS_PROF_ATTN_BWD = 5, LAS_PROF_ADAM = 6, LAS_PROF_SPELLER_FWD = 7,
-                   LAS_PROF_SPELLER_BWD = 8 };
+                   LAS_PROF_SPELLER_BWD = 8,
+                   LAS_PROF_GEMM_GATES_SIDE = 9 /* gate GEMMs launched with max_ctas > 0: beside a recurrence kernel, on the SMs it leaves free */ };
 class LasProfScope {
 public:
     LasProfScope(int kind, void* stream, double work);

@@ -217,6 +217,7 @@ class _BackwardOverlap:
         self.dev = dev
         self.side = torch.cuda.Stream(device=dev)
         self.pending = []            # closures fn(max_ctas), run with the side stream current
+        self.keepalive = []          # main-stream tensors the side stream reads, released after the join
         self.task_id = None          # autograd graph task the queue belongs to
         self.sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
 
@@ -247,10 +248,34 @@ def _overlap_finish():
                 st.side.wait_stream(main)
                 st.run_pending(0)
             main.wait_stream(st.side)
+        st.keepalive = []            # main-stream work enqueued from here on is ordered behind everything the side stream read
+
+
+_PROFILER_ATTACHED: Optional[bool] = None
+
+
+def _profiler_attached() -> bool:
+    """True when a kernel-serialising profiler (Nsight Compute / Nsight Systems injection) is attached to this process.  The
+    overlap's hand-off -- a stream waiting on a counter that a kernel on another stream bumps -- did not complete under `ncu`
+    (the run hung), so the plain autograd route is taken there; kernel times and shares under ncu are those of the serial
+    schedule either way."""
+    global _PROFILER_ATTACHED
+    if _PROFILER_ATTACHED is None:
+        hit = any(k in os.environ for k in ('CUDA_INJECTION64_PATH', 'CUDA_INJECTION32_PATH', 'NV_NSIGHT_INJECTION_PORT_BASE',
+                                            'NV_NSIGHT_INJECTION_TRANSPORT_TYPE', 'NV_TPS_LAUNCH_TOKEN'))
+        if not hit:
+            try:
+                with open('/proc/self/maps') as f:
+                    maps = f.read().lower()
+                hit = any(k in maps for k in ('cuda-injection', 'nsight-compute', 'nsight_compute', 'nsight-systems', 'libtoolsinjection'))
+            except OSError:
+                hit = False
+        _PROFILER_ATTACHED = bool(hit)
+    return _PROFILER_ATTACHED
 
 
 def _overlap_ok(wrefs) -> bool:
-    if wrefs is None or torch.is_grad_enabled() or os.environ.get('LAS_BWD_OVERLAP', '1') == '0':
+    if wrefs is None or torch.is_grad_enabled() or os.environ.get('LAS_BWD_OVERLAP', '1') == '0' or _profiler_attached():
         return False
     for w in wrefs:
         g = w.grad
@@ -415,6 +440,7 @@ class LSTMLayerFunction(torch.autograd.Function):
             tid = torch._C._current_graph_task_id()
             if ovl.task_id != tid:                 # first layer of this backward pass (or leftovers of an aborted one)
                 ovl.pending = []
+                ovl.keepalive = []
                 ovl.task_id = tid
                 torch.autograd.Variable._execution_engine.queue_callback(_overlap_finish)
             if ovl.pending:
@@ -462,16 +488,15 @@ class LSTMLayerFunction(torch.autograd.Function):
                 wrefs = ctx.wrefs
 
                 def run(max_ctas, dGb=dGb, xb=xb, hs=hs_pad, dG=dG, dbp=dbp, wrefs=wrefs, wdims=wdims):
-                    side = torch.cuda.current_stream()
                     for w, g in zip(wrefs, _lstm_weight_grads(dGb, xb, hs, dG, dbp, wdims, max_ctas=max_ctas, clone_bias=False)):
                         w.grad.add_(g)
                     for w in wrefs:                        # stands in for the post-accumulate-grad hook (bucket all-reduce)
                         ready = getattr(w, '_las_grad_ready', None)
                         if ready is not None:
                             ready(w)
-                    for t in (dGb, xb, hs, dG, dbp):
-                        if t is not None:
-                            t.record_stream(side)        # allocated on the main stream, read here
+                    # allocated on the main stream, read here: kept alive until the streams have joined (no record_stream: its
+                    # event-deferred frees make the caching allocator's steady state depend on timing)
+                    _overlap_state(dGb.device).keepalive.append((dGb, xb, hs, dG, dbp))
 
                 ovl.pending.append(run)
                 return (dx, None, None, None, None, None, None, *([None] * (4 * ndir)))

@@ -166,3 +166,24 @@ def test_lazy_host_tensor_waits_once_then_acts_like_a_plain_tensor():
     for fresh in (LazyHostTensor(base.clone(), Ev()),):
         n0 = Ev.n
         assert fresh.numpy().sum() == base.sum() and Ev.n == n0 + 1
+
+
+def test_backward_overlap_is_off_under_an_injected_profiler(monkeypatch):
+    """The side-stream hand-off of the backward overlap hung under `ncu`: with a CUDA injection library in the environment
+    (how ncu / nsys attach) the plain autograd route must be taken."""
+    import las_b200.functional as LF
+    monkeypatch.setattr(LF, '_PROFILER_ATTACHED', None)
+    monkeypatch.delenv('CUDA_INJECTION64_PATH', raising=False)
+    monkeypatch.delenv('NV_NSIGHT_INJECTION_PORT_BASE', raising=False)
+    assert LF._profiler_attached() is False
+    monkeypatch.setattr(LF, '_PROFILER_ATTACHED', None)
+    monkeypatch.setenv('CUDA_INJECTION64_PATH', '/opt/nvidia/nsight-compute/target/libcuda-injection64.so')
+    assert LF._profiler_attached() is True
+    import torch
+    w = torch.nn.Parameter(torch.zeros(2)); w.grad = torch.zeros(2); w._las_bucketed = True
+    with torch.no_grad():
+        assert LF._overlap_ok((w,)) is False
+        monkeypatch.setattr(LF, '_PROFILER_ATTACHED', False)
+        assert LF._overlap_ok((w,)) is True
+        monkeypatch.setenv('LAS_BWD_OVERLAP', '0')
+        assert LF._overlap_ok((w,)) is False
