@@ -256,9 +256,9 @@ _PROFILER_ATTACHED: Optional[bool] = None
 
 def _profiler_attached() -> bool:
     """True when a kernel-serialising profiler (Nsight Compute / Nsight Systems injection) is attached to this process.  The
-    overlap's hand-off -- a stream waiting on a counter that a kernel on another stream bumps -- did not complete under `ncu`
-    (the run hung), so the plain autograd route is taken there; kernel times and shares under ncu are those of the serial
-    schedule either way."""
+    overlap's hand-off is a stream waiting on a counter that a kernel on another stream bumps; a full-step `ncu` capture with it did
+    not finish within its time limit (deadlock under ncu's kernel serialisation or merely slow: not established), so the plain
+    autograd route is taken there.  Kernel times and shares under ncu are those of the serial schedule either way."""
     global _PROFILER_ATTACHED
     if _PROFILER_ATTACHED is None:
         hit = any(k in os.environ for k in ('CUDA_INJECTION64_PATH', 'CUDA_INJECTION32_PATH', 'NV_NSIGHT_INJECTION_PORT_BASE',

@@ -169,8 +169,8 @@ def test_lazy_host_tensor_waits_once_then_acts_like_a_plain_tensor():
 
 
 def test_backward_overlap_is_off_under_an_injected_profiler(monkeypatch):
-    """The side-stream hand-off of the backward overlap hung under `ncu`: with a CUDA injection library in the environment
-    (how ncu / nsys attach) the plain autograd route must be taken."""
+    """A full-step `ncu` capture with the backward overlap on did not finish in time: with a CUDA injection library in the
+    environment (how ncu / nsys attach) the plain autograd route must be taken."""
     import las_b200.functional as LF
     monkeypatch.setattr(LF, '_PROFILER_ATTACHED', None)
     monkeypatch.delenv('CUDA_INJECTION64_PATH', raising=False)
