@@ -279,7 +279,8 @@ def _overlap_ok(wrefs) -> bool:
         return False
     for w in wrefs:
         g = w.grad
-        if (not getattr(w, '_las_bucketed', False)) or g is None or g.dtype != torch.float32 or g.shape != w.shape or not g.is_contiguous():
+        if (not getattr(w, '_las_bucketed', False)) or (not w.requires_grad) or g is None or g.dtype != torch.float32 or g.shape != w.shape \
+                or not g.is_contiguous():
             return False
     return True
 
