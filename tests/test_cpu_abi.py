@@ -187,3 +187,25 @@ def test_backward_overlap_is_off_under_an_injected_profiler(monkeypatch):
         assert LF._overlap_ok((w,)) is True
         monkeypatch.setenv('LAS_BWD_OVERLAP', '0')
         assert LF._overlap_ok((w,)) is False
+
+
+def test_bf16_shadow_is_dropped_when_the_tensor_is_written_to(monkeypatch):
+    """lstm_layer leaves the kernel-written bf16 copy of its output on the tensor (functional._bf16_shadow); the next layer may
+    only use it while the fp32 tensor has not been modified since, has the same shape, and the tensor-pipe mode is on."""
+    import torch
+    import las_b200.functional as LF
+    monkeypatch.setattr(LF, 'use_tensor_cores', lambda: True)
+    y = torch.zeros(2, 3, 4)
+    assert LF._bf16_shadow(y) is None                       # nothing attached
+    y16 = torch.zeros(2, 3, 4, dtype=torch.bfloat16)
+    y._las_bf16 = (y16, y._version)
+    assert LF._bf16_shadow(y) is y16
+    assert LF._bf16_shadow(y[:, :2]) is None                # a view is another tensor object: no attribute
+    y.mul_(2.0)                                             # in-place edit by the caller -> stale copy must not be used
+    assert LF._bf16_shadow(y) is None
+    z = torch.zeros(2, 3, 4)
+    z._las_bf16 = (torch.zeros(2, 3, 8, dtype=torch.bfloat16), z._version)
+    assert LF._bf16_shadow(z) is None                       # shape mismatch
+    z._las_bf16 = (y16, z._version)
+    monkeypatch.setattr(LF, 'use_tensor_cores', lambda: False)
+    assert LF._bf16_shadow(z) is None                       # fp32 parity mode never uses it
