@@ -106,11 +106,19 @@ def _rows3d(x: torch.Tensor):
     return x.stride(0), x.stride(1)
 
 
+def _attach_bf16_shadow(y: torch.Tensor, y16: Optional[torch.Tensor]) -> None:
+    """Leaves the kernel-written bf16 copy on the fp32 tensor for the next lstm_layer / linear (see _bf16_shadow).  Inference
+    tensors (the reference evaluates under torch.inference_mode(), src/train.py:207,604) have no version counter, so a later
+    in-place edit could not be detected: no copy is attached there and the consumer casts as before."""
+    if y16 is not None and not y.is_inference():
+        y._las_bf16 = (y16, y._version)
+
+
 def _bf16_shadow(x: torch.Tensor) -> Optional[torch.Tensor]:
     """bf16 copy of `x` left on it by the recurrence kernel that produced it (lstm_layer), or None.  Only valid while `x` has not
     been written to since (version counter), so an in-place edit by the caller silently falls back to the cast pass."""
     sh = getattr(x, '_las_bf16', None)
-    if sh is None or not use_tensor_cores():
+    if sh is None or x.is_inference() or not use_tensor_cores():
         return None
     t, ver = sh
     if ver != x._version or tuple(t.shape) != tuple(x.shape) or t.device != x.device or not t.is_contiguous():
@@ -525,8 +533,7 @@ class LSTMLayerFunction(torch.autograd.Function):
 
 def lstm_layer(x, lens_dev, T, pyramid, mask, weights: Sequence[torch.Tensor]):
     y, y16 = LSTMLayerFunction.apply(x, lens_dev, int(T), bool(pyramid), mask, _bf16_shadow(x), tuple(weights), *weights)
-    if y16 is not None:
-        y._las_bf16 = (y16, y._version)          # picked up by the next lstm_layer / linear (see _bf16_shadow)
+    _attach_bf16_shadow(y, y16)
     return y
 
 

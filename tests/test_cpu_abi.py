@@ -209,3 +209,14 @@ def test_bf16_shadow_is_dropped_when_the_tensor_is_written_to(monkeypatch):
     z._las_bf16 = (y16, z._version)
     monkeypatch.setattr(LF, 'use_tensor_cores', lambda: False)
     assert LF._bf16_shadow(z) is None                       # fp32 parity mode never uses it
+    # inference tensors have no version counter (the reference's dev evaluation runs under torch.inference_mode()): nothing is
+    # attached, nothing is looked up, nothing raises
+    with torch.inference_mode():
+        yi = torch.zeros(2, 3, 4)
+        LF._attach_bf16_shadow(yi, torch.zeros(2, 3, 4, dtype=torch.bfloat16))
+        assert not hasattr(yi, '_las_bf16')
+        monkeypatch.setattr(LF, 'use_tensor_cores', lambda: True)
+        assert LF._bf16_shadow(yi) is None
+    yn = torch.zeros(2, 3, 4)
+    LF._attach_bf16_shadow(yn, y16)
+    assert LF._bf16_shadow(yn) is y16
