@@ -134,7 +134,8 @@ int las_lstm_rec_tc_supported(int B, int H, int ndir);
 size_t las_lstm_rec_tc_workspace_bytes(int B, int H, int ndir);
 int las_lstm_rec_fwd_tc(float* gates, const void* w_hh_bf16, const int* lens, const float* drop_mask, float* out, float* hs_pad,
                         float* cs_pad, int B, int T, int H, int ndir, int save_gates, void* ws, size_t ws_bytes, void* stream);
-/* Same, plus bf16 copies of the outputs that only GEMMs read afterwards (saves the separate fp32 -> bf16 cast passes):
+/* Same call sites (time loop of nn.LSTM on a PackedSequence + pad + locked dropout, src/modules.py:78-84,187-193), plus bf16
+ * copies of the outputs that only GEMMs read afterwards (saves the separate fp32 -> bf16 cast passes):
  * out_bf16 (B, T, ndir*H) = the layer output after locked dropout (next layer's / key_map's / value_map's operand),
  * hs_bf16 (B, T+2, ndir*H) = the zero-framed hidden states (dW_hh operand of backward).  Either may be NULL; hs_pad may be
  * NULL when hs_bf16 is given, out when nobody reads the fp32 output. */
