@@ -5,7 +5,9 @@ Generates tests/golden/*.npz by running the UNMODIFIED reference (imported from 
 on seeded weights and inputs from oracle/golden_util.py.  Runs only in the authoring container (the GPU box
 has no /root/reference); the fixtures it writes are committed and are what pins the oracle and the CUDA path.
 
-    python oracle/make_golden.py            # rewrites every fixture
+    python oracle/make_golden.py            # rewrites the small fixtures
+    python oracle/make_golden.py --large    # ... and the two fixtures at the benchmarked lengths (about 3 minutes)
+    python oracle/make_golden.py best_greedy_T3000      # only the named large fixture(s)
 
 Stub modules: torchsummaryX / Levenshtein / seaborn / matplotlib are imported by the reference for
 non-numerical purposes and are absent from this image.
@@ -93,8 +95,50 @@ class Recorder:
         torch.rand, torch.Tensor.bernoulli_, F.dropout = self._rand, self._bern, self._drop
 
 
+class Replayer:
+    """Feeds a Recorder's coins / masks back, in the same call order, to a second run of the reference (the float64 re-run that
+    measures the reference's own fp32 round-off at the large shapes)."""
+
+    def __init__(self, rec, dtype):
+        self.coins, self.locked, self.drops, self.dtype = list(rec.coins), [m.clone() for m in rec.locked], list(rec.drops), dtype
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self._rand, self._bern, self._drop = torch.rand, torch.Tensor.bernoulli_, F.dropout
+        rep = self
+
+        def rand(*a, **k):
+            if a == (1,):
+                return torch.tensor([rep.coins.pop(0)], dtype=torch.float64)
+            return rep._rand(*a, **k)
+
+        def bern(self_, *a, **k):
+            # the recorded tensor is the FINAL mask (0 or 1/keep after the in-place div_): put the 0/1 pattern back
+            m = rep.locked.pop(0)
+            return self_.copy_((m != 0).to(self_.dtype))
+
+        def drop(x, p=0.5, training=True, inplace=False):
+            if not training or p == 0.0:
+                return x
+            return x * rep.drops.pop(0).to(x.dtype)
+
+        torch.rand, torch.Tensor.bernoulli_, F.dropout = rand, bern, drop
+        return self
+
+    def __exit__(self, *exc):
+        import torch.nn.functional as F
+        torch.rand, torch.Tensor.bernoulli_, F.dropout = self._rand, self._bern, self._drop
+
+
+def _to_double(model):
+    model = model.double()
+    # init_hiddens is a plain Python list of Parameters (src/models.py:275-281): nn.Module.double() does not see it
+    model.spell.init_hiddens = [tuple(t.double() for t in h) for h in model.spell.init_hiddens]
+    return model
+
+
 def train_case(ref_models, name, cfg_name, seed, B, T, L, lx, ly, tf_rate, dropout=None, init_force=False,
-               grads_full=True):
+               grads_full=True, grads_sample=0, with_fp64=False):
     over = {}
     if dropout:
         over = dict(init_dropout=dropout[0], mid_dropout=dropout[1], final_dropout=dropout[2],
@@ -131,14 +175,37 @@ def train_case(ref_models, name, cfg_name, seed, B, T, L, lx, ly, tf_rate, dropo
         g = p.grad.numpy()
         if grads_full:
             out['grad.' + k] = g
+        elif grads_sample:
+            # large configs: every gradient's norm + a strided sample of its entries (<= grads_sample values, fixed stride)
+            stride = max(1, -(-g.size // grads_sample))
+            out['gradsample.' + k] = g.reshape(-1)[::stride].copy()
+            out['gradabsmax.' + k] = float(np.abs(g).max())
         out['gradnorm.' + k] = float(np.linalg.norm(g.astype(np.float64)))
     out['nograd'] = np.asarray(nograd)
+    if with_fp64:
+        # the same reference module in float64 with the recorded masks replayed: what the fp32 reference itself is off by
+        m64 = _to_double(build_ref_model(ref_models, cfg, sd)).train()
+        with Replayer(rec, torch.float64):
+            l64, _ = m64(torch.from_numpy(x).double(), torch.from_numpy(lx), torch.from_numpy(y), tf_rate, init_force)
+        loss64 = (crit(l64.view(-1, V), torch.from_numpy(y).view(-1)) * ymask).sum() / ymask.sum()
+        loss64.backward()
+        out['logits64'] = l64.detach().numpy()
+        out['loss64'] = loss64.item()
+        for k, p in m64.named_parameters():
+            if p.grad is None:
+                continue
+            g = p.grad.numpy()
+            stride = max(1, -(-g.size // grads_sample))
+            out['gradsample64.' + k] = g.reshape(-1)[::stride].copy()
+            out['gradnorm64.' + k] = float(np.linalg.norm(g))
+        print(f'{name}: reference fp32 vs its own float64 run: logits max abs diff {np.abs(out["logits"] - out["logits64"]).max():.3e} '
+              f'(max |logit| {np.abs(out["logits64"]).max():.2f}), loss diff {abs(loss.item() - loss64.item()):.3e}')
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
     print(f'{name}: loss={loss.item():.6f} logits={tuple(logits.shape)} att={tuple(att.shape)} '
           f'coins={len(rec.coins)} locked={len(rec.locked)} drops={len(rec.drops)} nograd={nograd}')
 
 
-def greedy_case(ref_models, name, cfg_name, seed, B, T, lx, max_steps=None, scale=1.0):
+def greedy_case(ref_models, name, cfg_name, seed, B, T, lx, max_steps=None, scale=1.0, with_fp64=False):
     over = {} if max_steps is None else dict(CHR_MAX_STEPS=max_steps)
     cfg = gu.get_config(cfg_name, **over)
     sd = gu.make_state_dict(cfg, seed, scale=scale)
@@ -150,9 +217,21 @@ def greedy_case(ref_models, name, cfg_name, seed, B, T, lx, max_steps=None, scal
     strs = [idx_to_str(c, VOCAB, 0, 29) for c in chars]
     gold = [idx_to_str(r, VOCAB, 0, 29) for r in y]
     ld = [levenshtein(s, g) for s, g in zip(strs, gold)]
+    extra = {}
+    if with_fp64:
+        # conditioning of the fixture: the same module in float64 (must give the same transcript) and the smallest top-1 / top-2
+        # logit gap per utterance -- an implementation whose logits are off by more than that gap may legitimately flip a step
+        m64 = _to_double(model)
+        with torch.no_grad():
+            l64, _ = m64(torch.from_numpy(x).double(), torch.from_numpy(lx))
+        assert np.array_equal(l64.argmax(-1).numpy(), chars), 'fixture is ill-conditioned: fp32 and float64 transcripts differ'
+        top2 = torch.topk(l64, 2, -1).values
+        extra = dict(logits64=l64.numpy(), margin_min=(top2[..., 0] - top2[..., 1]).min(dim=1).values.numpy())
+        print(f'{name}: reference fp32 vs its own float64 run: logits max abs diff {np.abs(logits.numpy() - l64.numpy()).max():.3e}, '
+              f'min top-1/top-2 gaps {extra["margin_min"]}')
     np.savez_compressed(os.path.join(OUT, name + '.npz'), cfg_name=cfg_name, seed=seed, scale=scale, x=x, lx=lx, y=y,
                         max_steps=cfg['speller_configs']['CHR_MAX_STEPS'], logits=logits.numpy(), att=att.numpy(),
-                        chars=chars, transcripts=np.asarray(strs), ld=np.asarray(ld, dtype=np.int64))
+                        chars=chars, transcripts=np.asarray(strs), ld=np.asarray(ld, dtype=np.int64), **extra)
     print(f'{name}: logits={tuple(logits.shape)} att={tuple(att.shape)} transcripts={strs[:2]} ld={ld}')
 
 
@@ -261,10 +340,30 @@ def collate_case(name, seed, lens, F=15, specaug=True):
     print(f'{name}: x={tuple(x.shape)} y={tuple(y.shape)} lx={lx.tolist()} masked_frac={(x == 0).float().mean():.3f}')
 
 
+def main_large(ref_models, only):
+    """Fixtures at BASELINE.json's benchmarked lengths (configs[1]: T=1600, L=300; configs[3]: T=3000, 600 greedy steps) with the
+    best config of config/sample-attention.yml:42-68 INCLUDING its dropouts (0.3 / 0.3 / 0.35, decoder 0.3; masks recorded).  Batch
+    of 3-4 ragged utterances so that the unmodified reference finishes in about a minute on the CPU."""
+    if not only or 'best_train_T1600_L300' in only:
+        train_case(ref_models, 'best_train_T1600_L300', 'best', 1111, B=3, T=1600, L=300, lx=[1600, 1433, 1197], ly=[300, 257, 281],
+                   tf_rate=1.0, dropout=(0.3, 0.3, 0.35, 0.3), grads_full=False, grads_sample=4096, with_fp64=True)
+    if not only or 'best_greedy_T3000' in only:
+        # weights x2.75 / seed 1500: between the fixed-point regime (smaller scale: 'HHHH...' for 600 steps) and the chaotic one
+        # (larger scale: the reference's own fp32 and float64 transcripts differ) -- every utterance has 30-350 token changes,
+        # fp32 == float64 transcript
+        greedy_case(ref_models, 'best_greedy_T3000', 'best', 1500, B=4, T=3000, lx=[3000, 2871, 2500, 1999], scale=2.75,
+                    with_fp64=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ref_models = import_reference()
+    only = [a for a in sys.argv[1:] if not a.startswith('-')]
+    if '--large' in sys.argv[1:] or only:
+        main_large(ref_models, only)
+        if only or '--large-only' in sys.argv[1:]:
+            return
     # (1) micro, ragged + unsorted lengths, odd at every pyramid level, teacher forcing 1.0, no dropout
     train_case(ref_models, 'micro_train_tf1', 'micro', 101, B=3, T=37, L=7, lx=[19, 37, 30], ly=[7, 5, 6], tf_rate=1.0)
     # (2) micro, max(lx) < padded T, a row of length exactly 8 (-> enc_len 1), tf 0.5 (coins recorded)

@@ -1,0 +1,248 @@
+"""GPU parity at the BENCHMARKED shapes and in the benchmarked mode (BASELINE.json configs[1] and configs[3]).
+
+Fixtures (oracle/make_golden.py --large, produced by the unmodified reference on the CPU in fp32):
+  best_train_T1600_L300 : best config of config/sample-attention.yml:42-68 WITH its dropouts (0.3 / 0.3 / 0.35, decoder 0.3; every
+                          mask recorded), B = 3 ragged utterances (1600, 1433, 1197 frames; odd lengths at pyramid levels), L = 300,
+                          teacher forcing 1.0: logits, loss, attention map, every gradient's norm + a strided sample of its entries.
+  best_greedy_T3000     : best config, eval mode, B = 4 ragged utterances up to T = 3000 (T_enc = 375), 600 greedy steps.
+
+Bars (north_star): fp32 mode 1e-4 relative (max-norm per tensor, tests/helpers.py::rel_err) on logits and on every gradient;
+bf16/AMP mode 2e-3 absolute on the logits; greedy transcripts identical in fp32 mode, per-utterance agreement reported and
+floored in bf16 mode.  Measured errors are appended to gpurun_out/parity_r2.jsonl (tabulated in DESIGN.md section 2).
+Reference lines: src/models.py:300-386 (Speller.forward), src/modules.py:158-194 (pyramLockedLSTM.forward)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT, gu, orc, load_golden, fixture_cfg, rel_err, grad_floor
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+TOL = 1e-4            # fp32: logits and gradients, relative
+AMP_TOL = 2e-3        # bf16 mode: logits, absolute
+
+
+def _record(**kw):
+    try:
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', 'parity_r2.jsonl'), 'a') as f:
+            f.write(json.dumps(kw) + '\n')
+    except OSError:
+        pass
+    print(json.dumps(kw))
+
+
+def _model(cfg, sd, train):
+    from las_b200.models import ListenAttendSpell
+    m = ListenAttendSpell(**cfg).to(DEV)
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    return m.train() if train else m.eval()
+
+
+def _masked_ce(logits, y, ly):
+    B, L, V = logits.shape
+    crit = torch.nn.CrossEntropyLoss(reduction='none')
+    mask = (torch.arange(L, device=logits.device).unsqueeze(0) < torch.as_tensor(ly, device=logits.device).unsqueeze(1)).flatten().to(torch.int)
+    return (crit(logits.float().view(-1, V), y.view(-1)) * mask).sum() / mask.sum()
+
+
+def _run_train_fixture(g, amp):
+    from las_b200.modules import set_mask_override
+    cfg = fixture_cfg(g)
+    sd = gu.make_state_dict(cfg, int(g['seed']))
+    model = _model(cfg, sd, train=True)
+    nl, nd = int(g['n_locked']), int(g['n_drops'])
+    locked = [torch.from_numpy(g[f'locked_mask_{i}']) for i in range(nl)] if nl else None
+    drops = [torch.from_numpy(g[f'drop_mask_{i}']) for i in range(nd)] if nd else None
+    set_mask_override(locked, drops, [float(c) for c in g['coins']])
+    try:
+        y = torch.from_numpy(g['y']).to(DEV)
+        x = torch.from_numpy(g['x']).to(DEV)
+        if amp:
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                logits, att = model(x, torch.from_numpy(g['lx']), y, float(g['tf_rate']), bool(g['init_force']))
+        else:
+            logits, att = model(x, torch.from_numpy(g['lx']), y, float(g['tf_rate']), bool(g['init_force']))
+        loss = _masked_ce(logits, y, g['ly'])
+        loss.backward()
+    finally:
+        set_mask_override(None, None, None)
+    torch.cuda.synchronize()
+    return model, logits.detach().float().cpu().numpy(), att, float(loss)
+
+
+def _grad_errors(model, g):
+    """Per gradient: |norm - ref| / max(ref, floor) and the max-norm relative error of the strided sample."""
+    floor = grad_floor(g)
+    nograd = set(str(s) for s in g['nograd'])
+    worst_norm, worst_samp = ('', 0.0), ('', 0.0)
+    for k, p in model.named_parameters():
+        if k in nograd:
+            assert p.grad is None, k
+            continue
+        got = p.grad.detach().float().cpu().numpy()
+        ref_norm = float(g['gradnorm.' + k])
+        en = abs(float(np.linalg.norm(got.astype(np.float64))) - ref_norm) / max(ref_norm, floor)
+        if en > worst_norm[1]:
+            worst_norm = (k, en)
+        ref_s = g['gradsample.' + k]
+        stride = max(1, -(-got.size // 4096))
+        got_s = got.reshape(-1)[::stride]
+        assert got_s.shape == ref_s.shape, k
+        # max-norm relative error against the tensor's own largest entry (not the sample's), floored like the small fixtures
+        es = float(np.abs(got_s.astype(np.float64) - ref_s).max() / max(float(g['gradabsmax.' + k]), floor))
+        if es > worst_samp[1]:
+            worst_samp = (k, es)
+    return worst_norm, worst_samp
+
+
+def test_best_train_T1600_L300_fp32_matches_reference():
+    """configs[1]'s lengths, fp32 parity mode: 1600 recurrent steps in the base layer, 300 decoder steps with the x16 energy
+    gain (src/models.py:93,170), every dropout on."""
+    from las_b200.precision import set_precision
+    g = load_golden('best_train_T1600_L300')
+    set_precision('fp32')
+    try:
+        model, logits, att, loss = _run_train_fixture(g, amp=False)
+    finally:
+        set_precision('auto')
+    e_logits = rel_err(logits, g['logits'])
+    e_att = float(np.abs(att.numpy() - g['att']).max())
+    wn, ws = _grad_errors(model, g)
+    _record(test='best_train_T1600_L300', mode='fp32', logits_rel=e_logits, logits_abs=float(np.abs(logits - g['logits']).max()),
+            att_abs=e_att, loss=loss, loss_ref=float(g['loss']), worst_gradnorm=wn, worst_gradsample=ws)
+    assert e_logits < TOL
+    assert e_att < 1e-5
+    assert abs(loss - float(g['loss'])) < 1e-5 * max(1.0, abs(float(g['loss'])))
+    assert wn[1] < TOL, wn
+    assert ws[1] < TOL, ws
+
+
+def test_best_train_T1600_L300_bf16_within_amp_tolerance():
+    """Same fixture in the mode bench.py times (torch.autocast -> tcgen05 gate GEMMs, DSMEM recurrence with bf16 h_t operands,
+    bf16 decoder GEMMs): logits within 2e-3 absolute of the fp32 reference; gradients reported and bounded."""
+    g = load_golden('best_train_T1600_L300')
+    model, logits, att, loss = _run_train_fixture(g, amp=True)
+    e_abs = float(np.abs(logits - g['logits']).max())
+    wn, ws = _grad_errors(model, g)
+    _record(test='best_train_T1600_L300', mode='bf16', logits_abs=e_abs, logits_rel=rel_err(logits, g['logits']),
+            att_abs=float(np.abs(att.numpy() - g['att']).max()), loss=loss, loss_ref=float(g['loss']), worst_gradnorm=wn,
+            worst_gradsample=ws)
+    assert e_abs < AMP_TOL
+    assert abs(loss - float(g['loss'])) < 1e-3
+    # bf16 operand rounding through 1600 + 800 + 400 + 200 recurrent steps and 300 decoder steps: gradients agree to a few per cent
+    assert wn[1] < 3e-2, wn
+    assert ws[1] < 5e-2, ws
+
+
+def _run_greedy_fixture(g, amp):
+    cfg = fixture_cfg(g)
+    sd = gu.make_state_dict(cfg, int(g['seed']), scale=float(g['scale']))
+    model = _model(cfg, sd, train=False)
+    x = torch.from_numpy(g['x']).to(DEV)
+    with torch.inference_mode():
+        if amp:
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                logits, att = model(x, torch.from_numpy(g['lx']))
+        else:
+            logits, att = model(x, torch.from_numpy(g['lx']))
+    torch.cuda.synchronize()
+    return model, logits.float().cpu().numpy(), att
+
+
+def test_best_greedy_T3000_fp32_transcripts_identical():
+    """configs[3]'s lengths (T = 3000 -> T_enc = 375, CHR_MAX_STEPS = 600), fp32 mode: identical index sequences, transcripts and
+    Levenshtein distances (north_star)."""
+    from las_b200.precision import set_precision
+    g = load_golden('best_greedy_T3000')
+    set_precision('fp32')
+    try:
+        model, logits, att = _run_greedy_fixture(g, amp=False)
+    finally:
+        set_precision('auto')
+    chars = logits.argmax(-1)
+    agree = [float((chars[b] == g['chars'][b]).mean()) for b in range(chars.shape[0])]
+    _record(test='best_greedy_T3000', mode='fp32', logits_rel=rel_err(logits, g['logits']), agreement=agree,
+            att_abs=float(np.abs(att.numpy() - g['att']).max()))
+    assert np.array_equal(chars, g['chars'])
+    assert np.array_equal(model.spell.last_chars.t().cpu().numpy(), g['chars'])
+    strs = [orc.idx_to_str(c, orc.VOCAB, 0, 29) for c in chars]
+    assert strs == [str(s) for s in g['transcripts']]
+    gold = [orc.idx_to_str(r, orc.VOCAB, 0, 29) for r in g['y']]
+    assert [orc.levenshtein(a, b) for a, b in zip(strs, gold)] == g['ld'].tolist()
+    # 600 steps of argmax feedback: measured against the reference's float64 run, no worse than 3x the reference's own fp32
+    # round-off (3.3e-5 here) or the bar
+    own = rel_err(g['logits'], g['logits64'])
+    assert rel_err(logits, g['logits64']) < max(TOL, 3 * own)
+
+
+def test_best_greedy_T3000_bf16_agreement():
+    """The mode bench.py's greedy leg runs in.  Greedy decoding feeds its own argmax back, so one flipped near-tie changes the rest
+    of an utterance; what is asserted: the first step's logits (no feedback yet) within the AMP tolerance, and per-utterance
+    agreement with the fp32 reference transcript reported and floored.  The fixture's own conditioning is stored beside it
+    (`margin_min`: smallest top-1/top-2 logit gap per utterance in the reference's float64 run)."""
+    g = load_golden('best_greedy_T3000')
+    model, logits, att = _run_greedy_fixture(g, amp=True)
+    chars = logits.argmax(-1)
+    agree = [float((chars[b] == g['chars'][b]).mean()) for b in range(chars.shape[0])]
+    first_div = [int(np.argmax(chars[b] != g['chars'][b])) if (chars[b] != g['chars'][b]).any() else -1 for b in range(chars.shape[0])]
+    e0 = float(np.abs(logits[:, 0] - g['logits'][:, 0]).max())
+    # logits error over the prefix on which the fed-back tokens still agree (teacher-forcing-equivalent region)
+    pref = []
+    for b in range(chars.shape[0]):
+        n = first_div[b] if first_div[b] >= 0 else chars.shape[1]
+        pref.append(float(np.abs(logits[b, :n + 1] - g['logits'][b, :n + 1]).max()))
+    _record(test='best_greedy_T3000', mode='bf16', agreement=agree, first_divergence=first_div, step0_logits_abs=e0,
+            agreeing_prefix_logits_abs=pref, margin_min=[float(v) for v in g['margin_min']] if 'margin_min' in g.files else None)
+    assert e0 < AMP_TOL
+    assert min(agree) >= 0.5, agree
+
+
+def test_lstm_layer_H512_B96_T800_bf16_vs_fp32_oracle():
+    """The benchmark configuration of the DSMEM recurrence kernels (H = 512 -> 16-CTA clusters, B = 96 -> three batch slices, two
+    directions) over a long sequence, forward AND BPTT, against the fp32 ORACLE (not kernel against kernel): layer output, input
+    gradient, and all eight parameter gradients.  Ragged lengths, locked dropout on."""
+    from las_b200 import functional as LF
+    from las_b200.precision import set_precision
+    H, D, B, T = 512, 64, 96, 800
+    rng = np.random.default_rng(77)
+    lens = [T] + sorted([int(v) for v in rng.integers(T // 2, T + 1, size=B - 1)], reverse=True)
+    x = torch.from_numpy(rng.standard_normal((B, T, D)).astype(np.float32))
+    k = 1 / np.sqrt(H)
+    names = ['weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0']
+    shapes = [(4 * H, D), (4 * H, H), (4 * H,), (4 * H,)]
+    p = {'l.' + n + suf: torch.from_numpy(rng.uniform(-k, k, size=s).astype(np.float32)) for suf in ['', '_reverse'] for n, s in zip(names, shapes)}
+    mask = torch.from_numpy((rng.random((B, 1, 2 * H)) > 0.3).astype(np.float32) / 0.7)
+    wout = torch.from_numpy(rng.standard_normal((B, T, 2 * H)).astype(np.float32) / np.sqrt(T))
+    torch.set_num_threads(os.cpu_count() or 8)
+    po = {k_: v.clone().requires_grad_(True) for k_, v in p.items()}
+    xo = x.clone().requires_grad_(True)
+    yo = orc.bilstm_layer(xo, lens, po, 'l.') * mask
+    (yo * wout).sum().backward()
+    out = {}
+    for mode in ('bf16', 'fp32'):
+        set_precision(mode)
+        try:
+            pc = {k_: v.clone().to(DEV).requires_grad_(True) for k_, v in p.items()}
+            xc = x.clone().to(DEV).requires_grad_(True)
+            ws = [pc['l.' + n + suf] for suf in ['', '_reverse'] for n in names]
+            yc = LF.lstm_layer(xc, torch.tensor(lens, dtype=torch.int32, device=DEV), T, False, mask.to(DEV), ws)
+            (yc * wout.to(DEV)).sum().backward()
+            torch.cuda.synchronize()
+        finally:
+            set_precision('auto')
+        errs = {'y_abs': float(np.abs(yc.detach().cpu().numpy() - yo.detach().numpy()).max()),
+                'dx_rel': rel_err(xc.grad.cpu().numpy(), xo.grad.numpy())}
+        for k_ in p:
+            errs[k_[2:]] = rel_err(pc[k_].grad.cpu().numpy(), po[k_].grad.numpy())
+        for b, l in enumerate(lens):
+            if l < T:
+                assert float(yc[b, l:].abs().max()) == 0.0
+        out[mode] = errs
+    _record(test='lstm_layer_H512_B96_T800', **out)
+    assert max(out['fp32'].values()) < TOL, out['fp32']
+    assert out['bf16']['y_abs'] < 2e-2, out['bf16']
+    assert max(v for k_, v in out['bf16'].items() if k_ != 'y_abs') < 3e-2, out['bf16']

@@ -93,3 +93,44 @@ def test_nonpositive_length_raises_like_pack_padded_sequence():
         orc.listener_forward(sd, x, [16, 0], 1, 3)
     with pytest.raises(RuntimeError):      # 7 frames -> length 0 at the third pyramid level
         orc.listener_forward(sd, x, [16, 7], 1, 3)
+
+
+def test_oracle_train_at_the_benchmarked_lengths():
+    """BASELINE configs[1]'s lengths (T = 1600, L = 300), best config with the yml's dropouts (masks replayed): the oracle against
+    the unmodified reference's logits, loss, gradient norms and strided gradient samples (about 20 s)."""
+    g = load_golden('best_train_T1600_L300')
+    torch.set_num_threads(os.cpu_count() or 8)
+    logits, att, loss, grads = oracle_train_from_fixture(g, torch.float32)
+    assert rel_err(logits.numpy(), g['logits']) < TOL
+    assert np.abs(att.numpy() - g['att']).max() < 1e-5
+    assert abs(float(loss) - float(g['loss'])) < 1e-5
+    # the fixture's own conditioning: the reference in float64 (same masks) agrees with its fp32 run far inside the bar
+    assert rel_err(g['logits'], g['logits64']) < 1e-5
+    floor = grad_floor(g)
+    for k, gr in grads.items():
+        if gr is None:
+            continue
+        got = gr.numpy()
+        ref_norm = float(g['gradnorm.' + k])
+        assert abs(float(np.linalg.norm(got.astype(np.float64))) - ref_norm) <= TOL * max(ref_norm, floor), k
+        stride = max(1, -(-got.size // 4096))
+        assert np.abs(got.reshape(-1)[::stride] - g['gradsample.' + k]).max() <= TOL * max(float(g['gradabsmax.' + k]), floor), k
+
+
+def test_oracle_greedy_at_the_benchmarked_lengths():
+    """BASELINE configs[3]'s lengths (T = 3000 -> T_enc = 375, 600 greedy steps): transcripts identical to the reference."""
+    g = load_golden('best_greedy_T3000')
+    cfg = fixture_cfg(g)
+    sd = gu.make_state_dict(cfg, int(g['seed']), scale=float(g['scale']))
+    p = {k: torch.from_numpy(v.copy()) for k, v in sd.items()}
+    torch.set_num_threads(os.cpu_count() or 8)
+    with torch.no_grad():
+        logits, att = orc.las_forward(p, torch.from_numpy(g['x']), g['lx'].tolist(), lstm_layers=1, plstm_layers=3, heads=1,
+                                      training=False, steps=600)
+    chars = logits.argmax(-1).numpy()
+    assert np.array_equal(chars, g['chars'])
+    assert [orc.idx_to_str(c, orc.VOCAB, 0, 29) for c in chars] == [str(s) for s in g['transcripts']]
+    # max-norm error against the reference's float64 run, no worse than 3x the reference's own fp32 round-off (or the bar)
+    own = rel_err(g['logits'], g['logits64'])
+    assert rel_err(logits.numpy(), g['logits64']) < max(TOL, 3 * own)
+    assert float(g['margin_min'].min()) > 10 * np.abs(g['logits'] - g['logits64']).max()      # transcripts are well separated
