@@ -15,6 +15,7 @@
 //   * QC[t] = [q_proj_t | ctx_t] is both the classifier input and where attention reads its query.
 #include "las_common.cuh"
 #include "las_b200.h"
+#include "dec_persist.h"
 #include <vector>
 #include <mutex>
 #include <stdlib.h>
@@ -30,6 +31,7 @@ int las_tc_plan_launch_split(const void* plan_mem, int a_batch, float* Cpart, lo
 int las_tc_plan_tiles(const void* plan_mem);
 int las_tc_plan_kiters(const void* plan_mem);
 int las_permute_cast_lstm_rows(const float* src, long long ld_src, void* dst, int H, int K, void* stream);
+int las_transpose_cast_f16(const float* src, void* dst, int rows, int cols, void* stream);   // decoder_persist.cu
 
 namespace {
 
@@ -368,10 +370,17 @@ struct Layout {
     // bf16 region (offsets in floats, buffers hold bf16): tensor-pipe mode only
     size_t Wcat0b, Wcat1b, Wqb, S0b, S1b, G0b, G1b, dQb, dlb, ohb, QCb, tmp32, skws, Wcat0p, Wcat1p, Gp0, Gp1, dSp0, dSp1, WqT;
     size_t skws_floats;
+    // persistent decoder-step kernel (decoder_persist.cu): fp16 weights / operand rows, hand-off counters, device coin flags
+    size_t Wcat0h, Wcat1h, WqTh, S0h, S1h;
+    int persist;
     // int workspace offsets
-    size_t tok, total_i;
+    size_t tok, pctr, ugold, total_i;
     int hist, ghist;
 };
+
+bool persist_wanted(const LasSpeller* s) {
+    return s->use_tc && s->kv_bf16 != 1 && las_dec_persist_fwd_supported(s->B, s->T, s->P, s->DH, s->DO, s->V, s->heads, s->init_force) != 0;
+}
 
 Layout make_layout(const LasSpeller* s) {
     Layout L{};
@@ -441,9 +450,22 @@ Layout make_layout(const LasSpeller* s) {
             }
         }
     }
+    L.persist = persist_wanted(s) ? 1 : 0;
+    if (L.persist) {
+        auto takeh = [&](size_t n_f16) { return take((n_f16 + 1) / 2 + 4); };
+        L.Wcat0h = takeh(4 * DH * (P + DH));
+        L.Wcat1h = takeh(4 * DO * (DH + DO));
+        L.WqTh = takeh(P * DO);
+        L.S0h = takeh((size_t)L.hist * B * (P + DH));
+        L.S1h = takeh((size_t)L.hist * B * (DH + DO));
+    }
     L.total_f = o;
     L.tok = 0;
-    L.total_i = s->training ? S * B : 4;
+    size_t oi = s->training ? S * B : 4;
+    oi = (oi + 31) & ~(size_t)31;                 // hand-off counters sit 128 bytes apart
+    L.pctr = oi; oi += L.persist ? las_dec_persist_ctr_words((int)B) : 0;
+    L.ugold = oi; oi += L.persist ? ((S + 3) & ~(size_t)3) : 0;
+    L.total_i = oi;
     return L;
 }
 
@@ -506,6 +528,12 @@ extern "C" int las_lstm_cell_bwd_f32(float* gates, const float* dh, const float*
     return LAS_OK;
 }
 
+// 1 when las_speller_fwd_f32 would run this shape as the persistent decoder-step kernel (tensor-pipe mode only); callers use it to
+// pick the K / V element type (fp32 or fp16) that path accepts
+extern "C" int las_speller_persistent(int B, int T, int P, int DH, int DO, int V, int heads, int init_force, int use_tc) {
+    return (use_tc && las_dec_persist_fwd_supported(B, T, P, DH, DO, V, heads, init_force)) ? 1 : 0;
+}
+
 extern "C" size_t las_speller_workspace_floats(const LasSpeller* s) { return s ? make_layout(s).total_f : 0; }
 extern "C" size_t las_speller_workspace_ints(const LasSpeller* s) { return s ? make_layout(s).total_i : 0; }
 
@@ -566,6 +594,7 @@ unsigned long long fnv1a(const void* p, size_t n, unsigned long long h) {
     return h;
 }
 int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st, GraphSeg* seg);
+int speller_fwd_persist(const LasSpeller* s, const Layout& L, cudaStream_t st);
 }  // namespace
 
 namespace {
@@ -662,10 +691,88 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
     kd.use_gold_host = nullptr;
     unsigned long long key = fnv1a(&kd, sizeof(LasSpeller), 1469598103934665603ULL);
     if (s->use_gold_host) key = fnv1a(s->use_gold_host, (size_t)s->steps, key);
+    // persistent decoder-step kernel: one cooperative launch for the whole loop (plus a handful of weight-preparation kernels),
+    // enqueued directly -- nothing to amortise with a graph, and no graph key that depends on the coin pattern
+    if (L.persist) return speller_fwd_persist(s, L, st);
     return run_graph_cached(key, st, [&](cudaStream_t q, GraphSeg* seg) { return speller_fwd_enqueue(s, L, q, seg); });
 }
 
 namespace {
+int speller_fwd_persist(const LasSpeller* s, const Layout& L, cudaStream_t st) {
+    const int B = s->B, T = s->T, P = s->P, E = s->E, DH = s->DH, DO = s->DO, V = s->V, S = s->steps;
+    const int K0 = P + DH, K1 = DH + DO;
+    float* f = s->fws;
+    float *Wcat0 = f + L.Wcat0, *Wcat1 = f + L.Wcat1, *Gemb = f + L.Gemb, *C0 = f + L.C0, *C1 = f + L.C1, *QC = f + L.QC;
+    const size_t fsz = sizeof(float);
+    __nv_bfloat16 *Wcat0b = (__nv_bfloat16*)(f + L.Wcat0b), *Wcat1b = (__nv_bfloat16*)(f + L.Wcat1b), *Wqb = (__nv_bfloat16*)(f + L.Wqb),
+                  *S0b = (__nv_bfloat16*)(f + L.S0b), *S1b = (__nv_bfloat16*)(f + L.S1b);
+    __half *Wcat0h = (__half*)(f + L.Wcat0h), *Wcat1h = (__half*)(f + L.Wcat1h), *WqTh = (__half*)(f + L.WqTh), *S0h = (__half*)(f + L.S0h),
+           *S1h = (__half*)(f + L.S1h);
+    // packed weights: [W_ih0[:, E:] | W_hh0], [W_ih1 | W_hh1]
+    LAS_CUDA(cudaMemcpy2DAsync(Wcat0, K0 * fsz, s->w_ih0 + E, (size_t)(E + P) * fsz, P * fsz, 4 * DH, cudaMemcpyDeviceToDevice, st));
+    LAS_CUDA(cudaMemcpy2DAsync(Wcat0 + P, K0 * fsz, s->w_hh0, DH * fsz, DH * fsz, 4 * DH, cudaMemcpyDeviceToDevice, st));
+    LAS_CUDA(cudaMemcpy2DAsync(Wcat1, K1 * fsz, s->w_ih1, DH * fsz, DH * fsz, 4 * DO, cudaMemcpyDeviceToDevice, st));
+    LAS_CUDA(cudaMemcpy2DAsync(Wcat1 + DH, K1 * fsz, s->w_hh1, DO * fsz, DO * fsz, 4 * DO, cudaMemcpyDeviceToDevice, st));
+    RC(las_cast_f32_to_f16(Wcat0, K0, 0, 0, Wcat0h, K0, 4 * DH, K0, K0, st));
+    RC(las_cast_f32_to_f16(Wcat1, K1, 0, 0, Wcat1h, K1, 4 * DO, K1, K1, st));
+    RC(las_transpose_cast_f16(s->wq, WqTh, P, DO, st));                          // (P, DO) fp32 -> (DO, P) fp16
+    if (s->training) {                                                           // backward's bf16 operands
+        RC(cast_rows(st, Wcat0, K0, Wcat0b, K0, 4 * DH, K0));
+        RC(cast_rows(st, Wcat1, K1, Wcat1b, K1, 4 * DO, K1));
+        RC(cast_rows(st, s->wq, DO, Wqb, DO, P, DO));
+        LAS_CUDA(cudaMemset2DAsync(S0b + P, K0 * 2, 0, DH * 2, B, st));          // h0_{-1} = 0
+        LAS_CUDA(cudaMemset2DAsync(S1b + DH, K1 * 2, 0, DO * 2, B, st));         // h1_{-1} = 0
+    }
+    LAS_CUDA(cudaMemset2DAsync(S0h + P, K0 * 2, 0, DH * 2, B, st));
+    LAS_CUDA(cudaMemset2DAsync(S1h + DH, K1 * 2, 0, DO * 2, B, st));
+    // embedding-side gate table (+ both cell-0 biases); zero initial cell states (src/models.py:275-281)
+    RC(gemm(st, s->emb, E, s->w_ih0, E + P, 1, Gemb, 4 * DH, V, 4 * DH, E, 0.f, s->b_ih0, s->b_hh0));
+    LAS_CUDA(cudaMemsetAsync(C0, 0, (size_t)B * DH * fsz, st));
+    LAS_CUDA(cudaMemsetAsync(C1, 0, (size_t)B * DO * fsz, st));
+    unsigned* ctr = (unsigned*)(s->iws + L.pctr);
+    const size_t ctr_words = las_dec_persist_ctr_words(B);
+    LAS_CUDA(cudaMemsetAsync(ctr, 0, ctr_words * sizeof(unsigned), st));
+    bool all_gold = s->training != 0;
+    if (s->training)
+        for (int t = 1; t < S; ++t) all_gold = all_gold && s->use_gold_host && s->use_gold_host[t];
+    int* ugold = s->iws + L.ugold;
+    if (s->training && !all_gold) {
+        std::vector<int> ug((size_t)S, 0);
+        for (int t = 1; t < S; ++t) ug[t] = (s->use_gold_host && s->use_gold_host[t]) ? 1 : 0;
+        LAS_CUDA(cudaMemcpyAsync(ugold, ug.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice, st));   // pageable source: staged before the call returns
+    }
+    LasDecPersistFwd a{};
+    a.B = B; a.T = T; a.P = P; a.DH = DH; a.DO = DO; a.V = V; a.steps = S; a.training = s->training; a.sos_idx = s->sos_idx;
+    a.hist = L.hist; a.ghist = L.ghist;
+    a.per_step_logits = all_gold ? 0 : 1;
+    a.kv16 = s->kv_bf16 == 2 ? 1 : 0;
+    a.scale = sqrtf((float)(P / s->heads));
+    a.emb = s->emb; a.cls_b = s->cls_b; a.bq = s->bq; a.b_ih1 = s->b_ih1; a.b_hh1 = s->b_hh1; a.init_query = s->init_query;
+    a.Gemb = Gemb; a.W0 = Wcat0h; a.W1 = Wcat1h; a.WqT = WqTh;
+    a.K = s->K; a.Vv = s->V_; a.enc_lens = s->enc_lens;
+    a.y = s->training ? s->dec_y : nullptr; a.ld_y = s->ld_y;
+    a.use_gold = (s->training && !all_gold) ? ugold : nullptr;
+    a.drop0 = s->drop0; a.drop1 = s->drop1;
+    a.S0h = S0h; a.S1h = S1h;
+    a.S0b = s->training ? S0b : nullptr; a.S1b = s->training ? S1b : nullptr;
+    a.C0 = C0; a.C1 = C1; a.G0 = f + L.G0; a.G1 = f + L.G1; a.QC = QC; a.W = f + L.W;
+    a.att0 = s->att0; a.logits = s->logits; a.chars = s->chars;
+    a.tok = s->training ? s->iws + L.tok : nullptr;
+    a.ctr = ctr; a.err = ctr + (ctr_words - 32);
+    RC(las_dec_persist_fwd_launch(&a, st));
+    if (all_gold) {
+        // all classifier rows at once: row m = t*B + b of QC[1..S] -> logits[b, t, :]
+        LasGemmF32 d{};
+        d.A = QC + (size_t)B * 2 * P; d.B = s->emb; d.C = s->logits; d.bias1 = s->cls_b;
+        d.M = S * B; d.N = V; d.K = 2 * P; d.batch = 1;
+        d.a_m_si = 2 * P; d.a_k_si = 1; d.b_k_si = 1; d.b_n_s = E;
+        d.c_m_inner = B; d.c_m_so = V; d.c_m_si = (long long)S * V;
+        d.alpha = 1.f; d.beta = 0.f;
+        RC(las_gemm_f32(&d, st));
+    }
+    return LAS_OK;
+}
+
 int speller_fwd_enqueue(const LasSpeller* s, const Layout& L, cudaStream_t st, GraphSeg* seg) {
     void* stream = (void*)st;
     (void)stream;

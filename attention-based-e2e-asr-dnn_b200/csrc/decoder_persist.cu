@@ -1,0 +1,724 @@
+// Persistent decoder-step kernel: the whole time loop of Speller.forward (reference src/models.py:336-385, with
+// AutoRegDecoderLSTMCell.forward src/modules.py:340-365 and MultiheadCrossAttention.forward src/models.py:157-192 inlined) as ONE
+// cooperative launch of one CTA per SM.  A decoder step is three sequentially dependent phases,
+//     ATT(t)  : q_t = query_map(h1_{t-1}) ; e = q.K^T.sqrt(d) ; length mask ; softmax ; ctx_t = w.V        (one CTA per batch row)
+//     C0(t)   : gates = Gemb[token_t] + [ctx_t | h0_{t-1}] . [W_ih0[:, E:] | W_hh0]^T ; LSTM cell ; dropout  (DH/32 CTAs per 32-row slice)
+//     C1(t)   : gates = b + [h0_t | h1_{t-1}] . [W_ih1 | W_hh1]^T ; LSTM cell ; dropout                     (DO/32 CTAs per 32-row slice)
+// and the launch-per-stage loop it replaces paid a kernel boundary (launch + prologue + weight re-read from L2) for each of them:
+// 31 us per step for ~10 us of dependent work.  Here
+//   * every cell CTA keeps its 128 x K fp16 weight slice (32 hidden units x 4 gates) in TENSOR MEMORY for the whole loop and uses it
+//     as the A operand of tcgen05.mma (".ts" form, M = 128); the B operand is the 32-row batch slice of the step's input row
+//     (N = 32), copied from L2 into shared memory in the UMMA K-major no-swizzle core-matrix layout; four independent TMEM
+//     accumulators (UMMAs into one accumulator serialise), summed in the epilogue;
+//   * the part of a cell's input row that is already known (its own recurrent state of the previous step) is loaded and multiplied
+//     BEFORE the phase hand-off it waits for, so only the freshly produced half (ctx_t / h0_t) is on the critical path;
+//   * phases hand off through L2 with one release/acquire counter per (phase, batch slice): red.release.gpu after the CTA's stores,
+//     one polling thread + bar.sync on the consumer side -- batch slices never wait for each other;
+//   * the query projection runs inside the attention CTA (fp16 Wq^T resident in shared memory, fp32 accumulate);
+//   * forward operands are IEEE fp16, not bf16: |h| <= 1/(1-p), the context is a convex combination of value rows and the weights are
+//     O(1), so the range is safe and the 3 extra mantissa bits cut the decoder's share of the AMP logit error 8x (measured with
+//     the operand-rounding emulation in DESIGN.md section 2: 2.3e-3 -> 3.0e-4 at T=1600 / L=300).  Gradients stay bf16.
+// Hand-off waits carry a watchdog (~2 s): a lost hand-off sets *err and traps instead of hanging the GPU.
+#include "las_common.cuh"
+#include "las_b200.h"
+#include "dec_persist.h"
+#include <float.h>
+#include <stdlib.h>
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int NW = NT / 32;
+constexpr int NBS = 32;          // batch rows per slice (UMMA N)
+constexpr int NACC = 4;          // independent TMEM accumulators
+constexpr int MAX_CHAINS = 2;    // batch slices one cell CTA may own
+constexpr int RU = 8;            // K (or V) rows in flight per warp: 8 KB per warp, 64 KB per SM
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// A operand from tensor memory (".ts" form): D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, no swizzle: LBO (next 8-element core along K) 512 B, SBO (next 8 rows) 128 B -- same operand layout as the DSMEM recurrence
+__device__ __forceinline__ uint64_t make_desc_k_noswz(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(512 >> 4) << 16;
+    d |= (uint64_t)(128 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// idesc: F32 accumulate, F16 x F16 (format bits 7..9 / 10..12 = 0), both K-major, M = 128, N = 32
+constexpr uint32_t IDESC_F16 = (1u << 4) | ((uint32_t)(NBS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+// loads that must observe other SMs' stores of this launch: L2 only (a stale L1 line of a ring-buffer slot would otherwise be legal)
+__device__ __forceinline__ uint4 ldcg_v4(const void* p) {
+    uint4 v;
+    // no "memory" clobber: a clobber orders the load against the st.shared that consumes the previous one and serialises a copy loop
+    // into one L2 round trip per iteration (measured: 0.4 us per 16 bytes per thread); callers sit behind a bar.sync anyway
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned short ldcg_u16(const void* p) {
+    unsigned short v;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ldcg_s32(const void* p) {
+    int v;
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg4u_stream(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// accurate to a few ulp (the old per-stage kernels use expf / tanhf; tanh.approx's 2^-11 would now dominate the fp16 operand rounding)
+// ex2.approx + rcp.approx: a few ulp, no IEEE-division slow path
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_acc(float x) {
+    const float e = __expf(-2.0f * fabsf(x));
+    return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+}
+
+// one thread polls with acquire semantics, the CTA follows through bar.sync (cumulativity makes the producers' stores visible to all)
+__device__ __forceinline__ void cta_wait_ge(const unsigned* ctr, unsigned target, unsigned* err) {
+    if (threadIdx.x == 0) {
+        long long t0 = 0;
+        unsigned spins = 0;
+        while ((int)(ld_acquire_gpu(ctr) - target) < 0) {
+            if ((++spins & 1023u) == 0) {
+                const long long now = clock64();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000LL) { *err = 1u; __threadfence_system(); __trap(); }
+            }
+        }
+    }
+    __syncthreads();
+}
+// all threads of the CTA have issued their global stores -> one release increment
+__device__ __forceinline__ void cta_signal(unsigned* ctr) {
+    __syncthreads();
+    if (threadIdx.x == 0) red_release_gpu_add(ctr, 1u);
+}
+
+__device__ __forceinline__ long long gtime_ns() {
+    long long v;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+    return v;
+}
+// debug timeline (las_dec_persist_set_debug): slot `sl` of step `st`, written by one thread of the CTA that owns the role
+#define DP_STAMP(cond, st, sl)                                                                   \
+    do {                                                                                         \
+        if (a.dbg && (cond) && threadIdx.x == 0 && (st) < 256) a.dbg[(st) * 16 + (sl)] = gtime_ns(); \
+    } while (0)
+
+struct SmemLayout {
+    uint32_t tile, ex, wq, sc, part, misc, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int T, int P, int DH, int DO) {
+    SmemLayout L;
+    const int K0 = P + DH, K1 = DH + DO, Kmax = K0 > K1 ? K0 : K1;
+    uint32_t o = 0;
+    L.tile = o; o += 64u * (uint32_t)Kmax;                   // 32 rows x Kmax fp16, core-matrix layout
+    L.ex = o; o += 4u * 32u * 32u * 4u;                      // [gate][row][unit] activated gates
+    L.wq = o; o += (uint32_t)DO * (uint32_t)P * 2u;          // WqT fp16
+    L.sc = o; o += (uint32_t)((T + 3) & ~3) * 4u;            // scaled energies of one batch row
+    L.part = o; o += (uint32_t)NW * (uint32_t)P * 4u;        // per-warp partial context
+    L.misc = o; o += 8192u;                                  // see `Misc`
+    L.total = o + 1024u;                                     // alignment slack
+    return L;
+}
+struct Misc {
+    float wm[NW], wsum[NW];
+    float qc[512];            // [q | ctx] of the current row (2P <= 512)
+    float h1s[256];           // decoder output h1 of the current row (DO <= 256)
+    float qpart[1024];        // query-projection partials [k group][P]  (k groups = NT / (P / 4))
+    float lg[32];             // logits of the current row (V <= 32)
+    unsigned long long tfull; // mbarrier: UMMAs of the current cell phase retired
+    uint32_t tmem_slot;
+};
+
+// 8 consecutive-in-register elements of one K / V row for this lane.  fp32 rows: floats [4l, 4l+4) and [128 + 4l, 128 + 4l + 4);
+// fp16 rows: halves [8l, 8l + 8).  Element i of the lane sits at column kcol<KV16>(lane, i).
+template <bool KV16>
+__device__ __forceinline__ int kcol(int lane, int i) { return KV16 ? lane * 8 + i : (i < 4 ? lane * 4 + i : 128 + lane * 4 + (i - 4)); }
+template <bool KV16, bool NA>
+__device__ __forceinline__ void load_row8(const void* base, long long row_off, int lane, int P, float (&v)[8]) {
+    if (KV16) {
+        if (lane * 8 < P) {
+            const uint4 r = NA ? ldg4u_stream(reinterpret_cast<const __half*>(base) + row_off + lane * 8)
+                               : __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(base) + row_off + lane * 8));
+            const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+    } else {
+        const float* p = reinterpret_cast<const float*>(base) + row_off;
+        const float4 a = (lane * 4 < P) ? (NA ? ldg4_stream(p + lane * 4) : __ldg(reinterpret_cast<const float4*>(p + lane * 4)))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b = (128 + lane * 4 < P) ? (NA ? ldg4_stream(p + 128 + lane * 4) : __ldg(reinterpret_cast<const float4*>(p + 128 + lane * 4)))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
+
+template <bool KV16, bool NA>
+__global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(const LasDecPersistFwd a) {
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int B = a.B, T = a.T, P = a.P, DH = a.DH, DO = a.DO, V = a.V, S = a.steps;
+    const int K0 = P + DH, K1 = DH + DO;
+    const int n0r = DH / 32, n1r = DO / 32;
+    const int n0 = n0r * a.ngroups, n1 = n1r * a.ngroups;
+    // ---- roles: the last n0 CTAs are cell-0 CTAs, the n1 before them cell-1 CTAs; attention rows start at CTA 0 ----
+    int role = 0, r = 0, sg = 0;
+    if (cta >= G - n0) { role = 1; r = (cta - (G - n0)) % n0r; sg = (cta - (G - n0)) / n0r; }
+    else if (cta >= G - n0 - n1) { role = 2; r = (cta - (G - n0 - n1)) % n1r; sg = (cta - (G - n0 - n1)) / n1r; }
+    const int H = role == 1 ? DH : DO, Kc = role == 1 ? K0 : K1;
+    const int kcrit = role == 1 ? P : DH;                   // columns [0, kcrit) arrive with the hand-off, [kcrit, Kc) are this role's own state
+    unsigned* ctr_att = a.ctr;                                // [slice] ATT(t) rows done
+    unsigned* ctr_c0 = a.ctr + 32 * a.nsl;                    // [slice] cell-0 CTAs done
+    unsigned* ctr_c1 = a.ctr + 64 * a.nsl;                    // [slice] cell-1 CTAs done
+
+    const SmemLayout L = smem_layout(T, P, DH, DO);
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t tile_sm = base + L.tile;
+    uint8_t* tile_ptr = sm + L.tile;
+    float* ex = reinterpret_cast<float*>(sm + L.ex);
+    const __half2* wq_s = reinterpret_cast<const __half2*>(sm + L.wq);
+    float* sc = reinterpret_cast<float*>(sm + L.sc);
+    float* part = reinterpret_cast<float*>(sm + L.part);
+    Misc* ms = reinterpret_cast<Misc*>(sm + L.misc);
+    const uint32_t tfull_bar = smem_u32(&ms->tfull);
+
+    if (tid == 0) {
+        mbar_init(tfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t tmem_base = 0;
+    if (role) {
+        if (warp == 2) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ms->tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    // query-projection weight (fp16, transposed) -> shared memory, for CTAs that own attention rows
+    if (cta < B) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.WqT);
+        uint4* dst = reinterpret_cast<uint4*>(sm + L.wq);
+        const int n16 = DO * P * 2 / 16;
+        for (int i = tid; i < n16; i += NT) dst[i] = src[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tmem_base = ms->tmem_slot;
+    const uint32_t tmem_w = tmem_base + NACC * NBS;
+    if (role && warp >= 4) {
+        // resident A operand: 128 x Kc fp16 slice (TMEM lane = gate * 32 + unit, two halves per 32-bit column)
+        const int qq = warp & 3;
+        const __half* Wsrc = role == 1 ? a.W0 : a.W1;
+        const uint32_t* wrow = reinterpret_cast<const uint32_t*>(Wsrc + ((long long)qq * H + r * 32 + lane) * Kc);
+        for (int cb = 0; cb < Kc / 64; ++cb) {
+            uint32_t v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 t4 = *reinterpret_cast<const uint4*>(wrow + cb * 32 + i * 4);
+                v[i * 4 + 0] = t4.x; v[i * 4 + 1] = t4.y; v[i * 4 + 2] = t4.z; v[i * 4 + 3] = t4.w;
+            }
+            tmem_st32(tmem_w + ((uint32_t)(qq * 32) << 16) + cb * 32, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    float cst[MAX_CHAINS][4];          // cell state of (batch rows warp*4 + i, unit lane) of every owned slice
+#pragma unroll
+    for (int c = 0; c < MAX_CHAINS; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cst[c][i] = 0.f;
+    uint32_t ncommit = 0;
+    const int chains = (a.nsl + a.ngroups - 1) / a.ngroups;
+
+    for (int ai = 0; ai <= S; ++ai) {
+        // =====================================================================================================================
+        // ATT(ai): one batch row per pass of this CTA
+        // =====================================================================================================================
+        for (int b = cta; b < B; b += G) {
+            const int slice = b / NBS;
+            const int slot = ai % a.hist;
+            __syncthreads();           // the deferred stores of the previous row / step have read sc[] and qc[]
+            if (ai > 0) cta_wait_ge(ctr_c1 + 32 * slice, (unsigned)(n1r * ai), a.err);
+            DP_STAMP(cta == 0, ai, 0);
+            if (tid < DO)
+                ms->h1s[tid] = ai == 0 ? a.init_query[tid]
+                                       : __half2float(__ushort_as_half(ldcg_u16(a.S1h + ((long long)slot * B + b) * K1 + DH + tid)));
+            __syncthreads();
+            {   // q = Wq . h1 + bq : thread = (output quad j4, k group kg); 64-bit shared loads of Wq^T, h1 broadcast four at a time
+                const int quadP = P >> 2, kgroups = NT / quadP, klen = DO / kgroups;
+                const int j4 = tid % quadP, kg = tid / quadP;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const uint2* wp = reinterpret_cast<const uint2*>(wq_s) + (long long)kg * klen * quadP + j4;
+                const float4* hp = reinterpret_cast<const float4*>(ms->h1s + kg * klen);
+#pragma unroll 4
+                for (int k4 = 0; k4 < klen / 4; ++k4) {
+                    const float4 hv = hp[k4];
+                    const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+                    for (int kk2 = 0; kk2 < 4; ++kk2) {
+                        const uint2 w4 = wp[(long long)(k4 * 4 + kk2) * quadP];
+                        const float2 wa = __half22float2(*reinterpret_cast<const __half2*>(&w4.x));
+                        const float2 wb = __half22float2(*reinterpret_cast<const __half2*>(&w4.y));
+                        acc[0] = fmaf(hk[kk2], wa.x, acc[0]); acc[1] = fmaf(hk[kk2], wa.y, acc[1]);
+                        acc[2] = fmaf(hk[kk2], wb.x, acc[2]); acc[3] = fmaf(hk[kk2], wb.y, acc[3]);
+                    }
+                }
+                *reinterpret_cast<float4*>(ms->qpart + kg * P + 4 * j4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                __syncthreads();
+                if (tid < P) {
+                    float q = a.bq[tid];
+                    for (int g2 = 0; g2 < kgroups; ++g2) q += ms->qpart[g2 * P + tid];
+                    ms->qc[tid] = q;
+                }
+                __syncthreads();
+            }
+            DP_STAMP(cta == 0, ai, 1);
+            const int len = min(a.enc_lens[b], T);
+            float qv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int k = kcol<KV16>(lane, i); qv[i] = k < P ? ms->qc[k] : 0.f; }
+            const long long mbase = (long long)b * T * P;
+            // ---- pass 1: scaled energies of every valid row into shared memory (8 rows = 8 independent reductions in flight per warp).
+            // Two passes (K, then V) instead of one online-softmax pass: with 8 warps per SM a warp that loads, reduces, rescales and
+            // accumulates in one loop exposes every latency once per iteration (measured 9.6 us per 410 KB row); the bytes are the same.
+            for (int tb = warp; tb < len; tb += NW * RU) {
+                float kk[RU][8];
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    const int t = tb + u * NW;
+                    if (t < len) load_row8<KV16, NA>(a.K, mbase + (long long)t * P, lane, P, kk[u]);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) kk[u][i] = 0.f;
+                    }
+                }
+                float e[RU];
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc = fmaf(kk[u][i], qv[i], acc);
+                    e[u] = acc;
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) e[u] += __shfl_xor_sync(0xffffffffu, e[u], off);
+                if (lane == 0) {
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) { const int t = tb + u * NW; if (t < len) sc[t] = e[u] * a.scale; }
+                }
+            }
+            DP_STAMP(cta == 0, ai, 14);
+            __syncthreads();
+            // ---- softmax statistics, computed redundantly by every warp from shared memory ----
+            float m_c = -INFINITY;
+            for (int t = lane; t < len; t += 32) m_c = fmaxf(m_c, sc[t]);
+            m_c = warp_max(m_c);
+            float s_c = 0.f;
+            for (int t = lane; t < len; t += 32) s_c += __expf(sc[t] - m_c);
+            s_c = warp_sum(s_c);
+            const float inv = 1.f / s_c;
+            // ---- pass 2: context = sum_t p_t V_t ----
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = 0.f;
+            for (int tb = warp; tb < len; tb += NW * RU) {
+                float vv[RU][8], pw[RU];
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    const int t = tb + u * NW;
+                    if (t < len) {
+                        load_row8<KV16, NA>(a.Vv, mbase + (long long)t * P, lane, P, vv[u]);
+                        pw[u] = __expf(sc[t] - m_c);
+                    } else {
+                        pw[u] = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) vv[u][i] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < RU; ++u)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = fmaf(pw[u], vv[u][i], o[i]);
+            }
+            DP_STAMP(cta == 0, ai, 2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int k = kcol<KV16>(lane, i); if (k < P) part[warp * P + k] = o[i]; }
+            __syncthreads();
+            if (tid < P) {
+                float rr = 0.f;
+#pragma unroll
+                for (int i = 0; i < NW; ++i) rr += part[i * P + tid];
+                rr *= inv;
+                ms->qc[P + tid] = rr;
+                a.S0h[((long long)slot * B + b) * K0 + tid] = __float2half_rn(rr);     // the only store cell 0 waits for
+            }
+            if (a.per_step_logits && ai > 0) {
+                // tied classifier on cat[q_proj, ctx] (src/models.py:370-373) + greedy argmax (:380; first maximum like torch.argmax)
+                __syncthreads();
+                for (int v = warp; v < V; v += NW) {
+                    const float* er = a.emb + (long long)v * 2 * P;
+                    float acc = 0.f;
+                    for (int k = lane * 4; k < 2 * P; k += 128) {
+                        const float4 e4 = *reinterpret_cast<const float4*>(er + k);
+                        const float4 x4 = *reinterpret_cast<const float4*>(ms->qc + k);
+                        acc = fmaf(e4.x, x4.x, acc); acc = fmaf(e4.y, x4.y, acc); acc = fmaf(e4.z, x4.z, acc); acc = fmaf(e4.w, x4.w, acc);
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == 0) ms->lg[v] = acc + a.cls_b[v];
+                }
+                __syncthreads();
+                if (tid < V) a.logits[((long long)b * S + (ai - 1)) * V + tid] = ms->lg[tid];
+                if (tid == 0) {
+                    int best = 0;
+                    float bv = ms->lg[0];
+                    for (int v = 1; v < V; ++v)
+                        if (ms->lg[v] > bv) { bv = ms->lg[v]; best = v; }
+                    a.chars[(long long)(ai - 1) * B + b] = best;
+                }
+            }
+            cta_signal(ctr_att + 32 * slice);
+            DP_STAMP(cta == 0, ai, 3);
+            // ---- history that only backward / the caller read: stored behind the hand-off, off the critical path ----
+            {
+                float* qcrow = a.QC + ((long long)slot * B + b) * 2 * P;
+                for (int k = tid; k < 2 * P; k += NT) qcrow[k] = ms->qc[k];
+                if (a.S0b && tid < P) a.S0b[((long long)slot * B + b) * K0 + tid] = __float2bfloat16(ms->qc[P + tid]);
+                // normalised weights; exact zeros past the length (src/models.py:171-175)
+                float* wrow = a.W + ((long long)slot * B + b) * T;
+                for (int t = tid; t < T; t += NT) {
+                    const float wv = t < len ? __expf(sc[t] - m_c) * inv : 0.f;
+                    wrow[t] = wv;
+                    if (b == 0 && a.att0) a.att0[(long long)ai * T + t] = wv;
+                }
+            }
+        }
+        if (ai == S) break;
+        // =====================================================================================================================
+        // C0(t) / C1(t)
+        // =====================================================================================================================
+        if (role) {
+            const int t = ai;
+            const int slot_in = t % a.hist, slot_out = (t + 1) % a.hist;
+#pragma unroll
+            for (int c = 0; c < MAX_CHAINS; ++c) {
+                const int slice = sg + c * a.ngroups;
+                if (c >= chains || slice >= a.nsl) continue;
+                const int b0 = slice * NBS;
+                const int rows = min(NBS, B - b0);
+                const __half* src = (role == 1 ? a.S0h : a.S1h) + ((long long)slot_in * B + b0) * Kc;
+                unsigned* ctr_self = (role == 1 ? ctr_c0 : ctr_c1) + 32 * slice;
+                const unsigned nr = (unsigned)(role == 1 ? n0r : n1r);
+                auto load_cols = [&](int kc_lo, int kc_hi) {       // 16-byte chunks (row n, core kc) -> core-matrix layout
+                    const int kcn = kc_hi - kc_lo, nchunks = NBS * kcn;
+                    for (int ch0 = tid; ch0 < nchunks; ch0 += 4 * NT) {         // four loads in flight per thread, then the four stores
+                        uint4 v[4];
+                        int dst[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int ch = ch0 + jj * NT;
+                            const int i8 = ch & 7, rest = ch >> 3;
+                            const int ngp = rest / kcn, kc = kc_lo + (rest - ngp * kcn);
+                            const int n = ngp * 8 + i8;
+                            dst[jj] = ch < nchunks ? kc * 512 + ngp * 128 + i8 * 16 : -1;
+                            v[jj] = (ch < nchunks && n < rows) ? ldcg_v4(src + (long long)n * Kc + kc * 8) : make_uint4(0u, 0u, 0u, 0u);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (dst[jj] >= 0) *reinterpret_cast<uint4*>(tile_ptr + dst[jj]) = v[jj];
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                };
+                auto issue = [&](int ks_lo, int ks_hi, uint32_t first, bool last) {   // 16-column k-steps
+                    if (warp == 1) {
+                        tc_fence_after();
+                        if (elect_one()) {
+                            uint32_t n_iss = first;
+                            for (int ks = ks_lo; ks < ks_hi; ++ks, ++n_iss) {
+                                const uint32_t d_tmem = tmem_base + (n_iss & (NACC - 1)) * NBS;
+                                umma_f16_ts(d_tmem, tmem_w + ks * 8, make_desc_k_noswz(tile_sm + (uint32_t)ks * 1024u), IDESC_F16, n_iss >= NACC ? 1u : 0u);
+                            }
+                            if (last) umma_commit(tfull_bar);
+                        }
+                        __syncwarp();
+                    }
+                };
+                // ---- own recurrent state of step t-1 (complete once every CTA of this role and slice has signalled step t-1) ----
+                if (t > 0) cta_wait_ge(ctr_self, nr * (unsigned)t, a.err);
+                load_cols(kcrit / 8, Kc / 8);
+                __syncthreads();
+                issue(kcrit / 16, Kc / 16, 0u, false);
+                DP_STAMP(role == 1 && r == 0 && slice == 0, t, 4);
+                // ---- the freshly produced half: ctx_t from ATT(t) / h0_t from C0(t) ----
+                if (role == 1) cta_wait_ge(ctr_att + 32 * slice, (unsigned)(rows * (t + 1)), a.err);
+                else cta_wait_ge(ctr_c0 + 32 * slice, (unsigned)(n0r * (t + 1)), a.err);
+                DP_STAMP(r == 0 && slice == 0, t, role == 1 ? 5 : 10);
+                load_cols(0, kcrit / 8);
+                __syncthreads();
+                issue(0, kcrit / 16, (uint32_t)((Kc - kcrit) / 16), true);
+                DP_STAMP(role == 1 && r == 0 && slice == 0, t, 6);
+                {
+                    // ===== epilogue on all 8 warps: warp = (gate q = TMEM lane quarter, batch-row half hf), lane = hidden unit =====
+                    const int q = warp & 3, hf = warp >> 2, j = lane;
+                    const int u = r * 32 + j;
+                    float xg[16];
+                    if (role == 1) {
+                        // token fed at step t (src/models.py:354-358): <sos>, the gold token y[:, t-1], or the previous argmax
+                        int tok = a.sos_idx;
+                        const int nrow = 16 * hf + (lane & 15);
+                        if (t > 0 && nrow < rows) {
+                            const bool gold = a.training && a.y && (!a.use_gold || a.use_gold[t]);
+                            tok = gold ? a.y[(long long)(b0 + nrow) * a.ld_y + t - 1] : ldcg_s32(a.chars + (long long)(t - 1) * B + b0 + nrow);
+                        }
+                        if (a.tok && r == 0 && q == 0 && lane < 16 && nrow < rows) a.tok[(long long)t * B + b0 + nrow] = tok;
+#pragma unroll
+                        for (int n = 0; n < 16; ++n) {
+                            const int tk = __shfl_sync(0xffffffffu, tok, n);
+                            xg[n] = a.Gemb[(long long)tk * 4 * DH + q * DH + u];
+                        }
+                    } else {
+                        const float bsum = a.b_ih1[q * DO + u] + a.b_hh1[q * DO + u];
+#pragma unroll
+                        for (int n = 0; n < 16; ++n) xg[n] = bsum;
+                    }
+                    const float* dmask = role == 1 ? a.drop0 : a.drop1;
+                    float mk[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int b = b0 + warp * 4 + i;
+                        mk[i] = (dmask && b < B) ? dmask[((long long)t * B + b) * H + u] : 1.f;
+                    }
+                    mbar_wait(tfull_bar, ncommit & 1u);
+                    if (a.dbg && r == 0 && slice == 0 && tid == 128 && t < 256) a.dbg[t * 16 + (role == 1 ? 7 : 12)] = gtime_ns();
+                    tc_fence_after();
+#pragma unroll
+                    for (int acc = 0; acc < NACC; ++acc) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NBS + 16 * hf), v);
+#pragma unroll
+                        for (int n = 0; n < 16; ++n) xg[n] += __uint_as_float(v[n]);
+                    }
+                    tc_fence_before();
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) {
+                        const float act = (q == 2) ? tanh_acc(xg[n]) : sigmoid_acc(xg[n]);
+                        ex[(q * 32 + 16 * hf + n) * 32 + j] = act;
+                        xg[n] = act;
+                    }
+                    if (a.dbg && role == 1 && r == 0 && slice == 0 && tid == 128 && t < 256) a.dbg[t * 16 + 9] = gtime_ns();
+                    __syncthreads();
+                    float ccv[4], hmv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int n = warp * 4 + i, b = b0 + n;
+                        ccv[i] = 0.f; hmv[i] = 0.f;
+                        if (b < B) {
+                            const float gi = ex[(0 * 32 + n) * 32 + j], gf = ex[(1 * 32 + n) * 32 + j];
+                            const float gg = ex[(2 * 32 + n) * 32 + j], go = ex[(3 * 32 + n) * 32 + j];
+                            const float cc = fmaf(gf, cst[c][i], gi * gg);
+                            cst[c][i] = cc;
+                            ccv[i] = cc;
+                            hmv[i] = go * tanh_acc(cc) * mk[i];      // the dropped h is the recurrent state (src/modules.py:356-357)
+                            const __half hh = __float2half_rn(hmv[i]);
+                            // what the next phase waits for: the fp16 operand rows
+                            if (role == 1) {
+                                a.S0h[((long long)slot_out * B + b) * K0 + P + u] = hh;      // recurrent slot of step t+1
+                                a.S1h[((long long)slot_in * B + b) * K1 + u] = hh;            // input slot of cell 1, step t
+                            } else {
+                                a.S1h[((long long)slot_out * B + b) * K1 + DH + u] = hh;
+                            }
+                        }
+                    }
+                    if (a.dbg && role == 1 && r == 0 && slice == 0 && tid == 128 && t < 256) a.dbg[t * 16 + 11] = gtime_ns();
+                    ++ncommit;
+                    cta_signal(ctr_self);
+                    DP_STAMP(r == 0 && slice == 0, t, role == 1 ? 8 : 13);
+                    // ---- history for backward: behind the hand-off ----
+                    float* Cst = role == 1 ? a.C0 : a.C1;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int n = warp * 4 + i, b = b0 + n;
+                        if (b < B) {
+                            Cst[((long long)slot_out * B + b) * H + u] = ccv[i];
+                            if (role == 1) {
+                                if (a.S0b) {
+                                    const __nv_bfloat16 hb = __float2bfloat16(hmv[i]);
+                                    a.S0b[((long long)slot_out * B + b) * K0 + P + u] = hb;
+                                    a.S1b[((long long)slot_in * B + b) * K1 + u] = hb;
+                                }
+                            } else if (a.S1b) {
+                                a.S1b[((long long)slot_out * B + b) * K1 + DH + u] = __float2bfloat16(hmv[i]);
+                            }
+                        }
+                    }
+                    if (a.training) {
+                        float* Gst = (role == 1 ? a.G0 : a.G1) + ((long long)(t % a.ghist) * B + b0 + 16 * hf) * 4 * H + q * H + u;
+#pragma unroll
+                        for (int n = 0; n < 16; ++n)
+                            if (16 * hf + n < rows) Gst[(long long)n * 4 * H] = xg[n];
+                    }
+                }
+                if (a.dbg && role == 1 && r == 0 && slice == 0 && tid == 128 && t < 256) a.dbg[t * 16 + 15] = gtime_ns();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (role && warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// dst[c][r] (fp16) = src[r][c]
+__global__ void __launch_bounds__(256) transpose_cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols) {
+    const long long n = (long long)rows * cols;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const int c = (int)(i / rows), r = (int)(i - (long long)c * rows);
+        dst[i] = __float2half_rn(src[(long long)r * cols + c]);
+    }
+}
+
+}  // namespace
+
+int las_transpose_cast_f16(const float* src, void* dst, int rows, int cols, void* stream) {
+    LAS_CHECK_ARG(src && dst && rows >= 1 && cols >= 1, "transpose_cast_f16: bad arguments");
+    const long long n = (long long)rows * cols;
+    const int grid = (int)((n + 255) / 256 < 148 * 4 ? (n + 255) / 256 : 148 * 4);
+    transpose_cast_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, rows, cols);
+    LAS_LAUNCH_CHECK();
+    return LAS_OK;
+}
+
+size_t las_dec_persist_ctr_words(int B) { return (size_t)3 * 32 * (size_t)((B + NBS - 1) / NBS) + 32; }
+
+static int persist_groups(int B, int DH, int DO, int num_sms) {
+    const int nsl = (B + NBS - 1) / NBS;
+    const int per = DH / 32 + DO / 32;
+    int ng = num_sms / per;
+    if (ng > nsl) ng = nsl;
+    return ng;
+}
+
+int las_dec_persist_fwd_supported(int B, int T, int P, int DH, int DO, int V, int heads, int init_force) {
+    const char* e = getenv("LAS_DEC_PERSIST");
+    if (e && atoi(e) == 0) return 0;
+    if (heads != 1 || init_force) return 0;
+    if (!(P == 64 || P == 128 || P == 256)) return 0;
+    if (DH % 32 || DO % 32 || DO > 256 || DO % (4 * (NT / (P / 4))) || V > 32 || V < 2) return 0;
+    const int K0 = P + DH, K1 = DH + DO;
+    if (K0 % 64 || K1 % 64 || K0 > 768 || K1 > 768) return 0;     // 128 x K fp16 = K/2 TMEM columns next to 128 accumulator columns
+    if (P % 16 || DH % 16) return 0;
+    const LasDeviceInfo* di = las_device_info();
+    if (!di || !di->coop_launch) return 0;
+    const int nsl = (B + NBS - 1) / NBS;
+    const int ng = persist_groups(B, DH, DO, di->num_sms);
+    if (ng < 1 || (nsl + ng - 1) / ng > MAX_CHAINS) return 0;
+    if (smem_layout(T, P, DH, DO).total > (uint32_t)di->max_smem_optin) return 0;
+    return 1;
+}
+
+static long long* g_dp_dbg = nullptr;
+extern "C" void las_dec_persist_set_debug(void* dev_buf) { g_dp_dbg = (long long*)dev_buf; }
+
+int las_dec_persist_fwd_launch(const LasDecPersistFwd* a0, cudaStream_t st) {
+    LasDecPersistFwd a = *a0;
+    a.dbg = g_dp_dbg;
+    const LasDeviceInfo* di = las_device_info();
+    a.nsl = (a.B + NBS - 1) / NBS;
+    a.ngroups = persist_groups(a.B, a.DH, a.DO, di->num_sms);
+    const size_t smem = smem_layout(a.T, a.P, a.DH, a.DO).total;
+    void* args[] = {(void*)&a};
+    const char* nae = getenv("LAS_DP_NA");                 // 1: K / V rows with ld.global.nc.L1::no_allocate (tuning switch)
+    const bool na = nae && atoi(nae) == 1;
+    void* fn = a.kv16 ? (na ? (void*)dec_persist_fwd_kernel<true, true> : (void*)dec_persist_fwd_kernel<true, false>)
+                      : (na ? (void*)dec_persist_fwd_kernel<false, true> : (void*)dec_persist_fwd_kernel<false, false>);
+    LAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAS_CUDA(cudaLaunchCooperativeKernel(fn, dim3(di->num_sms), dim3(NT), args, smem, st));
+    las_count_launch(1);
+    return LAS_OK;
+}

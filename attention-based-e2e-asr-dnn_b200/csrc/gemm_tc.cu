@@ -16,6 +16,7 @@
 //   MN-major operand tile 64k x mn   : mn/64 TMA boxes {64, 64, 1} of 8 KB; UMMA desc LBO = 8 KB, SBO = 1024 B,
 //                                      K-advance = 2048 B
 #include "las_common.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "las_b200.h"
 #include <cuda.h>
@@ -64,6 +65,7 @@ struct TcArgs {
     int splitk;       // >1: the K range of every output tile is split over `splitk` CTAs writing partials to Cpart
     float* Cpart;     // (splitk, R, ldp) partial sums
     long long ldp;
+    uint32_t fmt_clear;   // instruction-descriptor format bits to clear: bit 7 -> A is fp16, bit 10 -> B is fp16 (set = bf16)
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
         // ===== MMA issuer: the whole warp walks the loop (waits included) and ONE elected lane issues -- with `if (lane == 0)`
         // the branch is divergent, every tcgen05.mma gets wrapped in a divergence loop with R2UR moves (~65 cycles per issue,
         // more than a 128x64x16 UMMA takes); warp-uniform control flow keeps the descriptors in uniform registers =====
-        constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BN);
+        const uint32_t idesc = make_idesc(A_MN, B_MN, BN) & ~g.fmt_clear;     // kind::f16 takes fp16 / bf16 per operand
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t accphase = 0;
         for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += gridDim.x) {
@@ -584,6 +586,7 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
     TcArgs g{};
     g.C = d->C; g.bias1 = d->bias1; g.bias2 = d->bias2; g.c_bs = d->c_bs; g.ldc = d->ldc;
     g.N = d->N; g.accumulate = d->accumulate; g.lens = d->lens;
+    g.fmt_clear = (d->a_f16 ? (1u << 7) : 0u) | (d->b_f16 ? (1u << 10) : 0u);
     const double flops = d->prof_flops > 0 ? d->prof_flops : 2.0 * d->M * (double)d->N * d->K * d->a_batches * d->k_batches;
     LasProfScope prof(d->prof_tag == 1 ? (d->max_ctas > 0 ? LAS_PROF_GEMM_GATES_SIDE : LAS_PROF_GEMM_GATES) : LAS_PROF_GEMM_OTHER, stream, flops);
     // narrow N tiles when the 128x256 tiling would leave most SMs idle (decoder-step GEMMs: M = batch)
@@ -629,6 +632,7 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
 }
 
 // ---- fp32 -> bf16 cast with optional column padding: dst[r][c] = c < cols ? src[r*ld_src + c] : 0 ---------------------
+template <bool F16>
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, long long ld_src, long long inner, long long bs,
                                                         __nv_bfloat16* __restrict__ dst, long long ld_dst, long long rows, int cols,
                                                         int cols_pad) {
@@ -639,7 +643,8 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
         const float* srow = src + (inner > 0 ? (r / inner) * bs + (r % inner) * ld_src : r * ld_src);
         const float a = c < cols ? srow[c] : 0.f;
         const float b = c + 1 < cols ? srow[c + 1] : 0.f;
-        *reinterpret_cast<__nv_bfloat162*>(dst + r * ld_dst + c) = __floats2bfloat162_rn(a, b);
+        if (F16) *reinterpret_cast<__half2*>(dst + r * ld_dst + c) = __floats2half2_rn(a, b);
+        else *reinterpret_cast<__nv_bfloat162*>(dst + r * ld_dst + c) = __floats2bfloat162_rn(a, b);
     }
 }
 
@@ -652,7 +657,22 @@ extern "C" int las_cast_f32_to_bf16(const float* src, long long ld_src, long lon
     if (rc) return rc;
     long long total = rows * (long long)(cols_pad / 2);
     int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    cast_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, inner, bs, (__nv_bfloat16*)dst, ld_dst, rows, cols, cols_pad);
+    cast_bf16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, inner, bs, (__nv_bfloat16*)dst, ld_dst, rows, cols, cols_pad);
+    LAS_LAUNCH_CHECK();
+    return LAS_OK;
+}
+
+// same, IEEE half destination (decoder forward operands: |h| <= 1/(1-p), weights O(1) -- 10 mantissa bits instead of 7)
+extern "C" int las_cast_f32_to_f16(const float* src, long long ld_src, long long inner, long long bs, void* dst, long long ld_dst,
+                                   long long rows, int cols, int cols_pad, void* stream) {
+    LAS_CHECK_ARG(src && dst && rows >= 0 && cols >= 1 && cols_pad >= cols && cols_pad % 2 == 0 && ld_dst % 2 == 0,
+                  "cast_f16: bad arguments");
+    if (rows == 0) return LAS_OK;
+    int rc = las_set_device_of(dst);
+    if (rc) return rc;
+    long long total = rows * (long long)(cols_pad / 2);
+    int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    cast_bf16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, inner, bs, (__nv_bfloat16*)dst, ld_dst, rows, cols, cols_pad);
     LAS_LAUNCH_CHECK();
     return LAS_OK;
 }

@@ -44,6 +44,7 @@ class LasGemmTc(C.Structure):
         ('splitk', C.c_int),
         ('workspace', C.c_void_p),
         ('max_ctas', C.c_int),
+        ('a_f16', C.c_int), ('b_f16', C.c_int),
     ]
 
 
@@ -124,6 +125,7 @@ SIGNATURES = {
     'las_gemm_f32': (C.c_int, [C.POINTER(LasGemmF32), C.c_void_p]),
     'las_gemm_bf16_tc': (C.c_int, [C.POINTER(LasGemmTc), C.c_void_p]),
     'las_cast_f32_to_bf16': (C.c_int, [C.c_void_p, c_ll, c_ll, c_ll, C.c_void_p, c_ll, c_ll, C.c_int, C.c_int, C.c_void_p]),
+    'las_cast_f32_to_f16': (C.c_int, [C.c_void_p, c_ll, c_ll, c_ll, C.c_void_p, c_ll, c_ll, C.c_int, C.c_int, C.c_void_p]),
     'las_colsum_scratch_floats': (C.c_size_t, [C.c_int]),
     'las_colsum_f32': (C.c_int, [C.c_void_p, c_ll, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'las_lstm_rec_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
@@ -144,6 +146,7 @@ SIGNATURES = {
     'las_attn_step_bwd_f32': (C.c_int, [C.POINTER(LasAttnStep), C.c_void_p]),
     'las_lstm_cell_fwd_f32': (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p]),
     'las_lstm_cell_bwd_f32': (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
+    'las_speller_persistent': (C.c_int, [C.c_int] * 9),
     'las_speller_workspace_floats': (C.c_size_t, [C.POINTER(LasSpeller)]),
     'las_speller_workspace_ints': (C.c_size_t, [C.POINTER(LasSpeller)]),
     'las_speller_fwd_f32': (C.c_int, [C.POINTER(LasSpeller), C.c_void_p]),

@@ -55,8 +55,10 @@ def gemm_raw(A, B, Cout, M, N, K, *, am=(0, 0, 0), ak=(0, 1, 0), bk=(0, 1, 0), b
 def gemm_tc(A, B, Cout, M, N, K, *, a_batches=1, k_batches=1, a_s1, a_s2=0, b_s1, b_s2=0, c_bs=0, ldc, a_mn=False, b_mn=False,
             bias1=None, bias2=None, accumulate=False, lens=None, a_off=0, b_off=0, c_off=0, gate=True, flops=0.0, splitk=0,
             max_ctas=0):
-    """las_gemm_bf16_tc wrapper; A/B are bf16 tensors, Cout fp32; *_off are element offsets."""
+    """las_gemm_bf16_tc wrapper; A/B are bf16 (or fp16: the format is taken from the tensor's dtype) tensors, Cout fp32; *_off are
+    element offsets."""
     d = LasGemmTc()
+    d.a_f16, d.b_f16 = int(A.dtype == torch.float16), int(B.dtype == torch.float16)
     d.A = A.data_ptr() + 2 * a_off
     d.B = B.data_ptr() + 2 * b_off
     d.C = Cout.data_ptr() + 4 * c_off
@@ -751,16 +753,27 @@ class SpellerFunction(torch.autograd.Function):
         Bn, T, P = K.shape
         Vn = params[0].shape[0]
         use_tc = use_tensor_cores() and os.environ.get('LAS_DEC_TC', '1') == '1'
-        kv16 = bool(use_tc) and P % 4 == 0 and os.environ.get('LAS_KV_BF16', '0') == '1'   # measured slower than fp32 rows with 64-bit loads: off by default
+        # the persistent decoder-step kernel (one launch per loop) takes fp32 or fp16 K / V; the launch-per-stage loop fp32 or bf16
+        persist = bool(lib.las_speller_persistent(Bn, T, P, params[3].shape[1], params[7].shape[1], Vn, int(heads), int(bool(init_force)),
+                                                  int(bool(use_tc))))
+        if persist:
+            kv16 = 2 if os.environ.get('LAS_KV_F16', '0') == '1' else 0
+        else:
+            kv16 = 1 if (bool(use_tc) and P % 4 == 0 and os.environ.get('LAS_KV_BF16', '0') == '1') else 0   # measured slower than fp32 rows: off
         key = (dev.index, Bn, T, P, int(steps), int(heads), bool(training), bool(use_tc), kv16, bool(init_force), Vn,
                params[3].shape[1], params[7].shape[1], drop0 is not None)
         slot = _acquire_slot(key)
         # ---- stage the per-step inputs into the slot (device-to-device copies, a few tens of microseconds) ----
         if kv16:
-            # AMP mode option: K and V as bf16 (half the bytes per step); the energies and the context still accumulate in fp32
-            Kb = slot.buf('K', (Bn, T, P), torch.bfloat16, dev)
-            Vb = slot.buf('V', (Bn, T, P), torch.bfloat16, dev)
+            # AMP mode option: K and V as 16-bit rows (half the bytes per step); the energies and the context still accumulate in fp32
+            kdt = torch.float16 if kv16 == 2 else torch.bfloat16
+            Kb = slot.buf('K', (Bn, T, P), kdt, dev)
+            Vb = slot.buf('V', (Bn, T, P), kdt, dev)
             Kb.copy_(K); Vb.copy_(V)
+            if training and kv16 == 2:
+                # the backward loop's attention kernels read fp32 (or bf16) rows: keep an fp32 copy beside the fp16 one
+                slot.buf('K32', (Bn, T, P), torch.float32, dev).copy_(K)
+                slot.buf('V32', (Bn, T, P), torch.float32, dev).copy_(V)
         else:
             Kb = slot.buf('K', (Bn, T, P), torch.float32, dev)
             Vb = slot.buf('V', (Bn, T, P), torch.float32, dev)
@@ -808,6 +821,8 @@ class SpellerFunction(torch.autograd.Function):
         t = lease.slot.t
         K, V, enc_lens, dec_y, drop0, drop1, fws, iws = t['K'], t['V'], t['lens'], t.get('y'), t.get('drop0'), t.get('drop1'), t['fws'], t['iws']
         use_gold, steps, heads, sos_idx, pad_idx, use_tc, kv16, init_force = ctx.cfg
+        if kv16 == 2:
+            K, V, kv16 = t['K32'], t['V32'], 0
         s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, True, use_tc,
                                 init_force)
         s.kv_bf16 = int(kv16)

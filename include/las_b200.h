@@ -97,12 +97,17 @@ typedef struct {
     float* workspace;      /* split-K partial sums, >= splitk * M * round_up(N, 4) floats */
     int max_ctas;          /* > 0: launch at most this many (persistent) CTAs -- for a GEMM that runs on a second stream beside a
                             * recurrence kernel and should take only the SMs that kernel leaves free; 0: one CTA per SM */
+    int a_f16, b_f16;      /* != 0: that operand holds IEEE fp16 instead of bf16 (tcgen05 kind::f16 takes either, per operand):
+                            * the decoder's forward activations are fp16 (bounded range, 3 more mantissa bits), gradients stay bf16 */
 } LasGemmTc;
 int las_gemm_bf16_tc(const LasGemmTc* desc, void* stream);
 /* dst[r][c] (bf16, row stride ld_dst) = c < cols ? srcrow(r)[c] : 0, c < cols_pad; source row r starts at
  * (r / inner)*bs + (r % inner)*ld_src when inner > 0 (a (B,T,F) view with a batch stride), else at r*ld_src */
 int las_cast_f32_to_bf16(const float* src, long long ld_src, long long inner, long long bs, void* dst, long long ld_dst,
                          long long rows, int cols, int cols_pad, void* stream);
+/* same with an IEEE fp16 destination */
+int las_cast_f32_to_f16(const float* src, long long ld_src, long long inner, long long bs, void* dst, long long ld_dst,
+                        long long rows, int cols, int cols_pad, void* stream);
 
 /* column sums: out[n] (+)= sum_m X[m*ld + n], m < M, n < N.  Bias gradients (autograd of the bias adds in nn.LSTM /
  * nn.LSTMCell / nn.Linear). `scratch` needs las_colsum_scratch_floats(N) floats. */
@@ -231,7 +236,7 @@ typedef struct {
     int sos_idx, pad_idx;
     int training;                 /* 1: save history for backward */
     int use_tc;                   /* 1: decoder GEMMs as bf16 tcgen05 tiles (AMP mode); fwd and bwd must agree */
-    int kv_bf16;                  /* 1: K and V_ point to bf16 (B,T,P) memory */
+    int kv_bf16;                  /* 1: K and V_ point to bf16 (B,T,P) memory; 2: IEEE fp16 (persistent decoder-step kernel only) */
     int init_force;               /* 1: block-diagonal attention prior on every loop step (src/models.py:326-330,364-366) */
     /* parameters */
     const float* emb;             /* (V, E)  char_emb.weight == cls.weight */
@@ -253,6 +258,9 @@ typedef struct {
     float* fws; size_t fws_floats;
     int* iws; size_t iws_ints;
 } LasSpeller;
+/* 1 when las_speller_fwd_f32 runs this shape as ONE persistent decoder-step kernel (tensor-pipe mode, heads == 1, no init_force,
+ * dims that fit the TMEM-resident weight slices): K / V may then be fp32 (kv_bf16 = 0) or IEEE fp16 (kv_bf16 = 2), not bf16. */
+int las_speller_persistent(int B, int T, int P, int DH, int DO, int V, int heads, int init_force, int use_tc);
 size_t las_speller_workspace_floats(const LasSpeller* s);
 size_t las_speller_workspace_ints(const LasSpeller* s);
 int las_speller_fwd_f32(const LasSpeller* s, void* stream);
