@@ -586,6 +586,8 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
     TcArgs g{};
     g.C = d->C; g.bias1 = d->bias1; g.bias2 = d->bias2; g.c_bs = d->c_bs; g.ldc = d->ldc;
     g.N = d->N; g.accumulate = d->accumulate; g.lens = d->lens;
+    // measured on B200: a kind::f16 UMMA with one fp16 and one bf16 operand raises an illegal-instruction error, so both or neither
+    LAS_CHECK_ARG((d->a_f16 != 0) == (d->b_f16 != 0), "gemm_tc: both operands must have the same 16-bit format (fp16 x bf16 is not a legal tcgen05 kind::f16 pair)");
     g.fmt_clear = (d->a_f16 ? (1u << 7) : 0u) | (d->b_f16 ? (1u << 10) : 0u);
     const double flops = d->prof_flops > 0 ? d->prof_flops : 2.0 * d->M * (double)d->N * d->K * d->a_batches * d->k_batches;
     LasProfScope prof(d->prof_tag == 1 ? (d->max_ctas > 0 ? LAS_PROF_GEMM_GATES_SIDE : LAS_PROF_GEMM_GATES) : LAS_PROF_GEMM_OTHER, stream, flops);

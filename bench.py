@@ -2,7 +2,7 @@
 """bench.py -- LAS teacher-forced training throughput (BASELINE.json metric) on N B200s of one node.
 
     python bench.py --gpus 1 --steps K --warmup W                 # our arm (CUDA path through the public nn.Module API)
-    python bench.py --impl reference --gpus 1 --steps K --warmup W  # reference arm: the CPU port of the reference algorithm
+    python bench.py --impl reference --gpus 1 --steps K --warmup W  # reference arm: the unmodified reference on the host cores
     torchrun ... bench.py --gpus N ...                            # N > 1: one rank per GPU, NCCL gradient all-reduce
 
 A "step" = one pass of the hot path over one synthetic batch: Listener + Speller forward under teacher forcing, masked CE,
@@ -43,6 +43,8 @@ def parse():
     ap.add_argument('--config', default='best')
     ap.add_argument('--cpu-sample-batch', type=int, default=8, help='utterances of the CPU-baseline sample (about 10 s of CPU work per step at 8)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-dropout', action='store_true', help='run the model with every dropout at 0 (default: the yml values 0.3/0.3/0.35/0.3)')
+    ap.add_argument('--no-gpu-reference', action='store_true', help='skip timing the unmodified reference on the GPU (gpu_reference)')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help="bf16: the AMP path (gate GEMMs on the tensor pipe, like the reference's autocast runs); fp32: parity mode")
     ap.add_argument('--no-greedy', action='store_true', help='skip the greedy-decode leg (BASELINE configs[3]) reported under "greedy"')
@@ -166,13 +168,58 @@ def attn_step_replay_us(lib, B, T, P, dev, nrep=50):
     return out[0], out[1], 2.0 * B * T * P * 4
 
 
+def ref_runner(cmd_args, timeout=900):
+    """oracle/ref_runner.py in its own process (the reference's top-level package is called `src`, like the drop-in shim, so it
+    never shares a process with the product package).  Returns the JSON dict it prints, or None."""
+    staged = os.path.isdir(os.path.join(ROOT, 'oracle', '_ref', 'src')) or os.path.isdir('/root/reference/src')
+    if not staged:
+        return None
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT', 'PYTHONPATH')}
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', 'ref_runner.py')] + [str(a) for a in cmd_args], env=env,
+                             capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return None
+    for line in reversed(out.stdout.splitlines()):
+        if line.startswith('{'):
+            try:
+                return json.loads(line)
+            except ValueError:
+                continue
+    sys.stderr.write('ref_runner %s failed:\n%s\n' % (cmd_args, out.stderr[-1500:]))
+    return None
+
+
+def reference_cpu_step(cfg_name, B, T, L, steps=1, warmup=0):
+    """Seconds per train step of the UNMODIFIED reference on the host cores (all threads), or None when it is not staged."""
+    d = ref_runner(['bench', '--device', 'cpu', '--config', cfg_name, '--B', B, '--T', T, '--L', L, '--steps', steps, '--warmup', warmup])
+    return None if d is None else d['ms_per_step'] / 1e3
+
+
 def run_reference(args):
-    """Reference arm: the reference is pure Python (no compilable sources, nothing pip-installable: it ships no
-    setup.py / pyproject), and /root/reference does not exist on the GPU box, so this arm times the CPU port of its
-    algorithm (oracle/, pinned to the reference by tests/golden) on all host cores, on a bounded sample of the workload."""
+    """Reference arm: the UNMODIFIED reference (pure Python on PyTorch; staged by oracle/build_ref.sh into the git-ignored oracle/_ref so
+    that it travels to the GPU box) on all host cores, through its own nn.Module API and the trainer's step sequence
+    (oracle/ref_runner.py bench), on a bounded sample of the workload.  Falls back to the CPU port (oracle/las_oracle.py, pinned to the
+    reference by tests/golden) only when the staged copy is absent."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    per_utt = reference_cpu_step(args.config, 1, args.T, args.L)
+    if per_utt is not None:
+        # size the per-step sample so that the K timed steps take about two and a half minutes at most
+        B = int(max(1, min(args.cpu_sample_batch, 150.0 / (max(args.steps, 1) * max(per_utt, 1e-3)))))
+        d = ref_runner(['bench', '--device', 'cpu', '--config', args.config, '--B', B, '--T', args.T, '--L', args.L, '--steps', args.steps,
+                        '--warmup', min(args.warmup, 1)], timeout=1500)
+        if d is not None:
+            ms, val = d['ms_per_step'], d['utt_per_s']
+            sample = f'B={B} utterances of the same T={args.T}, L={args.L} workload per step (yml dropouts on)'
+            out = dict(impl='reference', metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                       ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                       config=dict(workload=f'{args.config} base-LAS teacher-forced train step, T={args.T}, L={args.L}', sample=sample),
+                       cpu_baseline=dict(value=val, unit=UNIT, cores=d['threads'], kind='reference', sample=sample),
+                       e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+            print(json.dumps(out), flush=True)
+            return
     for i in range(max(1, min(args.warmup, 1))):
         oracle_cpu_step(args.config, 1, max(args.T // 8, 8), max(args.L // 8, 2))      # warm the allocator / thread pool
     # size the per-step sample so that the K timed steps take about two and a half minutes at most: probe one utterance first
@@ -218,7 +265,10 @@ def main():
     _lib.check(lib.las_init(local), 'las_init')
 
     B, T, L = args.batch, args.T, args.L
-    cfg = gu.get_config(args.config)
+    # the config the bench names runs with ITS dropouts (config/sample-attention.yml:50-65: 0.3 / 0.3 / 0.35, decoder 0.3): mask
+    # draws, masked-output writes and the decoder's per-step mask staging are inside the timed region
+    drop = {} if args.no_dropout else dict(init_dropout=0.3, mid_dropout=0.3, final_dropout=0.35, dec_lstm_dropout=0.3)
+    cfg = gu.get_config(args.config, **drop)
     torch.manual_seed(11785)                     # the reference's seed (config/sample-attention.yml:11), same on every rank
     model = ListenAttendSpell(**cfg).to(dev).train()
     if world > 1:
@@ -415,20 +465,43 @@ def main():
                bwd_us_per_timestep=1e3 * prof['rec_bwd']['ms_per_step'] / max(T_total, 1), timesteps_per_step=T_total)
 
     cpu = None
+    gpu_ref = None
     if world == 1 and not args.no_cpu_baseline:
         Bs = args.cpu_sample_batch
-        sec = oracle_cpu_step(args.config, Bs, T, L)
-        cpu = dict(value=Bs / sec, unit=UNIT, cores=os.cpu_count(), kind='port',
-                   sample=f'one fwd+bwd+AdamW step of the CPU port (oracle/) at B={Bs}, T={T}, L={L}: {sec:.1f} s')
+        sec = reference_cpu_step(args.config, Bs, T, L)
+        if sec is not None:
+            cpu = dict(value=Bs / sec, unit=UNIT, cores=os.cpu_count(), kind='reference',
+                       sample=f'one train step (fwd+bwd+clip+AdamW, yml dropouts) of the unmodified reference (oracle/_ref) at B={Bs}, T={T}, L={L}: {sec:.1f} s')
+        else:
+            sec = oracle_cpu_step(args.config, Bs, T, L)
+            cpu = dict(value=Bs / sec, unit=UNIT, cores=os.cpu_count(), kind='port',
+                       sample=f'one fwd+bwd+AdamW step of the CPU port (oracle/) at B={Bs}, T={T}, L={L}: {sec:.1f} s')
+    if world == 1 and not args.no_gpu_reference:
+        # secondary comparator (SURVEY 2.1 / BASELINE.md section 3): the unmodified reference on this B200 through torch's cuDNN / cuBLAS
+        # path, same batch and lengths -- fp32, and under autocast as its trainer runs it (src/train.py:130, fp16 by default)
+        torch.cuda.empty_cache()
+        gpu_ref = {}
+        for amp in ('none', 'bf16', 'fp16'):
+            d = ref_runner(['bench', '--device', 'cuda', '--amp', amp, '--config', args.config, '--B', B, '--T', T, '--L', L, '--steps', 3,
+                            '--warmup', 2], timeout=600)
+            if d is not None:
+                gpu_ref['fp32' if amp == 'none' else amp + '_autocast'] = dict(ms_per_step=d['ms_per_step'], value=d['utt_per_s'], unit=UNIT)
+        if not gpu_ref:
+            gpu_ref = None
+        else:
+            gpu_ref['note'] = ('unmodified reference (oracle/_ref) on the same GPU: nn.LSTM -> cuDNN, per-step Python decoder loop with a '
+                               'blocking .cpu() per step (src/models.py:377), GradScaler + clip_grad_norm_ + torch AdamW; 3 timed steps')
 
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, min_warm), ms_per_step=ms_step,
                higher_is_better=True, scaling='weak', vs_baseline=None, dtype=('bf16' if args.precision == 'bf16' else 'f32'), data='synthetic',
                config=dict(workload=f'{args.config} base-LAS teacher-forced train step (fwd+bwd+unscale/clip/AdamW-amsgrad), '
-                                    f'batch {B}/GPU, T={T}, L={L}, tf_rate=1.0', global_batch=B * world, parallelism=f'dp{world}',
+                                    f'batch {B}/GPU, T={T}, L={L}, tf_rate=1.0, dropouts ' + ('off' if args.no_dropout else '0.3/0.3/0.35 + decoder 0.3 (yml)'),
+                           global_batch=B * world, parallelism=f'dp{world}',
                            l2_policy='inputs+activations per step (>2.5 GB) exceed the 126 MB L2; no explicit flush'),
                clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e),
                gpu_launches=int(launches), roofline=roofline, attn_roofline=attn_roofline, recurrence=rec,
-               kernel_ms_per_step={k: round(v['ms_per_step'], 3) for k, v in prof.items()}, greedy=greedy, cpu_baseline=cpu)
+               kernel_ms_per_step={k: round(v['ms_per_step'], 3) for k, v in prof.items()}, greedy=greedy, cpu_baseline=cpu,
+               gpu_reference=gpu_ref)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

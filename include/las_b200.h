@@ -97,8 +97,8 @@ typedef struct {
     float* workspace;      /* split-K partial sums, >= splitk * M * round_up(N, 4) floats */
     int max_ctas;          /* > 0: launch at most this many (persistent) CTAs -- for a GEMM that runs on a second stream beside a
                             * recurrence kernel and should take only the SMs that kernel leaves free; 0: one CTA per SM */
-    int a_f16, b_f16;      /* != 0: that operand holds IEEE fp16 instead of bf16 (tcgen05 kind::f16 takes either, per operand):
-                            * the decoder's forward activations are fp16 (bounded range, 3 more mantissa bits), gradients stay bf16 */
+    int a_f16, b_f16;      /* != 0: the operands hold IEEE fp16 instead of bf16 (bounded-range forward activations: 3 more mantissa
+                            * bits); both flags must agree -- a mixed fp16 x bf16 pair is an illegal instruction on B200 */
 } LasGemmTc;
 int las_gemm_bf16_tc(const LasGemmTc* desc, void* stream);
 /* dst[r][c] (bf16, row stride ld_dst) = c < cols ? srcrow(r)[c] : 0, c < cols_pad; source row r starts at

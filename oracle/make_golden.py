@@ -27,20 +27,10 @@ sys.path.insert(0, ROOT)
 from oracle import golden_util as gu            # noqa: E402
 from oracle.las_oracle import levenshtein, idx_to_str, VOCAB   # noqa: E402
 
-REF = os.environ.get('LAS_REFERENCE', '/root/reference')
 OUT = os.path.join(ROOT, 'tests', 'golden')
 
 
-def import_reference():
-    for name in ['torchsummaryX', 'Levenshtein', 'seaborn', 'matplotlib', 'matplotlib.pyplot']:
-        if name not in sys.modules:
-            sys.modules[name] = types.ModuleType(name)
-    sys.modules['torchsummaryX'].summary = lambda *a, **k: None
-    sys.modules['Levenshtein'].distance = levenshtein
-    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
-    sys.path.insert(0, REF)
-    import src.models as ref_models              # the reference, unmodified
-    return ref_models
+from oracle.ref_harness import Recorder, Replayer, import_reference, to_double as _to_double   # noqa: E402
 
 
 def build_ref_model(ref_models, cfg, sd_np):
@@ -54,86 +44,6 @@ def build_ref_model(ref_models, cfg, sd_np):
         assert tuple(v.shape) == tuple(sd_np[k].shape), (k, v.shape, sd_np[k].shape)
     model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd_np.items()})
     assert model.spell.cls.weight is model.spell.char_emb.weight
-    return model
-
-
-class Recorder:
-    """Records, in call order, every tf coin (torch.rand(1)), locked-dropout mask (Tensor.bernoulli_ followed by
-    an in-place div_) and nn.Dropout mask (F.dropout) the reference draws."""
-
-    def __init__(self):
-        self.coins, self.locked, self.drops = [], [], []
-
-    def __enter__(self):
-        import torch.nn.functional as F
-        self._rand, self._bern, self._drop = torch.rand, torch.Tensor.bernoulli_, F.dropout
-        rec = self
-
-        def rand(*a, **k):
-            r = rec._rand(*a, **k)
-            if tuple(r.shape) == (1,):
-                rec.coins.append(float(r.item()))
-            return r
-
-        def bern(self_, *a, **k):
-            r = rec._bern(self_, *a, **k)
-            rec.locked.append(r)            # later div_'ed in place -> holds the final mask
-            return r
-
-        def drop(x, p=0.5, training=True, inplace=False):
-            if not training or p == 0.0:
-                return x
-            m = rec._drop(torch.ones_like(x), p, True, False)
-            rec.drops.append(m)
-            return x * m
-
-        torch.rand, torch.Tensor.bernoulli_, F.dropout = rand, bern, drop
-        return self
-
-    def __exit__(self, *exc):
-        import torch.nn.functional as F
-        torch.rand, torch.Tensor.bernoulli_, F.dropout = self._rand, self._bern, self._drop
-
-
-class Replayer:
-    """Feeds a Recorder's coins / masks back, in the same call order, to a second run of the reference (the float64 re-run that
-    measures the reference's own fp32 round-off at the large shapes)."""
-
-    def __init__(self, rec, dtype):
-        self.coins, self.locked, self.drops, self.dtype = list(rec.coins), [m.clone() for m in rec.locked], list(rec.drops), dtype
-
-    def __enter__(self):
-        import torch.nn.functional as F
-        self._rand, self._bern, self._drop = torch.rand, torch.Tensor.bernoulli_, F.dropout
-        rep = self
-
-        def rand(*a, **k):
-            if a == (1,):
-                return torch.tensor([rep.coins.pop(0)], dtype=torch.float64)
-            return rep._rand(*a, **k)
-
-        def bern(self_, *a, **k):
-            # the recorded tensor is the FINAL mask (0 or 1/keep after the in-place div_): put the 0/1 pattern back
-            m = rep.locked.pop(0)
-            return self_.copy_((m != 0).to(self_.dtype))
-
-        def drop(x, p=0.5, training=True, inplace=False):
-            if not training or p == 0.0:
-                return x
-            return x * rep.drops.pop(0).to(x.dtype)
-
-        torch.rand, torch.Tensor.bernoulli_, F.dropout = rand, bern, drop
-        return self
-
-    def __exit__(self, *exc):
-        import torch.nn.functional as F
-        torch.rand, torch.Tensor.bernoulli_, F.dropout = self._rand, self._bern, self._drop
-
-
-def _to_double(model):
-    model = model.double()
-    # init_hiddens is a plain Python list of Parameters (src/models.py:275-281): nn.Module.double() does not see it
-    model.spell.init_hiddens = [tuple(t.double() for t in h) for h in model.spell.init_hiddens]
     return model
 
 
@@ -185,7 +95,7 @@ def train_case(ref_models, name, cfg_name, seed, B, T, L, lx, ly, tf_rate, dropo
     if with_fp64:
         # the same reference module in float64 with the recorded masks replayed: what the fp32 reference itself is off by
         m64 = _to_double(build_ref_model(ref_models, cfg, sd)).train()
-        with Replayer(rec, torch.float64):
+        with Replayer.from_recorder(rec):
             l64, _ = m64(torch.from_numpy(x).double(), torch.from_numpy(lx), torch.from_numpy(y), tf_rate, init_force)
         loss64 = (crit(l64.view(-1, V), torch.from_numpy(y).view(-1)) * ymask).sum() / ymask.sum()
         loss64.backward()
