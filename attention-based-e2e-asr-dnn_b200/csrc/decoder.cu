@@ -546,7 +546,9 @@ unsigned las_prof_mask_get();
 // pointer-stable pooled buffer set (las_b200/functional.py::_SpellerSlot) -- and replayed with a single cudaGraphLaunch.  Any capture failure falls back to direct
 // enqueueing.  LAS_DEC_GRAPH=0 disables it; it is also bypassed while per-kernel profiling of inner kernels is on.
 namespace {
-struct GraphEntry { unsigned long long key; std::vector<cudaGraphExec_t> execs; unsigned long long stamp; int nlaunch; };
+// `ident` = the bytes the key was hashed from (descriptor with the host coin pointer cleared, the coin flags, the gradient
+// pointers): compared on a hash hit, so a 64-bit collision can never replay a graph recorded for other pointers / coins
+struct GraphEntry { unsigned long long key; std::vector<cudaGraphExec_t> execs; unsigned long long stamp; int nlaunch; std::vector<unsigned char> ident; };
 
 // Lets an enqueue function cut the sequence it is recording into several graphs at decoder-step boundaries.  Launching a
 // 2000-node graph costs the host ~1 ms before the GPU sees its first node; when the host has no lead (the backward loop
@@ -584,7 +586,12 @@ struct GraphSeg {
 inline int seg_step(GraphSeg* seg, int i) { return (seg && seg->cut_at(i)) ? seg->cut() : LAS_OK; }
 std::vector<GraphEntry> g_graphs;
 unsigned long long g_graph_clock = 0;
-long long g_graph_captures = 0, g_graph_replays = 0;
+long long g_graph_captures = 0, g_graph_replays = 0, g_graph_direct = 0;
+// A capture + instantiate of a ~2000-node graph costs milliseconds; it only pays off when the same (shape, pointers, coin pattern)
+// comes back.  Ragged batches or tf_rate < 1 (a new coin pattern per batch) never repeat: after a short streak of misses, keys that
+// were not seen recently are enqueued directly instead of being captured.
+unsigned long long g_recent_keys[16];
+int g_recent_n = 0, g_miss_streak = 0;
 cudaStream_t g_capture_stream[64];
 bool g_capture_stream_ok[64];
 
@@ -605,7 +612,7 @@ std::mutex g_graph_mu;
 // remember (LRU of 8) and launch.  Any capture failure (and LAS_DEC_GRAPH=0, or per-kernel profiling of the inner kernels)
 // falls back to enqueueing directly on `st`.
 template <class F>
-int run_graph_cached(unsigned long long key, cudaStream_t st, F enqueue) {
+int run_graph_cached(unsigned long long key, const std::vector<unsigned char>& ident, cudaStream_t st, F enqueue) {
     const char* genv = getenv("LAS_DEC_GRAPH");
     const bool inner_prof = (las_prof_mask_get() & ((1u << LAS_PROF_GEMM_OTHER) | (1u << LAS_PROF_ATTN_FWD) | (1u << LAS_PROF_ATTN_BWD))) != 0;
     int dev = 0;
@@ -614,13 +621,22 @@ int run_graph_cached(unsigned long long key, cudaStream_t st, F enqueue) {
     key = fnv1a(&dev, sizeof(dev), key);
     std::lock_guard<std::mutex> lk(g_graph_mu);
     for (auto& e : g_graphs)
-        if (e.key == key) {
+        if (e.key == key && e.ident == ident) {
             e.stamp = ++g_graph_clock;
             ++g_graph_replays;
+            g_miss_streak = 0;
             for (auto x : e.execs) LAS_CUDA(cudaGraphLaunch(x, st));
             las_count_launch(e.nlaunch);          // the replay runs the same kernels the capture recorded
             return LAS_OK;
         }
+    {
+        bool seen = false;
+        for (int i = 0; i < g_recent_n; ++i) seen = seen || g_recent_keys[i] == key;
+        if (g_recent_n < 16) g_recent_keys[g_recent_n++] = key;
+        else { for (int i = 1; i < 16; ++i) g_recent_keys[i - 1] = g_recent_keys[i]; g_recent_keys[15] = key; }
+        ++g_miss_streak;
+        if (g_miss_streak > 3 && !seen) { ++g_graph_direct; return enqueue(st, (GraphSeg*)nullptr); }
+    }
     if (!g_capture_stream_ok[dev]) {
         if (cudaStreamCreateWithFlags(&g_capture_stream[dev], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return enqueue(st, (GraphSeg*)nullptr); }
         g_capture_stream_ok[dev] = true;
@@ -663,7 +679,7 @@ int run_graph_cached(unsigned long long key, cudaStream_t st, F enqueue) {
         for (auto x : g_graphs[lru].execs) cudaGraphExecDestroy(x);
         g_graphs.erase(g_graphs.begin() + lru);
     }
-    g_graphs.push_back({key, seg.execs, ++g_graph_clock, (int)(las_launch_count() - launches_before)});
+    g_graphs.push_back({key, seg.execs, ++g_graph_clock, (int)(las_launch_count() - launches_before), ident});
     ++g_graph_captures;
     for (auto x : seg.execs) LAS_CUDA(cudaGraphLaunch(x, st));
     return LAS_OK;
@@ -689,12 +705,13 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
     LasSpeller kd;
     memcpy(&kd, s, sizeof(LasSpeller));
     kd.use_gold_host = nullptr;
-    unsigned long long key = fnv1a(&kd, sizeof(LasSpeller), 1469598103934665603ULL);
-    if (s->use_gold_host) key = fnv1a(s->use_gold_host, (size_t)s->steps, key);
+    std::vector<unsigned char> ident((const unsigned char*)&kd, (const unsigned char*)&kd + sizeof(LasSpeller));
+    if (s->use_gold_host) ident.insert(ident.end(), s->use_gold_host, s->use_gold_host + s->steps);
+    const unsigned long long key = fnv1a(ident.data(), ident.size(), 1469598103934665603ULL);
     // persistent decoder-step kernel: one cooperative launch for the whole loop (plus a handful of weight-preparation kernels),
     // enqueued directly -- nothing to amortise with a graph, and no graph key that depends on the coin pattern
     if (L.persist) return speller_fwd_persist(s, L, st);
-    return run_graph_cached(key, st, [&](cudaStream_t q, GraphSeg* seg) { return speller_fwd_enqueue(s, L, q, seg); });
+    return run_graph_cached(key, ident, st, [&](cudaStream_t q, GraphSeg* seg) { return speller_fwd_enqueue(s, L, q, seg); });
 }
 
 namespace {
@@ -976,10 +993,11 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     LasSpeller kd;
     memcpy(&kd, s, sizeof(LasSpeller));
     kd.use_gold_host = nullptr;
-    unsigned long long key = fnv1a(&kd, sizeof(LasSpeller), 7809847782465536322ULL);
-    if (s->use_gold_host) key = fnv1a(s->use_gold_host, (size_t)s->steps, key);
-    key = fnv1a(g, sizeof(LasSpellerGrads), key);
-    return run_graph_cached(key, st, [&](cudaStream_t q, GraphSeg* seg) { return speller_bwd_enqueue(s, g, L, q, seg); });
+    std::vector<unsigned char> ident((const unsigned char*)&kd, (const unsigned char*)&kd + sizeof(LasSpeller));
+    if (s->use_gold_host) ident.insert(ident.end(), s->use_gold_host, s->use_gold_host + s->steps);
+    ident.insert(ident.end(), (const unsigned char*)g, (const unsigned char*)g + sizeof(LasSpellerGrads));
+    const unsigned long long key = fnv1a(ident.data(), ident.size(), 7809847782465536322ULL);
+    return run_graph_cached(key, ident, st, [&](cudaStream_t q, GraphSeg* seg) { return speller_bwd_enqueue(s, g, L, q, seg); });
 }
 
 namespace {

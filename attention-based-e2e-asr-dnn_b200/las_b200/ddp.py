@@ -16,10 +16,15 @@ Design:
     gradients that the backward overlap accumulates on its second stream report through `p._las_grad_ready` instead:
     the all-reduce is then issued from that stream, i.e. ordered behind the accumulation);
   * parameters that never receive a gradient (spell.attention.final_map.*) are excluded up front -- the
-    classic DDP "unused parameter" trap.
+    classic DDP "unused parameter" trap;
+  * gradient accumulation (the reference trainer's `accu_grad`, src/train.py:163-165): run every micro-batch but the last inside
+    `with reducer.no_sync():` -- the hooks then neither count nor launch, gradients just accumulate in the buckets -- and the last
+    one outside it, which arms the countdown again and reduces the accumulated sum once.  A hook that fires on an already reduced
+    bucket (a second backward without no_sync / zero_grad) raises instead of silently mixing reduced and local gradients.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
@@ -62,6 +67,7 @@ class BucketedGradReducer:
         self._handles: List[Optional[object]] = []
         self._bucket_of: Dict[int, int] = {}
         self._hooks = []
+        self._sync = True
         for bi, k in enumerate(self.bucket_names):
             ps = [p for _, p in groups[k]]
             n = sum(p.numel() for p in ps)
@@ -72,7 +78,8 @@ class BucketedGradReducer:
                 # gradients of this parameter may be accumulated in place outside autograd (functional.py, backward overlap); the code
                 # that does so calls p._las_grad_ready(p) afterwards -- on the stream the accumulation ran on -- in place of the hook
                 p._las_bucketed = True
-                p._las_grad_ready = self._make_hook(bi)
+                p._las_deferred = False
+                p._las_grad_ready = self._make_hook(bi, from_autograd=False)
                 off += p.numel()
                 self._bucket_of[id(p)] = bi
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
@@ -81,12 +88,36 @@ class BucketedGradReducer:
             self._pending.append(len(ps))
             self._handles.append(None)
 
-    def _make_hook(self, bi: int):
+    def _make_hook(self, bi: int, from_autograd: bool = True):
         def hook(param):
+            if from_autograd:
+                # torch calls the post-accumulate-grad hook even when the incoming gradient is None (verified on torch 2.11): a layer
+                # that took the backward-overlap route returned None for this parameter and will accumulate into p.grad LATER, on its
+                # second stream, then report through p._las_grad_ready.  Counting this early call would launch the bucket's all-reduce
+                # before the gradient exists (every rank would keep only its local gradient).
+                if getattr(param, '_las_deferred', False):
+                    return
+            else:
+                param._las_deferred = False
+            if not self._sync:               # inside no_sync(): accumulate locally, reduce with the last micro-batch
+                return
+            if self._pending[bi] <= 0:
+                raise RuntimeError('BucketedGradReducer: a gradient arrived for a bucket that was already reduced in this step; wrap '
+                                   'all but the last backward of an accumulation cycle in `with reducer.no_sync():` (or call '
+                                   'reducer.zero_grad() between steps)')
             self._pending[bi] -= 1
             if self._pending[bi] == 0:
                 self._launch(bi)
         return hook
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Gradient accumulation: backward passes inside this context add into the buckets without communicating."""
+        prev, self._sync = self._sync, False
+        try:
+            yield
+        finally:
+            self._sync = prev
 
     def _launch(self, bi: int):
         if self.world_size > 1 and self._handles[bi] is None:

@@ -509,6 +509,8 @@ class LSTMLayerFunction(torch.autograd.Function):
                     # event-deferred frees make the caching allocator's steady state depend on timing)
                     _overlap_state(dGb.device).keepalive.append((dGb, xb, hs, dG, dbp))
 
+                for w in wrefs:                            # the reducer's autograd hook must not count the None returned below
+                    w._las_deferred = True
                 ovl.pending.append(run)
                 return (dx, None, None, None, None, None, None, *([None] * (4 * ndir)))
             grads = _lstm_weight_grads(dGb, xb, hs_pad, dG, dbp, wdims)
@@ -691,21 +693,37 @@ def host_copy_lazy(t: torch.Tensor) -> torch.Tensor:
 
 
 class _SpellerSlot:
-    """One pointer-stable buffer set for a decoder loop of a given shape: the staged inputs (K, V, lengths, gold tokens,
-    dropout masks), the workspaces and the raw outputs.  las_speller_fwd_f32 replays a CUDA graph keyed on the descriptor
-    (every pointer in it), so a steady training / decoding loop must present the SAME pointers every step -- PyTorch's
-    caching allocator does not promise that for per-step allocations, a slot does."""
-    __slots__ = ('t', 'busy')
+    """One pointer-stable buffer set for a decoder loop: the staged inputs (K, V, lengths, gold tokens, dropout masks), the
+    workspaces and the raw outputs.  The launch-per-stage loop of las_speller_fwd_f32 replays a CUDA graph keyed on the descriptor
+    (every pointer in it), so a steady training / decoding loop must present the SAME pointers every step -- PyTorch's caching
+    allocator does not promise that for per-step allocations, a slot does.
+
+    Buffers are flat, grow-only and shared by every shape that fits: a ragged-batch epoch (a new (T, steps) almost every batch, the
+    reference trainer's normal case) settles on ONE buffer set sized for its largest batch instead of one set per distinct shape."""
+    __slots__ = ('t', 'v', 'busy')
 
     def __init__(self):
-        self.t, self.busy = {}, False
+        self.t, self.v, self.busy = {}, {}, False
 
     def buf(self, name, shape, dtype, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
         b = self.t.get(name)
-        if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
-            b = torch.empty(shape, dtype=dtype, device=device)
+        if b is None or b.dtype != dtype or b.device != device or b.numel() < n:
+            cap = n if b is None or b.dtype != dtype or b.device != device else max(n, int(b.numel() * 1.25))
+            cap = max(1, (cap + 255) // 256 * 256)
+            # never an inference tensor: the reference evaluates under torch.inference_mode() (src/train.py:207) and decodes test data
+            # outside it (src/infer.py:56-62); a buffer born inside could not be written in place afterwards
+            with torch.inference_mode(False):
+                b = torch.empty(cap, dtype=dtype, device=device)
             self.t[name] = b
-        return b
+        view = b[:n].view(*shape)
+        self.v[name] = view
+        return view
+
+    def nbytes(self):
+        return sum(b.numel() * b.element_size() for b in self.t.values())
 
 
 class _SlotLease:
@@ -725,14 +743,20 @@ class _SlotLease:
         self.release()
 
 
-_SPELLER_POOL = {}
+_SPELLER_POOL = {}        # device index -> list of slots (one per concurrently live forward, plus at most _POOL_SPARE idle ones)
+_POOL_SPARE = 2
 
 
 def _acquire_slot(key):
+    """key = (device index, training): eval slots carry no history, so they are kept apart from the (much larger) training slots."""
     slots = _SPELLER_POOL.setdefault(key, [])
-    for sl in slots:
-        if not sl.busy:
-            return sl
+    idle = [sl for sl in slots if not sl.busy]
+    if idle:
+        # largest first: the slot most likely to fit without growing; surplus idle slots (left by a burst of live forwards) are dropped
+        idle.sort(key=lambda sl: -sl.nbytes())
+        for extra in idle[_POOL_SPARE:]:
+            slots.remove(extra)
+        return idle[0]
     sl = _SpellerSlot()
     slots.append(sl)
     return sl
@@ -741,6 +765,11 @@ def _acquire_slot(key):
 def speller_pool_clear():
     """Drop every pooled decoder buffer set (they are retained between steps on purpose)."""
     _SPELLER_POOL.clear()
+
+
+def speller_pool_bytes():
+    """Device bytes currently held by the pooled decoder buffer sets."""
+    return sum(sl.nbytes() for slots in _SPELLER_POOL.values() for sl in slots)
 
 
 class SpellerFunction(torch.autograd.Function):
@@ -760,9 +789,7 @@ class SpellerFunction(torch.autograd.Function):
             kv16 = 2 if os.environ.get('LAS_KV_F16', '0') == '1' else 0
         else:
             kv16 = 1 if (bool(use_tc) and P % 4 == 0 and os.environ.get('LAS_KV_BF16', '0') == '1') else 0   # measured slower than fp32 rows: off
-        key = (dev.index, Bn, T, P, int(steps), int(heads), bool(training), bool(use_tc), kv16, bool(init_force), Vn,
-               params[3].shape[1], params[7].shape[1], drop0 is not None)
-        slot = _acquire_slot(key)
+        slot = _acquire_slot((dev.index, bool(training)))
         # ---- stage the per-step inputs into the slot (device-to-device copies, a few tens of microseconds) ----
         if kv16:
             # AMP mode option: K and V as 16-bit rows (half the bytes per step); the energies and the context still accumulate in fp32
@@ -806,6 +833,9 @@ class SpellerFunction(torch.autograd.Function):
         logits, att0, chars = logits_b.clone(), att0_b.clone(), chars_b.clone()      # the caller owns its outputs
         if training:
             ctx.lease = _SlotLease(slot)
+            ctx.views = dict(slot.v)
+            if drop0 is None:
+                ctx.views.pop('drop0', None); ctx.views.pop('drop1', None)
             ctx.save_for_backward(*params)
             ctx.cfg = (use_gold, steps, heads, sos_idx, pad_idx, use_tc, kv16, init_force)
         ctx.mark_non_differentiable(att0, chars)
@@ -818,7 +848,7 @@ class SpellerFunction(torch.autograd.Function):
         lease = ctx.lease
         if lease.slot is None:
             raise RuntimeError('speller backward called twice: the decoder history buffers were already released')
-        t = lease.slot.t
+        t = ctx.views                     # this forward's views into the slot's buffers
         K, V, enc_lens, dec_y, drop0, drop1, fws, iws = t['K'], t['V'], t['lens'], t.get('y'), t.get('drop0'), t.get('drop1'), t['fws'], t['iws']
         use_gold, steps, heads, sos_idx, pad_idx, use_tc, kv16, init_force = ctx.cfg
         if kv16 == 2:

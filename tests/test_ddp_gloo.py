@@ -51,12 +51,27 @@ class _ManualGradLinear(torch.autograd.Function):
         wp, bp = ctx.refs
         dx = dy @ w
         if getattr(wp, '_las_bucketed', False) and wp.grad is not None:
-            wp.grad.add_(dy.t() @ x)
-            bp.grad.add_(dy.sum(0))
-            for p in (wp, bp):
-                p._las_grad_ready(p)
+            # like LSTMLayerFunction.backward: mark the parameters as deferred (autograd will still call their post-accumulate hook
+            # with a None gradient), accumulate (here at once; in the product later, on the second stream), then report
+            wp._las_deferred = bp._las_deferred = True
+            ctx.deferred = (dy.t() @ x, dy.sum(0))
+            _DEFERRED.append((wp, bp, ctx.deferred))
             return dx, None, None, None
         return dx, dy.t() @ x, dy.sum(0), None
+
+
+_DEFERRED = []
+
+
+def _flush_deferred():
+    """Stands in for _BackwardOverlap.run_pending / _overlap_finish: the queued weight gradients are accumulated AFTER the autograd
+    hooks of their parameters have already fired with None."""
+    for wp, bp, (gw, gb) in _DEFERRED:
+        wp.grad.add_(gw)
+        bp.grad.add_(gb)
+        for p in (wp, bp):
+            p._las_grad_ready(p)
+    _DEFERRED.clear()
 
 
 class ToyManual(Toy):
@@ -69,6 +84,68 @@ class ToyManual(Toy):
 
 def _free_port():
     s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker_accumulate(rank, world, port, q):
+    """accu_grad = 2 (src/train.py:163-165): two micro-batches per optimizer step; the first inside no_sync()."""
+    from las_b200.ddp import BucketedGradReducer
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = ToyManual()
+    red = BucketedGradReducer(list(model.named_parameters()), world_size=world)
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(16, 5, generator=g)
+    Y = torch.randn(16, 3, generator=g)
+    xs, ys = X[rank * 8:(rank + 1) * 8], Y[rank * 8:(rank + 1) * 8]
+    ok = True
+    for it in range(2):
+        red.zero_grad()
+        with red.no_sync():
+            ((model(xs[:4]) - ys[:4]) ** 2).sum().backward()
+            _flush_deferred()
+            ok = ok and all(h is None for h in red._handles)                 # nothing was communicated
+        ((model(xs[4:]) - ys[4:]) ** 2).sum().backward()
+        _flush_deferred()
+        red.finish()
+    # a further backward without no_sync / zero_grad must raise instead of mixing reduced and local gradients
+    try:
+        ((model(xs[:4]) - ys[:4]) ** 2).sum().backward()
+        raised = False
+    except RuntimeError as e:
+        raised = 'already reduced' in str(e)
+    _DEFERRED.clear()
+    if rank == 0:
+        q.put((bool(ok), bool(raised)))
+    dist.destroy_process_group()
+
+
+def _worker_accumulate_values(rank, world, port, q):
+    from las_b200.ddp import BucketedGradReducer
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = ToyManual()
+    red = BucketedGradReducer(list(model.named_parameters()), world_size=world)
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(16, 5, generator=g)
+    Y = torch.randn(16, 3, generator=g)
+    xs, ys = X[rank * 8:(rank + 1) * 8], Y[rank * 8:(rank + 1) * 8]
+    for it in range(2):
+        red.zero_grad()
+        with red.no_sync():
+            ((model(xs[:4]) - ys[:4]) ** 2).sum().backward()
+            _flush_deferred()
+        ((model(xs[4:]) - ys[4:]) ** 2).sum().backward()
+        _flush_deferred()
+        red.finish()
+    grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    if rank == 0:
+        ref = Toy()
+        ref.load_state_dict(model.state_dict())
+        ((ref(X) - Y) ** 2).sum().backward()
+        q.put(all(torch.allclose(grads[k], p.grad, atol=1e-5) for k, p in ref.named_parameters() if p.grad is not None))
+    dist.destroy_process_group()
 
 
 def _worker(rank, world, port, q, manual=False):
@@ -88,7 +165,10 @@ def _worker(rank, world, port, q, manual=False):
         red.zero_grad()
         loss = ((model(xs) - ys) ** 2).sum()
         loss.backward()
-        if manual:                           # the pyramid buckets were launched by the ready callbacks, before finish()
+        if manual:
+            # the None-gradient hook calls must NOT have launched the pyramid buckets: their gradients do not exist yet
+            assert all(red._handles[red.bucket_names.index(k)] is None for k in ('pyramid.1', 'pyramid.0'))
+            _flush_deferred()                # ... now they do, and the ready callbacks launch them, before finish()
             assert all(red._handles[red.bucket_names.index(k)] is not None for k in ('pyramid.1', 'pyramid.0'))
         red.finish()
     grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
@@ -117,3 +197,26 @@ def test_bucketed_allreduce_matches_single_process(manual):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def _run2(target):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return q.get(timeout=5)
+
+
+def test_gradient_accumulation_with_no_sync_matches_single_process():
+    """Two micro-batches per step (the reference trainer's accu_grad): gradients equal one backward over the concatenated batch of
+    both ranks; the first micro-batch communicates nothing."""
+    assert _run2(_worker_accumulate_values) is True
+
+
+def test_second_backward_without_no_sync_raises():
+    assert _run2(_worker_accumulate) == (True, True)
