@@ -29,10 +29,15 @@ __global__ void __launch_bounds__(256) masked_ce_kernel(const float* __restrict_
         for (int v = lane; v < V; v += 32) sum += expf(lr[v] - mx);
         sum = warp_sum(sum);
         const float lse = logf(sum) + mx;
-        if (on && tgt >= 0 && tgt < V) nll = lse - lr[tgt];
+        // a non-masked target outside [0, V): nn.CrossEntropyLoss raises (host-side check, src/train.py:131-136); a sync-free kernel
+        // cannot, so the loss, the perplexity and this row's gradient become NaN -- loud (GradScaler skips the step, the trainer's
+        // printed loss is nan) instead of a silently wrong gradient
+        const bool bad = on && (tgt < 0 || tgt >= V);
+        if (on) nll = bad ? __int_as_float(0x7fc00000) : lse - lr[tgt];
         if (dlogits) {
             float* dr = dlogits + row * V;
-            for (int v = lane; v < V; v += 32) dr[v] = on ? (expf(lr[v] - lse) - (v == tgt ? 1.f : 0.f)) * inv_denom : 0.f;
+            for (int v = lane; v < V; v += 32)
+                dr[v] = bad ? __int_as_float(0x7fc00000) : (on ? (expf(lr[v] - lse) - (v == tgt ? 1.f : 0.f)) * inv_denom : 0.f);
         }
     }
     if (lane == 0) red[w] = nll;

@@ -28,20 +28,45 @@ class FusedAdamW(torch.optim.Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)
         super().__init__(params, defaults)
         self._status = None
+        self._pending = None          # (pinned host copy of [found_inf, norm], event, params that stepped) of the previous fused step
 
-    def _init_state(self, p):
+    def _init_state(self, p, amsgrad=True):
         st = self.state[p]
         if len(st) == 0:
             st['step'] = torch.tensor(0.0, dtype=torch.float32)      # same key set as torch.optim.AdamW
             st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
             st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            if True:
-                st['max_exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        if amsgrad and 'max_exp_avg_sq' not in st:                  # like torch.optim.AdamW: only with amsgrad
+            st['max_exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
         return st
+
+    def _reconcile(self):
+        """GradScaler.step skips the whole optimizer step on a non-finite gradient, so the step counters must not advance.  The
+        kernel knows (status[0]); the host learns it one call later from a pinned copy whose event has long fired by then (a whole
+        forward + backward was enqueued in between), and rolls the counters of the skipped step back -- exact bias correction
+        without a host sync in the step that is being timed."""
+        if self._pending is None:
+            return
+        host, ev, stepped = self._pending
+        self._pending = None
+        ev.synchronize()
+        if float(host[0]) != 0.0:
+            for p in stepped:
+                self.state[p]['step'] -= 1
+
+    def state_dict(self):
+        self._reconcile()
+        return super().state_dict()
 
     @torch.no_grad()
     def _run(self, inv_scale: float, max_norm: float):
         lib = _lib.load()
+        self._reconcile()
+        if max_norm > 0 and sum(1 for g in self.param_groups if any(p.grad is not None for p in g['params'])) > 1:
+            # clip_grad_norm_(model.parameters()) is ONE norm over every parameter; the kernel computes it per call
+            raise RuntimeError('FusedAdamW.step_fused clips by the global norm of ONE parameter group (the reference trainer builds one, '
+                               'src/train.py:71-77); put the parameters in a single group, or clip yourself and call step()')
+        stepped = []
         for group in self.param_groups:
             ps = [p for p in group['params'] if p.grad is not None]
             if not ps:
@@ -55,10 +80,11 @@ class FusedAdamW(torch.optim.Optimizer):
             for i, p in enumerate(ps):
                 if p.dtype != torch.float32 or not p.is_contiguous():
                     raise RuntimeError('FusedAdamW needs contiguous fp32 parameters')
-                st = self._init_state(p)
-                # NOTE: like torch, the step counter advances before the update; when a non-finite gradient makes the
-                # kernel skip, the caller rolls it back (see step_fused)
+                st = self._init_state(p, bool(group['amsgrad']))
+                # like torch, the step counter advances before the update; when a non-finite gradient makes the kernel skip, it
+                # is rolled back (see _reconcile / step_fused)
                 st['step'] += 1
+                stepped.append(p)
                 step = float(st['step'])
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 if g.dtype != torch.float32:
@@ -66,7 +92,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 p._las_g = g          # keep alive until the kernels ran
                 t = tab[i]
                 t.p, t.g, t.m, t.v = p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr()
-                t.vmax = st['max_exp_avg_sq'].data_ptr()
+                t.vmax = st['max_exp_avg_sq'].data_ptr() if group['amsgrad'] else 0
                 t.numel = p.numel()
                 t.step_size = group['lr'] / (1.0 - beta1 ** step)
                 t.bias_c2_sqrt = math.sqrt(1.0 - beta2 ** step)
@@ -86,6 +112,12 @@ class FusedAdamW(torch.optim.Optimizer):
                                               scratch.data_ptr(), status.data_ptr(), stream_ptr()), 'adamw_amsgrad_fused')
             self._status = status
             self._keep = (tab_t, ck_t, scratch)
+        if self._status is not None and stepped:
+            host = torch.empty(2, dtype=torch.float32, pin_memory=True)
+            host.copy_(self._status, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(stepped[0].device))
+            self._pending = (host, ev, stepped)
         return self._status
 
     @torch.no_grad()
@@ -99,14 +131,10 @@ class FusedAdamW(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step_fused(self, inv_scale: float = 1.0, max_norm: float = 5.0, sync_skip: bool = False):
-        """unscale + clip + AdamW in one go.  Returns the device tensor [found_inf, grad_norm].  With sync_skip=True the
-        host reads found_inf and rolls the step counters back on a skipped step (exact GradScaler semantics; costs a
-        sync).  Without it the counters keep advancing on skipped steps (only the bias correction of later steps is
-        affected, by one step)."""
+        """unscale + clip + AdamW in one go.  Returns the device tensor [found_inf, grad_norm].  A step skipped for a non-finite
+        gradient does not advance the step counters (GradScaler.step semantics): with sync_skip=True the host reads found_inf now
+        (one sync); without it the roll-back happens at the start of the next call / at state_dict() from a pinned copy (no sync)."""
         status = self._run(inv_scale, max_norm)
-        if sync_skip and status is not None and bool(status[0].item() != 0):
-            for group in self.param_groups:
-                for p in group['params']:
-                    if p.grad is not None and p in self.state:
-                        self.state[p]['step'] -= 1
+        if sync_skip:
+            self._reconcile()
         return status
