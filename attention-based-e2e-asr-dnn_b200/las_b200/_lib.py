@@ -146,6 +146,7 @@ SIGNATURES = {
     'las_attn_step_bwd_f32': (C.c_int, [C.POINTER(LasAttnStep), C.c_void_p]),
     'las_lstm_cell_fwd_f32': (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p]),
     'las_lstm_cell_bwd_f32': (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
+    'las_transcript_cut_i32': (C.c_int, [C.c_void_p, c_ll, c_ll, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'las_speller_persistent': (C.c_int, [C.c_int] * 9),
     'las_speller_workspace_floats': (C.c_size_t, [C.POINTER(LasSpeller)]),
     'las_speller_workspace_ints': (C.c_size_t, [C.POINTER(LasSpeller)]),

@@ -318,6 +318,13 @@ int las_adamw_amsgrad_fused(const LasAdamTensor* table, int n_tensors, const Las
                             double beta1, double beta2, float eps, double weight_decay, float inv_scale, float max_norm,
                             int amsgrad, float* scratch, float* status, void* stream);
 
+/* ---- device-side transcript cut -------------------------------------------------------------------
+ * Replaces the per-utterance host loop idx_to_str(pred_logits[b].argmax(-1), VOCAB, SOS_IDX, EOS_IDX) of src/infer.py:19-32,66
+ * (and src/train.py:405-419): chars[t*ld_step + b*ld_b] (the greedy argmax, int32, device) -> out[b][0..lens[b]) = the token ids
+ * with every <sos> dropped, cut before the first <eos>; out is (B, steps) bytes, lens (B) int32. */
+int las_transcript_cut_i32(const int* chars, long long ld_step, long long ld_b, int B, int steps, int sos_idx, int eos_idx,
+                           unsigned char* out, int* lens, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
