@@ -42,10 +42,10 @@ def greedy_transcripts(chars_or_logits: torch.Tensor, vocab: Sequence[str], sos_
     else:
         toks, lens = transcript_cut(chars_or_logits, sos_idx, eos_idx, time_major=True)
     B, steps = toks.shape
-    host = torch.empty(B * steps + 4 * B, dtype=torch.uint8, pin_memory=True)          # tokens and lengths in ONE copy
-    packed = torch.cat([toks.reshape(-1), lens.view(torch.uint8)])
+    host = torch.empty(4 * B + B * steps, dtype=torch.uint8, pin_memory=True)          # lengths and tokens in ONE copy
+    packed = torch.cat([lens.view(torch.uint8), toks.reshape(-1)])
     host.copy_(packed, non_blocking=True)
     torch.cuda.current_stream(toks.device).synchronize()
-    lens_h = host[B * steps:].view(torch.int32).tolist()
-    rows = host[:B * steps].view(B, steps).numpy()
+    lens_h = host[:4 * B].view(torch.int32).tolist()
+    rows = host[4 * B:].view(B, steps).numpy()
     return [''.join(vocab[int(t)] for t in rows[b, :lens_h[b]]) for b in range(B)]

@@ -130,6 +130,10 @@ def test_cross_attention_module_vs_oracle(heads, use_prior):
         if po['a.' + k].grad is None:
             assert prm.grad is None, k                     # final_map is never used
             continue
+        if k == 'key_map.bias':
+            # mathematically zero (a constant added to every energy of a row cancels in the softmax): both sides hold round-off only
+            assert float(prm.grad.abs().max()) < 1e-5 * gmax and float(po['a.' + k].grad.abs().max()) < 1e-5 * gmax
+            continue
         assert rel_err(prm.grad.cpu().numpy(), po['a.' + k].grad.numpy(), 1e-3 * gmax) < TOL, k
 
 
