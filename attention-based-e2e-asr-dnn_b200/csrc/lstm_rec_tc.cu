@@ -650,6 +650,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
                 const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
                 lenr[c][i] = (sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
             }
+        // locked-dropout mask of this thread's (row, unit) pairs: constant over time -> registers (a load per timestep sat on the
+        // critical path of every step: 2.49 -> 3.05 us per timestep with the yml's dropouts on)
+        float mreg[CHAINS][8];
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
+                mreg[c][i] = (a.mask && sg + c * a.bsg < a.nslices && b < a.B) ? a.mask[(long long)b * F + dir * H + u] : 1.f;
+            }
         for (int c = 0; c < CHAINS; ++c) {
             const int slice = sg + c * a.bsg;
             if (slice >= a.nslices) continue;
@@ -757,7 +767,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
                         if (a.hs16) a.hs16[so] = __float2bfloat16(hh[i]);
                         a.cs_pad[so] = cc[i];
                         if (a.out || a.out16) {
-                            const float m = a.mask ? a.mask[(long long)b * F + dir * H + u] : 1.f;
+                            const float m = mreg[c][i];
                             const long long oo = ((long long)b * T + t) * F + dir * H + u;
                             if (a.out) a.out[oo] = hh[i] * m;
                             if (a.out16) a.out16[oo] = __float2bfloat16(hh[i] * m);
