@@ -77,14 +77,17 @@ def _worker(rank, world, port, q, accumulate):
         fwd_bwd(ref_model, xc, lxc, yc, torch.full((world * Bl,), L, dtype=torch.int64))
         torch.cuda.synchronize()
         worst = ('', 0.0)
+        errs = []
         gmax = max(float(p.grad.abs().max()) for p in ref_model.parameters() if p.grad is not None)
         for n, p in ref_model.named_parameters():
             if p.grad is None:
                 continue
             ref = p.grad.detach().float().cpu().numpy()
             e = float(np.abs(got[n] * scale - ref).max() / max(float(np.abs(ref).max()), 1e-3 * gmax))
+            errs.append((e, n))
             if e > worst[1]:
                 worst = (n, e)
+        print('largest errors:', sorted(errs, reverse=True)[:6], flush=True)
         q.put(worst)
     dist.barrier()
     dist.destroy_process_group()
