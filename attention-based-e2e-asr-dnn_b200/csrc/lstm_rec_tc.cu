@@ -165,10 +165,7 @@ __host__ __device__ inline int rec_pieces(int KB) { return (KB % 2 == 0) ? 2 : 1
 
 constexpr int FWD_NACC = 4;          // independent TMEM accumulators per chain in the forward recurrence (one per k sub-step)
 
-// CLUSTER: the H/32 CTAs of a (direction, batch slice) group are ONE thread-block cluster and meet on the hardware cluster
-// barrier once per timestep (arrive.release after the h_t stores, wait.acquire before the TMA of the next step) instead of the
-// release/acquire counter in global memory: one fence + barrier hop instead of release fence -> counter -> poll.
-template <bool WTMEM, bool CLUSTER>
+template <bool WTMEM>
 __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW,
                                                                      const __grid_constant__ CUtensorMap tmH, const RecTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -246,14 +243,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                         tma_load_2d(w_sm + kb * 16384 + g * 4096, &tmW, wbar, kb * 64, dir * 4 * H + g * H + r * UNITS);
             }
             for (int s = 1; s < T; ++s) {
-                if (CLUSTER) {          // step s-1 of every chain has been published by the whole group
-                    cluster_arrive_release();
-                    cluster_wait_acquire();
-                }
                 for (int c = 0; c < a.chains; ++c) {
                     const int slice = sg + c * a.bsg;
                     if (slice >= a.nslices) continue;
-                    if (!CLUSTER) {
+                    {
                         const unsigned* ctr = a.ctr + dir * a.nslices + slice;
                         const unsigned target = (unsigned)(H / UNITS) * (unsigned)s;
                         while (ld_acquire_gpu(ctr) < target) { }
@@ -269,14 +262,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     REC_STAMP(1);
                 }
             }
-        } else if (CLUSTER) {
-            for (int s = 1; s < T; ++s) { cluster_arrive_release(); cluster_wait_acquire(); }     // every thread of the cluster takes part
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp walks the loop (waits included), one elected lane issues =====
         if (!WTMEM) mbar_wait(wbar, 0);
         for (int s = 1; s < T; ++s) {
-            if (CLUSTER) { cluster_arrive_release(); cluster_wait_acquire(); }
             for (int c = 0; c < a.chains; ++c) {
                 const int slice = sg + c * a.bsg;
                 if (slice >= a.nslices) continue;
@@ -309,10 +299,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                 if (lane == 0) REC_STAMP(3);
             }
         }
-    } else if (warp < 4) {
-        if (CLUSTER)
-            for (int s = 1; s < T; ++s) { cluster_arrive_release(); cluster_wait_acquire(); }
-    } else {
+    } else if (warp >= 4) {
         // ===== epilogue: one warp per gate =====
         const int q = warp & 3, j = lane;          // gate q, unit r*32 + j
         const int te = (warp - 4) * 32 + lane;     // 0..127
@@ -343,7 +330,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
         }
         for (int s = 0; s < T; ++s) {
             const int t = (dir == 0) ? s : (T - 1 - s);
-            if (CLUSTER && s > 0) cluster_wait_acquire();             // pairs with this thread's arrive at the end of step s-1
 #pragma unroll
             for (int c = 0; c < MAX_CHAINS; ++c) {
                 const int slice = sg + c * a.bsg;
@@ -397,20 +383,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     a.hbuf[((long long)(dir * 2 + (s & 1)) * a.Bpad + b) * H + u] = __float2bfloat16(hh[i]);
                 }
                 // publish step s of this chain FIRST (the release only has the 8 bf16 stores per thread in front of it) ...
-                if (CLUSTER) {
-                    // `ex` is reused by the next chain / step: keep the four warps together, then (last chain) arrive on the cluster barrier
-                    named_bar_sync(1, 128);
-                    if (te == 0) REC_STAMP(8);
-                    bool last = true;
-#pragma unroll
-                    for (int c2 = c + 1; c2 < MAX_CHAINS; ++c2)
-                        if (c2 < a.chains && sg + c2 * a.bsg < a.nslices) last = false;
-                    if (last && s + 1 < T) cluster_arrive_release();
-                } else {
-                    named_bar_sync(1, 128);
-                    if (te == 0) REC_STAMP(8);
-                    if (te == 0 && s + 1 < T) red_release_gpu_add(a.ctr + dir * a.nslices + slice, 1u);
-                }
+                named_bar_sync(1, 128);
+                if (te == 0) REC_STAMP(8);
+                if (te == 0 && s + 1 < T) red_release_gpu_add(a.ctr + dir * a.nslices + slice, 1u);
                 if (te == 0) REC_STAMP(9);
                 // ... then write what only backward / the next layer read; these stores overlap the wait for the next step
                 if (a.save) {
@@ -789,336 +764,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
     }
 }
 
-// =====================================================================================================================
-// "LL" exchange variant of the forward recurrence (the default).
-// The step-to-step exchange of h_t between the H/32 CTAs of a (direction, batch slice) group is the serial bottleneck of
-// the recurrence.  With a release/acquire counter it costs four dependent L2 round trips per step (writer: stores ->
-// release fence; reader: counter poll -> proxy fence -> TMA load); measured 4200 of the 8000 cycles of a step.
-// Here every 8-byte word of the exchange buffer carries its own validity tag -- {2 x bf16 of h_t, step number} -- the way
-// NCCL's LL protocol does: an 8-byte store is single-copy atomic, so a reader that sees the tag sees the data.  Writers
-// just store (no fence, no barrier, no counter); four loader warps poll the words themselves, strip the tags and lay the
-// 32 x H tile out in shared memory in the UMMA K-major SWIZZLE_128B layout, k-block by k-block, each k-block handed to
-// the MMA thread through its own mbarrier so the tensor pipe starts on the first 64 columns while the rest still arrive.
-// =====================================================================================================================
-constexpr int NLOAD = 96;                  // exchange loader threads: warps 0, 2, 3 (warp 1 issues the MMAs)
-constexpr int NTHREADS_LL = 256;
-constexpr int NACC = 4;                    // independent TMEM accumulators per chain (see the MMA issuer)
-
-// two tagged words per load; each 64-bit half is one scalar access (single-copy atomic): x = data0, y = tag0, z = data1, w = tag1
-__device__ __forceinline__ uint4 ld_ll16(const unsigned long long* p) {
-    unsigned long long w0, w1;
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
-    return make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
-}
-__device__ __forceinline__ void st_ll8(unsigned long long* p, uint32_t data, uint32_t tag) {
-    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)data;
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// four tagged words (32 bytes, one L2 sector) per load
-struct Ll32 { uint32_t d0, t0, d1, t1, d2, t2, d3, t3; };
-__device__ __forceinline__ Ll32 ld_ll32(const unsigned long long* p) {
-    unsigned long long w0, w1, w2, w3;
-    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(p) : "memory");
-    Ll32 r;
-    r.d0 = (uint32_t)w0; r.t0 = (uint32_t)(w0 >> 32); r.d1 = (uint32_t)w1; r.t1 = (uint32_t)(w1 >> 32);
-    r.d2 = (uint32_t)w2; r.t2 = (uint32_t)(w2 >> 32); r.d3 = (uint32_t)w3; r.t3 = (uint32_t)(w3 >> 32);
-    return r;
-}
-__device__ __forceinline__ unsigned long long ld_ll8(const unsigned long long* p) {
-    unsigned long long w;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-    return w;
-}
-
-// One 32 x H tile: tagged words (row stride ldw words; word k of a row = units 2k, 2k+1) -> shared memory, UMMA K-major
-// SWIZZLE_128B, k-block-major ([kb][32 rows][128 B]).  96 loader threads (warps 0, 2, 3), lt = 0..95: 16-byte output chunk
-// cc = lt & 7 (= one 32-byte sector of tagged words) of rows n0 = lt >> 3, n0 + 12 and (n0 < 8 only) n0 + 24, for every k-block.
-//   * waiting costs almost no L2 traffic: 16 lanes of warp 0 poll ONE sentinel word per source CTA (its last row, last unit
-//     pair); when all 16 carry the step's tag the three warps meet on a named barrier and issue the real loads.  (Polling with
-//     the real loads from 96 CTAs x 96 threads saturated the L2 and every latency with it -- measured.)  The sentinel is a
-//     hint, not a guarantee: every word is still validated by its own tag and re-loaded until valid.
-//   * the whole tile (KB x 3 sector loads per thread) is in flight at once;
-//   * ONE generic->async proxy fence per thread, after its last load has landed (a proxy fence with global loads in flight
-//     waits for them), then one arrive on `tile_bar`.
-template <int KB>
-__device__ __forceinline__ void ll_load_tile(const unsigned long long* __restrict__ tile, int ldw, uint32_t smem_tile, uint32_t tile_bar,
-                                             uint32_t tag, int lt, uint32_t reuse_bar, uint32_t reuse_parity, bool reuse_wait,
-                                             long long* dbg) {
-    const int cc = lt & 7, n0 = lt >> 3;
-    const bool third = n0 < 8;
-    if (lt < 32) {
-        // sentinel of source CTA r = lane (r < 2*KB): row 31, last word of its 16-word span
-        const unsigned long long* sp = tile + 31LL * ldw + ((lt < 2 * KB ? lt : 0) * 16 + 15);
-        for (;;) {
-            const bool ok = (uint32_t)(ld_ll8(sp) >> 32) == tag;
-            if (__all_sync(0xffffffffu, ok)) break;
-            __nanosleep(20);
-        }
-    }
-    if (dbg) dbg[0] = clock64();
-    named_bar_sync(2, NLOAD);
-    const unsigned long long* p[3];
-    uint32_t so[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const int n = (j == 2 && !third) ? n0 : n0 + 12 * j;         // inactive third task aliases the first (never stored)
-        p[j] = tile + (long long)n * ldw + cc * 4;
-        so[j] = smem_tile + n * 128 + ((cc ^ (n & 7)) << 4);
-    }
-    Ll32 buf[KB][3];
-#pragma unroll
-    for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) buf[kb][j] = ld_ll32(p[j] + kb * 32);
-    // fast peers can publish this step while OUR tensor pipe still reads the previous tile: wait for the previous step's MMAs
-    if (reuse_wait) mbar_wait(reuse_bar, reuse_parity);
-#pragma unroll
-    for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            Ll32& v = buf[kb][j];
-            while (v.t0 != tag || v.t1 != tag || v.t2 != tag || v.t3 != tag) v = ld_ll32(p[j] + kb * 32);
-            if (j < 2 || third)
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(so[j] + kb * 4096), "r"(v.d0), "r"(v.d1), "r"(v.d2), "r"(v.d3) : "memory");
-        }
-    }
-    if (dbg) dbg[11] = clock64();
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_arrive(tile_bar);
-}
-
-struct RecLlArgs {
-    float* gates; const int* lens; const float* mask; float* out; float* hs_pad; float* cs_pad;
-    unsigned long long* ll;   // (ndir, 2, Bpad, H/2) tagged words
-    int B, T, H, ndir, nslices, Bpad, chains, bsg, save;
-    long long* dbg;
-};
-
-constexpr int MAX_KB = 8;      // H <= 512 (W_hh slice of 128 x H bf16 must fit in shared memory anyway)
-
-template <int KB, int CHAINS>
-__global__ void __launch_bounds__(NTHREADS_LL, 1) lstm_rec_fwd_ll_kernel(const __grid_constant__ CUtensorMap tmW, const RecLlArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    const int H = a.H, T = a.T;
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t w_sm = base;                                   // KB x [128 rows x 128 B]
-    const uint32_t h_sm = w_sm + KB * 16384;                      // chains x KB x [32 rows x 128 B]
-    const uint32_t ex_off = (h_sm - smem_u32(smem_raw)) + CHAINS * KB * 4096;
-    float* ex = reinterpret_cast<float*>(smem_raw + ex_off);      // [4][32][32] gate exchange
-    const uint32_t bar_base = smem_u32(smem_raw) + ex_off + 4 * 32 * 32 * 4;
-    auto tile_bar = [&](int c) { return bar_base + 8u * c; };
-    auto tfull_bar = [&](int c) { return bar_base + 8u * (MAX_CHAINS + c); };
-    const uint32_t wbar = bar_base + 8u * (2 * MAX_CHAINS);
-    const uint32_t tmem_slot = wbar + 8u;
-    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-    const int r = blockIdx.x, sg = blockIdx.y, dir = blockIdx.z;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int F = a.ndir * H;
-    const long long brow = (long long)(T + 2) * F;
-    const int ldw = H / 2;
-    constexpr int NA = KB < NACC ? KB : NACC;                     // accumulators actually used
-    constexpr uint32_t TMEM_COLS = MAX_CHAINS * NACC * NB_SLICE;  // 256
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-        for (int c = 0; c < MAX_CHAINS; ++c) {
-            mbar_init(tile_bar(c), NLOAD);
-            mbar_init(tfull_bar(c), 1);
-        }
-        mbar_init(wbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_ptr;
-
-    if (warp == 1) {
-        if (lane == 0) {
-            // resident W_hh slice, once
-            mbar_arrive_expect_tx(wbar, (uint32_t)KB * 16384u);
-            for (int kb = 0; kb < KB; ++kb)
-                for (int g = 0; g < 4; ++g)
-                    tma_load_2d(w_sm + kb * 16384 + g * 4096, &tmW, wbar, kb * 64, dir * 4 * H + g * H + r * UNITS);
-        }
-        __syncwarp();
-        // ===== MMA issuer: the whole warp walks the loop, one elected lane issues.  Consecutive UMMAs into ONE accumulator
-        // serialise on it, so the K loop round-robins over NACC independent accumulators that the epilogue adds up. =====
-        mbar_wait(wbar, 0);
-        for (int s = 1; s < T; ++s) {
-            for (int c = 0; c < CHAINS; ++c) {
-                const int slice = sg + c * a.bsg;
-                if (slice >= a.nslices) continue;
-                mbar_wait(tile_bar(c), (uint32_t)((s - 1) & 1));
-                if (lane == 0) REC_STAMP(2);
-                tc_fence_after();
-                if (elect_one()) {
-#pragma unroll
-                    for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int acc = (kb * 4 + k) % NA;
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((c * NACC + acc) * NB_SLICE);
-                            const uint64_t bd = make_desc_k(h_sm + (c * KB + kb) * 4096 + k * 32);
-                            const uint64_t ad = make_desc_k(w_sm + kb * 16384 + k * 32);
-                            umma_bf16(d_tmem, ad, bd, IDESC, (kb * 4 + k) >= NA ? 1u : 0u);
-                        }
-                    }
-                    umma_commit(tfull_bar(c));
-                }
-                __syncwarp();
-                if (lane == 0) REC_STAMP(3);
-            }
-        }
-    } else if (warp < 4) {
-        // ===== exchange loaders (warps 0, 2, 3): poll the group's tagged h_{s-1} words, strip the tags, build the B operand =====
-        const int lt = (warp == 0 ? 0 : warp - 1) * 32 + lane;
-        for (int s = 1; s < T; ++s) {
-            for (int c = 0; c < CHAINS; ++c) {
-                const int slice = sg + c * a.bsg;
-                if (slice >= a.nslices) continue;
-                const unsigned long long* tile = a.ll + ((long long)(dir * 2 + ((s - 1) & 1)) * a.Bpad + slice * NB_SLICE) * ldw;
-                ll_load_tile<KB>(tile, ldw, h_sm + c * KB * 4096, tile_bar(c), (uint32_t)s, lt, tfull_bar(c), (uint32_t)(s & 1), s > 1,
-                                 (a.dbg && lt == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && s < 256) ? a.dbg + s * 16 : nullptr);
-                if (lt == 0) REC_STAMP(1);
-            }
-        }
-    } else {
-        // ===== epilogue (warps 4-7): one warp per gate =====
-        const int q = warp & 3, j = lane;          // gate q, unit r*32 + j
-        const int te = (warp - 4) * 32 + lane;     // 0..127
-        const int u = r * UNITS + j;
-        float cst[CHAINS][8];
-        int lenr[CHAINS][8];
-#pragma unroll
-        for (int c = 0; c < CHAINS; ++c)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                cst[c][i] = 0.f;
-                const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
-                lenr[c][i] = (sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
-            }
-        for (int c = 0; c < CHAINS; ++c) {
-            const int slice = sg + c * a.bsg;
-            if (slice >= a.nslices) continue;
-            for (int i = 0; i < 8; ++i) {
-                const int b = slice * NB_SLICE + q * 8 + i;
-                if (b < a.B) {
-                    const long long o0 = (long long)b * brow + dir * H + u, o1 = o0 + (long long)(T + 1) * F;
-                    a.hs_pad[o0] = 0.f; a.cs_pad[o0] = 0.f; a.hs_pad[o1] = 0.f; a.cs_pad[o1] = 0.f;
-                }
-            }
-        }
-        const bool odd = (j & 1) != 0;
-        for (int s = 0; s < T; ++s) {
-            const int t = (dir == 0) ? s : (T - 1 - s);
-#pragma unroll
-            for (int c = 0; c < CHAINS; ++c) {
-                const int slice = sg + c * a.bsg;
-                if (slice >= a.nslices) continue;
-                const int b0 = slice * NB_SLICE;
-                // input projection for (gate q, unit j) of the 32 batch rows: coalesced 128 B per row, issued before the wait
-                float xg[32];
-                float* gbase = a.gates + ((long long)t * a.ndir + dir) * 4 * H + q * H + u;
-                const long long gstride = (long long)T * a.ndir * 4 * H;
-#pragma unroll
-                for (int n = 0; n < 32; ++n) xg[n] = (b0 + n < a.B) ? gbase[(long long)(b0 + n) * gstride] : 0.f;
-                if (te == 0) REC_STAMP(4);
-                if (s > 0) {
-                    mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
-                    if (te == 0) REC_STAMP(5);
-                    tc_fence_after();
-#pragma unroll
-                    for (int acc = 0; acc < NA; ++acc) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c * NACC + acc) * NB_SLICE), v);
-#pragma unroll
-                        for (int n = 0; n < 32; ++n) xg[n] += __uint_as_float(v[n]);
-                    }
-                    if (te == 0) REC_STAMP(6);
-                }
-#pragma unroll
-                for (int n = 0; n < 32; ++n) {
-                    const float act = (q == 2) ? tanh_fast(xg[n]) : sigmoid_fast(xg[n]);
-                    ex[(q * 32 + n) * 32 + j] = act;
-                    xg[n] = act;                                   // kept for the deferred save below
-                }
-                tc_fence_before();
-                named_bar_sync(1, 128);
-                if (te == 0) REC_STAMP(7);
-                // cell update: thread (q, j) owns unit j for batch rows n = q*8 + i
-                float hh[8], cc[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int n = q * 8 + i;
-                    const float gi = ex[(0 * 32 + n) * 32 + j], gf = ex[(1 * 32 + n) * 32 + j];
-                    const float gg = ex[(2 * 32 + n) * 32 + j], go = ex[(3 * 32 + n) * 32 + j];
-                    const bool valid = t < lenr[c][i];
-                    cc[i] = 0.f; hh[i] = 0.f;
-                    if (valid) {
-                        cc[i] = fmaf(gf, cst[c][i], gi * gg);
-                        hh[i] = go * tanh_fast(cc[i]);
-                    }
-                    cst[c][i] = cc[i];
-                }
-                // publish h_t: tagged 8-byte words {units (2k, 2k+1), step}; even lanes carry rows 0-3 of this warp's 8, odd
-                // lanes rows 4-7.  Nothing else: no fence, no barrier, no counter -- the peers' loaders poll the words themselves.
-                if (s + 1 < T) {
-                    float oth[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) oth[i] = __shfl_xor_sync(0xffffffffu, hh[i], 1);
-                    unsigned long long* wbase = a.ll + ((long long)(dir * 2 + (s & 1)) * a.Bpad + b0 + q * 8 + (odd ? 4 : 0)) * ldw + (u >> 1);
-#pragma unroll
-                    for (int ii = 0; ii < 4; ++ii) {
-                        const float own = odd ? hh[4 + ii] : hh[ii], ot = odd ? oth[4 + ii] : oth[ii];
-                        st_ll8(wbase + (long long)ii * ldw, odd ? pack_bf16x2(ot, own) : pack_bf16x2(own, ot), (uint32_t)(s + 1));
-                    }
-                }
-                if (te == 0) REC_STAMP(9);
-                // `ex` is rewritten by this chain's next step only after every peer -- hence every warp of this CTA -- has
-                // published, i.e. has read it; with several chains per CTA the next chain reuses it right away
-                if (CHAINS > 1) named_bar_sync(1, 128);
-                // ... then what only backward / the next layer read; these stores overlap the wait for the next step
-                if (a.save) {
-#pragma unroll
-                    for (int n = 0; n < 32; ++n)
-                        if (b0 + n < a.B) gbase[(long long)(b0 + n) * gstride] = xg[n];
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int b = b0 + q * 8 + i;
-                    if (b < a.B) {
-                        const long long so = (long long)b * brow + (long long)(t + 1) * F + dir * H + u;
-                        a.hs_pad[so] = hh[i];
-                        a.cs_pad[so] = cc[i];
-                        if (a.out) {
-                            const float m = a.mask ? a.mask[(long long)b * F + dir * H + u] : 1.f;
-                            a.out[((long long)b * T + t) * F + dir * H + u] = hh[i] * m;
-                        }
-                    }
-                }
-                if (te == 0) REC_STAMP(10);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1236,45 +881,6 @@ static int rec_fwd_tc_impl(float* gates, const void* w_hh_bf16, const int* lens,
             return LAS_OK;
         }
     }
-    {
-        const char* e = getenv("LAS_REC_LL");
-        const int KBh = H / 64;
-        if ((e && atoi(e) != 0) && hs_pad && !out16 && !hs16 && (KBh == 1 || KBh == 2 || KBh == 4 || KBh == 8) && (p.chains == 1 || (e && atoi(e) == 2))) {
-            RecLlArgs la{};
-            la.gates = gates; la.lens = lens; la.mask = drop_mask; la.out = out; la.hs_pad = hs_pad; la.cs_pad = cs_pad;
-            la.ll = (unsigned long long*)((char*)ws + 1024);
-            la.B = B; la.T = T; la.H = H; la.ndir = ndir; la.nslices = p.nslices; la.Bpad = p.Bpad; la.chains = p.chains; la.bsg = p.bsg;
-            la.save = save_gates; la.dbg = g_rec_dbg;
-            const int KB = H / 64;
-            const size_t smem = 1024 + (size_t)KB * 16384 + (size_t)p.chains * KB * 4096 + 4 * 32 * 32 * 4 +
-                                8 * (MAX_CHAINS * MAX_KB + MAX_CHAINS + 2) + 64;
-            LAS_CHECK_ARG(smem <= (size_t)las_device_info()->max_smem_optin, "lstm_rec_fwd_tc: needs %zu B of shared memory", smem);
-            CUtensorMap tmW;
-            rc = make_map_2d(&tmW, w_hh_bf16, H, (long long)ndir * 4 * H, 64, 32);
-            if (rc) return rc;
-            void* kern = nullptr;
-            const int key = KB * 10 + p.chains;
-            switch (key) {
-                case 11: kern = (void*)lstm_rec_fwd_ll_kernel<1, 1>; break;
-                case 12: kern = (void*)lstm_rec_fwd_ll_kernel<1, 2>; break;
-                case 21: kern = (void*)lstm_rec_fwd_ll_kernel<2, 1>; break;
-                case 22: kern = (void*)lstm_rec_fwd_ll_kernel<2, 2>; break;
-                case 41: kern = (void*)lstm_rec_fwd_ll_kernel<4, 1>; break;
-                case 42: kern = (void*)lstm_rec_fwd_ll_kernel<4, 2>; break;
-                case 81: kern = (void*)lstm_rec_fwd_ll_kernel<8, 1>; break;
-                case 82: kern = (void*)lstm_rec_fwd_ll_kernel<8, 2>; break;
-                default: break;
-            }
-            LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            // tags are step numbers: clear the words of the previous launch
-            LAS_CUDA(cudaMemsetAsync(la.ll, 0, (size_t)ndir * 2 * p.Bpad * H * 4, st));
-            LasProfScope prof(LAS_PROF_REC_FWD, stream, (double)T);
-            void* args[] = {(void*)&tmW, (void*)&la};
-            LAS_CUDA(cudaLaunchCooperativeKernel(kern, dim3(p.rs, p.bsg, ndir), dim3(NTHREADS_LL), args, smem, st));
-            las_count_launch(1);
-            return LAS_OK;
-        }
-    }
     RecTcArgs a{};
     a.gates = gates; a.lens = lens; a.mask = drop_mask; a.out = out; a.hs_pad = hs_pad; a.cs_pad = cs_pad; a.out16 = out16; a.hs16 = hs16;
     a.ctr = (unsigned*)ws; a.hbuf = (__nv_bfloat16*)((char*)ws + 1024);
@@ -1332,35 +938,9 @@ static int rec_fwd_tc_impl(float* gates, const void* w_hh_bf16, const int* lens,
             cudaGetLastError();         // fall through to the global-memory exchange
         }
     }
-    // LAS_REC_CLUSTER=1: one thread-block cluster per (direction, batch slice) group (<= 16 CTAs: non-portable size, every B200
-    // GPC has >= 16 SMs) synchronised by the hardware cluster barrier instead of the counter.  Measured NOT faster: the
-    // arrive.release costs the same ~1000-cycle store fence as red.release and the barrier another ~1000 cycles to complete
-    // across 16 SMs (6416 vs 6389 cycles/step at B=96; 2x slower with two chains per CTA).  Off by default.
-    const char* ce = getenv("LAS_REC_CLUSTER");
-    bool use_cluster = (ce && atoi(ce) != 0) && p.rs <= 16;
     LAS_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
     LasProfScope prof(LAS_PROF_REC_FWD, stream, (double)T);
-    if (use_cluster) {
-        auto kc = a.w_tmem ? lstm_rec_fwd_tc_kernel<true, true> : lstm_rec_fwd_tc_kernel<false, true>;
-        cudaError_t e1 = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-        if (e1 == cudaSuccess && p.rs > 8) e1 = cudaFuncSetAttribute(kc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e1 == cudaSuccess) {
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(p.rs, p.bsg, ndir); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = p.smem; cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = p.rs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int nclusters = 0;
-            e1 = cudaOccupancyMaxActiveClusters(&nclusters, kc, &cfg);
-            // clusters are independent of one another (a group never waits for another group), so they need not all be co-resident
-            if (e1 == cudaSuccess && nclusters >= 1) e1 = cudaLaunchKernelEx(&cfg, kc, tmW, tmH, a);
-            else if (e1 == cudaSuccess) e1 = cudaErrorInvalidConfiguration;
-        }
-        if (e1 == cudaSuccess) { las_count_launch(1); return LAS_OK; }
-        cudaGetLastError();         // fall back to the counter-based cooperative launch
-    }
-    void* kern = a.w_tmem ? (void*)lstm_rec_fwd_tc_kernel<true, false> : (void*)lstm_rec_fwd_tc_kernel<false, false>;
+    void* kern = a.w_tmem ? (void*)lstm_rec_fwd_tc_kernel<true> : (void*)lstm_rec_fwd_tc_kernel<false>;
     LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     void* args[] = {(void*)&tmW, (void*)&tmH, (void*)&a};
     LAS_CUDA(cudaLaunchCooperativeKernel(kern, dim3(p.rs, p.bsg, ndir), dim3(NTHREADS), args, p.smem, st));

@@ -52,3 +52,28 @@ def make_inputs(seed: int, B: int, T: int, L: int, lx: List[int] = None, input_d
         x[b, lx[b]:] = 0.0
     y = rng.integers(1, 29, size=(B, L)).astype(np.int64)
     return x, lx, y
+
+
+# config/rewriter.yml:46-63 -- the char-to-char attention seq2seq LM of src/lmtrain.py (BASELINE.json configs[4])
+REWRITER_CONFIGS: Dict[str, dict] = {
+    'rw_yml': dict(vocab_size=30, emb_dim=256, enc_lstm_layers=2, enc_lstm_hid_dim=256, enc_dropouts=[0.3, 0.3], att_proj_dim=128,
+                   att_heads=4, att_dropout=0.2, dec_lstm_layers=2, dec_lstm_hid_dim=256, dec_lstm_out_dim=128, dec_lstm_dropout=0.3,
+                   CHR_PAD_IDX=29, CHR_MAX_STEPS=600, CHR_SOS_IDX=0),
+}
+
+
+def get_rewriter_config(name: str = 'rw_yml', **overrides) -> dict:
+    cfg = copy.deepcopy(REWRITER_CONFIGS[name])
+    cfg.update(overrides)
+    return cfg
+
+
+def make_token_inputs(seed: int, B: int, Tx: int, L: int, lx=None):
+    """Rewriter inputs: x tokens (B, Tx) in 1..28 padded with 29 past each length, lx, y tokens (B, L)."""
+    rng = np.random.default_rng(seed)
+    lx = np.asarray(lx if lx is not None else [Tx] * B, dtype=np.int64)
+    x = rng.integers(1, 29, size=(B, Tx)).astype(np.int64)
+    for b in range(B):
+        x[b, lx[b]:] = 29
+    y = rng.integers(1, 29, size=(B, L)).astype(np.int64)
+    return x, lx, y

@@ -287,7 +287,8 @@ def _profiler_attached() -> bool:
 
 
 def _overlap_ok(wrefs) -> bool:
-    if wrefs is None or torch.is_grad_enabled() or os.environ.get('LAS_BWD_OVERLAP', '1') == '0' or _profiler_attached():
+    mode = os.environ.get('LAS_BWD_OVERLAP', '1')          # 0: off; 1: on unless a kernel-serialising profiler is attached; 2: on regardless
+    if wrefs is None or torch.is_grad_enabled() or mode == '0' or (mode != '2' and _profiler_attached()):
         return False
     for w in wrefs:
         g = w.grad

@@ -48,6 +48,9 @@ def parse():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help="bf16: the AMP path (gate GEMMs on the tensor pipe, like the reference's autocast runs); fp32: parity mode")
     ap.add_argument('--no-greedy', action='store_true', help='skip the greedy-decode leg (BASELINE configs[3]) reported under "greedy"')
+    ap.add_argument('--no-fp32-leg', action='store_true', help='skip the two fp32-parity-mode steps reported under "fp32_mode"')
+    ap.add_argument('--no-rewriter', action='store_true', help='skip the Rewriter leg (BASELINE configs[4]) reported under "rewriter"')
+    ap.add_argument('--rewriter-batch', type=int, default=64)
     ap.add_argument('--greedy-batch', type=int, default=256)
     ap.add_argument('--greedy-T', type=int, default=3000)
     return ap.parse_args()
@@ -96,6 +99,31 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
                     samples=len(sm))
+
+
+def ncu_dram_bytes(kernel_prefix):
+    """dram read + write bytes per launch of the first row whose kernel name starts with `kernel_prefix` in the newest committed
+    `ncu --set full` extract under profiles/ (columns: kernel, dram_rd [GB], dram_wr [GB], ...), or None."""
+    for name in ('ncu_full_r2_kernels.csv', 'ncu_full_r1_final_kernels.csv', 'ncu_full_r1_kernels.csv'):
+        path = os.path.join(ROOT, 'profiles', name)
+        if not os.path.exists(path):
+            continue
+        for line in open(path):
+            if line.startswith('#') or line.startswith('kernel,'):
+                continue
+            if kernel_prefix in line:
+                tail = line[line.index(kernel_prefix) + len(kernel_prefix):].split(',')
+                nums = []
+                for tok in tail:
+                    try:
+                        nums.append(float(tok))
+                    except ValueError:
+                        continue
+                # the template arguments come first (integers), then dram_rd, dram_wr in GB: take the first two non-integers
+                frac = [v for v in nums if abs(v - round(v)) > 1e-9]
+                if len(frac) >= 2:
+                    return dict(bytes=(frac[0] + frac[1]) * 1e9, source='profiles/' + name)
+    return None
 
 
 def oracle_cpu_step(cfg_name, B, T, L, seed=11785):
@@ -377,6 +405,60 @@ def main():
     e2e_value = world * B / (ms_e2e / 1e3)
     h2d = x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()
 
+    # ---- the same train step in fp32 parity mode (the mode that carries the 1e-4 evidence): FFMA GEMMs + fp32 recurrence ----
+    fp32_mode = None
+    if rank == 0 or world > 1:
+        from las_b200.precision import set_precision
+        if args.precision == 'bf16' and not args.no_fp32_leg:
+            def step32():
+                reducer.zero_grad()
+                set_precision('fp32')
+                try:
+                    logits, _att = model(x_dev, lx, y_dev, 1.0, False)
+                    loss, _ppl = masked_ce(logits, y_dev, ly_cpu)
+                    (loss * scale).backward()
+                finally:
+                    set_precision('auto')
+                reducer.finish()
+                opt.step_fused(inv_scale=1.0 / (scale * world), max_norm=5.0)
+            step32()
+            ms32 = timed(step32, 2) / 2
+            fp32_mode = dict(ms_per_step=ms32, value=world * B / (ms32 / 1e3), unit=UNIT, note='fp32 parity mode (LAS_PRECISION=fp32), 2 timed steps')
+
+    # ---- Rewriter (BASELINE configs[4], src/lmtrain.py:95-253, config/rewriter.yml): char-to-char LM, tf_rate 0.5 ----
+    rewriter = None
+    if not args.no_rewriter:
+        from las_b200.lm import Rewriter
+        rcfg = gu.get_rewriter_config('rw_yml')
+        Br, Tr = args.rewriter_batch, 200
+        torch.manual_seed(11785)
+        rw = Rewriter(**rcfg).to(dev).train()
+        if world > 1:
+            for p in rw.parameters():
+                dist.broadcast(p.data, 0)
+        rw_red = BucketedGradReducer(list(rw.named_parameters()), world_size=world, bucket_key=lambda n: 'rewriter')
+        rw_opt = FusedAdamW(rw.parameters(), lr=1e-3, weight_decay=5e-6, amsgrad=True)
+        xr_np, lxr_np, yr_np = gu.make_token_inputs(777 + rank, Br, Tr, Tr)
+        xr, yr, lxr = torch.from_numpy(xr_np).to(dev), torch.from_numpy(yr_np).to(dev), torch.from_numpy(lxr_np)
+        lyr = torch.full((Br,), Tr, dtype=torch.int64)
+
+        def rw_step():
+            rw_red.zero_grad()
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=(args.precision == 'bf16')):
+                lg, _ = rw(xr, lxr, yr, 0.5)
+            loss, _ = masked_ce(lg, yr, lyr)
+            (loss * scale).backward()
+            rw_red.finish()
+            rw_opt.step_fused(inv_scale=1.0 / (scale * world), max_norm=5.0)
+        for _ in range(3):
+            rw_step()
+        ms_rw = timed(rw_step, 5) / 5
+        rewriter = dict(metric='rewriter_train_sequences_per_sec', value=world * Br / (ms_rw / 1e3), unit='sequences/s', ms_per_step=ms_rw,
+                        config=dict(workload=f'Rewriter (config/rewriter.yml dims: emb 256, 2x BiLSTM 256, P 128 x 4 heads, dec 256/128, yml dropouts), '
+                                             f'batch {Br}/GPU, Tx = L = {Tr}, tf_rate 0.5 (never takes effect: src/lmtrain.py:231), fwd+bwd+AdamW'))
+        del rw, rw_red, rw_opt
+        torch.cuda.empty_cache()
+
     # ---- greedy decoding (BASELINE configs[3]): eval mode, CHR_MAX_STEPS = 600 steps always (src/models.py:315), no collective ----
     greedy = None
     if not args.no_greedy:
@@ -434,6 +516,8 @@ def main():
         return
 
     pk = peaks()
+    gemm_traffic = ncu_dram_bytes('gemm_bf16_tc_kernel<0, 0, ')
+    attn_traffic = ncu_dram_bytes('attn_step_split_kernel<0')
     gg = prof['gemm_gates']
     tf_achieved = (gg['work_per_step'] / 1e12) / (gg['ms_per_step'] / 1e3) if gg['ms_per_step'] > 0 else 0.0
     gs = prof.get('gemm_gates_side', dict(ms_per_step=0.0, work_per_step=0.0))
@@ -441,8 +525,10 @@ def main():
     # free (functional.py, backward overlap): their time is hidden, not comparable with a whole-GPU peak, and reported apart
     roofline = dict(kernel='lstm input-gate GEMMs that own the GPU (fwd + dgrad all layers, wgrad of the base layer)' if gs['ms_per_step'] > 0
                     else 'lstm input-gate GEMMs (fwd + dgrad + wgrad, all layers)', bound='tensor', achieved=tf_achieved,
-                    peak=pk['tf_sustained'], unit='TFLOP/s', frac=tf_achieved / pk['tf_sustained'], traffic=1.545e9,
-                    traffic_note='dram read+write of the largest launch (layer-1 forward, M=76800 N=4096 K=2048: 1.29 TFLOP), ncu --set full, profiles/ncu_full_r1_kernels.csv',
+                    peak=pk['tf_sustained'], unit='TFLOP/s', frac=tf_achieved / pk['tf_sustained'],
+                    traffic=(gemm_traffic or {}).get('bytes'),
+                    traffic_note='dram read+write of the largest launch (layer-1 forward, M=76800 N=4096 K=2048: 1.29 TFLOP, 1.59 GB algorithmic), '
+                                 'read at run time from the committed ncu --set full extract ' + str((gemm_traffic or {}).get('source')),
                     peak_source=pk['source'] + ' bf16 sustained', ms_per_step=gg['ms_per_step'], flops_per_step=gg['work_per_step'],
                     beside_recurrence=dict(ms_per_step=gs['ms_per_step'], flops_per_step=gs['work_per_step'], max_ctas=52,
                                            note='wgrad GEMMs of layers 1-3, capped to the SMs the BPTT kernel leaves free; overlapped with it'))
@@ -452,11 +538,13 @@ def main():
     at_gbs = attn_replay['bytes_per_launch'] / attn_replay['us_fwd'] / 1e3
     at_gbs_bwd = attn_replay['bytes_per_launch'] / attn_replay['us_bwd'] / 1e3
     attn_roofline = dict(kernel='fused attention step fwd (energy+masked softmax+context), single-pass T-split', bound='hbm',
-                         achieved=at_gbs, peak=pk['hbm'], unit='GB/s', frac=at_gbs / pk['hbm'], traffic=39.45e6,
-                         traffic_note='dram read+write per launch with a flushed L2 (ncu --set full, profiles/ncu_full_r1_final_kernels.csv): K and V are read exactly once; in the decoder loop they are L2 hits',
+                         achieved=at_gbs, peak=pk['hbm'], unit='GB/s', frac=at_gbs / pk['hbm'], frac_of_8tbs=at_gbs / 8000.0,
+                         traffic=(attn_traffic or {}).get('bytes'),
+                         traffic_note='dram read+write per launch with a flushed L2 (ncu --set full extract ' + str((attn_traffic or {}).get('source')) +
+                                      '): K and V are read exactly once; in the decoder loop they are L2 hits',
                          peak_source=pk['source'],
                          us_per_launch=attn_replay['us_fwd'], bytes_per_launch=attn_replay['bytes_per_launch'],
-                         bwd=dict(achieved=at_gbs_bwd, frac=at_gbs_bwd / pk['hbm'], us_per_launch=attn_replay['us_bwd']),
+                         bwd=dict(achieved=at_gbs_bwd, frac=at_gbs_bwd / pk['hbm'], frac_of_8tbs=at_gbs_bwd / 8000.0, us_per_launch=attn_replay['us_bwd']),
                          method='50 launches captured in a CUDA graph, replayed, CUDA events on the replay stream; K/V (39 MB) L2-warm as in the loop',
                          in_loop_evented_us_per_launch=1e3 * af['ms_per_step'] / max(af['launches_per_step'], 1),
                          note='K/V of one batch fit in the 126 MB L2, so algorithmic GB/s can exceed what DRAM alone would give')
@@ -501,7 +589,9 @@ def main():
                clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e),
                gpu_launches=int(launches), roofline=roofline, attn_roofline=attn_roofline, recurrence=rec,
                kernel_ms_per_step={k: round(v['ms_per_step'], 3) for k, v in prof.items()}, greedy=greedy, cpu_baseline=cpu,
-               gpu_reference=gpu_ref)
+               gpu_reference=gpu_ref, fp32_mode=fp32_mode, rewriter=rewriter,
+               decoder_step_us=dict(fwd=1e3 * prof['speller_fwd']['ms_per_step'] / max(L, 1), bwd=1e3 * prof['speller_bwd']['ms_per_step'] / max(L, 1),
+                                    note='whole decoder loop / L steps; forward = one persistent cooperative kernel (csrc/decoder_persist.cu)'))
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

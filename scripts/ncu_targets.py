@@ -32,4 +32,14 @@ _lib.check(lib.las_transpose_cast_bf16(w_hh.data_ptr(), w_t.data_ptr(), ndir, 4 
 dgb = torch.empty(B * Tr, ndir * 4 * H, dtype=torch.bfloat16, device=DEV)
 _lib.check(lib.las_lstm_rec_fwd_tc(gates.data_ptr(), wb.data_ptr(), lens_dev.data_ptr(), None, None, hs.data_ptr(), cs.data_ptr(), B, Tr, H, ndir, 1, ws.data_ptr(), nbytes, st), 'fwd')
 _lib.check(lib.las_lstm_rec_bwd_tc(dout.data_ptr(), gates.data_ptr(), dgb.data_ptr(), cs.data_ptr(), w_t.data_ptr(), lens_dev.data_ptr(), None, B, Tr, H, ndir, ws.data_ptr(), nbytes, st), 'bwd')
+# 4. the persistent decoder-step kernel (Speller forward loop as one cooperative launch): best dims, B=96, T_enc=200, 60 steps
+from las_b200 import configs
+from las_b200.models import ListenAttendSpell
+torch.manual_seed(1)
+m = ListenAttendSpell(**configs.get_config('best', dec_lstm_dropout=0.3)).to(DEV).train()
+enc_h = torch.randn(B, 200, 1024, device=DEV) * 0.3
+yy = torch.randint(1, 29, (B, 60), device=DEV)
+for _ in range(2):
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        m.spell(enc_h, torch.full((B,), 200, dtype=torch.int64), yy, 1.0, False)
 torch.cuda.synchronize(); print('ok')
