@@ -111,18 +111,12 @@ def ncu_dram_bytes(kernel_prefix):
         for line in open(path):
             if line.startswith('#') or line.startswith('kernel,'):
                 continue
-            if kernel_prefix in line:
-                tail = line[line.index(kernel_prefix) + len(kernel_prefix):].split(',')
-                nums = []
-                for tok in tail:
-                    try:
-                        nums.append(float(tok))
-                    except ValueError:
-                        continue
-                # the template arguments come first (integers), then dram_rd, dram_wr in GB: take the first two non-integers
-                frac = [v for v in nums if abs(v - round(v)) > 1e-9]
-                if len(frac) >= 2:
-                    return dict(bytes=(frac[0] + frac[1]) * 1e9, source='profiles/' + name)
+            if kernel_prefix in line and '>,' in line:
+                rest = line.split('>,', 1)[1].split(',')          # columns after the kernel name: dram_rd [GB], dram_wr [GB], ...
+                try:
+                    return dict(bytes=(float(rest[0]) + float(rest[1])) * 1e9, source='profiles/' + name)
+                except (ValueError, IndexError):
+                    continue
     return None
 
 

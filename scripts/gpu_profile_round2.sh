@@ -3,8 +3,8 @@ set -x
 mkdir -p gpurun_out
 timeout -s KILL 200 python scripts/ncu_step.py 2 > gpurun_out/ncu_step_plain.log 2>&1 || { tail -5 gpurun_out/ncu_step_plain.log; exit 1; }
 tail -1 gpurun_out/ncu_step_plain.log
-# launch list of exactly one train step, backward overlap FORCED ON under the profiler (does the CTA-start hand-off survive kernel serialisation?)
-LAS_BWD_OVERLAP=2 timeout -s KILL 420 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+# launch list of exactly one train step, backward overlap on (its default, also under the profiler)
+timeout -s KILL 420 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches_r2_overlap.csv python scripts/ncu_step.py 2 > gpurun_out/ncu_step_overlap.log 2>&1; echo "ncu overlap-on rc=$?"
 tail -2 gpurun_out/ncu_step_overlap.log
 # the same with the default (overlap switched off under an attached profiler): the serial schedule

@@ -168,25 +168,22 @@ def test_lazy_host_tensor_waits_once_then_acts_like_a_plain_tensor():
         assert fresh.numpy().sum() == base.sum() and Ev.n == n0 + 1
 
 
-def test_backward_overlap_is_off_under_an_injected_profiler(monkeypatch):
-    """A full-step `ncu` capture with the backward overlap on did not finish in time: with a CUDA injection library in the
-    environment (how ncu / nsys attach) the plain autograd route must be taken."""
+def test_backward_overlap_eligibility_does_not_depend_on_an_attached_profiler(monkeypatch):
+    """Round 1 switched the backward overlap off when a CUDA injection library (ncu / nsys) was in the environment, because a whole
+    bench under ncu had not finished in time.  A one-step launch list with the overlap on completes (profiles/launches_r2_step_summary.csv),
+    so the schedule is the same with and without a profiler; LAS_BWD_OVERLAP=0 is the only switch."""
     import las_b200.functional as LF
-    monkeypatch.setattr(LF, '_PROFILER_ATTACHED', None)
-    monkeypatch.delenv('CUDA_INJECTION64_PATH', raising=False)
-    monkeypatch.delenv('NV_NSIGHT_INJECTION_PORT_BASE', raising=False)
-    assert LF._profiler_attached() is False
-    monkeypatch.setattr(LF, '_PROFILER_ATTACHED', None)
-    monkeypatch.setenv('CUDA_INJECTION64_PATH', '/opt/nvidia/nsight-compute/target/libcuda-injection64.so')
-    assert LF._profiler_attached() is True
     import torch
+    assert not hasattr(LF, '_profiler_attached')
     w = torch.nn.Parameter(torch.zeros(2)); w.grad = torch.zeros(2); w._las_bucketed = True
+    monkeypatch.delenv('LAS_BWD_OVERLAP', raising=False)
+    monkeypatch.setenv('CUDA_INJECTION64_PATH', '/opt/nvidia/nsight-compute/target/libcuda-injection64.so')
     with torch.no_grad():
-        assert LF._overlap_ok((w,)) is False
-        monkeypatch.setattr(LF, '_PROFILER_ATTACHED', False)
         assert LF._overlap_ok((w,)) is True
         monkeypatch.setenv('LAS_BWD_OVERLAP', '0')
         assert LF._overlap_ok((w,)) is False
+    monkeypatch.delenv('LAS_BWD_OVERLAP', raising=False)
+    assert LF._overlap_ok((w,)) is False                    # grad mode on: an autograd.grad / double-backward caller takes the plain route
 
 
 def test_bf16_shadow_is_dropped_when_the_tensor_is_written_to(monkeypatch):
