@@ -14,7 +14,6 @@ struct LasDecPersistFwd {
     int hist, ghist;
     int per_step_logits;           // 1: classifier + argmax inside the loop (greedy decoding, teacher forcing rate < 1)
     int kv16;                      // 1: K / V hold fp16
-    int kres_rows;                 // K rows per owned attention row kept in shared memory as fp16 (set by the launcher)
     float scale;                   // sqrt(P / heads)   (reference src/models.py:93,170: e = q.K / norm_factor)
     // parameters
     const float* emb;              // (V, 2P) tied classifier weight

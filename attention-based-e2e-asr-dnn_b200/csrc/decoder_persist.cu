@@ -179,19 +179,18 @@ __device__ __forceinline__ long long gtime_ns() {
     } while (0)
 
 struct SmemLayout {
-    uint32_t tile, ex, sc, part, misc, kres, total;
+    uint32_t tile, ex, wq, sc, part, misc, total;
 };
-// `kres_rows` K rows (fp16) of every attention row this CTA owns stay in shared memory for the whole loop
-__host__ __device__ inline SmemLayout smem_layout(int T, int P, int DH, int DO, int kres_rows_total) {
+__host__ __device__ inline SmemLayout smem_layout(int T, int P, int DH, int DO) {
     SmemLayout L;
     const int K0 = P + DH, K1 = DH + DO, Kmax = K0 > K1 ? K0 : K1;
     uint32_t o = 0;
     L.tile = o; o += 64u * (uint32_t)Kmax;                   // 32 rows x Kmax fp16, core-matrix layout
     L.ex = o; o += 4u * 32u * 32u * 4u;                      // [gate][row][unit] activated gates
+    L.wq = o; o += (uint32_t)DO * (uint32_t)P * 2u;          // WqT fp16
     L.sc = o; o += (uint32_t)((T + 3) & ~3) * 4u;            // scaled energies of one batch row
     L.part = o; o += (uint32_t)NW * (uint32_t)P * 4u;        // per-warp partial context
     L.misc = o; o += 8192u;                                  // see `Misc`
-    L.kres = o; o += (uint32_t)kres_rows_total * (uint32_t)P * 2u;      // resident K rows, fp16
     L.total = o + 1024u;                                     // alignment slack
     return L;
 }
@@ -251,13 +250,13 @@ __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(const LasDecPers
     unsigned* ctr_c0 = a.ctr + 32 * a.nsl;                    // [slice] cell-0 CTAs done
     unsigned* ctr_c1 = a.ctr + 64 * a.nsl;                    // [slice] cell-1 CTAs done
 
-    const SmemLayout L = smem_layout(T, P, DH, DO, a.kres_rows * ((B + (int)gridDim.x - 1) / (int)gridDim.x));
+    const SmemLayout L = smem_layout(T, P, DH, DO);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t tile_sm = base + L.tile;
     uint8_t* tile_ptr = sm + L.tile;
     float* ex = reinterpret_cast<float*>(sm + L.ex);
-    __half* kres_s = reinterpret_cast<__half*>(sm + L.kres);
+    const __half2* wq_s = reinterpret_cast<const __half2*>(sm + L.wq);
     float* sc = reinterpret_cast<float*>(sm + L.sc);
     float* part = reinterpret_cast<float*>(sm + L.part);
     Misc* ms = reinterpret_cast<Misc*>(sm + L.misc);
@@ -274,26 +273,12 @@ __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(const LasDecPers
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
-    // resident keys: the first kres_rows K rows of every attention row this CTA owns, as fp16 (the energies are sums of 256 products: fp16
-    // keys move the logits by < 1e-4), read at 128 B/clk from shared memory instead of ~32 B/clk per SM from L2
-    {
-        int own = 0;
-        for (int b = cta; b < B; b += G, ++own) {
-            const int nres = min(min(a.enc_lens[b], T), a.kres_rows);
-            __half* dst = kres_s + (long long)own * a.kres_rows * P;
-            const long long src0 = (long long)b * T * P;
-            for (int i = tid; i < nres * P / 4; i += NT) {
-                float4 v;
-                if (KV16) {
-                    const uint2 r = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(a.K) + src0) + i);
-                    *reinterpret_cast<uint2*>(dst + 4 * i) = r;
-                } else {
-                    v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.K) + src0) + i);
-                    *reinterpret_cast<__half2*>(dst + 4 * i) = __floats2half2_rn(v.x, v.y);
-                    *reinterpret_cast<__half2*>(dst + 4 * i + 2) = __floats2half2_rn(v.z, v.w);
-                }
-            }
-        }
+    // query-projection weight (fp16, transposed) -> shared memory, for CTAs that own attention rows
+    if (cta < B) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.WqT);
+        uint4* dst = reinterpret_cast<uint4*>(sm + L.wq);
+        const int n16 = DO * P * 2 / 16;
+        for (int i = tid; i < n16; i += NT) dst[i] = src[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -346,18 +331,15 @@ __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(const LasDecPers
                 const int quadP = P >> 2, kgroups = NT / quadP, klen = DO / kgroups;
                 const int j4 = tid % quadP, kg = tid / quadP;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                const uint2* wp = reinterpret_cast<const uint2*>(a.WqT) + (long long)kg * klen * quadP + j4;      // L2-resident, shared by every CTA
+                const uint2* wp = reinterpret_cast<const uint2*>(wq_s) + (long long)kg * klen * quadP + j4;
                 const float4* hp = reinterpret_cast<const float4*>(ms->h1s + kg * klen);
 #pragma unroll 4
                 for (int k4 = 0; k4 < klen / 4; ++k4) {
                     const float4 hv = hp[k4];
                     const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
-                    uint2 wl[4];
-#pragma unroll
-                    for (int kk2 = 0; kk2 < 4; ++kk2) wl[kk2] = __ldg(wp + (long long)(k4 * 4 + kk2) * quadP);
 #pragma unroll
                     for (int kk2 = 0; kk2 < 4; ++kk2) {
-                        const uint2 w4 = wl[kk2];
+                        const uint2 w4 = wp[(long long)(k4 * 4 + kk2) * quadP];
                         const float2 wa = __half22float2(*reinterpret_cast<const __half2*>(&w4.x));
                         const float2 wb = __half22float2(*reinterpret_cast<const __half2*>(&w4.y));
                         acc[0] = fmaf(hk[kk2], wa.x, acc[0]); acc[1] = fmaf(hk[kk2], wa.y, acc[1]);
@@ -382,42 +364,7 @@ __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(const LasDecPers
             // ---- pass 1: scaled energies of every valid row into shared memory (8 rows = 8 independent reductions in flight per warp).
             // Two passes (K, then V) instead of one online-softmax pass: with 8 warps per SM a warp that loads, reduces, rescales and
             // accumulates in one loop exposes every latency once per iteration (measured 9.6 us per 410 KB row); the bytes are the same.
-            const int own = (b - cta) / G;
-            const int nres = min(len, a.kres_rows);
-            {   // resident rows: 16-byte shared loads, lane l holds columns [8l, 8l + 8)
-                const __half* kr = kres_s + (long long)own * a.kres_rows * P;
-                float qs8[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) qs8[i] = (lane * 8 + i < P) ? ms->qc[lane * 8 + i] : 0.f;
-                for (int tb = warp; tb < nres; tb += NW * RU) {
-                    float e[RU];
-#pragma unroll
-                    for (int u = 0; u < RU; ++u) {
-                        const int t = tb + u * NW;
-                        float acc = 0.f;
-                        if (t < nres && lane * 8 < P) {
-                            const uint4 r = *reinterpret_cast<const uint4*>(kr + (long long)t * P + lane * 8);
-                            const __half2* h = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float2 f = __half22float2(h[i]);
-                                acc = fmaf(f.x, qs8[2 * i], acc);
-                                acc = fmaf(f.y, qs8[2 * i + 1], acc);
-                            }
-                        }
-                        e[u] = acc;
-                    }
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-                        for (int u = 0; u < RU; ++u) e[u] += __shfl_xor_sync(0xffffffffu, e[u], off);
-                    if (lane == 0) {
-#pragma unroll
-                        for (int u = 0; u < RU; ++u) { const int t = tb + u * NW; if (t < nres) sc[t] = e[u] * a.scale; }
-                    }
-                }
-            }
-            for (int tb = nres + warp; tb < len; tb += NW * RU) {          // rows that did not fit: streamed from L2 / HBM
+            for (int tb = warp; tb < len; tb += NW * RU) {
                 float kk[RU][8];
 #pragma unroll
                 for (int u = 0; u < RU; ++u) {
@@ -751,7 +698,7 @@ int las_dec_persist_fwd_supported(int B, int T, int P, int DH, int DO, int V, in
     const int nsl = (B + NBS - 1) / NBS;
     const int ng = persist_groups(B, DH, DO, di->num_sms);
     if (ng < 1 || (nsl + ng - 1) / ng > MAX_CHAINS) return 0;
-    if (smem_layout(T, P, DH, DO, 0).total + 1024u > (uint32_t)di->max_smem_optin) return 0;
+    if (smem_layout(T, P, DH, DO).total > (uint32_t)di->max_smem_optin) return 0;
     return 1;
 }
 
@@ -764,14 +711,7 @@ int las_dec_persist_fwd_launch(const LasDecPersistFwd* a0, cudaStream_t st) {
     const LasDeviceInfo* di = las_device_info();
     a.nsl = (a.B + NBS - 1) / NBS;
     a.ngroups = persist_groups(a.B, a.DH, a.DO, di->num_sms);
-    // resident K rows per owned attention row: whatever the 227 KB leave after the fixed regions (1 KB static), at most T
-    const int own_max = (a.B + di->num_sms - 1) / di->num_sms;
-    const long long room = (long long)di->max_smem_optin - 1024 - (long long)smem_layout(a.T, a.P, a.DH, a.DO, 0).total;
-    long long kr = room > 0 ? room / ((long long)own_max * a.P * 2) : 0;
-    const char* kre = getenv("LAS_DP_KRES");               // tuning switch: 0 disables the residency
-    if (kre && atoi(kre) == 0) kr = 0;
-    a.kres_rows = (int)(kr < a.T ? kr : a.T);
-    const size_t smem = smem_layout(a.T, a.P, a.DH, a.DO, a.kres_rows * own_max).total;
+    const size_t smem = smem_layout(a.T, a.P, a.DH, a.DO).total;
     void* args[] = {(void*)&a};
     const char* nae = getenv("LAS_DP_NA");                 // 1: K / V rows with ld.global.nc.L1::no_allocate (tuning switch)
     const bool na = nae && atoi(nae) == 1;
