@@ -710,7 +710,11 @@ extern "C" int las_speller_fwd_f32(const LasSpeller* s, void* stream) {
     const unsigned long long key = fnv1a(ident.data(), ident.size(), 1469598103934665603ULL);
     // persistent decoder-step kernel: one cooperative launch for the whole loop (plus a handful of weight-preparation kernels),
     // enqueued directly -- nothing to amortise with a graph, and no graph key that depends on the coin pattern
-    if (L.persist) return speller_fwd_persist(s, L, st);
+    if (L.persist) {
+        const int rc = speller_fwd_persist(s, L, st);
+        if (rc == LAS_OK || s->kv_bf16 == 2) return rc;          // fp16 K / V only exist for the persistent kernel
+        cudaGetLastError();      // e.g. the cooperative launch was refused (device shared through MPS): the launch-per-stage loop still runs
+    }
     return run_graph_cached(key, ident, st, [&](cudaStream_t q, GraphSeg* seg) { return speller_fwd_enqueue(s, L, q, seg); });
 }
 

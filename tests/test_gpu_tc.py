@@ -362,3 +362,87 @@ def test_tc_gemm_fp16_operands():
     assert rel_err(Cw.cpu().numpy(), torch.einsum('brk,brn->kn', A.double(), X.double()).cpu().numpy()) < 1e-5
     with pytest.raises(RuntimeError, match='same 16-bit format'):
         LF.gemm_tc(A, W.to(torch.bfloat16), C, R, N, K, a_batches=B, a_s1=K, a_s2=R * K, b_s1=K, c_bs=R * N, ldc=N)
+
+
+def _speller_vs_oracle(B, T, L, lx, tf_coins=None, seed=5):
+    """best-config Speller in bf16 mode (the persistent decoder-step kernel) vs the fp32 oracle Speller, both on the encodings the
+    fp32 Listener produces for a seeded batch (realistic operand magnitudes; the oracle does not have to run the encoder)."""
+    from las_b200.models import ListenAttendSpell
+    from las_b200.modules import set_mask_override
+    cfg = gu.get_config('best')
+    sd = gu.make_state_dict(cfg, seed)
+    model = ListenAttendSpell(**gu.get_config('best')).to(DEV).train()
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    x, lx, y = gu.make_inputs(seed + 1, B, T, L, lx=lx)
+    with torch.no_grad():
+        enc_h, enc_l = model.listen(torch.from_numpy(x).to(DEV), torch.from_numpy(lx))
+    y = torch.from_numpy(y)
+    tf = 1.0
+    coins = [True] * L
+    if tf_coins is not None:
+        tf, coins = 0.5, [True] + list(tf_coins)
+        set_mask_override(None, None, [0.1 if c else 0.9 for c in tf_coins])      # raw draws: <= 0.5 takes the gold token
+    try:
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            logits, att = model.spell(enc_h, enc_l, y.to(DEV), tf, False)
+    finally:
+        set_mask_override(None, None, None)
+    p = {k: torch.from_numpy(v.copy()) for k, v in sd.items()}
+    with torch.no_grad():
+        ol, oatt = orc.speller_forward(p, enc_h.cpu(), [int(v) for v in enc_l], heads=1, training=True, steps=L, dec_y=y, coins=coins)
+    return logits.detach().float().cpu().numpy(), ol.numpy(), att.numpy(), oatt.numpy()
+
+
+def test_persistent_decoder_more_rows_than_sms_and_two_slices_per_cell_cta():
+    """B = 200 > 148 CTAs: attention CTAs own two batch rows, 7 batch slices over 6 slice groups -> cell CTAs own two slices (the greedy
+    configuration's structure); ragged encoder lengths incl. 1."""
+    from las_b200 import _lib
+    B, T, L = 200, 320, 5
+    assert _lib.load().las_speller_persistent(B, T // 8, 256, 512, 256, 30, 1, 0, 1) == 1
+    rng = np.random.default_rng(3)
+    lx = [T, 8] + [int(v) for v in rng.integers(9, T + 1, size=B - 2)]
+    got, ref, att, oatt = _speller_vs_oracle(B, T, L, lx)
+    assert np.abs(got - ref).max() < 2e-3
+    assert np.abs(att - oatt).max() < 1e-3
+
+
+def test_persistent_decoder_teacher_forcing_coins_and_argmax_feedback():
+    """tf_rate 0.5 (the reference yml's default): per-step classifier + argmax inside the kernel, the coin decides per step whether
+    the gold token or the fed-back argmax is embedded (src/models.py:354-358); device-side coin flags, no graph key."""
+    B, T, L = 5, 240, 10
+    coins = [True, False, False, True, False, True, False, False, True]          # steps 1..9
+    got, ref, _, _ = _speller_vs_oracle(B, T, L, [240, 96, 200, 240, 56], tf_coins=coins)
+    same = got.argmax(-1) == ref.argmax(-1)
+    # identical fed-back tokens wherever the top-1 / top-2 gap is not a near-tie; logits within the AMP bar on agreeing prefixes
+    for b in range(B):
+        n = int(np.argmax(~same[b])) if (~same[b]).any() else L
+        assert n >= L - 1 or np.sort(ref[b, n])[-1] - np.sort(ref[b, n])[-2] < 5e-3, (b, n)
+        assert np.abs(got[b, :min(n + 1, L)] - ref[b, :min(n + 1, L)]).max() < 2e-3
+    assert same.mean() > 0.9
+
+
+def test_persistent_decoder_greedy_matches_launch_per_stage_loop(monkeypatch):
+    """Eval mode (CHR_MAX_STEPS greedy steps, hist = 2 ring buffers): the persistent kernel (fp16 operands) against the
+    launch-per-stage loop (LAS_DEC_PERSIST=0, bf16 operands) -- the fed-back argmax is the returned logits' argmax in both, first-step
+    logits agree to operand rounding, transcripts agree except after a near-tie."""
+    from las_b200.models import ListenAttendSpell
+    cfg = gu.get_config('best', CHR_MAX_STEPS=25)
+    sd = gu.make_state_dict(cfg, 9, scale=2.0)
+    model = ListenAttendSpell(**gu.get_config('best', CHR_MAX_STEPS=25)).to(DEV).eval()
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    B, T = 160, 264
+    rng = np.random.default_rng(10)
+    x, lx, _ = gu.make_inputs(11, B, T, 1, lx=[T] + [int(v) for v in rng.integers(8, T + 1, size=B - 1)])
+    outs = []
+    for persist in ('1', '0'):
+        monkeypatch.setenv('LAS_DEC_PERSIST', persist)
+        with torch.inference_mode():
+            enc_h, enc_l = model.listen(torch.from_numpy(x).to(DEV), torch.from_numpy(lx))
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                lg, _ = model.spell(enc_h, enc_l)
+        outs.append((lg.float().cpu().numpy(), model.spell.last_chars.t().cpu().numpy()))
+    (la, ca), (lb, cb) = outs
+    assert np.array_equal(ca, la.argmax(-1)) and np.array_equal(cb, lb.argmax(-1))
+    scale = np.abs(lb[:, 0]).max()
+    assert np.abs(la[:, 0] - lb[:, 0]).max() < 5e-3 * max(1.0, scale)
+    assert (ca == cb).mean() > 0.9
