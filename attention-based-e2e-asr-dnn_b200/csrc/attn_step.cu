@@ -8,6 +8,7 @@
 // and K and V are each read exactly once per step: algorithmic bytes = 2 * B * T_enc * P * 4.
 #include "las_common.cuh"
 #include "las_b200.h"
+#include "attn_tail.h"
 #include <float.h>
 #include <stdlib.h>
 
@@ -268,18 +269,35 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, unsigned r
     return v;
 }
 
-template <bool BWD, bool KV16>
-__global__ void __launch_bounds__(NT2, 2) attn_step_split_kernel(LasAttnStep a) {
+constexpr int TAIL_MAX_SPLIT = 8;
+
+template <bool BWD, bool KV16, bool TAIL>
+__global__ void __launch_bounds__(NT2, 2) attn_step_split_kernel(LasAttnStep a, LasAttnCellTail tl) {
     extern __shared__ __align__(16) float sm[];
-    pdl_wait();
-    pdl_trigger();
     const int T = a.T, P = a.P, heads = a.heads, d = P / heads;
     const int S = gridDim.x, rank = blockIdx.x;
     const int bh = blockIdx.y, b = bh / heads, h = bh - b * heads;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int cap = ((T + S - 1) / S + 3) & ~3;
+    // fused tail (attn_tail.h): this CTA's DO/S output columns of dh1 = dq . Wq, then LSTMCell-1 backward for them
+    const int nper = TAIL ? tl.DO / S : 8;
+    float* dqs = sm + cap + 2 * NW2 + 16 + 4 + d + NW2 * d;       // [d]          dq_total of the row (every CTA of the cluster holds all of it)
+    float* gpart = dqs + d;                                       // [kg][nper]   partial dh1 sums of the k groups
+    __nv_bfloat16* wq_s = reinterpret_cast<__nv_bfloat16*>(gpart + (TAIL ? (NT2 / (nper / 2)) * nper : 0));      // [P][nper]
+    if constexpr (TAIL) {
+        // the weight slice does not depend on the predecessor kernel: fetch it before the programmatic-launch wait, asynchronously
+        const int cpr = nper / 8;                                 // 16-byte chunks per weight row
+        const __nv_bfloat16* wsrc = reinterpret_cast<const __nv_bfloat16*>(tl.wq_bf16) + rank * nper;
+        for (int i = tid; i < P * cpr; i += NT2) {
+            const int k = i / cpr, j = i - k * cpr;
+            cp_async16(wq_s + k * nper + j * 8, wsrc + (long long)k * tl.DO + j * 8);
+        }
+        cp_async_commit();
+    }
+    pdl_wait();
+    pdl_trigger();
     const int len = min(a.lens[b], T);
     const int per = (len + S - 1) / S;                       // rows of this (row, head) per CTA
-    const int cap = ((T + S - 1) / S + 3) & ~3;
     const int t_lo = min(rank * per, len), t_hi = min(t_lo + per, len);
     float* sc = sm;                 // [cap]    fwd: scaled energies of this CTA's rows
     float* wm = sm + cap;           // [NW2]    per-warp running max
@@ -391,6 +409,26 @@ __global__ void __launch_bounds__(NT2, 2) attn_step_split_kernel(LasAttnStep a) 
             }
         }
     }
+    // ---- fused tail: operands of the cell backward and the classifier-path dq, fetched behind the merges below ----
+    float t_g[4] = {0.f, 0.f, 0.f, 0.f}, t_c = 0.f, t_cp = 0.f, t_dc = 0.f, t_mask = 1.f, t_rec = 0.f, t_dq_old = 0.f;
+    const int tu = rank * nper + tid;                        // hidden unit of thread tid < nper
+    if constexpr (TAIL) {
+        if (tid < d && a.dq_accumulate) t_dq_old = a.dq[(long long)b * a.ld_dq + tid];     // read before any CTA of the pair writes dq
+        if (tid < nper) {
+            const int H = tl.DO;
+            float pb[TAIL_MAX_SPLIT];
+            const int nb = tl.dh_b ? (tl.nsplit_b > 1 ? tl.nsplit_b : 1) : 0;
+#pragma unroll
+            for (int sp = 0; sp < TAIL_MAX_SPLIT; ++sp) pb[sp] = sp < nb ? tl.dh_b[sp * tl.stride_b + (long long)b * tl.ld_b + tu] : 0.f;
+            const float* g = tl.G + (long long)b * 4 * H + tu;
+            t_g[0] = g[0]; t_g[1] = g[H]; t_g[2] = g[2 * H]; t_g[3] = g[3 * H];
+            t_c = tl.c[(long long)b * tl.ld_c + tu]; t_cp = tl.c_prev[(long long)b * tl.ld_cp + tu];
+            t_dc = tl.first ? 0.f : tl.dc[(long long)b * H + tu];
+            if (tl.mask) t_mask = tl.mask[(long long)b * H + tu];
+#pragma unroll
+            for (int sp = 0; sp < TAIL_MAX_SPLIT; ++sp) t_rec += pb[sp];
+        }
+    }
     // ---- merge the warps of this CTA ----
     if (lane == 0) { wm[w] = m_run; wsum[w] = s_run; }
 #pragma unroll
@@ -451,8 +489,56 @@ __global__ void __launch_bounds__(NT2, 2) attn_step_split_kernel(LasAttnStep a) 
             }
         }
     }
-    // ---- output columns [rank*dper, (rank+1)*dper) of this (row, head): sum the cluster's partial vectors over DSMEM ----
     const int dper = (d + S - 1) / S;
+    if constexpr (TAIL) {
+        // every CTA of the pair sums ALL d columns (it needs the whole dq vector for its slice of dq . Wq); it stores its own columns
+        if (tid < d) {
+            float r = 0.f;
+            for (int j = 0; j < S; ++j) r += ld_dsmem_f32(cta_o + tid, (unsigned)j);
+            const float tot = t_dq_old + r;
+            dqs[tid] = tot;
+            if (tid / dper == rank) {
+                a.dq[(long long)b * a.ld_dq + tid] = tot;
+                if (a.dq_bf16) ((__nv_bfloat16*)a.dq_bf16)[(long long)b * a.ld_dq_bf16 + tid] = __float2bfloat16(tot);
+            }
+        }
+        cluster_sync_all();      // peers are done reading this CTA's shared memory; dqs is complete (the barrier is also a CTA barrier)
+        cp_async_wait<0>();
+        __syncthreads();         // every thread's part of the weight slice has landed
+        const int pairs = nper / 2, kg = NT2 / pairs, kper = P / kg;
+        {
+            const int j = tid % pairs, g = tid / pairs;
+            float a0 = 0.f, a1 = 0.f;
+            const unsigned* wrow = reinterpret_cast<const unsigned*>(wq_s) + j;
+#pragma unroll 8
+            for (int k = g * kper; k < (g + 1) * kper; ++k) {
+                const unsigned w2 = wrow[k * pairs];
+                const float x = dqs[k];
+                a0 = fmaf(x, __uint_as_float(w2 << 16), a0);
+                a1 = fmaf(x, __uint_as_float(w2 & 0xffff0000u), a1);
+            }
+            gpart[g * nper + 2 * j] = a0; gpart[g * nper + 2 * j + 1] = a1;
+        }
+        __syncthreads();
+        if (tid < nper) {
+            // LSTMCell-1 backward of hidden unit tu (decoder.cu::cell_bwd_kernel with dh_a = dq . Wq)
+            const int H = tl.DO;
+            float dh = 0.f;
+            for (int g = 0; g < kg; ++g) dh += gpart[g * nper + tid];
+            dh = (dh + t_rec) * t_mask;
+            const float gi = t_g[0], gf = t_g[1], gg = t_g[2], go = t_g[3];
+            const float tc = tanhf(t_c);
+            const float dct = fmaf(dh * go, 1.f - tc * tc, t_dc);
+            const float d0 = dct * gg * gi * (1.f - gi), d1 = dct * t_cp * gf * (1.f - gf);
+            const float d2 = dct * gi * (1.f - gg * gg), d3 = dh * tc * go * (1.f - go);
+            float* g = tl.G + (long long)b * 4 * H + tu;
+            g[0] = d0; g[H] = d1; g[2 * H] = d2; g[3 * H] = d3;
+            __nv_bfloat16* gb = reinterpret_cast<__nv_bfloat16*>(tl.Gb) + (long long)b * 4 * H + tu;
+            gb[0] = __float2bfloat16(d0); gb[H] = __float2bfloat16(d1); gb[2 * H] = __float2bfloat16(d2); gb[3 * H] = __float2bfloat16(d3);
+            tl.dc[(long long)b * H + tu] = dct * gf;
+        }
+    } else {
+    // ---- output columns [rank*dper, (rank+1)*dper) of this (row, head): sum the cluster's partial vectors over DSMEM ----
     for (int i = tid; i < dper; i += NT2) {
         const int p = rank * dper + i;
         if (p >= d) break;
@@ -474,6 +560,7 @@ __global__ void __launch_bounds__(NT2, 2) attn_step_split_kernel(LasAttnStep a) 
         }
     }
     cluster_sync_all();          // keep this CTA's shared memory alive until every peer has read it
+    }
 }
 
 int check(const LasAttnStep* a, bool bwd) {
@@ -504,12 +591,17 @@ int launch_one(const LasAttnStep* a, size_t smem, cudaStream_t st) {
     LAS_CUDA(las_launch(attn_step_kernel<BWD, RU, KV16>, dim3(a->B * a->heads), dim3(NT), smem, st, *a));
     return LAS_OK;
 }
-template <bool BWD, bool KV16>
-int launch_split(const LasAttnStep* a, int S, cudaStream_t st) {
+size_t tail_smem_floats(int P, int DO, int S) {
+    const int nper = DO / S, kg = NT2 / (nper / 2);
+    return (size_t)P + (size_t)kg * nper + (size_t)P * nper / 2;       // dqs + gpart + bf16 weight slice
+}
+
+template <bool BWD, bool KV16, bool TAIL>
+int launch_split(const LasAttnStep* a, int S, cudaStream_t st, const LasAttnCellTail* tail = nullptr) {
     const int d = a->P / a->heads;
     const int cap = ((a->T + S - 1) / S + 3) & ~3;
-    const size_t smem = sizeof(float) * ((size_t)cap + 2 * NW2 + 16 + 4 + d + (size_t)NW2 * d);
-    if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_split_kernel<BWD, KV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = sizeof(float) * ((size_t)cap + 2 * NW2 + 16 + 4 + d + (size_t)NW2 * d + (TAIL ? tail_smem_floats(a->P, tail->DO, S) : 0));
+    if (smem > 48 * 1024) LAS_CUDA(cudaFuncSetAttribute(attn_step_split_kernel<BWD, KV16, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(S, a->B * a->heads, 1);
     cfg.blockDim = dim3(NT2, 1, 1);
@@ -521,7 +613,9 @@ int launch_split(const LasAttnStep* a, int S, cudaStream_t st) {
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = las_pdl_active() ? 2 : 1;
-    LAS_CUDA(cudaLaunchKernelEx(&cfg, attn_step_split_kernel<BWD, KV16>, *a));
+    LasAttnCellTail tl{};
+    if (TAIL) tl = *tail;
+    LAS_CUDA(cudaLaunchKernelEx(&cfg, attn_step_split_kernel<BWD, KV16, TAIL>, *a, tl));
     return LAS_OK;
 }
 
@@ -542,7 +636,7 @@ int launch_attn(const LasAttnStep* a, size_t smem, cudaStream_t st) {
     // single-pass T-split kernel; backward needs the saved context for it (dot = dctx . ctx).  LAS_ATTN_SPLIT=0 or a
     // backward descriptor without ctx selects the two-phase one-CTA-per-row kernel.
     const int S = ((BWD && !a->ctx) || a->fmask) ? 0 : split_factor(a);
-    if (S >= 1) return a->kv_bf16 ? launch_split<BWD, true>(a, S, st) : launch_split<BWD, false>(a, S, st);
+    if (S >= 1) return a->kv_bf16 ? launch_split<BWD, true, false>(a, S, st) : launch_split<BWD, false, false>(a, S, st);
     const bool big = a->B * a->heads >= las_device_info()->num_sms;
     if (a->kv_bf16) return big ? launch_one<BWD, 4, true>(a, smem, st) : launch_one<BWD, 8, true>(a, smem, st);
     return big ? launch_one<BWD, 4, false>(a, smem, st) : launch_one<BWD, 8, false>(a, smem, st);
@@ -572,6 +666,40 @@ extern "C" int las_attn_step_bwd_f32(const LasAttnStep* a, void* stream) {
     size_t smem = smem_bytes(a);
     LasProfScope prof(LAS_PROF_ATTN_BWD, stream, 2.0 * a->B * (double)a->T * a->P * (a->kv_bf16 ? 2 : 4));
     rc = launch_attn<true>(a, smem, (cudaStream_t)stream);
+    if (rc) return rc;
+    LAS_LAUNCH_CHECK();
+    return LAS_OK;
+}
+
+// ---- fused backward step (attn_tail.h) ----
+static int tail_split(const LasAttnStep* a, int DO) {
+    if (!a || a->heads != 1 || a->fmask || !a->ctx || a->kv_bf16 || a->P > NT2 || DO < 16) return 0;
+    const int S = split_factor(a);
+    if (S < 1 || S > 2 || DO % (8 * S) != 0) return 0;
+    const int nper = DO / S, pairs = nper / 2;
+    if (pairs > NT2 || NT2 % pairs != 0 || a->P % (NT2 / pairs) != 0 || nper > NT2) return 0;
+    const int cap = ((a->T + S - 1) / S + 3) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)cap + 2 * NW2 + 16 + 4 + a->P + (size_t)NW2 * a->P + tail_smem_floats(a->P, DO, S));
+    return smem <= (S == 2 ? 100 : 200) * 1024 ? S : 0;          // pairs: two CTAs per SM stay resident; one CTA per row: at most one per SM anyway
+}
+
+int las_attn_step_bwd_cell_supported(const LasAttnStep* a, int DO) {
+    const char* e = getenv("LAS_BWD_FUSE_TAIL");
+    if (e && *e == '0') return 0;
+    return tail_split(a, DO) > 0 ? 1 : 0;
+}
+
+int las_attn_step_bwd_cell(const LasAttnStep* a, const LasAttnCellTail* tail, void* stream) {
+    int rc = check(a, true);
+    if (rc) return rc;
+    LAS_CHECK_ARG(tail && tail->wq_bf16 && tail->G && tail->Gb && tail->c && tail->c_prev && tail->dc, "attn_step_bwd_cell: null tail operand");
+    LAS_CHECK_ARG(tail->nsplit_b <= TAIL_MAX_SPLIT, "attn_step_bwd_cell: at most %d recurrent partials", TAIL_MAX_SPLIT);
+    const int S = tail_split(a, tail->DO);
+    LAS_CHECK_ARG(S > 0, "attn_step_bwd_cell: shape not supported (ask las_attn_step_bwd_cell_supported)");
+    rc = las_set_device_of(a->K);
+    if (rc) return rc;
+    LasProfScope prof(LAS_PROF_ATTN_BWD, stream, 2.0 * a->B * (double)a->T * a->P * 4);
+    rc = launch_split<true, false, true>(a, S, (cudaStream_t)stream, tail);
     if (rc) return rc;
     LAS_LAUNCH_CHECK();
     return LAS_OK;

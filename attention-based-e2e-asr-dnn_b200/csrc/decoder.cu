@@ -16,6 +16,7 @@
 #include "las_common.cuh"
 #include "las_b200.h"
 #include "dec_persist.h"
+#include "attn_tail.h"
 #include <vector>
 #include <mutex>
 #include <stdlib.h>
@@ -1000,6 +1001,10 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     std::vector<unsigned char> ident((const unsigned char*)&kd, (const unsigned char*)&kd + sizeof(LasSpeller));
     if (s->use_gold_host) ident.insert(ident.end(), s->use_gold_host, s->use_gold_host + s->steps);
     ident.insert(ident.end(), (const unsigned char*)g, (const unsigned char*)g + sizeof(LasSpellerGrads));
+    for (const char* name : {"LAS_BWD_FUSE_TAIL", "LAS_ATTN_SPLIT"}) {       // tuning switches that change which kernels the graph holds
+        const char* e = getenv(name);
+        ident.push_back((unsigned char)((e && *e) ? *e : 0));
+    }
     const unsigned long long key = fnv1a(ident.data(), ident.size(), 7809847782465536322ULL);
     return run_graph_cached(key, ident, st, [&](cudaStream_t q, GraphSeg* seg) { return speller_bwd_enqueue(s, g, L, q, seg); });
 }
@@ -1086,10 +1091,7 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
         at.dq = dQCn; at.de = DE + (size_t)rn * B * heads * T;
         at.dq_bf16 = tc ? (void*)(dQb + (size_t)rn * B * P) : nullptr; at.ld_dq_bf16 = P;
         if (s->init_force) { at.fmask = FM + (size_t)t * T; at.ld_fmask = 0; at.w2 = W2 + (size_t)rn * B * heads * T; }
-        RC(las_attn_step_bwd_f32(&at, st));
-        // dh1_t (dropped) = dq_total . Wq  (+ recurrent path, added inside cell_bwd)
-        if (tc) RC(las_tc_plan_launch(&bq1, rn, dh1, DO, nullptr, nullptr, st));
-        else RC(gemm(st, dQCn, 2 * P, s->wq, DO, 0, dh1, DO, B, DO, P));
+        const bool fuse_tail = tc && las_attn_step_bwd_cell_supported(&at, DO) != 0;      // asked per step: the descriptor is complete here
         CellBwd b1{};
         b1.G = G1 + (size_t)t * B * 4 * DO;
         b1.dh_a = dh1; b1.ld_a = DO;
@@ -1098,8 +1100,21 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
         b1.c = C1 + (size_t)rn * B * DO; b1.ld_c = DO; b1.c_prev = C1 + (size_t)t * B * DO; b1.ld_cp = DO;
         b1.dc = dc1; b1.first = (t == S - 1); b1.B = B; b1.H = DO;
         b1.Gb = tc ? G1b + (size_t)t * B * 4 * DO : nullptr;
-        LAS_CUDA(las_launch(cell_bwd_kernel, dim3(ceil_div(B * DO, 256)), dim3(256), 0, st, b1));
-        LAS_LAUNCH_CHECK();
+        if (fuse_tail) {
+            // attention backward + dh1 = dq_total . Wq + cell-1 backward in ONE launch (attn_tail.h)
+            LasAttnCellTail tl{};
+            tl.wq_bf16 = Wqb; tl.DO = DO; tl.G = b1.G; tl.dh_b = b1.dh_b; tl.ld_b = b1.ld_b; tl.stride_b = b1.stride_b; tl.nsplit_b = b1.nsplit_b;
+            tl.mask = b1.mask; tl.c = b1.c; tl.ld_c = b1.ld_c; tl.c_prev = b1.c_prev; tl.ld_cp = b1.ld_cp; tl.dc = b1.dc; tl.Gb = b1.Gb;
+            tl.first = b1.first;
+            RC(las_attn_step_bwd_cell(&at, &tl, st));
+        } else {
+            RC(las_attn_step_bwd_f32(&at, st));
+            // dh1_t (dropped) = dq_total . Wq  (+ recurrent path, added inside cell_bwd)
+            if (tc) RC(las_tc_plan_launch(&bq1, rn, dh1, DO, nullptr, nullptr, st));
+            else RC(gemm(st, dQCn, 2 * P, s->wq, DO, 0, dh1, DO, B, DO, P));
+            LAS_CUDA(las_launch(cell_bwd_kernel, dim3(ceil_div(B * DO, 256)), dim3(256), 0, st, b1));
+            LAS_LAUNCH_CHECK();
+        }
         // dS1[t] = dG1_t . Wcat1  -> [dh0_t | dh1_{t-1}]
         if (tc) RC(las_tc_plan_launch_split(&bq2, t, dS1, K1, skb1, st));
         else RC(gemm(st, b1.G, 4 * DO, Wcat1, K1, 0, dS1, K1, B, K1, 4 * DO));

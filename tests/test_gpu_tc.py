@@ -446,3 +446,37 @@ def test_persistent_decoder_greedy_matches_launch_per_stage_loop(monkeypatch):
     scale = np.abs(lb[:, 0]).max()
     assert np.abs(la[:, 0] - lb[:, 0]).max() < 5e-3 * max(1.0, scale)
     assert (ca == cb).mean() > 0.9
+
+
+@pytest.mark.parametrize('T,lx', [(72, [72, 40, 8]), (640, [640, 512, 77])])
+def test_fused_backward_step_matches_separate_launches(T, lx, monkeypatch):
+    """Backward decoder step: attention backward + dh1 = dq . Wq + LSTMCell-1 backward in ONE launch (csrc/attn_tail.h; one CTA per
+    row at T_enc = 9, a CTA pair per row at T_enc = 80) against the three separate launches (LAS_BWD_FUSE_TAIL=0), same masks.  The fused
+    form multiplies the fp32 dq by the bf16 weights, the separate GEMM rounds dq to bf16 first: not bit-identical, so both are also
+    measured against the fp32-mode gradients of the same model and masks -- the fused step must not be further away."""
+    from las_b200.models import ListenAttendSpell
+    sd = gu.make_state_dict(gu.get_config('best'), 21)
+    B, L = len(lx), 7
+    x, lxa, y = gu.make_inputs(22, B, T, L, lx=lx)
+    ly = torch.tensor([L, L - 2, 3][:B])
+    grads = {}
+    for name, fuse, amp in (('fp32', '1', False), ('fused', '1', True), ('separate', '0', True)):
+        monkeypatch.setenv('LAS_BWD_FUSE_TAIL', fuse)
+        torch.manual_seed(5)
+        model = ListenAttendSpell(**gu.get_config('best', mid_dropout=0.3, dec_lstm_dropout=0.3)).to(DEV).train()
+        model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
+            logits, _ = model(torch.from_numpy(x).to(DEV), torch.from_numpy(lxa), torch.from_numpy(y).to(DEV), 1.0, False)
+        mask = (torch.arange(L)[None, :] < ly[:, None]).to(DEV)
+        loss = (torch.nn.functional.cross_entropy(logits.float().reshape(-1, 30), torch.from_numpy(y).to(DEV).reshape(-1), reduction='none')
+                * mask.reshape(-1)).sum() / mask.sum()
+        loss.backward()
+        grads[name] = {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None}
+    assert set(grads['fused']) == set(grads['separate']) == set(grads['fp32'])
+    gmax = max(float(np.abs(v).max()) for v in grads['fp32'].values())
+    err = {n: max((rel_err(grads[n][k], grads['fp32'][k], 1e-2 * gmax), k) for k in grads['fp32']) for n in ('fused', 'separate')}
+    ab = max((rel_err(grads['fused'][k], grads['separate'][k], 1e-2 * gmax), k) for k in grads['fp32'])
+    print(f'backward step vs fp32 mode: fused {err["fused"]}, separate {err["separate"]}; fused vs separate {ab}')
+    assert ab[0] > 0.0, 'both runs took the same path'
+    assert ab[0] < 1e-2, ab
+    assert err['fused'][0] < 1.25 * err['separate'][0] + 1e-3, err
