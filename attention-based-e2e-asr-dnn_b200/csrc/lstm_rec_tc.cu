@@ -45,6 +45,8 @@ struct RecTcArgs {
     const __nv_bfloat16* w_gl;  // W_hh bf16 (ndir, 4H, H) for the TMEM-resident-A variant
     int w_tmem;            // 1: W_hh slice lives in TMEM (A operand from tensor memory); 0: in shared memory
     long long* dbg;        // optional (debug): per-step clock64 stamps of CTA (0,0,0), 16 slots per step
+    unsigned* progress;    // optional (DSMEM kernel): one word per cluster (dir * gridDim.y + batch-slice group); every CTA adds 1 each time
+    int progress_every;    //   its stores of another `progress_every` steps are visible device-wide (las_lstm_rec_fwd_arm_progress)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -592,6 +594,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
                 const int t = (dir == 0) ? s : (T - 1 - s);
                 if (s + 1 < T) load_x(s + 1);                                      // in flight while waiting below
                 asm volatile("bar.sync 2, 224;" ::: "memory");                    // `ex` of step s complete (and xgs[s & 1] consumed)
+                // the epilogue warps stored h / c / out of step s-1 before arriving at that barrier: every `progress_every` steps one
+                // helper thread makes them visible device-wide and counts this CTA in (a consumer on another stream waits for the
+                // cluster's count: the next layer's gate GEMM starts on the rows both directions have passed)
+                if (a.progress && warp == 0 && lane == 0 && s > 0 && s % a.progress_every == 0) {
+                    __threadfence();
+                    atomicAdd(a.progress + dir * gridDim.y + sg, 1u);
+                }
                 if (a.save) {
                     float* gb = a.gates + ((long long)t * a.ndir + dir) * 4 * H + r * UNITS + c4;
                     for (int grp = hw; grp < 32; grp += 3) {
@@ -848,6 +857,42 @@ extern "C" size_t las_lstm_rec_tc_workspace_bytes(int B, int H, int ndir) {
     return 1024 + (size_t)ndir * 2 * 4 * nsl * NB_SLICE * H * 4;
 }
 
+// ---- forward progress counters (next layer's gate GEMM pipelined behind this layer's recurrence) ----
+static thread_local unsigned* t_prog_ctr = nullptr;
+static thread_local int t_prog_every = 0, t_prog_clusters = 0, t_prog_rs = 0;
+extern "C" void las_lstm_rec_fwd_arm_progress(void* counters, int every) {
+    t_prog_ctr = (unsigned*)counters;
+    t_prog_every = every;
+    t_prog_clusters = 0;
+    t_prog_rs = 0;
+}
+extern "C" int las_lstm_rec_fwd_progress_info(int* clusters, int* ctas_per_cluster) {
+    if (clusters) *clusters = t_prog_clusters;
+    if (ctas_per_cluster) *ctas_per_cluster = t_prog_rs;
+    return t_prog_clusters > 0 ? 1 : 0;
+}
+typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static WaitValue32Fn get_wait_value32() {
+    // (driver entry point looked up at run time: the library must load on machines without libcuda, e.g. for the CPU-side ABI tests)
+    static WaitValue32Fn fn = nullptr;
+    if (!fn) {
+        void* pfn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &pfn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (WaitValue32Fn)pfn;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+extern "C" int las_stream_wait_value_geq(void* stream, const void* dev_word, unsigned value) {
+    WaitValue32Fn fn = get_wait_value32();
+    if (!fn) { las_set_error("cuStreamWaitValue32 is not available"); return LAS_ERR_UNSUPPORTED; }
+    const CUresult rc = fn((CUstream)stream, (CUdeviceptr)dev_word, value, CU_STREAM_WAIT_VALUE_GEQ);
+    if (rc != CUDA_SUCCESS) { las_set_error("cuStreamWaitValue32 failed (%d)", (int)rc); return LAS_ERR_CUDA; }
+    return LAS_OK;
+}
+
 static int rec_fwd_tc_impl(float* gates, const void* w_hh_bf16, const int* lens, const float* drop_mask, float* out, float* hs_pad,
                            float* cs_pad, int B, int T, int H, int ndir, int save_gates, void* ws, size_t ws_bytes,
                            __nv_bfloat16* out16, __nv_bfloat16* hs16, void* stream) {
@@ -860,6 +905,10 @@ static int rec_fwd_tc_impl(float* gates, const void* w_hh_bf16, const int* lens,
     if (rc) return rc;
     if (ws_bytes < las_lstm_rec_tc_workspace_bytes(B, H, ndir)) { las_set_error("lstm_rec_fwd_tc: workspace too small"); return LAS_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
+    // a progress request is for THIS launch only (one chain per CTA, DSMEM kernel); anything else leaves progress_info() at 0 clusters
+    unsigned* prog_ctr = t_prog_ctr;
+    const int prog_every = t_prog_every;
+    t_prog_ctr = nullptr; t_prog_every = 0; t_prog_clusters = 0; t_prog_rs = 0;
     {
         // LAS_REC_SPLIT_BATCH=1: with more batch slices than one chain per CTA allows (B > 128 at H = 512), run the rows in passes of
         // `bsg` slices with the one-chain DSMEM kernel (every array is batch-major: a pass is a pointer offset).  Measured SLOWER at
@@ -931,8 +980,15 @@ static int rec_fwd_tc_impl(float* gates, const void* w_hh_bf16, const int* lens,
                 if (e1 == cudaSuccess && nclusters < 1) e1 = cudaErrorInvalidConfiguration;
                 if (e1 == cudaSuccess) {
                     LasProfScope prof(LAS_PROF_REC_FWD, stream, (double)T);
+                    const bool publish = prog_ctr && prog_every > 0 && p.bsg * ndir <= 64;
+                    a.progress = publish ? prog_ctr : nullptr; a.progress_every = prog_every;
                     e1 = cudaLaunchKernelEx(&cfg, kd, a);
-                    if (e1 == cudaSuccess) { las_count_launch(1); return LAS_OK; }
+                    if (e1 == cudaSuccess) {
+                        if (publish) { t_prog_clusters = p.bsg * ndir; t_prog_rs = p.rs; }
+                        las_count_launch(1);
+                        return LAS_OK;
+                    }
+                    a.progress = nullptr;
                 }
             }
             cudaGetLastError();         // fall through to the global-memory exchange
@@ -2161,17 +2217,7 @@ static int launch_bwd_dsm(const float* dout, float* gates, void* dgates_bf16, co
         return LAS_ERR_UNSUPPORTED;
     }
     if (a.start_ctr) {
-        // (driver entry point looked up at run time: the library must load on machines without libcuda, e.g. for the CPU-side ABI tests)
-        typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-        static WaitValue32Fn wait_value32 = nullptr;
-        if (!wait_value32) {
-            void* pfn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &pfn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-                wait_value32 = (WaitValue32Fn)pfn;
-            else
-                cudaGetLastError();
-        }
+        WaitValue32Fn wait_value32 = get_wait_value32();
         if (wait_value32 && wait_value32((CUstream)t_start_stream, (CUdeviceptr)a.start_ctr, target, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS) {
             t_start_armed = false;
             t_start_mode = 1;

@@ -312,9 +312,126 @@ def _lstm_weight_grads(dGb, xb, hs, dG, dbp, dims, max_ctas=0, clone_bias=True):
 # One (Bi)LSTM layer over a padded batch with PackedSequence semantics (+ optional pyramidal frame-pair concat and
 # locked dropout): reference src/modules.py:74-84 (LockedLSTM loop body) and :165-193 (pyramLockedLSTM loop body).
 # ----------------------------------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------------------------------
+# Forward pipelining: the NEXT layer's gate projection beside this layer's recurrence.
+#
+# The forward recurrence is latency bound and occupies rs * slices * ndir SMs (96 of 148 at B = 96, H = 512).  The next layer's input
+# GEMM (reference: inside nn.LSTM, src/modules.py:80 / :189) needs, for output row t, this layer's output at time t (frames 2t, 2t+1
+# under the pyramid) from BOTH directions -- available once the forward direction has passed it and the reverse direction has come
+# back to it, i.e. from the middle of the sequence outwards.  The recurrence kernel publishes per-cluster progress counters
+# (las_lstm_rec_fwd_arm_progress); the GEMM is issued as 128-row time tiles on the second stream, each behind a cuStreamWaitValue32 on
+# those counters, in the order the tiles become ready.  The tiles only the last steps release run after the kernel.  The consumer
+# (the next lstm_layer call) finds the finished gates on its input tensor (`_las_pregates`) and waits for the second stream's event.
+# LAS_FWD_PIPELINE=0 switches it off.
+# ----------------------------------------------------------------------------------------------------------------------
+_PROGRESS_EVERY = 32
+_PIPE_TILE = 128
+
+
+class _PreGates:
+    __slots__ = ('gates', 'wcat', 'event', 'x16', 'wkey', 'pyramid', 'T', 'Kp', 'Dp', 'tiles_early', 'tiles_late')
+
+
+def _weights_key(weights) -> tuple:
+    return tuple((id(w), w._version) for w in weights)
+
+
+def _pipeline_ok(nxt, x16) -> bool:
+    return (nxt is not None and x16 is not None and os.environ.get('LAS_FWD_PIPELINE', '1') != '0'
+            and not torch.is_inference_mode_enabled())
+
+
+def _pipeline_prepare(nxt, Bn, F_, dev):
+    """Main stream, BEFORE the recurrence launch: the next layer's bf16 weights / biases / output buffer and the progress counters."""
+    ws = [_f32c(w) for w in nxt['weights']]
+    ndir = len(ws) // 4
+    H = ws[1].shape[1]
+    G4 = 4 * H
+    NG = ndir * G4
+    pyr = bool(nxt['pyramid'])
+    Dp = F_
+    Kp = 2 * Dp if pyr else Dp
+    if Dp % 8 != 0 or Dp < 64 or ws[0].shape[1] != Kp:
+        return None
+    wcat = torch.empty(NG, Kp, dtype=torch.bfloat16, device=dev)
+    for d in range(ndir):
+        cast_bf16(ws[4 * d], G4, Kp, Kp, Kp, dst=wcat, dst_off=d * G4 * Kp)
+    b1 = torch.cat([ws[4 * d + 2] for d in range(ndir)])
+    b2 = torch.cat([ws[4 * d + 3] for d in range(ndir)])
+    Tn = int(nxt['T'])
+    gates = torch.empty(Bn, Tn, ndir, G4, dtype=torch.float32, device=dev)
+    counters = torch.zeros(64, dtype=torch.int32, device=dev)
+    return dict(wcat=wcat, b1=b1, b2=b2, gates=gates, counters=counters, NG=NG, Kp=Kp, Dp=Dp, Tn=Tn, pyr=pyr, ndir=ndir, H=H)
+
+
+def _pipeline_issue(prep, nxt, out16, Bn, T, ev_ready, ev_rec_done):
+    """After the recurrence launch: the tiles of the next layer's gate GEMM on the second stream, behind the progress counters."""
+    lib = _lib.load()
+    ncl, rs = C.c_int(0), C.c_int(0)
+    publishes = bool(lib.las_lstm_rec_fwd_progress_info(C.byref(ncl), C.byref(rs)))
+    dev = out16.device
+    side = _overlap_state(dev).side
+    fac = 2 if prep['pyr'] else 1
+    Tn, NG, Kp, Dp = prep['Tn'], prep['NG'], prep['Kp'], prep['Dp']
+    kmax = (T - 1) // _PROGRESS_EVERY
+    tiles = []
+    for t0 in range(0, Tn, _PIPE_TILE):
+        t1 = min(t0 + _PIPE_TILE, Tn)
+        ready = max(fac * t1, T - fac * t0)                         # recurrence steps < ready must be complete (both directions)
+        k = -(-ready // _PROGRESS_EVERY)
+        tiles.append((k if (publishes and k <= kmax) else None, t0, t1))
+    early = sorted([t for t in tiles if t[0] is not None])
+    late = [t for t in tiles if t[0] is None]
+    xb = out16.view(Bn * T, -1)
+    a_s1 = 2 * Dp if prep['pyr'] else Dp
+
+    def tile_gemm(t0, t1):
+        R = t1 - t0
+        gemm_tc(xb, prep['wcat'], prep['gates'], R, NG, Kp, a_batches=Bn, a_s1=a_s1, a_s2=T * Dp, b_s1=Kp, c_bs=Tn * NG, ldc=NG,
+                bias1=prep['b1'], bias2=prep['b2'], a_off=t0 * a_s1, c_off=t0 * NG, flops=2.0 * Bn * R * NG * Kp)
+
+    cptr = prep['counters'].data_ptr()
+    with torch.cuda.stream(side):
+        side.wait_event(ev_ready)
+        waited = 0
+        for k, t0, t1 in early:
+            if k > waited:
+                for c in range(ncl.value):
+                    check(lib.las_stream_wait_value_geq(side.cuda_stream, cptr + 4 * c, rs.value * k), 'stream_wait_value')
+                waited = k
+            tile_gemm(t0, t1)
+        side.wait_event(ev_rec_done)
+        for _, t0, t1 in late:
+            tile_gemm(t0, t1)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    pre = _PreGates()
+    pre.gates, pre.wcat, pre.event, pre.x16 = prep['gates'], prep['wcat'], ev, out16
+    pre.wkey, pre.pyramid, pre.T, pre.Kp, pre.Dp = _weights_key(nxt['weights']), prep['pyr'], Tn, Kp, Dp
+    pre.tiles_early, pre.tiles_late = len(early), len(late)
+    # allocated on the main stream, used on the second one: the allocator must not hand the memory out again before that stream is done
+    # (the stream waits on the counters may still be pending when this function returns; the gates may never be taken over)
+    for t in (prep['counters'], prep['b1'], prep['b2'], prep['wcat'], prep['gates'], out16):
+        t.record_stream(side)
+    return pre
+
+
+def _pregates_for(x, x16, pyramid, T, weights):
+    """The gates a previous lstm_layer call already projected for THIS layer (same input tensor, unchanged since; same weights)."""
+    pre = getattr(x, '_las_pregates', None)
+    if pre is None or x16 is None or pre.x16.data_ptr() != x16.data_ptr() or pre.pyramid != bool(pyramid) or pre.T != int(T):
+        return None
+    if pre.wkey != _weights_key(weights):
+        return None
+    return pre
+
+
+last_pipeline_stats = {}
+
+
 class LSTMLayerFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, lens_dev, T, pyramid, mask, x16, wrefs, *weights):
+    def forward(ctx, x, lens_dev, T, pyramid, mask, x16, wrefs, nxt, pre, *weights):
         """x (B, Tin, D) fp32 with contiguous features; lens_dev (B) int32 = lengths AFTER the pyramid halving;
         T = max of those lengths; weights = (w_ih, w_hh, b_ih, b_hh) per direction."""
         _require_cuda(x, lens_dev, *weights)
@@ -358,13 +475,19 @@ class LSTMLayerFunction(torch.autograd.Function):
                 xb = x16.view(Bn * Tin, D)                                                # written by the producing recurrence kernel
             else:
                 xb = cast_bf16(x, Bn * Tin, D, Dp, st, inner=Tin, bs=sb)                  # (B*Tin, Dp) bf16, compact
-            wcat = torch.empty(NG, Kp, dtype=torch.bfloat16, device=dev)
-            for d in range(ndir):
-                cast_bf16(ws[4 * d], G4, Din, Kp, Din, dst=wcat, dst_off=d * G4 * Kp)
-            b1 = torch.cat([ws[4 * d + 2] for d in range(ndir)])
-            b2 = torch.cat([ws[4 * d + 3] for d in range(ndir)])
-            gemm_tc(xb, wcat, gates, T, NG, Kp, a_batches=Bn, a_s1=(2 * Dp if pyramid else Dp), a_s2=Tin * Dp, b_s1=Kp,
-                    c_bs=T * NG, ldc=NG, bias1=b1, bias2=b2, lens=lens_dev, flops=2.0 * Bn * T * NG * Din)
+            if pre is not None and pre.Kp == Kp and pre.Dp == Dp and xb.data_ptr() == pre.x16.data_ptr() \
+                    and tuple(pre.gates.shape) == tuple(gates.shape):
+                # projected beside the previous layer's recurrence (second stream): take it over once that stream is done
+                gates, wcat = pre.gates, pre.wcat
+                torch.cuda.current_stream(dev).wait_event(pre.event)
+            else:
+                wcat = torch.empty(NG, Kp, dtype=torch.bfloat16, device=dev)
+                for d in range(ndir):
+                    cast_bf16(ws[4 * d], G4, Din, Kp, Din, dst=wcat, dst_off=d * G4 * Kp)
+                b1 = torch.cat([ws[4 * d + 2] for d in range(ndir)])
+                b2 = torch.cat([ws[4 * d + 3] for d in range(ndir)])
+                gemm_tc(xb, wcat, gates, T, NG, Kp, a_batches=Bn, a_s1=(2 * Dp if pyramid else Dp), a_s2=Tin * Dp, b_s1=Kp,
+                        c_bs=T * NG, ldc=NG, bias1=b1, bias2=b2, lens=lens_dev, flops=2.0 * Bn * T * NG * Din)
         else:
             for d in range(ndir):
                 w_ih, _, b_ih, b_hh = ws[4 * d:4 * d + 4]
@@ -385,14 +508,26 @@ class LSTMLayerFunction(torch.autograd.Function):
         out = torch.empty(Bn, T, F_, dtype=torch.float32, device=dev) if mask is not None else None
         if mask is not None:
             mask = _f32c(mask).reshape(Bn, F_)
+        pre_next = None
         if rec_tc:
             # tensor-pipe recurrence: W_hh as bf16 (ndir*4H, H), resident in shared memory inside the kernel
             w_hh_b = cast_bf16(w_hh, ndir * G4, H, H, H)
             nbytes = lib.las_lstm_rec_tc_workspace_bytes(Bn, H, ndir)
             wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            prep = _pipeline_prepare(nxt, Bn, F_, dev) if _pipeline_ok(nxt, out16) else None
+            if prep is not None:
+                main = torch.cuda.current_stream(dev)
+                ev_ready = torch.cuda.Event()
+                ev_ready.record(main)
+                lib.las_lstm_rec_fwd_arm_progress(prep['counters'].data_ptr(), _PROGRESS_EVERY)
             check(lib.las_lstm_rec_fwd_tc_ex(gates.data_ptr(), w_hh_b.data_ptr(), lens_dev.data_ptr(), ptr(mask), ptr(out),
                                              ptr(hs_pad), cs_pad.data_ptr(), Bn, T, H, ndir, int(train), wsb.data_ptr(),
                                              nbytes, ptr(out16), ptr(hs16), stream_ptr()), 'lstm_rec_fwd_tc')
+            if prep is not None:
+                ev_rec_done = torch.cuda.Event()
+                ev_rec_done.record(main)
+                pre_next = _pipeline_issue(prep, nxt, out16, Bn, T, ev_ready, ev_rec_done)
+                last_pipeline_stats[(Bn, T, H)] = (pre_next.tiles_early, pre_next.tiles_late)
         else:
             nbytes = lib.las_lstm_rec_workspace_bytes(Bn, H, ndir)
             wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -408,6 +543,8 @@ class LSTMLayerFunction(torch.autograd.Function):
         y = out if out is not None else hs_pad[:, 1:T + 1]
         if out16 is not None:
             ctx.mark_non_differentiable(out16)
+        ctx.pre_next = None
+        LSTMLayerFunction._handoff = pre_next          # picked up by lstm_layer right after apply() (not a tensor: cannot be returned)
         return y, out16
 
     @staticmethod
@@ -494,9 +631,9 @@ class LSTMLayerFunction(torch.autograd.Function):
                 for w in wrefs:                            # the reducer's autograd hook must not count the None returned below
                     w._las_deferred = True
                 ovl.pending.append(run)
-                return (dx, None, None, None, None, None, None, *([None] * (4 * ndir)))
+                return (dx, None, None, None, None, None, None, None, None, *([None] * (4 * ndir)))
             grads = _lstm_weight_grads(dGb, xb, hs_pad, dG, dbp, wdims)
-            return (dx, None, None, None, None, None, None, *grads)
+            return (dx, None, None, None, None, None, None, None, None, *grads)
         if ctx.needs_input_grad[0]:
             full = (Tin * D == T * Din)
             dx = (torch.empty if full else torch.zeros)(Bn, Tin, D, dtype=torch.float32, device=dev)
@@ -514,12 +651,20 @@ class LSTMLayerFunction(torch.autograd.Function):
             db = torch.empty(G4, dtype=torch.float32, device=dev)
             colsum(dG, NG, M, G4, db, x_off=d * G4)
             grads += [dw_ih, dw_hh, db, db.clone()]
-        return (dx, None, None, None, None, None, None, *grads)
+        return (dx, None, None, None, None, None, None, None, None, *grads)
 
 
-def lstm_layer(x, lens_dev, T, pyramid, mask, weights: Sequence[torch.Tensor]):
-    y, y16 = LSTMLayerFunction.apply(x, lens_dev, int(T), bool(pyramid), mask, _bf16_shadow(x), tuple(weights), *weights)
+def lstm_layer(x, lens_dev, T, pyramid, mask, weights: Sequence[torch.Tensor], next_layer: Optional[dict] = None):
+    """next_layer (optional): dict(weights=<the following layer's 4*ndir tensors>, pyramid=bool, T=<its sequence length>) -- lets this
+    layer project the following layer's gates beside its own recurrence (see "Forward pipelining" above)."""
+    x16 = _bf16_shadow(x)
+    pre = _pregates_for(x, x16, pyramid, T, weights)
+    LSTMLayerFunction._handoff = None
+    y, y16 = LSTMLayerFunction.apply(x, lens_dev, int(T), bool(pyramid), mask, x16, tuple(weights), next_layer, pre, *weights)
     _attach_bf16_shadow(y, y16)
+    handoff, LSTMLayerFunction._handoff = LSTMLayerFunction._handoff, None
+    if handoff is not None and y16 is not None and getattr(y, '_las_bf16', None) is not None:
+        y._las_pregates = handoff
     return y
 
 

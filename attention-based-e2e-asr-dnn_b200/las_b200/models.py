@@ -38,6 +38,9 @@ class Listener(nn.Module):
                                        bidirectional=self.bidirectional, mid_dropout=self.mid_dropout,
                                        final_dropout=self.final_dropout)
 
+        # the base stack's last layer feeds the pyramid's first: told through the instance dict so that no submodule gets registered twice
+        self.base.__dict__['_las_next'] = self.pyramid
+
     def forward(self, x, lx):
         return self.pyramid(*self.base(x, lx))
 

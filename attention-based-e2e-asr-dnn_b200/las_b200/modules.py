@@ -56,6 +56,14 @@ def _lstm_weights(lstm: nn.LSTM):
     return ws
 
 
+def _first_layer_hint(block, lx):
+    """next_layer hint for the layer that feeds `block` (a pyramLockedLSTM: its first layer halves the time axis)."""
+    if block is None or not isinstance(block, pyramLockedLSTM) or len(block.plstms) == 0:
+        return None
+    Tn = int((lx // 2).max())
+    return dict(weights=_lstm_weights(block.plstms[0]), pyramid=True, T=Tn) if Tn > 0 else None
+
+
 class LockedLSTM(nn.Module):
     """Stack of 1-layer (Bi)LSTMs with locked dropout -- reference src/modules.py:11-85."""
 
@@ -84,7 +92,12 @@ class LockedLSTM(nn.Module):
             lens_dev = lx.to(device=x.device, dtype=torch.int32, non_blocking=True)
             F_ = self.uniform_hid_dim * (int(self.bidirectional) + 1)
             mask = _locked_mask(x.size(0), F_, p, self.training, x.device)
-            x = LF.lstm_layer(x, lens_dev, T, False, mask, _lstm_weights(lstm))
+            # what consumes this layer's output (lets it project the consumer's gates beside its own recurrence, LF "Forward pipelining")
+            if i + 1 < len(self.lstms):
+                nxt = dict(weights=_lstm_weights(self.lstms[i + 1]), pyramid=False, T=T)
+            else:
+                nxt = _first_layer_hint(self.__dict__.get('_las_next'), lx)
+            x = LF.lstm_layer(x, lens_dev, T, False, mask, _lstm_weights(lstm), nxt)
         return x, lx.clone()
 
 
@@ -120,7 +133,10 @@ class pyramLockedLSTM(nn.Module):
             lens_dev = lx.to(device=x.device, dtype=torch.int32, non_blocking=True)
             F_ = self.uniform_hid_dim * (int(self.bidirectional) + 1)
             mask = _locked_mask(x.size(0), F_, p, self.training, x.device)
-            x = LF.lstm_layer(x, lens_dev, T, True, mask, _lstm_weights(plstm))
+            nxt = None
+            if i + 1 < len(self.plstms) and int((lx // 2).max()) > 0:
+                nxt = dict(weights=_lstm_weights(self.plstms[i + 1]), pyramid=True, T=int((lx // 2).max()))
+            x = LF.lstm_layer(x, lens_dev, T, True, mask, _lstm_weights(plstm), nxt)
         return x, lx.clone()
 
 

@@ -156,6 +156,20 @@ int las_lstm_rec_fwd_tc_ex(float* gates, const void* w_hh_bf16, const int* lens,
  * las_launch_start_mode(): 1 if the last armed call released side_stream at kernel start, 0 if at kernel end. */
 void las_set_launch_start_stream(void* side_stream);
 int las_launch_start_mode(void);
+
+/* Forward counterpart: progress counters of the tensor-pipe forward recurrence, so that the NEXT layer's gate projection
+ * (reference: the nn.LSTM input GEMM of src/modules.py:80 / :189 for layer l+1) can start on another stream, on the SMs the recurrence
+ * leaves idle, for the time rows BOTH directions have already passed -- instead of after the whole layer.
+ * las_lstm_rec_fwd_arm_progress(counters, every): the next las_lstm_rec_fwd_tc[_ex] call of this thread publishes: `counters` (>= 64
+ *   zeroed 32-bit words, device memory, zeroed by the caller on the launch stream) gets one word per cluster (direction x batch-slice
+ *   group); each CTA of the cluster adds 1 after every `every` steps once its outputs of those steps are visible device-wide.  Steps
+ *   < k*every of a cluster are complete when its word >= k * ctas_per_cluster.
+ * las_lstm_rec_fwd_progress_info(&clusters, &ctas_per_cluster): 1 if that launch publishes (clusters > 0); 0 if it ran a kernel that
+ *   does not (the caller then waits for the launch to finish, as without the request).
+ * las_stream_wait_value_geq(stream, word, value): cuStreamWaitValue32(GEQ) -- work queued on `stream` afterwards waits for the word. */
+void las_lstm_rec_fwd_arm_progress(void* counters, int every);
+int las_lstm_rec_fwd_progress_info(int* clusters, int* ctas_per_cluster);
+int las_stream_wait_value_geq(void* stream, const void* dev_word, unsigned value);
 /* debug aid: device buffer (256*16 long long) receiving clock64 stamps of CTA (0,0,0) per timestep; NULL disables */
 void las_lstm_rec_tc_set_debug(void* dev_buf);
 /* BPTT on the tensor pipe.  w_hh_t_bf16 = W_hh transposed per direction, (ndir, H, 4H) bf16 (las_transpose_cast_bf16).

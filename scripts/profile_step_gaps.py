@@ -54,3 +54,9 @@ small = collections.Counter();
 for g, n, _, _ in gaps:
     small[n.split('<')[0][:40]] += g
 for n, g in small.most_common(12): print(f'  total gap {g / 1e3:7.2f} ms before {n}')
+# per-kernel device time (sum of durations; kernels on the side stream overlap others, so the sum exceeds the busy time)
+tot = collections.Counter(); cnt = collections.Counter()
+for e in evs:
+    tot[e.name[:90]] += e.time_range.end - e.time_range.start; cnt[e.name[:90]] += 1
+print('per step (3 steps averaged):')
+for n, g in tot.most_common(40): print(f'  {g / 3e3:8.3f} ms  x{cnt[n] / 3:7.1f}  {n}')

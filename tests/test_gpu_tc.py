@@ -480,3 +480,34 @@ def test_fused_backward_step_matches_separate_launches(T, lx, monkeypatch):
     assert ab[0] > 0.0, 'both runs took the same path'
     assert ab[0] < 1e-2, ab
     assert err['fused'][0] < 1.25 * err['separate'][0] + 1e-3, err
+
+
+def test_forward_pipelining_is_bit_identical(monkeypatch):
+    """The next layer's gate projection issued as time tiles on the second stream behind the recurrence's progress counters
+    (functional.py "Forward pipelining") against the plain layer-after-layer order: same tiles of the same GEMM, so logits and every
+    gradient must be bit-identical; ragged lengths, yml dropouts."""
+    from las_b200 import functional as LF
+    from las_b200.models import ListenAttendSpell
+    sd = gu.make_state_dict(gu.get_config('best'), 31)
+    B, T, L = 4, 1280, 5
+    x, lxa, y = gu.make_inputs(32, B, T, L, lx=[1280, 1100, 640, 37])
+    res = {}
+    for pipe in ('1', '0'):
+        monkeypatch.setenv('LAS_FWD_PIPELINE', pipe)
+        LF.last_pipeline_stats.clear()
+        torch.manual_seed(6)
+        model = ListenAttendSpell(**gu.get_config('best', init_dropout=0.3, mid_dropout=0.3, final_dropout=0.35)).to(DEV).train()
+        model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            logits, _ = model(torch.from_numpy(x).to(DEV), torch.from_numpy(lxa), torch.from_numpy(y).to(DEV), 1.0, False)
+        logits.float().square().mean().backward()
+        torch.cuda.synchronize()
+        res[pipe] = (logits.detach().cpu().numpy().copy(), {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None},
+                     dict(LF.last_pipeline_stats))
+    stats = res['1'][2]
+    print('pipelined tiles (early, late) per layer:', stats)
+    assert stats and sum(e for e, _ in stats.values()) >= 3, stats        # tiles that really ran beside a recurrence
+    assert not res['0'][2]
+    assert np.array_equal(res['1'][0], res['0'][0])
+    for k in res['0'][1]:
+        assert np.array_equal(res['1'][1][k], res['0'][1][k]), k
