@@ -866,6 +866,16 @@ extern "C" void las_lstm_rec_fwd_arm_progress(void* counters, int every) {
     t_prog_clusters = 0;
     t_prog_rs = 0;
 }
+// backward: the BPTT kernel publishes the same way (steps < k * every of a cluster have their d(pre-activation) rows in the bf16
+// gate-gradient matrix when its word >= k * ctas_per_cluster); las_lstm_rec_fwd_progress_info reports the last armed launch of either kind
+static thread_local unsigned* t_bprog_ctr = nullptr;
+static thread_local int t_bprog_every = 0;
+extern "C" void las_lstm_rec_bwd_arm_progress(void* counters, int every) {
+    t_bprog_ctr = (unsigned*)counters;
+    t_bprog_every = every;
+    t_prog_clusters = 0;
+    t_prog_rs = 0;
+}
 extern "C" int las_lstm_rec_fwd_progress_info(int* clusters, int* ctas_per_cluster) {
     if (clusters) *clusters = t_prog_clusters;
     if (ctas_per_cluster) *ctas_per_cluster = t_prog_rs;
@@ -1049,6 +1059,8 @@ struct RecTcBwdArgs {
                               // d(pre-activation) write-back into `gates` is skipped (its only reader was the bias column sum)
     long long* dbg;
     unsigned* start_ctr;      // optional: every CTA adds 1 when it starts (a second stream waits for the sum, see las_set_launch_start_stream)
+    unsigned* progress;       // optional (DSMEM kernel): per-cluster progress words, see las_lstm_rec_bwd_arm_progress
+    int progress_every;
 };
 
 constexpr uint32_t IDESC_BWD = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UNITS >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
@@ -1360,6 +1372,7 @@ static int rec_bwd_tc_impl(const float* dout, float* gates, void* dgates_bf16, c
     if (rc) return rc;
     if (ws_bytes < las_lstm_rec_tc_workspace_bytes(B, H, ndir)) { las_set_error("lstm_rec_bwd_tc: workspace too small"); return LAS_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
+    struct DisarmProgress { ~DisarmProgress() { t_bprog_ctr = nullptr; t_bprog_every = 0; } } disarm_progress;      // the request is for this call only
     static thread_local int depth = 0;
     struct Depth { Depth() { ++depth; } ~Depth() { --depth; } } depth_scope;
     StartEventScope start_event_scope(st, depth == 1);
@@ -1368,6 +1381,7 @@ static int rec_bwd_tc_impl(const float* dout, float* gates, void* dgates_bf16, c
         const char* sb = getenv("LAS_REC_SPLIT_BATCH");
         const char* de = getenv("LAS_REC_DSMEM");
         if (p.chains > 1 && !dbp && (sb && atoi(sb) == 1) && !(de && atoi(de) == 0) && H % 128 == 0 && H <= 512) {
+            t_bprog_ctr = nullptr;          // per-pass launches: no whole-batch progress
             const int rows = p.bsg * NB_SLICE;
             const long long F = (long long)ndir * H;
             for (int b0 = 0; b0 < B; b0 += rows) {
@@ -2121,6 +2135,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
                 if (te == 0) REC_STAMP(10);
             }
         }
+        // progress for a consumer on another stream (the dX GEMM of this layer, tile by tile): the epilogue warps have stored the bf16
+        // gate gradients of step s; warp 0 (idle in this kernel) makes them visible device-wide and counts the CTA in
+        if (a.progress && (s + 1) % a.progress_every == 0) {
+            if (warp >= 4) {
+                asm volatile("bar.arrive 5, 160;" ::: "memory");
+            } else if (warp == 0) {
+                asm volatile("bar.sync 5, 160;" ::: "memory");
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(a.progress + dir * gridDim.y + sg, 1u);
+                }
+            }
+        }
     }
     if (a.dbp) {
         // bias gradients: the four epilogue warps hold partial sums of the same 32 units over different batch rows; add them up in
@@ -2179,6 +2206,7 @@ static int launch_bwd_dsm(const float* dout, float* gates, void* dgates_bf16, co
     a.dbg = g_rec_dbg; a.Bpad = nslices * NB_SLICE;
     a.w_t = (const __nv_bfloat16*)w_hh_t_bf16;
     a.dbp = dbp;
+    if (t_bprog_ctr && t_bprog_every > 0 && nslices * ndir <= 64) { a.progress = t_bprog_ctr; a.progress_every = t_bprog_every; }
     auto kd = lstm_rec_bwd_dsm_kernel;
     if (cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return LAS_ERR_UNSUPPORTED; }
     if (rs > 8 && cudaFuncSetAttribute(kd, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return LAS_ERR_UNSUPPORTED; }
@@ -2223,6 +2251,7 @@ static int launch_bwd_dsm(const float* dout, float* gates, void* dgates_bf16, co
             t_start_mode = 1;
         }                           // else: still armed -> the caller's scope makes the side stream wait for completion
     }
+    if (a.progress) { t_prog_clusters = nslices * ndir; t_prog_rs = rs; }
     las_count_launch(1);
     return LAS_OK;
 }

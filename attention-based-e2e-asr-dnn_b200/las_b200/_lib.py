@@ -137,6 +137,7 @@ SIGNATURES = {
     'las_set_launch_start_stream': (None, [C.c_void_p]),
     'las_launch_start_mode': (C.c_int, []),
     'las_lstm_rec_fwd_arm_progress': (None, [C.c_void_p, C.c_int]),
+    'las_lstm_rec_bwd_arm_progress': (None, [C.c_void_p, C.c_int]),
     'las_lstm_rec_fwd_progress_info': (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'las_stream_wait_value_geq': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint]),
     'las_lstm_rec_fwd_tc_ex': (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -250,6 +250,17 @@ def _overlap_state(dev: torch.device) -> _BackwardOverlap:
     return st
 
 
+_DGRAD_STREAMS: dict = {}
+
+
+def _dgrad_stream(dev: torch.device) -> torch.cuda.Stream:
+    """Third stream (high priority: its work is on the critical path of backward, the weight gradients on the second stream are not)."""
+    st = _DGRAD_STREAMS.get(dev.index)
+    if st is None:
+        st = _DGRAD_STREAMS[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
+    return st
+
+
 def _overlap_finish():
     """End of the backward pass (autograd engine callback, caller's thread): issue what is still queued, join the streams."""
     for st in _OVERLAP.values():
@@ -364,6 +375,41 @@ def _pipeline_prepare(nxt, Bn, F_, dev):
     return dict(wcat=wcat, b1=b1, b2=b2, gates=gates, counters=counters, NG=NG, Kp=Kp, Dp=Dp, Tn=Tn, pyr=pyr, ndir=ndir, H=H)
 
 
+def _issue_tiles(stream, counters, ncl, rs, early, late, ev_ready, ev_done, tile_fn):
+    """`early` = [(k, t0, t1)] sorted by k: tile_fn(t0, t1) runs on `stream` once every cluster's progress word is >= rs * k;
+    `late` tiles run after `ev_done` (the recurrence kernel has finished).  Returns the event recorded behind the last tile."""
+    lib = _lib.load()
+    cptr = counters.data_ptr()
+    with torch.cuda.stream(stream):
+        stream.wait_event(ev_ready)
+        waited = 0
+        for k, t0, t1 in early:
+            if k > waited:
+                for c in range(ncl):
+                    check(lib.las_stream_wait_value_geq(stream.cuda_stream, cptr + 4 * c, rs * k), 'stream_wait_value')
+                waited = k
+            tile_fn(t0, t1)
+        stream.wait_event(ev_done)
+        for _, t0, t1 in late:
+            tile_fn(t0, t1)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+    return ev
+
+
+def _time_tiles(Tn, T, fac, publishes):
+    """128-row time tiles [t0, t1) of a (B, Tn) row space whose row t needs recurrence steps < max(fac*t1, T - fac*t0) of BOTH
+    directions; (k, t0, t1) with k = the progress count to wait for, None when only the end of the kernel releases the tile."""
+    kmax = (T - 1) // _PROGRESS_EVERY
+    tiles = []
+    for t0 in range(0, Tn, _PIPE_TILE):
+        t1 = min(t0 + _PIPE_TILE, Tn)
+        ready = max(fac * t1, T - fac * t0)
+        k = -(-ready // _PROGRESS_EVERY)
+        tiles.append((k if (publishes and k <= kmax) else None, t0, t1))
+    return sorted([t for t in tiles if t[0] is not None]), [t for t in tiles if t[0] is None]
+
+
 def _pipeline_issue(prep, nxt, out16, Bn, T, ev_ready, ev_rec_done):
     """After the recurrence launch: the tiles of the next layer's gate GEMM on the second stream, behind the progress counters."""
     lib = _lib.load()
@@ -373,15 +419,7 @@ def _pipeline_issue(prep, nxt, out16, Bn, T, ev_ready, ev_rec_done):
     side = _overlap_state(dev).side
     fac = 2 if prep['pyr'] else 1
     Tn, NG, Kp, Dp = prep['Tn'], prep['NG'], prep['Kp'], prep['Dp']
-    kmax = (T - 1) // _PROGRESS_EVERY
-    tiles = []
-    for t0 in range(0, Tn, _PIPE_TILE):
-        t1 = min(t0 + _PIPE_TILE, Tn)
-        ready = max(fac * t1, T - fac * t0)                         # recurrence steps < ready must be complete (both directions)
-        k = -(-ready // _PROGRESS_EVERY)
-        tiles.append((k if (publishes and k <= kmax) else None, t0, t1))
-    early = sorted([t for t in tiles if t[0] is not None])
-    late = [t for t in tiles if t[0] is None]
+    early, late = _time_tiles(Tn, T, fac, publishes)
     xb = out16.view(Bn * T, -1)
     a_s1 = 2 * Dp if prep['pyr'] else Dp
 
@@ -390,21 +428,7 @@ def _pipeline_issue(prep, nxt, out16, Bn, T, ev_ready, ev_rec_done):
         gemm_tc(xb, prep['wcat'], prep['gates'], R, NG, Kp, a_batches=Bn, a_s1=a_s1, a_s2=T * Dp, b_s1=Kp, c_bs=Tn * NG, ldc=NG,
                 bias1=prep['b1'], bias2=prep['b2'], a_off=t0 * a_s1, c_off=t0 * NG, flops=2.0 * Bn * R * NG * Kp)
 
-    cptr = prep['counters'].data_ptr()
-    with torch.cuda.stream(side):
-        side.wait_event(ev_ready)
-        waited = 0
-        for k, t0, t1 in early:
-            if k > waited:
-                for c in range(ncl.value):
-                    check(lib.las_stream_wait_value_geq(side.cuda_stream, cptr + 4 * c, rs.value * k), 'stream_wait_value')
-                waited = k
-            tile_gemm(t0, t1)
-        side.wait_event(ev_rec_done)
-        for _, t0, t1 in late:
-            tile_gemm(t0, t1)
-        ev = torch.cuda.Event()
-        ev.record(side)
+    ev = _issue_tiles(side, prep['counters'], ncl.value, rs.value, early, late, ev_ready, ev_rec_done, tile_gemm)
     pre = _PreGates()
     pre.gates, pre.wcat, pre.event, pre.x16 = prep['gates'], prep['wcat'], ev, out16
     pre.wkey, pre.pyramid, pre.T, pre.Kp, pre.Dp = _weights_key(nxt['weights']), prep['pyr'], Tn, Kp, Dp
@@ -576,10 +600,19 @@ class LSTMLayerFunction(torch.autograd.Function):
             if ovl.pending:
                 ev = True
                 lib.las_set_launch_start_stream(ovl.side.cuda_stream)
+        dx_pipe = None
         if rec_tc:
             w_hh_t = torch.empty(ndir, H, G4, dtype=torch.bfloat16, device=dev)
             check(lib.las_transpose_cast_bf16(w_hh.data_ptr(), w_hh_t.data_ptr(), ndir, G4, H, stream_ptr()), 'transpose_cast')
             dGb = torch.empty(M, NG, dtype=torch.bfloat16, device=dev)
+            if tc and ctx.needs_input_grad[0] and os.environ.get('LAS_BWD_PIPELINE', '1') != '0' and T > _PIPE_TILE:
+                # the layer's dX GEMM, tile by tile beside its own BPTT kernel (row t has both directions' gate gradients once the two
+                # sweeps have crossed it: from the middle outwards), on a third stream: dX is what the layer below waits for
+                main = torch.cuda.current_stream(dev)
+                dx_pipe = dict(dx=torch.zeros(Bn, Tin, D, dtype=torch.float32, device=dev),
+                               counters=torch.zeros(64, dtype=torch.int32, device=dev), ev_ready=torch.cuda.Event(), main=main)
+                dx_pipe['ev_ready'].record(main)
+                lib.las_lstm_rec_bwd_arm_progress(dx_pipe['counters'].data_ptr(), _PROGRESS_EVERY)
             nsl = lib.las_lstm_rec_bwd_tc_dbias_slices(Bn, H, ndir) if os.environ.get('LAS_REC_DBIAS', '1') == '1' else 0
             if nsl > 0:
                 # bias gradients accumulated inside the BPTT kernel (per direction and batch slice); no fp32 dG write-back, no
@@ -609,7 +642,30 @@ class LSTMLayerFunction(torch.autograd.Function):
             xb, wcat = x, ws[0]
             if dGb is None:
                 dGb = cast_bf16(dG, M, NG, NG, NG)                                        # (B*T, NG) bf16
-            if ctx.needs_input_grad[0]:
+            if dx_pipe is not None:
+                ncl, rs = C.c_int(0), C.c_int(0)
+                publishes = bool(lib.las_lstm_rec_fwd_progress_info(C.byref(ncl), C.byref(rs)))
+                main = dx_pipe['main']
+                ev_done = torch.cuda.Event()
+                ev_done.record(main)
+                dx = dx_pipe['dx']
+                early, late = _time_tiles(T, T, 1, publishes)
+
+                def dx_tile(t0, t1, dGb=dGb, wcat=wcat, dx=dx):
+                    gemm_tc(dGb, wcat, dx, t1 - t0, Din, NG, a_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=Kp, b_mn=True, c_bs=Tin * D,
+                            ldc=Din, a_off=t0 * NG, c_off=t0 * Din, flops=2.0 * Bn * (t1 - t0) * NG * Din)
+
+                if early:
+                    third = _dgrad_stream(dev)
+                    ev = _issue_tiles(third, dx_pipe['counters'], ncl.value, rs.value, early, late, dx_pipe['ev_ready'], ev_done, dx_tile)
+                    main.wait_event(ev)
+                    for t in (dx_pipe['counters'], dGb, wcat, dx):
+                        t.record_stream(third)
+                else:
+                    for _, t0, t1 in late:
+                        dx_tile(t0, t1)
+                last_pipeline_stats[('bwd', Bn, T, H)] = (len(early), len(late))
+            elif ctx.needs_input_grad[0]:
                 dx = torch.zeros(Bn, Tin, D, dtype=torch.float32, device=dev)             # tiles past a row's length are skipped
                 gemm_tc(dGb, wcat, dx, T, Din, NG, a_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=Kp, b_mn=True, c_bs=Tin * D,
                         ldc=Din, lens=lens_dev, flops=2.0 * Bn * T * NG * Din)

@@ -168,6 +168,9 @@ int las_launch_start_mode(void);
  *   does not (the caller then waits for the launch to finish, as without the request).
  * las_stream_wait_value_geq(stream, word, value): cuStreamWaitValue32(GEQ) -- work queued on `stream` afterwards waits for the word. */
 void las_lstm_rec_fwd_arm_progress(void* counters, int every);
+/* same for the next las_lstm_rec_bwd_tc[_db] call: BPTT steps < k*every of a cluster have written their rows of the bf16 gate-gradient
+ * matrix when its word >= k * ctas_per_cluster (the layer's dX GEMM then starts from the middle of the sequence outwards). */
+void las_lstm_rec_bwd_arm_progress(void* counters, int every);
 int las_lstm_rec_fwd_progress_info(int* clusters, int* ctas_per_cluster);
 int las_stream_wait_value_geq(void* stream, const void* dev_word, unsigned value);
 /* debug aid: device buffer (256*16 long long) receiving clock64 stamps of CTA (0,0,0) per timestep; NULL disables */

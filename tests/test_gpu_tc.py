@@ -494,6 +494,7 @@ def test_forward_pipelining_is_bit_identical(monkeypatch):
     res = {}
     for pipe in ('1', '0'):
         monkeypatch.setenv('LAS_FWD_PIPELINE', pipe)
+        monkeypatch.setenv('LAS_BWD_PIPELINE', pipe)          # same scheme for each layer's dX GEMM beside its BPTT kernel
         LF.last_pipeline_stats.clear()
         torch.manual_seed(6)
         model = ListenAttendSpell(**gu.get_config('best', init_dropout=0.3, mid_dropout=0.3, final_dropout=0.35)).to(DEV).train()
@@ -506,8 +507,9 @@ def test_forward_pipelining_is_bit_identical(monkeypatch):
                      dict(LF.last_pipeline_stats))
     stats = res['1'][2]
     print('pipelined tiles (early, late) per layer:', stats)
-    assert stats and sum(e for e, _ in stats.values()) >= 3, stats        # tiles that really ran beside a recurrence
-    assert not res['0'][2]
+    assert sum(e for k, (e, _) in stats.items() if k[0] != 'bwd') >= 3, stats        # tiles that really ran beside a forward recurrence
+    assert sum(e for k, (e, _) in stats.items() if k[0] == 'bwd') >= 3, stats        # ... and beside a BPTT kernel
+    assert all(e == 0 for e, _ in res['0'][2].values()), res['0'][2]
     assert np.array_equal(res['1'][0], res['0'][0])
     for k in res['0'][1]:
         assert np.array_equal(res['1'][1][k], res['0'][1][k]), k
