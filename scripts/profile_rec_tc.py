@@ -20,7 +20,7 @@ for it in range(2):
     lib.las_lstm_rec_tc_set_debug(dbg.data_ptr() if it == 1 else None)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    _lib.check(lib.las_lstm_rec_fwd_tc(gates.data_ptr(), wb.data_ptr(), lens_dev.data_ptr(), None, None, hs.data_ptr(), cs.data_ptr(), B, T, H, ndir, 1, ws.data_ptr(), nbytes, st), 'tc')
+    _lib.check(lib.las_lstm_rec_fwd_tc(gates.data_ptr(), wb.data_ptr(), lens_dev.data_ptr(), None, None, hs.data_ptr(), cs.data_ptr(), B, T, H, ndir, int(os.environ.get("SAVE", "1")), ws.data_ptr(), nbytes, st), 'tc')
     e1.record(); torch.cuda.synchronize()
     print(f'run {it}: {e0.elapsed_time(e1) * 1e3 / T:.2f} us/step')
 lib.las_lstm_rec_tc_set_debug(None)
