@@ -179,7 +179,7 @@ __device__ __forceinline__ long long gtime_ns() {
     } while (0)
 
 struct SmemLayout {
-    uint32_t tile, ex, wq, sc, part, misc, total;
+    uint32_t tile, ex, wq, sc, ph, part, misc, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int T, int P, int DH, int DO) {
     SmemLayout L;
@@ -189,6 +189,7 @@ __host__ __device__ inline SmemLayout smem_layout(int T, int P, int DH, int DO) 
     L.ex = o; o += 4u * 32u * 32u * 4u;                      // [gate][row][unit] activated gates
     L.wq = o; o += (uint32_t)DO * (uint32_t)P * 2u;          // WqT fp16
     L.sc = o; o += (uint32_t)((T + 3) & ~3) * 4u;            // scaled energies of one batch row
+    L.ph = o; o += (uint32_t)((T + 15) & ~15) * 2u;          // fp16 softmax numerators of that row (tensor-core V pass)
     L.part = o; o += (uint32_t)NW * (uint32_t)P * 4u;        // per-warp partial context
     L.misc = o; o += 8192u;                                  // see `Misc`
     L.total = o + 1024u;                                     // alignment slack
@@ -200,9 +201,21 @@ struct Misc {
     float h1s[256];           // decoder output h1 of the current row (DO <= 256)
     float qpart[1024];        // query-projection partials [k group][P]  (k groups = NT / (P / 4))
     float lg[32];             // logits of the current row (V <= 32)
+    __half qh[256];           // fp16 copy of q (P <= 256): B operand of the tensor-core K pass (fp16 K / V rows)
     unsigned long long tfull; // mbarrier: UMMAs of the current cell phase retired
     uint32_t tmem_slot;
 };
+
+// mma.sync m16n8k16, fp16 operands, fp32 accumulate: D += A . B   (A 16x16 row-major fragments, B 16x8 "col" fragments)
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 // 8 consecutive-in-register elements of one K / V row for this lane.  fp32 rows: floats [4l, 4l+4) and [128 + 4l, 128 + 4l + 4);
 // fp16 rows: halves [8l, 8l + 8).  Element i of the lane sits at column kcol<KV16>(lane, i).
@@ -258,6 +271,7 @@ __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(const LasDecPers
     float* ex = reinterpret_cast<float*>(sm + L.ex);
     const __half2* wq_s = reinterpret_cast<const __half2*>(sm + L.wq);
     float* sc = reinterpret_cast<float*>(sm + L.sc);
+    __half* ph = reinterpret_cast<__half*>(sm + L.ph);
     float* part = reinterpret_cast<float*>(sm + L.part);
     Misc* ms = reinterpret_cast<Misc*>(sm + L.misc);
     const uint32_t tfull_bar = smem_u32(&ms->tfull);
@@ -313,6 +327,19 @@ __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(const LasDecPers
     uint32_t ncommit = 0;
     const int chains = (a.nsl + a.ngroups - 1) / a.ngroups;
 
+    auto load_kblock = [&](int brow, int t0, uint4 (&xa)[8], uint4 (&xb)[8]) {
+        const int g = lane >> 2, c = lane & 3;
+        const int lenr = min(a.enc_lens[brow], T);
+        const __half* Kh = reinterpret_cast<const __half*>(a.K) + (long long)brow * T * P;
+        const int ta = t0 + g, tbb = t0 + g + 8;
+#pragma unroll
+        for (int pb = 0; pb < 8; ++pb) {
+            const bool in = pb * 32 < P;
+            xa[pb] = (in && ta < lenr) ? __ldg(reinterpret_cast<const uint4*>(Kh + (long long)ta * P + pb * 32 + c * 8)) : make_uint4(0u, 0u, 0u, 0u);
+            xb[pb] = (in && tbb < lenr) ? __ldg(reinterpret_cast<const uint4*>(Kh + (long long)tbb * P + pb * 32 + c * 8)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+
     for (int ai = 0; ai <= S; ++ai) {
         // =====================================================================================================================
         // ATT(ai): one batch row per pass of this CTA
@@ -352,6 +379,7 @@ __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(const LasDecPers
                     float q = a.bq[tid];
                     for (int g2 = 0; g2 < kgroups; ++g2) q += ms->qpart[g2 * P + tid];
                     ms->qc[tid] = q;
+                    if (KV16) ms->qh[tid] = __float2half_rn(q);
                 }
                 __syncthreads();
             }
@@ -364,6 +392,32 @@ __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(const LasDecPers
             // ---- pass 1: scaled energies of every valid row into shared memory (8 rows = 8 independent reductions in flight per warp).
             // Two passes (K, then V) instead of one online-softmax pass: with 8 warps per SM a warp that loads, reduces, rescales and
             // accumulates in one loop exposes every latency once per iteration (measured 9.6 us per 410 KB row); the bytes are the same.
+            if constexpr (KV16) {
+                // fp16 rows on the tensor pipe: 16 K rows x 16 columns per mma as the A operand, q (replicated over the 8 output
+                // columns) as B, so D[row][*] accumulates the row's energy over the 16 k-steps of P = 256.  A dot product does not care
+                // in which order its terms are paired, so each lane loads 16 CONTIGUOUS bytes per row (columns p0 + 8c .. + 8, c = lane & 3)
+                // and feeds them to two mmas as the logical k-slots {2c, 2c+1, 8+2c, 9+2c}; q is read in the same permutation.
+                const int g = lane >> 2, c = lane & 3;
+                for (int t0 = warp * 16; t0 < len; t0 += NW * 16) {
+                    const int ta = t0 + g, tbb = t0 + g + 8;
+                    const bool va = ta < len, vb = tbb < len;
+                    uint4 xa[8], xb[8];
+                    load_kblock(b, t0, xa, xb);
+                    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int pb = 0; pb < 8; ++pb) {
+                        if (pb * 32 < P) {
+                            const uint4 qq = *reinterpret_cast<const uint4*>(ms->qh + pb * 32 + c * 8);
+                            mma_f16_16816(d, xa[pb].x, xb[pb].x, xa[pb].y, xb[pb].y, qq.x, qq.y);
+                            mma_f16_16816(d, xa[pb].z, xb[pb].z, xa[pb].w, xb[pb].w, qq.z, qq.w);
+                        }
+                    }
+                    if (c == 0) {
+                        if (va) sc[ta] = d[0] * a.scale;
+                        if (vb) sc[tbb] = d[2] * a.scale;
+                    }
+                }
+            } else
             for (int tb = warp; tb < len; tb += NW * RU) {
                 float kk[RU][8];
 #pragma unroll
@@ -393,6 +447,21 @@ __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(const LasDecPers
                 }
             }
             DP_STAMP(cta == 0, ai, 14);
+            // fp16 V rows: this warp's first 16-position block does not depend on the softmax -- in flight during the statistics below
+            uint4 vpre[4][4];
+            if constexpr (KV16) {
+                const int g = lane >> 2, c = lane & 3;
+                const int nchunk = P / 64 > 0 ? P / 64 : 1;
+                const __half* Vh = reinterpret_cast<const __half*>(a.Vv) + mbase + 8 * g;
+                const int t0 = warp * 16;
+                const int tt[4] = {t0 + 2 * c, t0 + 2 * c + 1, t0 + 8 + 2 * c, t0 + 9 + 2 * c};
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        vpre[ch][i] = (ch < nchunk && tt[i] < len) ? __ldg(reinterpret_cast<const uint4*>(Vh + (long long)tt[i] * P + ch * 64))
+                                                                   : make_uint4(0u, 0u, 0u, 0u);
+            }
             __syncthreads();
             // ---- softmax statistics, computed redundantly by every warp from shared memory ----
             float m_c = -INFINITY;
@@ -402,10 +471,82 @@ __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(const LasDecPers
             for (int t = lane; t < len; t += 32) s_c += __expf(sc[t] - m_c);
             s_c = warp_sum(s_c);
             const float inv = 1.f / s_c;
+            if constexpr (KV16) {
+                // numerators as fp16 pairs for the A / B fragments of the V pass (zero up to the next multiple of 16 positions)
+                for (int t = tid; t < ((len + 15) & ~15); t += NT) ph[t] = __float2half_rn(t < len ? __expf(sc[t] - m_c) : 0.f);
+                __syncthreads();
+            }
             // ---- pass 2: context = sum_t p_t V_t ----
             float o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = 0.f;
+            if constexpr (KV16) {
+                // context on the tensor pipe, transposed: D (16 columns x 8) = A (16 columns x 16 positions) . B (16 positions x 8), with
+                // A = a block of V^T and B = the softmax numerators of the 16 positions (the same in all 8 output columns).  The A
+                // fragment wants two POSITIONS of one column per register; memory has two columns of one position: each lane loads 16
+                // contiguous bytes (8 columns) of its four positions and a byte permute pairs them up -- register j of the lane (columns
+                // 2j, 2j+1 of its 8) feeds mma j, whose output rows g / g+8 stand for those two columns.
+                // A warp owns whole rows (16 positions x all P columns per round, like the K pass: the rows' lines are fetched together).
+                const int g = lane >> 2, c = lane & 3;
+                const int nchunk = P / 64 > 0 ? P / 64 : 1;
+                constexpr int MAXCH = 4;           // P <= 256
+                const int tsplit = NW;
+                const __half* Vh = reinterpret_cast<const __half*>(a.Vv) + mbase + 8 * g;
+                float acc[MAXCH][4][4];
+#pragma unroll
+                for (int ch = 0; ch < MAXCH; ++ch)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { acc[ch][j][0] = 0.f; acc[ch][j][1] = 0.f; acc[ch][j][2] = 0.f; acc[ch][j][3] = 0.f; }
+                for (int t0 = warp * 16; t0 < len; t0 += NW * 16) {
+                    uint4 r[MAXCH][4];
+                    const int tt[4] = {t0 + 2 * c, t0 + 2 * c + 1, t0 + 8 + 2 * c, t0 + 9 + 2 * c};
+                    if (t0 == warp * 16) {
+#pragma unroll
+                        for (int ch = 0; ch < MAXCH; ++ch)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) r[ch][i] = vpre[ch][i];
+                    } else {
+#pragma unroll
+                        for (int ch = 0; ch < MAXCH; ++ch)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                r[ch][i] = (ch < nchunk && tt[i] < len) ? __ldg(reinterpret_cast<const uint4*>(Vh + (long long)tt[i] * P + ch * 64))
+                                                                        : make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    const uint32_t wa = *reinterpret_cast<const uint32_t*>(ph + t0 + 2 * c), wb = *reinterpret_cast<const uint32_t*>(ph + t0 + 8 + 2 * c);
+#pragma unroll
+                    for (int ch = 0; ch < MAXCH; ++ch) {
+                        if (ch < nchunk) {
+                            const uint32_t r0[4] = {r[ch][0].x, r[ch][0].y, r[ch][0].z, r[ch][0].w}, r1[4] = {r[ch][1].x, r[ch][1].y, r[ch][1].z, r[ch][1].w};
+                            const uint32_t r2[4] = {r[ch][2].x, r[ch][2].y, r[ch][2].z, r[ch][2].w}, r3[4] = {r[ch][3].x, r[ch][3].y, r[ch][3].z, r[ch][3].w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                mma_f16_16816(acc[ch][j], __byte_perm(r0[j], r1[j], 0x5410u), __byte_perm(r0[j], r1[j], 0x7632u),
+                                              __byte_perm(r2[j], r3[j], 0x5410u), __byte_perm(r2[j], r3[j], 0x7632u), wa, wb);
+                        }
+                    }
+                }
+                DP_STAMP(cta == 0, ai, 2);
+                // output columns of D are identical: lanes with c == 0 hold columns 64 ch + 8g + 2j (acc[..][0]) and + 2j + 1 (acc[..][2])
+                if (c == 0) {
+#pragma unroll
+                    for (int ch = 0; ch < MAXCH; ++ch)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (ch < nchunk) {
+                                part[warp * P + ch * 64 + 8 * g + 2 * j] = acc[ch][j][0];
+                                part[warp * P + ch * 64 + 8 * g + 2 * j + 1] = acc[ch][j][2];
+                            }
+                }
+                __syncthreads();
+                if (tid < P) {
+                    float rr = 0.f;
+                    for (int i = 0; i < tsplit; ++i) rr += part[i * P + tid];
+                    rr *= inv;
+                    ms->qc[P + tid] = rr;
+                    a.S0h[((long long)slot * B + b) * K0 + tid] = __float2half_rn(rr);     // the only store cell 0 waits for
+                }
+            } else {
             for (int tb = warp; tb < len; tb += NW * RU) {
                 float vv[RU][8], pw[RU];
 #pragma unroll
@@ -436,6 +577,7 @@ __global__ void __launch_bounds__(NT, 1) dec_persist_fwd_kernel(const LasDecPers
                 rr *= inv;
                 ms->qc[P + tid] = rr;
                 a.S0h[((long long)slot * B + b) * K0 + tid] = __float2half_rn(rr);     // the only store cell 0 waits for
+            }
             }
             if (a.per_step_logits && ai > 0) {
                 // tied classifier on cat[q_proj, ctx] (src/models.py:370-373) + greedy argmax (:380; first maximum like torch.argmax)

@@ -969,7 +969,10 @@ class SpellerFunction(torch.autograd.Function):
         persist = bool(lib.las_speller_persistent(Bn, T, P, params[3].shape[1], params[7].shape[1], Vn, int(heads), int(bool(init_force)),
                                                   int(bool(use_tc))))
         if persist:
-            kv16 = 2 if os.environ.get('LAS_KV_F16', '0') == '1' else 0
+            # fp16 K / V rows: both attention passes run on the tensor pipe (mma.sync, fp32 accumulate) and stream half the bytes:
+            # 24.3 -> 21.3 us per decoder step at the train shape, 99.9 -> 90.1 ms per greedy batch; logits 9.4e-4 -> 1.0e-3 from the fp32
+            # reference at T = 1600, L = 300 (the reference under autocast computes K and V in 16 bits as well).  LAS_KV_F16=0: fp32 rows
+            kv16 = 2 if os.environ.get('LAS_KV_F16', '1') == '1' else 0
         else:
             kv16 = 1 if (bool(use_tc) and P % 4 == 0 and os.environ.get('LAS_KV_BF16', '0') == '1') else 0   # measured slower than fp32 rows: off
         slot = _acquire_slot((dev.index, bool(training)))
