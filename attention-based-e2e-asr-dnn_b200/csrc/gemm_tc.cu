@@ -590,7 +590,9 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
     LAS_CHECK_ARG((d->a_f16 != 0) == (d->b_f16 != 0), "gemm_tc: both operands must have the same 16-bit format (fp16 x bf16 is not a legal tcgen05 kind::f16 pair)");
     g.fmt_clear = (d->a_f16 ? (1u << 7) : 0u) | (d->b_f16 ? (1u << 10) : 0u);
     const double flops = d->prof_flops > 0 ? d->prof_flops : 2.0 * d->M * (double)d->N * d->K * d->a_batches * d->k_batches;
-    LasProfScope prof(d->prof_tag == 1 ? (d->max_ctas > 0 ? LAS_PROF_GEMM_GATES_SIDE : LAS_PROF_GEMM_GATES) : LAS_PROF_GEMM_OTHER, stream, flops);
+    LasProfScope prof(d->prof_tag == 2 ? LAS_PROF_GEMM_GATES_SIDE
+                                       : d->prof_tag == 1 ? (d->max_ctas > 0 ? LAS_PROF_GEMM_GATES_SIDE : LAS_PROF_GEMM_GATES) : LAS_PROF_GEMM_OTHER,
+                      stream, flops);
     // narrow N tiles when the 128x256 tiling would leave most SMs idle (decoder-step GEMMs: M = batch)
     const long long tiles256 = (long long)ceil_div(d->M, BM) * ceil_div(d->N, 256) * d->a_batches;
     const bool narrow = tiles256 < 40 && !(d->a_mn_major && d->splitk > 1);

@@ -54,7 +54,7 @@ def gemm_raw(A, B, Cout, M, N, K, *, am=(0, 0, 0), ak=(0, 1, 0), bk=(0, 1, 0), b
 
 def gemm_tc(A, B, Cout, M, N, K, *, a_batches=1, k_batches=1, a_s1, a_s2=0, b_s1, b_s2=0, c_bs=0, ldc, a_mn=False, b_mn=False,
             bias1=None, bias2=None, accumulate=False, lens=None, a_off=0, b_off=0, c_off=0, gate=True, flops=0.0, splitk=0,
-            max_ctas=0):
+            max_ctas=0, side=False):
     """las_gemm_bf16_tc wrapper; A/B are bf16 (or fp16: the format is taken from the tensor's dtype) tensors, Cout fp32; *_off are
     element offsets."""
     d = LasGemmTc()
@@ -69,7 +69,7 @@ def gemm_tc(A, B, Cout, M, N, K, *, a_batches=1, k_batches=1, a_s1, a_s2=0, b_s1
     d.c_bs, d.ldc = int(c_bs), int(ldc)
     d.a_mn_major, d.b_mn_major, d.accumulate = int(a_mn), int(b_mn), int(accumulate)
     d.lens = ptr(lens)
-    d.prof_tag = 1 if gate else 0
+    d.prof_tag = (2 if side else 1) if gate else 0          # side: beside a recurrence kernel, timed apart (las_b200.h)
     d.prof_flops = float(flops)
     d.max_ctas = int(max_ctas)
     ws = None
@@ -388,10 +388,10 @@ def _issue_tiles(stream, counters, ncl, rs, early, late, ev_ready, ev_done, tile
                 for c in range(ncl):
                     check(lib.las_stream_wait_value_geq(stream.cuda_stream, cptr + 4 * c, rs * k), 'stream_wait_value')
                 waited = k
-            tile_fn(t0, t1)
+            tile_fn(t0, t1, True)
         stream.wait_event(ev_done)
         for _, t0, t1 in late:
-            tile_fn(t0, t1)
+            tile_fn(t0, t1, False)
         ev = torch.cuda.Event()
         ev.record(stream)
     return ev
@@ -423,10 +423,10 @@ def _pipeline_issue(prep, nxt, out16, Bn, T, ev_ready, ev_rec_done):
     xb = out16.view(Bn * T, -1)
     a_s1 = 2 * Dp if prep['pyr'] else Dp
 
-    def tile_gemm(t0, t1):
+    def tile_gemm(t0, t1, beside):
         R = t1 - t0
         gemm_tc(xb, prep['wcat'], prep['gates'], R, NG, Kp, a_batches=Bn, a_s1=a_s1, a_s2=T * Dp, b_s1=Kp, c_bs=Tn * NG, ldc=NG,
-                bias1=prep['b1'], bias2=prep['b2'], a_off=t0 * a_s1, c_off=t0 * NG, flops=2.0 * Bn * R * NG * Kp)
+                bias1=prep['b1'], bias2=prep['b2'], a_off=t0 * a_s1, c_off=t0 * NG, flops=2.0 * Bn * R * NG * Kp, side=beside)
 
     ev = _issue_tiles(side, prep['counters'], ncl.value, rs.value, early, late, ev_ready, ev_rec_done, tile_gemm)
     pre = _PreGates()
@@ -651,9 +651,9 @@ class LSTMLayerFunction(torch.autograd.Function):
                 dx = dx_pipe['dx']
                 early, late = _time_tiles(T, T, 1, publishes)
 
-                def dx_tile(t0, t1, dGb=dGb, wcat=wcat, dx=dx):
+                def dx_tile(t0, t1, beside=False, dGb=dGb, wcat=wcat, dx=dx):
                     gemm_tc(dGb, wcat, dx, t1 - t0, Din, NG, a_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=Kp, b_mn=True, c_bs=Tin * D,
-                            ldc=Din, a_off=t0 * NG, c_off=t0 * Din, flops=2.0 * Bn * (t1 - t0) * NG * Din)
+                            ldc=Din, a_off=t0 * NG, c_off=t0 * Din, flops=2.0 * Bn * (t1 - t0) * NG * Din, side=beside)
 
                 if early:
                     third = _dgrad_stream(dev)

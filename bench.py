@@ -383,6 +383,33 @@ def main():
             prof[name] = dict(ms_per_step=ms.value, launches_per_step=float(n.value), work_per_step=work.value)
         lib.las_prof_reset()
 
+    # gate-GEMM roofline: in the timed region most of these GEMMs run as 128-row time tiles BESIDE the recurrence kernels,
+    # where a launch's duration says nothing about the kernel.  Two extra (untimed) steps with that pipelining switched off run the
+    # same kernel as full-size launches that own the GPU; EVERY rank runs them (gradient all-reduce inside), rank 0 records.
+    saved_env = {k: os.environ.get(k) for k in ('LAS_FWD_PIPELINE', 'LAS_BWD_PIPELINE')}
+    os.environ['LAS_FWD_PIPELINE'] = '0'
+    os.environ['LAS_BWD_PIPELINE'] = '0'
+    step(x_dev, y_dev)
+    torch.cuda.synchronize()
+    lib.las_prof_reset()
+    lib.las_prof_enable(((1 << 0) | (1 << 9)) if rank == 0 else 0)
+    NUNP = 2
+    for _ in range(NUNP):
+        step(x_dev, y_dev)
+    torch.cuda.synchronize()
+    lib.las_prof_enable(0)
+    for k, v in saved_env.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+    if rank == 0:
+        for name in ('gemm_gates', 'gemm_gates_side'):
+            ms, n, work = C.c_double(), C.c_longlong(), C.c_double()
+            _lib.check(lib.las_prof_collect(PROF_KINDS[name], C.byref(ms), C.byref(n), C.byref(work)), 'prof_collect')
+            prof[name + '_unpipelined'] = dict(ms_per_step=ms.value / NUNP, launches_per_step=n.value / NUNP, work_per_step=work.value / NUNP)
+        lib.las_prof_reset()
+
     attn_replay = None
     if rank == 0:
         Pq = cfg['speller_configs']['att_proj_dim']
@@ -512,7 +539,8 @@ def main():
     pk = peaks()
     gemm_traffic = ncu_dram_bytes('gemm_bf16_tc_kernel<0, 0, ')
     attn_traffic = ncu_dram_bytes('attn_step_split_kernel<0')
-    gg = prof['gemm_gates']
+    gg = prof['gemm_gates_unpipelined']
+    gg_timed = prof['gemm_gates']
     tf_achieved = (gg['work_per_step'] / 1e12) / (gg['ms_per_step'] / 1e3) if gg['ms_per_step'] > 0 else 0.0
     gs = prof.get('gemm_gates_side', dict(ms_per_step=0.0, work_per_step=0.0))
     # the weight-gradient GEMMs of layers 1-3 run on a second stream BESIDE the BPTT kernel of the layer below, on the 52 SMs it leaves
@@ -524,8 +552,13 @@ def main():
                     traffic_note='dram read+write of the largest launch (layer-1 forward, M=76800 N=4096 K=2048: 1.29 TFLOP, 1.59 GB algorithmic), '
                                  'read at run time from the committed ncu --set full extract ' + str((gemm_traffic or {}).get('source')),
                     peak_source=pk['source'] + ' bf16 sustained', ms_per_step=gg['ms_per_step'], flops_per_step=gg['work_per_step'],
+                    measured='CUDA events around every launch of the kernel in 2 extra steps after the timed region, with LAS_FWD_PIPELINE=0 and '
+                             'LAS_BWD_PIPELINE=0: full-size launches that own the GPU.  In the timed region the same kernel ran as in '
+                             '`in_timed_region`: part of it as 128-row time tiles beside the recurrence kernels (`beside_recurrence`)',
+                    in_timed_region=dict(owning_gpu=dict(ms_per_step=gg_timed['ms_per_step'], flops_per_step=gg_timed['work_per_step'],
+                                                         launches_per_step=gg_timed['launches_per_step'])),
                     beside_recurrence=dict(ms_per_step=gs['ms_per_step'], flops_per_step=gs['work_per_step'], max_ctas=52,
-                                           note='wgrad GEMMs of layers 1-3, capped to the SMs the BPTT kernel leaves free; overlapped with it'))
+                                           note="wgrad GEMMs of layers 1-3 (capped to the SMs the BPTT kernel leaves free) and the time tiles of the next layer's gate GEMM / this layer's dX GEMM issued behind the recurrence kernels' progress counters: overlapped with those kernels"))
     af = prof['attn_fwd']
     # attention step: the kernel's own duration = graph-replayed back-to-back launches at the workload shape (the decoder loop
     # replays it the same way); the per-launch-evented in-loop figure is kept beside it (it includes launch/event gaps)

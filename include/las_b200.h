@@ -65,7 +65,8 @@ typedef struct {
     long long c_m_so, c_m_si; int c_m_inner; /* C's n stride is 1 */
     long long bsA, bsB, bsC;                 /* batch strides (elements) */
     float alpha, beta;
-    int prof_tag;                            /* 1: count this launch as an LSTM input-gate GEMM in las_prof_* */
+    int prof_tag;                            /* 1: count this launch as an LSTM input-gate GEMM in las_prof_*; 2: ... one that runs beside a
+                                              * recurrence kernel on the SMs it leaves free (timed apart: its duration is not a whole-GPU figure) */
 } LasGemmF32;
 int las_gemm_f32(const LasGemmF32* desc, void* stream);
 
