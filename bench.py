@@ -104,7 +104,7 @@ class ClockSampler(threading.Thread):
 def ncu_dram_bytes(kernel_prefix):
     """dram read + write bytes per launch of the first row whose kernel name starts with `kernel_prefix` in the newest committed
     `ncu --set full` extract under profiles/ (columns: kernel, dram_rd [GB], dram_wr [GB], ...), or None."""
-    for name in ('ncu_full_r2_kernels.csv', 'ncu_full_r1_final_kernels.csv', 'ncu_full_r1_kernels.csv'):
+    for name in ('ncu_full_r2_final_kernels.csv', 'ncu_full_r2_kernels.csv', 'ncu_full_r1_final_kernels.csv', 'ncu_full_r1_kernels.csv'):
         path = os.path.join(ROOT, 'profiles', name)
         if not os.path.exists(path):
             continue
