@@ -671,6 +671,218 @@ extern "C" int las_attn_step_bwd_f32(const LasAttnStep* a, void* stream) {
     return LAS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward decoder step on the tensor pipe (fp16 K / V rows): one CTA of 8 warps per batch row, single head.
+//   dw_t = dctx . V_t            -> mma.sync m16n8k16: A = 16 V rows x 16 columns, B = dctx (replicated over the 8 output columns)
+//   de_t = w_t (dw_t - dctx.ctx) sqrt(d)
+//   dq   = sum_t de_t K_t        -> mma.sync: A = K^T block (16 columns x 16 positions, paired up in registers with a byte permute),
+//                                   B = de of the 16 positions (replicated)
+// Same fragment tricks as the forward passes in decoder_persist.cu (16 contiguous bytes per lane and row; a dot product does not
+// care how its terms are paired).  Gradients have no fixed range: dctx is scaled by a power of two per row so that its largest
+// element is in [0.5, 1) before it is rounded to fp16 -- de then stays far from both ends of the fp16 range -- and dq / the stored de
+// are scaled back in fp32.  A warp loads BOTH its V block and its K block before the first mma (one L2 round trip per 16 positions:
+// 128 + 64 registers of operands and accumulators, hence one CTA per SM), then the fused tail of attn_tail.h runs on the whole
+// 256-column dq in this CTA: no cluster, no DSMEM merge.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+constexpr int BT_NT = 256, BT_NW = BT_NT / 32;
+
+__global__ void __launch_bounds__(BT_NT, 1) attn_bwd_tc_kernel(LasAttnStep a, LasAttnCellTail tl) {
+    extern __shared__ __align__(16) float sm[];
+    const int T = a.T, P = a.P;                    // single head: d == P, P in {64, 128, 192, 256}
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int DO = tl.DO;
+    float* part = sm;                              // [BT_NW][P]  per-warp partial dq
+    float* dqs = part + BT_NW * P;                 // [P]         dq_total of the row
+    float* red = dqs + P;                          // [2 * BT_NW] block reductions
+    float* gpart = red + 2 * BT_NW;                // [kg][DO]    partial dh1 sums of the k groups
+    const int pairs = DO / 2, kg = BT_NT / pairs, kper = P / kg;
+    __half* dxh = reinterpret_cast<__half*>(gpart + kg * DO);     // [P] scaled dctx as fp16 (B operand of the first mma)
+    __nv_bfloat16* wq_s = reinterpret_cast<__nv_bfloat16*>(dxh + ((P + 7) & ~7));      // [P][DO] query_map.weight, bf16
+    {
+        // the weights do not depend on the predecessor kernel: fetched before the programmatic-launch wait, asynchronously
+        const int cpr = DO / 8;
+        const __nv_bfloat16* wsrc = reinterpret_cast<const __nv_bfloat16*>(tl.wq_bf16);
+        for (int i = tid; i < P * cpr; i += BT_NT) cp_async16(wq_s + i * 8, wsrc + (long long)i * 8);
+        cp_async_commit();
+    }
+    pdl_wait();
+    pdl_trigger();
+    const int len = min(a.lens[b], T);
+
+    // ---- dctx_total (classifier path + cell-0 path of the next step, split-K partials), its scale, dctx . ctx ----
+    float dct = 0.f, dq_old = 0.f;
+    if (tid < P) {
+        dct = a.dctx[(long long)b * a.ld_dctx + tid];
+        if (a.dctx2) {
+            float e[8];
+            const int ns = a.dctx2_nsplit > 1 ? a.dctx2_nsplit : 1;
+#pragma unroll
+            for (int sp = 0; sp < 8; ++sp) e[sp] = sp < ns ? a.dctx2[sp * a.dctx2_split_stride + (long long)b * a.ld_dctx2 + tid] : 0.f;
+#pragma unroll
+            for (int sp = 0; sp < 8; ++sp) dct += e[sp];
+            a.dctx[(long long)b * a.ld_dctx + tid] = dct;          // the batched dV GEMM after the loop reads the total
+        }
+        if (a.dq_accumulate) dq_old = a.dq[(long long)b * a.ld_dq + tid];
+    }
+    float amax = warp_max(fabsf(dct));
+    float dot = warp_sum(tid < P ? dct * a.ctx[(long long)b * a.ld_ctx + tid] : 0.f);
+    if (lane == 0) { red[w] = amax; red[BT_NW + w] = dot; }
+    // ---- operands of the cell backward (thread = hidden unit), in flight behind everything below ----
+    float t_g[4] = {0.f, 0.f, 0.f, 0.f}, t_c = 0.f, t_cp = 0.f, t_dc = 0.f, t_mask = 1.f, t_rec = 0.f;
+    if (tid < DO) {
+        float pb[TAIL_MAX_SPLIT];
+        const int nb = tl.dh_b ? (tl.nsplit_b > 1 ? tl.nsplit_b : 1) : 0;
+#pragma unroll
+        for (int sp = 0; sp < TAIL_MAX_SPLIT; ++sp) pb[sp] = sp < nb ? tl.dh_b[sp * tl.stride_b + (long long)b * tl.ld_b + tid] : 0.f;
+        const float* gp = tl.G + (long long)b * 4 * DO + tid;
+        t_g[0] = gp[0]; t_g[1] = gp[DO]; t_g[2] = gp[2 * DO]; t_g[3] = gp[3 * DO];
+        t_c = tl.c[(long long)b * tl.ld_c + tid]; t_cp = tl.c_prev[(long long)b * tl.ld_cp + tid];
+        t_dc = tl.first ? 0.f : tl.dc[(long long)b * DO + tid];
+        if (tl.mask) t_mask = tl.mask[(long long)b * DO + tid];
+#pragma unroll
+        for (int sp = 0; sp < TAIL_MAX_SPLIT; ++sp) t_rec += pb[sp];
+    }
+    __syncthreads();
+    amax = red[0]; dot = red[BT_NW];
+#pragma unroll
+    for (int i = 1; i < BT_NW; ++i) { amax = fmaxf(amax, red[i]); dot += red[BT_NW + i]; }
+    int ex = 0;
+    if (amax > 0.f && amax < 3.0e38f) frexpf(amax, &ex);
+    const float sc_up = ldexpf(1.f, -ex), sc_dn = ldexpf(1.f, ex);       // amax * sc_up in [0.5, 1)
+    if (tid < P) dxh[tid] = __float2half_rn(dct * sc_up);
+    const float dot_s = dot * sc_up;
+    __syncthreads();
+
+    const __half* Kh = reinterpret_cast<const __half*>(tl.K_f16) + (long long)b * T * P;
+    const __half* Vh = reinterpret_cast<const __half*>(tl.V_f16) + (long long)b * T * P;
+    const float* wrow_c = a.w + (long long)b * a.ld_w;
+    float* derow = a.de + (long long)b * a.ld_w;
+    const int nchunk = P / 64 > 0 ? (P + 63) / 64 : 1;
+    float acc[4][4][4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[ch][j][0] = 0.f; acc[ch][j][1] = 0.f; acc[ch][j][2] = 0.f; acc[ch][j][3] = 0.f; }
+
+    for (int t0 = w * 16; t0 < len; t0 += BT_NW * 16) {
+        // V block, "row" pattern: lane (g, c) holds rows t0+g / t0+g+8, columns 32 pb + 8c .. + 8
+        const int ta = t0 + g, tb = t0 + g + 8;
+        const bool va = ta < len, vb = tb < len;
+        uint4 xa[8], xb[8];
+#pragma unroll
+        for (int pb = 0; pb < 8; ++pb) {
+            const bool in = pb * 32 < P;
+            xa[pb] = (in && va) ? __ldg(reinterpret_cast<const uint4*>(Vh + (long long)ta * P + pb * 32 + c * 8)) : make_uint4(0u, 0u, 0u, 0u);
+            xb[pb] = (in && vb) ? __ldg(reinterpret_cast<const uint4*>(Vh + (long long)tb * P + pb * 32 + c * 8)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        // K block, "transposed" pattern: lane (g, c) holds positions t0+2c, +1, t0+8+2c, +1, columns 64 ch + 8g .. + 8
+        const int tt[4] = {t0 + 2 * c, t0 + 2 * c + 1, t0 + 8 + 2 * c, t0 + 9 + 2 * c};
+        uint4 r[4][4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                r[ch][i] = (ch < nchunk && tt[i] < len) ? __ldg(reinterpret_cast<const uint4*>(Kh + (long long)tt[i] * P + ch * 64 + 8 * g))
+                                                        : make_uint4(0u, 0u, 0u, 0u);
+        const float wa_ = va ? wrow_c[ta] : 0.f, wb_ = vb ? wrow_c[tb] : 0.f;
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int pb = 0; pb < 8; ++pb) {
+            if (pb * 32 < P) {
+                const uint4 qq = *reinterpret_cast<const uint4*>(dxh + pb * 32 + c * 8);
+                mma_f16_16816(d, xa[pb].x, xb[pb].x, xa[pb].y, xb[pb].y, qq.x, qq.y);
+                mma_f16_16816(d, xa[pb].z, xb[pb].z, xa[pb].w, xb[pb].w, qq.z, qq.w);
+            }
+        }
+        // every lane of row group g holds dw (scaled) of rows t0+g (d[0]) and t0+g+8 (d[2])
+        const float de_a = wa_ * (d[0] - dot_s) * a.scale, de_b = wb_ * (d[2] - dot_s) * a.scale;      // 0 past the length (w = 0)
+        if (c == 0) {
+            if (va) derow[ta] = de_a * sc_dn;
+            if (vb) derow[tb] = de_b * sc_dn;
+        }
+        // B fragment of the second mma: positions 2c, 2c+1 (rows held by lane groups g = 2c, 2c+1) and 8+2c, 9+2c
+        const uint32_t fb0 = pack_h2(__shfl_sync(0xffffffffu, de_a, (2 * c) * 4), __shfl_sync(0xffffffffu, de_a, (2 * c + 1) * 4));
+        const uint32_t fb1 = pack_h2(__shfl_sync(0xffffffffu, de_b, (2 * c) * 4), __shfl_sync(0xffffffffu, de_b, (2 * c + 1) * 4));
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            if (ch < nchunk) {
+                const uint32_t r0[4] = {r[ch][0].x, r[ch][0].y, r[ch][0].z, r[ch][0].w}, r1[4] = {r[ch][1].x, r[ch][1].y, r[ch][1].z, r[ch][1].w};
+                const uint32_t r2[4] = {r[ch][2].x, r[ch][2].y, r[ch][2].z, r[ch][2].w}, r3[4] = {r[ch][3].x, r[ch][3].y, r[ch][3].z, r[ch][3].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    mma_f16_16816(acc[ch][j], __byte_perm(r0[j], r1[j], 0x5410u), __byte_perm(r0[j], r1[j], 0x7632u),
+                                  __byte_perm(r2[j], r3[j], 0x5410u), __byte_perm(r2[j], r3[j], 0x7632u), fb0, fb1);
+            }
+        }
+    }
+    // output columns of D are identical: lanes with c == 0 hold columns 64 ch + 8g + 2j (acc[..][0]) and + 2j + 1 (acc[..][2])
+    if (c == 0) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (ch * 64 + 8 * g + 2 * j < P) {
+                    part[w * P + ch * 64 + 8 * g + 2 * j] = acc[ch][j][0];
+                    part[w * P + ch * 64 + 8 * g + 2 * j + 1] = acc[ch][j][2];
+                }
+    }
+    for (int t = len + tid; t < T; t += BT_NT) derow[t] = 0.f;
+    __syncthreads();
+    if (tid < P) {
+        float rsum = 0.f;
+#pragma unroll
+        for (int i = 0; i < BT_NW; ++i) rsum += part[i * P + tid];
+        const float tot = dq_old + rsum * sc_dn;
+        dqs[tid] = tot;
+        a.dq[(long long)b * a.ld_dq + tid] = tot;
+        if (a.dq_bf16) ((__nv_bfloat16*)a.dq_bf16)[(long long)b * a.ld_dq_bf16 + tid] = __float2bfloat16(tot);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // ---- dh1 = dq_total . Wq from shared memory, then LSTMCell-1 backward (same arithmetic as the TAIL branch of attn_step_split_kernel) ----
+    {
+        const int j = tid % pairs, gk = tid / pairs;
+        float a0 = 0.f, a1 = 0.f;
+        const unsigned* wr = reinterpret_cast<const unsigned*>(wq_s) + j;
+#pragma unroll 8
+        for (int k = gk * kper; k < (gk + 1) * kper; ++k) {
+            const unsigned w2 = wr[k * pairs];
+            const float x = dqs[k];
+            a0 = fmaf(x, __uint_as_float(w2 << 16), a0);
+            a1 = fmaf(x, __uint_as_float(w2 & 0xffff0000u), a1);
+        }
+        gpart[gk * DO + 2 * j] = a0; gpart[gk * DO + 2 * j + 1] = a1;
+    }
+    __syncthreads();
+    if (tid < DO) {
+        float dh = 0.f;
+        for (int gk = 0; gk < kg; ++gk) dh += gpart[gk * DO + tid];
+        dh = (dh + t_rec) * t_mask;
+        const float gi = t_g[0], gf = t_g[1], gg = t_g[2], go = t_g[3];
+        const float tc = tanhf(t_c);
+        const float dctt = fmaf(dh * go, 1.f - tc * tc, t_dc);
+        const float d0 = dctt * gg * gi * (1.f - gi), d1 = dctt * t_cp * gf * (1.f - gf);
+        const float d2 = dctt * gi * (1.f - gg * gg), d3 = dh * tc * go * (1.f - go);
+        float* gp = tl.G + (long long)b * 4 * DO + tid;
+        gp[0] = d0; gp[DO] = d1; gp[2 * DO] = d2; gp[3 * DO] = d3;
+        __nv_bfloat16* gb = reinterpret_cast<__nv_bfloat16*>(tl.Gb) + (long long)b * 4 * DO + tid;
+        gb[0] = __float2bfloat16(d0); gb[DO] = __float2bfloat16(d1); gb[2 * DO] = __float2bfloat16(d2); gb[3 * DO] = __float2bfloat16(d3);
+        tl.dc[(long long)b * DO + tid] = dctt * gf;
+    }
+}
+
 // ---- fused backward step (attn_tail.h) ----
 static int tail_split(const LasAttnStep* a, int DO) {
     if (!a || a->heads != 1 || a->fmask || !a->ctx || a->kv_bf16 || a->P > NT2 || DO < 16) return 0;
@@ -689,9 +901,46 @@ int las_attn_step_bwd_cell_supported(const LasAttnStep* a, int DO) {
     return tail_split(a, DO) > 0 ? 1 : 0;
 }
 
+static size_t bwd_tc_smem(int P, int DO) {
+    const int kg = BT_NT / (DO / 2);
+    return sizeof(float) * ((size_t)BT_NW * P + P + 2 * BT_NW + (size_t)kg * DO) + 2 * (size_t)((P + 7) & ~7) + 2 * (size_t)P * DO + 16;
+}
+// tensor-pipe form: fp16 K / V copies given, single head, one thread per hidden unit and per attention column
+static bool bwd_tc_ok(const LasAttnStep* a, const LasAttnCellTail* tail) {
+    const char* e = getenv("LAS_BWD_ATT_TC");
+    if (e && *e == '0') return false;
+    if (!tail->K_f16 || !tail->V_f16 || a->heads != 1 || a->fmask || !a->ctx || a->kv_bf16) return false;
+    const int P = a->P, DO = tail->DO;
+    if (P % 64 != 0 || P > 256 || DO % 16 != 0 || DO > BT_NT || DO < 32) return false;
+    const int pairs = DO / 2;
+    if (BT_NT % pairs != 0 || P % (BT_NT / pairs) != 0) return false;
+    return bwd_tc_smem(P, DO) <= 200 * 1024;
+}
+
 int las_attn_step_bwd_cell(const LasAttnStep* a, const LasAttnCellTail* tail, void* stream) {
     int rc = check(a, true);
     if (rc) return rc;
+    if (tail && bwd_tc_ok(a, tail)) {
+        LAS_CHECK_ARG(tail->wq_bf16 && tail->G && tail->Gb && tail->c && tail->c_prev && tail->dc, "attn_step_bwd_cell: null tail operand");
+        LAS_CHECK_ARG(tail->nsplit_b <= TAIL_MAX_SPLIT, "attn_step_bwd_cell: at most %d recurrent partials", TAIL_MAX_SPLIT);
+        rc = las_set_device_of(a->K);
+        if (rc) return rc;
+        LasProfScope prof(LAS_PROF_ATTN_BWD, stream, 2.0 * a->B * (double)a->T * a->P * 2);
+        const size_t smem = bwd_tc_smem(a->P, tail->DO);
+        LAS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(a->B, 1, 1);
+        cfg.blockDim = dim3(BT_NT, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = las_pdl_active() ? 1 : 0;
+        LAS_CUDA(cudaLaunchKernelEx(&cfg, attn_bwd_tc_kernel, *a, *tail));
+        LAS_LAUNCH_CHECK();
+        return LAS_OK;
+    }
     LAS_CHECK_ARG(tail && tail->wq_bf16 && tail->G && tail->Gb && tail->c && tail->c_prev && tail->dc, "attn_step_bwd_cell: null tail operand");
     LAS_CHECK_ARG(tail->nsplit_b <= TAIL_MAX_SPLIT, "attn_step_bwd_cell: at most %d recurrent partials", TAIL_MAX_SPLIT);
     const int S = tail_split(a, tail->DO);

@@ -23,6 +23,9 @@ struct LasAttnCellTail {
     float* dc;                // (B, DO) carried in / out
     void* Gb;                 // (B, 4*DO) bf16 copy of d(pre-activation)
     int first;                // 1: carried-in dc is zero
+    // optional IEEE fp16 copies of K / V (B, T, P): the attention part then runs on the tensor pipe (attn_bwd_tc_kernel)
+    const void* K_f16;
+    const void* V_f16;
 };
 
 // 1 when las_attn_step_bwd_cell can run this step fused (single head, T-split kernel, weight slice fits shared memory)

@@ -1001,7 +1001,7 @@ extern "C" int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g
     std::vector<unsigned char> ident((const unsigned char*)&kd, (const unsigned char*)&kd + sizeof(LasSpeller));
     if (s->use_gold_host) ident.insert(ident.end(), s->use_gold_host, s->use_gold_host + s->steps);
     ident.insert(ident.end(), (const unsigned char*)g, (const unsigned char*)g + sizeof(LasSpellerGrads));
-    for (const char* name : {"LAS_BWD_FUSE_TAIL", "LAS_ATTN_SPLIT"}) {       // tuning switches that change which kernels the graph holds
+    for (const char* name : {"LAS_BWD_FUSE_TAIL", "LAS_ATTN_SPLIT", "LAS_BWD_ATT_TC"}) {       // tuning switches that change which kernels the graph holds
         const char* e = getenv(name);
         ident.push_back((unsigned char)((e && *e) ? *e : 0));
     }
@@ -1106,6 +1106,7 @@ int speller_bwd_enqueue(const LasSpeller* s, const LasSpellerGrads* g, const Lay
             tl.wq_bf16 = Wqb; tl.DO = DO; tl.G = b1.G; tl.dh_b = b1.dh_b; tl.ld_b = b1.ld_b; tl.stride_b = b1.stride_b; tl.nsplit_b = b1.nsplit_b;
             tl.mask = b1.mask; tl.c = b1.c; tl.ld_c = b1.ld_c; tl.c_prev = b1.c_prev; tl.ld_cp = b1.ld_cp; tl.dc = b1.dc; tl.Gb = b1.Gb;
             tl.first = b1.first;
+            tl.K_f16 = s->K_f16; tl.V_f16 = s->V_f16;
             RC(las_attn_step_bwd_cell(&at, &tl, st));
         } else {
             RC(las_attn_step_bwd_f32(&at, st));

@@ -92,6 +92,7 @@ class LasSpeller(C.Structure):
         ('logits', C.c_void_p), ('att0', C.c_void_p), ('chars', C.c_void_p),
         ('fws', C.c_void_p), ('fws_floats', C.c_size_t),
         ('iws', C.c_void_p), ('iws_ints', C.c_size_t),
+        ('K_f16', C.c_void_p), ('V_f16', C.c_void_p),
     ]
 
 

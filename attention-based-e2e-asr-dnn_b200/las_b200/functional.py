@@ -1037,11 +1037,15 @@ class SpellerFunction(torch.autograd.Function):
         t = ctx.views                     # this forward's views into the slot's buffers
         K, V, enc_lens, dec_y, drop0, drop1, fws, iws = t['K'], t['V'], t['lens'], t.get('y'), t.get('drop0'), t.get('drop1'), t['fws'], t['iws']
         use_gold, steps, heads, sos_idx, pad_idx, use_tc, kv16, init_force = ctx.cfg
+        K16 = V16 = None
         if kv16 == 2:
+            K16, V16 = K, V                # the forward's fp16 rows: the backward attention step streams them through the tensor pipe
             K, V, kv16 = t['K32'], t['V32'], 0
         s, keep = _speller_desc(K, V, enc_lens, params, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, True, use_tc,
                                 init_force)
         s.kv_bf16 = int(kv16)
+        if K16 is not None:
+            s.K_f16, s.V_f16 = K16.data_ptr(), V16.data_ptr()
         s.fws, s.fws_floats, s.iws, s.iws_ints = fws.data_ptr(), fws.numel(), iws.data_ptr(), iws.numel()
         # outputs of fwd are not needed by bwd but the descriptor check wants non-null
         s.logits, s.chars = fws.data_ptr(), t['chars'].data_ptr()

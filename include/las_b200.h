@@ -275,6 +275,9 @@ typedef struct {
     /* workspaces */
     float* fws; size_t fws_floats;
     int* iws; size_t iws_ints;
+    /* optional (backward, tensor-pipe mode): IEEE fp16 copies of K / V_ (B,T,P).  When both are given the backward loop's attention step
+     * streams them (half the bytes) through mma.sync instead of the fp32 rows; NULL: fp32 rows */
+    const void* K_f16; const void* V_f16;
 } LasSpeller;
 /* 1 when las_speller_fwd_f32 runs this shape as ONE persistent decoder-step kernel (tensor-pipe mode, heads == 1, no init_force,
  * dims that fit the TMEM-resident weight slices): K / V may then be fp32 (kv_bf16 = 0) or IEEE fp16 (kv_bf16 = 2), not bf16. */

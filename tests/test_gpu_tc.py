@@ -460,8 +460,9 @@ def test_fused_backward_step_matches_separate_launches(T, lx, monkeypatch):
     x, lxa, y = gu.make_inputs(22, B, T, L, lx=lx)
     ly = torch.tensor([L, L - 2, 3][:B])
     grads = {}
-    for name, fuse, amp in (('fp32', '1', False), ('fused', '1', True), ('separate', '0', True)):
+    for name, fuse, amp, att_tc in (('fp32', '1', False, '1'), ('fused', '1', True, '0'), ('separate', '0', True, '0'), ('fused_tc', '1', True, '1')):
         monkeypatch.setenv('LAS_BWD_FUSE_TAIL', fuse)
+        monkeypatch.setenv('LAS_BWD_ATT_TC', att_tc)      # 1: fp16 K / V rows through mma.sync in the fused backward step (attn_bwd_tc_kernel)
         torch.manual_seed(5)
         model = ListenAttendSpell(**gu.get_config('best', mid_dropout=0.3, dec_lstm_dropout=0.3)).to(DEV).train()
         model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
@@ -474,12 +475,15 @@ def test_fused_backward_step_matches_separate_launches(T, lx, monkeypatch):
         grads[name] = {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None}
     assert set(grads['fused']) == set(grads['separate']) == set(grads['fp32'])
     gmax = max(float(np.abs(v).max()) for v in grads['fp32'].values())
-    err = {n: max((rel_err(grads[n][k], grads['fp32'][k], 1e-2 * gmax), k) for k in grads['fp32']) for n in ('fused', 'separate')}
+    err = {n: max((rel_err(grads[n][k], grads['fp32'][k], 1e-2 * gmax), k) for k in grads['fp32']) for n in ('fused', 'separate', 'fused_tc')}
     ab = max((rel_err(grads['fused'][k], grads['separate'][k], 1e-2 * gmax), k) for k in grads['fp32'])
-    print(f'backward step vs fp32 mode: fused {err["fused"]}, separate {err["separate"]}; fused vs separate {ab}')
-    assert ab[0] > 0.0, 'both runs took the same path'
-    assert ab[0] < 1e-2, ab
+    ac = max((rel_err(grads['fused_tc'][k], grads['fused'][k], 1e-2 * gmax), k) for k in grads['fp32'])
+    print(f'backward step vs fp32 mode: fused {err["fused"]}, separate {err["separate"]}, tensor-pipe attention {err["fused_tc"]}; '
+          f'fused vs separate {ab}; tensor-pipe vs FMA attention {ac}')
+    assert ab[0] > 0.0 and ac[0] > 0.0, 'two runs took the same path'
+    assert ab[0] < 1e-2 and ac[0] < 1e-2, (ab, ac)
     assert err['fused'][0] < 1.25 * err['separate'][0] + 1e-3, err
+    assert err['fused_tc'][0] < 1.25 * err['separate'][0] + 1e-3, err
 
 
 def test_forward_pipelining_is_bit_identical(monkeypatch):
