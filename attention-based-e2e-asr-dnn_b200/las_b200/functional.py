@@ -450,6 +450,89 @@ def _pregates_for(x, x16, pyramid, T, weights):
     return pre
 
 
+_WG_TILE = 256
+
+
+def _wgrad_tiles_behind_bptt(ovl, wg, dGb, xb, hsb, dbp, wrefs, wdims) -> bool:
+    """Weight gradients of the layer that ends the backward pass, as time tiles on the second stream behind the progress counters of
+    its own BPTT kernel.  dW of direction d sums over that direction's gate gradients only, and the BPTT sweep of direction 0 produces
+    them from the last frame down, that of direction 1 from the first frame up: tiles become ready from the first steps on.  Each
+    tile is a K-chunk of the (4H x Din) / (4H x H) GEMMs, accumulated in place (fp32).  Returns False when the kernel that ran does not
+    publish progress (the caller then queues the work as before)."""
+    lib = _lib.load()
+    ncl, rs = C.c_int(0), C.c_int(0)
+    if not lib.las_lstm_rec_fwd_progress_info(C.byref(ncl), C.byref(rs)) or ncl.value <= 0:
+        return False
+    Bn, Tin, T, H, ndir, Din, pyramid, Dp, Kp = wdims
+    F_, G4 = ndir * H, 4 * H
+    NG = ndir * G4
+    dev = dGb.device
+    side = ovl.side
+    free = ovl.sm_count - 4 * (H // 128) * ((Bn + 31) // 32) * ndir
+    if free < 16:
+        return False
+    nper = ncl.value // ndir                                # clusters (batch-slice groups) per direction; word index = dir * nper + group
+    kmax = T // _PROGRESS_EVERY                              # increments a CTA makes: after steps every, 2*every, ... <= T
+    main = wg['main']
+    ev_done = torch.cuda.Event()
+    ev_done.record(main)
+    work = []                                                # (k or None, direction, t0, t1)
+    for d in range(ndir):
+        for t0 in range(0, T, _WG_TILE):
+            t1 = min(t0 + _WG_TILE, T)
+            ready = (T - t0) if d == 0 else t1               # BPTT steps that must be complete (direction 0 sweeps t = T-1 .. 0)
+            k = -(-ready // _PROGRESS_EVERY)
+            work.append((k if k <= kmax else None, d, t0, t1))
+    early = sorted([wk for wk in work if wk[0] is not None])
+    late = [wk for wk in work if wk[0] is None]
+    b_s1 = 2 * Dp if pyramid else Dp
+    dwcat, dw_hh = wg['dwcat'], wg['dw_hh']
+
+    def tile(d, t0, t1, beside):
+        R = t1 - t0
+        cap = free if beside else 0
+        gemm_tc(dGb, xb, dwcat, G4, Kp, R, k_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=b_s1, b_s2=Tin * Dp, ldc=Kp, a_mn=True, b_mn=True,
+                a_off=d * G4 + t0 * NG, b_off=t0 * b_s1, c_off=d * G4 * Kp, accumulate=True, flops=2.0 * Bn * R * G4 * Din, max_ctas=cap,
+                side=beside)
+        gemm_tc(dGb, hsb, dw_hh[d], G4, H, R, k_batches=Bn, a_s1=NG, a_s2=T * NG, b_s1=F_, b_s2=(T + 2) * F_, ldc=H, a_mn=True, b_mn=True,
+                a_off=d * G4 + t0 * NG, b_off=(2 * F_ if d == 1 else 0) + d * H + t0 * F_, accumulate=True, gate=False, max_ctas=cap)
+
+    cptr = wg['counters'].data_ptr()
+    with torch.cuda.stream(side):
+        side.wait_event(wg['ev_ready'])
+        waited = [0] * ndir
+        for k, d, t0, t1 in early:
+            if k > waited[d]:
+                for cix in range(d * nper, (d + 1) * nper):
+                    check(lib.las_stream_wait_value_geq(side.cuda_stream, cptr + 4 * cix, rs.value * k), 'stream_wait_value')
+                waited[d] = k
+            tile(d, t0, t1, True)
+        side.wait_event(ev_done)
+        for _, d, t0, t1 in late:
+            tile(d, t0, t1, False)
+        grads = []
+        for d in range(ndir):
+            db = torch.empty(G4, dtype=torch.float32, device=dev)
+            colsum(dbp, G4, dbp.shape[1], G4, db, x_off=d * dbp.shape[1] * G4)
+            grads += [dwcat[d * G4:(d + 1) * G4, :Din], dw_hh[d], db, db]
+        for w, g in zip(wrefs, grads):
+            w.grad.add_(g)
+
+    def report(max_ctas, wrefs=wrefs):
+        # stands in for the post-accumulate-grad hook (bucket all-reduce).  Not now: autograd's own hook call for these parameters (with
+        # the None gradients this backward returns) comes AFTER this function and must still find them marked as deferred; the queue
+        # runs on the second stream, behind the accumulation above, when the backward pass ends
+        for w in wrefs:
+            ready = getattr(w, '_las_grad_ready', None)
+            if ready is not None:
+                ready(w)
+
+    ovl.pending.append(report)
+    ovl.keepalive.append((dGb, xb, hsb, dbp, wg['counters'], dwcat, dw_hh))
+    last_pipeline_stats[('wgrad', Bn, T, H)] = (len(early), len(late))
+    return True
+
+
 last_pipeline_stats = {}
 
 
@@ -600,7 +683,7 @@ class LSTMLayerFunction(torch.autograd.Function):
             if ovl.pending:
                 ev = True
                 lib.las_set_launch_start_stream(ovl.side.cuda_stream)
-        dx_pipe = None
+        dx_pipe = wg_pipe = None
         if rec_tc:
             w_hh_t = torch.empty(ndir, H, G4, dtype=torch.bfloat16, device=dev)
             check(lib.las_transpose_cast_bf16(w_hh.data_ptr(), w_hh_t.data_ptr(), ndir, G4, H, stream_ptr()), 'transpose_cast')
@@ -613,6 +696,16 @@ class LSTMLayerFunction(torch.autograd.Function):
                                counters=torch.zeros(64, dtype=torch.int32, device=dev), ev_ready=torch.cuda.Event(), main=main)
                 dx_pipe['ev_ready'].record(main)
                 lib.las_lstm_rec_bwd_arm_progress(dx_pipe['counters'].data_ptr(), _PROGRESS_EVERY)
+            elif tc and ovl is not None and not ctx.needs_input_grad[0] and os.environ.get('LAS_BWD_WGRAD_PIPELINE', '1') != '0' \
+                    and T > 2 * _WG_TILE and hs_pad.dtype == torch.bfloat16:
+                # the layer that ends the backward pass (its input needs no gradient): nothing runs after its BPTT kernel that its own
+                # weight-gradient GEMMs could hide behind, so they follow that kernel's progress, direction by direction (below)
+                main = torch.cuda.current_stream(dev)
+                wg_pipe = dict(counters=torch.zeros(64, dtype=torch.int32, device=dev), ev_ready=torch.cuda.Event(), main=main,
+                               dwcat=torch.zeros(NG, Kp, dtype=torch.float32, device=dev),
+                               dw_hh=[torch.zeros(G4, H, dtype=torch.float32, device=dev) for _ in range(ndir)])
+                wg_pipe['ev_ready'].record(main)
+                lib.las_lstm_rec_bwd_arm_progress(wg_pipe['counters'].data_ptr(), _PROGRESS_EVERY)
             nsl = lib.las_lstm_rec_bwd_tc_dbias_slices(Bn, H, ndir) if os.environ.get('LAS_REC_DBIAS', '1') == '1' else 0
             if nsl > 0:
                 # bias gradients accumulated inside the BPTT kernel (per direction and batch slice); no fp32 dG write-back, no
@@ -686,6 +779,8 @@ class LSTMLayerFunction(torch.autograd.Function):
 
                 for w in wrefs:                            # the reducer's autograd hook must not count the None returned below
                     w._las_deferred = True
+                if wg_pipe is not None and dbp is not None and _wgrad_tiles_behind_bptt(ovl, wg_pipe, dGb, xb, hs_pad, dbp, wrefs, wdims):
+                    return (dx, None, None, None, None, None, None, None, None, *([None] * (4 * ndir)))
                 ovl.pending.append(run)
                 return (dx, None, None, None, None, None, None, None, None, *([None] * (4 * ndir)))
             grads = _lstm_weight_grads(dGb, xb, hs_pad, dG, dbp, wdims)

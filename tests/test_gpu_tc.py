@@ -517,3 +517,49 @@ def test_forward_pipelining_is_bit_identical(monkeypatch):
     assert np.array_equal(res['1'][0], res['0'][0])
     for k in res['0'][1]:
         assert np.array_equal(res['1'][1][k], res['0'][1][k]), k
+
+
+def test_base_layer_weight_gradients_behind_their_own_bptt_kernel(monkeypatch):
+    """The layer that ends the backward pass has no later BPTT kernel to hide its weight-gradient GEMMs behind: they run as time tiles
+    (K-chunks accumulated in fp32) behind the progress counters of its OWN BPTT kernel, direction by direction
+    (functional._wgrad_tiles_behind_bptt).  Same products, different summation order than the one-GEMM form: equal to 1e-5 of the
+    tensor's scale; everything else bit-identical."""
+    import copy
+    from las_b200 import functional as LF
+    from las_b200.models import ListenAttendSpell
+    from las_b200.ddp import BucketedGradReducer
+    from las_b200 import configs as gcfg
+    from las_b200.loss import masked_ce
+    B, T, L = 4, 1280, 5
+    x, lx, y = gcfg.make_inputs(41, B, T, L, lx=[1280, 1000, 700, 64])
+    x, y, lx = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV), torch.from_numpy(lx)
+    ly = torch.full((B,), L, dtype=torch.int64)
+    torch.manual_seed(8)
+    m0 = ListenAttendSpell(**gcfg.get_config('best', mid_dropout=0.3)).to(DEV).train()
+    res = {}
+    for pipe in ('1', '0'):
+        monkeypatch.setenv('LAS_BWD_WGRAD_PIPELINE', pipe)
+        LF.last_pipeline_stats.clear()
+        model = copy.deepcopy(m0)
+        red = BucketedGradReducer(list(model.named_parameters()), world_size=1)
+        red.zero_grad()
+        torch.manual_seed(9)
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            logits, _ = model(x, lx, y, 1.0, False)
+        loss, _ = masked_ce(logits, y, ly)
+        (loss * 1024.0).backward()
+        red.finish()
+        torch.cuda.synchronize()
+        res[pipe] = ({n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}, dict(LF.last_pipeline_stats))
+    st = res['1'][1]
+    print('tiles (early, late):', st)
+    assert any(k[0] == 'wgrad' and e >= 4 for k, (e, _) in st.items()), st
+    assert not any(k[0] == 'wgrad' for k in res['0'][1])
+    for n, g in res['0'][0].items():
+        h = res['1'][0][n]
+        if n.startswith('listen.base.') and 'bias' not in n:
+            scale = g.abs().max().item()
+            assert (g - h).abs().max().item() <= 1e-5 * scale + 1e-12, (n, (g - h).abs().max().item(), scale)
+            assert not torch.equal(g, h) or scale == 0.0, n          # the tiled form really ran
+        else:
+            assert torch.equal(g, h), n
