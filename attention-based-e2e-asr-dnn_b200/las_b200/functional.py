@@ -340,7 +340,18 @@ _PIPE_TILE = 128
 
 
 class _PreGates:
-    __slots__ = ('gates', 'wcat', 'event', 'x16', 'wkey', 'pyramid', 'T', 'Kp', 'Dp', 'tiles_early', 'tiles_late')
+    """Gates of the next layer, projected on the second stream.  Holds every tensor that stream touches: they were allocated on the
+    main stream, so their memory may only go back to the allocator once the main stream is ordered behind the second stream's work --
+    which the consumer does (wait_event) when it takes the gates over, and __del__ does when nobody did.  (No Tensor.record_stream: its
+    event-deferred frees make the caching allocator's steady state depend on timing -- seen as 40 -> 45 ms steps in one run out of three.)"""
+    __slots__ = ('gates', 'wcat', 'event', 'x16', 'wkey', 'pyramid', 'T', 'Kp', 'Dp', 'tiles_early', 'tiles_late', 'keep', 'consumed')
+
+    def __del__(self):
+        try:
+            if not getattr(self, 'consumed', True):
+                torch.cuda.current_stream(self.gates.device).wait_event(self.event)
+        except Exception:                  # interpreter shutdown
+            pass
 
 
 def _weights_key(weights) -> tuple:
@@ -433,10 +444,8 @@ def _pipeline_issue(prep, nxt, out16, Bn, T, ev_ready, ev_rec_done):
     pre.gates, pre.wcat, pre.event, pre.x16 = prep['gates'], prep['wcat'], ev, out16
     pre.wkey, pre.pyramid, pre.T, pre.Kp, pre.Dp = _weights_key(nxt['weights']), prep['pyr'], Tn, Kp, Dp
     pre.tiles_early, pre.tiles_late = len(early), len(late)
-    # allocated on the main stream, used on the second one: the allocator must not hand the memory out again before that stream is done
-    # (the stream waits on the counters may still be pending when this function returns; the gates may never be taken over)
-    for t in (prep['counters'], prep['b1'], prep['b2'], prep['wcat'], prep['gates'], out16):
-        t.record_stream(side)
+    pre.keep = (prep['counters'], prep['b1'], prep['b2'])        # see the class comment
+    pre.consumed = False
     return pre
 
 
@@ -587,6 +596,7 @@ class LSTMLayerFunction(torch.autograd.Function):
                 # projected beside the previous layer's recurrence (second stream): take it over once that stream is done
                 gates, wcat = pre.gates, pre.wcat
                 torch.cuda.current_stream(dev).wait_event(pre.event)
+                pre.consumed = True
             else:
                 wcat = torch.empty(NG, Kp, dtype=torch.bfloat16, device=dev)
                 for d in range(ndir):
@@ -751,9 +761,7 @@ class LSTMLayerFunction(torch.autograd.Function):
                 if early:
                     third = _dgrad_stream(dev)
                     ev = _issue_tiles(third, dx_pipe['counters'], ncl.value, rs.value, early, late, dx_pipe['ev_ready'], ev_done, dx_tile)
-                    main.wait_event(ev)
-                    for t in (dx_pipe['counters'], dGb, wcat, dx):
-                        t.record_stream(third)
+                    main.wait_event(ev)                  # everything the main stream does from here on is ordered behind the tiles
                 else:
                     for _, t0, t1 in late:
                         dx_tile(t0, t1)

@@ -471,9 +471,9 @@ def main():
             (loss * scale).backward()
             rw_red.finish()
             rw_opt.step_fused(inv_scale=1.0 / (scale * world), max_norm=5.0)
-        for _ in range(3):
+        for _ in range(8):                  # the decoder-loop graphs (forward / backward, three segments each) settle within a few steps
             rw_step()
-        ms_rw = timed(rw_step, 5) / 5
+        ms_rw = timed(rw_step, 10) / 10
         rewriter = dict(metric='rewriter_train_sequences_per_sec', value=world * Br / (ms_rw / 1e3), unit='sequences/s', ms_per_step=ms_rw,
                         config=dict(workload=f'Rewriter (config/rewriter.yml dims: emb 256, 2x BiLSTM 256, P 128 x 4 heads, dec 256/128, yml dropouts), '
                                              f'batch {Br}/GPU, Tx = L = {Tr}, tf_rate 0.5 (never takes effect: src/lmtrain.py:231), fwd+bwd+AdamW'))
