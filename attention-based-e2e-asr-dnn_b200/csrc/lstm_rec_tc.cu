@@ -459,26 +459,45 @@ __device__ __forceinline__ uint64_t make_desc_k_noswz(uint32_t saddr) {     // K
     return d;
 }
 
-template <int CHAINS>
-__global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const RecTcArgs a) {
+// =====================================================================================================================
+// The kernel: 384 threads = warps 0, 2, 3 helpers, warp 1 UMMA issue, warps 4..11 epilogue.
+//   * epilogue warps 4+q and 8+q share TMEM lane quarter q (= gate q) and split the 32 batch columns of the tile in halves: every
+//     thread activates 16 gates and updates 4 cells (round 2; with four epilogue warps -- 32 activations and 8 cells per thread -- a
+//     step took 2.45 us instead of 2.34);
+//   * the helper warps do everything in global memory that is not the step-to-step dependency: they stage the input projection
+//     x-gates of step s+1 in shared memory while step s runs and copy the activated gates of step s out (backward reads them); the
+//     epilogue warps keep only the h / c / out stores: after publishing, an SM's global-memory instructions queue behind its
+//     outgoing DSMEM copies, and that queue -- not the exchange -- had become the critical path;
+//   * optional progress counters for consumers on other streams (las_lstm_rec_fwd_arm_progress).
+// One chain per CTA.
+// =====================================================================================================================
+constexpr int NTHREADS8 = 384;
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS8, 1) lstm_rec_fwd_dsm_kernel(const RecTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const int H = a.H, T = a.T;
     const int RS = H / UNITS;                                     // CTAs per group = cluster size
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t TILE = (uint32_t)RS * 2048u;                   // 32 rows x H bf16
-    const uint32_t h_sm = base;                                   // [chain][parity][TILE]
-    const uint32_t stage_sm = h_sm + CHAINS * 2 * TILE;         // [chain][2 KB]: this CTA's slice in core-matrix layout
-    const uint32_t ex_off = (stage_sm - smem_u32(smem_raw)) + CHAINS * 2048;
+    const uint32_t h_sm = base;                                   // [parity][TILE]
+    const uint32_t stage_sm = h_sm + 2 * TILE;                    // 2 KB: this CTA's slice in core-matrix layout
+    const uint32_t ex_off = (stage_sm - smem_u32(smem_raw)) + 2048;
     float* ex = reinterpret_cast<float*>(smem_raw + ex_off);      // [4][32][32] gate exchange
-    float* xgs = ex + 4 * 32 * 32;                                // [2][4][32][32] input projection of the next steps (CHAINS == 1: staged by the helper warps)
+    float* xgs = ex + 4 * 32 * 32;                                // [2][4][32][32] input projection of the next steps
     const uint32_t bar_base = smem_u32(smem_raw) + ex_off + 3 * 4 * 32 * 32 * 4;
-    auto hbar = [&](int c, int par, int half) { return bar_base + 8u * ((c * 2 + par) * 2 + half); };       // 8 barriers
-    auto tfull_bar = [&](int c) { return bar_base + 8u * (8 + c); };
+    auto hbar = [&](int par, int half) { return bar_base + 8u * (par * 2 + half); };
+    const uint32_t tfull_bar = bar_base + 8u * 8;
     const uint32_t tmem_slot = bar_base + 8u * 10;
-    // accumulators free again (epilogue -> MMA warp).  With the counter/TMA exchange the operand of step s+1 cannot arrive before
-    // this CTA has published step s, i.e. after its epilogue has read the accumulators; here the first half of the operand comes
-    // from OTHER CTAs only when r >= RS/2, so that ordering must be explicit.
-    auto tempty_bar = [&](int c) { return bar_base + 8u * (11 + c); };
+    const uint32_t tempty_bar = bar_base + 8u * 11;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     uint8_t* stage_ptr = smem_raw + (stage_sm - smem_u32(smem_raw));
 
@@ -490,8 +509,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
     const int nhalf = RS >= 2 ? 2 : 1;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < 8; ++i) mbar_init(bar_base + 8u * i, 1);
-        for (int c = 0; c < MAX_CHAINS; ++c) { mbar_init(tfull_bar(c), 1); mbar_init(tempty_bar(c), 4); }
+        for (int i = 0; i < 4; ++i) mbar_init(bar_base + 8u * i, 1);
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const uint32_t tmem_cols = 512u;
@@ -504,7 +524,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const uint32_t tmem_w = tmem_base + MAX_CHAINS * FWD_NACC * NB_SLICE;
-    if (warp >= 4) {
+    if (warp >= 4 && warp < 8) {
         // resident A operand: this CTA's 128 x H slice of W_hh in tensor memory (TMEM lane = gate row, two bf16 per column)
         const int qq = warp & 3;
         const uint32_t* wrow = reinterpret_cast<const uint32_t*>(a.w_gl + ((long long)dir * 4 * H + qq * H + r * UNITS + lane) * H);
@@ -528,45 +548,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
     if (warp == 1) {
         // ===== MMA issuer (whole warp walks the loop, one elected lane issues) =====
         for (int s = 1; s < T; ++s) {
+            if (sg >= a.nslices) continue;
             const int par = (s - 1) & 1;                          // buffer holding h_{s-1}
             const uint32_t phase = (uint32_t)(((s - 1) >> 1) & 1);
-            for (int c = 0; c < CHAINS; ++c) {
-                const int slice = sg + c * a.bsg;
-                if (slice >= a.nslices) continue;
-                const uint32_t buf = h_sm + (uint32_t)(c * 2 + par) * TILE;
-                if (s > 1) mbar_wait(tempty_bar(c), (uint32_t)(s & 1));          // the epilogue has read step s-1's accumulators
-                for (int hf = 0; hf < nhalf; ++hf) {
-                    if (lane == 0) mbar_arrive_expect_tx(hbar(c, par, hf), (uint32_t)(hf == 0 ? halfsrc : RS - halfsrc) * 2048u);
-                    __syncwarp();
-                    mbar_wait(hbar(c, par, hf), phase);
-                    if (lane == 0 && hf == 0) REC_STAMP(2);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const int ks_lo = hf == 0 ? 0 : halfsrc * 2, ks_hi = hf == 0 ? (nhalf == 2 ? halfsrc * 2 : RS * 2) : RS * 2;    // 16-unit k-steps
-                        for (int ks = ks_lo; ks < ks_hi; ++ks) {
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((c * FWD_NACC + (ks & 3)) * NB_SLICE);
-                            const uint64_t bd = make_desc_k_noswz(buf + (uint32_t)ks * 1024u);
-                            umma_bf16_ts(d_tmem, tmem_w + ks * 8, bd, IDESC, ks >= 4 ? 1u : 0u);
-                        }
-                        if (ks_hi == RS * 2) umma_commit(tfull_bar(c));
+            const uint32_t buf = h_sm + (uint32_t)par * TILE;
+            if (s > 1) mbar_wait(tempty_bar, (uint32_t)(s & 1));          // the epilogue has read step s-1's accumulators
+            for (int hf = 0; hf < nhalf; ++hf) {
+                if (lane == 0) mbar_arrive_expect_tx(hbar(par, hf), (uint32_t)(hf == 0 ? halfsrc : RS - halfsrc) * 2048u);
+                __syncwarp();
+                mbar_wait(hbar(par, hf), phase);
+                if (lane == 0 && hf == 0) REC_STAMP(2);
+                tc_fence_after();
+                if (elect_one()) {
+                    const int ks_lo = hf == 0 ? 0 : halfsrc * 2, ks_hi = hf == 0 ? (nhalf == 2 ? halfsrc * 2 : RS * 2) : RS * 2;    // 16-unit k-steps
+                    for (int ks = ks_lo; ks < ks_hi; ++ks) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((ks & 3) * NB_SLICE);
+                        const uint64_t bd = make_desc_k_noswz(buf + (uint32_t)ks * 1024u);
+                        umma_bf16_ts(d_tmem, tmem_w + ks * 8, bd, IDESC, ks >= 4 ? 1u : 0u);
                     }
-                    __syncwarp();
+                    if (ks_hi == RS * 2) umma_commit(tfull_bar);
                 }
-                if (lane == 0) REC_STAMP(3);
+                __syncwarp();
             }
+            if (lane == 0) REC_STAMP(3);
         }
     } else if (warp < 4) {
-        // ===== helper warps (0, 2, 3; CHAINS == 1): everything in global memory that is not the step-to-step dependency.
-        //   * stage the input projection x-gates of step s+1 in shared memory while step s runs (the epilogue then reads them
-        //     with LDS instead of waiting on 32 global loads per thread right when the tensor pipe delivers);
-        //   * copy the activated gates of step s from the exchange tile to global memory (backward reads them).
-        // The epilogue warps keep only the 24 stores per thread of h / c / out: after publishing, their global-memory
-        // instructions queue behind the outgoing DSMEM copies, and that queue -- not the exchange -- had become the critical path.
-        if (CHAINS == 1 && sg < a.nslices) {
+        // ===== helper warps (0, 2, 3): x-gate staging for the next step, gate saves of this one =====
+        if (sg < a.nslices) {
             const int hw = warp == 0 ? 0 : warp - 1;       // 0..2
             const int b0 = sg * NB_SLICE;
             const long long gstride = (long long)T * a.ndir * 4 * H;
-            // 128-bit accesses: lane = (row-in-group = lane >> 3, 4 units = 4 * (lane & 7)); 32 groups of 4 (gate, row) pairs over 3 warps
             const int rg = lane >> 3, c4 = 4 * (lane & 7);
             float4 xr[11];
             auto load_x = [&](int s2) {
@@ -589,14 +600,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
             };
             load_x(0);
             store_x(0);
-            asm volatile("bar.arrive 4, 224;" ::: "memory");                      // x-gates of step 0 staged
+            asm volatile("bar.arrive 4, 352;" ::: "memory");                      // x-gates of step 0 staged
             for (int s = 0; s < T; ++s) {
                 const int t = (dir == 0) ? s : (T - 1 - s);
                 if (s + 1 < T) load_x(s + 1);                                      // in flight while waiting below
-                asm volatile("bar.sync 2, 224;" ::: "memory");                    // `ex` of step s complete (and xgs[s & 1] consumed)
+                asm volatile("bar.sync 2, 352;" ::: "memory");                    // `ex` of step s complete (and xgs[s & 1] consumed)
                 // the epilogue warps stored h / c / out of step s-1 before arriving at that barrier: every `progress_every` steps one
                 // helper thread makes them visible device-wide and counts this CTA in (a consumer on another stream waits for the
-                // cluster's count: the next layer's gate GEMM starts on the rows both directions have passed, DESIGN.md 4.6)
+                // cluster's count: the next layer's gate GEMM starts on the rows both directions have passed, DESIGN.md 4.7)
                 if (a.progress && warp == 0 && lane == 0 && s > 0 && s % a.progress_every == 0) {
                     __threadfence();
                     atomicAdd(a.progress + dir * gridDim.y + sg, 1u);
@@ -610,156 +621,115 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_dsm_kernel(const Rec
                             *reinterpret_cast<float4*>(gb + (long long)(b0 + n) * gstride + qq * H) = *reinterpret_cast<const float4*>(ex + pr * 32 + c4);
                     }
                 }
-                asm volatile("bar.arrive 3, 224;" ::: "memory");                  // `ex` may be rewritten
+                asm volatile("bar.arrive 3, 352;" ::: "memory");                  // `ex` may be rewritten
                 if (s + 1 < T) {
                     store_x((s + 1) & 1);                                          // that buffer was consumed at step s-1
-                    asm volatile("bar.arrive 4, 224;" ::: "memory");              // x-gates of step s+1 staged
+                    asm volatile("bar.arrive 4, 352;" ::: "memory");              // x-gates of step s+1 staged
                 }
             }
         }
-    } else {
-        // ===== epilogue: one warp per gate =====
-        const int q = warp & 3, j = lane;          // gate q, unit r*32 + j
-        const int te = (warp - 4) * 32 + lane;     // 0..127
+    } else if (sg < a.nslices) {
+        // ===== epilogue: warp e = warp - 4: gate q = e & 3 (TMEM lane quarter), column half hf = e >> 2 =====
+        const int e = warp - 4, q = e & 3, hf = e >> 2, j = lane;
+        const int te = e * 32 + lane;              // 0..255
         const int u = r * UNITS + j;
-        const bool helpers = CHAINS == 1;
-        float xg[32];
-        float cst[CHAINS][8];
-        int lenr[CHAINS][8];
+        const int b0 = sg * NB_SLICE;
+        float xg[16];
+        float cst[4], mreg[4];
+        int lenr[4];
 #pragma unroll
-        for (int c = 0; c < CHAINS; ++c)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                cst[c][i] = 0.f;
-                const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
-                lenr[c][i] = (sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
-            }
-        // locked-dropout mask of this thread's (row, unit) pairs: constant over time -> registers (a load per timestep sat on the
-        // critical path of every step: 2.49 -> 3.05 us per timestep with the yml's dropouts on)
-        float mreg[CHAINS][8];
-#pragma unroll
-        for (int c = 0; c < CHAINS; ++c)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
-                mreg[c][i] = (a.mask && sg + c * a.bsg < a.nslices && b < a.B) ? a.mask[(long long)b * F + dir * H + u] : 1.f;
-            }
-        for (int c = 0; c < CHAINS; ++c) {
-            const int slice = sg + c * a.bsg;
-            if (slice >= a.nslices) continue;
-            for (int i = 0; i < 8; ++i) {
-                const int b = slice * NB_SLICE + q * 8 + i;
-                if (b < a.B) {
-                    const long long o0 = (long long)b * brow + dir * H + u, o1 = o0 + (long long)(T + 1) * F;
-                    a.cs_pad[o0] = 0.f; a.cs_pad[o1] = 0.f;
-                    if (a.hs_pad) { a.hs_pad[o0] = 0.f; a.hs_pad[o1] = 0.f; }
-                    if (a.hs16) { a.hs16[o0] = __float2bfloat16(0.f); a.hs16[o1] = __float2bfloat16(0.f); }
-                }
+        for (int i = 0; i < 4; ++i) {
+            cst[i] = 0.f;
+            const int b = b0 + e * 4 + i;           // cell phase: warp e owns batch rows 4e .. 4e+3
+            lenr[i] = b < a.B ? a.lens[b] : 0;
+            mreg[i] = (a.mask && b < a.B) ? a.mask[(long long)b * F + dir * H + u] : 1.f;
+            if (b < a.B) {
+                const long long o0 = (long long)b * brow + dir * H + u, o1 = o0 + (long long)(T + 1) * F;
+                a.cs_pad[o0] = 0.f; a.cs_pad[o1] = 0.f;
+                if (a.hs_pad) { a.hs_pad[o0] = 0.f; a.hs_pad[o1] = 0.f; }
+                if (a.hs16) { a.hs16[o0] = __float2bfloat16(0.f); a.hs16[o1] = __float2bfloat16(0.f); }
             }
         }
         for (int s = 0; s < T; ++s) {
             const int t = (dir == 0) ? s : (T - 1 - s);
+            asm volatile("bar.sync 4, 352;" ::: "memory");              // the helper warps have staged this step's x-gates
 #pragma unroll
-            for (int c = 0; c < CHAINS; ++c) {
-                const int slice = sg + c * a.bsg;
-                if (slice >= a.nslices) continue;
-                const int b0 = slice * NB_SLICE;
-                float* gbase = a.gates + ((long long)t * a.ndir + dir) * 4 * H + q * H + u;
-                const long long gstride = (long long)T * a.ndir * 4 * H;
-                if (helpers) {
-                    asm volatile("bar.sync 4, 224;" ::: "memory");              // the helper warps have staged this step's x-gates
+            for (int n = 0; n < 16; ++n) xg[n] = xgs[((s & 1) * 128 + q * 32 + 16 * hf + n) * 32 + j];
+            if (te == 0) REC_STAMP(4);
+            if (s > 0) {
+                mbar_wait(tfull_bar, (uint32_t)((s - 1) & 1));
+                if (te == 0) REC_STAMP(5);
+                tc_fence_after();
 #pragma unroll
-                    for (int n = 0; n < 32; ++n) xg[n] = xgs[((s & 1) * 128 + q * 32 + n) * 32 + j];
-                } else {
+                for (int acc = 0; acc < FWD_NACC; ++acc) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NB_SLICE + 16 * hf), v);
 #pragma unroll
-                    for (int n = 0; n < 32; ++n) xg[n] = (b0 + n < a.B) ? gbase[(long long)(b0 + n) * gstride] : 0.f;
-                }
-                if (te == 0) REC_STAMP(4);
-                if (s > 0) {
-                    mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
-                    if (te == 0) REC_STAMP(5);
-                    tc_fence_after();
-#pragma unroll
-                    for (int acc = 0; acc < FWD_NACC; ++acc) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c * FWD_NACC + acc) * NB_SLICE), v);
-#pragma unroll
-                        for (int n = 0; n < 32; ++n) xg[n] += __uint_as_float(v[n]);
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(c));
-                    if (te == 0) REC_STAMP(6);
-                }
-                if (helpers && s > 0) asm volatile("bar.sync 3, 224;" ::: "memory");       // the savers are done with the previous step's `ex`
-#pragma unroll
-                for (int n = 0; n < 32; ++n) {
-                    const float act = (q == 2) ? tanh_fast(xg[n]) : sigmoid_fast(xg[n]);
-                    ex[(q * 32 + n) * 32 + j] = act;
-                    xg[n] = act;                                   // kept for the deferred save below (when there are no savers)
+                    for (int n = 0; n < 16; ++n) xg[n] += __uint_as_float(v[n]);
                 }
                 tc_fence_before();
-                // the bulk copies of the previous step must have finished READING the staging tile before it is rewritten
-                if (te < RS && s > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                named_bar_sync(1, 128);
-                if (helpers) asm volatile("bar.arrive 2, 224;" ::: "memory");               // `ex` complete: the savers may copy it out
-                if (te == 0) REC_STAMP(7);
-                float hh[8], cc[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int n = q * 8 + i;
-                    const float gi = ex[(0 * 32 + n) * 32 + j], gf = ex[(1 * 32 + n) * 32 + j];
-                    const float gg = ex[(2 * 32 + n) * 32 + j], go = ex[(3 * 32 + n) * 32 + j];
-                    const bool valid = t < lenr[c][i];
-                    cc[i] = 0.f; hh[i] = 0.f;
-                    if (valid) {
-                        cc[i] = fmaf(gf, cst[c][i], gi * gg);
-                        hh[i] = go * tanh_fast(cc[i]);
-                    }
-                    cst[c][i] = cc[i];
-                }
-                if (s + 1 < T) {
-                    // stage h_t (bf16) in core-matrix layout: core (kc = j/8, ng = q), row i, element j%8
-                    __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage_ptr + c * 2048 + (j >> 3) * 512 + q * 128) + (j & 7);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) st[i * 8] = __float2bfloat16(hh[i]);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                }
-                named_bar_sync(1, 128);
-                if (te == 0) REC_STAMP(8);
-                if (s + 1 < T && te < RS) {
-                    // thread `te` pushes this CTA's slice into peer te's buffer for step s+1 (parity s&1) and signals its barrier
-                    const int par = s & 1;
-                    const uint32_t dst = mapa_u32(h_sm + (uint32_t)(c * 2 + par) * TILE + (uint32_t)r * 2048u, (uint32_t)te);
-                    const uint32_t rbar = mapa_u32(hbar(c, par, (nhalf == 2 && r >= halfsrc) ? 1 : 0), (uint32_t)te);
-                    bulk_copy_to_peer(dst, stage_sm + c * 2048, 2048u, rbar);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                if (te == 0) REC_STAMP(9);
-                // ... then what only backward / the next layer read; these stores overlap the exchange and the next step's UMMAs
-                if (a.save && !helpers) {
-#pragma unroll
-                    for (int n = 0; n < 32; ++n)
-                        if (b0 + n < a.B) gbase[(long long)(b0 + n) * gstride] = xg[n];
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int b = b0 + q * 8 + i;
-                    if (b < a.B) {
-                        const long long so = (long long)b * brow + (long long)(t + 1) * F + dir * H + u;
-                        if (a.hs_pad) a.hs_pad[so] = hh[i];
-                        if (a.hs16) a.hs16[so] = __float2bfloat16(hh[i]);
-                        a.cs_pad[so] = cc[i];
-                        if (a.out || a.out16) {
-                            const float m = mreg[c][i];
-                            const long long oo = ((long long)b * T + t) * F + dir * H + u;
-                            if (a.out) a.out[oo] = hh[i] * m;
-                            if (a.out16) a.out16[oo] = __float2bfloat16(hh[i] * m);
-                        }
-                    }
-                }
-                if (te == 0) REC_STAMP(10);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar);
+                if (te == 0) REC_STAMP(6);
             }
+            if (s > 0) asm volatile("bar.sync 3, 352;" ::: "memory");       // the savers are done with the previous step's `ex`
+#pragma unroll
+            for (int n = 0; n < 16; ++n) ex[(q * 32 + 16 * hf + n) * 32 + j] = (q == 2) ? tanh_fast(xg[n]) : sigmoid_fast(xg[n]);
+            tc_fence_before();
+            // the bulk copies of the previous step must have finished READING the staging tile before it is rewritten
+            if (te < RS && s > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            named_bar_sync(1, 256);
+            asm volatile("bar.arrive 2, 352;" ::: "memory");               // `ex` complete: the savers may copy it out
+            if (te == 0) REC_STAMP(7);
+            float hh[4], cc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int n = e * 4 + i;
+                const float gi = ex[(0 * 32 + n) * 32 + j], gf = ex[(1 * 32 + n) * 32 + j];
+                const float gg = ex[(2 * 32 + n) * 32 + j], go = ex[(3 * 32 + n) * 32 + j];
+                const bool valid = t < lenr[i];
+                cc[i] = 0.f; hh[i] = 0.f;
+                if (valid) {
+                    cc[i] = fmaf(gf, cst[i], gi * gg);
+                    hh[i] = go * tanh_fast(cc[i]);
+                }
+                cst[i] = cc[i];
+            }
+            if (s + 1 < T) {
+                // stage h_t (bf16) in core-matrix layout: core (kc = j/8, ng = row/8 = e>>1), row-in-core (e&1)*4 + i, element j%8
+                __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage_ptr + (j >> 3) * 512 + (e >> 1) * 128 + (e & 1) * 64) + (j & 7);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st[i * 8] = __float2bfloat16(hh[i]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            named_bar_sync(1, 256);
+            if (te == 0) REC_STAMP(8);
+            if (s + 1 < T && te < RS) {
+                // thread `te` pushes this CTA's slice into peer te's buffer for step s+1 (parity s&1) and signals its barrier
+                const int par = s & 1;
+                const uint32_t dst = mapa_u32(h_sm + (uint32_t)par * TILE + (uint32_t)r * 2048u, (uint32_t)te);
+                const uint32_t rbar = mapa_u32(hbar(par, (nhalf == 2 && r >= halfsrc) ? 1 : 0), (uint32_t)te);
+                bulk_copy_to_peer(dst, stage_sm, 2048u, rbar);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (te == 0) REC_STAMP(9);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int b = b0 + e * 4 + i;
+                if (b < a.B) {
+                    const long long so = (long long)b * brow + (long long)(t + 1) * F + dir * H + u;
+                    if (a.hs_pad) a.hs_pad[so] = hh[i];
+                    if (a.hs16) a.hs16[so] = __float2bfloat16(hh[i]);
+                    a.cs_pad[so] = cc[i];
+                    if (a.out || a.out16) {
+                        const float m = mreg[i];
+                        const long long oo = ((long long)b * T + t) * F + dir * H + u;
+                        if (a.out) a.out[oo] = hh[i] * m;
+                        if (a.out16) a.out16[oo] = __float2bfloat16(hh[i] * m);
+                    }
+                }
+            }
+            if (te == 0) REC_STAMP(10);
         }
         if (te < RS) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
@@ -975,12 +945,12 @@ static int rec_fwd_tc_impl(float* gates, const void* w_hh_bf16, const int* lens,
         // at most 6 clusters: with 8 (B = 128 bidirectional) every GPC exchanges at once and a step takes 4.9 us instead of 2.5
         const bool few = p.nslices * ndir <= 6 || (de && atoi(de) == 2);
         if ((!de || atoi(de) != 0) && few && p.chains == 1 && p.rs <= 16 && H <= 512 && dsmem <= (size_t)las_device_info()->max_smem_optin) {
-            auto kd = p.chains == 1 ? lstm_rec_fwd_dsm_kernel<1> : lstm_rec_fwd_dsm_kernel<2>;
+            auto kd = lstm_rec_fwd_dsm_kernel;
             cudaError_t e1 = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);
             if (e1 == cudaSuccess && p.rs > 8) e1 = cudaFuncSetAttribute(kd, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             if (e1 == cudaSuccess) {
                 cudaLaunchConfig_t cfg{};
-                cfg.gridDim = dim3(p.rs, p.bsg, ndir); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = dsmem; cfg.stream = st;
+                cfg.gridDim = dim3(p.rs, p.bsg, ndir); cfg.blockDim = dim3(NTHREADS8); cfg.dynamicSmemBytes = dsmem; cfg.stream = st;
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = p.rs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
