@@ -1791,7 +1791,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
 // no global exchange buffer), and the gate-partial reduction uses the same push.  W_hh^T tile resident in tensor memory.
 // Cluster rank = ub * 4 + kq.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const RecTcBwdArgs a) {
+__global__ void __launch_bounds__(NTHREADS8, 1) lstm_rec_bwd_dsm_kernel(const RecTcBwdArgs a) {
     constexpr bool WTMEM = true;
     extern __shared__ uint8_t smem_raw[];
     if (a.start_ctr && threadIdx.x == 0) atomicAdd(a.start_ctr, 1u);   // "this CTA is resident"
@@ -1840,7 +1840,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
         mbar_init(wbar, 1);
         mbar_init(rbar(0), 1); mbar_init(rbar(1), 1);
         for (int i = 0; i < 4; ++i) mbar_init(hbar(i >> 1, i & 1), 1);
-        mbar_init(tempty, 4);
+        mbar_init(tempty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // TMEM map: BWD_NACC independent accumulators per chain first, then (WTMEM) the resident W_hh^T tile (H/2 columns)
@@ -1855,7 +1855,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
     const uint32_t tmem_base = *tmem_slot_ptr;
     const uint32_t tmem_w = tmem_base + MAX_CHAINS * BWD_NACC * NB_SLICE;
     if (WTMEM) {
-        if (warp >= 4) {
+        if (warp >= 4 && warp < 8) {
             // A operand in tensor memory: TMEM lane = unit row of the block, column pair = two consecutive k (gate rows of gate kq)
             const int qq = warp & 3;
             const uint32_t* wrow = reinterpret_cast<const uint32_t*>(a.w_t + ((long long)(dir * H + ub * 128 + qq * 32 + lane)) * G4 + kq * H);
@@ -1881,23 +1881,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
     // Epilogue ownership: thread (warp q, lane) finalises FOUR consecutive units u0..u0+3 (u0 = block base + 4*(lane & 7)) for TWO
     // batch rows (q*8 + 2*(lane >> 3) + {0, 1}), so that every global access of the pointwise backward is a 128-bit one: a quarter
     // of the memory instructions of a one-unit-per-lane mapping (their issue rate, not the exchange, had become the critical path).
+    // EIGHT epilogue warps (round 2; 4 units x ONE batch row per thread): warp e = warp - 4 reads TMEM lane quarter q = e & 3, batch columns
+    // 16 (e >> 2) .. + 16 of the accumulators, and finalises batch rows 4e .. 4e + 3 of the slice
     const int q = warp & 3, j = lane;
+    const int e8 = warp >= 4 ? warp - 4 : 0, hf8 = e8 >> 2;
     const int te = (warp - 4) * 32 + lane;
     const int jj = lane & 7, rr = lane >> 3;
     const int u0 = ub * 128 + kq * 32 + 4 * jj;        // first of the 4 units this thread finalises
-    const int rl0 = q * 8 + rr * 2;                    // first of its 2 batch rows inside the 32-row slice
-    float4 dcst[MAX_CHAINS][2];
-    float4 mkr[MAX_CHAINS][2];                         // locked-dropout mask: constant over time
-    float4 cnext[MAX_CHAINS][2];                       // c_{t-1} loaded at this step = c_t of the next step (time runs backwards)
+    const int rl0 = e8 * 4 + rr;                       // its batch row inside the 32-row slice
+    constexpr int NR = 1;                              // rows per thread
+    float4 dcst[MAX_CHAINS][NR];
+    float4 mkr[MAX_CHAINS][NR];                        // locked-dropout mask: constant over time
+    float4 cnext[MAX_CHAINS][NR];                      // c_{t-1} loaded at this step = c_t of the next step (time runs backwards)
     float4 dbacc[MAX_CHAINS][4];                       // bias-gradient partial sums (gate x 4 units) over this thread's rows, all steps
-    int lenr[MAX_CHAINS][2];
+    int lenr[MAX_CHAINS][NR];
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < MAX_CHAINS; ++c) {
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) dbacc[c][gq] = z4;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NR; ++i) {
             dcst[c][i] = z4; cnext[c][i] = z4;
             const int b = (sg + c * a.bsg) * NB_SLICE + rl0 + i;
             lenr[c][i] = (warp >= 4 && c < a.chains && sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
@@ -1921,8 +1925,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
             const uint32_t rphase = (uint32_t)((riter >> 1) & 1);
             if (s > 0) ++riter;
             ++iter;
-            float4 gi[2], gf[2], gg[2], go[2], ct[2], cp[2], dh[2], rec[2];
-            bool valid[2];
+            float4 gi[NR], gf[NR], gg[NR], go[NR], ct[NR], cp[NR], dh[NR], rec[NR];
+            bool valid[NR];
             if (warp == 0) {
                 // (no producer: the operand is pushed into this CTA's buffers by its peers)
             } else if (warp == 1) {
@@ -1954,7 +1958,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
             } else if (warp >= 4) {
                 // operands of the pointwise backward for this thread's unit, issued before waiting on the tensor pipe
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < NR; ++i) {
                     const int b = b0 + rl0 + i;
                     valid[i] = t < lenr[c][i];
                     // pure 128-bit loads, no branches: rows past B are clamped to a valid address; invalid rows are zeroed in the
@@ -1975,31 +1979,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
                     mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
                     if (te == 0) REC_STAMP(5);
                     tc_fence_after();
-                    float accv[32];
+                    float accv[16];
 #pragma unroll
                     for (int acc = 0; acc < BWD_NACC; ++acc) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c * BWD_NACC + acc) * NB_SLICE), v);
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c * BWD_NACC + acc) * NB_SLICE + 16 * hf8), v);
 #pragma unroll
-                        for (int n = 0; n < 32; ++n) accv[n] = acc ? accv[n] + __uint_as_float(v[n]) : __uint_as_float(v[n]);
+                        for (int n = 0; n < 16; ++n) accv[n] = acc ? accv[n] + __uint_as_float(v[n]) : __uint_as_float(v[n]);
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty);
-                    // TMEM lane = unit (32q + lane) of the block, column = batch row.  Warp q holds exactly the 32 units CTA q of the
-                    // cluster finalises: stage them as [row][unit] and push the 4 KB piece into CTA q's receive buffer
+                    // TMEM lane = unit (32q + lane) of the block, column = batch row.  Warps q and 4+q hold the 32 units CTA q of the
+                    // cluster finalises, 16 batch rows each: stage them as [row][unit] and push the 2 KB half piece into CTA q's receive buffer
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the piece staged two iterations ago has been read
                     __syncwarp();
-                    float* stg = part0 + (rpar * 4 + q) * 1024;
+                    float* stg = part0 + (rpar * 4 + q) * 1024 + hf8 * 512;
 #pragma unroll
-                    for (int n = 0; n < 32; ++n) stg[n * 32 + lane] = accv[n];
+                    for (int n = 0; n < 16; ++n) stg[n * 32 + lane] = accv[n];
                     tc_fence_before();
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
                         const uint32_t peer = (uint32_t)(ub * 4 + q);
-                        const uint32_t dst = mapa_u32(rcv_saddr0 + (uint32_t)((rpar * 4 + kq) * 4096), peer);
-                        bulk_copy_to_peer(dst, part_saddr0 + (uint32_t)((rpar * 4 + q) * 4096), 4096u, mapa_u32(rbar(rpar), peer));
+                        const uint32_t dst = mapa_u32(rcv_saddr0 + (uint32_t)((rpar * 4 + kq) * 4096 + hf8 * 2048), peer);
+                        bulk_copy_to_peer(dst, part_saddr0 + (uint32_t)((rpar * 4 + q) * 4096 + hf8 * 2048), 2048u, mapa_u32(rbar(rpar), peer));
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     if (te == 0) {
@@ -2014,7 +2018,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
                     if (te == 0) REC_STAMP(7);
                     const float* rcv = rcv0 + rpar * 4 * 1024;
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
+                    for (int i = 0; i < NR; ++i) {
                         const int o = (rl0 + i) * 32 + 4 * jj;
                         const float4 p0 = *reinterpret_cast<const float4*>(rcv + o), p1 = *reinterpret_cast<const float4*>(rcv + 1024 + o);
                         const float4 p2 = *reinterpret_cast<const float4*>(rcv + 2048 + o), p3 = *reinterpret_cast<const float4*>(rcv + 3072 + o);
@@ -2031,7 +2035,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1, 256);
                 auto pw = [&](float gi_, float gf_, float gg_, float go_, float ct_, float cp_, float dh_, float mk_, float rec_, float dc_,
                               bool ok, float& dai, float& daf, float& dag, float& dao, float& dcn) {
                     dai = daf = dag = dao = dcn = 0.f;
@@ -2053,7 +2057,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
                     return r;
                 };
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < NR; ++i) {
                     const int b = b0 + rl0 + i;
                     float4 dI, dF, dG, dO, dC;
                     pw(gi[i].x, gf[i].x, gg[i].x, go[i].x, ct[i].x, cp[i].x, dh[i].x, mkr[c][i].x, rec[i].x, dcst[c][i].x, valid[i], dI.x, dF.x, dG.x, dO.x, dC.x);
@@ -2065,7 +2069,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
                     // what the peers' next step reads: bf16 d(pre-activation), staged per gate in the UMMA no-swizzle core-matrix layout
                     // (core (kc = unit/8, ng = row/8) at kc*512 + ng*128; row-in-core 16 B apart): 4 units = one 64-bit store
                     if (s + 1 < T) {
-                        uint8_t* xp = xst_ptr + (jj >> 1) * 512 + q * 128 + (rr * 2 + i) * 16 + (jj & 1) * 8;
+                        uint8_t* xp = xst_ptr + (jj >> 1) * 512 + (e8 >> 1) * 128 + ((e8 & 1) * 4 + rr + i) * 16 + (jj & 1) * 8;
                         *reinterpret_cast<uint2*>(xp) = pack4(dI); *reinterpret_cast<uint2*>(xp + 2048) = pack4(dF);
                         *reinterpret_cast<uint2*>(xp + 4096) = pack4(dG); *reinterpret_cast<uint2*>(xp + 6144) = pack4(dO);
                     }
@@ -2076,7 +2080,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
                     dbacc[c][3].x += dO.x; dbacc[c][3].y += dO.y; dbacc[c][3].z += dO.z; dbacc[c][3].w += dO.w;
                 }
                 if (s + 1 < T) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                named_bar_sync(1, 128);
+                named_bar_sync(1, 256);
                 if (te == 0) REC_STAMP(8);
                 if (s + 1 < T && te < RS) {
                     // thread `te` pushes the slice of gate g = te & 3 into the operand buffer of the consumer of that gate in unit block
@@ -2089,7 +2093,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
                 }
                 if (te == 0) REC_STAMP(9);
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < NR; ++i) {
                     const int b = b0 + rl0 + i;
                     if (b >= a.B) continue;
                     if (!a.dbp) {
@@ -2109,9 +2113,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
         // gate gradients of step s; warp 0 (idle in this kernel) makes them visible device-wide and counts the CTA in
         if (a.progress && (s + 1) % a.progress_every == 0) {
             if (warp >= 4) {
-                asm volatile("bar.arrive 5, 160;" ::: "memory");
+                asm volatile("bar.arrive 5, 288;" ::: "memory");
             } else if (warp == 0) {
-                asm volatile("bar.sync 5, 160;" ::: "memory");
+                asm volatile("bar.sync 5, 288;" ::: "memory");
                 if (lane == 0) {
                     __threadfence();
                     atomicAdd(a.progress + dir * gridDim.y + sg, 1u);
@@ -2123,12 +2127,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
         // bias gradients: the four epilogue warps hold partial sums of the same 32 units over different batch rows; add them up in
         // a fixed order and store this (direction, batch slice)'s row -- the host sums the few slice rows (deterministic)
         __syncthreads();
-        float* red = part0;                   // [chain][q][rr][gate][32 units] floats (8 K floats; the partial tiles are idle now)
+        float* red = part0;                   // [chain][warp e][rr][gate][32 units] floats (8 K floats; the partial tiles are idle now)
         if (warp >= 4) {
 #pragma unroll
             for (int c = 0; c < MAX_CHAINS; ++c)
 #pragma unroll
-                for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<float4*>(red + ((((c * 4 + q) * 4 + rr) * 4 + gq) * 32) + 4 * jj) = dbacc[c][gq];
+                for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<float4*>(red + ((((c * 8 + e8) * 4 + rr) * 4 + gq) * 32) + 4 * jj) = dbacc[c][gq];
         }
         __syncthreads();
         if (warp == 4) {
@@ -2139,7 +2143,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_bwd_dsm_kernel(const Rec
                 for (int gq = 0; gq < 4; ++gq) {
                     float v = 0.f;
 #pragma unroll
-                    for (int pq = 0; pq < 16; ++pq) v += red[(((c * 16 + pq) * 4 + gq) * 32) + j];      // fixed order over (q, rr)
+                    for (int pq = 0; pq < 32; ++pq) v += red[(((c * 32 + pq) * 4 + gq) * 32) + j];      // fixed order over (warp, rr)
                     a.dbp[((long long)(dir * a.nslices + slice) * 4 + gq) * H + ub * 128 + kq * 32 + j] = v;
                 }
             }
@@ -2181,7 +2185,7 @@ static int launch_bwd_dsm(const float* dout, float* gates, void* dgates_bf16, co
     if (cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return LAS_ERR_UNSUPPORTED; }
     if (rs > 8 && cudaFuncSetAttribute(kd, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return LAS_ERR_UNSUPPORTED; }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(rs, nslices, ndir); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(rs, nslices, ndir); cfg.blockDim = dim3(NTHREADS8); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = rs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
