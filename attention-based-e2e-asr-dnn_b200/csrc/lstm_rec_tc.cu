@@ -1793,6 +1793,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHREADS, 1)
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS8, 1) lstm_rec_bwd_dsm_kernel(const RecTcBwdArgs a) {
     constexpr bool WTMEM = true;
+    constexpr int NC = 1;              // chains per CTA: this kernel is only launched with one (launch_bwd_dsm); the barrier layout keeps MAX_CHAINS slots
     extern __shared__ uint8_t smem_raw[];
     if (a.start_ctr && threadIdx.x == 0) atomicAdd(a.start_ctr, 1u);   // "this CTA is resident"
 
@@ -1833,7 +1834,7 @@ __global__ void __launch_bounds__(NTHREADS8, 1) lstm_rec_bwd_dsm_kernel(const Re
     const unsigned group = (unsigned)(4 * (H / 128));  // CTAs sharing one (direction, batch slice)
 
     if (warp == 0 && lane == 0) {
-        for (int c = 0; c < MAX_CHAINS; ++c) {
+        for (int c = 0; c < NC; ++c) {
             mbar_init(tfull_bar(c), 1);
             for (int pc = 0; pc < 4; ++pc) mbar_init(piece_bar(c, pc), 1);
         }
@@ -1890,14 +1891,14 @@ __global__ void __launch_bounds__(NTHREADS8, 1) lstm_rec_bwd_dsm_kernel(const Re
     const int u0 = ub * 128 + kq * 32 + 4 * jj;        // first of the 4 units this thread finalises
     const int rl0 = e8 * 4 + rr;                       // its batch row inside the 32-row slice
     constexpr int NR = 1;                              // rows per thread
-    float4 dcst[MAX_CHAINS][NR];
-    float4 mkr[MAX_CHAINS][NR];                        // locked-dropout mask: constant over time
-    float4 cnext[MAX_CHAINS][NR];                      // c_{t-1} loaded at this step = c_t of the next step (time runs backwards)
-    float4 dbacc[MAX_CHAINS][4];                       // bias-gradient partial sums (gate x 4 units) over this thread's rows, all steps
-    int lenr[MAX_CHAINS][NR];
+    float4 dcst[NC][NR];
+    float4 mkr[NC][NR];                        // locked-dropout mask: constant over time
+    float4 cnext[NC][NR];                      // c_{t-1} loaded at this step = c_t of the next step (time runs backwards)
+    float4 dbacc[NC][4];                       // bias-gradient partial sums (gate x 4 units) over this thread's rows, all steps
+    int lenr[NC][NR];
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c < MAX_CHAINS; ++c) {
+    for (int c = 0; c < NC; ++c) {
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) dbacc[c][gq] = z4;
 #pragma unroll
@@ -1917,7 +1918,7 @@ __global__ void __launch_bounds__(NTHREADS8, 1) lstm_rec_bwd_dsm_kernel(const Re
         const int t_prev = (dir == 0) ? (T - s) : (s - 1);
         const int fprev = (dir == 0) ? t : t + 2, fcur = t + 1;
 #pragma unroll
-        for (int c = 0; c < MAX_CHAINS; ++c) {
+        for (int c = 0; c < NC; ++c) {
             const int slice = sg + c * a.bsg;
             if (c >= a.chains || slice >= a.nslices) continue;          // uniform across the cluster (same sg, chains)
             const int b0 = slice * NB_SLICE;
@@ -2130,7 +2131,7 @@ __global__ void __launch_bounds__(NTHREADS8, 1) lstm_rec_bwd_dsm_kernel(const Re
         float* red = part0;                   // [chain][warp e][rr][gate][32 units] floats (8 K floats; the partial tiles are idle now)
         if (warp >= 4) {
 #pragma unroll
-            for (int c = 0; c < MAX_CHAINS; ++c)
+            for (int c = 0; c < NC; ++c)
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<float4*>(red + ((((c * 8 + e8) * 4 + rr) * 4 + gq) * 32) + 4 * jj) = dbacc[c][gq];
         }
