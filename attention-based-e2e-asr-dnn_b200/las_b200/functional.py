@@ -698,24 +698,29 @@ class LSTMLayerFunction(torch.autograd.Function):
             w_hh_t = torch.empty(ndir, H, G4, dtype=torch.bfloat16, device=dev)
             check(lib.las_transpose_cast_bf16(w_hh.data_ptr(), w_hh_t.data_ptr(), ndir, G4, H, stream_ptr()), 'transpose_cast')
             dGb = torch.empty(M, NG, dtype=torch.bfloat16, device=dev)
-            if tc and ctx.needs_input_grad[0] and os.environ.get('LAS_BWD_PIPELINE', '1') != '0' and T > _PIPE_TILE:
-                # the layer's dX GEMM, tile by tile beside its own BPTT kernel (row t has both directions' gate gradients once the two
-                # sweeps have crossed it: from the middle outwards), on a third stream: dX is what the layer below waits for
+            want_dx = tc and ctx.needs_input_grad[0] and os.environ.get('LAS_BWD_PIPELINE', '1') != '0' and T > _PIPE_TILE
+            # weight gradients behind the layer's OWN BPTT kernel (direction by direction, from its first steps on): for the layer that
+            # ends the backward pass nothing else could hide them; for a long layer above it this empties the next BPTT kernel's window,
+            # which the shorter kernels of round 2 no longer covered
+            wg_mode = os.environ.get('LAS_BWD_WGRAD_PIPELINE', '1')          # 0: off, 1: the layer that ends the backward pass, 2: every long layer
+            want_wg = tc and ovl is not None and wg_mode != '0' and T > 2 * _WG_TILE and hs_pad.dtype == torch.bfloat16 \
+                and (wg_mode == '2' or not ctx.needs_input_grad[0])
+            if want_dx or want_wg:
                 main = torch.cuda.current_stream(dev)
-                dx_pipe = dict(dx=torch.zeros(Bn, Tin, D, dtype=torch.float32, device=dev),
-                               counters=torch.zeros(64, dtype=torch.int32, device=dev), ev_ready=torch.cuda.Event(), main=main)
-                dx_pipe['ev_ready'].record(main)
-                lib.las_lstm_rec_bwd_arm_progress(dx_pipe['counters'].data_ptr(), _PROGRESS_EVERY)
-            elif tc and ovl is not None and not ctx.needs_input_grad[0] and os.environ.get('LAS_BWD_WGRAD_PIPELINE', '1') != '0' \
-                    and T > 2 * _WG_TILE and hs_pad.dtype == torch.bfloat16:
-                # the layer that ends the backward pass (its input needs no gradient): nothing runs after its BPTT kernel that its own
-                # weight-gradient GEMMs could hide behind, so they follow that kernel's progress, direction by direction (below)
-                main = torch.cuda.current_stream(dev)
-                wg_pipe = dict(counters=torch.zeros(64, dtype=torch.int32, device=dev), ev_ready=torch.cuda.Event(), main=main,
-                               dwcat=torch.zeros(NG, Kp, dtype=torch.float32, device=dev),
-                               dw_hh=[torch.zeros(G4, H, dtype=torch.float32, device=dev) for _ in range(ndir)])
-                wg_pipe['ev_ready'].record(main)
-                lib.las_lstm_rec_bwd_arm_progress(wg_pipe['counters'].data_ptr(), _PROGRESS_EVERY)
+                counters = torch.zeros(64, dtype=torch.int32, device=dev)        # one set of progress words serves both consumers
+                if want_dx:
+                    # the layer's dX GEMM, tile by tile beside its own BPTT kernel (row t has both directions' gate gradients once the
+                    # two sweeps have crossed it: from the middle outwards), on a third stream: dX is what the layer below waits for
+                    dx_pipe = dict(dx=torch.zeros(Bn, Tin, D, dtype=torch.float32, device=dev), counters=counters,
+                                   ev_ready=torch.cuda.Event(), main=main)
+                if want_wg:
+                    wg_pipe = dict(counters=counters, ev_ready=torch.cuda.Event(), main=main,
+                                   dwcat=torch.zeros(NG, Kp, dtype=torch.float32, device=dev),
+                                   dw_hh=[torch.zeros(G4, H, dtype=torch.float32, device=dev) for _ in range(ndir)])
+                for pipe in (dx_pipe, wg_pipe):
+                    if pipe is not None:
+                        pipe['ev_ready'].record(main)
+                lib.las_lstm_rec_bwd_arm_progress(counters.data_ptr(), _PROGRESS_EVERY)
             nsl = lib.las_lstm_rec_bwd_tc_dbias_slices(Bn, H, ndir) if os.environ.get('LAS_REC_DBIAS', '1') == '1' else 0
             if nsl > 0:
                 # bias gradients accumulated inside the BPTT kernel (per direction and batch slice); no fp32 dG write-back, no
