@@ -448,14 +448,15 @@ def test_persistent_decoder_greedy_matches_launch_per_stage_loop(monkeypatch):
     assert (ca == cb).mean() > 0.9
 
 
-@pytest.mark.parametrize('T,lx', [(72, [72, 40, 8]), (640, [640, 512, 77])])
-def test_fused_backward_step_matches_separate_launches(T, lx, monkeypatch):
+@pytest.mark.parametrize('cfgname,T,lx', [('best', 72, [72, 40, 8]), ('best', 640, [640, 512, 77]), ('tiny', 96, [96, 61, 10])])
+def test_fused_backward_step_matches_separate_launches(cfgname, T, lx, monkeypatch):
     """Backward decoder step: attention backward + dh1 = dq . Wq + LSTMCell-1 backward in ONE launch (csrc/attn_tail.h; one CTA per
     row at T_enc = 9, a CTA pair per row at T_enc = 80) against the three separate launches (LAS_BWD_FUSE_TAIL=0), same masks.  The fused
     form multiplies the fp32 dq by the bf16 weights, the separate GEMM rounds dq to bf16 first: not bit-identical, so both are also
     measured against the fp32-mode gradients of the same model and masks -- the fused step must not be further away."""
     from las_b200.models import ListenAttendSpell
-    sd = gu.make_state_dict(gu.get_config('best'), 21)
+    # 'tiny': P = 64, DH = 128, DO = 64 (one 64-column chunk, eight k groups in the fused dq . Wq) -- the small-dimension paths of both kernels
+    sd = gu.make_state_dict(gu.get_config(cfgname), 21)
     B, L = len(lx), 7
     x, lxa, y = gu.make_inputs(22, B, T, L, lx=lx)
     ly = torch.tensor([L, L - 2, 3][:B])
@@ -464,7 +465,7 @@ def test_fused_backward_step_matches_separate_launches(T, lx, monkeypatch):
         monkeypatch.setenv('LAS_BWD_FUSE_TAIL', fuse)
         monkeypatch.setenv('LAS_BWD_ATT_TC', att_tc)      # 1: fp16 K / V rows through mma.sync in the fused backward step (attn_bwd_tc_kernel)
         torch.manual_seed(5)
-        model = ListenAttendSpell(**gu.get_config('best', mid_dropout=0.3, dec_lstm_dropout=0.3)).to(DEV).train()
+        model = ListenAttendSpell(**gu.get_config(cfgname, mid_dropout=0.3, dec_lstm_dropout=0.3)).to(DEV).train()
         model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
         with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
             logits, _ = model(torch.from_numpy(x).to(DEV), torch.from_numpy(lxa), torch.from_numpy(y).to(DEV), 1.0, False)
