@@ -167,8 +167,20 @@ __host__ __device__ inline int rec_pieces(int KB) { return (KB % 2 == 0) ? 2 : 1
 
 constexpr int FWD_NACC = 4;          // independent TMEM accumulators per chain in the forward recurrence (one per k sub-step)
 
+// recurrence kernels with eight epilogue warps: warps 0..3 as before (producer / helpers, UMMA issue), warps 4..11 epilogue
+constexpr int NTHREADS8 = 384;
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 template <bool WTMEM>
-__global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW,
+__global__ void __launch_bounds__(NTHREADS8, 1) lstm_rec_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW,
                                                                      const __grid_constant__ CUtensorMap tmH, const RecTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const int H = a.H, T = a.T, KB = H / 64;
@@ -216,7 +228,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
     // 32-bit column, K ascending; TMEM lane = gate row, the layout tcgen05.mma expects for an A operand in tensor memory)
     const uint32_t tmem_w = tmem_base + MAX_CHAINS * FWD_NACC * NB_SLICE;
     if (WTMEM) {
-        if (warp >= 4) {
+        if (warp >= 4 && warp < 8) {
             const int q = warp & 3;
             const uint32_t* wrow = reinterpret_cast<const uint32_t*>(a.w_gl + ((long long)dir * 4 * H + q * H + r * UNITS + lane) * H);
             for (int cb = 0; cb < H / 64; ++cb) {
@@ -302,26 +314,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: one warp per gate =====
-        const int q = warp & 3, j = lane;          // gate q, unit r*32 + j
-        const int te = (warp - 4) * 32 + lane;     // 0..127
+        // ===== epilogue: EIGHT warps (round 2): warp e = warp - 4 reads gate q = e & 3 (TMEM lane quarter) for batch columns
+        // 16 (e >> 2) .. + 16 and updates the cells of batch rows 4e .. 4e + 3 =====
+        const int e = warp - 4, q = e & 3, hf = e >> 2, j = lane;          // gate q, unit r*32 + j
+        const int te = e * 32 + lane;              // 0..255
         const int u = r * UNITS + j;
-        float cst[MAX_CHAINS][8];
-        int lenr[MAX_CHAINS][8];      // lengths of this thread's 8 batch rows per chain (0 for rows >= B): loaded once
+        float cst[MAX_CHAINS][4];
+        int lenr[MAX_CHAINS][4];      // lengths of this thread's 4 batch rows per chain (0 for rows >= B): loaded once
 #pragma unroll
         for (int c = 0; c < MAX_CHAINS; ++c)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 cst[c][i] = 0.f;
-                const int b = (sg + c * a.bsg) * NB_SLICE + q * 8 + i;
+                const int b = (sg + c * a.bsg) * NB_SLICE + e * 4 + i;
                 lenr[c][i] = (c < a.chains && sg + c * a.bsg < a.nslices && b < a.B) ? a.lens[b] : 0;
             }
         // zero the pad frames (0 and T+1) of this CTA's (rows, units): the shifted h_{t-1} / c_{t-1} reads of backward
         for (int c = 0; c < a.chains; ++c) {
             const int slice = sg + c * a.bsg;
             if (slice >= a.nslices) continue;
-            for (int i = 0; i < 8; ++i) {
-                const int b = slice * NB_SLICE + q * 8 + i;
+            for (int i = 0; i < 4; ++i) {
+                const int b = slice * NB_SLICE + e * 4 + i;
                 if (b < a.B) {
                     const long long o0 = (long long)b * brow + dir * H + u, o1 = o0 + (long long)(T + 1) * F;
                     a.cs_pad[o0] = 0.f; a.cs_pad[o1] = 0.f;
@@ -338,11 +351,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                 if (c >= a.chains || slice >= a.nslices) continue;
                 const int b0 = slice * NB_SLICE;
                 // input projection for (gate q, unit j) of the 32 batch rows: coalesced 128 B per row, issued before the wait
-                float xg[32];
+                float xg[16];
                 float* gbase = a.gates + ((long long)t * a.ndir + dir) * 4 * H + q * H + u;
                 const long long gstride = (long long)T * a.ndir * 4 * H;
 #pragma unroll
-                for (int n = 0; n < 32; ++n) xg[n] = (b0 + n < a.B) ? gbase[(long long)(b0 + n) * gstride] : 0.f;
+                for (int n = 0; n < 16; ++n) xg[n] = (b0 + 16 * hf + n < a.B) ? gbase[(long long)(b0 + 16 * hf + n) * gstride] : 0.f;
                 if (te == 0) REC_STAMP(4);
                 if (s > 0) {
                     mbar_wait(tfull_bar(c), (uint32_t)((s - 1) & 1));
@@ -350,28 +363,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     tc_fence_after();
 #pragma unroll
                     for (int acc = 0; acc < FWD_NACC; ++acc) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c * FWD_NACC + acc) * NB_SLICE), v);
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c * FWD_NACC + acc) * NB_SLICE + 16 * hf), v);
 #pragma unroll
-                        for (int n = 0; n < 32; ++n) xg[n] += __uint_as_float(v[n]);
+                        for (int n = 0; n < 16; ++n) xg[n] += __uint_as_float(v[n]);
                     }
                     if (te == 0) REC_STAMP(6);
                 }
 #pragma unroll
-                for (int n = 0; n < 32; ++n) {
+                for (int n = 0; n < 16; ++n) {
                     const float pre = xg[n];
                     const float act = (q == 2) ? tanh_fast(pre) : sigmoid_fast(pre);
-                    ex[(q * 32 + n) * 32 + j] = act;
+                    ex[(q * 32 + 16 * hf + n) * 32 + j] = act;
                     xg[n] = act;                                   // kept for the deferred save below
                 }
                 tc_fence_before();
-                named_bar_sync(1, 128);
+                named_bar_sync(1, 256);
                 if (te == 0) REC_STAMP(7);
-                // cell update: thread (q, j) owns unit j for batch rows n = q*8 + i
-                float hh[8], cc[8];
+                // cell update: thread (e, j) owns unit j for batch rows n = 4e + i
+                float hh[4], cc[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int n = q * 8 + i, b = b0 + n;
+                for (int i = 0; i < 4; ++i) {
+                    const int n = e * 4 + i, b = b0 + n;
                     const float gi = ex[(0 * 32 + n) * 32 + j], gf = ex[(1 * 32 + n) * 32 + j];
                     const float gg = ex[(2 * 32 + n) * 32 + j], go = ex[(3 * 32 + n) * 32 + j];
                     const bool valid = t < lenr[c][i];
@@ -384,20 +397,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_fwd_tc_kernel(const __gr
                     // the only data peers wait for: h_t as bf16
                     a.hbuf[((long long)(dir * 2 + (s & 1)) * a.Bpad + b) * H + u] = __float2bfloat16(hh[i]);
                 }
-                // publish step s of this chain FIRST (the release only has the 8 bf16 stores per thread in front of it) ...
-                named_bar_sync(1, 128);
+                // publish step s of this chain FIRST (the release only has the 4 bf16 stores per thread in front of it) ...
+                named_bar_sync(1, 256);
                 if (te == 0) REC_STAMP(8);
                 if (te == 0 && s + 1 < T) red_release_gpu_add(a.ctr + dir * a.nslices + slice, 1u);
                 if (te == 0) REC_STAMP(9);
                 // ... then write what only backward / the next layer read; these stores overlap the wait for the next step
                 if (a.save) {
 #pragma unroll
-                    for (int n = 0; n < 32; ++n)
-                        if (b0 + n < a.B) gbase[(long long)(b0 + n) * gstride] = xg[n];
+                    for (int n = 0; n < 16; ++n)
+                        if (b0 + 16 * hf + n < a.B) gbase[(long long)(b0 + 16 * hf + n) * gstride] = xg[n];
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int b = b0 + q * 8 + i;
+                for (int i = 0; i < 4; ++i) {
+                    const int b = b0 + e * 4 + i;
                     if (b < a.B) {
                         const long long so = (long long)b * brow + (long long)(t + 1) * F + dir * H + u;
                         if (a.hs_pad) a.hs_pad[so] = hh[i];
@@ -471,16 +484,6 @@ __device__ __forceinline__ uint64_t make_desc_k_noswz(uint32_t saddr) {     // K
 //   * optional progress counters for consumers on other streams (las_lstm_rec_fwd_arm_progress).
 // One chain per CTA.
 // =====================================================================================================================
-constexpr int NTHREADS8 = 384;
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 __global__ void __launch_bounds__(NTHREADS8, 1) lstm_rec_fwd_dsm_kernel(const RecTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -979,7 +982,7 @@ static int rec_fwd_tc_impl(float* gates, const void* w_hh_bf16, const int* lens,
     void* kern = a.w_tmem ? (void*)lstm_rec_fwd_tc_kernel<true> : (void*)lstm_rec_fwd_tc_kernel<false>;
     LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     void* args[] = {(void*)&tmW, (void*)&tmH, (void*)&a};
-    LAS_CUDA(cudaLaunchCooperativeKernel(kern, dim3(p.rs, p.bsg, ndir), dim3(NTHREADS), args, p.smem, st));
+    LAS_CUDA(cudaLaunchCooperativeKernel(kern, dim3(p.rs, p.bsg, ndir), dim3(NTHREADS8), args, p.smem, st));
     las_count_launch(1);
     return LAS_OK;
 }
