@@ -671,6 +671,8 @@ extern "C" int las_attn_step_bwd_f32(const LasAttnStep* a, void* stream) {
     return LAS_OK;
 }
 
+namespace {
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Backward decoder step on the tensor pipe (fp16 K / V rows): one CTA of 8 warps per batch row, single head.
 //   dw_t = dctx . V_t            -> mma.sync m16n8k16: A = 16 V rows x 16 columns, B = dctx (replicated over the 8 output columns)
@@ -882,6 +884,8 @@ __global__ void __launch_bounds__(BT_NT, 1) attn_bwd_tc_kernel(LasAttnStep a, La
         tl.dc[(long long)b * DO + tid] = dctt * gf;
     }
 }
+
+}  // namespace
 
 // ---- fused backward step (attn_tail.h) ----
 static int tail_split(const LasAttnStep* a, int DO) {
