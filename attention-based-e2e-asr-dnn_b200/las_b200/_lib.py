@@ -163,6 +163,7 @@ SIGNATURES = {
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     'las_speller_graph_stats': (None, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     'las_speller_bwd_f32': (C.c_int, [C.POINTER(LasSpeller), C.POINTER(LasSpellerGrads), C.c_void_p]),
+    'las_speller_bwd_phases_f32': (C.c_int, [C.POINTER(LasSpeller), C.POINTER(LasSpellerGrads), C.c_int, C.c_void_p]),
     'las_adamw_amsgrad_fused': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_float,
                                           C.c_double, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -274,6 +274,16 @@ def _overlap_finish():
         st.keepalive = []            # main-stream work enqueued from here on is ordered behind everything the side stream read
 
 
+def _overlap_begin(ovl: _BackwardOverlap) -> None:
+    """First deferring node of a backward pass (or leftovers of an aborted one): reset the queue, register the end-of-pass join."""
+    tid = torch._C._current_graph_task_id()
+    if ovl.task_id != tid:
+        ovl.pending = []
+        ovl.keepalive = []
+        ovl.task_id = tid
+        torch.autograd.Variable._execution_engine.queue_callback(_overlap_finish)
+
+
 def _overlap_ok(wrefs) -> bool:
     # LAS_BWD_OVERLAP=0 switches the overlap off.  It stays on under Nsight Compute: a one-step launch list with the overlap on completes
     # (profiles/launches_r2_step_summary.csv) -- ncu serialises kernels, the cuStreamWaitValue32 hand-off is enqueued after the BPTT
@@ -684,12 +694,7 @@ class LSTMLayerFunction(torch.autograd.Function):
         ovl = _overlap_state(dev) if (rec_tc and _overlap_ok(ctx.wrefs)) else None
         ev = False
         if ovl is not None:
-            tid = torch._C._current_graph_task_id()
-            if ovl.task_id != tid:                 # first layer of this backward pass (or leftovers of an aborted one)
-                ovl.pending = []
-                ovl.keepalive = []
-                ovl.task_id = tid
-                torch.autograd.Variable._execution_engine.queue_callback(_overlap_finish)
+            _overlap_begin(ovl)
             if ovl.pending:
                 ev = True
                 lib.las_set_launch_start_stream(ovl.side.cuda_stream)
@@ -1065,9 +1070,10 @@ def speller_pool_bytes():
 
 class SpellerFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, K, V, enc_lens, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, init_force, *params):
+    def forward(ctx, K, V, enc_lens, dec_y, use_gold, drop0, drop1, steps, heads, sos_idx, pad_idx, training, init_force, wrefs, *params):
         _require_cuda(K, V, enc_lens, *params)
         lib = _lib.load()
+        ctx.wrefs = wrefs                # the caller's Parameter objects when it allows their gradients to be accumulated out of band
         params = tuple(_f32c(p) for p in params)
         dev = K.device
         Bn, T, P = K.shape
@@ -1170,14 +1176,51 @@ class SpellerFunction(torch.autograd.Function):
         dKb = slot.buf('dK', tuple(K.shape), torch.float32, K.device)
         dVb = slot.buf('dV', tuple(V.shape), torch.float32, K.device)
         g.dK, g.dV = dKb.data_ptr(), dVb.data_ptr()
-        check(lib.las_speller_bwd_f32(C.byref(s), C.byref(g), stream_ptr()), 'speller_bwd')
-        grads = [t_.clone() for t_ in gbufs]           # the caller (autograd) owns what it receives
+        # Parameter gradients beside the encoder's backward (the decoder's share of the "backward overlap" above): when the caller's
+        # parameters keep their gradients in the reducer's buckets, only the loop + dK / dV are enqueued here; the batched parameter
+        # gradients (a dozen split-K GEMMs, column sums and small FFMA GEMMs, ~0.5 ms at B = 96, L = 300 that nothing downstream
+        # waits for) are queued like an encoder layer's weight gradients: the top encoder layer's backward issues them on the second
+        # stream beside its BPTT kernel, they accumulate straight into p.grad and report to the reducer.  LAS_BWD_SPELLER_OVERLAP=0: off.
+        wrefs = ctx.wrefs
+        ovl = None
+        if wrefs is not None and use_tc and os.environ.get('LAS_BWD_SPELLER_OVERLAP', '1') != '0' and _overlap_ok(wrefs) \
+                and all(w.shape == p.shape for w, p in zip(wrefs, params)):
+            ovl = _overlap_state(K.device)
+        if ovl is None:
+            check(lib.las_speller_bwd_f32(C.byref(s), C.byref(g), stream_ptr()), 'speller_bwd')
+            grads = [t_.clone() for t_ in gbufs]           # the caller (autograd) owns what it receives
+            dK, dV = dKb.clone(), dVb.clone()
+            lease.release()
+            return (dK, dV, None, None, None, None, None, None, None, None, None, None, None, None, *grads)
+        _overlap_begin(ovl)
+        check(lib.las_speller_bwd_phases_f32(C.byref(s), C.byref(g), 1, stream_ptr()), 'speller_bwd (loop)')
         dK, dV = dKb.clone(), dVb.clone()
-        lease.release()
-        return (dK, dV, None, None, None, None, None, None, None, None, None, None, None, *grads)
+
+        def run(_max_ctas, s=s, g=g, keep=keep, gbufs=gbufs, wrefs=wrefs, lease=lease, held=(t, params, dl)):
+            # side stream current; ordered behind the loop by the caller (BPTT launch-start hand-off or wait_stream at the end of the pass)
+            check(lib.las_speller_bwd_phases_f32(C.byref(s), C.byref(g), 2, stream_ptr()), 'speller_bwd (parameter gradients)')
+            for w, gb in zip(wrefs, gbufs):
+                w.grad.add_(gb)
+            for w in wrefs:                                # stands in for the post-accumulate-grad hook (bucket all-reduce)
+                ready = getattr(w, '_las_grad_ready', None)
+                if ready is not None:
+                    ready(w)
+            # the slot's buffers are read on the side stream: the slot goes back to the pool now, but whoever takes it next writes on
+            # the main stream, which joins the side stream at the end of this backward pass (_overlap_finish) before anything else runs
+            _overlap_state(gbufs[0].device).keepalive.append((gbufs, held, keep))
+            lease.release()
+
+        for w in wrefs:                                    # the reducer's autograd hook must not count the None returned below
+            w._las_deferred = True
+        ovl.pending.append(run)
+        return (dK, dV, None, None, None, None, None, None, None, None, None, None, None, None, *([None] * len(gbufs)))
 
 
 def speller_loop(K, V, enc_lens, params, *, steps, heads, sos_idx, pad_idx, training, dec_y=None, use_gold=None,
-                 drop0=None, drop1=None, init_force=False):
+                 drop0=None, drop1=None, init_force=False, defer_param_grads=False):
+    """defer_param_grads: the caller guarantees that `params` are used by nothing else in the autograd graph of this step (true for the
+    LAS Speller; NOT for the Rewriter, whose char_emb also embeds the encoder's input), so their gradients may be accumulated into
+    p.grad on the second stream beside the encoder's backward instead of being returned through autograd (SpellerFunction.backward)."""
+    wrefs = tuple(params) if (defer_param_grads and training) else None
     return SpellerFunction.apply(K, V, enc_lens, dec_y, use_gold, drop0, drop1, int(steps), int(heads), int(sos_idx),
-                                 int(pad_idx), bool(training), bool(init_force), *params)
+                                 int(pad_idx), bool(training), bool(init_force), wrefs, *params)

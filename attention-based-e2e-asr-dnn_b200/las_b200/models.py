@@ -191,7 +191,7 @@ class Speller(nn.Module):
         logits, att0, chars = LF.speller_loop(K, V, lens_dev, params, steps=steps, heads=self.att_heads,
                                               sos_idx=self.CHR_SOS_IDX, pad_idx=self.CHR_PAD_IDX, training=self.training,
                                               dec_y=dec_y if self.training else None, use_gold=use_gold, drop0=drop0, drop1=drop1,
-                                              init_force=bool(init_force))
+                                              init_force=bool(init_force), defer_param_grads=True)
         self.last_chars = chars                         # (steps, B) greedy indices, device-side (extra, not in reference)
         # reference returns the attention map of sample 0 as a CPU tensor (heads, T_enc, steps+1) (:349,377,385):
         # one D2H at the end instead of one blocking copy per step

@@ -525,9 +525,13 @@ def main():
         greedy = dict(metric='las_greedy_decode_chars_per_sec', value=world * Bg * steps_g / (ms_g / 1e3), unit='chars/s',
                       ms_per_batch=ms_g, e2e_value=world * Bg * steps_g / (ms_ge / 1e3),
                       config=dict(workload=f'{args.config} base-LAS greedy decode, batch {Bg}/GPU, T={Tg}, {steps_g} steps (CHR_MAX_STEPS), eval mode'),
-                      attn_step=dict(us_per_launch=1e3 * ga['ms'] / max(ga['n'], 1), bytes_per_launch=ga['work'] / max(ga['n'], 1),
-                                     gbs=(ga['work'] / 1e9) / (ga['ms'] / 1e3) if ga['ms'] > 0 else 0.0,
-                                     method='CUDA events around every launch inside the decode loop (includes the per-launch event/launch gap)'),
+                      attn_step=(dict(us_per_launch=1e3 * ga['ms'] / ga['n'], bytes_per_launch=ga['work'] / ga['n'],
+                                      gbs=(ga['work'] / 1e9) / (ga['ms'] / 1e3) if ga['ms'] > 0 else 0.0,
+                                      method='CUDA events around every launch inside the decode loop (includes the per-launch event/launch gap)')
+                                 if ga['n'] > 0 else
+                                 dict(us_per_launch=None, launches=0,
+                                      note='no separate attention launches: the attention phase runs inside the persistent decoder kernel '
+                                           '(csrc/decoder_persist.cu); see attn_step_replay for the stand-alone kernel at this shape')),
                       attn_step_replay=ga_replay)
         model.train()
 
@@ -573,7 +577,10 @@ def main():
                          us_per_launch=attn_replay['us_fwd'], bytes_per_launch=attn_replay['bytes_per_launch'],
                          bwd=dict(achieved=at_gbs_bwd, frac=at_gbs_bwd / pk['hbm'], frac_of_8tbs=at_gbs_bwd / 8000.0, us_per_launch=attn_replay['us_bwd']),
                          method='50 launches captured in a CUDA graph, replayed, CUDA events on the replay stream; K/V (39 MB) L2-warm as in the loop',
-                         in_loop_evented_us_per_launch=1e3 * af['ms_per_step'] / max(af['launches_per_step'], 1),
+                         in_loop_evented_us_per_launch=(1e3 * af['ms_per_step'] / af['launches_per_step'] if af['launches_per_step'] > 0 else None),
+                         in_loop_note=(None if af['launches_per_step'] > 0 else 'the forward decoder loop launches no attention kernel in AMP mode: its '
+                                       'attention phase is part of dec_persist_fwd_kernel (decoder_step_us.fwd); this kernel serves the backward loop, '
+                                       'fp32 mode and the stand-alone module'),
                          note='K/V of one batch fit in the 126 MB L2, so algorithmic GB/s can exceed what DRAM alone would give')
     T_total = prof['rec_fwd']['work_per_step']
     rec = dict(fwd_us_per_timestep=1e3 * prof['rec_fwd']['ms_per_step'] / max(T_total, 1),

@@ -299,6 +299,12 @@ typedef struct {
     float* dK; float* dV;         /* (B,T,P) */
 } LasSpellerGrads;
 int las_speller_bwd_f32(const LasSpeller* s, const LasSpellerGrads* g, void* stream);
+/* The same backward in two separately enqueueable parts (autograd of src/models.py:336-385 has no such split: the reference computes
+ * every gradient on one stream).  phases bit 0: the backward time loop, the initial attention step and dK / dV -- everything the
+ * encoder's backward (src/models.py:60-66) waits for; bit 1: the batched parameter gradients (d_emb ... d_init_query), which read what
+ * bit 0 left in the workspace and feed only the optimizer, so a caller may enqueue them on a second stream once the first part has
+ * been enqueued (ordered behind it) and let them run beside the encoder's BPTT kernels.  phases = 3 is las_speller_bwd_f32. */
+int las_speller_bwd_phases_f32(const LasSpeller* s, const LasSpellerGrads* g, int phases, void* stream);
 
 /* ---- device-side collate + SpecAugment ---------------------------------------------------------------------------------
  * Replaces pad_sequence + FrequencyMasking / TimeMasking of datasetTrainDev.collate_fn (src/utils.py:95-128, maskers :82-84)

@@ -325,18 +325,41 @@ def test_backward_overlap_matches_plain_autograd():
         torch.cuda.synchronize()
         return outs
 
+    # the decoder's share of the overlap: the 13 parameters of the Speller loop (tied embedding / classifier weight, classifier bias,
+    # both cells, query_map, init_query) get their gradients from las_speller_bwd_phases_f32(phases = 2) on the second stream beside the
+    # top encoder layer's BPTT kernel, accumulated into the bucket views: same kernels on the same operands, and 0 + g == g
+    speller_loop_params = ['spell.char_emb.weight', 'spell.cls.bias', 'spell.init_query', 'spell.attention.query_map.weight',
+                           'spell.attention.query_map.bias'] + [f'spell.lstms.lstms.{i}.{w}_{k}' for i in (0, 1) for w in ('weight', 'bias')
+                                                                for k in ('ih', 'hh')]
+    names = dict(m0.named_parameters())
+    assert all(n in names for n in speller_loop_params), [n for n in speller_loop_params if n not in names]
+    from las_b200 import functional as LF
+    calls = []
+    lib = LF._lib.load()
+    orig = lib.las_speller_bwd_phases_f32
+
+    class _Spy:                                   # ctypes function pointers take no attributes: wrap the library object's entry
+        def __call__(self, s_, g_, phases, stream):
+            calls.append(int(phases))
+            return orig(s_, g_, phases, stream)
     g_plain = run(m0, False)
-    g_ovl = run(m1, True)
+    assert calls == []
+    lib.las_speller_bwd_phases_f32 = _Spy()
+    try:
+        g_ovl = run(m1, True)
+    finally:
+        lib.las_speller_bwd_phases_f32 = orig
+    assert calls == [1, 2, 1, 2], calls           # the deferred route was taken in both passes: loop first, parameter gradients later
     checked = 0
     for it in range(2):
         for n, g in g_plain[it].items():
             assert n in g_ovl[it], n
-            if n.startswith('listen.'):
+            if n.startswith('listen.') or n in speller_loop_params:
                 assert torch.equal(g, g_ovl[it][n]), (it, n, (g - g_ovl[it][n]).abs().max().item())
                 checked += 1
             else:
                 torch.testing.assert_close(g, g_ovl[it][n], rtol=1e-5, atol=1e-6)
-    assert checked >= 2 * 4 * 8
+    assert checked >= 2 * (4 * 8 + len(speller_loop_params))
 
 
 def test_tc_gemm_fp16_operands():
