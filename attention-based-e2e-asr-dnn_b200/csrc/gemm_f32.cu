@@ -8,6 +8,7 @@
 // max(lx)" rule be pure addressing instead of copies.
 #include "las_common.cuh"
 #include "las_b200.h"
+#include <stdint.h>
 
 namespace {
 
@@ -33,10 +34,12 @@ struct GemmArgs {
     long long bsA, bsB, bsC;
     float alpha, beta;
     int a_kfast, b_nfast;
+    int c_vec4;          // every C row start, the batch stride and N are multiples of 4 floats and C is 16-byte aligned: 128-bit stores
 };
 
 template <int BM, int BN, int BK, int TM, int TN>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_f32_kernel(GemmArgs g) {
+__global__ void __launch_bounds__((BM / TM) * (BN / TN), ((BM / TM) * (BN / TN) >= 256) ? 2 : ((BM / TM) * (BN / TN) == 128 ? 3 : 1)) gemm_f32_kernel(GemmArgs g) {
+    // 256-thread tiles: two CTAs per SM (128 registers) -- one CTA is 2 warps per scheduler, too few to cover the shared-memory latency
     constexpr int NT = (BM / TM) * (BN / TN);
     constexpr int PAD = 4;
     __shared__ __align__(16) float As[2][BK][BM + PAD];
@@ -140,6 +143,25 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_f32_kernel(GemmArg
         int m = m0 + ty * 4 + (i / 4) * SM_ + (i % 4);
         if (m >= g.M) continue;
         float* crow = C + g.cm(m);
+        if (g.c_vec4) {
+            // a thread's columns come in groups of four consecutive ones: one 128-bit store per group instead of four scalar stores
+            // whose lanes sit 16 bytes apart (a (28800 x 512) output with K = 30 -- the decoder's dQC -- is all epilogue)
+#pragma unroll
+            for (int jg = 0; jg < GN; ++jg) {
+                const int n = n0 + tx * 4 + jg * SN_;
+                if (n >= g.N) continue;          // N % 4 == 0: the group is entirely inside or entirely outside
+                float4 v = make_float4(g.alpha * acc[i][jg * 4 + 0], g.alpha * acc[i][jg * 4 + 1], g.alpha * acc[i][jg * 4 + 2],
+                                       g.alpha * acc[i][jg * 4 + 3]);
+                if (g.bias1) { v.x += __ldg(g.bias1 + n); v.y += __ldg(g.bias1 + n + 1); v.z += __ldg(g.bias1 + n + 2); v.w += __ldg(g.bias1 + n + 3); }
+                if (g.bias2) { v.x += __ldg(g.bias2 + n); v.y += __ldg(g.bias2 + n + 1); v.z += __ldg(g.bias2 + n + 2); v.w += __ldg(g.bias2 + n + 3); }
+                if (g.beta != 0.f) {
+                    const float4 o = *reinterpret_cast<const float4*>(crow + n);
+                    v.x += g.beta * o.x; v.y += g.beta * o.y; v.z += g.beta * o.z; v.w += g.beta * o.w;
+                }
+                *reinterpret_cast<float4*>(crow + n) = v;
+            }
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             int n = n0 + tx * 4 + (j / 4) * SN_ + (j % 4);
@@ -185,10 +207,15 @@ extern "C" int las_gemm_f32(const LasGemmF32* d, void* stream) {
     g.alpha = d->alpha; g.beta = d->beta;
     g.a_kfast = (d->a_k_si == 1) ? 1 : 0;
     g.b_nfast = (d->b_n_s == 1) ? 1 : 0;
+    g.c_vec4 = (d->N % 4 == 0 && d->c_m_si % 4 == 0 && (d->c_m_inner == 0 || d->c_m_so % 4 == 0) && d->bsC % 4 == 0 &&
+                ((uintptr_t)d->C & 15) == 0) ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     LasProfScope prof(d->prof_tag == 1 ? LAS_PROF_GEMM_GATES : LAS_PROF_GEMM_OTHER, stream,
                       2.0 * d->M * (double)d->N * d->K * d->batch);
     const LasDeviceInfo* di = las_device_info();
+    // a tall output with at most 32 columns (the tied classifier over all decoder steps: 28800 x 30, K = 512) would spend three quarters
+    // of a 128-column tile on padding
+    if (g.N <= 32 && (long long)ceil_div(g.M, 128) * d->batch >= di->num_sms) return launch<128, 32, 16, 8, 4>(g, d->batch, st);
     long long big_tiles = (long long)ceil_div(g.M, 128) * ceil_div(g.N, 128) * d->batch;
     if (big_tiles >= di->num_sms) return launch<128, 128, 8, 8, 8>(g, d->batch, st);
     long long mid_tiles = (long long)ceil_div(g.M, 64) * ceil_div(g.N, 64) * d->batch;

@@ -30,7 +30,10 @@ def _masked_ce(logits, y, ly):
 # ----------------------------------------------------------------------------------------------------------------------
 # building blocks
 # ----------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('M,N,K', [(1, 1, 1), (96, 2048, 768), (300, 30, 512), (257, 129, 65), (1000, 64, 15), (4096, 512, 300)])
+@pytest.mark.parametrize('M,N,K', [(1, 1, 1), (96, 2048, 768), (300, 30, 512), (257, 129, 65), (1000, 64, 15), (4096, 512, 300),
+                                   (28800, 30, 512),        # the tied classifier over all decoder steps: the tall 128 x 32 tile
+                                   (19001, 32, 70),         # same tile, N a multiple of 4: its 128-bit epilogue, ragged last row tile
+                                   (28800, 512, 30)])       # dQC = dlogits . emb: all epilogue (128-bit stores)
 def test_gemm_f32_vs_torch(M, N, K):
     from las_b200 import functional as LF
     g = torch.Generator(device='cpu').manual_seed(M * 7 + N)
@@ -47,6 +50,15 @@ def test_gemm_f32_vs_torch(M, N, K):
     LF.gemm_raw(D, A, C2, N, K, M, am=(0, 1, 0), ak=(0, N, 0), bk=(0, K, 0), bn=1, cm=(0, K, 0))
     ref2 = (D.double().t() @ A.double()).float()
     assert rel_err(C2.cpu().numpy(), ref2.cpu().numpy()) < 1e-5
+    # accumulate form (beta = 1, alpha = 0.5, both biases) into a padded row pitch, and into a pitch that is NOT a multiple of four
+    # floats (scalar epilogue): every epilogue branch sees the same arithmetic
+    for pitch in (N + 4 - N % 4 if N % 4 else N + 8, N + 1):
+        C3 = torch.randn(M, pitch, generator=g).to(DEV)
+        ref3 = C3.clone()
+        ref3[:, :N] = (0.5 * (A.double() @ Bm.double().t()) + C3[:, :N].double() + 2 * bias.double()).float()
+        LF.gemm_raw(A, Bm, C3, M, N, K, am=(0, K, 0), ak=(0, 1, 0), bk=(0, 1, 0), bn=K, cm=(0, pitch, 0), bias1=bias, bias2=bias,
+                    alpha=0.5, beta=1.0)
+        assert rel_err(C3.cpu().numpy(), ref3.cpu().numpy()) < 1e-5        # columns past N untouched
 
 
 def test_gemm_two_level_index_is_the_pyramid_reshape():
