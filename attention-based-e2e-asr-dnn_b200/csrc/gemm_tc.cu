@@ -66,6 +66,9 @@ struct TcArgs {
     float* Cpart;     // (splitk, R, ldp) partial sums
     long long ldp;
     uint32_t fmt_clear;   // instruction-descriptor format bits to clear: bit 7 -> A is fp16, bit 10 -> B is fp16 (set = bf16)
+    // K-major A and B only: the reduction runs over chunks of `kc_iters` K iterations whose starts lie `kc_stride` elements apart in BOTH
+    // operands (0: one contiguous K range).  This is how one direction's half of a BiLSTM output feeds the next layer's gate GEMM.
+    int kc_iters, kc_stride;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
@@ -217,15 +220,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
                     mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
                     const int kb = kit / g.kt_per_b, kk = kit - kb * g.kt_per_b;
+                    const int kcoord = g.kc_iters > 0 ? (kk / g.kc_iters) * g.kc_stride + (kk % g.kc_iters) * BK : kk * BK;
                     if (!A_MN) {
-                        tma_load_3d(sa, &tmA, full_bar(stage), kk * BK, mtile * BM, b);
+                        tma_load_3d(sa, &tmA, full_bar(stage), kcoord, mtile * BM, b);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BM / 64; ++j)
                             tma_load_3d(sa + j * 8192, &tmA, full_bar(stage), mtile * BM + j * 64, kk * BK, kb);
                     }
                     if (!B_MN) {
-                        tma_load_3d(sb, &tmB, full_bar(stage), kk * BK, ntile * BN, 0);
+                        tma_load_3d(sb, &tmB, full_bar(stage), kcoord, ntile * BN, 0);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BN / 64; ++j)
@@ -339,9 +343,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
             const bool plain = splitk > 1;                          // partials carry no bias / accumulate
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
+                const int n0 = ntile * BN + c * 32;
+                // accumulate form: C += tile as fire-and-forget 128-bit reductions at L2 (red.global.add.v4.f32; one writer per element per
+                // launch and launches of one stream are ordered, so the sum is the same single fp32 add as load + add + store, and
+                // deterministic).  Loads inside the drain loop are one dependent L2 round trip per store -- no load may move above the
+                // preceding store to the same array -- and made a K = 1024 tile's epilogue three times as long as its UMMAs (measured
+                // with the direction-half gate tiles: 37.8 -> 42.1 ms per train step); eight prefetched loads per 32-column block still
+                // left it epilogue-bound (13 us per output tile against 8 us of UMMAs).
+                const bool acc_full = !plain && g.accumulate && n0 + 32 <= g.N;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
-                const int n0 = ntile * BN + c * 32;
                 if (n0 >= g.N) continue;                            // warp-uniform
                 // stage: thread `lane` owns row r0+lane -> tileS[lane][0..31]
 #pragma unroll
@@ -363,8 +374,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
                             float4 o = *reinterpret_cast<const float4*>(tileS + rr * EPI_LD + cq);
                             o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
                             float4* dst = reinterpret_cast<float4*>(cbase + (long long)(r0 + rr) * ldo + n);
-                            if (!plain && g.accumulate) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                            *dst = o;
+                            if (acc_full)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                            else
+                                *dst = o;
                         }
                     }
                 } else {
@@ -601,11 +614,20 @@ extern "C" int las_gemm_bf16_tc(const LasGemmTc* d, void* stream) {
     if (!d->a_mn_major) {
         // A: (K contiguous, M rows [stride a_s1], a_batches [stride a_s2]); reduction is a single K range
         LAS_CHECK_ARG(d->k_batches == 1, "gemm_tc: K-major A cannot have K batches");
-        rc = make_map(&ta, d->A, d->K, d->M, d->a_batches, d->a_s1, d->a_s2, BK, BM);
+        long long kspan = d->K;         // extent of the contiguous dimension the tensor maps cover
+        if (d->k_chunk > 0) {
+            // chunked reduction: K = nchunk * k_chunk elements, chunk c starts at c * k_chunk_stride in A's and in B's K dimension
+            LAS_CHECK_ARG(!d->b_mn_major && d->k_chunk % BK == 0 && d->K % d->k_chunk == 0 && d->k_chunk_stride >= d->k_chunk &&
+                              d->k_chunk_stride % 8 == 0,
+                          "gemm_tc: chunked K needs K-major A and B, k_chunk %% %d == 0, K %% k_chunk == 0, stride >= chunk", BK);
+            g.kc_iters = d->k_chunk / BK; g.kc_stride = d->k_chunk_stride;
+            kspan = (long long)(d->K / d->k_chunk - 1) * d->k_chunk_stride + d->k_chunk;
+        }
+        rc = make_map(&ta, d->A, kspan, d->M, d->a_batches, d->a_s1, d->a_s2, BK, BM);
         if (rc) return rc;
         g.R = d->M; g.NB = d->a_batches; g.mt_per_b = ceil_div(d->M, BM); g.kt_per_b = ceil_div(d->K, BK); g.KB = 1;
         if (!d->b_mn_major) {
-            rc = make_map(&tb, d->B, d->K, d->N, 1, d->b_s1, 0, BK, BNsel);        // B: (K contiguous, N rows)
+            rc = make_map(&tb, d->B, kspan, d->N, 1, d->b_s1, 0, BK, BNsel);        // B: (K contiguous, N rows)
             if (rc) return rc;
             return narrow ? launch_tc<false, false, 64>(ta, tb, g, st) : launch_tc<false, false, 256>(ta, tb, g, st);
         }

@@ -45,6 +45,7 @@ class LasGemmTc(C.Structure):
         ('workspace', C.c_void_p),
         ('max_ctas', C.c_int),
         ('a_f16', C.c_int), ('b_f16', C.c_int),
+        ('k_chunk', C.c_int), ('k_chunk_stride', c_ll),
     ]
 
 

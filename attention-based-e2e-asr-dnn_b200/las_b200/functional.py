@@ -54,9 +54,10 @@ def gemm_raw(A, B, Cout, M, N, K, *, am=(0, 0, 0), ak=(0, 1, 0), bk=(0, 1, 0), b
 
 def gemm_tc(A, B, Cout, M, N, K, *, a_batches=1, k_batches=1, a_s1, a_s2=0, b_s1, b_s2=0, c_bs=0, ldc, a_mn=False, b_mn=False,
             bias1=None, bias2=None, accumulate=False, lens=None, a_off=0, b_off=0, c_off=0, gate=True, flops=0.0, splitk=0,
-            max_ctas=0, side=False):
+            max_ctas=0, side=False, k_chunk=0, k_chunk_stride=0):
     """las_gemm_bf16_tc wrapper; A/B are bf16 (or fp16: the format is taken from the tensor's dtype) tensors, Cout fp32; *_off are
-    element offsets."""
+    element offsets.  k_chunk > 0: the reduction runs over K / k_chunk chunks whose starts are k_chunk_stride elements apart in both
+    operands (las_b200.h)."""
     d = LasGemmTc()
     d.a_f16, d.b_f16 = int(A.dtype == torch.float16), int(B.dtype == torch.float16)
     d.A = A.data_ptr() + 2 * a_off
@@ -72,6 +73,7 @@ def gemm_tc(A, B, Cout, M, N, K, *, a_batches=1, k_batches=1, a_s1, a_s2=0, b_s1
     d.prof_tag = (2 if side else 1) if gate else 0          # side: beside a recurrence kernel, timed apart (las_b200.h)
     d.prof_flops = float(flops)
     d.max_ctas = int(max_ctas)
+    d.k_chunk, d.k_chunk_stride = int(k_chunk), int(k_chunk_stride)
     ws = None
     if a_mn and splitk == 0:
         # weight-gradient form: few output tiles, long reduction -> split K so every SM has a tile
@@ -431,7 +433,60 @@ def _time_tiles(Tn, T, fac, publishes):
     return sorted([t for t in tiles if t[0] is not None]), [t for t in tiles if t[0] is None]
 
 
-def _pipeline_issue(prep, nxt, out16, Bn, T, ev_ready, ev_rec_done):
+def _issue_direction_halves(side, prep, ncl, rs, T, fac, Hp, ev_ready, ev_rec_done, tile_gemm, half_gemm):
+    """The same tiles with the reduction split by the producing layer's DIRECTION.  Row t of the next layer's input is
+    [h_fwd | h_bwd] of frame t (frames 2t, 2t+1 under the pyramid): the forward sweep has written its half of rows < t1 after fac * t1
+    steps, the reverse sweep its half of rows >= t0 after T - fac * t0 steps -- each half of every tile becomes ready at its own time,
+    from the first steps on, instead of both sweeps having to cross the tile (the second half of the kernel only).  The half that comes
+    first writes (+ biases), the other one accumulates (fp32).  A tile neither half of which is released before the kernel ends runs
+    as one full-K GEMM.  Returns (event, halves beside the kernel, GEMMs after it)."""
+    lib = _lib.load()
+    Tn = prep['Tn']
+    nper = ncl // 2                                          # word index = direction * nper + batch-slice group (lstm_rec_tc.cu)
+    kmax = (T - 1) // _PROGRESS_EVERY
+    early, late_tiles = [], []
+    for t0 in range(0, Tn, _PIPE_TILE):
+        t1 = min(t0 + _PIPE_TILE, Tn)
+        ks = []
+        for d in (0, 1):
+            ready = min(fac * t1, T) if d == 0 else T - fac * t0
+            k = -(-ready // _PROGRESS_EVERY)
+            ks.append(k if k <= kmax else None)
+        if ks[0] is None and ks[1] is None:
+            late_tiles.append((None, t0, t1))
+            continue
+        for d in (0, 1):
+            if ks[d] is not None:
+                early.append((ks[d], d, t0, t1))
+        for d in (0, 1):
+            if ks[d] is None:
+                late_tiles.append((d, t0, t1))
+    early.sort()
+    started = set()
+    cptr = prep['counters'].data_ptr()
+    with torch.cuda.stream(side):
+        side.wait_event(ev_ready)
+        waited = [0, 0]
+        for k, d, t0, t1 in early:
+            if k > waited[d]:
+                for cix in range(d * nper, (d + 1) * nper):
+                    check(lib.las_stream_wait_value_geq(side.cuda_stream, cptr + 4 * cix, rs * k), 'stream_wait_value')
+                waited[d] = k
+            half_gemm(d, t0, t1, t0 not in started, True)
+            started.add(t0)
+        side.wait_event(ev_rec_done)
+        for d, t0, t1 in late_tiles:
+            if d is None:
+                tile_gemm(t0, t1, False)
+            else:
+                half_gemm(d, t0, t1, t0 not in started, False)
+                started.add(t0)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    return ev, len(early), len(late_tiles)
+
+
+def _pipeline_issue(prep, nxt, out16, Bn, T, ev_ready, ev_rec_done, ndir_prev=1):
     """After the recurrence launch: the tiles of the next layer's gate GEMM on the second stream, behind the progress counters."""
     lib = _lib.load()
     ncl, rs = C.c_int(0), C.c_int(0)
@@ -440,20 +495,37 @@ def _pipeline_issue(prep, nxt, out16, Bn, T, ev_ready, ev_rec_done):
     side = _overlap_state(dev).side
     fac = 2 if prep['pyr'] else 1
     Tn, NG, Kp, Dp = prep['Tn'], prep['NG'], prep['Kp'], prep['Dp']
-    early, late = _time_tiles(Tn, T, fac, publishes)
     xb = out16.view(Bn * T, -1)
     a_s1 = 2 * Dp if prep['pyr'] else Dp
+    gates, wcat, b1, b2 = prep['gates'], prep['wcat'], prep['b1'], prep['b2']
 
     def tile_gemm(t0, t1, beside):
         R = t1 - t0
-        gemm_tc(xb, prep['wcat'], prep['gates'], R, NG, Kp, a_batches=Bn, a_s1=a_s1, a_s2=T * Dp, b_s1=Kp, c_bs=Tn * NG, ldc=NG,
-                bias1=prep['b1'], bias2=prep['b2'], a_off=t0 * a_s1, c_off=t0 * NG, flops=2.0 * Bn * R * NG * Kp, side=beside)
+        gemm_tc(xb, wcat, gates, R, NG, Kp, a_batches=Bn, a_s1=a_s1, a_s2=T * Dp, b_s1=Kp, c_bs=Tn * NG, ldc=NG,
+                bias1=b1, bias2=b2, a_off=t0 * a_s1, c_off=t0 * NG, flops=2.0 * Bn * R * NG * Kp, side=beside)
 
-    ev = _issue_tiles(side, prep['counters'], ncl.value, rs.value, early, late, ev_ready, ev_rec_done, tile_gemm)
+    Hp = Dp // 2                                             # one direction's width in the producing layer's output
+    # LAS_FWD_KSPLIT=0: whole tiles behind BOTH sweeps (bit-identical to the unpipelined GEMM); default: direction halves
+    ksplit = (ndir_prev == 2 and publishes and ncl.value >= 2 and ncl.value % 2 == 0 and Dp % 2 == 0 and Hp % 64 == 0
+              and os.environ.get('LAS_FWD_KSPLIT', '1') != '0')
+    if ksplit:
+        def half_gemm(d, t0, t1, first, beside):
+            R = t1 - t0
+            gemm_tc(xb, wcat, gates, R, NG, fac * Hp, a_batches=Bn, a_s1=a_s1, a_s2=T * Dp, b_s1=Kp, c_bs=Tn * NG, ldc=NG,
+                    bias1=b1 if first else None, bias2=b2 if first else None, accumulate=not first, a_off=t0 * a_s1 + d * Hp,
+                    b_off=d * Hp, c_off=t0 * NG, flops=2.0 * Bn * R * NG * fac * Hp, side=beside,
+                    k_chunk=(Hp if fac == 2 else 0), k_chunk_stride=(Dp if fac == 2 else 0))
+
+        ev, n_early, n_late = _issue_direction_halves(side, prep, ncl.value, rs.value, T, fac, Hp, ev_ready, ev_rec_done, tile_gemm,
+                                                      half_gemm)
+    else:
+        early, late = _time_tiles(Tn, T, fac, publishes)
+        ev = _issue_tiles(side, prep['counters'], ncl.value, rs.value, early, late, ev_ready, ev_rec_done, tile_gemm)
+        n_early, n_late = len(early), len(late)
     pre = _PreGates()
     pre.gates, pre.wcat, pre.event, pre.x16 = prep['gates'], prep['wcat'], ev, out16
     pre.wkey, pre.pyramid, pre.T, pre.Kp, pre.Dp = _weights_key(nxt['weights']), prep['pyr'], Tn, Kp, Dp
-    pre.tiles_early, pre.tiles_late = len(early), len(late)
+    pre.tiles_early, pre.tiles_late = n_early, n_late
     pre.keep = (prep['counters'], prep['b1'], prep['b2'])        # see the class comment
     pre.consumed = False
     return pre
@@ -653,7 +725,7 @@ class LSTMLayerFunction(torch.autograd.Function):
             if prep is not None:
                 ev_rec_done = torch.cuda.Event()
                 ev_rec_done.record(main)
-                pre_next = _pipeline_issue(prep, nxt, out16, Bn, T, ev_ready, ev_rec_done)
+                pre_next = _pipeline_issue(prep, nxt, out16, Bn, T, ev_ready, ev_rec_done, ndir_prev=ndir)
                 last_pipeline_stats[(Bn, T, H)] = (pre_next.tiles_early, pre_next.tiles_late)
         else:
             nbytes = lib.las_lstm_rec_workspace_bytes(Bn, H, ndir)

@@ -100,6 +100,11 @@ typedef struct {
                             * recurrence kernel and should take only the SMs that kernel leaves free; 0: one CTA per SM */
     int a_f16, b_f16;      /* != 0: the operands hold IEEE fp16 instead of bf16 (bounded-range forward activations: 3 more mantissa
                             * bits); both flags must agree -- a mixed fp16 x bf16 pair is an illegal instruction on B200 */
+    int k_chunk;           /* > 0 (a_mn_major = b_mn_major = 0 only): the reduction runs over K / k_chunk chunks of k_chunk elements whose */
+    long long k_chunk_stride; /* starts lie k_chunk_stride elements apart in BOTH operands' K dimension.  One direction's half of a BiLSTM
+                            * layer's output (src/modules.py:80: [h_fwd | h_bwd] per frame, two frames per row under the pyramid concat of
+                            * :171-185) times the matching columns of the next layer's W_ih: that half of the gate projection can start as
+                            * soon as ITS sweep has passed a frame, without waiting for the other direction */
 } LasGemmTc;
 int las_gemm_bf16_tc(const LasGemmTc* desc, void* stream);
 /* dst[r][c] (bf16, row stride ld_dst) = c < cols ? srcrow(r)[c] : 0, c < cols_pad; source row r starts at

@@ -520,9 +520,13 @@ def test_forward_pipelining_is_bit_identical(monkeypatch):
     B, T, L = 4, 1280, 5
     x, lxa, y = gu.make_inputs(32, B, T, L, lx=[1280, 1100, 640, 37])
     res = {}
-    for pipe in ('1', '0'):
-        monkeypatch.setenv('LAS_FWD_PIPELINE', pipe)
-        monkeypatch.setenv('LAS_BWD_PIPELINE', pipe)          # same scheme for each layer's dX GEMM beside its BPTT kernel
+    for pipe in ('1', '0', 'halves'):
+        monkeypatch.setenv('LAS_FWD_PIPELINE', '0' if pipe == '0' else '1')
+        monkeypatch.setenv('LAS_BWD_PIPELINE', '0' if pipe == '0' else '1')          # same scheme for each layer's dX GEMM beside its BPTT kernel
+        # whole tiles behind BOTH sweeps are the same GEMM tiles as the unpipelined launch; the default (direction halves, the second one
+        # accumulating) sums the same products in another order: checked below at the accuracy of the mode, and exactly at the level
+        # of the gate pre-activations in test_direction_half_gate_tiles
+        monkeypatch.setenv('LAS_FWD_KSPLIT', '1' if pipe == 'halves' else '0')
         LF.last_pipeline_stats.clear()
         torch.manual_seed(6)
         model = ListenAttendSpell(**gu.get_config('best', init_dropout=0.3, mid_dropout=0.3, final_dropout=0.35)).to(DEV).train()
@@ -541,6 +545,82 @@ def test_forward_pipelining_is_bit_identical(monkeypatch):
     assert np.array_equal(res['1'][0], res['0'][0])
     for k in res['0'][1]:
         assert np.array_equal(res['1'][1][k], res['0'][1][k]), k
+    # direction halves: more of them run beside the recurrences than whole tiles did; results agree at the accuracy of bf16 mode (a
+    # different fp32 summation order flips a bf16 rounding of h here and there)
+    hstats = res['halves'][2]
+    print('direction halves (beside, after) per layer:', hstats)
+    assert sum(e for k, (e, _) in hstats.items() if k[0] != 'bwd') > sum(e for k, (e, _) in stats.items() if k[0] != 'bwd'), (hstats, stats)
+    dl = float(np.abs(res['halves'][0] - res['0'][0]).max())
+    print('direction halves vs unpipelined: max abs logit difference', dl)
+    assert dl < 2e-3, dl
+    gmax = max(float(np.abs(v).max()) for v in res['0'][1].values())
+    for k in res['0'][1]:
+        ref = res['0'][1][k]
+        # floor: key_map.bias has a mathematically zero gradient (a constant added to every energy), pure round-off on both sides
+        assert np.abs(res['halves'][1][k] - ref).max() <= 5e-2 * np.abs(ref).max() + 1e-4 * gmax, k
+
+
+def test_tc_gemm_chunked_reduction():
+    """las_gemm_bf16_tc with k_chunk / k_chunk_stride: the reduction covers chunk c at column c * stride of BOTH operands -- one
+    direction's half of a pyramid row [f(2t) b(2t) f(2t+1) b(2t+1)] against the matching columns of W_ih -- plain and accumulating."""
+    from las_b200 import functional as LF
+    g = torch.Generator(device='cpu').manual_seed(5)
+    B, T, H, N = 3, 150, 128, 320                    # frames (B, 2T, 2H); rows = frame pairs, K = 4H
+    x = torch.randn(B, 2 * T, 2 * H, generator=g).to(torch.bfloat16).to(DEV)
+    W = torch.randn(N, 4 * H, generator=g).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    rows = x.double().reshape(B, T, 4 * H)
+    out = torch.empty(B, T, N, device=DEV)
+    full = None
+    for d in (1, 0):                                  # reverse half first (writes, + bias), forward half accumulates
+        cols = torch.cat([torch.arange(d * H, (d + 1) * H), torch.arange(2 * H + d * H, 2 * H + (d + 1) * H)]).to(DEV)
+        part = rows[:, :, cols] @ W.double()[:, cols].t()
+        full = part + bias.double() if full is None else full + part
+        LF.gemm_tc(x.view(B * 2 * T, 2 * H), W, out, T, N, 2 * H, a_batches=B, a_s1=4 * H, a_s2=2 * T * 2 * H, b_s1=4 * H, c_bs=T * N, ldc=N,
+                   bias1=bias if d == 1 else None, accumulate=(d == 0), a_off=d * H, b_off=d * H, k_chunk=H, k_chunk_stride=2 * H)
+        assert rel_err(out.cpu().numpy(), full.float().cpu().numpy()) < 1e-5
+    ref = (rows @ W.double().t() + bias.double()).float()
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+def test_direction_half_gate_tiles(monkeypatch):
+    """Gate pre-activations of the NEXT layer projected beside a BiLSTM layer's recurrence as direction halves
+    (functional._issue_direction_halves) against whole tiles (LAS_FWD_KSPLIT=0) and against fp64 arithmetic on the layer's own bf16
+    output: every (row, gate) exact up to the fp32 summation order; the layer output itself is bit-identical."""
+    from las_b200 import functional as LF
+    H, D, B, T = 128, 64, 40, 1100
+    rng = np.random.default_rng(3)
+    lens = [T, T - 1] + sorted([int(v) for v in rng.integers(5, T + 1, size=B - 2)], reverse=True)
+    x = torch.from_numpy(rng.standard_normal((B, T, D)).astype(np.float32)).to(DEV)
+    k = 1 / np.sqrt(H)
+    shapes = [(4 * H, D), (4 * H, H), (4 * H,), (4 * H,)]
+    ws = [torch.from_numpy(rng.uniform(-k, k, size=s_).astype(np.float32)).to(DEV) for _ in range(2) for s_ in shapes]
+    shapes_n = [(4 * H, 4 * H), (4 * H, H), (4 * H,), (4 * H,)]              # the pyramid layer above: input = two frames x two directions
+    wn = [torch.from_numpy(rng.uniform(-k, k, size=s_).astype(np.float32)).to(DEV) for _ in range(2) for s_ in shapes_n]
+    lens_dev = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    Tn = T // 2
+    got = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('LAS_FWD_KSPLIT', mode)
+        LF.last_pipeline_stats.clear()
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            y = LF.lstm_layer(x, lens_dev, T, False, None, ws, next_layer=dict(weights=wn, pyramid=True, T=Tn))
+        pre = getattr(y, '_las_pregates', None)
+        assert pre is not None, 'the next layer\'s gates were not projected beside the recurrence'
+        pre.event.synchronize()
+        torch.cuda.synchronize()
+        got[mode] = (y.detach().clone(), pre.gates.detach().clone(), y._las_bf16[0].detach().clone(), dict(LF.last_pipeline_stats))
+    print('direction halves (beside, after):', got['1'][3], ' whole tiles:', got['0'][3])
+    assert sum(e for e, _ in got['1'][3].values()) > sum(e for e, _ in got['0'][3].values())
+    assert torch.equal(got['1'][0], got['0'][0])
+    y16 = got['1'][2].double().reshape(B, T, 2 * H)[:, :2 * Tn].reshape(B, Tn, 4 * H)
+    wcat = torch.cat([wn[0], wn[4]]).to(torch.bfloat16).double()
+    bsum = torch.cat([wn[2] + wn[3], wn[6] + wn[7]]).double()
+    ref = (y16 @ wcat.t() + bsum).float().reshape(B, Tn, 2, 4 * H)
+    scale = float(ref.abs().max())
+    for mode in ('1', '0'):
+        err = float((got[mode][1] - ref).abs().max())
+        assert err <= 2e-5 * scale, (mode, err, scale)
 
 
 def test_base_layer_weight_gradients_behind_their_own_bptt_kernel(monkeypatch):
