@@ -36,7 +36,8 @@ constexpr int BM = 128, BK = 64;
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KB
 constexpr int EPI_LD = 36;                          // floats per staged row (144 B: 16-byte aligned, conflict-free STS.128/LDS.128)
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;      // one 32x32 fp32 transpose tile per epilogue warp
+constexpr int EPI_BIAS = 256;                        // per epilogue warp: bias1 + bias2 of the tile's (at most 256) columns
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4 + 4 * EPI_BIAS * 4;      // one 32x32 fp32 transpose tile per epilogue warp + its bias sums
 constexpr int NTHREADS = 256;
 template <int BN> struct Cfg {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
@@ -125,6 +126,20 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+// the load without its wait: the caller overlaps it with other work and calls tmem_ld_wait() before it touches r[]
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -279,6 +294,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
         // ===== epilogue: TMEM -> registers -> smem transpose -> (+bias, +C) -> 128-byte coalesced global stores =====
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         float* tileS = epi_sm + q * 32 * EPI_LD;
+        float* biasS = epi_sm + 4 * 32 * EPI_LD + q * EPI_BIAS;
         int acc = 0; uint32_t accphase = 0;
         for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += gridDim.x) {
             const int split = tile0 % splitk, tile = tile0 / splitk;
@@ -341,9 +357,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
             if (splitk > 1) { cbase = g.Cpart + (long long)split * g.R * g.ldp; ldo = g.ldp; }
             else { cbase = g.C + (long long)b * g.c_bs; ldo = g.ldc; }
             const bool plain = splitk > 1;                          // partials carry no bias / accumulate
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            const bool has_bias = !plain && (g.bias1 || g.bias2);
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            uint32_t va[32], vb[32];
+            tmem_ld32_issue(tbase, va);                             // chunk 0 is on its way while the bias sums are fetched
+            if (has_bias) {
+                // bias1 + bias2 of the tile's columns, once per tile (they used to be two dependent global loads per 32-column chunk in
+                // front of every drain: 8 % of all warp-stall samples of the K = 64 base-layer projection, which is all epilogue)
+                for (int j = lane; j < BN; j += 32) {
+                    const int n = ntile * BN + j;
+                    float v = 0.f;
+                    if (n < g.N) { if (g.bias1) v += g.bias1[n]; if (g.bias2) v += g.bias2[n]; }
+                    biasS[j] = v;
+                }
+                __syncwarp();
+            }
+            // one 32-column chunk: stage thread `lane`'s row (tileS[lane][0..31]), then drain 4 rows x 128 contiguous bytes per instruction
+            auto chunk = [&](const uint32_t (&v)[32], int c) {
                 const int n0 = ntile * BN + c * 32;
+                if (n0 >= g.N) return;                              // warp-uniform
                 // accumulate form: C += tile as fire-and-forget 128-bit reductions at L2 (red.global.add.v4.f32; one writer per element per
                 // launch and launches of one stream are ordered, so the sum is the same single fp32 add as load + add + store, and
                 // deterministic).  Loads inside the drain loop are one dependent L2 round trip per store -- no load may move above the
@@ -351,33 +383,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
                 // with the direction-half gate tiles: 37.8 -> 42.1 ms per train step); eight prefetched loads per 32-column block still
                 // left it epilogue-bound (13 us per output tile against 8 us of UMMAs).
                 const bool acc_full = !plain && g.accumulate && n0 + 32 <= g.N;
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
-                if (n0 >= g.N) continue;                            // warp-uniform
-                // stage: thread `lane` owns row r0+lane -> tileS[lane][0..31]
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(tileS + lane * EPI_LD + j) =
                         make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                 __syncwarp();
-                // drain: each instruction writes 4 rows x 128 contiguous bytes
                 const int cq = (lane & 7) * 4, rsub = lane >> 3;
                 const int n = n0 + cq;
                 if (n0 + 32 <= g.N) {
                     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (!plain && g.bias1) { const float4 t = *reinterpret_cast<const float4*>(g.bias1 + n); bb.x += t.x; bb.y += t.y; bb.z += t.z; bb.w += t.w; }
-                    if (!plain && g.bias2) { const float4 t = *reinterpret_cast<const float4*>(g.bias2 + n); bb.x += t.x; bb.y += t.y; bb.z += t.z; bb.w += t.w; }
+                    if (has_bias) bb = *reinterpret_cast<const float4*>(biasS + c * 32 + cq);
+                    float4 o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = *reinterpret_cast<const float4*>(tileS + (i * 4 + rsub) * EPI_LD + cq);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int rr = i * 4 + rsub;
                         if (r0 + rr < g.R) {
-                            float4 o = *reinterpret_cast<const float4*>(tileS + rr * EPI_LD + cq);
-                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                            o[i].x += bb.x; o[i].y += bb.y; o[i].z += bb.z; o[i].w += bb.w;
                             float4* dst = reinterpret_cast<float4*>(cbase + (long long)(r0 + rr) * ldo + n);
                             if (acc_full)
-                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o[i].x), "f"(o[i].y), "f"(o[i].z), "f"(o[i].w) : "memory");
                             else
-                                *dst = o;
+                                *dst = o[i];
                         }
                     }
                 } else {
@@ -386,8 +414,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
                         if (r0 + rr >= g.R) continue;
                         for (int e = 0; e < 4 && n + e < g.N; ++e) {
                             float o = tileS[rr * EPI_LD + cq + e];
-                            if (!plain && g.bias1) o += g.bias1[n + e];
-                            if (!plain && g.bias2) o += g.bias2[n + e];
+                            if (has_bias) o += biasS[c * 32 + cq + e];
                             float* dst = cbase + (long long)(r0 + rr) * ldo + n + e;
                             if (!plain && g.accumulate) o += *dst;
                             *dst = o;
@@ -395,6 +422,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
                     }
                 }
                 __syncwarp();
+            };
+            // the accumulator read of chunk c + 1 is in flight while chunk c is staged and drained
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c += 2) {
+                tmem_ld_wait();
+                tmem_ld32_issue(tbase + (c + 1) * 32, vb);          // BN / 32 is even (2 or 8)
+                chunk(va, c);
+                tmem_ld_wait();
+                if (c + 2 < BN / 32) tmem_ld32_issue(tbase + (c + 2) * 32, va);
+                chunk(vb, c + 1);
             }
             tc_fence_before();
             __syncwarp();
