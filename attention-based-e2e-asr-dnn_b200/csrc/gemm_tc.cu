@@ -364,11 +364,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16_tc_kernel(const __grid_
             if (has_bias) {
                 // bias1 + bias2 of the tile's columns, once per tile (they used to be two dependent global loads per 32-column chunk in
                 // front of every drain: 8 % of all warp-stall samples of the K = 64 base-layer projection, which is all epilogue)
-                for (int j = lane; j < BN; j += 32) {
-                    const int n = ntile * BN + j;
-                    float v = 0.f;
-                    if (n < g.N) { if (g.bias1) v += g.bias1[n]; if (g.bias2) v += g.bias2[n]; }
-                    biasS[j] = v;
+                // (every load of a lane is issued before the first add: one round trip per tile -- a scalar loop here was still 11 % of the samples)
+                constexpr int NV = BN / 128;                         // 128-bit pieces per lane: 2 (BN = 256) or 0 (BN = 64: scalar below)
+                float4 t1[NV > 0 ? NV : 1], t2[NV > 0 ? NV : 1];
+                const bool vec = (g.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.bias1) | reinterpret_cast<uintptr_t>(g.bias2)) & 15) == 0;
+                if (NV > 0 && vec) {
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        const int n = ntile * BN + (i * 32 + lane) * 4;
+                        const bool in = n < g.N;
+                        t1[i] = (in && g.bias1) ? *reinterpret_cast<const float4*>(g.bias1 + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        t2[i] = (in && g.bias2) ? *reinterpret_cast<const float4*>(g.bias2 + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NV; ++i)
+                        *reinterpret_cast<float4*>(biasS + (i * 32 + lane) * 4) =
+                            make_float4(t1[i].x + t2[i].x, t1[i].y + t2[i].y, t1[i].z + t2[i].z, t1[i].w + t2[i].w);
+                } else {
+                    for (int j = lane; j < BN; j += 32) {
+                        const int n = ntile * BN + j;
+                        float v = 0.f;
+                        if (n < g.N) { if (g.bias1) v += g.bias1[n]; if (g.bias2) v += g.bias2[n]; }
+                        biasS[j] = v;
+                    }
                 }
                 __syncwarp();
             }
