@@ -634,6 +634,9 @@ class LSTMLayerFunction(torch.autograd.Function):
         T = max of those lengths; weights = (w_ih, w_hh, b_ih, b_hh) per direction."""
         _require_cuda(x, lens_dev, *weights)
         lib = _lib.load()
+        # the bf16 copy of the output (second return value) feeds only GEMMs outside autograd: without this, backward is handed a
+        # zero-filled (B, T, 2H) bf16 "gradient" for it on every layer (0.15 ms of fills per train step in front of the BPTT kernels)
+        ctx.set_materialize_grads(False)
         ndir = len(weights) // 4
         assert ndir in (1, 2) and len(weights) == 4 * ndir
         if x.dtype != torch.float32:
@@ -754,6 +757,8 @@ class LSTMLayerFunction(torch.autograd.Function):
         F_, G4 = ndir * H, 4 * H
         NG = ndir * G4
         dev = x.device
+        if dy is None:                     # the layer's output was not used (gradients are not materialised, see forward)
+            dy = torch.zeros(Bn, T, ndir * H, dtype=torch.float32, device=dev)
         dy = _f32c(dy)
         rec_tc = tc and os.environ.get('LAS_REC_TC', '1') == '1' and bool(lib.las_lstm_rec_tc_supported(Bn, H, ndir))
         nbytes = lib.las_lstm_rec_tc_workspace_bytes(Bn, H, ndir) if rec_tc else lib.las_lstm_rec_workspace_bytes(Bn, H, ndir)
@@ -788,8 +793,14 @@ class LSTMLayerFunction(torch.autograd.Function):
                 if want_dx:
                     # the layer's dX GEMM, tile by tile beside its own BPTT kernel (row t has both directions' gate gradients once the
                     # two sweeps have crossed it: from the middle outwards), on a third stream: dX is what the layer below waits for
-                    dx_pipe = dict(dx=torch.zeros(Bn, Tin, D, dtype=torch.float32, device=dev), counters=counters,
-                                   ev_ready=torch.cuda.Event(), main=main)
+                    # the tiles cover every row t < T of every utterance (no length skipping on this route): only the frames the layer
+                    # never read (the odd frame the pyramid drops, src/modules.py:171-175) need zeros -- not a fill of the whole
+                    # (B, Tin, D) gradient in front of the BPTT kernel (0.15 ms per train step)
+                    dx_new = torch.empty(Bn, Tin, D, dtype=torch.float32, device=dev)
+                    used = (T * Din) // D
+                    if used < Tin:
+                        dx_new[:, used:].zero_()
+                    dx_pipe = dict(dx=dx_new, counters=counters, ev_ready=torch.cuda.Event(), main=main)
                 if want_wg:
                     wg_pipe = dict(counters=counters, ev_ready=torch.cuda.Event(), main=main,
                                    dwcat=torch.zeros(NG, Kp, dtype=torch.float32, device=dev),
