@@ -433,6 +433,35 @@ def _time_tiles(Tn, T, fac, publishes):
     return sorted([t for t in tiles if t[0] is not None]), [t for t in tiles if t[0] is None]
 
 
+def direction_half_schedule(Tn: int, T: int, fac: int, every: int = _PROGRESS_EVERY, tile: int = _PIPE_TILE):
+    """Pure host logic of the direction-half pipelining (tests/test_cpu_schedule.py checks it against a step-by-step simulation of the
+    two sweeps).  Rows [t0, t1) of the consuming layer read frames [fac*t0, fac*t1) of a T-step BiLSTM layer.  Direction 0 (forward
+    sweep, frame s at step s) has written them after min(fac*t1, T) steps, direction 1 (reverse sweep, frame T-1-s at step s) after
+    T - fac*t0 steps.  The kernel publishes "steps < every*k are complete" for k = 1 .. (T-1)//every, nothing later.
+    Returns (early, late): early = [(k, d, t0, t1)] sorted by k -- half d of the tile may run once direction d's progress count is k;
+    late = [(d or None, t0, t1)] -- halves only the end of the kernel releases; d = None: neither half was early, one full-K GEMM."""
+    kmax = (T - 1) // every
+    early, late = [], []
+    for t0 in range(0, Tn, tile):
+        t1 = min(t0 + tile, Tn)
+        ks = []
+        for d in (0, 1):
+            ready = min(fac * t1, T) if d == 0 else T - fac * t0
+            k = -(-ready // every)
+            ks.append(k if k <= kmax else None)
+        if ks[0] is None and ks[1] is None:
+            late.append((None, t0, t1))
+            continue
+        for d in (0, 1):
+            if ks[d] is not None:
+                early.append((ks[d], d, t0, t1))
+        for d in (0, 1):
+            if ks[d] is None:
+                late.append((d, t0, t1))
+    early.sort()
+    return early, late
+
+
 def _issue_direction_halves(side, prep, ncl, rs, T, fac, Hp, ev_ready, ev_rec_done, tile_gemm, half_gemm):
     """The same tiles with the reduction split by the producing layer's DIRECTION.  Row t of the next layer's input is
     [h_fwd | h_bwd] of frame t (frames 2t, 2t+1 under the pyramid): the forward sweep has written its half of rows < t1 after fac * t1
@@ -441,27 +470,8 @@ def _issue_direction_halves(side, prep, ncl, rs, T, fac, Hp, ev_ready, ev_rec_do
     first writes (+ biases), the other one accumulates (fp32).  A tile neither half of which is released before the kernel ends runs
     as one full-K GEMM.  Returns (event, halves beside the kernel, GEMMs after it)."""
     lib = _lib.load()
-    Tn = prep['Tn']
     nper = ncl // 2                                          # word index = direction * nper + batch-slice group (lstm_rec_tc.cu)
-    kmax = (T - 1) // _PROGRESS_EVERY
-    early, late_tiles = [], []
-    for t0 in range(0, Tn, _PIPE_TILE):
-        t1 = min(t0 + _PIPE_TILE, Tn)
-        ks = []
-        for d in (0, 1):
-            ready = min(fac * t1, T) if d == 0 else T - fac * t0
-            k = -(-ready // _PROGRESS_EVERY)
-            ks.append(k if k <= kmax else None)
-        if ks[0] is None and ks[1] is None:
-            late_tiles.append((None, t0, t1))
-            continue
-        for d in (0, 1):
-            if ks[d] is not None:
-                early.append((ks[d], d, t0, t1))
-        for d in (0, 1):
-            if ks[d] is None:
-                late_tiles.append((d, t0, t1))
-    early.sort()
+    early, late_tiles = direction_half_schedule(prep['Tn'], T, fac)
     started = set()
     cptr = prep['counters'].data_ptr()
     with torch.cuda.stream(side):
