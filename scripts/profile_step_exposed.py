@@ -36,7 +36,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
-LOOP = ('lstm_rec_', 'dec_persist', 'attn_bwd_tc_kernel', 'cell_bwd_kernel', 'gemm_bf16_tc_kernel<0, 1, 64', 'attn_step_split_kernel')
+LOOP = ('lstm_rec_', 'dec_persist', 'attn_bwd_tc_kernel', 'cell_bwd_kernel', 'gemm_bf16_tc_kernel<0, 1, 64', 'gemm_bf16_tc_kernel<false, true, 64', 'attn_step_split_kernel')
 def is_loop(n): return any(k in n for k in LOOP)
 t0, t1 = evs[0].time_range.start, max(e.time_range.end for e in evs)
 # sweep: boundaries of all events
