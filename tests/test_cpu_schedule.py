@@ -70,3 +70,24 @@ def test_direction_halves_release_work_from_the_start():
     assert len(early_h) >= 2 * len(early_w)
     ks = sorted(k for k, *_ in early_h)
     assert max(b - a for a, b in zip(ks, ks[1:])) * EVERY <= 256 + EVERY          # no gap longer than one tile's frames
+
+
+@pytest.mark.parametrize('T,fac', [(1600, 2), (800, 2), (401, 2), (200, 2), (1600, 1), (800, 1), (130, 1), (64, 1)])
+def test_whole_tile_schedule_matches_sweep_simulation(T, fac):
+    """functional._time_tiles: whole 128-row tiles behind BOTH sweeps (LAS_FWD_KSPLIT=0, and every layer's dX GEMM behind its BPTT
+    kernel, whose two sweeps run the other way round -- the condition is symmetric in the directions)."""
+    from las_b200.functional import _time_tiles, _PROGRESS_EVERY as EVERY, _PIPE_TILE as TILE
+    Tn = T // fac
+    early, late = _time_tiles(Tn, T, fac, True)
+    kmax = (T - 1) // EVERY
+    tiles = [(t0, min(t0 + TILE, Tn)) for t0 in range(0, Tn, TILE)]
+    assert sorted((t0, t1) for _, t0, t1 in early + late) == tiles
+    assert early == sorted(early)
+    for k, t0, t1 in early:
+        need = max(_simulate_ready(T, fac, t0, t1, 0), _simulate_ready(T, fac, t0, t1, 1))
+        assert 1 <= k <= kmax and EVERY * k >= need and EVERY * (k - 1) < need, (k, t0, t1, need)
+    for _, t0, t1 in late:
+        assert max(_simulate_ready(T, fac, t0, t1, 0), _simulate_ready(T, fac, t0, t1, 1)) > EVERY * kmax
+    # a kernel that publishes nothing releases nothing early
+    e0, l0 = _time_tiles(Tn, T, fac, False)
+    assert e0 == [] and sorted((t0, t1) for _, t0, t1 in l0) == tiles
