@@ -220,3 +220,72 @@ def test_gradient_accumulation_with_no_sync_matches_single_process():
 
 def test_second_backward_without_no_sync_raises():
     assert _run2(_worker_accumulate) == (True, True)
+
+
+class ToyMixedSpell(Toy):
+    """The Speller's case (las_b200.functional.SpellerFunction.backward, deferred route): ONE bucket ('spell') holds parameters whose
+    gradients arrive through autograd (key_map / value_map: ordinary Linear layers) and parameters whose gradients are accumulated later
+    on the second stream and reported through p._las_grad_ready (the 13 parameters of the decoder loop; here: spell.cls)."""
+
+    def __init__(self):
+        super().__init__()
+        self.spell.attention.key_map = torch.nn.Linear(6, 6)
+
+    def forward(self, x):
+        x = torch.tanh(self.listen.base(x))
+        for l in self.listen.pyramid.plstms:
+            x = torch.tanh(l(x))
+        x = torch.tanh(self.spell.attention.key_map(x))
+        c = self.spell.cls
+        return _ManualGradLinear.apply(x, c.weight, c.bias, (c.weight, c.bias))
+
+
+class ToyMixedRef(Toy):
+    def __init__(self):
+        super().__init__()
+        self.spell.attention.key_map = torch.nn.Linear(6, 6)
+
+    def forward(self, x):
+        x = torch.tanh(self.listen.base(x))
+        for l in self.listen.pyramid.plstms:
+            x = torch.tanh(l(x))
+        x = torch.tanh(self.spell.attention.key_map(x))
+        return self.spell.cls(x)
+
+
+def _worker_mixed_bucket(rank, world, port, q):
+    from las_b200.ddp import BucketedGradReducer
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = ToyMixedSpell()
+    red = BucketedGradReducer(list(model.named_parameters()), world_size=world)
+    bi = red.bucket_names.index('spell')
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(8, 5, generator=g)
+    Y = torch.randn(8, 3, generator=g)
+    xs, ys = X[rank * 4:(rank + 1) * 4], Y[rank * 4:(rank + 1) * 4]
+    ok = True
+    for it in range(2):
+        red.zero_grad()
+        ((model(xs) - ys) ** 2).sum().backward()
+        # key_map's gradients have arrived through autograd, the deferred ones have not: the bucket must NOT have been reduced yet
+        # (every other bucket is complete and already in flight)
+        ok = ok and red._handles[bi] is None and red._pending[bi] == 2
+        ok = ok and all(red._handles[i] is not None for i in range(len(red.buckets)) if i != bi)
+        _flush_deferred()
+        ok = ok and red._handles[bi] is not None
+        red.finish()
+    grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    if rank == 0:
+        ref = ToyMixedRef()
+        ref.load_state_dict(model.state_dict())
+        ((ref(X) - Y) ** 2).sum().backward()
+        same = all(torch.allclose(grads[k], p.grad, atol=1e-5) for k, p in ref.named_parameters() if p.grad is not None)
+        q.put((bool(ok), bool(same)))
+    dist.destroy_process_group()
+
+
+def test_bucket_with_deferred_and_autograd_parameters():
+    """The 'spell' bucket is reduced once, after BOTH its autograd-delivered gradients and the ones accumulated out of band exist."""
+    assert _run2(_worker_mixed_bucket) == (True, True)
